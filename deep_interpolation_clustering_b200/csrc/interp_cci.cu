@@ -1,0 +1,315 @@
+// CrossChannelInterp forward / backward for sm_100a.
+//
+// Reference: interpolation_layer.py:99-127; closed-form backward in SURVEY.md Appendix A.2.
+// Per encounter (planar rows y, w, y' of length R for each of C vitals):
+//     what[c,r] = softmax over c of w[.,r]
+//     ybar[c]   = mean over r of y[c,.]
+//     z[c',r]   = sum_c what[c,r] (y[c,r] - ybar[c]) K[c,c'] + ybar[c']
+//     out       = [ z | exp(w) | y' - z ]
+// HBM-bound (reads and writes 12 C R bytes per encounter): one CTA per encounter, one
+// thread per reference point, the C values of a point live in registers, every global
+// access is coalesced along r, the only cross-thread step is the mean over r.
+#include "common.cuh"
+
+namespace dic {
+namespace {
+
+constexpr int kCciThreads = 128;
+
+// Block-wide sums of MAXC per-thread values; result broadcast to all threads via smem.
+template <int MAXC>
+__device__ __forceinline__ void block_sum_vec(float (&v)[MAXC], int C, float* red /*[warps][MAXC]*/,
+                                              float* bcast /*[MAXC]*/) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) {
+    if (c < C) {
+      const float s = warp_sum(v[c]);
+      if (lane == 0) red[warp * MAXC + c] = s;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < C) {
+    float s = 0.f;
+    for (int w = 0; w < nwarps; ++w) s += red[w * MAXC + threadIdx.x];
+    bcast[threadIdx.x] = s;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c)
+    if (c < C) v[c] = bcast[c];
+  __syncthreads();
+}
+
+template <int MAXC>
+__global__ void __launch_bounds__(kCciThreads)
+cci_fwd_kernel(const float* __restrict__ u, const float* __restrict__ kernel, float* __restrict__ out,
+               int C, int R) {
+  __shared__ float sK[MAXC * MAXC];
+  __shared__ float red[(kCciThreads / 32) * MAXC];
+  __shared__ float bcast[MAXC];
+  const int64_t b = blockIdx.x;
+  const float* ub = u + b * (int64_t)(3 * C) * R;
+  float* ob = out + b * (int64_t)(3 * C) * R;
+  for (int i = threadIdx.x; i < C * C; i += blockDim.x) sK[i] = __ldg(kernel + i);
+
+  // pass 1: ybar[c] = mean_r y[c, r]
+  float ybar[MAXC];
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) ybar[c] = 0.f;
+  for (int r = threadIdx.x; r < R; r += blockDim.x) {
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c)
+      if (c < C) ybar[c] += ub[c * R + r];
+  }
+  block_sum_vec<MAXC>(ybar, C, red, bcast);
+  const float invR = 1.0f / (float)R;
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) ybar[c] *= invR;
+
+  // pass 2 (rows are L1/L2 hot)
+  for (int r = threadIdx.x; r < R; r += blockDim.x) {
+    float a[MAXC], w[MAXC];
+    float wmax = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+      if (c < C) {
+        w[c] = ub[(C + c) * R + r];
+        wmax = fmaxf(wmax, w[c]);
+      }
+    }
+    const float shift = (wmax == -INFINITY) ? 0.f : wmax;   // torch.logsumexp guards an all -inf row
+    float den = 0.f;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+      if (c < C) {
+        a[c] = expf(w[c] - shift);
+        den += a[c];
+      }
+    }
+    const float inv_den = 1.0f / den;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+      if (c < C) {
+        a[c] = a[c] * inv_den * (ub[c * R + r] - ybar[c]);
+        ob[(C + c) * R + r] = expf(w[c]);                    // intensity, :104
+      }
+    }
+#pragma unroll
+    for (int cp = 0; cp < MAXC; ++cp) {
+      if (cp < C) {
+        float z = 0.f;
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c)
+          if (c < C) z = fmaf(a[c], sK[c * C + cp], z);
+        z += ybar[cp];
+        ob[cp * R + r] = z;
+        ob[(2 * C + cp) * R + r] = ub[(2 * C + cp) * R + r] - z;   // transient minus smooth, :122-123
+      }
+    }
+  }
+}
+
+// Backward (Appendix A.2).  Per encounter:
+//   gzt = gz - gT;  uu[c,r] = sum_c' K[c,c'] gzt[c',r]
+//   dK[c,c'] += what[c,r] (y[c,r]-ybar[c]) gzt[c',r]
+//   dy[c,r]  = what uu - mean_r(what uu) + mean_r(gzt[c,.])
+//   dw[c,r]  = what[c,r] ( (y-ybar) uu - sum_c'' what (y-ybar) uu ) + exp(w) gI
+//   dy'[c,r] = gT
+template <int MAXC>
+__global__ void __launch_bounds__(kCciThreads)
+cci_bwd_kernel(const float* __restrict__ u, const float* __restrict__ kernel,
+               const float* __restrict__ grad_out, float* __restrict__ grad_u,
+               float* __restrict__ partial /*(B, C*C)*/, int C, int R) {
+  __shared__ float sK[MAXC * MAXC];
+  __shared__ float red[(kCciThreads / 32) * MAXC];
+  __shared__ float bcast[MAXC];
+  __shared__ float sdK[(kCciThreads / 32) * MAXC * MAXC];   // one slice per warp: no atomics
+  const int64_t b = blockIdx.x;
+  const float* ub = u + b * (int64_t)(3 * C) * R;
+  const float* gb = grad_out + b * (int64_t)(3 * C) * R;
+  float* dub = grad_u + b * (int64_t)(3 * C) * R;
+  for (int i = threadIdx.x; i < C * C; i += blockDim.x) sK[i] = __ldg(kernel + i);
+  for (int i = threadIdx.x; i < (kCciThreads / 32) * MAXC * MAXC; i += blockDim.x) sdK[i] = 0.f;
+  float* my_dK = sdK + (threadIdx.x >> 5) * MAXC * MAXC;
+
+  float ybar[MAXC];
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) ybar[c] = 0.f;
+  for (int r = threadIdx.x; r < R; r += blockDim.x) {
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c)
+      if (c < C) ybar[c] += ub[c * R + r];
+  }
+  block_sum_vec<MAXC>(ybar, C, red, bcast);   // also orders the sK/sdK initialisation
+  const float invR = 1.0f / (float)R;
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) ybar[c] *= invR;
+
+  // pass A: the two means over r that dy needs, and dK
+  float m_wu[MAXC], m_g[MAXC];
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) m_wu[c] = m_g[c] = 0.f;
+  for (int r0 = 0; r0 < R; r0 += blockDim.x) {
+    const int r = r0 + threadIdx.x;
+    const bool live = r < R;
+    float what[MAXC], gzt[MAXC];
+    if (live) {
+      float wmax = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < MAXC; ++c)
+        if (c < C) {
+          what[c] = ub[(C + c) * R + r];
+          wmax = fmaxf(wmax, what[c]);
+        }
+      const float shift = (wmax == -INFINITY) ? 0.f : wmax;
+      float den = 0.f;
+#pragma unroll
+      for (int c = 0; c < MAXC; ++c)
+        if (c < C) {
+          what[c] = expf(what[c] - shift);
+          den += what[c];
+        }
+      const float inv_den = 1.0f / den;
+#pragma unroll
+      for (int c = 0; c < MAXC; ++c)
+        if (c < C) {
+          what[c] *= inv_den;
+          gzt[c] = gb[c * R + r] - gb[(2 * C + c) * R + r];
+          m_g[c] += gzt[c];
+        }
+#pragma unroll
+      for (int c = 0; c < MAXC; ++c)
+        if (c < C) {
+          float uu = 0.f;
+#pragma unroll
+          for (int cp = 0; cp < MAXC; ++cp)
+            if (cp < C) uu = fmaf(sK[c * C + cp], gzt[cp], uu);
+          m_wu[c] += what[c] * uu;
+        }
+    }
+    // dK: warp-reduce each of the C*C products into this warp's private slice
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+      if (c < C) {
+        const float ac = live ? what[c] * (ub[c * R + r] - ybar[c]) : 0.f;
+#pragma unroll
+        for (int cp = 0; cp < MAXC; ++cp) {
+          if (cp < C) {
+            const float s = warp_sum(live ? ac * gzt[cp] : 0.f);
+            if ((threadIdx.x & 31) == 0) my_dK[c * C + cp] += s;
+          }
+        }
+      }
+    }
+  }
+  block_sum_vec<MAXC>(m_wu, C, red, bcast);
+  block_sum_vec<MAXC>(m_g, C, red, bcast);
+  for (int i = threadIdx.x; i < C * C; i += blockDim.x) {   // fixed warp order: deterministic
+    float t = 0.f;
+    for (int w = 0; w < kCciThreads / 32; ++w) t += sdK[w * MAXC * MAXC + i];
+    partial[b * (int64_t)(C * C) + i] = t;
+  }
+
+  // pass B: the gradients themselves
+  for (int r = threadIdx.x; r < R; r += blockDim.x) {
+    float what[MAXC], w[MAXC], gzt[MAXC], t[MAXC], uu[MAXC];
+    float wmax = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c)
+      if (c < C) {
+        w[c] = ub[(C + c) * R + r];
+        wmax = fmaxf(wmax, w[c]);
+      }
+    const float shift = (wmax == -INFINITY) ? 0.f : wmax;
+    float den = 0.f;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c)
+      if (c < C) {
+        what[c] = expf(w[c] - shift);
+        den += what[c];
+      }
+    const float inv_den = 1.0f / den;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c)
+      if (c < C) {
+        what[c] *= inv_den;
+        gzt[c] = gb[c * R + r] - gb[(2 * C + c) * R + r];
+      }
+    float tw = 0.f;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c)
+      if (c < C) {
+        float s = 0.f;
+#pragma unroll
+        for (int cp = 0; cp < MAXC; ++cp)
+          if (cp < C) s = fmaf(sK[c * C + cp], gzt[cp], s);
+        uu[c] = s;
+        t[c] = (ub[c * R + r] - ybar[c]) * s;
+        tw = fmaf(what[c], t[c], tw);
+      }
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c)
+      if (c < C) {
+        dub[c * R + r] = what[c] * uu[c] - m_wu[c] * invR + m_g[c] * invR;
+        dub[(C + c) * R + r] = what[c] * (t[c] - tw) + expf(w[c]) * gb[(C + c) * R + r];
+        dub[(2 * C + c) * R + r] = gb[(2 * C + c) * R + r];
+      }
+  }
+}
+
+int check(const void* u, const void* kernel, int64_t B, int C, int R) {
+  DIC_REQUIRE(u && kernel, DIC_ERR_INVALID_ARGUMENT, "null pointer argument");
+  DIC_REQUIRE(B >= 0 && C > 0 && R > 0, DIC_ERR_INVALID_ARGUMENT, "bad sizes B=%lld C=%d R=%d",
+              (long long)B, C, R);
+  DIC_REQUIRE(C <= 16, DIC_ERR_UNSUPPORTED, "CrossChannelInterp supports d_dim <= 16 (got %d)", C);
+  DIC_REQUIRE(B <= 2147483647LL, DIC_ERR_UNSUPPORTED, "B=%lld exceeds the grid limit", (long long)B);
+  return DIC_OK;
+}
+
+}  // namespace
+}  // namespace dic
+
+using namespace dic;
+
+extern "C" int dic_cci_fwd(const float* u, const float* kernel, float* out, int64_t B, int C, int R,
+                           dic_stream_t stream) {
+  int rc = check(u, kernel, B, C, R);
+  if (rc) return rc;
+  DIC_REQUIRE(out, DIC_ERR_INVALID_ARGUMENT, "null output pointer");
+  if (B == 0) return DIC_OK;
+  cudaStream_t st = as_stream(stream);
+  if (C <= 8) cci_fwd_kernel<8><<<(unsigned)B, kCciThreads, 0, st>>>(u, kernel, out, C, R);
+  else cci_fwd_kernel<16><<<(unsigned)B, kCciThreads, 0, st>>>(u, kernel, out, C, R);
+  DIC_LAUNCH_CHECK("cci_fwd_kernel");
+  return DIC_OK;
+}
+
+extern "C" size_t dic_cci_bwd_workspace_bytes(int64_t B, int C) {
+  if (B < 0 || C <= 0) return 0;
+  size_t part = ((size_t)B * C * C * sizeof(float) + 255) / 256 * 256;
+  return part + (size_t)kColsumBlocks * C * C * sizeof(double) + 256;
+}
+
+extern "C" int dic_cci_bwd(const float* u, const float* kernel, const float* grad_out, float* grad_u,
+                           float* d_kernel, void* workspace, int64_t B, int C, int R,
+                           dic_stream_t stream) {
+  int rc = check(u, kernel, B, C, R);
+  if (rc) return rc;
+  DIC_REQUIRE(grad_out && grad_u && d_kernel && workspace, DIC_ERR_INVALID_ARGUMENT,
+              "null pointer argument");
+  cudaStream_t st = as_stream(stream);
+  if (B == 0) {
+    DIC_CUDA(cudaMemsetAsync(d_kernel, 0, sizeof(float) * C * C, st));
+    return DIC_OK;
+  }
+  unsigned char* ws = static_cast<unsigned char*>(workspace);
+  float* partial = reinterpret_cast<float*>(ws);
+  double* red = reinterpret_cast<double*>(ws + ((size_t)B * C * C * sizeof(float) + 255) / 256 * 256);
+  if (C <= 8)
+    cci_bwd_kernel<8><<<(unsigned)B, kCciThreads, 0, st>>>(u, kernel, grad_out, grad_u, partial, C, R);
+  else
+    cci_bwd_kernel<16><<<(unsigned)B, kCciThreads, 0, st>>>(u, kernel, grad_out, grad_u, partial, C, R);
+  DIC_LAUNCH_CHECK("cci_bwd_kernel");
+  return colsum_f32_launch(partial, nullptr, d_kernel, nullptr, red, B, C * C, st);
+}

@@ -1,0 +1,275 @@
+// RBF read-out (grid -> observation times) forward / backward for sm_100a.
+//
+// Reference: rbf.py:57-108 with the gaussian basis rbf.py:129-131, after compress_fc
+// (v = compress_fc output, (B, C, R)); closed-form backward in SURVEY.md Appendix A.3.
+//     beta = softplus(kernel[c])
+//     phi[t,r] = m_t exp(-beta (d_t - r_r)^2),  N_t = sum_r phi
+//     rec_t = m_t * sum_r phi[t,r] v[c,r] / (N_t + 1e-10)
+// The reduction runs over the reference grid (the transpose of SCI).  There is no
+// softmax shift in the reference (plain exp, absolute epsilon), so none is applied here.
+//
+// Forward: one CTA per encounter, one thread per (vital, observation); the vital's grid
+// row (r_j, v_j) is read as shared-memory broadcasts; one MUFU.EX2 per (t, r).
+// Backward: the reduction for grad_v runs over observations, so the encounter is staged
+// like SCI (interp_stage.cuh) and each lane owns RPT grid points.
+#include "interp_stage.cuh"
+
+namespace dic {
+namespace {
+
+constexpr int kRbfFwdThreads = 256;
+constexpr int kMaxWarps = 16;
+
+__global__ void __launch_bounds__(kRbfFwdThreads)
+rbf_fwd_kernel(const float* __restrict__ v, const float* __restrict__ x,
+               const float* __restrict__ kernel, const float* __restrict__ ref_t,
+               float* __restrict__ rec, float* __restrict__ inv_norm, int C, int T, int R, int Rp) {
+  extern __shared__ __align__(16) float smem[];
+  float2* srv = reinterpret_cast<float2*>(smem);     // [C][Rp] (r_j, v_cj); pad: (0, 0) never read
+  float* snb = smem + 2 * C * Rp;                     // [C] -beta_c log2(e)
+  for (int c = threadIdx.x; c < C; c += blockDim.x) snb[c] = -softplus_ref(__ldg(kernel + c)) * kLog2e;
+  const int64_t b = blockIdx.x;
+  const float* vb = v + b * (int64_t)C * R;
+  for (int i = threadIdx.x; i < C * Rp; i += blockDim.x) {
+    const int c = i / Rp, j = i - c * Rp;
+    srv[i] = j < R ? make_float2(__ldg(ref_t + j), __ldg(vb + c * R + j)) : make_float2(0.f, 0.f);
+  }
+  __syncthreads();
+  const float* mb = x + (b * (int64_t)(4 * C) + C) * T;       // mask plane rows
+  const float* db = x + (b * (int64_t)(4 * C) + 2 * C) * T;   // time plane rows
+  float* rb = rec + b * (int64_t)C * T;
+  float* nb = inv_norm ? inv_norm + b * (int64_t)C * T : nullptr;
+  for (int i = threadIdx.x; i < C * T; i += blockDim.x) {
+    const int c = i / T;
+    const float m = __ldg(mb + i);
+    float out = 0.f, inv = 0.f;
+    if (m != 0.f) {
+      const float d = __ldg(db + i);
+      const float nb2 = snb[c];
+      const float2* row = srv + c * Rp;
+      float N = 0.f, S = 0.f;
+      int j = 0;
+      for (; j + 2 <= R; j += 2) {
+        const float4 p = *reinterpret_cast<const float4*>(row + j);   // (r0, v0, r1, v1)
+        const float d0 = d - p.x, d1 = d - p.z;
+        const float e0 = ex2_approx(d0 * d0 * nb2), e1 = ex2_approx(d1 * d1 * nb2);
+        N += e0;
+        S = fmaf(e0, p.y, S);
+        N += e1;
+        S = fmaf(e1, p.w, S);
+      }
+      if (j < R) {
+        const float2 p = row[j];
+        const float d0 = d - p.x;
+        const float e0 = ex2_approx(d0 * d0 * nb2);
+        N += e0;
+        S = fmaf(e0, p.y, S);
+      }
+      // phi = m e  =>  N_ref = m N, sum phi v = m S
+      inv = 1.0f / (m * N + 1e-10f);
+      out = (m * S) * inv * m;                                  // rbf.py:106-107
+    }
+    rb[i] = out;
+    if (nb) nb[i] = inv;
+  }
+}
+
+struct RbfSmem {
+  uint64_t* bar;
+  float* rows;     // [3][C][Tp]: d | a' = m^2 g invN | a'S = m g invN rec
+  int* n_valid;    // [C]
+  float* part;     // [C * ceil(R/32)]
+};
+
+__device__ __forceinline__ RbfSmem rbf_carve(unsigned char* base, int C, int Tp) {
+  RbfSmem s;
+  s.bar = reinterpret_cast<uint64_t*>(base);
+  s.rows = reinterpret_cast<float*>(base + 16);
+  s.n_valid = reinterpret_cast<int*>(s.rows + 3 * C * Tp);
+  s.part = reinterpret_cast<float*>(s.n_valid + C);
+  return s;
+}
+
+static size_t rbf_bwd_smem_bytes(int C, int Tp, int R) {
+  return 16 + sizeof(float) * (3 * (size_t)C * Tp) + sizeof(int) * C +
+         sizeof(float) * (size_t)C * ((R + 31) / 32);
+}
+
+// grad_v[c,r] = sum_t a'_t e_tr,  d beta_c = -sum_{t,r} n_tr e_tr (a'_t v_r - a'S_t)
+// with e_tr = exp(-beta n_tr), a'_t = m_t^2 g_t invN_t, a'S_t = m_t g_t invN_t rec_t.
+template <int RPT>
+__global__ void __launch_bounds__(kMaxWarps * 32)
+rbf_bwd_kernel(const float* __restrict__ v, const float* __restrict__ x,
+               const float* __restrict__ kernel, const float* __restrict__ ref_t,
+               const float* __restrict__ rec, const float* __restrict__ inv_norm,
+               const float* __restrict__ grad_rec, float* __restrict__ grad_v,
+               float* __restrict__ partial, int C, int T, int Tp, int R) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const RbfSmem s = rbf_carve(smem_raw, C, Tp);
+  const int64_t b = blockIdx.x;
+  const float* mb = x + (b * (int64_t)(4 * C) + C) * T;
+  const float* db = x + (b * (int64_t)(4 * C) + 2 * C) * T;
+  const float* rb = rec + b * (int64_t)C * T;
+  const float* nb = inv_norm + b * (int64_t)C * T;
+  const float* gb = grad_rec + b * (int64_t)C * T;
+  float* sd = s.rows;
+  float* sa = s.rows + C * Tp;
+  float* sas = s.rows + 2 * C * Tp;
+  for (int i = threadIdx.x; i < C * T; i += blockDim.x) {
+    const int c = i / T, t = i - c * T;
+    const float m = __ldg(mb + i);
+    const float gi = __ldg(gb + i) * __ldg(nb + i) * m;
+    sd[c * Tp + t] = __ldg(db + i);
+    sa[c * Tp + t] = gi * m;
+    sas[c * Tp + t] = gi * __ldg(rb + i);
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int c = warp; c < C; c += nwarps) {
+    // drop observations that carry no gradient (masked, or zero upstream): keep a' != 0
+    const int n = warp_compact3(sas + c * Tp, sa + c * Tp, sd + c * Tp, T, lane, false);
+    warp_pad4(sd + c * Tp, sa + c * Tp, sas + c * Tp, n, lane);
+    if (lane == 0) s.n_valid[c] = n;
+  }
+  __syncthreads();
+
+  const int chunks = (R + 32 * RPT - 1) / (32 * RPT);
+  const float* vb = v + b * (int64_t)C * R;
+  float* gvb = grad_v + b * (int64_t)C * R;
+  for (int task = warp; task < C * chunks; task += nwarps) {
+    const int c = task / chunks, chunk = task - c * chunks;
+    const float* rd = sd + c * Tp;
+    const float* ra = sa + c * Tp;
+    const float* ras = sas + c * Tp;
+    const int n = s.n_valid[c];
+    const float nb2 = -softplus_ref(__ldg(kernel + c)) * kLog2e;
+    int ridx[RPT];
+    float rr[RPT], vv[RPT], dv[RPT], acc[RPT];
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) {
+      ridx[k] = chunk * 32 * RPT + k * 32 + lane;
+      const int rc = min(ridx[k], R - 1);
+      rr[k] = __ldg(ref_t + rc);
+      vv[k] = __ldg(vb + c * R + rc);
+      dv[k] = acc[k] = 0.f;
+    }
+    const int n4 = (n + 3) & ~3;
+    for (int t0 = 0; t0 < n4; t0 += 4) {
+      const float4 d4 = *reinterpret_cast<const float4*>(rd + t0);
+      const float4 a4 = *reinterpret_cast<const float4*>(ra + t0);
+      const float4 s4 = *reinterpret_cast<const float4*>(ras + t0);
+      const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
+      const float aa[4] = {a4.x, a4.y, a4.z, a4.w};
+      const float as[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) {
+          const float dl = dd[j] - rr[k];
+          const float n2 = dl * dl;
+          const float e = ex2_approx(n2 * nb2);
+          dv[k] = fmaf(e, aa[j], dv[k]);
+          const float tt = fmaf(aa[j], vv[k], -as[j]);
+          acc[k] = fmaf(e * n2, tt, acc[k]);
+        }
+      }
+    }
+    float tot = 0.f;
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) {
+      if (ridx[k] < R) {
+        gvb[c * R + ridx[k]] = dv[k];
+        tot += acc[k];
+      }
+    }
+    tot = warp_sum(tot);
+    if (lane == 0) s.part[task] = tot;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float t = 0.f;
+    for (int k = 0; k < chunks; ++k) t += s.part[c * chunks + k];
+    partial[b * C + c] = -t;
+  }
+}
+
+__global__ void sigmoid_vec_kernel(const float* __restrict__ kernel, float* __restrict__ out, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) out[c] = sigmoid_ref(kernel[c]);
+}
+
+int check(const void* v, const void* x, const void* kernel, const void* ref_t, int64_t B, int C,
+          int T, int R) {
+  DIC_REQUIRE(v && x && kernel && ref_t, DIC_ERR_INVALID_ARGUMENT, "null pointer argument");
+  DIC_REQUIRE(B >= 0 && C > 0 && T > 0 && R > 0, DIC_ERR_INVALID_ARGUMENT,
+              "bad sizes B=%lld C=%d T=%d R=%d", (long long)B, C, T, R);
+  DIC_REQUIRE(B <= 2147483647LL, DIC_ERR_UNSUPPORTED, "B=%lld exceeds the grid limit", (long long)B);
+  return DIC_OK;
+}
+
+}  // namespace
+}  // namespace dic
+
+using namespace dic;
+
+extern "C" int dic_rbf_fwd(const float* v, const float* x, const float* kernel, const float* ref_t,
+                           float* rec, float* inv_norm, int64_t B, int C, int T, int R,
+                           dic_stream_t stream) {
+  int rc = check(v, x, kernel, ref_t, B, C, T, R);
+  if (rc) return rc;
+  DIC_REQUIRE(rec, DIC_ERR_INVALID_ARGUMENT, "null output pointer");
+  if (B == 0) return DIC_OK;
+  const int Rp = round_up(R, 2);
+  const size_t smem = sizeof(float2) * (size_t)C * Rp + sizeof(float) * C;
+  DIC_REQUIRE(smem <= (size_t)kMaxSmemBytes, DIC_ERR_UNSUPPORTED,
+              "C=%d R=%d needs %zu bytes of shared memory (limit %d)", C, R, smem, kMaxSmemBytes);
+  if (smem > 48 * 1024)
+    DIC_CUDA(cudaFuncSetAttribute(rbf_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  rbf_fwd_kernel<<<(unsigned)B, kRbfFwdThreads, smem, as_stream(stream)>>>(v, x, kernel, ref_t, rec,
+                                                                          inv_norm, C, T, R, Rp);
+  DIC_LAUNCH_CHECK("rbf_fwd_kernel");
+  return DIC_OK;
+}
+
+extern "C" int dic_rbf_bwd(const float* v, const float* x, const float* kernel, const float* ref_t,
+                           const float* rec, const float* inv_norm, const float* grad_rec,
+                           float* grad_v, float* d_kernel, void* workspace, int64_t B, int C, int T,
+                           int R, dic_stream_t stream) {
+  int rc = check(v, x, kernel, ref_t, B, C, T, R);
+  if (rc) return rc;
+  DIC_REQUIRE(rec && inv_norm && grad_rec && grad_v && d_kernel && workspace,
+              DIC_ERR_INVALID_ARGUMENT, "null pointer argument");
+  cudaStream_t st = as_stream(stream);
+  if (B == 0) {
+    DIC_CUDA(cudaMemsetAsync(d_kernel, 0, sizeof(float) * C, st));
+    return DIC_OK;
+  }
+  const int Tp = round_up(T, 4);
+  const size_t smem = rbf_bwd_smem_bytes(C, Tp, R);
+  DIC_REQUIRE(smem <= (size_t)kMaxSmemBytes, DIC_ERR_UNSUPPORTED,
+              "C=%d T=%d needs %zu bytes of shared memory per encounter (limit %d)", C, T, smem,
+              kMaxSmemBytes);
+  const int rpt = R <= 32 ? 1 : (R <= 64 ? 2 : 3);
+  const int chunks = (R + 32 * rpt - 1) / (32 * rpt);
+  int warps = C * chunks;
+  warps = warps > kMaxWarps ? kMaxWarps : (warps < 4 ? 4 : warps);
+  unsigned char* ws = static_cast<unsigned char*>(workspace);
+  float* partial = reinterpret_cast<float*>(ws);
+  size_t off = ((size_t)B * C * sizeof(float) + 255) / 256 * 256;
+  double* red = reinterpret_cast<double*>(ws + off);
+  float* sig = reinterpret_cast<float*>(ws + off + (size_t)kColsumBlocks * C * sizeof(double));
+#define DIC_RBF_BWD(RPT_)                                                                        \
+  {                                                                                              \
+    if (smem > 48 * 1024)                                                                        \
+      DIC_CUDA(cudaFuncSetAttribute(rbf_bwd_kernel<RPT_>,                                        \
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+    rbf_bwd_kernel<RPT_><<<(unsigned)B, warps * 32, smem, st>>>(                                 \
+        v, x, kernel, ref_t, rec, inv_norm, grad_rec, grad_v, partial, C, T, Tp, R);             \
+  }
+  if (rpt == 1) DIC_RBF_BWD(1) else if (rpt == 2) DIC_RBF_BWD(2) else DIC_RBF_BWD(3)
+#undef DIC_RBF_BWD
+  DIC_LAUNCH_CHECK("rbf_bwd_kernel");
+  sigmoid_vec_kernel<<<(C + 127) / 128, 128, 0, st>>>(kernel, sig, C);
+  DIC_LAUNCH_CHECK("sigmoid_vec_kernel");
+  return colsum_f32_launch(partial, nullptr, d_kernel, sig, red, B, C, st);
+}

@@ -1,0 +1,358 @@
+// SingleChannelInterp forward / backward for sm_100a.
+//
+// Reference: interpolation_layer.py:31-86 (forward); the backward is what autograd
+// derives from it (closed form in SURVEY.md Appendix A.1).
+//
+// Per (encounter b, vital c, reference point r) with alpha = softplus(kernel[c]):
+//     s_t  = -alpha (d_t - r)^2 + log m_t
+//     w    = logsumexp_t s_t                       (log-intensity)
+//     y    = sum_t softmax_t(s) x_t                (low-pass)
+//     y'   = the same with 10 alpha                (high-pass, kappa = 10)
+//
+// Kernel design (one CTA = one encounter, one warp-task = one vital x 32*RPT grid points)
+//   * rows are staged with one TMA bulk copy and canonicalised (interp_stage.cuh);
+//   * the softmax shift is known without a pass over the data: the maximum of s_t is at the
+//     observation nearest to r, found by binary search in the sorted times (d*);
+//   * the exponent is evaluated as -(alpha log2 e) (d - d*)(d + d* - 2r), the exact
+//     difference of squares, so no large squares are subtracted;
+//   * ONE MUFU.EX2 per (t, r): the high-pass weight is e^10 (4 FMULs) because both filters
+//     share the shift;
+//   * accumulators stay in registers, each lane owns RPT grid points, observations are
+//     read as 128-bit shared-memory broadcasts; outputs are written coalesced along r.
+#include "interp_stage.cuh"
+
+namespace dic {
+namespace {
+
+constexpr int kMaxWarps = 16;
+
+struct SciSmem {
+  // dynamic shared memory layout: bar | rows[3][C][Tp] | n_valid[C] (int) | part[C*ceil(R/32)]
+  float* rows;
+  int* n_valid;
+  float* part;
+  uint64_t* bar;
+};
+
+__device__ __forceinline__ SciSmem sci_carve(unsigned char* base, int C, int Tp) {
+  SciSmem s;
+  s.bar = reinterpret_cast<uint64_t*>(base);
+  s.rows = reinterpret_cast<float*>(base + 16);
+  s.n_valid = reinterpret_cast<int*>(s.rows + 3 * C * Tp);
+  s.part = reinterpret_cast<float*>(s.n_valid + C);
+  return s;
+}
+
+static size_t sci_smem_bytes(int C, int Tp, int R) {
+  return 16 + sizeof(float) * (3 * (size_t)C * Tp) + sizeof(int) * C +
+         sizeof(float) * (size_t)C * ((R + 31) / 32);
+}
+
+// Stage + canonicalise one encounter.  After return (CTA-synchronised):
+//   rows[0][c] = m*x, rows[1][c] = m, rows[2][c] = d, all compacted+sorted+padded; n_valid[c].
+__device__ __forceinline__ void sci_stage(const SciSmem& s, const float* xb, int C, int T, int Tp,
+                                          bool use_tma) {
+  stage_rows(s.rows, xb, 3 * C, T, Tp, s.bar, use_tma);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int c = warp; c < C; c += nwarps) {
+    float* sx = s.rows + (0 * C + c) * Tp;
+    float* sm = s.rows + (1 * C + c) * Tp;
+    float* sd = s.rows + (2 * C + c) * Tp;
+    const int n = warp_compact3(sx, sm, sd, T, lane, /*fold_mask_into_r0=*/true);
+    warp_sort3(sd, sx, sm, n, lane);
+    warp_pad4(sd, sx, sm, n, lane);
+    if (lane == 0) s.n_valid[c] = n;
+  }
+  __syncthreads();
+}
+
+template <int RPT>
+__global__ void __launch_bounds__(kMaxWarps * 32)
+sci_fwd_kernel(const float* __restrict__ x, const float* __restrict__ kernel,
+               const float* __restrict__ ref_t, float* __restrict__ u, float* __restrict__ stats,
+               int C, int T, int Tp, int R, int use_tma) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const SciSmem s = sci_carve(smem_raw, C, Tp);
+  const int64_t b = blockIdx.x;
+  sci_stage(s, x + b * (int64_t)(4 * C) * T, C, T, Tp, use_tma != 0);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int chunks = (R + 32 * RPT - 1) / (32 * RPT);
+  float* ub = u + b * (int64_t)(3 * C) * R;
+  float* sb = stats ? stats + b * (int64_t)(2 * C) * R : nullptr;
+
+  for (int task = warp; task < C * chunks; task += nwarps) {
+    const int c = task / chunks, chunk = task - c * chunks;
+    const float* sx = s.rows + (0 * C + c) * Tp;
+    const float* sm = s.rows + (1 * C + c) * Tp;
+    const float* sd = s.rows + (2 * C + c) * Tp;
+    const int n = s.n_valid[c];
+    const float alpha = softplus_ref(__ldg(kernel + c));
+    const float a = alpha * kLog2e;
+
+    int ridx[RPT];
+    float rr[RPT], dstar[RPT], cr[RPT], s1[RPT], sy[RPT], s10[RPT], sy10[RPT];
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) {
+      ridx[k] = chunk * 32 * RPT + k * 32 + lane;
+      rr[k] = __ldg(ref_t + min(ridx[k], R - 1));
+      dstar[k] = n > 0 ? sd[nearest_sorted(sd, n, rr[k])] : 0.f;
+      cr[k] = a * (2.f * rr[k] - dstar[k]);
+      s1[k] = sy[k] = s10[k] = sy10[k] = 0.f;
+    }
+    const int n4 = (n + 3) & ~3;
+    for (int t0 = 0; t0 < n4; t0 += 4) {
+      const float4 d4 = *reinterpret_cast<const float4*>(sd + t0);
+      const float4 x4 = *reinterpret_cast<const float4*>(sx + t0);
+      const float4 m4 = *reinterpret_cast<const float4*>(sm + t0);
+      const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
+      const float xx[4] = {x4.x, x4.y, x4.z, x4.w};
+      const float mm[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) {
+          const float uu = dd[j] - dstar[k];
+          const float vv = fmaf(-a, dd[j], cr[k]);
+          const float e = ex2_approx(uu * vv);
+          const float e2 = e * e, e4 = e2 * e2, e8 = e4 * e4, e10 = e8 * e2;
+          s1[k] = fmaf(mm[j], e, s1[k]);
+          sy[k] = fmaf(xx[j], e, sy[k]);
+          s10[k] = fmaf(mm[j], e10, s10[k]);
+          sy10[k] = fmaf(xx[j], e10, sy10[k]);
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) {
+      if (ridx[k] < R) {
+        float y, w, y10;
+        if (n > 0) {
+          const float dr = dstar[k] - rr[k];
+          w = logf(s1[k]) - alpha * dr * dr;
+          y = sy[k] / s1[k];
+          y10 = sy10[k] / s10[k];
+        } else {  // all-masked channel: the reference yields -inf / NaN (logsumexp of -inf)
+          w = -INFINITY;
+          y = y10 = __int_as_float(0x7fc00000);
+        }
+        ub[(0 * C + c) * R + ridx[k]] = y;
+        ub[(1 * C + c) * R + ridx[k]] = w;
+        ub[(2 * C + c) * R + ridx[k]] = y10;
+        if (sb) {
+          sb[(0 * C + c) * R + ridx[k]] = s1[k];
+          sb[(1 * C + c) * R + ridx[k]] = s10[k];
+        }
+      }
+    }
+  }
+}
+
+// Backward: d/d alpha_c = sum_{t,r} -n_tr (ds_t + 10 ds'_t)   (Appendix A.1), with
+//   ds_t  = e   (mx A  + m B ),  A  = gy /S1,       B  = (gw - y gy)/S1
+//   ds'_t = e10 (mx A' + m B'),  A' = gy'/S10,      B' = -y' gy'/S10
+// and n_tr = nmin - arg/a.  Writes one partial per (encounter, vital).
+template <int RPT>
+__global__ void __launch_bounds__(kMaxWarps * 32)
+sci_bwd_kernel(const float* __restrict__ x, const float* __restrict__ kernel,
+               const float* __restrict__ ref_t, const float* __restrict__ u,
+               const float* __restrict__ stats, const float* __restrict__ grad_u,
+               float* __restrict__ partial, int C, int T, int Tp, int R, int use_tma) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const SciSmem s = sci_carve(smem_raw, C, Tp);
+  const int64_t b = blockIdx.x;
+  sci_stage(s, x + b * (int64_t)(4 * C) * T, C, T, Tp, use_tma != 0);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int chunks = (R + 32 * RPT - 1) / (32 * RPT);
+  const float* ub = u + b * (int64_t)(3 * C) * R;
+  const float* gb = grad_u + b * (int64_t)(3 * C) * R;
+  const float* sb = stats + b * (int64_t)(2 * C) * R;
+
+  for (int task = warp; task < C * chunks; task += nwarps) {
+    const int c = task / chunks, chunk = task - c * chunks;
+    const float* sx = s.rows + (0 * C + c) * Tp;
+    const float* sm = s.rows + (1 * C + c) * Tp;
+    const float* sd = s.rows + (2 * C + c) * Tp;
+    const int n = s.n_valid[c];
+    float tot = 0.f;
+    if (n > 0) {  // an all-masked channel contributes nothing (the reference's grad is NaN there)
+      const float alpha = softplus_ref(__ldg(kernel + c));
+      const float a = alpha * kLog2e;
+      const float inv_a = 1.0f / a;
+
+      float dstar[RPT], cr[RPT], nmin[RPT], A[RPT], Bc[RPT], A10[RPT], B10[RPT], acc[RPT];
+#pragma unroll
+      for (int k = 0; k < RPT; ++k) {
+        const int r = chunk * 32 * RPT + k * 32 + lane;
+        const bool live = r < R;
+        const int rc = min(r, R - 1);
+        const float rr = __ldg(ref_t + rc);
+        dstar[k] = sd[nearest_sorted(sd, n, rr)];
+        cr[k] = a * (2.f * rr - dstar[k]);
+        const float dr = dstar[k] - rr;
+        nmin[k] = dr * dr;
+        const float y = ub[(0 * C + c) * R + rc], y10 = ub[(2 * C + c) * R + rc];
+        const float gy = live ? gb[(0 * C + c) * R + rc] : 0.f;
+        const float gw = live ? gb[(1 * C + c) * R + rc] : 0.f;
+        const float gy10 = live ? gb[(2 * C + c) * R + rc] : 0.f;
+        const float i1 = 1.0f / sb[(0 * C + c) * R + rc];
+        const float i10 = 10.0f / sb[(1 * C + c) * R + rc];
+        A[k] = gy * i1;
+        Bc[k] = (gw - y * gy) * i1;
+        A10[k] = gy10 * i10;
+        B10[k] = -y10 * gy10 * i10;
+        acc[k] = 0.f;
+      }
+      const int n4 = (n + 3) & ~3;
+      for (int t0 = 0; t0 < n4; t0 += 4) {
+        const float4 d4 = *reinterpret_cast<const float4*>(sd + t0);
+        const float4 x4 = *reinterpret_cast<const float4*>(sx + t0);
+        const float4 m4 = *reinterpret_cast<const float4*>(sm + t0);
+        const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
+        const float xx[4] = {x4.x, x4.y, x4.z, x4.w};
+        const float mm[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+          for (int k = 0; k < RPT; ++k) {
+            const float uu = dd[j] - dstar[k];
+            const float vv = fmaf(-a, dd[j], cr[k]);
+            const float arg = uu * vv;
+            const float e = ex2_approx(arg);
+            const float e2 = e * e, e4 = e2 * e2, e8 = e4 * e4, e10 = e8 * e2;
+            const float g1 = fmaf(xx[j], A[k], mm[j] * Bc[k]);
+            const float g10 = fmaf(xx[j], A10[k], mm[j] * B10[k]);
+            const float h = fmaf(e10, g10, e * g1);
+            const float nn = fmaf(arg, -inv_a, nmin[k]);
+            acc[k] = fmaf(nn, h, acc[k]);
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < RPT; ++k) tot += acc[k];
+      tot = warp_sum(tot);
+    }
+    if (lane == 0) s.part[task] = tot;
+  }
+  __syncthreads();
+  // chunks of one vital are summed in a fixed order -> deterministic partials
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float t = 0.f;
+    for (int k = 0; k < chunks; ++k) t += s.part[c * chunks + k];
+    partial[b * C + c] = -t;
+  }
+}
+
+// d_kernel[c] = sigmoid(kernel[c]) * sum_b partial[b][c]
+__global__ void sigmoid_vec_kernel(const float* __restrict__ kernel, float* __restrict__ out, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) out[c] = sigmoid_ref(kernel[c]);
+}
+
+int pick_rpt(int R) { return R <= 32 ? 1 : (R <= 64 ? 2 : 3); }
+
+int pick_warps(int C, int R, int rpt) {
+  const int chunks = (R + 32 * rpt - 1) / (32 * rpt);
+  int w = C * chunks;
+  if (w > kMaxWarps) w = kMaxWarps;
+  if (w < 2) w = 2;
+  return w;
+}
+
+template <typename K>
+int prepare(K kern, size_t smem) {
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
+  }
+  return DIC_OK;
+}
+
+int check_common(const void* x, const void* kernel, const void* ref_t, int64_t B, int C, int T, int R) {
+  DIC_REQUIRE(x && kernel && ref_t, DIC_ERR_INVALID_ARGUMENT, "null pointer argument");
+  DIC_REQUIRE(B >= 0 && C > 0 && T > 0 && R > 0, DIC_ERR_INVALID_ARGUMENT,
+              "bad sizes B=%lld C=%d T=%d R=%d", (long long)B, C, T, R);
+  DIC_REQUIRE(B <= 2147483647LL, DIC_ERR_UNSUPPORTED, "B=%lld exceeds the grid limit; split the batch",
+              (long long)B);
+  DIC_REQUIRE(sci_smem_bytes(C, round_up(T, 4), R) <= (size_t)kMaxSmemBytes, DIC_ERR_UNSUPPORTED,
+              "C=%d T=%d needs %zu bytes of shared memory per encounter (limit %d)", C, T,
+              sci_smem_bytes(C, round_up(T, 4), R), kMaxSmemBytes);
+  return DIC_OK;
+}
+
+}  // namespace
+}  // namespace dic
+
+using namespace dic;
+
+extern "C" int dic_sci_fwd(const float* x, const float* kernel, const float* ref_t, float* u,
+                           float* stats, int64_t B, int C, int T, int R, dic_stream_t stream) {
+  int rc = check_common(x, kernel, ref_t, B, C, T, R);
+  if (rc) return rc;
+  DIC_REQUIRE(u, DIC_ERR_INVALID_ARGUMENT, "null output pointer");
+  if (B == 0) return DIC_OK;
+  const int Tp = round_up(T, 4);
+  const size_t smem = sci_smem_bytes(C, Tp, R);
+  const int use_tma = (Tp == T) && aligned16(x) && ((3LL * C * T * 4) % 16 == 0) &&
+                      (((int64_t)4 * C * T * 4) % 16 == 0);
+  const int rpt = pick_rpt(R);
+  const int threads = 32 * pick_warps(C, R, rpt);
+  cudaStream_t st = as_stream(stream);
+#define DIC_SCI_FWD(RPT_)                                                                   \
+  {                                                                                         \
+    rc = prepare(sci_fwd_kernel<RPT_>, smem);                                               \
+    if (rc) return rc;                                                                      \
+    sci_fwd_kernel<RPT_><<<(unsigned)B, threads, smem, st>>>(x, kernel, ref_t, u, stats, C, \
+                                                              T, Tp, R, use_tma);           \
+  }
+  if (rpt == 1) DIC_SCI_FWD(1) else if (rpt == 2) DIC_SCI_FWD(2) else DIC_SCI_FWD(3)
+#undef DIC_SCI_FWD
+  DIC_LAUNCH_CHECK("sci_fwd_kernel");
+  return DIC_OK;
+}
+
+extern "C" size_t dic_interp_bwd_workspace_bytes(int64_t B, int C) {
+  if (B < 0 || C <= 0) return 0;
+  size_t part = ((size_t)B * C * sizeof(float) + 255) / 256 * 256;
+  return part + (size_t)kColsumBlocks * C * sizeof(double) + (size_t)C * sizeof(float) + 256;
+}
+
+extern "C" int dic_sci_bwd(const float* x, const float* kernel, const float* ref_t, const float* u,
+                           const float* stats, const float* grad_u, float* d_kernel,
+                           void* workspace, int64_t B, int C, int T, int R, dic_stream_t stream) {
+  int rc = check_common(x, kernel, ref_t, B, C, T, R);
+  if (rc) return rc;
+  DIC_REQUIRE(u && stats && grad_u && d_kernel && workspace, DIC_ERR_INVALID_ARGUMENT,
+              "null pointer argument");
+  cudaStream_t st = as_stream(stream);
+  if (B == 0) {
+    DIC_CUDA(cudaMemsetAsync(d_kernel, 0, sizeof(float) * C, st));
+    return DIC_OK;
+  }
+  const int Tp = round_up(T, 4);
+  const size_t smem = sci_smem_bytes(C, Tp, R);
+  const int use_tma = (Tp == T) && aligned16(x) && ((3LL * C * T * 4) % 16 == 0) &&
+                      (((int64_t)4 * C * T * 4) % 16 == 0);
+  const int rpt = pick_rpt(R);
+  const int threads = 32 * pick_warps(C, R, rpt);
+  unsigned char* ws = static_cast<unsigned char*>(workspace);
+  float* partial = reinterpret_cast<float*>(ws);
+  size_t off = ((size_t)B * C * sizeof(float) + 255) / 256 * 256;
+  double* red = reinterpret_cast<double*>(ws + off);
+  float* sig = reinterpret_cast<float*>(ws + off + (size_t)kColsumBlocks * C * sizeof(double));
+#define DIC_SCI_BWD(RPT_)                                                                      \
+  {                                                                                            \
+    rc = prepare(sci_bwd_kernel<RPT_>, smem);                                                  \
+    if (rc) return rc;                                                                         \
+    sci_bwd_kernel<RPT_><<<(unsigned)B, threads, smem, st>>>(x, kernel, ref_t, u, stats,       \
+                                                              grad_u, partial, C, T, Tp, R,    \
+                                                              use_tma);                        \
+  }
+  if (rpt == 1) DIC_SCI_BWD(1) else if (rpt == 2) DIC_SCI_BWD(2) else DIC_SCI_BWD(3)
+#undef DIC_SCI_BWD
+  DIC_LAUNCH_CHECK("sci_bwd_kernel");
+  sigmoid_vec_kernel<<<(C + 127) / 128, 128, 0, st>>>(kernel, sig, C);
+  DIC_LAUNCH_CHECK("sigmoid_vec_kernel");
+  return colsum_f32_launch(partial, nullptr, d_kernel, sig, red, B, C, st);
+}

@@ -1,0 +1,125 @@
+// Per-encounter staging shared by the SCI forward/backward and RBF backward kernels.
+//
+// One CTA owns one encounter.  Its observation rows are brought into shared memory
+// (one 1-D TMA bulk copy when the span is 16-byte friendly), then every channel is
+// CANONICALISED by one warp: observations with a zero mask are dropped (stable
+// compaction), the rest are sorted by time (odd-even transposition with early exit:
+// free for the left-packed, time-ordered rows the reference pipeline produces,
+// p0_data_process.py:44-67; correct for the jittered or shuffled rows of
+// dataloader.py:207-208), and the tail is padded to a multiple of four with
+// zero-weight entries so the inner loops can use 128-bit shared loads.
+#pragma once
+
+#include "common.cuh"
+
+namespace dic {
+
+// Stable in-place compaction of three parallel rows by `keep(m)`; returns the count.
+// r0 <- f0(r0, m) lets the caller fold the mask into the value row on the fly.
+// Executed by ONE warp.
+__device__ __forceinline__ int warp_compact3(float* r0, float* rm, float* r2, int T, int lane,
+                                             bool fold_mask_into_r0) {
+  int n = 0;
+  for (int t0 = 0; t0 < T; t0 += 32) {
+    const int t = t0 + lane;
+    float a = 0.f, m = 0.f, d = 0.f;
+    if (t < T) {
+      a = r0[t];
+      m = rm[t];
+      d = r2[t];
+    }
+    const bool keep = (t < T) && (m != 0.f);
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    const int pos = n + __popc(bal & ((1u << lane) - 1u));
+    __syncwarp();
+    if (keep) {
+      r0[pos] = fold_mask_into_r0 ? a * m : a;
+      rm[pos] = m;
+      r2[pos] = d;
+    }
+    n += __popc(bal);
+    __syncwarp();
+  }
+  return n;
+}
+
+// Odd-even transposition sort of rows (key, a, b) by key, ascending; one warp.
+// Terminates after the first full pass without a swap.
+__device__ __forceinline__ void warp_sort3(float* key, float* a, float* b, int n, int lane) {
+  if (n < 2) return;
+  for (int pass = 0; pass < n; ++pass) {
+    int swapped = 0;
+#pragma unroll
+    for (int phase = 0; phase < 2; ++phase) {
+      for (int i = phase + 2 * lane; i + 1 < n; i += 64) {
+        const float k0 = key[i], k1 = key[i + 1];
+        if (k0 > k1) {
+          key[i] = k1;
+          key[i + 1] = k0;
+          float t = a[i];
+          a[i] = a[i + 1];
+          a[i + 1] = t;
+          t = b[i];
+          b[i] = b[i + 1];
+          b[i + 1] = t;
+          swapped = 1;
+        }
+      }
+      __syncwarp();
+    }
+    if (!__any_sync(0xffffffffu, swapped)) break;
+  }
+}
+
+// Pads rows to a multiple of 4 entries with zero-weight copies of the last key.
+__device__ __forceinline__ void warp_pad4(float* key, float* a, float* b, int n, int lane) {
+  const int n4 = (n + 3) & ~3;
+  if (lane < n4 - n) {
+    key[n + lane] = n > 0 ? key[n - 1] : 0.f;
+    a[n + lane] = 0.f;
+    b[n + lane] = 0.f;
+  }
+  __syncwarp();
+}
+
+// Index of the key nearest to r in sorted key[0..n), n >= 1.
+__device__ __forceinline__ int nearest_sorted(const float* key, int n, float r) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (key[mid] < r) lo = mid + 1; else hi = mid;
+  }
+  if (lo == n) return n - 1;
+  if (lo == 0) return 0;
+  return (r - key[lo - 1] <= key[lo] - r) ? lo - 1 : lo;
+}
+
+// Brings `nrows` consecutive global rows of length T (row stride T) into shared rows of
+// stride Tp.  Uses one TMA bulk copy when Tp == T and the span is 16-byte aligned/sized;
+// otherwise plain coalesced loads.  Must be called by all threads; ends with the data
+// visible to the whole CTA.
+__device__ __forceinline__ void stage_rows(float* smem_rows, const float* gsrc, int nrows, int T,
+                                           int Tp, uint64_t* bar, bool use_tma) {
+  if (use_tma) {
+    if (threadIdx.x == 0) {
+      mbar_init(bar, 1);
+      fence_proxy_async();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const uint32_t bytes = static_cast<uint32_t>(nrows) * T * 4u;
+      mbar_expect_tx(bar, bytes);
+      bulk_g2s(smem_rows, gsrc, bytes, bar);
+    }
+    mbar_wait(bar, 0);
+  } else {
+    const int total = nrows * T;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+      const int row = i / T, t = i - row * T;
+      smem_rows[row * Tp + t] = __ldg(gsrc + i);
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace dic

@@ -1,0 +1,498 @@
+// k-means (Lloyd) / k-means++ / pairwise-distance "inertia" kernels for sm_100a.
+//
+// The reference delegates to scikit-learn (unpinned; 1.9.0 in the container):
+//   KMeans.fit / fit_predict / predict      p2_clustering_optK.py:260,284,372,377,
+//                                           clustering_trainer.py:75-82
+//   pairwise_distances(X[a == c]) -> mean   p2_clustering_optK.py:334-351
+// These kernels implement the same arithmetic (sklearn/cluster/_k_means_lloyd.pyx:23-218,
+// _k_means_common.pyx:96-124, _kmeans.py:224-281) in the data's own dtype (float32 data,
+// float64 reference draws) with float64 cross-block reductions.
+//
+// Lloyd pass = one read of X.  A CTA streams tiles of TILE rows through shared memory
+// (coalesced global reads, odd 16-byte row stride => conflict-free 128-bit reads), phase 1
+// gives each thread one row against all K centres (centres broadcast from shared memory, 4
+// centres register-blocked), phase 2 re-maps threads to columns and adds the tile into
+// per-CTA [K][D] sums (no atomics on the data path).  HBM-bound: N*D*sizeof(T) bytes/pass.
+#include "common.cuh"
+
+namespace dic {
+namespace {
+
+template <typename T> struct Vec16;
+template <> struct Vec16<float> { using type = float4; static constexpr int n = 4; };
+template <> struct Vec16<double> { using type = double2; static constexpr int n = 2; };
+
+__device__ __forceinline__ float dot16(const float4& a, const float4& b, float acc) {
+  acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); return fmaf(a.w, b.w, acc);
+}
+__device__ __forceinline__ double dot16(const double2& a, const double2& b, double acc) {
+  acc = fma(a.x, b.x, acc); return fma(a.y, b.y, acc);
+}
+__device__ __forceinline__ float sqd16(const float4& a, const float4& b, float acc) {
+  const float p = a.x - b.x, q = a.y - b.y, r = a.z - b.z, s = a.w - b.w;
+  acc = fmaf(p, p, acc); acc = fmaf(q, q, acc); acc = fmaf(r, r, acc); return fmaf(s, s, acc);
+}
+__device__ __forceinline__ double sqd16(const double2& a, const double2& b, double acc) {
+  const double p = a.x - b.x, q = a.y - b.y;
+  acc = fma(p, p, acc); return fma(q, q, acc);
+}
+
+// Row stride in 16-byte units: covers D elements, forced odd (conflict-free 128-bit reads).
+template <typename T> static inline int row_stride16(int D) {
+  const int per = 16 / (int)sizeof(T);
+  return ((D + per - 1) / per) | 1;
+}
+
+struct KmLayout {
+  size_t off_c, off_cn, off_acc, off_cnt, off_lab, off_x, total;
+};
+template <typename T> static KmLayout km_layout(int K, int D, int tile) {
+  const int s16 = row_stride16<T>(D);
+  KmLayout L;
+  size_t o = 0;
+  L.off_c = o;   o += (size_t)K * s16 * 16;
+  L.off_x = o;   o += (size_t)tile * s16 * 16;
+  L.off_acc = o; o += (size_t)K * D * sizeof(T);
+  o = (o + 15) & ~(size_t)15;
+  L.off_cn = o;  o += (size_t)K * sizeof(T);
+  o = (o + 15) & ~(size_t)15;
+  L.off_cnt = o; o += (size_t)K * sizeof(int);
+  L.off_lab = o; o += (size_t)tile * sizeof(int);
+  L.total = (o + 15) & ~(size_t)15;
+  return L;
+}
+
+template <typename T>
+__global__ void kmeans_assign_kernel(const T* __restrict__ X, const T* __restrict__ centers,
+                                     int32_t* __restrict__ labels, double* __restrict__ ws, int64_t N, int D,
+                                     int K, int s16, int flags, KmLayout L, int want_sums) {
+  using V = typename Vec16<T>::type;
+  constexpr int PER = Vec16<T>::n;
+  extern __shared__ __align__(16) unsigned char smem[];
+  V* sc = reinterpret_cast<V*>(smem + L.off_c);
+  V* sx = reinterpret_cast<V*>(smem + L.off_x);
+  T* sacc = reinterpret_cast<T*>(smem + L.off_acc);
+  T* scn = reinterpret_cast<T*>(smem + L.off_cn);
+  int* scnt = reinterpret_cast<int*>(smem + L.off_cnt);
+  int* slab = reinterpret_cast<int*>(smem + L.off_lab);
+  const int tile = blockDim.x, tid = threadIdx.x;
+  const int Dp = s16 * PER;
+
+  // centres (zero padded to Dp), their squared norms, zeroed accumulators
+  for (int i = tid; i < K * Dp; i += tile) {
+    const int k = i / Dp, d = i - k * Dp;
+    reinterpret_cast<T*>(sc)[i] = d < D ? centers[(int64_t)k * D + d] : T(0);
+  }
+  for (int i = tid; i < K * D; i += tile) sacc[i] = T(0);
+  for (int i = tid; i < K; i += tile) scnt[i] = 0;
+  __syncthreads();
+  for (int k = tid; k < K; k += tile) {
+    T s = T(0);
+    for (int d = 0; d < D; ++d) {
+      const T c = reinterpret_cast<T*>(sc)[k * Dp + d];
+      s += c * c;
+    }
+    scn[k] = s;
+  }
+  __syncthreads();
+
+  double inertia = 0.0, dist_sum = 0.0;
+  int changed = 0;
+  const int64_t ntiles = (N + tile - 1) / tile;
+  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int64_t row0 = t * tile;
+    const int rows = (int)min((int64_t)tile, N - row0);
+    // coalesced load of rows*D contiguous elements into padded shared rows
+    const T* src = X + row0 * D;
+    for (int i = tid; i < rows * D; i += tile) {
+      const int r = i / D, d = i - r * D;
+      reinterpret_cast<T*>(sx)[r * Dp + d] = src[i];
+    }
+    if (Dp != D)
+      for (int i = tid; i < rows * (Dp - D); i += tile) {
+        const int r = i / (Dp - D), d = D + (i - r * (Dp - D));
+        reinterpret_cast<T*>(sx)[r * Dp + d] = T(0);
+      }
+    __syncthreads();
+
+    if (tid < rows) {
+      const V* xr = sx + tid * s16;
+      int best = 0;
+      if (flags & DIC_KM_KEEP_LABELS) {
+        best = labels[row0 + tid];
+      } else {
+        T bestd = T(0);
+        for (int kb = 0; kb < K; kb += 4) {
+          const V* c0 = sc + min(kb + 0, K - 1) * s16;
+          const V* c1 = sc + min(kb + 1, K - 1) * s16;
+          const V* c2 = sc + min(kb + 2, K - 1) * s16;
+          const V* c3 = sc + min(kb + 3, K - 1) * s16;
+          T a0 = T(0), a1 = T(0), a2 = T(0), a3 = T(0);
+          for (int j = 0; j < s16; ++j) {
+            const V xv = xr[j];
+            a0 = dot16(xv, c0[j], a0);
+            a1 = dot16(xv, c1[j], a1);
+            a2 = dot16(xv, c2[j], a2);
+            a3 = dot16(xv, c3[j], a3);
+          }
+          const T acc[4] = {a0, a1, a2, a3};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int k = kb + i;
+            if (k < K) {
+              const T dk = scn[k] - T(2) * acc[i];      // ||c||^2 - 2 x.c  (||x||^2 omitted)
+              if (k == 0 || dk < bestd) {               // strict '<': lowest index wins ties
+                bestd = dk;
+                best = k;
+              }
+            }
+          }
+        }
+        if (flags & DIC_KM_COUNT_CHANGES) changed += (labels[row0 + tid] != best);
+        labels[row0 + tid] = best;
+      }
+      // direct squared distance to the chosen centre
+      const V* cb = sc + best * s16;
+      T d2 = T(0);
+      for (int j = 0; j < s16; ++j) d2 = sqd16(xr[j], cb[j], d2);
+      inertia += (double)d2;
+      dist_sum += sqrt((double)d2);
+      slab[tid] = best;
+      if (want_sums) atomicAdd(&scnt[best], 1);
+    }
+    __syncthreads();
+    if (want_sums) {
+      for (int d = tid; d < D; d += tile) {
+        for (int r = 0; r < rows; ++r) {
+          const int k = slab[r];
+          sacc[k * D + d] += reinterpret_cast<const T*>(sx)[r * Dp + d];
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  // per-block partials: [K*D] sums | [K] counts | inertia | changed | dist_sum | 0
+  double* out = ws + (int64_t)blockIdx.x * ((int64_t)K * D + K + 4);
+  if (want_sums) {
+    for (int i = tid; i < K * D; i += tile) out[i] = (double)sacc[i];
+    for (int i = tid; i < K; i += tile) out[(int64_t)K * D + i] = (double)scnt[i];
+  }
+  // block reduction of the three scalars (reuse the tile buffer)
+  double* red = reinterpret_cast<double*>(sx);
+  inertia = warp_sum(inertia);
+  dist_sum = warp_sum(dist_sum);
+  double ch = warp_sum((double)changed);
+  const int warp = tid >> 5, lane = tid & 31, nwarps = (tile + 31) >> 5;
+  if (lane == 0) {
+    red[warp * 3 + 0] = inertia;
+    red[warp * 3 + 1] = ch;
+    red[warp * 3 + 2] = dist_sum;
+  }
+  __syncthreads();
+  if (tid < 3) {
+    double s = 0.0;
+    for (int w = 0; w < nwarps; ++w) s += red[w * 3 + tid];
+    out[(int64_t)K * D + K + tid] = s;
+  }
+  if (tid == 3) out[(int64_t)K * D + K + 3] = 0.0;
+}
+
+__global__ void kmeans_finish_kernel(const double* __restrict__ ws, double* __restrict__ sums,
+                                     double* __restrict__ counts, double* __restrict__ stats, int nblocks,
+                                     int K, int D) {
+  const int64_t stride = (int64_t)K * D + K + 4;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nsum = sums ? K * D + K : 0;
+  if (i < nsum) {
+    double s = 0.0;
+    for (int b = 0; b < nblocks; ++b) s += ws[b * stride + i];
+    if (i < K * D) sums[i] = s; else counts[i - K * D] = s;
+  }
+  if (i < 4) {
+    double s = 0.0;
+    for (int b = 0; b < nblocks; ++b) s += ws[b * stride + (int64_t)K * D + K + i];
+    stats[i] = s;
+  }
+}
+
+// ---- k-means++ potentials -----------------------------------------------------------------
+constexpr int kMaxCands = 16;
+constexpr int kPotThreads = 256;
+constexpr int kPotBlocks = 148 * 4;
+
+template <typename T>
+__global__ void __launch_bounds__(kPotThreads)
+kmeans_min_d2_kernel(const T* __restrict__ X, const T* __restrict__ cands, const T* __restrict__ min_d2,
+                     T* __restrict__ min_d2_out, double* __restrict__ ws, int64_t N, int D, int L) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  T* sc = reinterpret_cast<T*>(smem);                  // [L][D]
+  for (int i = threadIdx.x; i < L * D; i += blockDim.x) sc[i] = cands[i];
+  __syncthreads();
+  // one warp per row: lanes stride over D (coalesced), shuffle-reduce the L distances
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  double pot[kMaxCands];
+#pragma unroll
+  for (int l = 0; l < kMaxCands; ++l) pot[l] = 0.0;
+  for (int64_t row = (int64_t)blockIdx.x * wpb + warp; row < N; row += (int64_t)gridDim.x * wpb) {
+    const T* xr = X + row * D;
+    T part[kMaxCands];
+#pragma unroll
+    for (int l = 0; l < kMaxCands; ++l) part[l] = T(0);
+    for (int d = lane; d < D; d += 32) {
+      const T xv = xr[d];
+#pragma unroll
+      for (int l = 0; l < kMaxCands; ++l) {
+        if (l < L) {
+          const T df = xv - sc[l * D + d];
+          part[l] += df * df;
+        }
+      }
+    }
+    const T prev = min_d2 ? min_d2[row] : T(0);
+#pragma unroll
+    for (int l = 0; l < kMaxCands; ++l) {
+      if (l < L) {
+        T v = part[l];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (min_d2 && prev < v) v = prev;
+        if (lane == 0) {
+          pot[l] += (double)v;
+          if (min_d2_out && l == 0) min_d2_out[row] = v;
+        }
+      }
+    }
+  }
+  __shared__ double red[kPotThreads / 32][kMaxCands];
+  if (lane == 0)
+    for (int l = 0; l < kMaxCands; ++l) red[warp][l] = pot[l];
+  __syncthreads();
+  if (threadIdx.x < L) {
+    double s = 0.0;
+    for (int w = 0; w < wpb; ++w) s += red[w][threadIdx.x];
+    ws[(int64_t)blockIdx.x * L + threadIdx.x] = s;
+  }
+}
+
+__global__ void sum_blocks_kernel(const double* __restrict__ ws, double* __restrict__ out, int nblocks, int cols) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  double s = 0.0;
+  for (int b = 0; b < nblocks; ++b) s += ws[(int64_t)b * cols + c];
+  out[c] = s;
+}
+
+// ---- pairwise Euclidean distance sum ----------------------------------------------------------
+// 64 x 64 tile of the n x n distance matrix per step, upper triangle only (off-diagonal tiles
+// count twice), 256 threads x (4 x 4) register tile, direct (x_i - x_j)^2 accumulation in the
+// data dtype, sqrt, float64 running sum per thread.
+constexpr int kPwTile = 64;
+constexpr int kPwThreads = 256;
+constexpr int kPwChunk = 32;        // feature columns staged per step
+constexpr int kPwBlocks = 148 * 4;
+
+template <typename T>
+__global__ void __launch_bounds__(kPwThreads)
+pairwise_sum_kernel(const T* __restrict__ X, double* __restrict__ ws, int64_t n, int D) {
+  __shared__ T sa[kPwChunk][kPwTile + 1];   // [d][row]: rows of the i-tile, transposed
+  __shared__ T sb[kPwChunk][kPwTile + 1];
+  const int tid = threadIdx.x;
+  const int ti = tid / 16, tj = tid % 16;          // 16 x 16 threads, each a 4 x 4 sub-tile
+  const int64_t nb = (n + kPwTile - 1) / kPwTile;
+  const int64_t ntiles = nb * (nb + 1) / 2;
+  double total = 0.0;
+  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    // unrank t -> (bi <= bj) in the upper triangle, row-major
+    int64_t bi = (int64_t)((2.0 * nb + 1.0 - sqrt((2.0 * nb + 1.0) * (2.0 * nb + 1.0) - 8.0 * (double)t)) * 0.5);
+    while (bi * nb - bi * (bi - 1) / 2 > t) --bi;
+    while ((bi + 1) * nb - (bi + 1) * bi / 2 <= t) ++bi;
+    const int64_t bj = bi + (t - (bi * nb - bi * (bi - 1) / 2));
+    const int64_t i0 = bi * kPwTile, j0 = bj * kPwTile;
+    T acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) acc[a][b] = T(0);
+    for (int d0 = 0; d0 < D; d0 += kPwChunk) {
+      __syncthreads();
+      for (int idx = tid; idx < kPwTile * kPwChunk; idx += kPwThreads) {
+        const int r = idx / kPwChunk, d = idx % kPwChunk;
+        const int64_t gi = i0 + r, gj = j0 + r;
+        sa[d][r] = (gi < n && d0 + d < D) ? X[gi * D + d0 + d] : T(0);
+        sb[d][r] = (gj < n && d0 + d < D) ? X[gj * D + d0 + d] : T(0);
+      }
+      __syncthreads();
+#pragma unroll 8
+      for (int d = 0; d < kPwChunk; ++d) {
+        T av[4], bv[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) av[a] = sa[d][ti * 4 + a];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) bv[b] = sb[d][tj * 4 + b];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            const T df = av[a] - bv[b];
+            acc[a][b] += df * df;
+          }
+      }
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int64_t gi = i0 + ti * 4 + a, gj = j0 + tj * 4 + b;
+        if (gi < n && gj < n && gi != gj) s += sqrt((double)acc[a][b]);
+      }
+    total += (bi == bj) ? s : 2.0 * s;
+  }
+  __shared__ double red[kPwThreads / 32];
+  total = warp_sum(total);
+  if ((tid & 31) == 0) red[tid >> 5] = total;
+  __syncthreads();
+  if (tid == 0) {
+    double s = 0.0;
+    for (int w = 0; w < kPwThreads / 32; ++w) s += red[w];
+    ws[blockIdx.x] = s;
+  }
+}
+
+int km_blocks(int K, int D) {
+  int64_t per = (int64_t)K * D + K + 4;
+  int64_t b = (8LL << 20) / per;
+  if (b > 148 * 8) b = 148 * 8;
+  if (b < 148) b = 148;
+  return (int)b;
+}
+
+template <typename T>
+int launch_assign(const void* X, const void* centers, int32_t* labels, double* sums, double* counts,
+                  double* stats, void* workspace, int64_t N, int D, int K, int flags, cudaStream_t st) {
+  const int s16 = row_stride16<T>(D);
+  int tile = 128;
+  KmLayout L = km_layout<T>(K, D, tile);
+  while (tile > 32 && L.total > 100 * 1024) {
+    tile >>= 1;
+    L = km_layout<T>(K, D, tile);
+  }
+  DIC_REQUIRE(L.total <= (size_t)kMaxSmemBytes, DIC_ERR_UNSUPPORTED,
+              "K=%d D=%d needs %zu bytes of shared memory (limit %d)", K, D, L.total, kMaxSmemBytes);
+  auto kern = kmeans_assign_kernel<T>;
+  if (L.total > 48 * 1024)
+    DIC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+  const int64_t ntiles = (N + tile - 1) / tile;
+  int blocks = km_blocks(K, D);
+  if (ntiles < blocks) blocks = (int)ntiles;
+  if (blocks < 1) blocks = 1;
+  double* ws = static_cast<double*>(workspace);
+  kern<<<blocks, tile, L.total, st>>>(static_cast<const T*>(X), static_cast<const T*>(centers), labels, ws,
+                                      N, D, K, s16, flags, L, sums != nullptr);
+  DIC_LAUNCH_CHECK("kmeans_assign_kernel");
+  const int n = K * D + K + 4;
+  kmeans_finish_kernel<<<(n + 255) / 256, 256, 0, st>>>(ws, sums, counts, stats, blocks, K, D);
+  DIC_LAUNCH_CHECK("kmeans_finish_kernel");
+  return DIC_OK;
+}
+
+template <typename T>
+int launch_min_d2(const void* X, const void* cands, const void* min_d2, void* min_d2_out, double* pots,
+                  void* workspace, int64_t N, int D, int L, cudaStream_t st) {
+  const size_t smem = (size_t)L * D * sizeof(T);
+  auto kern = kmeans_min_d2_kernel<T>;
+  if (smem > 48 * 1024)
+    DIC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int64_t want = (N + kPotThreads / 32 - 1) / (kPotThreads / 32);
+  int blocks = (int)(want < kPotBlocks ? want : kPotBlocks);
+  if (blocks < 1) blocks = 1;
+  double* ws = static_cast<double*>(workspace);
+  kern<<<blocks, kPotThreads, smem, st>>>(static_cast<const T*>(X), static_cast<const T*>(cands),
+                                          static_cast<const T*>(min_d2), static_cast<T*>(min_d2_out), ws, N,
+                                          D, L);
+  DIC_LAUNCH_CHECK("kmeans_min_d2_kernel");
+  sum_blocks_kernel<<<1, 32, 0, st>>>(ws, pots, blocks, L);
+  DIC_LAUNCH_CHECK("sum_blocks_kernel");
+  return DIC_OK;
+}
+
+template <typename T>
+int launch_pairwise(const void* X, double* out, void* workspace, int64_t n, int D, cudaStream_t st) {
+  const int64_t nb = (n + kPwTile - 1) / kPwTile;
+  const int64_t ntiles = nb * (nb + 1) / 2;
+  int blocks = (int)(ntiles < kPwBlocks ? ntiles : kPwBlocks);
+  if (blocks < 1) blocks = 1;
+  double* ws = static_cast<double*>(workspace);
+  pairwise_sum_kernel<T><<<blocks, kPwThreads, 0, st>>>(static_cast<const T*>(X), ws, n, D);
+  DIC_LAUNCH_CHECK("pairwise_sum_kernel");
+  sum_blocks_kernel<<<1, 32, 0, st>>>(ws, out, blocks, 1);
+  DIC_LAUNCH_CHECK("sum_blocks_kernel");
+  return DIC_OK;
+}
+
+}  // namespace
+}  // namespace dic
+
+using namespace dic;
+
+extern "C" size_t dic_kmeans_workspace_bytes(int K, int D) {
+  if (K <= 0 || D <= 0) return 0;
+  size_t a = (size_t)km_blocks(K, D) * ((size_t)K * D + K + 4) * sizeof(double);
+  size_t b = (size_t)kPotBlocks * kMaxCands * sizeof(double);
+  return (a > b ? a : b) + 256;
+}
+
+extern "C" int dic_kmeans_assign(const void* X, const void* centers, int32_t* labels, double* sums,
+                                 double* counts, double* stats, void* workspace, int64_t N, int D, int K,
+                                 int dtype, int flags, dic_stream_t stream) {
+  DIC_REQUIRE(X && centers && labels && stats && workspace, DIC_ERR_INVALID_ARGUMENT, "null pointer argument");
+  DIC_REQUIRE((sums == nullptr) == (counts == nullptr), DIC_ERR_INVALID_ARGUMENT,
+              "sums and counts must be given together");
+  DIC_REQUIRE(N >= 0 && D > 0 && K > 0, DIC_ERR_INVALID_ARGUMENT, "bad sizes N=%lld D=%d K=%d", (long long)N, D, K);
+  DIC_REQUIRE(K <= 64 && D <= 512, DIC_ERR_UNSUPPORTED, "k-means supports K <= 64, D <= 512 (got K=%d D=%d)", K, D);
+  DIC_REQUIRE(dtype == 0 || dtype == 1, DIC_ERR_INVALID_ARGUMENT, "dtype must be 0 (float32) or 1 (float64)");
+  cudaStream_t st = as_stream(stream);
+  if (N == 0) {
+    if (sums) {
+      DIC_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * K * D, st));
+      DIC_CUDA(cudaMemsetAsync(counts, 0, sizeof(double) * K, st));
+    }
+    DIC_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 4, st));
+    return DIC_OK;
+  }
+  return dtype == 0 ? launch_assign<float>(X, centers, labels, sums, counts, stats, workspace, N, D, K, flags, st)
+                    : launch_assign<double>(X, centers, labels, sums, counts, stats, workspace, N, D, K, flags, st);
+}
+
+extern "C" int dic_kmeans_min_d2(const void* X, const void* cands, const void* min_d2, void* min_d2_out,
+                                 double* pots, void* workspace, int64_t N, int D, int L, int dtype,
+                                 dic_stream_t stream) {
+  DIC_REQUIRE(X && cands && pots && workspace, DIC_ERR_INVALID_ARGUMENT, "null pointer argument");
+  DIC_REQUIRE(N > 0 && D > 0 && L > 0, DIC_ERR_INVALID_ARGUMENT, "bad sizes N=%lld D=%d L=%d", (long long)N, D, L);
+  DIC_REQUIRE(L <= kMaxCands, DIC_ERR_UNSUPPORTED, "at most %d candidates per call (got %d)", kMaxCands, L);
+  DIC_REQUIRE(!min_d2_out || L == 1, DIC_ERR_INVALID_ARGUMENT, "min_d2_out requires exactly one candidate");
+  DIC_REQUIRE(dtype == 0 || dtype == 1, DIC_ERR_INVALID_ARGUMENT, "dtype must be 0 (float32) or 1 (float64)");
+  cudaStream_t st = as_stream(stream);
+  return dtype == 0 ? launch_min_d2<float>(X, cands, min_d2, min_d2_out, pots, workspace, N, D, L, st)
+                    : launch_min_d2<double>(X, cands, min_d2, min_d2_out, pots, workspace, N, D, L, st);
+}
+
+extern "C" size_t dic_pairwise_workspace_bytes(int64_t n) {
+  (void)n;
+  return (size_t)kPwBlocks * sizeof(double) + 256;
+}
+
+extern "C" int dic_pairwise_dist_sum(const void* Xc, double* out, void* workspace, int64_t n, int D, int dtype,
+                                     dic_stream_t stream) {
+  DIC_REQUIRE(Xc && out && workspace, DIC_ERR_INVALID_ARGUMENT, "null pointer argument");
+  DIC_REQUIRE(n >= 0 && D > 0, DIC_ERR_INVALID_ARGUMENT, "bad sizes n=%lld D=%d", (long long)n, D);
+  DIC_REQUIRE(dtype == 0 || dtype == 1, DIC_ERR_INVALID_ARGUMENT, "dtype must be 0 (float32) or 1 (float64)");
+  cudaStream_t st = as_stream(stream);
+  if (n == 0) {
+    DIC_CUDA(cudaMemsetAsync(out, 0, sizeof(double), st));
+    return DIC_OK;
+  }
+  return dtype == 0 ? launch_pairwise<float>(Xc, out, workspace, n, D, st)
+                    : launch_pairwise<double>(Xc, out, workspace, n, D, st);
+}

@@ -1,0 +1,145 @@
+"""K-selection sweep (gap statistic / elbow) on device - mirror of the ``KM`` class of
+p2_clustering_optK.py:226-410 without its plotting.
+
+``KM.compute_gap_internal_metric(clustering, data, k_max, n_references, version)`` keeps the
+reference's signature and returns the same pandas DataFrame (index k = 2..k_max, columns
+``['k','gap','ref','act','ref_s', *internal metric names]``).  The "inertia" of the reference
+(mean intra-cluster mean pairwise Euclidean distance, :334-342) is evaluated by the tiled
+``dic_pairwise_dist_sum`` kernel without materialising the n_c x n_c matrix, so the sweep
+runs at N = 1M where the reference needs terabytes.
+
+Reference draws use ``np.random.random_sample`` on the host exactly like :370 so that a
+seeded run sees the same draws; pass ``draw=`` to inject your own.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import internal_eval
+from .kmeans import KMeansB200, _DT
+
+
+def _as_device(X, device=None):
+    if isinstance(X, torch.Tensor):
+        return X.contiguous()
+    X = np.asarray(X)
+    if X.dtype not in (np.float32, np.float64):
+        X = X.astype(np.float64)
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+    return torch.from_numpy(np.ascontiguousarray(X)).to(dev)
+
+
+def pairwise_dist_sum(Xc):
+    """sum over the full n x n Euclidean distance matrix of the rows of Xc (device tensor)."""
+    Xc = Xc.contiguous()
+    n, D = Xc.shape
+    out = torch.empty(1, dtype=torch.float64, device=Xc.device)
+    L = _lib.lib()
+    ws = torch.empty(int(L.dic_pairwise_workspace_bytes(n)), dtype=torch.uint8, device=Xc.device)
+    with torch.cuda.device(Xc.device):
+        _lib.check(L.dic_pairwise_dist_sum(_lib.ptr(Xc), _lib.ptr(out), _lib.ptr(ws), n, D, _DT[Xc.dtype],
+                                           _lib.current_stream(Xc.device)), "dic_pairwise_dist_sum")
+    return out
+
+
+class KM(object):
+    """p2_clustering_optK.py:226-410 (constructor signature kept; plots are out of scope)."""
+
+    def __init__(self, k_max, out_path=None, internal_metrics=(), n_init=10, gap_b=10):
+        self.k_max = k_max
+        self.out_path = os.path.join(out_path, "plot") if out_path else None
+        if self.out_path:
+            os.makedirs(self.out_path, exist_ok=True)
+        self.internal_metrics_names = list(internal_metrics)
+        self.internal_metrics = self.get_internal_metrics()
+        self.n_init = n_init
+        self.gap_b = gap_b
+
+    def get_internal_metrics(self):
+        table = {"Dunn_Index": internal_eval.DunnIndex, "Sihouette": internal_eval.Sihouette,
+                 "Davies-Bouldin_Index": internal_eval.DBIndex, "Calinski-Harabasz": internal_eval.CHIndex}
+        return [table[name]() for name in self.internal_metrics_names]
+
+    # ---- the two "inertia" definitions ---------------------------------------------------------
+    def _cluster_sums(self, a, X):
+        Xd = _as_device(X)
+        ad = torch.as_tensor(np.asarray(a) if not isinstance(a, torch.Tensor) else a).to(Xd.device)
+        out = []
+        for c in torch.unique(ad).tolist():                      # np.unique(a): sorted labels present
+            Xc = Xd[ad == c]
+            out.append((pairwise_dist_sum(Xc), Xc.shape[0]))
+        return out
+
+    def compute_inertia_v1(self, a, X):
+        """mean_c [ mean of the full n_c x n_c distance matrix ]   (:334-342)."""
+        W = [float(s) / (n * n) for s, n in self._cluster_sums(a, X)]
+        return float(np.mean(W))
+
+    def computer_intertia_v2(self, a, X):
+        """sum_c [ sum of the full distance matrix / (2 n_c) ]      (:344-351, name as upstream)."""
+        return float(sum(float(s) / (2 * n) for s, n in self._cluster_sums(a, X)))
+
+    # ---- gap statistic -----------------------------------------------------------------------
+    def compute_gap_internal_metric(self, clustering, data, k_max=5, n_references=5, version=2, draw=None):
+        import pandas as pd
+        data = np.asarray(data) if not isinstance(data, torch.Tensor) else data.cpu().numpy()
+        if len(data.shape) == 1:
+            data = data.reshape(-1, 1)
+        draw = np.random.random_sample if draw is None else draw
+        inertia = self.compute_inertia_v1 if version == 1 else self.computer_intertia_v2
+        data_min = data.min()
+        data_rng = data.max() - data_min                                             # :360
+        k_rng = range(2, k_max + 1)
+        vals = pd.DataFrame(index=k_rng, columns=["k", "gap", "ref", "act", "ref_s"] + self.internal_metrics_names)
+        data_dev = _as_device(data)
+        for k in k_rng:
+            local_inertia = []
+            clustering.n_clusters = k                                                # :367
+            for _ in range(n_references):
+                reference = draw(data.shape) * data_rng + data_min                   # :370 (float64)
+                ref_dev = _as_device(reference)
+                assignments = clustering.fit_predict(ref_dev if _accepts_tensor(clustering) else reference)
+                local_inertia.append(inertia(assignments, ref_dev))
+            ref = np.mean(np.log(local_inertia))                                     # :374
+            ref_s = np.sqrt(1 + 1 / n_references) * np.std(np.log(local_inertia))    # :375
+            assignments = clustering.fit_predict(data_dev if _accepts_tensor(clustering) else data)
+            act = np.log(inertia(assignments, data_dev))                             # :377-379
+            gap = ref - act                                                          # :393
+            a_host = assignments.cpu().numpy() if isinstance(assignments, torch.Tensor) else np.asarray(assignments)
+            metric_values = [m(data_dev, a_host) for m in self.internal_metrics]     # :401-405
+            vals.loc[k] = [k, gap, ref, act, ref_s] + metric_values
+        return vals
+
+    # ---- elbow ---------------------------------------------------------------------------------
+    def elbow(self, train_feat, valid_feat, device=None):
+        """p2_clustering_optK.py:255-265: distortion = sum_i min_j ||x_i - c_j|| / N per k."""
+        tr, va = [], []
+        Xt, Xv = _as_device(train_feat, device), _as_device(valid_feat, device)
+        for k in range(2, self.k_max + 1):
+            km = KMeansB200(n_clusters=k, init="k-means++").fit(Xt)                  # :260
+            tr.append(km.score_distortion(Xt))
+            va.append(km.score_distortion(Xv))
+        return tr, va
+
+    def train(self, train_data, valid_data, select_opt_k, **kwargs):
+        """Numbers of p2_clustering_optK.py:250-332 (CSV written when out_path is set; no plots)."""
+        train_feat, valid_feat = train_data["hidden"], valid_data["hidden"]
+        results = {}
+        for method in select_opt_k:
+            if method == "elbow":
+                results["elbow"] = self.elbow(train_feat, valid_feat)
+            elif method == "gap_sts":
+                df = self.compute_gap_internal_metric(KMeansB200(n_init=self.n_init), train_feat, self.k_max,
+                                                      n_references=self.gap_b, version=1).astype(float)
+                if self.out_path:
+                    df.to_csv(os.path.join(self.out_path, "gap_sts_v1.csv"), index=False)
+                results["gap_sts"] = df
+        return results
+
+
+def _accepts_tensor(clustering):
+    return isinstance(clustering, KMeansB200) or getattr(clustering, "accepts_device_tensors", False)

@@ -1,0 +1,257 @@
+"""sklearn-``KMeans``-compatible estimator backed by the sm_100a Lloyd kernels.
+
+Stands behind the reference's calls ``KMeans(n_clusters=K, n_init=20).fit_predict(hidden)``
+(clustering_trainer.py:75-82), ``KMeans(n_init=...)`` handed to the gap routine
+(p2_clustering_optK.py:284, with ``clustering.n_clusters = k`` set at :367),
+``KMeans(n_clusters=k, init='k-means++').fit(train_feat)`` (:260) and
+p4_clustering_final.py:159-174.  Same duck type: constructor kwargs ``n_clusters, init,
+n_init, max_iter, tol, random_state``; settable ``n_clusters``; ``fit / fit_predict /
+predict``; ``cluster_centers_`` (writable ndarray), ``labels_``, ``inertia_``, ``n_iter_``.
+Inputs and outputs are host numpy arrays (CUDA tensors are accepted and stay on device).
+
+The algorithm follows scikit-learn 1.9.0 step by step: dtype preserved
+(float32 data, float64 reference draws), mean-centring, tol * mean(var), k-means++ with
+2+int(ln K) greedy trials consuming the numpy RandomState exactly like sklearn (so a shared
+global stream stays in step), strict-'<' argmin, empty-cluster relocation, label-equality or
+centre-shift stopping, a final E-step when not strictly converged, best of n_init by inertia.
+"""
+from __future__ import annotations
+
+import numbers
+
+import numpy as np
+import torch
+
+from . import _lib
+
+_DT = {torch.float32: 0, torch.float64: 1}
+DIC_KM_COUNT_CHANGES = 1
+DIC_KM_KEEP_LABELS = 2
+
+
+def _check_random_state(seed):
+    """sklearn.utils.check_random_state: None -> numpy's global RandomState singleton."""
+    if seed is None or seed is np.random:
+        return np.random.mtrand._rand
+    if isinstance(seed, numbers.Integral):
+        return np.random.RandomState(seed)
+    if isinstance(seed, np.random.RandomState):
+        return seed
+    raise ValueError(f"{seed!r} cannot be used to seed a numpy.random.RandomState instance")
+
+
+def _same_clustering(a, b, K):
+    """Equal up to a permutation of the labels (sklearn _k_means_common.pyx:_is_same_clustering)."""
+    a = np.asarray(a, np.int64)
+    b = np.asarray(b, np.int64)
+    pairs = np.unique(a * K + b)
+    return len(np.unique(pairs // K)) == len(pairs)
+
+
+class _Device:
+    """Device-side state and kernel calls for one (X, K) problem."""
+
+    def __init__(self, X, K):
+        self.X = X
+        self.N, self.D = X.shape
+        self.K = K
+        self.dt = _DT[X.dtype]
+        self.dev = X.device
+        L = _lib.lib()
+        self.ws = torch.empty(max(int(L.dic_kmeans_workspace_bytes(max(K, 16), self.D)), 16), dtype=torch.uint8,
+                              device=self.dev)
+        self.labels = torch.full((self.N,), -1, dtype=torch.int32, device=self.dev)
+        self.sums = torch.empty((K, self.D), dtype=torch.float64, device=self.dev)
+        self.counts = torch.empty(K, dtype=torch.float64, device=self.dev)
+        self.stats = torch.empty(4, dtype=torch.float64, device=self.dev)
+
+    def assign(self, centers, flags=0, want_sums=True, labels=None):
+        labels = self.labels if labels is None else labels
+        with torch.cuda.device(self.dev):
+            _lib.check(_lib.lib().dic_kmeans_assign(
+                _lib.ptr(self.X), _lib.ptr(centers), _lib.ptr(labels),
+                _lib.ptr(self.sums) if want_sums else None, _lib.ptr(self.counts) if want_sums else None,
+                _lib.ptr(self.stats), _lib.ptr(self.ws), self.N, self.D, centers.shape[0], self.dt, flags,
+                _lib.current_stream(self.dev)), "dic_kmeans_assign")
+
+    def min_d2(self, cands, prev, out):
+        L = cands.shape[0]
+        pots = torch.empty(L, dtype=torch.float64, device=self.dev)
+        with torch.cuda.device(self.dev):
+            _lib.check(_lib.lib().dic_kmeans_min_d2(
+                _lib.ptr(self.X), _lib.ptr(cands), _lib.ptr(prev), _lib.ptr(out), _lib.ptr(pots),
+                _lib.ptr(self.ws), self.N, self.D, L, self.dt, _lib.current_stream(self.dev)),
+                "dic_kmeans_min_d2")
+        return pots
+
+
+class KMeansB200:
+    """K-means on a B200; drop-in for ``sklearn.cluster.KMeans`` as the reference uses it."""
+
+    def __init__(self, n_clusters=8, *, init="k-means++", n_init="auto", max_iter=300, tol=1e-4, verbose=0,
+                 random_state=None, copy_x=True, algorithm="lloyd", device=None):
+        self.n_clusters = n_clusters
+        self.init = init
+        self.n_init = n_init
+        self.max_iter = max_iter
+        self.tol = tol
+        self.verbose = verbose
+        self.random_state = random_state
+        self.copy_x = copy_x
+        self.algorithm = algorithm
+        self.device = device
+
+    # ---- helpers ---------------------------------------------------------------------------
+    def _device(self):
+        if not torch.cuda.is_available():
+            raise RuntimeError("KMeansB200 needs a CUDA device: there is no CPU fallback")
+        return torch.device(self.device) if self.device is not None else torch.device("cuda", torch.cuda.current_device())
+
+    def _to_device(self, X):
+        dev = self._device()
+        if isinstance(X, torch.Tensor):
+            if X.dtype not in _DT:
+                X = X.to(torch.float64)
+            X = X.to(dev)
+        else:
+            X = np.asarray(X)
+            if X.dtype not in (np.float32, np.float64):
+                X = X.astype(np.float64)              # sklearn validate_data(dtype=[float64, float32])
+            X = torch.from_numpy(np.ascontiguousarray(X)).to(dev)
+        if X.dim() != 2:
+            raise ValueError(f"Expected 2D array, got {X.dim()}D array instead")
+        return X.contiguous()
+
+    def _n_init(self):
+        if self.n_init == "auto":
+            return 1 if (isinstance(self.init, str) and self.init == "k-means++") or not isinstance(self.init, str) else 10
+        return int(self.n_init)
+
+    def _kmeans_plusplus(self, st, rng):
+        """sklearn/cluster/_kmeans.py:224-281 on device; the RandomState is consumed in the same
+        order and quantity as sklearn does (choice, then uniform(size=trials) per centre)."""
+        K, N = self.n_clusters, st.N
+        trials = 2 + int(np.log(K))
+        centers = torch.empty((K, st.D), dtype=st.X.dtype, device=st.dev)
+        first = int(rng.choice(N, p=np.full(N, 1.0 / N))) if N < (1 << 22) else int(rng.randint(N))
+        centers[0] = st.X[first]
+        closest = torch.empty(N, dtype=st.X.dtype, device=st.dev)
+        pot = st.min_d2(centers[0:1], None, closest)[0]
+        for c in range(1, K):
+            rv = torch.from_numpy(rng.uniform(size=trials)).to(st.dev) * pot
+            cum = torch.cumsum(closest.to(torch.float64), 0)
+            cand = torch.searchsorted(cum, rv).clamp_(max=N - 1)
+            pots = st.min_d2(st.X[cand].contiguous(), closest, None)
+            best = torch.argmin(pots)
+            centers[c] = st.X[cand[best]]
+            pot = st.min_d2(centers[c:c + 1], closest, closest)[0]
+        return centers
+
+    def _relocate_empty(self, st, centers_old):
+        """sklearn _k_means_common.pyx:167-212 (rare path; torch ops on device)."""
+        empty = torch.nonzero(st.counts == 0).flatten()
+        n_empty = int(empty.numel())
+        if n_empty == 0:
+            return
+        lab = st.labels.long()
+        dist = ((st.X - centers_old[lab]) ** 2).sum(1)
+        if float(dist.max()) == 0.0:
+            return
+        far = torch.topk(dist, n_empty).indices           # farthest first, like argpartition[:-n-1:-1]
+        for new_id, idx in zip(empty.tolist(), far.tolist()):
+            old_id = int(lab[idx])
+            row = st.X[idx].to(torch.float64)
+            st.sums[old_id] -= row
+            st.sums[new_id] = row
+            st.counts[new_id] = 1
+            st.counts[old_id] -= 1
+
+    def _lloyd(self, st, centers, tol_eff):
+        """One run of sklearn/cluster/_kmeans.py:630-757."""
+        st.labels.fill_(-1)
+        strict = False
+        n_iter = 0
+        for i in range(self.max_iter):
+            n_iter = i + 1
+            st.assign(centers, DIC_KM_COUNT_CHANGES)
+            changed, n_empty = st.stats[1], (st.counts == 0).sum()
+            if int(n_empty) > 0:
+                self._relocate_empty(st, centers)
+            cnt = st.counts.clamp(min=1.0)[:, None]
+            new = torch.where(st.counts[:, None] > 0, st.sums / cnt, centers.to(torch.float64)).to(centers.dtype)
+            shift2 = float(((new - centers).to(torch.float64) ** 2).sum())
+            centers = new
+            if int(changed) == 0:
+                strict = True
+                break
+            if shift2 <= tol_eff:
+                break
+        if strict:
+            st.assign(centers, DIC_KM_KEEP_LABELS, want_sums=False)
+        else:
+            st.assign(centers, 0, want_sums=False)
+        inertia = float(st.stats[0])
+        return st.labels.clone(), inertia, centers, n_iter
+
+    # ---- sklearn API -------------------------------------------------------------------------
+    def fit(self, X, y=None, sample_weight=None):
+        if sample_weight is not None:
+            raise NotImplementedError("sample_weight is not supported (the reference never passes it)")
+        as_tensor = isinstance(X, torch.Tensor)
+        X = self._to_device(X)
+        K = int(self.n_clusters)
+        if X.shape[0] < K:
+            raise ValueError(f"n_samples={X.shape[0]} should be >= n_clusters={K}.")
+        rng = _check_random_state(self.random_state)
+        init = self.init
+        init_arr = None
+        if not isinstance(init, str):
+            init_arr = torch.as_tensor(np.asarray(init), dtype=X.dtype).to(X.device)
+            if tuple(init_arr.shape) != (K, X.shape[1]):
+                raise ValueError(f"The shape of the initial centers {tuple(init_arr.shape)} does not match "
+                                 f"the number of clusters {K} / features {X.shape[1]}.")
+        elif init != "k-means++":
+            raise NotImplementedError("init must be 'k-means++' or an array of centres")
+        mean = X.mean(dim=0)
+        Xc = X - mean                                                    # _kmeans.py:1487-1493
+        tol_eff = float(torch.var(Xc, dim=0, unbiased=False).mean()) * self.tol   # _kmeans.py:285-293
+        st = _Device(Xc, K)
+        best = None
+        for _ in range(self._n_init()):
+            c0 = (init_arr - mean) if init_arr is not None else self._kmeans_plusplus(st, rng)
+            labels, inertia, centers, n_iter = self._lloyd(st, c0.contiguous(), tol_eff)
+            if best is None or (inertia < best[1] and not _same_clustering(labels.cpu().numpy(),
+                                                                           best[0].cpu().numpy(), K)):
+                best = (labels, inertia, centers, n_iter)
+        labels, inertia, centers, n_iter = best
+        centers = centers + mean                                         # _kmeans.py:1543-1546
+        self._centers_dev = centers
+        self.cluster_centers_ = centers if as_tensor else centers.cpu().numpy()
+        self.labels_ = labels if as_tensor else labels.cpu().numpy()
+        self.inertia_ = inertia
+        self.n_iter_ = n_iter
+        self.n_features_in_ = X.shape[1]
+        return self
+
+    def fit_predict(self, X, y=None, sample_weight=None):
+        return self.fit(X, sample_weight=sample_weight).labels_
+
+    def predict(self, X):
+        if not hasattr(self, "cluster_centers_"):
+            raise RuntimeError("This KMeansB200 instance is not fitted yet")
+        as_tensor = isinstance(X, torch.Tensor)
+        X = self._to_device(X)
+        centers = torch.as_tensor(np.asarray(self.cluster_centers_) if not isinstance(self.cluster_centers_, torch.Tensor)
+                                  else self.cluster_centers_).to(device=X.device, dtype=X.dtype).contiguous()
+        st = _Device(X, centers.shape[0])
+        st.assign(centers, 0, want_sums=False)
+        return st.labels if as_tensor else st.labels.cpu().numpy()
+
+    def score_distortion(self, X):
+        """sum_i min_j ||x_i - c_j|| / N - the elbow distortion of p2_clustering_optK.py:261-264."""
+        X = self._to_device(X)
+        centers = torch.as_tensor(np.asarray(self.cluster_centers_) if not isinstance(self.cluster_centers_, torch.Tensor)
+                                  else self.cluster_centers_).to(device=X.device, dtype=X.dtype).contiguous()
+        st = _Device(X, centers.shape[0])
+        st.assign(centers, 0, want_sums=False)
+        return float(st.stats[2]) / X.shape[0]

@@ -1,0 +1,197 @@
+/*
+ * dic_b200.h - C ABI of libdic_b200.so: the B200 (sm_100a) hot path of
+ * Deep_Interpolation_Clustering.
+ *
+ * The reference has no FFI: its hot path is Python nn.Modules and sklearn calls.
+ * Each entry point below states the reference interface it stands behind
+ * (file:line in the upstream repository).  A caller binds these with ctypes (see
+ * INTEGRATION.md); the package's own nn.Module mirrors do exactly that.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - all matrices are dense, row-major, float32 unless stated;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*;
+ *     NULL = legacy default stream) and keeps no global mutable state;
+ *   - return value 0 = success, < 0 = error (dic_status); never throws; the
+ *     message of the calling thread's last error is dic_last_error();
+ *   - inputs are never modified; outputs are fully overwritten.
+ *
+ * Planar layouts used across the boundary (the nn.Module mirrors expose the
+ * reference's permuted views of these buffers):
+ *   x      (B, 4C, T)  planes [value | padding mask | time in hours | hold-out]
+ *                       interpolation_layer.py:26-30; the hold-out plane is never read
+ *   u      (B, 3C, R)  SCI output rows [y (C) | w (C) | y' (C)]; the reference returns
+ *                       u.permute(0,2,1), interpolation_layer.py:84-85
+ *   cci    (B, 3C, R)  rows [z | exp(w) | y' - z]; interpolation_layer.py:124-126
+ *   v      (B, C, R)   compress_fc output, rbf.py:101-103
+ *   rec    (B, C, T)   RBF output, rbf.py:107
+ */
+#ifndef DIC_B200_H
+#define DIC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DIC_B200_VERSION 100 /* major*10000 + minor*100 + patch */
+
+typedef void* dic_stream_t;
+
+enum dic_status {
+  DIC_OK = 0,
+  DIC_ERR_INVALID_ARGUMENT = -1, /* NULL pointer, non-positive size, misaligned buffer  */
+  DIC_ERR_UNSUPPORTED = -2,      /* shape outside the kernels' limits (see each call)   */
+  DIC_ERR_CUDA = -3,             /* a CUDA runtime call / launch failed                 */
+  DIC_ERR_NO_DEVICE = -4         /* no sm_100 device visible                            */
+};
+
+/* ---- library ------------------------------------------------------------------- */
+const char* dic_last_error(void);
+int dic_version(void);
+/* Fills SM count and compute capability of the current device. */
+int dic_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- interpolation network -------------------------------------------------------
+ * SingleChannelInterp.forward, interpolation_layer.py:31-86.
+ *   kernel (C)  raw parameter; alpha = log(1+exp(kernel)) is applied inside (:51)
+ *   ref_t  (R)  reference grid, torch.linspace(0, H, R) (:41)
+ *   u      (B,3C,R) out
+ *   stats  (B,2C,R) out, may be NULL: shifted partition sums [sum e | sum e^10] that the
+ *          backward pass re-uses (saved-for-backward state, 8CR bytes per encounter)
+ * Limits: 12*C*round_up(T,4) + 64 bytes of shared memory <= 227 KB.
+ */
+int dic_sci_fwd(const float* x, const float* kernel, const float* ref_t, float* u, float* stats,
+                int64_t B, int C, int T, int R, dic_stream_t stream);
+
+/* Bytes of scratch dic_sci_bwd / dic_rbf_bwd need (per-encounter partials + reduction). */
+size_t dic_interp_bwd_workspace_bytes(int64_t B, int C);
+
+/* Gradient of dic_sci_fwd wrt `kernel` (what autograd produces for
+ * interpolation_layer.py:51-83).  grad_u (B,3C,R) is the upstream gradient in planar
+ * layout.  No input gradient is produced.
+ *   d_kernel (C) out (overwritten, deterministic two-stage reduction)
+ */
+int dic_sci_bwd(const float* x, const float* kernel, const float* ref_t, const float* u,
+                const float* stats, const float* grad_u, float* d_kernel, void* workspace,
+                int64_t B, int C, int T, int R, dic_stream_t stream);
+
+/* CrossChannelInterp.forward, interpolation_layer.py:99-127.
+ *   u (B,3C,R) in, kernel (C,C) in, out (B,3C,R).  Limit: C <= 16.
+ */
+int dic_cci_fwd(const float* u, const float* kernel, float* out, int64_t B, int C, int R,
+                dic_stream_t stream);
+
+size_t dic_cci_bwd_workspace_bytes(int64_t B, int C);
+
+/* Gradients of dic_cci_fwd: grad_u (B,3C,R) and d_kernel (C,C). */
+int dic_cci_bwd(const float* u, const float* kernel, const float* grad_out, float* grad_u,
+                float* d_kernel, void* workspace, int64_t B, int C, int R, dic_stream_t stream);
+
+/* RBF.forward after compress_fc, rbf.py:69-80,95-97,104-107 with the gaussian basis
+ * rbf.py:129-131.
+ *   v (B,C,R) in, x (B,4C,T) in (mask and time planes are read), kernel (C), ref_t (R)
+ *   rec (B,C,T) out
+ *   inv_norm (B,C,T) out, may be NULL: 1/(sum_r phi + 1e-10), saved for the backward pass
+ */
+int dic_rbf_fwd(const float* v, const float* x, const float* kernel, const float* ref_t,
+                float* rec, float* inv_norm, int64_t B, int C, int T, int R,
+                dic_stream_t stream);
+
+/* Gradients of dic_rbf_fwd wrt v (flows into compress_fc) and kernel.
+ *   grad_rec (B,C,T) upstream; grad_v (B,C,R) out; d_kernel (C) out
+ */
+int dic_rbf_bwd(const float* v, const float* x, const float* kernel, const float* ref_t,
+                const float* rec, const float* inv_norm, const float* grad_rec, float* grad_v,
+                float* d_kernel, void* workspace, int64_t B, int C, int T, int R,
+                dic_stream_t stream);
+
+/* ---- DEC soft assignment ----------------------------------------------------------
+ * ClusterAssignment.forward, dec.py:49-63.  z (B,D), mu (K,D) -> q (B,K).
+ *   labels (B) int32 out, may be NULL: argmax_j q (clustering_trainer.py:473-484)
+ *   colsum (K) float64 out, may be NULL: f_j = sum_i q_ij (dec.py:73), so that
+ *          target_distribution needs no second pass over q
+ * Limits: K <= 32, D % 4 == 0, D <= 1024.  workspace: dic_dec_workspace_bytes(K, D).
+ */
+size_t dic_dec_workspace_bytes(int K, int D);
+int dic_dec_q_fwd(const float* z, const float* mu, float* q, int32_t* labels, double* colsum,
+                  void* workspace, int64_t B, int D, int K, float alpha, dic_stream_t stream);
+
+/* target_distribution, dec.py:66-76, with the column sum f (K, float64) supplied by the
+ * caller (local, or all-reduced across ranks for a sharded batch). */
+int dic_dec_p(const float* q, const double* colsum, float* p, int64_t B, int K,
+              dic_stream_t stream);
+
+/* Backward of dic_dec_q_fwd for an arbitrary upstream grad_q (B,K):
+ *   grad_z (B,D) out, grad_mu (K,D) out. */
+int dic_dec_q_bwd(const float* z, const float* mu, const float* grad_q, float* grad_z,
+                  float* grad_mu, void* workspace, int64_t B, int D, int K, float alpha,
+                  dic_stream_t stream);
+
+/* Fused DEC step: given z, mu and the (global) column sum f, computes
+ *   p = target(q) (detached), kl_sum = sum_ij p (log p - log q)   [Net.kl_loss,
+ *   clustering_interp.py:205-207, before the 1/B of 'batchmean'],
+ *   grad_z = scale * dKL/dz, grad_mu = scale * dKL/dmu  (closed form).
+ * Pass scale = weight / B_global.  p, grad_z may be NULL.  kl_sum is one float64. */
+int dic_dec_kl_fwd_bwd(const float* z, const float* mu, const double* colsum, float* p,
+                       double* kl_sum, float* grad_z, float* grad_mu, void* workspace,
+                       int64_t B, int D, int K, float alpha, float scale, dic_stream_t stream);
+
+/* ---- k-means / gap statistic (sklearn.cluster.KMeans as called at
+ * p2_clustering_optK.py:260,284,372,377; clustering_trainer.py:75-82) ----------------
+ * dtype: 0 = float32, 1 = float64 (the reference feeds float64 reference draws,
+ * p2_clustering_optK.py:370).  X (N,D) and centers (K,D) share the dtype.
+ *
+ * One Lloyd pass (sklearn/cluster/_k_means_lloyd.pyx:23-218): E-step + accumulation of
+ * everything the M-step and the stopping rule need.
+ *   labels (N) int32 in/out: argmin_j ||c_j||^2 - 2 x.c_j, lowest index on ties
+ *   sums (K,D) float64 out, counts (K) float64 out: per-cluster sums and sizes
+ *   stats (4) float64 out: [ sum_i ||x_i - c_label||^2 (computed directly, like
+ *          _k_means_common.pyx:96-124),  number of labels that changed,
+ *          sum_i ||x_i - c_label|| (the elbow distortion numerator,
+ *          p2_clustering_optK.py:261-264),  0 ]
+ *   flags: DIC_KM_COUNT_CHANGES  compare with the previous content of `labels`
+ *          DIC_KM_KEEP_LABELS    do not re-assign: accumulate for the given labels
+ * sums/counts may be NULL (predict / inertia only).  Limits: K <= 64, D <= 512.
+ */
+#define DIC_KM_COUNT_CHANGES 1
+#define DIC_KM_KEEP_LABELS 2
+size_t dic_kmeans_workspace_bytes(int K, int D);
+int dic_kmeans_assign(const void* X, const void* centers, int32_t* labels, double* sums,
+                      double* counts, double* stats, void* workspace, int64_t N, int D, int K,
+                      int dtype, int flags, dic_stream_t stream);
+
+/* k-means++ potentials (sklearn/cluster/_kmeans.py:224-281): for each of L candidate centres
+ *   pots[l] = sum_i min(min_d2[i], ||x_i - cand_l||^2)          (float64, L <= 16)
+ * min_d2 (N, same dtype as X) may be NULL (treated as +inf: first centre).  If
+ * min_d2_out is not NULL (L must be 1) it receives the element-wise minimum: the commit. */
+int dic_kmeans_min_d2(const void* X, const void* cands, const void* min_d2, void* min_d2_out,
+                      double* pots, void* workspace, int64_t N, int D, int L, int dtype,
+                      dic_stream_t stream);
+
+/* Sum of all pairwise Euclidean distances inside one cluster, the kernel behind
+ * KM.compute_inertia_v1 / computer_intertia_v2, p2_clustering_optK.py:334-351:
+ *   Xc (n,D) rows of one cluster (gathered by the caller), out (1) float64 =
+ *   sum_{i,i'} ||x_i - x_i'||  over the FULL n x n matrix (zero diagonal included).
+ * The n x n matrix is never materialised.  Limit: D <= 512. */
+size_t dic_pairwise_workspace_bytes(int64_t n);
+int dic_pairwise_dist_sum(const void* Xc, double* out, void* workspace, int64_t n, int D,
+                          int dtype, dic_stream_t stream);
+
+/* ---- utilities -------------------------------------------------------------------- */
+/* Deterministic column sums of a (rows, cols) float32 matrix into float64. */
+size_t dic_colsum_workspace_bytes(int cols);
+int dic_colsum_f32(const float* a, double* out, void* workspace, int64_t rows, int cols,
+                   dic_stream_t stream);
+
+/* Roofline probes: run a MUFU.EX2-only / FFMA-only loop on every SM and report the
+ * achieved rate (operations per second) measured with CUDA events. */
+int dic_probe_mufu(double* ex2_per_second_host, dic_stream_t stream);
+int dic_probe_ffma(double* ffma_per_second_host, dic_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIC_B200_H */

@@ -1,0 +1,220 @@
+"""GPU parity of the interpolation network (SCI / CCI / RBF) against the oracle.
+
+Every call goes nn.Module mirror -> autograd Function -> ctypes -> C ABI -> sm_100a kernel.
+Truth = the reference run in float64 (tests/golden, written by oracle/gen_golden.py) or the
+numpy oracle in float64 on seeded inputs; tolerance = rtol 1e-5 (BASELINE.json) plus an
+absolute floor of 1e-5 x the tensor's RMS for entries that cancel to ~0.
+"""
+import numpy as np
+import pytest
+import torch
+
+from gpu_util import RTOL_GRID, record, scale_atol
+
+pytestmark = pytest.mark.gpu
+
+CASES = ["interp_c1", "interp_c2", "interp_c5", "interp_smoke", "interp_odd", "interp_dense"]
+
+
+def _modules(g, dev):
+    import deep_interpolation_clustering_b200 as dic
+    x = g["x"]
+    C, T = x.shape[1] // 4, x.shape[2]
+    R, H = int(g["R"]), float(g["hours"])
+    sci = dic.SingleChannelInterp(R, H, C, T, dev)
+    cci = dic.CrossChannelInterp(C, T, dev)
+    rbf = dic.RBF(H, R, C, C, 0.0, dic.basis_func_dict()["gaussian"], dev)
+    rbf.compress_fc = torch.nn.Identity()       # golden v is the kernel boundary
+    sci.kernel.data = torch.tensor(g["sci_kernel"], device=dev)
+    cci.kernel.data = torch.tensor(g["cci_kernel"], device=dev)
+    rbf.kernel.data = torch.tensor(g["rbf_kernel"], device=dev)
+    return sci, cci, rbf
+
+
+def _check(name, got, truth, rtol=RTOL_GRID):
+    return record(name, got.detach().cpu().numpy(), truth, rtol, scale_atol(truth, rtol))
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_forward_matches_reference_f64(golden, case):
+    g = golden(case)
+    dev = torch.device("cuda:0")
+    sci, cci, rbf = _modules(g, dev)
+    x = torch.tensor(g["x"], device=dev)
+    s = sci(x)
+    assert s.shape == g["sci_out"].shape
+    C, R = g["x"].shape[1] // 4, int(g["R"])
+    assert s.stride() == (3 * C * R, 1, R)            # the reference's permuted view
+    c = cci(s)
+    r = rbf(torch.tensor(g["v"], device=dev), x)
+    _check(f"{case}/sci", s, g["sci_out_f64"])
+    _check(f"{case}/cci", c, g["cci_out_f64"])
+    _check(f"{case}/rbf", r, g["rbf_out_f64"])
+    # and within the float32 reference's own error of the shipped float32 numbers
+    _check(f"{case}/sci_vs_f32ref", s, g["sci_out"], 1e-4)
+    _check(f"{case}/cci_vs_f32ref", c, g["cci_out"], 1e-4)
+    _check(f"{case}/rbf_vs_f32ref", r, g["rbf_out"], 1e-4)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_backward_matches_reference_f64(golden, case):
+    g = golden(case)
+    dev = torch.device("cuda:0")
+    sci, cci, rbf = _modules(g, dev)
+    x = torch.tensor(g["x"], device=dev)
+    v = torch.tensor(g["v"], device=dev, requires_grad=True)
+    s = sci(x)
+    s.retain_grad()
+    c = cci(s)
+    r = rbf(v, x)
+    (c * torch.tensor(g["g_cci"], device=dev)).sum().backward()
+    (r * torch.tensor(g["g_rbf"], device=dev)).sum().backward()
+    _check(f"{case}/d_sci_out", s.grad, g["d_sci_out_f64"])
+    _check(f"{case}/d_cci_kernel", cci.kernel.grad, g["d_cci_kernel_f64"])
+    _check(f"{case}/d_sci_kernel", sci.kernel.grad, g["d_sci_kernel_f64"])
+    _check(f"{case}/dv", v.grad, g["dv_f64"])
+    _check(f"{case}/d_rbf_kernel", rbf.kernel.grad, g["d_rbf_kernel_f64"])
+
+
+def test_allmasked_channel_semantics(golden):
+    """w = -inf, y = y' = NaN for an all-masked channel, like the reference."""
+    g = golden("interp_allmasked")
+    dev = torch.device("cuda:0")
+    sci, cci, _ = _modules(g, dev)
+    x = torch.tensor(g["x"], device=dev)
+    s = sci(x)
+    _check("allmasked/sci", s, g["sci_out_f64"])
+    _check("allmasked/cci", cci(s), g["cci_out_f64"])
+
+
+def test_config1_full_size_vs_oracle():
+    """BASELINE config 1: 1,000 encounters x 6 vitals x <=64 obs, 48 reference points."""
+    from deep_interpolation_clustering_b200 import synth
+    import deep_interpolation_clustering_b200 as dic
+    from oracle import interp_oracle
+    dev = torch.device("cuda:0")
+    B, C, T, R, H = 1000, 6, 64, 48, 24.0
+    xn = synth.make_encounters(B, C, T, H, seed=0)
+    p = synth.make_interp_params(C, seed=1)
+    rng = np.random.RandomState(2)
+    vn = rng.normal(size=(B, C, R)).astype(np.float32)
+    gc = rng.normal(size=(B, R, 3 * C)).astype(np.float32)
+    rt = interp_oracle.linspace_grid(H, R)
+    x64 = xn.astype(np.float64)
+    s64 = interp_oracle.sci_forward(x64, p["sci_kernel"].astype(np.float64), rt, C)
+    c64 = interp_oracle.cci_forward(s64, p["cci_kernel"].astype(np.float64), C)
+    r64 = interp_oracle.rbf_forward(vn, x64, p["rbf_kernel"].astype(np.float64), rt, C)
+    du64, dK64 = interp_oracle.cci_backward(s64, p["cci_kernel"].astype(np.float64), C, gc)
+    dk64 = interp_oracle.sci_backward(x64, p["sci_kernel"].astype(np.float64), rt, C, du64)
+    grec = interp_oracle.rec_loss_grad(x64, r64, C)
+    dv64, dkr64 = interp_oracle.rbf_backward(vn, x64, p["rbf_kernel"].astype(np.float64), rt, C, grec)
+    loss64 = interp_oracle.rec_loss(x64, r64, C)
+
+    sci = dic.SingleChannelInterp(R, H, C, T, dev)
+    cci = dic.CrossChannelInterp(C, T, dev)
+    rbf = dic.RBF(H, R, C, C, 0.0, dic.basis_func_dict()["gaussian"], dev)
+    rbf.compress_fc = torch.nn.Identity()
+    sci.kernel.data = torch.tensor(p["sci_kernel"], device=dev)
+    cci.kernel.data = torch.tensor(p["cci_kernel"], device=dev)
+    rbf.kernel.data = torch.tensor(p["rbf_kernel"], device=dev)
+    x = torch.tensor(xn, device=dev)
+    v = torch.tensor(vn, device=dev, requires_grad=True)
+    c = cci(sci(x))
+    rec = rbf(v, x)
+    m = x[:, C:2 * C]
+    loss = ((rec * m - x[:, :C] * m) ** 2).sum() / (m == 1.0).sum()     # pretrain_interp.py:169-175
+    ((c * torch.tensor(gc, device=dev)).sum() + loss).backward()
+    _check("c1/cci_out", c, c64)
+    _check("c1/rbf_out", rec, r64)
+    _check("c1/rec_loss", loss, loss64)
+    _check("c1/d_sci_kernel", sci.kernel.grad, dk64)
+    _check("c1/d_cci_kernel", cci.kernel.grad, dK64)
+    _check("c1/d_rbf_kernel", rbf.kernel.grad, dkr64)
+    _check("c1/dv", v.grad, dv64)
+
+
+def test_rbf_module_state_dict_dropin(golden):
+    """The full RBF module (compress_fc included) loads the reference's state dict by key and
+    reproduces its eval-mode output."""
+    import deep_interpolation_clustering_b200 as dic
+    g = golden("rbf_module")
+    dev = torch.device("cuda:0")
+    x = torch.tensor(g["x"], device=dev)
+    C, T = x.shape[1] // 4, x.shape[2]
+    rbf = dic.RBF(float(g["hours"]), int(g["R"]), g["interp"].shape[1], C, 0.2,
+                  dic.basis_func_dict()["gaussian"], dev).to(dev)
+    sd = {k[3:]: torch.tensor(v) for k, v in g.items() if k.startswith("sd.")}
+    assert set(sd) == set(rbf.state_dict())
+    rbf.load_state_dict(sd, strict=True)
+    rbf.eval()
+    with torch.no_grad():
+        out = rbf(torch.tensor(g["interp"], device=dev), x)
+    _check("rbf_module/out", out, g["out"], 1e-4)       # TF32-free cuBLAS vs CPU GEMM in compress_fc
+
+
+def test_shape_and_device_errors():
+    import deep_interpolation_clustering_b200 as dic
+    dev = torch.device("cuda:0")
+    sci = dic.SingleChannelInterp(8, 24.0, 6, 16, dev)
+    with pytest.raises(RuntimeError):
+        sci(torch.zeros(2, 24, 17, device=dev))          # timestamp mismatch, as the reference
+    with pytest.raises(RuntimeError):
+        sci(torch.zeros(2, 24, 16))                      # CPU tensor: no fallback
+    with pytest.raises(TypeError):
+        sci(torch.zeros(2, 24, 16, device=dev, dtype=torch.float64))
+
+
+def test_batch_independence_and_constant_signal_large():
+    """Size-independent properties at a BASELINE-config-2-shaped batch (T=256, R=96):
+    (i) every encounter's output equals the output of that encounter alone (indexing at large B);
+    (ii) a constant signal is reproduced by both filters (weights sum to 1)."""
+    import deep_interpolation_clustering_b200 as dic
+    from deep_interpolation_clustering_b200 import synth
+    dev = torch.device("cuda:0")
+    B, C, T, R, H = 65536, 6, 256, 96, 24.0
+    x = synth.make_encounters_device(B, C, T, H, 5.0, seed=3, device=dev)
+    sci = dic.SingleChannelInterp(R, H, C, T, dev)
+    cci = dic.CrossChannelInterp(C, T, dev)
+    with torch.no_grad():
+        full = cci(sci(x))
+        idx = torch.tensor([0, 1, 4097, 32768, B - 2, B - 1], device=dev)
+        part = cci(sci(x[idx].contiguous()))
+        assert torch.equal(full[idx], part)
+        xc = x.clone()
+        xc[:, :C] = 1.75 * xc[:, C:2 * C]
+        s = sci(xc)
+        y, y10 = s[:, :, :C], s[:, :, 2 * C:]
+        assert torch.allclose(y, torch.full_like(y, 1.75), rtol=1e-5, atol=0)
+        assert torch.allclose(y10, torch.full_like(y10, 1.75), rtol=1e-5, atol=0)
+        assert torch.isfinite(s).all()
+
+
+def test_unsorted_and_weighted_masks_vs_oracle():
+    """Shuffled observation order and fractional mask weights (log m acts as a weight,
+    interpolation_layer.py:59) follow the same closed form."""
+    import deep_interpolation_clustering_b200 as dic
+    from deep_interpolation_clustering_b200 import synth
+    from oracle import interp_oracle
+    dev = torch.device("cuda:0")
+    B, C, T, R, H = 16, 6, 40, 24, 24.0
+    xn = synth.make_adversarial_encounters(B, C, T, H, seed=9)
+    rng = np.random.RandomState(10)
+    w = rng.uniform(0.25, 1.0, size=(B, C, T)).astype(np.float32)
+    xn[:, C:2 * C] *= w                                  # fractional weights on valid entries
+    p = synth.make_interp_params(C, seed=1)
+    rt = interp_oracle.linspace_grid(H, R)
+    s64 = interp_oracle.sci_forward(xn.astype(np.float64), p["sci_kernel"].astype(np.float64), rt, C)
+    vn = rng.normal(size=(B, C, R)).astype(np.float32)
+    r64 = interp_oracle.rbf_forward(vn, xn.astype(np.float64), p["rbf_kernel"].astype(np.float64), rt, C)
+    sci = dic.SingleChannelInterp(R, H, C, T, dev)
+    rbf = dic.RBF(H, R, C, C, 0.0, dic.basis_func_dict()["gaussian"], dev)
+    rbf.compress_fc = torch.nn.Identity()
+    sci.kernel.data = torch.tensor(p["sci_kernel"], device=dev)
+    rbf.kernel.data = torch.tensor(p["rbf_kernel"], device=dev)
+    x = torch.tensor(xn, device=dev)
+    _check("weighted/sci", sci(x), s64)
+    _check("weighted/rbf", rbf(torch.tensor(vn, device=dev), x), r64)
+    gs = rng.normal(size=s64.shape).astype(np.float32)
+    dk64 = interp_oracle.sci_backward(xn.astype(np.float64), p["sci_kernel"].astype(np.float64), rt, C, gs)
+    (sci(x) * torch.tensor(gs, device=dev)).sum().backward()
+    _check("weighted/d_sci_kernel", sci.kernel.grad, dk64)

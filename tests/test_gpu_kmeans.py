@@ -1,0 +1,140 @@
+"""GPU parity of the k-means / gap-statistic path against scikit-learn 1.9.0 results
+(tests/golden/kmeans.npz, gap.npz - produced by oracle/gen_golden.py through sklearn and the
+reference's own KM class).
+
+Labels are compared bit-exactly; a mismatch is tolerated only where the float64 margin between
+the two nearest centres is below 1e-5 of the distance (a documented near-tie, BASELINE.json).
+"""
+import numpy as np
+import pytest
+import torch
+
+from gpu_util import record
+
+pytestmark = pytest.mark.gpu
+
+
+def _labels_equal_mod_ties(name, got, want, X, centers):
+    got, want = np.asarray(got), np.asarray(want)
+    bad = np.nonzero(got != want)[0]
+    if bad.size == 0:
+        return
+    X64, C64 = np.asarray(X, np.float64), np.asarray(centers, np.float64)
+    d = ((X64[bad, None, :] - C64[None]) ** 2).sum(2)
+    d.sort(axis=1)
+    margin = (d[:, 1] - d[:, 0]) / np.maximum(d[:, 0], 1e-30)
+    assert np.all(margin < 1e-5), f"{name}: {bad.size} label mismatches, worst margin {margin.max():.3e}"
+
+
+@pytest.mark.parametrize("dtag", ["f32", "f64"])
+@pytest.mark.parametrize("k", [2, 4, 7])
+def test_lloyd_matches_sklearn(golden, dtag, k):
+    from deep_interpolation_clustering_b200.kmeans import KMeansB200
+    g = golden("kmeans")
+    X = g["X"].astype(np.float32 if dtag == "f32" else np.float64)
+    pre = f"{dtag}_k{k}_"
+    km = KMeansB200(n_clusters=k, init=X[:k].copy(), n_init=1).fit(X)
+    assert km.labels_.dtype == np.int32 and km.cluster_centers_.dtype == X.dtype
+    _labels_equal_mod_ties(pre + "labels", km.labels_, g[pre + "labels"], X, g[pre + "centers"])
+    assert km.n_iter_ == int(g[pre + "n_iter"])
+    record(pre + "centers", km.cluster_centers_, g[pre + "centers"], 1e-5, 1e-5)
+    record(pre + "inertia", km.inertia_, g[pre + "inertia"], 1e-5, 0)
+    Xv = g["Xv"].astype(X.dtype)
+    _labels_equal_mod_ties(pre + "predict", km.predict(Xv), g[pre + "predict"], Xv, g[pre + "centers"])
+    record(pre + "elbow", km.score_distortion(X), g[pre + "elbow_train"], 1e-5, 0)
+    # fit_predict is fit().labels_, and cluster_centers_ is a writable ndarray (p4 mutates it)
+    km.cluster_centers_[0] += 0.0
+
+
+def test_empty_cluster_relocation(golden):
+    from deep_interpolation_clustering_b200.kmeans import KMeansB200
+    g = golden("kmeans")
+    km = KMeansB200(n_clusters=3, init=g["reloc_init"], n_init=1).fit(g["X"])
+    _labels_equal_mod_ties("reloc", km.labels_, g["reloc_labels"], g["X"], g["reloc_centers"])
+    assert km.n_iter_ == int(g["reloc_n_iter"])
+    record("reloc_centers", km.cluster_centers_, g["reloc_centers"], 1e-5, 1e-5)
+    record("reloc_inertia", km.inertia_, g["reloc_inertia"], 1e-5, 0)
+
+
+def test_inertia_definitions(golden):
+    from deep_interpolation_clustering_b200.gap import KM
+    g = golden("kmeans")
+    a, X = g["f32_k4_labels"], g["X"]
+    km = KM(5)
+    record("inertia_v1_f32", km.compute_inertia_v1(a, X), g["inertia_v1_f32"], 1e-5, 0)
+    record("inertia_v2_f32", km.computer_intertia_v2(a, X), g["inertia_v2_f32"], 1e-5, 0)
+    record("inertia_v1_f64", km.compute_inertia_v1(a, X.astype(np.float64)), g["inertia_v1_f64"], 1e-9, 0)
+    record("inertia_v2_f64", km.computer_intertia_v2(a, X.astype(np.float64)), g["inertia_v2_f64"], 1e-9, 0)
+
+
+class _FixedInit:
+    """Same duck type gen_golden.py handed to the reference: init = first k rows."""
+    accepts_device_tensors = False
+
+    def __init__(self):
+        self.n_clusters = 2
+
+    def fit_predict(self, X):
+        from deep_interpolation_clustering_b200.kmeans import KMeansB200
+        X = np.ascontiguousarray(X)
+        return KMeansB200(n_clusters=self.n_clusters, init=X[:self.n_clusters].copy(), n_init=1).fit_predict(X)
+
+
+@pytest.mark.parametrize("version", [1, 2])
+def test_gap_statistic_dataframe(golden, version):
+    from deep_interpolation_clustering_b200.gap import KM
+    g = golden("gap")
+    names = ["Sihouette", "Davies-Bouldin_Index", "Calinski-Harabasz"]
+    km = KM(5, None, names, 1, 3)
+    np.random.seed(7)
+    df = km.compute_gap_internal_metric(_FixedInit(), g["X"], k_max=5, n_references=3, version=version)
+    assert list(df.columns) == ["k", "gap", "ref", "act", "ref_s"] + names
+    assert list(df.index) == [2, 3, 4, 5]
+    for col in ("k", "gap", "ref", "act"):
+        record(f"gap_v{version}/{col}", df[col].to_numpy(np.float64), g[f"v{version}_{col}"], 1e-5, 1e-6)
+    record(f"gap_v{version}/ref_s", df["ref_s"].to_numpy(np.float64), g[f"v{version}_ref_s"], 1e-3, 1e-6)
+    for col in names:
+        record(f"gap_v{version}/{col}", df[col].to_numpy(np.float64), g[f"v{version}_{col}"], 1e-5, 1e-6)
+
+
+def test_kmeans_plusplus_quality_and_stream(golden):
+    """k-means++ seeding on device: reaches the blob optimum, and consumes the numpy stream in
+    the same quantity as sklearn (1 + (K-1) * (2 + int(ln K)) doubles per init)."""
+    from sklearn.cluster import KMeans
+    from deep_interpolation_clustering_b200.kmeans import KMeansB200
+    g = golden("kmeans")
+    X = g["X"]
+    ref = KMeans(n_clusters=5, n_init=3, random_state=0).fit(X)
+    km = KMeansB200(n_clusters=5, n_init=3, random_state=0).fit(X)
+    assert km.inertia_ <= ref.inertia_ * 1.02
+    r1, r2 = np.random.RandomState(5), np.random.RandomState(5)
+    KMeans(n_clusters=5, n_init=2, random_state=r1).fit(X)
+    KMeansB200(n_clusters=5, n_init=2, random_state=r2).fit(X)
+    assert r1.uniform() == r2.uniform()
+
+
+def test_config4_size_properties():
+    """1M x 64 (BASELINE config 4 shape), K = 10: fixed point (predict == labels_ away from
+    ties), centres are the means of their members, inertia equals the direct sum."""
+    from deep_interpolation_clustering_b200.kmeans import KMeansB200
+    from deep_interpolation_clustering_b200 import synth
+    dev = torch.device("cuda:0")
+    X = torch.from_numpy(synth.make_blobs(1_000_000, 64, 5, seed=4)).to(dev)
+    km = KMeansB200(n_clusters=10, n_init=1, random_state=3).fit(X)
+    lab, cen = km.labels_.long(), km.cluster_centers_
+    means = torch.zeros_like(cen, dtype=torch.float64).index_add_(0, lab, X.double())
+    means /= torch.bincount(lab, minlength=10).double()[:, None]
+    assert torch.allclose(means.float(), cen, rtol=1e-4, atol=1e-4)
+    direct = float(((X.double() - cen.double()[lab]) ** 2).sum())
+    assert abs(direct - km.inertia_) <= 1e-5 * direct
+    again = km.predict(X).long()
+    frac = float((again != lab).double().mean())
+    assert frac < 1e-3, frac
+
+
+def test_errors():
+    from deep_interpolation_clustering_b200.kmeans import KMeansB200
+    with pytest.raises(ValueError):
+        KMeansB200(n_clusters=5).fit(np.zeros((3, 4), np.float32))
+    with pytest.raises(ValueError):
+        KMeansB200(n_clusters=2, init=np.zeros((3, 4))).fit(np.zeros((10, 4), np.float32))

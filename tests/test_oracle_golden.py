@@ -158,3 +158,46 @@ def test_gap_statistic(golden, version):
     res = kmeans_oracle.gap_statistic(fit_predict, X, k_max=5, n_references=3, version=version)
     for col in ("k", "gap", "ref", "act", "ref_s"):
         _close(res[col], g[f"v{version}_{col}"], 1e-6, 1e-7, col)
+
+
+@pytest.mark.parametrize("case", ["interp_c1", "interp_smoke", "interp_odd"])
+def test_ref_port_matches_reference(golden, case):
+    """The torch-CPU port timed as the CPU baseline reproduces the reference's float32 run."""
+    import torch
+    from oracle import ref_port
+    g = golden(case)
+    C = g["x"].shape[1] // 4
+    R, H = int(g["R"]), float(g["hours"])
+    sci, cci, rbf = ref_port.SingleChannelInterp(R, H, C), ref_port.CrossChannelInterp(C), \
+        ref_port.RBFReadout(R, H, C)
+    sci.kernel.data = torch.tensor(g["sci_kernel"])
+    cci.kernel.data = torch.tensor(g["cci_kernel"])
+    rbf.kernel.data = torch.tensor(g["rbf_kernel"])
+    x = torch.tensor(g["x"])
+    v = torch.tensor(g["v"], requires_grad=True)
+    s = sci(x)
+    c = cci(s)
+    r = rbf(v, x)
+    (c * torch.tensor(g["g_cci"])).sum().backward()
+    (r * torch.tensor(g["g_rbf"])).sum().backward()
+    _close(s.detach().numpy(), g["sci_out"], 1e-5, 1e-5, "sci")
+    _close(c.detach().numpy(), g["cci_out"], 1e-5, 1e-5, "cci")
+    _close(r.detach().numpy(), g["rbf_out"], 1e-5, 1e-5, "rbf")
+    _close(sci.kernel.grad.numpy(), g["d_sci_kernel"], 1e-4, 1e-4, "d sci.kernel")
+    _close(cci.kernel.grad.numpy(), g["d_cci_kernel"], 1e-4, 1e-4, "d cci.kernel")
+    _close(rbf.kernel.grad.numpy(), g["d_rbf_kernel"], 1e-4, 1e-4, "d rbf.kernel")
+    _close(v.grad.numpy(), g["dv"], 1e-4, 1e-5, "dv")
+
+
+def test_ref_port_dec(golden):
+    import torch
+    from oracle import ref_port
+    g = golden("dec_k4")
+    z = torch.tensor(g["z"], requires_grad=True)
+    mu = torch.tensor(g["mu"], requires_grad=True)
+    loss, q, p = ref_port.dec_step(z, mu, float(g["alpha"]))
+    _close(q.numpy(), g["q"], 0, 1e-6, "q")
+    _close(p.numpy(), g["p"], 0, 1e-6, "p")
+    _close(loss.numpy(), g["kl"], 1e-5, 1e-8, "kl")
+    _close(z.grad.numpy(), g["dz_kl"], 1e-4, 1e-8, "dz")
+    _close(mu.grad.numpy(), g["dmu_kl"], 1e-4, 1e-7, "dmu")
