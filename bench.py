@@ -1,0 +1,462 @@
+#!/usr/bin/env python
+"""Headline benchmark: encounters/s of (interpolation fwd+bwd + DEC assign) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload = BASELINE.json configs[1] ("c2"): 1,000,000 synthetic encounters x 6 vitals x <=256
+irregular observations in 24 h, 96 reference points, per GPU (weak scaling: every rank owns
+its own 1M-encounter shard), plus the DEC q/p assignment of one 256-d latent per encounter
+(K = 4).  One step = one pass of the whole hot path over the shard:
+
+    SCI fwd -> CCI fwd -> CCI bwd -> SCI bwd -> RBF fwd -> RBF bwd -> DEC q (+labels, column sum)
+    -> all-reduce(column sum) -> DEC p -> all-reduce(parameter gradients)
+
+`value`  : whole-job encounters/s, inputs resident in HBM, CUDA-event timed, max over ranks.
+`e2e`    : the same metric through the public nn.Module API with HOST (pinned) input buffers:
+           H2D of every chunk of x, autograd fwd+bwd, D2H of loss/grads/labels in the timed region.
+`roofline`: dominant kernel vs the measured HBM peak (schema of the task); `roofline_sfu` adds
+           the MUFU.EX2 view, which is the resource that actually binds the interpolation kernels.
+`cpu_baseline`: the reference's algorithm (oracle/ref_port.py, torch-CPU autograd) on a bounded
+           sample of the same workload on this box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+C, T, R, HOURS, D_LAT, K_CLUST = 6, 256, 96, 24.0, 256, 4
+CFG_NAME = "c2: interp fwd+bwd + DEC assign, 1M enc x 6 vitals x <=256 obs, 96 ref points"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--encounters", type=int, default=1_000_000, help="encounters per GPU per step")
+    ap.add_argument("--e2e-encounters", type=int, default=262_144)
+    ap.add_argument("--e2e-chunk", type=int, default=32_768)
+    ap.add_argument("--cpu-sample", type=int, default=256, help="encounters in the CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU arm (reference algorithm on host cores)
+# ----------------------------------------------------------------------------------------------
+def cpu_arm(sample, steps, warmup):
+    """Times oracle/ref_port (the reference's ATen-level algorithm) on `sample` encounters of the
+    c2 shape + the DEC step on the same number of latents.  Returns encounters/s."""
+    import numpy as np
+    import torch
+    from deep_interpolation_clustering_b200 import synth
+    from oracle import ref_port
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    x = torch.from_numpy(synth.make_encounters(sample, C, T, HOURS, seed=0))
+    p = synth.make_interp_params(C, seed=1)
+    rng = np.random.RandomState(2)
+    v = torch.from_numpy(rng.normal(size=(sample, C, R)).astype(np.float32)).requires_grad_(True)
+    g = torch.from_numpy(rng.normal(size=(sample, R, 3 * C)).astype(np.float32))
+    zn, mun = synth.make_latents(sample, D_LAT, K_CLUST, seed=3)
+    z = torch.from_numpy(zn).requires_grad_(True)
+    mu = torch.from_numpy(mun).requires_grad_(True)
+    sci, cci, rbf = ref_port.SingleChannelInterp(R, HOURS, C), ref_port.CrossChannelInterp(C), \
+        ref_port.RBFReadout(R, HOURS, C)
+    sci.kernel.data = torch.from_numpy(p["sci_kernel"])
+    cci.kernel.data = torch.from_numpy(p["cci_kernel"])
+    rbf.kernel.data = torch.from_numpy(p["rbf_kernel"])
+
+    def step():
+        for t in (sci.kernel, cci.kernel, rbf.kernel, v, z, mu):
+            t.grad = None
+        ref_port.interp_step(sci, cci, rbf, x, v, g)
+        ref_port.dec_step(z, mu, 1.0)
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return sample / dt, dt, cores
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks sampler (NVML)
+# ----------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            pass
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ----------------------------------------------------------------------------------------------
+# device arm
+# ----------------------------------------------------------------------------------------------
+class HotPath:
+    """Preallocated buffers + direct C-ABI calls for one shard (no allocation in the timed loop)."""
+
+    # launches of OUR kernels behind each C-ABI call (kernel + reductions)
+    LAUNCHES = dict(sci_fwd=1, cci_fwd=1, cci_bwd=3, sci_bwd=4, rbf_fwd=1, rbf_bwd=4, dec_q=2, dec_p=1)
+
+    def __init__(self, B, dev, seed):
+        import torch
+        from deep_interpolation_clustering_b200 import _lib, synth
+        self.t, self.L, self._lib, self.B, self.dev = torch, _lib.lib(), _lib, B, dev
+        f32 = dict(dtype=torch.float32, device=dev)
+        g = torch.Generator(device=dev)
+        g.manual_seed(seed + 100)
+        self.x = synth.make_encounters_device(B, C, T, HOURS, 5.0, seed, dev)
+        p = synth.make_interp_params(C, seed=1)
+        self.k_sci = torch.tensor(p["sci_kernel"], **f32)
+        self.k_cci = torch.tensor(p["cci_kernel"], **f32)
+        self.k_rbf = torch.tensor(p["rbf_kernel"], **f32)
+        self.ref_t = torch.linspace(0, HOURS, R).to(dev)
+        self.u = torch.empty((B, 3 * C, R), **f32)
+        self.stats = torch.empty((B, 2 * C, R), **f32)
+        self.out = torch.empty((B, 3 * C, R), **f32)
+        self.g_out = torch.randn((B, 3 * C, R), generator=g, **f32)
+        self.g_u = torch.empty((B, 3 * C, R), **f32)
+        self.v = torch.randn((B, C, R), generator=g, **f32)
+        self.rec = torch.empty((B, C, T), **f32)
+        self.inv = torch.empty((B, C, T), **f32)
+        self.g_rec = torch.randn((B, C, T), generator=g, **f32)
+        self.g_v = torch.empty((B, C, R), **f32)
+        self.z, self.mu = synth.make_latents_device(B, D_LAT, K_CLUST, seed + 7, dev)
+        self.q = torch.empty((B, K_CLUST), **f32)
+        self.p = torch.empty((B, K_CLUST), **f32)
+        self.labels = torch.empty(B, dtype=torch.int32, device=dev)
+        self.colsum = torch.empty(K_CLUST, dtype=torch.float64, device=dev)
+        self.grads = torch.empty(C + C * C + C, **f32)          # packed [d sci.kernel | d cci.kernel | d rbf.kernel]
+        self.ws_i = torch.empty(int(self.L.dic_interp_bwd_workspace_bytes(B, C)), dtype=torch.uint8, device=dev)
+        self.ws_c = torch.empty(int(self.L.dic_cci_bwd_workspace_bytes(B, C)), dtype=torch.uint8, device=dev)
+        self.ws_d = torch.empty(int(self.L.dic_dec_workspace_bytes(K_CLUST, D_LAT)), dtype=torch.uint8, device=dev)
+        self.n_valid = float(self.x[:, C:2 * C].sum())
+
+    def kernels(self, st):
+        """[(name, callable)] in step order; each callable issues one C-ABI call on stream st."""
+        L, P, B = self.L, self._lib.ptr, self.B
+        chk = self._lib.check
+        gs, gc, gr = self.grads[:C], self.grads[C:C + C * C], self.grads[C + C * C:]
+        return [
+            ("sci_fwd", lambda: chk(L.dic_sci_fwd(P(self.x), P(self.k_sci), P(self.ref_t), P(self.u), P(self.stats),
+                                                  B, C, T, R, st), "sci_fwd")),
+            ("cci_fwd", lambda: chk(L.dic_cci_fwd(P(self.u), P(self.k_cci), P(self.out), B, C, R, st), "cci_fwd")),
+            ("cci_bwd", lambda: chk(L.dic_cci_bwd(P(self.u), P(self.k_cci), P(self.g_out), P(self.g_u), P(gc),
+                                                  P(self.ws_c), B, C, R, st), "cci_bwd")),
+            ("sci_bwd", lambda: chk(L.dic_sci_bwd(P(self.x), P(self.k_sci), P(self.ref_t), P(self.u), P(self.stats),
+                                                  P(self.g_u), P(gs), P(self.ws_i), B, C, T, R, st), "sci_bwd")),
+            ("rbf_fwd", lambda: chk(L.dic_rbf_fwd(P(self.v), P(self.x), P(self.k_rbf), P(self.ref_t), P(self.rec),
+                                                  P(self.inv), B, C, T, R, st), "rbf_fwd")),
+            ("rbf_bwd", lambda: chk(L.dic_rbf_bwd(P(self.v), P(self.x), P(self.k_rbf), P(self.ref_t), P(self.rec),
+                                                  P(self.inv), P(self.g_rec), P(self.g_v), P(gr), P(self.ws_i),
+                                                  B, C, T, R, st), "rbf_bwd")),
+            ("dec_q", lambda: chk(L.dic_dec_q_fwd(P(self.z), P(self.mu), P(self.q), P(self.labels), P(self.colsum),
+                                                  P(self.ws_d), B, D_LAT, K_CLUST, 1.0, st), "dec_q")),
+            ("dec_p", lambda: chk(L.dic_dec_p(P(self.q), P(self.colsum), P(self.p), B, K_CLUST, st), "dec_p")),
+        ]
+
+    def algorithmic(self):
+        """Algorithmic HBM bytes and MUFU exps per launch (split per kernel)."""
+        B, nv = self.B, self.n_valid
+        ct, cr = C * T * 4.0, C * R * 4.0
+        byt = dict(sci_fwd=3 * ct + 3 * cr + 2 * cr, cci_fwd=6 * cr, cci_bwd=9 * cr,
+                   sci_bwd=3 * ct + 3 * cr + 2 * cr + 3 * cr, rbf_fwd=2 * ct + cr + 2 * ct,
+                   rbf_bwd=2 * ct + 3 * ct + cr + cr, dec_q=D_LAT * 4.0 + K_CLUST * 4.0 + 4.0, dec_p=2 * K_CLUST * 4.0)
+        ex2 = dict(sci_fwd=2 * nv * R, sci_bwd=2 * nv * R, rbf_fwd=nv * R, rbf_bwd=nv * R)
+        return {k: v * B for k, v in byt.items()}, ex2
+
+
+def device_arm(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from deep_interpolation_clustering_b200 import _lib
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.encounters
+    hp = HotPath(B, dev, seed=1000 * rank)
+    stream = torch.cuda.current_stream(dev)
+    st = stream.cuda_stream
+    kernels = hp.kernels(st)
+
+    def step():
+        for name, fn in kernels:
+            if name == "dec_p" and world > 1:
+                dist.all_reduce(hp.colsum)               # f_j over the global batch (dec.py:73)
+            fn()
+        if world > 1:
+            dist.all_reduce(hp.grads)                    # parameter gradients of the sharded batch
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t_ms) / args.steps
+    value = world * B / (ms_per_step * 1e-3)
+
+    # per-kernel durations (CUDA events on the launching stream), for the roofline objects
+    per = {n: [] for n, _ in kernels}
+    for _ in range(3):
+        for name, fn in kernels:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            fn()
+            b.record(stream)
+            b.synchronize()
+            per[name].append(a.elapsed_time(b))
+    kms = {n: statistics.mean(v) for n, v in per.items()}
+
+    e2e = None
+    if not args.no_e2e:
+        e2e = e2e_arm(args, hp, dev, world)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return None
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    mufu = ctypes.c_double()
+    _lib.check(_lib.lib().dic_probe_mufu(ctypes.byref(mufu), st), "probe_mufu")
+    ffma = ctypes.c_double()
+    _lib.check(_lib.lib().dic_probe_ffma(ctypes.byref(ffma), st), "probe_ffma")
+    byt, ex2 = hp.algorithmic()
+    ktab = {}
+    for n, m in kms.items():
+        ktab[n] = {"ms": round(m, 4), "share": round(m / sum(kms.values()), 4),
+                   "algorithmic_gb": round(byt[n] / 1e9, 3), "gbps": round(byt[n] / 1e9 / (m * 1e-3), 1),
+                   "hbm_frac": round(byt[n] / 1e9 / (m * 1e-3) / hbm_peak, 4)}
+        if n in ex2:
+            ktab[n]["gex2_per_s"] = round(ex2[n] / 1e9 / (m * 1e-3), 1)
+            ktab[n]["mufu_frac"] = round(ex2[n] / (m * 1e-3) / mufu.value, 4)
+    dom = max(kms, key=kms.get)
+    roofline = {"kernel": dom, "bound": "hbm", "achieved": ktab[dom]["gbps"], "peak": hbm_peak, "unit": "GB/s",
+                "frac": ktab[dom]["hbm_frac"], "traffic": None, "peak_source": peak_src,
+                "note": "interpolation kernels are MUFU/issue bound, not HBM bound: see roofline_sfu"}
+    roofline_sfu = {"kernel": dom, "bound": "sfu", "unit": "Gex2/s",
+                    "achieved": ktab[dom].get("gex2_per_s"), "peak": round(mufu.value / 1e9, 1),
+                    "frac": ktab[dom].get("mufu_frac"), "ffma_peak_gops": round(ffma.value / 1e9, 1),
+                    "peak_source": "dic_probe_mufu: ex2.approx-only kernel timed in this run",
+                    "note": "algorithmic exps = 2 per (valid obs, ref point) for SCI (low+high pass), 1 for RBF; "
+                            "the kernels issue ONE MUFU.EX2 per pair (high-pass = e^10), so frac may exceed 1"}
+
+    line = {
+        "metric": "encounters/s (interp fwd+bwd + DEC assign)", "value": round(value, 1), "unit": "encounters/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": CFG_NAME, "encounters_per_gpu": B, "vitals": C, "max_obs": T, "ref_points": R,
+                   "hours": HOURS, "latent_dim": D_LAT, "clusters": K_CLUST, "mean_valid_obs": round(hp.n_valid / (B * C), 2),
+                   "parallelism": f"encounter-sharded x{world}", "l2": "inputs (24.6 GB/GPU) exceed L2"},
+        "clocks": clocks, "gpu_launches": args.steps * sum(HotPath.LAUNCHES.values()),
+        "kernels": ktab, "roofline": roofline, "roofline_sfu": roofline_sfu, "e2e": e2e,
+    }
+    if not args.no_cpu_baseline:
+        v, dt, cores = cpu_arm(args.cpu_sample, 2, 1)
+        line["cpu_baseline"] = {"value": round(v, 1), "unit": "encounters/s", "cores": cores, "kind": "port",
+                                "sample": f"{args.cpu_sample} encounters of the c2 shape + {args.cpu_sample} latents, "
+                                          f"oracle/ref_port.py (torch CPU autograd), {dt:.2f} s/step"}
+    if world > 1:
+        dist.destroy_process_group()
+    return line
+
+
+def e2e_arm(args, hp, dev, world):
+    """Public-API path with host buffers: pinned x chunks -> H2D -> nn.Module fwd/bwd (autograd) + DEC step
+    -> D2H of loss, parameter grads and labels.  Double-buffered on a copy stream."""
+    import torch
+    import torch.distributed as dist
+    import deep_interpolation_clustering_b200 as dic
+    from deep_interpolation_clustering_b200 import functional as F_
+    Bc = min(args.e2e_chunk, hp.B)
+    n_chunks = max(1, min(args.e2e_encounters, hp.B) // Bc)
+    host = [hp.x[i * Bc:(i + 1) * Bc].cpu().pin_memory() for i in range(min(2, n_chunks))]
+    dbuf = [torch.empty_like(hp.x[:Bc]) for _ in range(2)]
+    sci = dic.SingleChannelInterp(R, HOURS, C, T, dev)
+    cci = dic.CrossChannelInterp(C, T, dev)
+    rbf = dic.RBF(HOURS, R, C, C, 0.0, dic.basis_func_dict()["gaussian"], dev)
+    rbf.compress_fc = torch.nn.Identity()
+    sci.kernel.data, cci.kernel.data, rbf.kernel.data = hp.k_sci.clone(), hp.k_cci.clone(), hp.k_rbf.clone()
+    params = [sci.kernel, cci.kernel, rbf.kernel]
+    copy_stream = torch.cuda.Stream(dev)
+    main = torch.cuda.current_stream(dev)
+    host_out = torch.empty(C + C * C + C + 1, dtype=torch.float32).pin_memory()
+    host_lab = torch.empty(Bc, dtype=torch.int32).pin_memory()
+    ready = [torch.cuda.Event() for _ in range(2)]
+    free = [torch.cuda.Event() for _ in range(2)]
+
+    def step():
+        for p_ in params:
+            p_.grad = None
+        loss_acc = torch.zeros((), device=dev)
+        with torch.cuda.stream(copy_stream):
+            dbuf[0].copy_(host[0], non_blocking=True)
+            ready[0].record(copy_stream)
+        for i in range(n_chunks):
+            cur = i & 1
+            if i + 1 < n_chunks:
+                with torch.cuda.stream(copy_stream):
+                    if i >= 1:
+                        copy_stream.wait_event(free[cur ^ 1])
+                    dbuf[cur ^ 1].copy_(host[(i + 1) % len(host)], non_blocking=True)
+                    ready[cur ^ 1].record(copy_stream)
+            main.wait_event(ready[cur])
+            x = dbuf[cur]
+            sl = slice(i * Bc, (i + 1) * Bc)
+            v = hp.v[sl].detach().requires_grad_(True)
+            out = cci(sci(x))
+            rec = rbf(v, x)
+            m = x[:, C:2 * C]
+            loss = (out.permute(0, 2, 1) * hp.g_out[sl]).sum() / Bc + ((rec * m - x[:, :C] * m) ** 2).sum() / m.sum()
+            loss.backward()
+            res = F_.dec_kl_step(hp.z[sl], hp.mu, 1.0, weight=10.0, want_grad_z=False)
+            loss_acc = loss_acc + loss.detach()
+            host_lab.copy_(res["labels"], non_blocking=True)
+            free[cur].record(main)
+        packed = torch.cat([sci.kernel.grad, cci.kernel.grad.flatten(), rbf.kernel.grad, loss_acc[None]])
+        if world > 1:
+            dist.all_reduce(packed)
+        host_out.copy_(packed, non_blocking=True)
+        main.synchronize()
+
+    for _ in range(2):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    n = max(2, args.steps // 2)
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(main)
+    for _ in range(n):
+        step()
+    e1.record(main)
+    torch.cuda.synchronize(dev)
+    wall = time.perf_counter() - t0
+    ms = max(e0.elapsed_time(e1), wall * 1e3)
+    t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    per_step = float(t_ms) / n
+    enc = n_chunks * Bc
+    return {"value": round(world * enc / (per_step * 1e-3), 1), "unit": "encounters/s",
+            "h2d_bytes_per_step": int(enc * 4 * C * T * 4), "d2h_bytes_per_step": int(enc * 4 + host_out.numel() * 4),
+            "encounters_per_step_per_gpu": enc, "chunk": Bc, "ms_per_step": round(per_step, 3),
+            "path": "pinned host x -> H2D (copy stream, double buffered) -> SingleChannelInterp/CrossChannelInterp/RBF "
+                    "modules (autograd fwd+bwd) + dec_kl_step -> D2H labels, loss, parameter grads"}
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        steps, warmup = max(1, args.steps), max(1, min(args.warmup, 2))
+        v, dt, cores = cpu_arm(args.cpu_sample, steps, warmup)
+        line = {"impl": "reference", "metric": "encounters/s (interp fwd+bwd + DEC assign)", "value": round(v, 1),
+                "unit": "encounters/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+                "ms_per_step": round(dt * 1e3, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": CFG_NAME, "vitals": C, "max_obs": T, "ref_points": R, "hours": HOURS,
+                           "latent_dim": D_LAT, "clusters": K_CLUST},
+                "cpu_baseline": {"value": round(v, 1), "unit": "encounters/s", "cores": cores, "kind": "port",
+                                 "sample": f"each step = {args.cpu_sample} encounters of the c2 shape (bounded sample; the "
+                                           "reference's (B,C,T,R) temporaries cap its batch) through oracle/ref_port.py, the "
+                                           "torch-CPU restatement of the reference (the reference itself is Python and does not "
+                                           "travel to the GPU box)"},
+                "e2e": {"value": round(v, 1), "unit": "encounters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line), flush=True)
+        return
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        sys.stderr.write(f"--gpus {args.gpus} needs torchrun with {args.gpus} ranks; running 1 rank\n")
+    line = device_arm(args, rank, world, local_rank)
+    if line is not None:
+        print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

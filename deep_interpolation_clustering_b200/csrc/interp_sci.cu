@@ -13,8 +13,10 @@
 //   * rows are staged with one TMA bulk copy and canonicalised (interp_stage.cuh);
 //   * the softmax shift is known without a pass over the data: the maximum of s_t is at the
 //     observation nearest to r, found by binary search in the sorted times (d*);
-//   * the exponent is evaluated as -(alpha log2 e) (d - d*)(d + d* - 2r), the exact
-//     difference of squares, so no large squares are subtracted;
+//   * the exponent -(alpha log2 e) ((d-r)^2 - (d*-r)^2) is formed as fma(delta, delta, -hi) - lo
+//     with (d*-r)^2 = hi + lo carried as an exact two-float: the difference of squares is
+//     rounded once, so the high-pass weight e^10 stays ~30x closer to the float64 truth than the
+//     reference's own float32 evaluation (which subtracts numbers in the hundreds);
 //   * ONE MUFU.EX2 per (t, r): the high-pass weight is e^10 (4 FMULs) because both filters
 //     share the shift;
 //   * accumulators stay in registers, each lane owns RPT grid points, observations are
@@ -49,19 +51,23 @@ static size_t sci_smem_bytes(int C, int Tp, int R) {
 }
 
 // Stage + canonicalise one encounter.  After return (CTA-synchronised):
-//   rows[0][c] = m*x, rows[1][c] = m, rows[2][c] = d, all compacted+sorted+padded; n_valid[c].
+//   rows[0][c] = m*x (forward) or x (backward), rows[1][c] = m, rows[2][c] = d, all
+//   compacted+sorted+padded; n_valid[c] = count, negated when some kept weight is not exactly 1.
 __device__ __forceinline__ void sci_stage(const SciSmem& s, const float* xb, int C, int T, int Tp,
-                                          bool use_tma) {
+                                          bool use_tma, bool fold_mask) {
   stage_rows(s.rows, xb, 3 * C, T, Tp, s.bar, use_tma);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   for (int c = warp; c < C; c += nwarps) {
     float* sx = s.rows + (0 * C + c) * Tp;
     float* sm = s.rows + (1 * C + c) * Tp;
     float* sd = s.rows + (2 * C + c) * Tp;
-    const int n = warp_compact3(sx, sm, sd, T, lane, /*fold_mask_into_r0=*/true);
+    const int n = warp_compact3(sx, sm, sd, T, lane, fold_mask);
     warp_sort3(sd, sx, sm, n, lane);
+    int weighted = 0;
+    for (int t = lane; t < n; t += 32) weighted |= (sm[t] != 1.0f);
+    weighted = __any_sync(0xffffffffu, weighted);
     warp_pad4(sd, sx, sm, n, lane);
-    if (lane == 0) s.n_valid[c] = n;
+    if (lane == 0) s.n_valid[c] = weighted ? -n : n;
   }
   __syncthreads();
 }
@@ -74,7 +80,7 @@ sci_fwd_kernel(const float* __restrict__ x, const float* __restrict__ kernel,
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const SciSmem s = sci_carve(smem_raw, C, Tp);
   const int64_t b = blockIdx.x;
-  sci_stage(s, x + b * (int64_t)(4 * C) * T, C, T, Tp, use_tma != 0);
+  sci_stage(s, x + b * (int64_t)(4 * C) * T, C, T, Tp, use_tma != 0, /*fold_mask=*/true);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int chunks = (R + 32 * RPT - 1) / (32 * RPT);
@@ -86,20 +92,22 @@ sci_fwd_kernel(const float* __restrict__ x, const float* __restrict__ kernel,
     const float* sx = s.rows + (0 * C + c) * Tp;
     const float* sm = s.rows + (1 * C + c) * Tp;
     const float* sd = s.rows + (2 * C + c) * Tp;
-    const int n = s.n_valid[c];
+    const int n = abs(s.n_valid[c]);
     const float alpha = softplus_ref(__ldg(kernel + c));
     const float a = alpha * kLog2e;
 
     int ridx[RPT];
-    float rr[RPT], dstar[RPT], cr[RPT], s1[RPT], sy[RPT], s10[RPT], sy10[RPT];
+    float rr[RPT], nhi[RPT], nlo[RPT], s1[RPT], sy[RPT], s10[RPT], sy10[RPT];
 #pragma unroll
     for (int k = 0; k < RPT; ++k) {
       ridx[k] = chunk * 32 * RPT + k * 32 + lane;
       rr[k] = __ldg(ref_t + min(ridx[k], R - 1));
-      dstar[k] = n > 0 ? sd[nearest_sorted(sd, n, rr[k])] : 0.f;
-      cr[k] = a * (2.f * rr[k] - dstar[k]);
+      const float dst = (n > 0 ? sd[nearest_sorted(sd, n, rr[k])] : 0.f) - rr[k];   // delta* = d* - r
+      nhi[k] = dst * dst;
+      nlo[k] = fmaf(dst, dst, -nhi[k]);        // exact residual: delta*^2 = nhi + nlo
       s1[k] = sy[k] = s10[k] = sy10[k] = 0.f;
     }
+    const float na = -a;
     const int n4 = (n + 3) & ~3;
     for (int t0 = 0; t0 < n4; t0 += 4) {
       const float4 d4 = *reinterpret_cast<const float4*>(sd + t0);
@@ -112,9 +120,9 @@ sci_fwd_kernel(const float* __restrict__ x, const float* __restrict__ kernel,
       for (int j = 0; j < 4; ++j) {
 #pragma unroll
         for (int k = 0; k < RPT; ++k) {
-          const float uu = dd[j] - dstar[k];
-          const float vv = fmaf(-a, dd[j], cr[k]);
-          const float e = ex2_approx(uu * vv);
+          const float dl = dd[j] - rr[k];
+          const float tt = fmaf(dl, dl, -nhi[k]) - nlo[k];      // (d-r)^2 - (d*-r)^2 >= 0
+          const float e = ex2_approx(tt * na);
           const float e2 = e * e, e4 = e2 * e2, e8 = e4 * e4, e10 = e8 * e2;
           s1[k] = fmaf(mm[j], e, s1[k]);
           sy[k] = fmaf(xx[j], e, sy[k]);
@@ -128,8 +136,7 @@ sci_fwd_kernel(const float* __restrict__ x, const float* __restrict__ kernel,
       if (ridx[k] < R) {
         float y, w, y10;
         if (n > 0) {
-          const float dr = dstar[k] - rr[k];
-          w = logf(s1[k]) - alpha * dr * dr;
+          w = logf(s1[k]) - alpha * nhi[k];
           y = sy[k] / s1[k];
           y10 = sy10[k] / s10[k];
         } else {  // all-masked channel: the reference yields -inf / NaN (logsumexp of -inf)
@@ -149,9 +156,72 @@ sci_fwd_kernel(const float* __restrict__ x, const float* __restrict__ kernel,
 }
 
 // Backward: d/d alpha_c = sum_{t,r} -n_tr (ds_t + 10 ds'_t)   (Appendix A.1), with
-//   ds_t  = e   (mx A  + m B ),  A  = gy /S1,       B  = (gw - y gy)/S1
-//   ds'_t = e10 (mx A' + m B'),  A' = gy'/S10,      B' = -y' gy'/S10
-// and n_tr = nmin - arg/a.  Writes one partial per (encounter, vital).
+//   ds_t  = m e   ((x - y ) A  + B),  A  = gy /S1,  B = gw/S1
+//   ds'_t = m e10 ((x - y') A')    ,  A' = gy'/S10
+// and n_tr = (d_t - r)^2.  (x - y) is formed first: when one observation dominates, y ~ x_t and
+// x A - y A would cancel catastrophically (measured 9e-5 relative on d kernel; 5e-6 this way).
+template <int RPT, bool WEIGHTED>
+__device__ __forceinline__ float sci_bwd_task(const float* __restrict__ sx, const float* __restrict__ sm,
+                                              const float* __restrict__ sd, int n, float a, int chunk,
+                                              int lane, int c, int C, int R,
+                                              const float* __restrict__ ref_t, const float* __restrict__ ub,
+                                              const float* __restrict__ gb, const float* __restrict__ sb) {
+  const float na = -a;
+  float rr[RPT], nhi[RPT], nlo[RPT], yy[RPT], yy10[RPT], A[RPT], Bc[RPT], A10[RPT], acc[RPT];
+#pragma unroll
+  for (int k = 0; k < RPT; ++k) {
+    const int r = chunk * 32 * RPT + k * 32 + lane;
+    const bool live = r < R;
+    const int rc = min(r, R - 1);
+    rr[k] = __ldg(ref_t + rc);
+    const float dst = sd[nearest_sorted(sd, n, rr[k])] - rr[k];
+    nhi[k] = dst * dst;
+    nlo[k] = fmaf(dst, dst, -nhi[k]);
+    yy[k] = ub[(0 * C + c) * R + rc];
+    yy10[k] = ub[(2 * C + c) * R + rc];
+    const float gy = live ? gb[(0 * C + c) * R + rc] : 0.f;
+    const float gw = live ? gb[(1 * C + c) * R + rc] : 0.f;
+    const float gy10 = live ? gb[(2 * C + c) * R + rc] : 0.f;
+    const float i1 = 1.0f / sb[(0 * C + c) * R + rc];
+    const float i10 = 10.0f / sb[(1 * C + c) * R + rc];
+    A[k] = gy * i1;
+    Bc[k] = gw * i1;
+    A10[k] = gy10 * i10;
+    acc[k] = 0.f;
+  }
+  const int n4 = (n + 3) & ~3;
+  for (int t0 = 0; t0 < n4; t0 += 4) {
+    const float4 d4 = *reinterpret_cast<const float4*>(sd + t0);
+    const float4 x4 = *reinterpret_cast<const float4*>(sx + t0);
+    const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
+    const float xx[4] = {x4.x, x4.y, x4.z, x4.w};
+    float mm[4] = {1.f, 1.f, 1.f, 1.f};
+    if (WEIGHTED || t0 + 4 > n) {       // padding entries carry weight 0
+      const float4 m4 = *reinterpret_cast<const float4*>(sm + t0);
+      mm[0] = m4.x; mm[1] = m4.y; mm[2] = m4.z; mm[3] = m4.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+      for (int k = 0; k < RPT; ++k) {
+        const float dl = dd[j] - rr[k];
+        const float tt = fmaf(dl, dl, -nhi[k]) - nlo[k];
+        const float e = ex2_approx(tt * na);
+        const float e2 = e * e, e4 = e2 * e2, e8 = e4 * e4, e10 = e8 * e2;
+        const float g1 = fmaf(xx[j] - yy[k], A[k], Bc[k]);
+        const float g10 = (xx[j] - yy10[k]) * A10[k];
+        float h = fmaf(e10, g10, e * g1);
+        if (WEIGHTED || t0 + 4 > n) h *= mm[j];
+        acc[k] = fmaf(tt + nhi[k], h, acc[k]);             // n_tr = (n - nmin) + nmin
+      }
+    }
+  }
+  float tot = 0.f;
+#pragma unroll
+  for (int k = 0; k < RPT; ++k) tot += acc[k];
+  return warp_sum(tot);
+}
+
 template <int RPT>
 __global__ void __launch_bounds__(kMaxWarps * 32)
 sci_bwd_kernel(const float* __restrict__ x, const float* __restrict__ kernel,
@@ -161,7 +231,7 @@ sci_bwd_kernel(const float* __restrict__ x, const float* __restrict__ kernel,
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const SciSmem s = sci_carve(smem_raw, C, Tp);
   const int64_t b = blockIdx.x;
-  sci_stage(s, x + b * (int64_t)(4 * C) * T, C, T, Tp, use_tma != 0);
+  sci_stage(s, x + b * (int64_t)(4 * C) * T, C, T, Tp, use_tma != 0, /*fold_mask=*/false);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int chunks = (R + 32 * RPT - 1) / (32 * RPT);
@@ -174,64 +244,12 @@ sci_bwd_kernel(const float* __restrict__ x, const float* __restrict__ kernel,
     const float* sx = s.rows + (0 * C + c) * Tp;
     const float* sm = s.rows + (1 * C + c) * Tp;
     const float* sd = s.rows + (2 * C + c) * Tp;
-    const int n = s.n_valid[c];
+    const int nv = s.n_valid[c];
     float tot = 0.f;
-    if (n > 0) {  // an all-masked channel contributes nothing (the reference's grad is NaN there)
-      const float alpha = softplus_ref(__ldg(kernel + c));
-      const float a = alpha * kLog2e;
-      const float inv_a = 1.0f / a;
-
-      float dstar[RPT], cr[RPT], nmin[RPT], A[RPT], Bc[RPT], A10[RPT], B10[RPT], acc[RPT];
-#pragma unroll
-      for (int k = 0; k < RPT; ++k) {
-        const int r = chunk * 32 * RPT + k * 32 + lane;
-        const bool live = r < R;
-        const int rc = min(r, R - 1);
-        const float rr = __ldg(ref_t + rc);
-        dstar[k] = sd[nearest_sorted(sd, n, rr)];
-        cr[k] = a * (2.f * rr - dstar[k]);
-        const float dr = dstar[k] - rr;
-        nmin[k] = dr * dr;
-        const float y = ub[(0 * C + c) * R + rc], y10 = ub[(2 * C + c) * R + rc];
-        const float gy = live ? gb[(0 * C + c) * R + rc] : 0.f;
-        const float gw = live ? gb[(1 * C + c) * R + rc] : 0.f;
-        const float gy10 = live ? gb[(2 * C + c) * R + rc] : 0.f;
-        const float i1 = 1.0f / sb[(0 * C + c) * R + rc];
-        const float i10 = 10.0f / sb[(1 * C + c) * R + rc];
-        A[k] = gy * i1;
-        Bc[k] = (gw - y * gy) * i1;
-        A10[k] = gy10 * i10;
-        B10[k] = -y10 * gy10 * i10;
-        acc[k] = 0.f;
-      }
-      const int n4 = (n + 3) & ~3;
-      for (int t0 = 0; t0 < n4; t0 += 4) {
-        const float4 d4 = *reinterpret_cast<const float4*>(sd + t0);
-        const float4 x4 = *reinterpret_cast<const float4*>(sx + t0);
-        const float4 m4 = *reinterpret_cast<const float4*>(sm + t0);
-        const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
-        const float xx[4] = {x4.x, x4.y, x4.z, x4.w};
-        const float mm[4] = {m4.x, m4.y, m4.z, m4.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-#pragma unroll
-          for (int k = 0; k < RPT; ++k) {
-            const float uu = dd[j] - dstar[k];
-            const float vv = fmaf(-a, dd[j], cr[k]);
-            const float arg = uu * vv;
-            const float e = ex2_approx(arg);
-            const float e2 = e * e, e4 = e2 * e2, e8 = e4 * e4, e10 = e8 * e2;
-            const float g1 = fmaf(xx[j], A[k], mm[j] * Bc[k]);
-            const float g10 = fmaf(xx[j], A10[k], mm[j] * B10[k]);
-            const float h = fmaf(e10, g10, e * g1);
-            const float nn = fmaf(arg, -inv_a, nmin[k]);
-            acc[k] = fmaf(nn, h, acc[k]);
-          }
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < RPT; ++k) tot += acc[k];
-      tot = warp_sum(tot);
+    if (nv != 0) {   // an all-masked channel contributes nothing (the reference's grad is NaN there)
+      const float a = softplus_ref(__ldg(kernel + c)) * kLog2e;
+      tot = nv < 0 ? sci_bwd_task<RPT, true>(sx, sm, sd, -nv, a, chunk, lane, c, C, R, ref_t, ub, gb, sb)
+                   : sci_bwd_task<RPT, false>(sx, sm, sd, nv, a, chunk, lane, c, C, R, ref_t, ub, gb, sb);
     }
     if (lane == 0) s.part[task] = tot;
   }

@@ -12,7 +12,7 @@ import torch
 from . import _lib
 
 __all__ = ["sci", "cci", "rbf_readout", "dec_soft_assign", "dec_target_distribution",
-           "dec_kl_step", "colsum"]
+           "dec_assign", "dec_kl_from_colsum", "dec_kl_step", "colsum"]
 
 
 def _require_cuda_f32(t, name):
@@ -230,14 +230,30 @@ def dec_target_distribution(q, colsum_f64=None):
 
 
 @torch.no_grad()
-def dec_kl_step(z, mu, alpha=1.0, weight=1.0, batch=None, colsum_f64=None, want_p=True, want_grad_z=True):
-    """Fused DEC step (no autograd graph): q column sum -> p, KL, closed-form gradients.
+def dec_assign(z, mu, alpha=1.0):
+    """Stage 1 of the fused DEC step: q (B,K), hard labels argmax_j q (B, int32) and the local
+    column sum f_j = sum_i q_ij (K, float64) in one pass over z."""
+    _require_cuda_f32(z, "batch")
+    _require_cuda_f32(mu, "cluster_centers")
+    z, mu = z.contiguous(), mu.contiguous()
+    B, D = z.shape
+    K = mu.shape[0]
+    L = _lib.lib()
+    with torch.cuda.device(z.device):
+        q = torch.empty((B, K), dtype=torch.float32, device=z.device)
+        labels = torch.empty(B, dtype=torch.int32, device=z.device)
+        f = torch.empty(K, dtype=torch.float64, device=z.device)
+        ws = _ws(L.dic_dec_workspace_bytes(K, D), z.device)
+        _lib.check(L.dic_dec_q_fwd(_lib.ptr(z), _lib.ptr(mu), _lib.ptr(q), _lib.ptr(labels), _lib.ptr(f),
+                                   _lib.ptr(ws), B, D, K, float(alpha), _lib.current_stream(z.device)),
+                   "dic_dec_q_fwd")
+    return dict(q=q, labels=labels, colsum=f)
 
-    Returns dict(q, labels, colsum, p, kl, grad_z, grad_mu) where ``kl`` is the
-    'batchmean' KL (sum / batch) times ``weight`` and the gradients are of that value.
-    ``colsum_f64`` lets a caller supply the all-reduced column sum of a sharded batch;
-    ``batch`` is the global batch size for the 1/B factor.
-    """
+
+@torch.no_grad()
+def dec_kl_from_colsum(z, mu, colsum_f64, alpha=1.0, weight=1.0, batch=None, want_p=True, want_grad_z=True):
+    """Stage 2: p = target(q) with the given (global) column sum, the 'batchmean' KL times
+    ``weight`` and its closed-form gradients wrt z and mu."""
     _require_cuda_f32(z, "batch")
     _require_cuda_f32(mu, "cluster_centers")
     z, mu = z.contiguous(), mu.contiguous()
@@ -245,21 +261,29 @@ def dec_kl_step(z, mu, alpha=1.0, weight=1.0, batch=None, colsum_f64=None, want_
     K = mu.shape[0]
     Bg = B if batch is None else int(batch)
     L = _lib.lib()
+    f = colsum_f64.to(device=z.device, dtype=torch.float64).contiguous()
     with torch.cuda.device(z.device):
-        st = _lib.current_stream(z.device)
-        q = torch.empty((B, K), dtype=torch.float32, device=z.device)
-        labels = torch.empty(B, dtype=torch.int32, device=z.device)
-        f = torch.empty(K, dtype=torch.float64, device=z.device)
         ws = _ws(L.dic_dec_workspace_bytes(K, D), z.device)
-        _lib.check(L.dic_dec_q_fwd(_lib.ptr(z), _lib.ptr(mu), _lib.ptr(q), _lib.ptr(labels), _lib.ptr(f),
-                                   _lib.ptr(ws), B, D, K, float(alpha), st), "dic_dec_q_fwd")
-        if colsum_f64 is not None:
-            f = colsum_f64.to(device=z.device, dtype=torch.float64).contiguous()
-        p = torch.empty_like(q) if want_p else None
+        p = torch.empty((B, K), dtype=torch.float32, device=z.device) if want_p else None
         kl = torch.empty(1, dtype=torch.float64, device=z.device)
         gz = torch.empty_like(z) if want_grad_z else None
         gmu = torch.empty_like(mu)
         _lib.check(L.dic_dec_kl_fwd_bwd(_lib.ptr(z), _lib.ptr(mu), _lib.ptr(f), _lib.ptr(p), _lib.ptr(kl),
                                         _lib.ptr(gz), _lib.ptr(gmu), _lib.ptr(ws), B, D, K, float(alpha),
-                                        float(weight) / Bg, st), "dic_dec_kl_fwd_bwd")
-    return dict(q=q, labels=labels, colsum=f, p=p, kl=kl * (float(weight) / Bg), grad_z=gz, grad_mu=gmu)
+                                        float(weight) / Bg, _lib.current_stream(z.device)), "dic_dec_kl_fwd_bwd")
+    return dict(p=p, kl=kl * (float(weight) / Bg), grad_z=gz, grad_mu=gmu)
+
+
+def dec_kl_step(z, mu, alpha=1.0, weight=1.0, batch=None, colsum_f64=None, want_p=True, want_grad_z=True):
+    """Fused DEC step (no autograd graph): q + column sum -> p, KL, closed-form gradients.
+
+    Returns dict(q, labels, colsum, p, kl, grad_z, grad_mu) where ``kl`` is the 'batchmean' KL
+    (sum / batch) times ``weight`` and the gradients are of that value.  ``colsum_f64`` lets a
+    caller supply the all-reduced column sum of a sharded batch; ``batch`` is the global batch
+    size for the 1/B factor.
+    """
+    out = dec_assign(z, mu, alpha)
+    f = out["colsum"] if colsum_f64 is None else colsum_f64
+    out.update(dec_kl_from_colsum(z, mu, f, alpha, weight, batch, want_p, want_grad_z))
+    out["colsum"] = f
+    return out

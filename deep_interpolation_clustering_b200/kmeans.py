@@ -21,6 +21,7 @@ import numbers
 
 import numpy as np
 import torch
+import torch.distributed as dist
 
 from . import _lib
 
@@ -46,6 +47,36 @@ def _same_clustering(a, b, K):
     b = np.asarray(b, np.int64)
     pairs = np.unique(a * K + b)
     return len(np.unique(pairs // K)) == len(pairs)
+
+
+class _Comm:
+    """The exchange steps of a row-sharded fit (identity when there is a single rank)."""
+
+    def __init__(self, group):
+        self.group = group
+        self.on = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        self.rank = dist.get_rank(group) if self.on else 0
+        self.size = dist.get_world_size(group) if self.on else 1
+
+    def sum_(self, *tensors):
+        """In-place all-reduce(sum) of several tensors as ONE packed float64 message."""
+        if not self.on:
+            return
+        flat = torch.cat([t.reshape(-1).to(torch.float64) for t in tensors])
+        dist.all_reduce(flat, group=self.group)
+        off = 0
+        for t in tensors:
+            n = t.numel()
+            t.copy_(flat[off:off + n].view_as(t).to(t.dtype))
+            off += n
+
+    def gather(self, t):
+        """All-gather of equally shaped tensors -> stacked (size, ...)."""
+        if not self.on:
+            return t[None]
+        out = [torch.empty_like(t) for _ in range(self.size)]
+        dist.all_gather(out, t.contiguous(), group=self.group)
+        return torch.stack(out)
 
 
 class _Device:
@@ -86,10 +117,18 @@ class _Device:
 
 
 class KMeansB200:
-    """K-means on a B200; drop-in for ``sklearn.cluster.KMeans`` as the reference uses it."""
+    """K-means on a B200; drop-in for ``sklearn.cluster.KMeans`` as the reference uses it.
+
+    ``process_group``: when given (or when torch.distributed is initialised and
+    ``sharded=True``), X holds only this rank's ROWS; every rank must pass the same
+    ``random_state`` seed / init.  The exchange steps are: global mean and variance, k-means++
+    potentials and candidate rows, and ONE packed all-reduce of [sums | counts | stats] per Lloyd
+    iteration.  ``labels_`` then covers the local rows; centres and inertia are global.
+    """
 
     def __init__(self, n_clusters=8, *, init="k-means++", n_init="auto", max_iter=300, tol=1e-4, verbose=0,
-                 random_state=None, copy_x=True, algorithm="lloyd", device=None):
+                 random_state=None, copy_x=True, algorithm="lloyd", device=None, sharded=False,
+                 process_group=None, _backend=None):
         self.n_clusters = n_clusters
         self.init = init
         self.n_init = n_init
@@ -100,9 +139,14 @@ class KMeansB200:
         self.copy_x = copy_x
         self.algorithm = algorithm
         self.device = device
+        self.sharded = sharded or process_group is not None
+        self.process_group = process_group
+        self._backend = _backend            # test hook: a CPU stand-in for _Device (gloo tests)
 
     # ---- helpers ---------------------------------------------------------------------------
     def _device(self):
+        if self._backend is not None:
+            return torch.device("cpu")
         if not torch.cuda.is_available():
             raise RuntimeError("KMeansB200 needs a CUDA device: there is no CPU fallback")
         return torch.device(self.device) if self.device is not None else torch.device("cuda", torch.cuda.current_device())
@@ -122,51 +166,92 @@ class KMeansB200:
             raise ValueError(f"Expected 2D array, got {X.dim()}D array instead")
         return X.contiguous()
 
+    def _state(self, X, K):
+        return (self._backend or _Device)(X, K)
+
     def _n_init(self):
         if self.n_init == "auto":
             return 1 if (isinstance(self.init, str) and self.init == "k-means++") or not isinstance(self.init, str) else 10
         return int(self.n_init)
 
-    def _kmeans_plusplus(self, st, rng):
+    def _rows(self, st, comm, idx_global, offset):
+        """Rows of the GLOBAL matrix by global index: owners contribute, the rest add zeros."""
+        idx = idx_global - offset
+        mine = (idx >= 0) & (idx < st.N)
+        rows = torch.zeros((idx.numel(), st.D), dtype=st.X.dtype, device=st.dev)
+        if bool(mine.any()) or not comm.on:
+            rows[mine] = st.X[idx[mine]]
+        comm.sum_(rows)
+        return rows
+
+    def _kmeans_plusplus(self, st, rng, comm, n_global, offset):
         """sklearn/cluster/_kmeans.py:224-281 on device; the RandomState is consumed in the same
         order and quantity as sklearn does (choice, then uniform(size=trials) per centre)."""
         K, N = self.n_clusters, st.N
         trials = 2 + int(np.log(K))
         centers = torch.empty((K, st.D), dtype=st.X.dtype, device=st.dev)
-        first = int(rng.choice(N, p=np.full(N, 1.0 / N))) if N < (1 << 22) else int(rng.randint(N))
-        centers[0] = st.X[first]
+        first = int(rng.choice(n_global, p=np.full(n_global, 1.0 / n_global)))
+        centers[0] = self._rows(st, comm, torch.tensor([first], device=st.dev), offset)[0]
         closest = torch.empty(N, dtype=st.X.dtype, device=st.dev)
-        pot = st.min_d2(centers[0:1], None, closest)[0]
+        pot = st.min_d2(centers[0:1], None, closest)
+        comm.sum_(pot)
+        pot = pot[0]
         for c in range(1, K):
             rv = torch.from_numpy(rng.uniform(size=trials)).to(st.dev) * pot
             cum = torch.cumsum(closest.to(torch.float64), 0)
-            cand = torch.searchsorted(cum, rv).clamp_(max=N - 1)
-            pots = st.min_d2(st.X[cand].contiguous(), closest, None)
+            if comm.on:      # global cumulative sum = local one + the totals of the lower ranks
+                totals = comm.gather(cum[-1:] if N else cum.new_zeros(1)).flatten()
+                base = totals[:comm.rank].sum()
+                below = torch.cumsum(totals, 0)
+                owner = torch.searchsorted(below, rv).clamp_(max=comm.size - 1)
+                local = torch.searchsorted(cum, rv - base).clamp_(max=max(N - 1, 0))
+                cand = torch.where(owner == comm.rank, local + offset, torch.full_like(local, -1))
+                cand_rows = self._rows(st, comm, cand, offset) if N else self._rows(st, comm, cand, offset)
+            else:
+                cand = torch.searchsorted(cum, rv).clamp_(max=N - 1)
+                cand_rows = st.X[cand].contiguous()
+            pots = st.min_d2(cand_rows, closest, None)
+            comm.sum_(pots)
             best = torch.argmin(pots)
-            centers[c] = st.X[cand[best]]
-            pot = st.min_d2(centers[c:c + 1], closest, closest)[0]
+            centers[c] = cand_rows[best]
+            pot = st.min_d2(centers[c:c + 1], closest, closest)
+            comm.sum_(pot)
+            pot = pot[0]
         return centers
 
-    def _relocate_empty(self, st, centers_old):
-        """sklearn _k_means_common.pyx:167-212 (rare path; torch ops on device)."""
+    def _relocate_empty(self, st, centers_old, comm):
+        """sklearn _k_means_common.pyx:167-212 (rare path; torch ops on device).  Sharded: every
+        rank offers its n_empty farthest rows, all ranks pick the same global winners and apply
+        the same corrections to the (already global) sums and counts."""
         empty = torch.nonzero(st.counts == 0).flatten()
         n_empty = int(empty.numel())
         if n_empty == 0:
             return
         lab = st.labels.long()
-        dist = ((st.X - centers_old[lab]) ** 2).sum(1)
-        if float(dist.max()) == 0.0:
+        dist2 = ((st.X - centers_old[lab]) ** 2).sum(1)
+        k = min(n_empty, st.N)
+        top = torch.topk(dist2, k)
+        cand_d = torch.full((n_empty,), -1.0, dtype=torch.float64, device=st.dev)
+        cand_lab = torch.zeros(n_empty, dtype=torch.float64, device=st.dev)
+        cand_row = torch.zeros((n_empty, st.D), dtype=torch.float64, device=st.dev)
+        cand_d[:k] = top.values.to(torch.float64)
+        cand_lab[:k] = lab[top.indices].to(torch.float64)
+        cand_row[:k] = st.X[top.indices].to(torch.float64)
+        all_d = comm.gather(cand_d).flatten()
+        all_lab = comm.gather(cand_lab).flatten()
+        all_row = comm.gather(cand_row).reshape(-1, st.D)
+        if float(all_d.max()) <= 0.0:
             return
-        far = torch.topk(dist, n_empty).indices           # farthest first, like argpartition[:-n-1:-1]
-        for new_id, idx in zip(empty.tolist(), far.tolist()):
-            old_id = int(lab[idx])
-            row = st.X[idx].to(torch.float64)
+        order = torch.argsort(all_d, descending=True, stable=True)[:n_empty]   # farthest first
+        for new_id, j in zip(empty.tolist(), order.tolist()):
+            old_id = int(all_lab[j])
+            row = all_row[j]
             st.sums[old_id] -= row
             st.sums[new_id] = row
             st.counts[new_id] = 1
             st.counts[old_id] -= 1
 
-    def _lloyd(self, st, centers, tol_eff):
+    def _lloyd(self, st, centers, tol_eff, comm):
         """One run of sklearn/cluster/_kmeans.py:630-757."""
         st.labels.fill_(-1)
         strict = False
@@ -174,9 +259,10 @@ class KMeansB200:
         for i in range(self.max_iter):
             n_iter = i + 1
             st.assign(centers, DIC_KM_COUNT_CHANGES)
+            comm.sum_(st.sums, st.counts, st.stats)          # the one exchange step per iteration
             changed, n_empty = st.stats[1], (st.counts == 0).sum()
             if int(n_empty) > 0:
-                self._relocate_empty(st, centers)
+                self._relocate_empty(st, centers, comm)
             cnt = st.counts.clamp(min=1.0)[:, None]
             new = torch.where(st.counts[:, None] > 0, st.sums / cnt, centers.to(torch.float64)).to(centers.dtype)
             shift2 = float(((new - centers).to(torch.float64) ** 2).sum())
@@ -190,8 +276,18 @@ class KMeansB200:
             st.assign(centers, DIC_KM_KEEP_LABELS, want_sums=False)
         else:
             st.assign(centers, 0, want_sums=False)
+        comm.sum_(st.stats)
         inertia = float(st.stats[0])
         return st.labels.clone(), inertia, centers, n_iter
+
+    def _same_as_best(self, labels, best_labels, K, comm):
+        if not comm.on:
+            return _same_clustering(labels.cpu().numpy(), best_labels.cpu().numpy(), K)
+        table = torch.zeros(K * K, dtype=torch.float64, device=labels.device)
+        table.index_add_(0, labels.long() * K + best_labels.long(), torch.ones(labels.numel(), dtype=torch.float64,
+                                                                               device=labels.device))
+        comm.sum_(table)
+        return bool(((table.view(K, K) > 0).sum(1) <= 1).all())
 
     # ---- sklearn API -------------------------------------------------------------------------
     def fit(self, X, y=None, sample_weight=None):
@@ -200,8 +296,15 @@ class KMeansB200:
         as_tensor = isinstance(X, torch.Tensor)
         X = self._to_device(X)
         K = int(self.n_clusters)
-        if X.shape[0] < K:
-            raise ValueError(f"n_samples={X.shape[0]} should be >= n_clusters={K}.")
+        comm = _Comm(self.process_group if self.sharded else None) if self.sharded else _Comm.__new__(_Comm)
+        if not self.sharded:
+            comm.group, comm.on, comm.rank, comm.size = None, False, 0, 1
+        n_local = torch.tensor([float(X.shape[0])], dtype=torch.float64, device=X.device)
+        counts_all = comm.gather(n_local).flatten()
+        n_global = int(counts_all.sum())
+        offset = int(counts_all[:comm.rank].sum())
+        if n_global < K:
+            raise ValueError(f"n_samples={n_global} should be >= n_clusters={K}.")
         rng = _check_random_state(self.random_state)
         init = self.init
         init_arr = None
@@ -212,16 +315,27 @@ class KMeansB200:
                                  f"the number of clusters {K} / features {X.shape[1]}.")
         elif init != "k-means++":
             raise NotImplementedError("init must be 'k-means++' or an array of centres")
-        mean = X.mean(dim=0)
+        if comm.on:
+            tot = X.sum(dim=0, dtype=torch.float64)
+            comm.sum_(tot)
+            mean = (tot / n_global).to(X.dtype)
+        else:
+            mean = X.mean(dim=0)
         Xc = X - mean                                                    # _kmeans.py:1487-1493
-        tol_eff = float(torch.var(Xc, dim=0, unbiased=False).mean()) * self.tol   # _kmeans.py:285-293
-        st = _Device(Xc, K)
+        if comm.on:
+            ss = (Xc.to(torch.float64) ** 2).sum(0)
+            s1 = Xc.sum(0, dtype=torch.float64)
+            comm.sum_(ss, s1)
+            var = ss / n_global - (s1 / n_global) ** 2
+            tol_eff = float(var.mean()) * self.tol
+        else:
+            tol_eff = float(torch.var(Xc, dim=0, unbiased=False).mean()) * self.tol   # _kmeans.py:285-293
+        st = self._state(Xc, K)
         best = None
         for _ in range(self._n_init()):
-            c0 = (init_arr - mean) if init_arr is not None else self._kmeans_plusplus(st, rng)
-            labels, inertia, centers, n_iter = self._lloyd(st, c0.contiguous(), tol_eff)
-            if best is None or (inertia < best[1] and not _same_clustering(labels.cpu().numpy(),
-                                                                           best[0].cpu().numpy(), K)):
+            c0 = (init_arr - mean) if init_arr is not None else self._kmeans_plusplus(st, rng, comm, n_global, offset)
+            labels, inertia, centers, n_iter = self._lloyd(st, c0.contiguous(), tol_eff, comm)
+            if best is None or (inertia < best[1] and not self._same_as_best(labels, best[0], K, comm)):
                 best = (labels, inertia, centers, n_iter)
         labels, inertia, centers, n_iter = best
         centers = centers + mean                                         # _kmeans.py:1543-1546
@@ -236,22 +350,26 @@ class KMeansB200:
     def fit_predict(self, X, y=None, sample_weight=None):
         return self.fit(X, sample_weight=sample_weight).labels_
 
+    def _centers_for(self, X):
+        c = self.cluster_centers_
+        c = c if isinstance(c, torch.Tensor) else torch.as_tensor(np.asarray(c))
+        return c.to(device=X.device, dtype=X.dtype).contiguous()
+
     def predict(self, X):
         if not hasattr(self, "cluster_centers_"):
             raise RuntimeError("This KMeansB200 instance is not fitted yet")
         as_tensor = isinstance(X, torch.Tensor)
         X = self._to_device(X)
-        centers = torch.as_tensor(np.asarray(self.cluster_centers_) if not isinstance(self.cluster_centers_, torch.Tensor)
-                                  else self.cluster_centers_).to(device=X.device, dtype=X.dtype).contiguous()
-        st = _Device(X, centers.shape[0])
+        centers = self._centers_for(X)
+        st = self._state(X, centers.shape[0])
         st.assign(centers, 0, want_sums=False)
         return st.labels if as_tensor else st.labels.cpu().numpy()
 
     def score_distortion(self, X):
-        """sum_i min_j ||x_i - c_j|| / N - the elbow distortion of p2_clustering_optK.py:261-264."""
+        """sum_i min_j ||x_i - c_j|| / N - the elbow distortion of p2_clustering_optK.py:261-264
+        (local rows only when sharded; all-reduce numerator and N yourself)."""
         X = self._to_device(X)
-        centers = torch.as_tensor(np.asarray(self.cluster_centers_) if not isinstance(self.cluster_centers_, torch.Tensor)
-                                  else self.cluster_centers_).to(device=X.device, dtype=X.dtype).contiguous()
-        st = _Device(X, centers.shape[0])
+        centers = self._centers_for(X)
+        st = self._state(X, centers.shape[0])
         st.assign(centers, 0, want_sums=False)
         return float(st.stats[2]) / X.shape[0]

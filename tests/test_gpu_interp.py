@@ -35,6 +35,15 @@ def _check(name, got, truth, rtol=RTOL_GRID):
     return record(name, got.detach().cpu().numpy(), truth, rtol, scale_atol(truth, rtol))
 
 
+def _check_groups(name, got, truth, C, rtol=RTOL_GRID):
+    """(B, R, 3C) outputs: the three channel groups have very different magnitudes (the
+    log-intensity w reaches hundreds), so each group gets its own RMS-scaled floor."""
+    got = got.detach().cpu().numpy()
+    for i, grp in enumerate(("a", "b", "c")):
+        sl = slice(i * C, (i + 1) * C)
+        record(f"{name}[{grp}]", got[..., sl], truth[..., sl], rtol, scale_atol(truth[..., sl], rtol))
+
+
 @pytest.mark.parametrize("case", CASES)
 def test_forward_matches_reference_f64(golden, case):
     g = golden(case)
@@ -47,8 +56,8 @@ def test_forward_matches_reference_f64(golden, case):
     assert s.stride() == (3 * C * R, 1, R)            # the reference's permuted view
     c = cci(s)
     r = rbf(torch.tensor(g["v"], device=dev), x)
-    _check(f"{case}/sci", s, g["sci_out_f64"])
-    _check(f"{case}/cci", c, g["cci_out_f64"])
+    _check_groups(f"{case}/sci", s, g["sci_out_f64"], C)
+    _check_groups(f"{case}/cci", c, g["cci_out_f64"], C)
     _check(f"{case}/rbf", r, g["rbf_out_f64"])
     # and within the float32 reference's own error of the shipped float32 numbers
     _check(f"{case}/sci_vs_f32ref", s, g["sci_out"], 1e-4)
@@ -69,7 +78,7 @@ def test_backward_matches_reference_f64(golden, case):
     r = rbf(v, x)
     (c * torch.tensor(g["g_cci"], device=dev)).sum().backward()
     (r * torch.tensor(g["g_rbf"], device=dev)).sum().backward()
-    _check(f"{case}/d_sci_out", s.grad, g["d_sci_out_f64"])
+    _check_groups(f"{case}/d_sci_out", s.grad, g["d_sci_out_f64"], g["x"].shape[1] // 4)
     _check(f"{case}/d_cci_kernel", cci.kernel.grad, g["d_cci_kernel_f64"])
     _check(f"{case}/d_sci_kernel", sci.kernel.grad, g["d_sci_kernel_f64"])
     _check(f"{case}/dv", v.grad, g["dv_f64"])
@@ -124,7 +133,7 @@ def test_config1_full_size_vs_oracle():
     m = x[:, C:2 * C]
     loss = ((rec * m - x[:, :C] * m) ** 2).sum() / (m == 1.0).sum()     # pretrain_interp.py:169-175
     ((c * torch.tensor(gc, device=dev)).sum() + loss).backward()
-    _check("c1/cci_out", c, c64)
+    _check_groups("c1/cci_out", c, c64, C)
     _check("c1/rbf_out", rec, r64)
     _check("c1/rec_loss", loss, loss64)
     _check("c1/d_sci_kernel", sci.kernel.grad, dk64)
@@ -212,7 +221,7 @@ def test_unsorted_and_weighted_masks_vs_oracle():
     sci.kernel.data = torch.tensor(p["sci_kernel"], device=dev)
     rbf.kernel.data = torch.tensor(p["rbf_kernel"], device=dev)
     x = torch.tensor(xn, device=dev)
-    _check("weighted/sci", sci(x), s64)
+    _check_groups("weighted/sci", sci(x), s64, C)
     _check("weighted/rbf", rbf(torch.tensor(vn, device=dev), x), r64)
     gs = rng.normal(size=s64.shape).astype(np.float32)
     dk64 = interp_oracle.sci_backward(xn.astype(np.float64), p["sci_kernel"].astype(np.float64), rt, C, gs)
