@@ -71,6 +71,32 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// Transposed butterfly: reduces KP per-lane values across the warp in log2(KP) halving steps
+// (KP/2 + KP/4 + ... shuffles) followed by plain xor steps; afterwards lane L holds the total of
+// value index L >> (5 - log2 KP).  KP is a power of two <= 32.
+template <int KP>
+__device__ __forceinline__ float warp_reduce_multi(float (&v)[KP], int lane) {
+  int n = KP;
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    if (n > 1) {
+      n >>= 1;
+      const bool up = (lane & off) != 0;
+#pragma unroll
+      for (int i = 0; i < (KP > 1 ? KP / 2 : 1); ++i) {
+        if (i < n) {
+          const float send = up ? v[i] : v[i + n];
+          const float keep = up ? v[i + n] : v[i];
+          v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+      }
+    } else {
+      v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
+    }
+  }
+  return v[0];
+}
+
 __device__ __forceinline__ float softplus_ref(float k) {
   // log(1 + exp(k)) with the plain formula of interpolation_layer.py:51 / rbf.py:78
   return logf(1.0f + expf(k));

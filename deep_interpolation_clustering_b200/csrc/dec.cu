@@ -23,29 +23,6 @@ namespace {
 constexpr int kDecWarps = 8;
 constexpr int kDecThreads = kDecWarps * 32;
 
-template <int KP>
-__device__ __forceinline__ float warp_reduce_multi(float (&v)[KP], int lane) {
-  int n = KP;
-#pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) {
-    if (n > 1) {
-      n >>= 1;
-      const bool up = (lane & off) != 0;
-#pragma unroll
-      for (int i = 0; i < (KP > 1 ? KP / 2 : 1); ++i) {
-        if (i < n) {
-          const float send = up ? v[i] : v[i + n];
-          const float keep = up ? v[i + n] : v[i];
-          v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-        }
-      }
-    } else {
-      v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
-    }
-  }
-  return v[0];
-}
-
 template <int KP> struct Log2 { static constexpr int v = 1 + Log2<KP / 2>::v; };
 template <> struct Log2<1> { static constexpr int v = 0; };
 

@@ -258,6 +258,221 @@ cci_bwd_kernel(const float* __restrict__ u, const float* __restrict__ kernel,
   }
 }
 
+// ---- warp-per-encounter variants (C <= 8: the reference's C is 6) ---------------------------
+// One warp owns one encounter, lane l owns reference points l, l+32, ...; every cross-thread
+// step is a shuffle reduction, so there is no block barrier and no shared-memory traffic on the
+// data path.  HBM-bound: ~1.1k warp instructions per encounter against 20.7 KB of traffic.
+constexpr int kCciWarps = 4;
+
+__device__ __forceinline__ void softmax_c8(const float* __restrict__ wrow /*ub + C*R + r*/, int C, int R,
+                                           float (&w)[8], float (&what)[8]) {
+  float wmax = -INFINITY;
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+    if (c < C) {
+      w[c] = wrow[c * R];
+      wmax = fmaxf(wmax, w[c]);
+    }
+  const float shift = (wmax == -INFINITY) ? 0.f : wmax;   // torch.logsumexp guards an all -inf row
+  float den = 0.f;
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+    if (c < C) {
+      what[c] = expf(w[c] - shift);
+      den += what[c];
+    }
+  const float inv_den = 1.0f / den;
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+    if (c < C) what[c] *= inv_den;
+}
+
+// Stages one encounter's (3C x R) tile(s) into this warp's slice of shared memory with 1-D TMA
+// bulk copies on a per-warp mbarrier: the loads of all warps of all resident CTAs are in flight
+// at once (>= 100 KB per SM), which is what an HBM-bound kernel with this little work needs.
+__device__ __forceinline__ const float* warp_tile_load(unsigned char* smem, int warp, int lane, int ntiles,
+                                                       const float* g0, const float* g1, uint32_t bytes) {
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem) + warp;
+  float* tile = reinterpret_cast<float*>(smem + 64 + (size_t)warp * ntiles * bytes);
+  if (lane == 0) {
+    mbar_init(bar, 1);
+    fence_proxy_async();
+  }
+  __syncwarp();
+  if (lane == 0) {
+    mbar_expect_tx(bar, bytes * ntiles);
+    bulk_g2s(tile, g0, bytes, bar);
+    if (ntiles > 1) bulk_g2s(reinterpret_cast<unsigned char*>(tile) + bytes, g1, bytes, bar);
+  }
+  mbar_wait(bar, 0);
+  return tile;
+}
+
+template <bool TILE>
+__global__ void __launch_bounds__(kCciWarps * 32)
+cci_fwd_warp_kernel(const float* __restrict__ u, const float* __restrict__ kernel, float* __restrict__ out,
+                    int64_t B, int C, int R) {
+  extern __shared__ __align__(128) unsigned char dyn_smem[];
+  __shared__ float sK[64];
+  for (int i = threadIdx.x; i < C * C; i += blockDim.x) sK[i] = __ldg(kernel + i);
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t b = (int64_t)blockIdx.x * kCciWarps + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const float* ub = u + b * (int64_t)(3 * C) * R;
+  if (TILE) ub = warp_tile_load(dyn_smem, threadIdx.x >> 5, lane, 1, ub, nullptr, (uint32_t)(3 * C * R) * 4u);
+  float* ob = out + b * (int64_t)(3 * C) * R;
+  float ybar[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) ybar[c] = 0.f;
+  for (int r = lane; r < R; r += 32) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      if (c < C) ybar[c] += ub[c * R + r];
+  }
+  const float invR = 1.0f / (float)R;
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+    if (c < C) ybar[c] = warp_sum(ybar[c]) * invR;
+  for (int r = lane; r < R; r += 32) {
+    float w[8], a[8];
+    softmax_c8(ub + C * R + r, C, R, w, a);
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      if (c < C) {
+        a[c] *= ub[c * R + r] - ybar[c];
+        ob[(C + c) * R + r] = expf(w[c]);                          // intensity, :104
+      }
+#pragma unroll
+    for (int cp = 0; cp < 8; ++cp)
+      if (cp < C) {
+        float z = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          if (c < C) z = fmaf(a[c], sK[c * C + cp], z);
+        z += ybar[cp];
+        ob[cp * R + r] = z;
+        ob[(2 * C + cp) * R + r] = ub[(2 * C + cp) * R + r] - z;   // transient minus smooth, :122-123
+      }
+  }
+}
+
+template <bool TILE>
+__global__ void __launch_bounds__(kCciWarps * 32)
+cci_bwd_warp_kernel(const float* __restrict__ u, const float* __restrict__ kernel,
+                    const float* __restrict__ grad_out, float* __restrict__ grad_u,
+                    float* __restrict__ partial /*(B, C*C)*/, int64_t B, int C, int R) {
+  extern __shared__ __align__(128) unsigned char dyn_smem[];
+  __shared__ float sK[64];
+  for (int i = threadIdx.x; i < C * C; i += blockDim.x) sK[i] = __ldg(kernel + i);
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t b = (int64_t)blockIdx.x * kCciWarps + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const float* ub = u + b * (int64_t)(3 * C) * R;
+  const float* gb = grad_out + b * (int64_t)(3 * C) * R;
+  if (TILE) {
+    ub = warp_tile_load(dyn_smem, threadIdx.x >> 5, lane, 2, ub, gb, (uint32_t)(3 * C * R) * 4u);
+    gb = ub + 3 * C * R;
+  }
+  float* dub = grad_u + b * (int64_t)(3 * C) * R;
+  const float invR = 1.0f / (float)R;
+
+  float ybar[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) ybar[c] = 0.f;
+  for (int r = lane; r < R; r += 32) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      if (c < C) ybar[c] += ub[c * R + r];
+  }
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+    if (c < C) ybar[c] = warp_sum(ybar[c]) * invR;
+
+  // pass A: dK products and the two means over r that dy needs
+  float acc0[32], acc1[32], means[16];        // dK rows 0-3 | rows 4-7 | [mean(what uu) | mean(gzt)]
+#pragma unroll
+  for (int i = 0; i < 32; ++i) acc0[i] = acc1[i] = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) means[i] = 0.f;
+  for (int r = lane; r < R; r += 32) {
+    float w[8], what[8], gzt[8];
+    softmax_c8(ub + C * R + r, C, R, w, what);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      gzt[c] = 0.f;
+      if (c < C) {
+        gzt[c] = gb[c * R + r] - gb[(2 * C + c) * R + r];
+        means[8 + c] += gzt[c];
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      if (c < C) {
+        float uu = 0.f;
+#pragma unroll
+        for (int cp = 0; cp < 8; ++cp)
+          if (cp < C) uu = fmaf(sK[c * C + cp], gzt[cp], uu);
+        means[c] = fmaf(what[c], uu, means[c]);
+        const float ac = what[c] * (ub[c * R + r] - ybar[c]);
+#pragma unroll
+        for (int cp = 0; cp < 8; ++cp) {
+          if (c < 4) acc0[c * 8 + cp] = fmaf(ac, gzt[cp], acc0[c * 8 + cp]);
+          else acc1[(c - 4) * 8 + cp] = fmaf(ac, gzt[cp], acc1[(c - 4) * 8 + cp]);
+        }
+      }
+  }
+  {
+    // lane l ends with dK[(l >> 3) (+4), l & 7]: one coalesced store per half
+    const float v0 = warp_reduce_multi<32>(acc0, lane);
+    const float v1 = warp_reduce_multi<32>(acc1, lane);
+    const int c0 = lane >> 3, cp = lane & 7;
+    float* pb = partial + b * (int64_t)(C * C);
+    if (c0 < C && cp < C) pb[c0 * C + cp] = v0;
+    if (c0 + 4 < C && cp < C) pb[(c0 + 4) * C + cp] = v1;
+  }
+  float m_wu[8], m_g[8];
+  {
+    const float v = warp_reduce_multi<16>(means, lane) * invR;    // lane l holds value l >> 1
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      m_wu[c] = __shfl_sync(0xffffffffu, v, c << 1);
+      m_g[c] = __shfl_sync(0xffffffffu, v, (8 + c) << 1);
+    }
+  }
+
+  // pass B: the gradients (rows are L1/L2 hot)
+  for (int r = lane; r < R; r += 32) {
+    float w[8], what[8], gzt[8], t[8], uu[8];
+    softmax_c8(ub + C * R + r, C, R, w, what);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      gzt[c] = 0.f;
+      if (c < C) gzt[c] = gb[c * R + r] - gb[(2 * C + c) * R + r];
+    }
+    float tw = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      if (c < C) {
+        float s = 0.f;
+#pragma unroll
+        for (int cp = 0; cp < 8; ++cp)
+          if (cp < C) s = fmaf(sK[c * C + cp], gzt[cp], s);
+        uu[c] = s;
+        t[c] = (ub[c * R + r] - ybar[c]) * s;
+        tw = fmaf(what[c], t[c], tw);
+      }
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      if (c < C) {
+        dub[c * R + r] = what[c] * uu[c] - m_wu[c] + m_g[c];
+        dub[(C + c) * R + r] = what[c] * (t[c] - tw) + expf(w[c]) * gb[(C + c) * R + r];
+        dub[(2 * C + c) * R + r] = gb[(2 * C + c) * R + r];
+      }
+  }
+}
+
 int check(const void* u, const void* kernel, int64_t B, int C, int R) {
   DIC_REQUIRE(u && kernel, DIC_ERR_INVALID_ARGUMENT, "null pointer argument");
   DIC_REQUIRE(B >= 0 && C > 0 && R > 0, DIC_ERR_INVALID_ARGUMENT, "bad sizes B=%lld C=%d R=%d",
@@ -279,8 +494,18 @@ extern "C" int dic_cci_fwd(const float* u, const float* kernel, float* out, int6
   DIC_REQUIRE(out, DIC_ERR_INVALID_ARGUMENT, "null output pointer");
   if (B == 0) return DIC_OK;
   cudaStream_t st = as_stream(stream);
-  if (C <= 8) cci_fwd_kernel<8><<<(unsigned)B, kCciThreads, 0, st>>>(u, kernel, out, C, R);
-  else cci_fwd_kernel<16><<<(unsigned)B, kCciThreads, 0, st>>>(u, kernel, out, C, R);
+  if (C <= 8) {
+    const unsigned grid = (unsigned)((B + kCciWarps - 1) / kCciWarps);
+    const size_t tile = (size_t)3 * C * R * 4;
+    const size_t smem = 64 + kCciWarps * tile;
+    if (tile % 16 == 0 && aligned16(u) && smem <= 100 * 1024) {
+      if (smem > 48 * 1024)
+        DIC_CUDA(cudaFuncSetAttribute(cci_fwd_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem));
+      cci_fwd_warp_kernel<true><<<grid, kCciWarps * 32, smem, st>>>(u, kernel, out, B, C, R);
+    } else
+      cci_fwd_warp_kernel<false><<<grid, kCciWarps * 32, 0, st>>>(u, kernel, out, B, C, R);
+  } else cci_fwd_kernel<16><<<(unsigned)B, kCciThreads, 0, st>>>(u, kernel, out, C, R);
   DIC_LAUNCH_CHECK("cci_fwd_kernel");
   return DIC_OK;
 }
@@ -306,9 +531,18 @@ extern "C" int dic_cci_bwd(const float* u, const float* kernel, const float* gra
   unsigned char* ws = static_cast<unsigned char*>(workspace);
   float* partial = reinterpret_cast<float*>(ws);
   double* red = reinterpret_cast<double*>(ws + ((size_t)B * C * C * sizeof(float) + 255) / 256 * 256);
-  if (C <= 8)
-    cci_bwd_kernel<8><<<(unsigned)B, kCciThreads, 0, st>>>(u, kernel, grad_out, grad_u, partial, C, R);
-  else
+  if (C <= 8) {
+    const unsigned grid = (unsigned)((B + kCciWarps - 1) / kCciWarps);
+    const size_t tile = (size_t)3 * C * R * 4, smem = 64 + kCciWarps * 2 * tile;
+    if (tile % 16 == 0 && aligned16(u) && aligned16(grad_out) && smem <= 100 * 1024) {
+      if (smem > 48 * 1024)
+        DIC_CUDA(cudaFuncSetAttribute(cci_bwd_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem));
+      cci_bwd_warp_kernel<true><<<grid, kCciWarps * 32, smem, st>>>(u, kernel, grad_out, grad_u, partial, B, C, R);
+    } else {
+      cci_bwd_warp_kernel<false><<<grid, kCciWarps * 32, 0, st>>>(u, kernel, grad_out, grad_u, partial, B, C, R);
+    }
+  } else
     cci_bwd_kernel<16><<<(unsigned)B, kCciThreads, 0, st>>>(u, kernel, grad_out, grad_u, partial, C, R);
   DIC_LAUNCH_CHECK("cci_bwd_kernel");
   return colsum_f32_launch(partial, nullptr, d_kernel, nullptr, red, B, C * C, st);

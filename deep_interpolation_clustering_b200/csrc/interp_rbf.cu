@@ -18,23 +18,45 @@ namespace dic {
 namespace {
 
 constexpr int kRbfFwdThreads = 256;
-constexpr int kMaxWarps = 16;
+constexpr int kMaxWarps = 8;
+
+// Window cut-off: a (t, r) pair whose basis value is below 2^-kRbfCut (9e-10) is skipped.  The
+// normaliser N_t is >= ~1 whenever the observation lies on the grid's span, so the relative
+// error of the truncation is < R * 1e-9.  Observations more than one hour outside the grid
+// span, and non-uniform grids, take the full range.
+constexpr float kRbfCut = 30.0f;
 
 __global__ void __launch_bounds__(kRbfFwdThreads)
 rbf_fwd_kernel(const float* __restrict__ v, const float* __restrict__ x,
                const float* __restrict__ kernel, const float* __restrict__ ref_t,
                float* __restrict__ rec, float* __restrict__ inv_norm, int C, int T, int R, int Rp) {
   extern __shared__ __align__(16) float smem[];
-  float2* srv = reinterpret_cast<float2*>(smem);     // [C][Rp] (r_j, v_cj); pad: (0, 0) never read
+  float2* srv = reinterpret_cast<float2*>(smem);     // [C][Rp] (r_j, v_cj); pad: (huge, 0) => e = 0
   float* snb = smem + 2 * C * Rp;                     // [C] -beta_c log2(e)
-  for (int c = threadIdx.x; c < C; c += blockDim.x) snb[c] = -softplus_ref(__ldg(kernel + c)) * kLog2e;
+  int* strip = reinterpret_cast<int*>(snb + C);       // [C] grid points per window (even)
+  const float r0 = __ldg(ref_t), rl = __ldg(ref_t + R - 1);
+  const float h = R > 1 ? (rl - r0) / (float)(R - 1) : 1.0f;
+  int irregular = !(h > 0.f);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float b2 = softplus_ref(__ldg(kernel + c)) * kLog2e;
+    snb[c] = -b2;
+    // window = +-sqrt(cut / (beta log2 e)) hours -> grid points, +2 points of slack each side
+    strip[c] = (2 * ((int)ceilf(sqrtf(kRbfCut / b2) / h) + 2) + 1) & ~1;
+  }
   const int64_t b = blockIdx.x;
   const float* vb = v + b * (int64_t)C * R;
   for (int i = threadIdx.x; i < C * Rp; i += blockDim.x) {
     const int c = i / Rp, j = i - c * Rp;
-    srv[i] = j < R ? make_float2(__ldg(ref_t + j), __ldg(vb + c * R + j)) : make_float2(0.f, 0.f);
+    if (j < R) {
+      const float rj = __ldg(ref_t + j);
+      irregular |= fabsf(rj - (r0 + h * (float)j)) > 0.01f * h;
+      srv[i] = make_float2(rj, __ldg(vb + c * R + j));
+    } else {
+      srv[i] = make_float2(3.0e18f, 0.f);
+    }
   }
-  __syncthreads();
+  irregular = __syncthreads_or(irregular);
+  const float inv_h = 1.0f / h;
   const float* mb = x + (b * (int64_t)(4 * C) + C) * T;       // mask plane rows
   const float* db = x + (b * (int64_t)(4 * C) + 2 * C) * T;   // time plane rows
   float* rb = rec + b * (int64_t)C * T;
@@ -47,23 +69,24 @@ rbf_fwd_kernel(const float* __restrict__ v, const float* __restrict__ x,
       const float d = __ldg(db + i);
       const float nb2 = snb[c];
       const float2* row = srv + c * Rp;
+      // Every lane walks the same number of grid points (swin[c] -> trip), starting at its own
+      // even offset: uniform trip count, no divergence, no union-of-windows penalty.
+      int jlo = 0, trip = Rp;
+      if (!irregular && d >= r0 - 1.0f && d <= rl + 1.0f) {
+        trip = min(Rp, strip[c]);
+        jlo = min(max(0, ((int)floorf((d - r0) * inv_h) - (trip >> 1) + 1) & ~1), Rp - trip);
+      }
       float N = 0.f, S = 0.f;
-      int j = 0;
-      for (; j + 2 <= R; j += 2) {
-        const float4 p = *reinterpret_cast<const float4*>(row + j);   // (r0, v0, r1, v1)
+      const float2* rw = row + jlo;
+#pragma unroll 2
+      for (int j = 0; j < trip; j += 2) {
+        const float4 p = *reinterpret_cast<const float4*>(rw + j);   // (r0, v0, r1, v1)
         const float d0 = d - p.x, d1 = d - p.z;
         const float e0 = ex2_approx(d0 * d0 * nb2), e1 = ex2_approx(d1 * d1 * nb2);
         N += e0;
         S = fmaf(e0, p.y, S);
         N += e1;
         S = fmaf(e1, p.w, S);
-      }
-      if (j < R) {
-        const float2 p = row[j];
-        const float d0 = d - p.x;
-        const float e0 = ex2_approx(d0 * d0 * nb2);
-        N += e0;
-        S = fmaf(e0, p.y, S);
       }
       // phi = m e  =>  N_ref = m N, sum phi v = m S
       inv = 1.0f / (m * N + 1e-10f);
@@ -78,6 +101,7 @@ struct RbfSmem {
   uint64_t* bar;
   float* rows;     // [3][C][Tp]: d | a' = m^2 g invN | a'S = m g invN rec
   int* n_valid;    // [C]
+  int* order;      // [C] vitals by descending count
   float* part;     // [C * ceil(R/32)]
 };
 
@@ -86,17 +110,20 @@ __device__ __forceinline__ RbfSmem rbf_carve(unsigned char* base, int C, int Tp)
   s.bar = reinterpret_cast<uint64_t*>(base);
   s.rows = reinterpret_cast<float*>(base + 16);
   s.n_valid = reinterpret_cast<int*>(s.rows + 3 * C * Tp);
-  s.part = reinterpret_cast<float*>(s.n_valid + C);
+  s.order = s.n_valid + C;
+  s.part = reinterpret_cast<float*>(s.order + C);
   return s;
 }
 
 static size_t rbf_bwd_smem_bytes(int C, int Tp, int R) {
-  return 16 + sizeof(float) * (3 * (size_t)C * Tp) + sizeof(int) * C +
+  return 16 + sizeof(float) * (3 * (size_t)C * Tp) + 2 * sizeof(int) * C +
          sizeof(float) * (size_t)C * ((R + 31) / 32);
 }
 
 // grad_v[c,r] = sum_t a'_t e_tr,  d beta_c = -sum_{t,r} n_tr e_tr (a'_t v_r - a'S_t)
 // with e_tr = exp(-beta n_tr), a'_t = m_t^2 g_t invN_t, a'S_t = m_t g_t invN_t rec_t.
+// Same structure as the SCI kernels: rows sorted by time, each lane owns RPT adjacent grid
+// points and walks only the observations within +-sqrt(kRbfCut / (beta log2 e)) hours of them.
 template <int RPT>
 __global__ void __launch_bounds__(kMaxWarps * 32)
 rbf_bwd_kernel(const float* __restrict__ v, const float* __restrict__ x,
@@ -112,52 +139,85 @@ rbf_bwd_kernel(const float* __restrict__ v, const float* __restrict__ x,
   const float* rb = rec + b * (int64_t)C * T;
   const float* nb = inv_norm + b * (int64_t)C * T;
   const float* gb = grad_rec + b * (int64_t)C * T;
-  float* sd = s.rows;
-  float* sa = s.rows + C * Tp;
-  float* sas = s.rows + 2 * C * Tp;
-  for (int i = threadIdx.x; i < C * T; i += blockDim.x) {
-    const int c = i / T, t = i - c * T;
-    const float m = __ldg(mb + i);
-    const float gi = __ldg(gb + i) * __ldg(nb + i) * m;
-    sd[c * Tp + t] = __ldg(db + i);
-    sa[c * Tp + t] = gi * m;
-    sas[c * Tp + t] = gi * __ldg(rb + i);
+  float* sd = s.rows;                 // times
+  float* sa = s.rows + C * Tp;        // mask first, then a'
+  float* sas = s.rows + 2 * C * Tp;   // a'S
+  for (int i = threadIdx.x; i < C * Tp; i += blockDim.x) {
+    const int c = i / Tp, t = i - c * Tp;
+    const bool in = t < T;
+    sd[i] = in ? __ldg(db + c * T + t) : 0.f;
+    sa[i] = in ? __ldg(mb + c * T + t) : 0.f;
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   for (int c = warp; c < C; c += nwarps) {
-    // drop observations that carry no gradient (masked, or zero upstream): keep a' != 0
-    const int n = warp_compact3(sas + c * Tp, sa + c * Tp, sd + c * Tp, T, lane, false);
-    warp_pad4(sd + c * Tp, sa + c * Tp, sas + c * Tp, n, lane);
+    float* rd = sd + c * Tp;
+    float* ra = sa + c * Tp;
+    float* ras = sas + c * Tp;
+    int n = warp_canonical_count(ra, rd, Tp, lane);
+    __syncwarp();
+    for (int t = lane; t < T; t += 32) {        // mask -> a', a'S (each lane rewrites its own slots)
+      const float m = ra[t];
+      const float gi = __ldg(gb + c * T + t) * __ldg(nb + c * T + t) * m;
+      ra[t] = gi * m;
+      ras[t] = gi * __ldg(rb + c * T + t);
+    }
+    __syncwarp();
+    if (n < 0) {   // general rows: keep entries that carry gradient (a' != 0), sort by time
+      n = warp_compact3(ras, ra, rd, T, lane, false);
+      warp_sort3(rd, ra, ras, n, lane);
+    }
+    warp_pad4_far(rd, ra, ras, n, lane);
     if (lane == 0) s.n_valid[c] = n;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int c = 0; c < C; ++c) {
+      const int key = s.n_valid[c];
+      int j = c;
+      while (j > 0 && s.n_valid[s.order[j - 1]] < key) {
+        s.order[j] = s.order[j - 1];
+        --j;
+      }
+      s.order[j] = c;
+    }
   }
   __syncthreads();
 
   const int chunks = (R + 32 * RPT - 1) / (32 * RPT);
+  const int ntasks = C * chunks;
   const float* vb = v + b * (int64_t)C * R;
   float* gvb = grad_v + b * (int64_t)C * R;
-  for (int task = warp; task < C * chunks; task += nwarps) {
-    const int c = task / chunks, chunk = task - c * chunks;
+  for (int round = 0;; ++round) {
+    if (round * nwarps >= ntasks) break;
+    const int task = round * nwarps + ((round & 1) ? (nwarps - 1 - warp) : warp);
+    if (task >= ntasks) continue;
+    const int c = s.order[task / chunks], chunk = task % chunks;
     const float* rd = sd + c * Tp;
     const float* ra = sa + c * Tp;
     const float* ras = sas + c * Tp;
     const int n = s.n_valid[c];
-    const float nb2 = -softplus_ref(__ldg(kernel + c)) * kLog2e;
+    const float b2 = softplus_ref(__ldg(kernel + c)) * kLog2e;
+    const float nb2 = -b2;
     int ridx[RPT];
     float rr[RPT], vv[RPT], dv[RPT], acc[RPT];
 #pragma unroll
     for (int k = 0; k < RPT; ++k) {
-      ridx[k] = chunk * 32 * RPT + k * 32 + lane;
+      ridx[k] = (chunk * 32 + lane) * RPT + k;
       const int rc = min(ridx[k], R - 1);
       rr[k] = __ldg(ref_t + rc);
       vv[k] = __ldg(vb + c * R + rc);
       dv[k] = acc[k] = 0.f;
     }
-    const int n4 = (n + 3) & ~3;
-    for (int t0 = 0; t0 < n4; t0 += 4) {
-      const float4 d4 = *reinterpret_cast<const float4*>(rd + t0);
-      const float4 a4 = *reinterpret_cast<const float4*>(ra + t0);
-      const float4 s4 = *reinterpret_cast<const float4*>(ras + t0);
+    const float wcut = sqrtf(kRbfCut / b2);
+    const Window w = make_window(rd, n, rr[0], rr[RPT - 1], wcut, wcut, false);
+    const float* pd = rd + w.lo;
+    const float* pa = ra + w.lo;
+    const float* ps = ras + w.lo;
+    for (int t0 = 0; t0 < w.trip; t0 += 4) {
+      const float4 d4 = *reinterpret_cast<const float4*>(pd + t0);
+      const float4 a4 = *reinterpret_cast<const float4*>(pa + t0);
+      const float4 s4 = *reinterpret_cast<const float4*>(ps + t0);
       const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
       const float aa[4] = {a4.x, a4.y, a4.z, a4.w};
       const float as[4] = {s4.x, s4.y, s4.z, s4.w};
@@ -183,7 +243,7 @@ rbf_bwd_kernel(const float* __restrict__ v, const float* __restrict__ x,
       }
     }
     tot = warp_sum(tot);
-    if (lane == 0) s.part[task] = tot;
+    if (lane == 0) s.part[c * chunks + chunk] = tot;
   }
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -220,7 +280,7 @@ extern "C" int dic_rbf_fwd(const float* v, const float* x, const float* kernel, 
   DIC_REQUIRE(rec, DIC_ERR_INVALID_ARGUMENT, "null output pointer");
   if (B == 0) return DIC_OK;
   const int Rp = round_up(R, 2);
-  const size_t smem = sizeof(float2) * (size_t)C * Rp + sizeof(float) * C;
+  const size_t smem = sizeof(float2) * (size_t)C * Rp + 2 * sizeof(float) * C;
   DIC_REQUIRE(smem <= (size_t)kMaxSmemBytes, DIC_ERR_UNSUPPORTED,
               "C=%d R=%d needs %zu bytes of shared memory (limit %d)", C, R, smem, kMaxSmemBytes);
   if (smem > 48 * 1024)
@@ -251,8 +311,8 @@ extern "C" int dic_rbf_bwd(const float* v, const float* x, const float* kernel, 
               kMaxSmemBytes);
   const int rpt = R <= 32 ? 1 : (R <= 64 ? 2 : 3);
   const int chunks = (R + 32 * rpt - 1) / (32 * rpt);
-  int warps = C * chunks;
-  warps = warps > kMaxWarps ? kMaxWarps : (warps < 4 ? 4 : warps);
+  int warps = (C * chunks + 1) / 2;      // two tasks per warp, paired heavy + light (snake order)
+  warps = warps > kMaxWarps ? kMaxWarps : (warps < 2 ? 2 : warps);
   unsigned char* ws = static_cast<unsigned char*>(workspace);
   float* partial = reinterpret_cast<float*>(ws);
   size_t off = ((size_t)B * C * sizeof(float) + 255) / 256 * 256;

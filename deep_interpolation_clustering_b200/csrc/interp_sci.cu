@@ -10,7 +10,9 @@
 //     y'   = the same with 10 alpha                (high-pass, kappa = 10)
 //
 // Kernel design (one CTA = one encounter, one warp-task = one vital x 32*RPT grid points)
-//   * rows are staged with one TMA bulk copy and canonicalised (interp_stage.cuh);
+//   * rows are staged with one TMA bulk copy and canonicalised (interp_stage.cuh): a vectorised
+//     check accepts the pipeline's left-packed time-ordered rows as they are, anything else is
+//     compacted and sorted;
 //   * the softmax shift is known without a pass over the data: the maximum of s_t is at the
 //     observation nearest to r, found by binary search in the sorted times (d*);
 //   * the exponent -(alpha log2 e) ((d-r)^2 - (d*-r)^2) is formed as fma(delta, delta, -hi) - lo
@@ -19,21 +21,27 @@
 //     reference's own float32 evaluation (which subtracts numbers in the hundreds);
 //   * ONE MUFU.EX2 per (t, r): the high-pass weight is e^10 (4 FMULs) because both filters
 //     share the shift;
-//   * accumulators stay in registers, each lane owns RPT grid points, observations are
-//     read as 128-bit shared-memory broadcasts; outputs are written coalesced along r.
+//   * sliding windows: a Gaussian weight below 2^-kCut of the largest one is dropped, so a lane
+//     only walks the observations within +-sqrt(nmin + kCut/a) hours of its grid points, and
+//     only the inner +-sqrt(nmin + kCut/(10a)) feeds the high-pass sums (make_window);
+//   * accumulators stay in registers, each lane owns RPT ADJACENT grid points, observations are
+//     read as 128-bit shared loads; vitals are dealt to warps heaviest-first in snake order so
+//     the warps of a CTA finish together.
 #include "interp_stage.cuh"
 
 namespace dic {
 namespace {
 
-constexpr int kMaxWarps = 16;
+constexpr int kMaxWarps = 8;
+constexpr float kCut = 34.0f;      // log2 of the dropped weight ratio (2^-34 = 5.8e-11)
 
 struct SciSmem {
-  // dynamic shared memory layout: bar | rows[3][C][Tp] | n_valid[C] (int) | part[C*ceil(R/32)]
-  float* rows;
-  int* n_valid;
-  float* part;
+  // dynamic shared memory layout: bar | rows[3][C][Tp] | n_valid[C] | order[C] | part[C*chunks]
   uint64_t* bar;
+  float* rows;
+  int* n_valid;   // > 0: binary mask; < 0: weighted (|n| entries); 0: all masked
+  int* order;     // vitals sorted by descending observation count
+  float* part;
 };
 
 __device__ __forceinline__ SciSmem sci_carve(unsigned char* base, int C, int Tp) {
@@ -41,18 +49,19 @@ __device__ __forceinline__ SciSmem sci_carve(unsigned char* base, int C, int Tp)
   s.bar = reinterpret_cast<uint64_t*>(base);
   s.rows = reinterpret_cast<float*>(base + 16);
   s.n_valid = reinterpret_cast<int*>(s.rows + 3 * C * Tp);
-  s.part = reinterpret_cast<float*>(s.n_valid + C);
+  s.order = s.n_valid + C;
+  s.part = reinterpret_cast<float*>(s.order + C);
   return s;
 }
 
 static size_t sci_smem_bytes(int C, int Tp, int R) {
-  return 16 + sizeof(float) * (3 * (size_t)C * Tp) + sizeof(int) * C +
+  return 16 + sizeof(float) * (3 * (size_t)C * Tp) + 2 * sizeof(int) * C +
          sizeof(float) * (size_t)C * ((R + 31) / 32);
 }
 
 // Stage + canonicalise one encounter.  After return (CTA-synchronised):
-//   rows[0][c] = m*x (forward) or x (backward), rows[1][c] = m, rows[2][c] = d, all
-//   compacted+sorted+padded; n_valid[c] = count, negated when some kept weight is not exactly 1.
+//   rows[0][c] = m*x (forward) or x (backward), rows[1][c] = m, rows[2][c] = d, compacted, sorted
+//   by time and padded to a multiple of 4 with null entries; n_valid[c]; order[].
 __device__ __forceinline__ void sci_stage(const SciSmem& s, const float* xb, int C, int T, int Tp,
                                           bool use_tma, bool fold_mask) {
   stage_rows(s.rows, xb, 3 * C, T, Tp, s.bar, use_tma);
@@ -61,15 +70,106 @@ __device__ __forceinline__ void sci_stage(const SciSmem& s, const float* xb, int
     float* sx = s.rows + (0 * C + c) * Tp;
     float* sm = s.rows + (1 * C + c) * Tp;
     float* sd = s.rows + (2 * C + c) * Tp;
-    const int n = warp_compact3(sx, sm, sd, T, lane, fold_mask);
-    warp_sort3(sd, sx, sm, n, lane);
+    int n = warp_canonical_count(sm, sd, Tp, lane);
     int weighted = 0;
-    for (int t = lane; t < n; t += 32) weighted |= (sm[t] != 1.0f);
-    weighted = __any_sync(0xffffffffu, weighted);
-    warp_pad4(sd, sx, sm, n, lane);
+    if (n < 0) {   // general rows: drop masked entries, sort by time, detect fractional weights
+      n = warp_compact3(sx, sm, sd, T, lane, fold_mask);
+      warp_sort3(sd, sx, sm, n, lane);
+      for (int t = lane; t < n; t += 32) weighted |= (sm[t] != 1.0f);
+      weighted = __any_sync(0xffffffffu, weighted);
+    }
+    warp_pad4_far(sd, sx, sm, n, lane);
     if (lane == 0) s.n_valid[c] = weighted ? -n : n;
   }
   __syncthreads();
+  if (threadIdx.x == 0) {   // insertion sort of C indices by descending count (C is ~6)
+    for (int c = 0; c < C; ++c) {
+      const int key = abs(s.n_valid[c]);
+      int j = c;
+      while (j > 0 && abs(s.n_valid[s.order[j - 1]]) < key) {
+        s.order[j] = s.order[j - 1];
+        --j;
+      }
+      s.order[j] = c;
+    }
+  }
+  __syncthreads();
+}
+
+// Task k of `ntasks` (heaviest vital first) in snake order over the warps.
+__device__ __forceinline__ int snake_task(int round, int warp, int nwarps) {
+  return round * nwarps + ((round & 1) ? (nwarps - 1 - warp) : warp);
+}
+
+template <int RPT, bool WEIGHTED>
+__device__ __forceinline__ void sci_fwd_task(const float* __restrict__ sx, const float* __restrict__ sm,
+                                             const float* __restrict__ sd, int n, float alpha, int chunk,
+                                             int lane, int c, int C, int R, const float* __restrict__ ref_t,
+                                             float* __restrict__ ub, float* __restrict__ sb) {
+  const float a = alpha * kLog2e, na = -a;
+  int ridx[RPT];
+  float rr[RPT], nhi[RPT], nlo[RPT], s1[RPT], sy[RPT], s10[RPT], sy10[RPT];
+  float nmax = 0.f;
+#pragma unroll
+  for (int k = 0; k < RPT; ++k) {
+    ridx[k] = (chunk * 32 + lane) * RPT + k;
+    rr[k] = __ldg(ref_t + min(ridx[k], R - 1));
+    const float dst = sd[nearest_sorted(sd, n, rr[k])] - rr[k];     // delta* = d* - r
+    nhi[k] = dst * dst;
+    nlo[k] = fmaf(dst, dst, -nhi[k]);          // exact residual: delta*^2 = nhi + nlo
+    nmax = fmaxf(nmax, nhi[k]);
+    s1[k] = sy[k] = s10[k] = sy10[k] = 0.f;
+  }
+  const Window w = make_window(sd, n, rr[0], rr[RPT - 1], sqrtf(nmax + kCut / a),
+                               sqrtf(nmax + kCut / (10.f * a)), WEIGHTED);
+  const float* pd = sd + w.lo;
+  const float* px = sx + w.lo;
+  const float* pm = sm + w.lo;
+
+  auto body = [&](int t0, bool inner) {
+    const float4 d4 = *reinterpret_cast<const float4*>(pd + t0);
+    const float4 x4 = *reinterpret_cast<const float4*>(px + t0);
+    const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
+    const float xx[4] = {x4.x, x4.y, x4.z, x4.w};
+    float mm[4] = {1.f, 1.f, 1.f, 1.f};
+    if (WEIGHTED) {
+      const float4 m4 = *reinterpret_cast<const float4*>(pm + t0);
+      mm[0] = m4.x; mm[1] = m4.y; mm[2] = m4.z; mm[3] = m4.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+      for (int k = 0; k < RPT; ++k) {
+        const float dl = dd[j] - rr[k];
+        const float tt = fmaf(dl, dl, -nhi[k]) - nlo[k];      // (d-r)^2 - (d*-r)^2 >= 0
+        const float e = ex2_approx(tt * na);
+        s1[k] = WEIGHTED ? fmaf(mm[j], e, s1[k]) : s1[k] + e;
+        sy[k] = fmaf(xx[j], e, sy[k]);
+        if (inner) {
+          const float e2 = e * e, e4 = e2 * e2, e8 = e4 * e4, e10 = e8 * e2;
+          s10[k] = WEIGHTED ? fmaf(mm[j], e10, s10[k]) : s10[k] + e10;
+          sy10[k] = fmaf(xx[j], e10, sy10[k]);
+        }
+      }
+    }
+  };
+  int t0 = 0;
+  for (; t0 < w.in0; t0 += 4) body(t0, false);
+  for (; t0 < w.in1; t0 += 4) body(t0, true);
+  for (; t0 < w.trip; t0 += 4) body(t0, false);
+
+#pragma unroll
+  for (int k = 0; k < RPT; ++k) {
+    if (ridx[k] < R) {
+      ub[(0 * C + c) * R + ridx[k]] = sy[k] / s1[k];
+      ub[(1 * C + c) * R + ridx[k]] = logf(s1[k]) - alpha * nhi[k];
+      ub[(2 * C + c) * R + ridx[k]] = sy10[k] / s10[k];
+      if (sb) {
+        sb[(0 * C + c) * R + ridx[k]] = s1[k];
+        sb[(1 * C + c) * R + ridx[k]] = s10[k];
+      }
+    }
+  }
 }
 
 template <int RPT>
@@ -84,71 +184,34 @@ sci_fwd_kernel(const float* __restrict__ x, const float* __restrict__ kernel,
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int chunks = (R + 32 * RPT - 1) / (32 * RPT);
+  const int ntasks = C * chunks;
   float* ub = u + b * (int64_t)(3 * C) * R;
   float* sb = stats ? stats + b * (int64_t)(2 * C) * R : nullptr;
 
-  for (int task = warp; task < C * chunks; task += nwarps) {
-    const int c = task / chunks, chunk = task - c * chunks;
+  for (int round = 0;; ++round) {
+    const int task = snake_task(round, warp, nwarps);
+    if (round * nwarps >= ntasks) break;
+    if (task >= ntasks) continue;
+    const int c = s.order[task / chunks], chunk = task % chunks;
     const float* sx = s.rows + (0 * C + c) * Tp;
     const float* sm = s.rows + (1 * C + c) * Tp;
     const float* sd = s.rows + (2 * C + c) * Tp;
-    const int n = abs(s.n_valid[c]);
+    const int nv = s.n_valid[c];
     const float alpha = softplus_ref(__ldg(kernel + c));
-    const float a = alpha * kLog2e;
-
-    int ridx[RPT];
-    float rr[RPT], nhi[RPT], nlo[RPT], s1[RPT], sy[RPT], s10[RPT], sy10[RPT];
+    if (nv > 0) {
+      sci_fwd_task<RPT, false>(sx, sm, sd, nv, alpha, chunk, lane, c, C, R, ref_t, ub, sb);
+    } else if (nv < 0) {
+      sci_fwd_task<RPT, true>(sx, sm, sd, -nv, alpha, chunk, lane, c, C, R, ref_t, ub, sb);
+    } else {
+      // all-masked vital: the reference yields w = -inf, y = y' = NaN (logsumexp of -inf)
 #pragma unroll
-    for (int k = 0; k < RPT; ++k) {
-      ridx[k] = chunk * 32 * RPT + k * 32 + lane;
-      rr[k] = __ldg(ref_t + min(ridx[k], R - 1));
-      const float dst = (n > 0 ? sd[nearest_sorted(sd, n, rr[k])] : 0.f) - rr[k];   // delta* = d* - r
-      nhi[k] = dst * dst;
-      nlo[k] = fmaf(dst, dst, -nhi[k]);        // exact residual: delta*^2 = nhi + nlo
-      s1[k] = sy[k] = s10[k] = sy10[k] = 0.f;
-    }
-    const float na = -a;
-    const int n4 = (n + 3) & ~3;
-    for (int t0 = 0; t0 < n4; t0 += 4) {
-      const float4 d4 = *reinterpret_cast<const float4*>(sd + t0);
-      const float4 x4 = *reinterpret_cast<const float4*>(sx + t0);
-      const float4 m4 = *reinterpret_cast<const float4*>(sm + t0);
-      const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
-      const float xx[4] = {x4.x, x4.y, x4.z, x4.w};
-      const float mm[4] = {m4.x, m4.y, m4.z, m4.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-#pragma unroll
-        for (int k = 0; k < RPT; ++k) {
-          const float dl = dd[j] - rr[k];
-          const float tt = fmaf(dl, dl, -nhi[k]) - nlo[k];      // (d-r)^2 - (d*-r)^2 >= 0
-          const float e = ex2_approx(tt * na);
-          const float e2 = e * e, e4 = e2 * e2, e8 = e4 * e4, e10 = e8 * e2;
-          s1[k] = fmaf(mm[j], e, s1[k]);
-          sy[k] = fmaf(xx[j], e, sy[k]);
-          s10[k] = fmaf(mm[j], e10, s10[k]);
-          sy10[k] = fmaf(xx[j], e10, sy10[k]);
-        }
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < RPT; ++k) {
-      if (ridx[k] < R) {
-        float y, w, y10;
-        if (n > 0) {
-          w = logf(s1[k]) - alpha * nhi[k];
-          y = sy[k] / s1[k];
-          y10 = sy10[k] / s10[k];
-        } else {  // all-masked channel: the reference yields -inf / NaN (logsumexp of -inf)
-          w = -INFINITY;
-          y = y10 = __int_as_float(0x7fc00000);
-        }
-        ub[(0 * C + c) * R + ridx[k]] = y;
-        ub[(1 * C + c) * R + ridx[k]] = w;
-        ub[(2 * C + c) * R + ridx[k]] = y10;
-        if (sb) {
-          sb[(0 * C + c) * R + ridx[k]] = s1[k];
-          sb[(1 * C + c) * R + ridx[k]] = s10[k];
+      for (int k = 0; k < RPT; ++k) {
+        const int r = (chunk * 32 + lane) * RPT + k;
+        if (r < R) {
+          ub[(0 * C + c) * R + r] = __int_as_float(0x7fc00000);
+          ub[(1 * C + c) * R + r] = -INFINITY;
+          ub[(2 * C + c) * R + r] = __int_as_float(0x7fc00000);
+          if (sb) sb[(0 * C + c) * R + r] = sb[(1 * C + c) * R + r] = 0.f;
         }
       }
     }
@@ -168,15 +231,17 @@ __device__ __forceinline__ float sci_bwd_task(const float* __restrict__ sx, cons
                                               const float* __restrict__ gb, const float* __restrict__ sb) {
   const float na = -a;
   float rr[RPT], nhi[RPT], nlo[RPT], yy[RPT], yy10[RPT], A[RPT], Bc[RPT], A10[RPT], acc[RPT];
+  float nmax = 0.f;
 #pragma unroll
   for (int k = 0; k < RPT; ++k) {
-    const int r = chunk * 32 * RPT + k * 32 + lane;
+    const int r = (chunk * 32 + lane) * RPT + k;
     const bool live = r < R;
     const int rc = min(r, R - 1);
     rr[k] = __ldg(ref_t + rc);
     const float dst = sd[nearest_sorted(sd, n, rr[k])] - rr[k];
     nhi[k] = dst * dst;
     nlo[k] = fmaf(dst, dst, -nhi[k]);
+    nmax = fmaxf(nmax, nhi[k]);
     yy[k] = ub[(0 * C + c) * R + rc];
     yy10[k] = ub[(2 * C + c) * R + rc];
     const float gy = live ? gb[(0 * C + c) * R + rc] : 0.f;
@@ -189,15 +254,20 @@ __device__ __forceinline__ float sci_bwd_task(const float* __restrict__ sx, cons
     A10[k] = gy10 * i10;
     acc[k] = 0.f;
   }
-  const int n4 = (n + 3) & ~3;
-  for (int t0 = 0; t0 < n4; t0 += 4) {
-    const float4 d4 = *reinterpret_cast<const float4*>(sd + t0);
-    const float4 x4 = *reinterpret_cast<const float4*>(sx + t0);
+  const Window w = make_window(sd, n, rr[0], rr[RPT - 1], sqrtf(nmax + kCut / a),
+                               sqrtf(nmax + kCut / (10.f * a)), WEIGHTED);
+  const float* pd = sd + w.lo;
+  const float* px = sx + w.lo;
+  const float* pm = sm + w.lo;
+
+  auto body = [&](int t0, bool inner) {
+    const float4 d4 = *reinterpret_cast<const float4*>(pd + t0);
+    const float4 x4 = *reinterpret_cast<const float4*>(px + t0);
     const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
     const float xx[4] = {x4.x, x4.y, x4.z, x4.w};
     float mm[4] = {1.f, 1.f, 1.f, 1.f};
-    if (WEIGHTED || t0 + 4 > n) {       // padding entries carry weight 0
-      const float4 m4 = *reinterpret_cast<const float4*>(sm + t0);
+    if (WEIGHTED) {
+      const float4 m4 = *reinterpret_cast<const float4*>(pm + t0);
       mm[0] = m4.x; mm[1] = m4.y; mm[2] = m4.z; mm[3] = m4.w;
     }
 #pragma unroll
@@ -207,15 +277,21 @@ __device__ __forceinline__ float sci_bwd_task(const float* __restrict__ sx, cons
         const float dl = dd[j] - rr[k];
         const float tt = fmaf(dl, dl, -nhi[k]) - nlo[k];
         const float e = ex2_approx(tt * na);
-        const float e2 = e * e, e4 = e2 * e2, e8 = e4 * e4, e10 = e8 * e2;
-        const float g1 = fmaf(xx[j] - yy[k], A[k], Bc[k]);
-        const float g10 = (xx[j] - yy10[k]) * A10[k];
-        float h = fmaf(e10, g10, e * g1);
-        if (WEIGHTED || t0 + 4 > n) h *= mm[j];
-        acc[k] = fmaf(tt + nhi[k], h, acc[k]);             // n_tr = (n - nmin) + nmin
+        float h = e * fmaf(xx[j] - yy[k], A[k], Bc[k]);
+        if (inner) {
+          const float e2 = e * e, e4 = e2 * e2, e8 = e4 * e4, e10 = e8 * e2;
+          h = fmaf(e10, (xx[j] - yy10[k]) * A10[k], h);
+        }
+        if (WEIGHTED) h *= mm[j];
+        acc[k] = fmaf(dl * dl, h, acc[k]);                    // n_tr = (d_t - r)^2
       }
     }
-  }
+  };
+  int t0 = 0;
+  for (; t0 < w.in0; t0 += 4) body(t0, false);
+  for (; t0 < w.in1; t0 += 4) body(t0, true);
+  for (; t0 < w.trip; t0 += 4) body(t0, false);
+
   float tot = 0.f;
 #pragma unroll
   for (int k = 0; k < RPT; ++k) tot += acc[k];
@@ -235,12 +311,16 @@ sci_bwd_kernel(const float* __restrict__ x, const float* __restrict__ kernel,
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int chunks = (R + 32 * RPT - 1) / (32 * RPT);
+  const int ntasks = C * chunks;
   const float* ub = u + b * (int64_t)(3 * C) * R;
   const float* gb = grad_u + b * (int64_t)(3 * C) * R;
   const float* sb = stats + b * (int64_t)(2 * C) * R;
 
-  for (int task = warp; task < C * chunks; task += nwarps) {
-    const int c = task / chunks, chunk = task - c * chunks;
+  for (int round = 0;; ++round) {
+    const int task = snake_task(round, warp, nwarps);
+    if (round * nwarps >= ntasks) break;
+    if (task >= ntasks) continue;
+    const int c = s.order[task / chunks], chunk = task % chunks;
     const float* sx = s.rows + (0 * C + c) * Tp;
     const float* sm = s.rows + (1 * C + c) * Tp;
     const float* sd = s.rows + (2 * C + c) * Tp;
@@ -251,7 +331,7 @@ sci_bwd_kernel(const float* __restrict__ x, const float* __restrict__ kernel,
       tot = nv < 0 ? sci_bwd_task<RPT, true>(sx, sm, sd, -nv, a, chunk, lane, c, C, R, ref_t, ub, gb, sb)
                    : sci_bwd_task<RPT, false>(sx, sm, sd, nv, a, chunk, lane, c, C, R, ref_t, ub, gb, sb);
     }
-    if (lane == 0) s.part[task] = tot;
+    if (lane == 0) s.part[c * chunks + chunk] = tot;
   }
   __syncthreads();
   // chunks of one vital are summed in a fixed order -> deterministic partials
@@ -272,7 +352,7 @@ int pick_rpt(int R) { return R <= 32 ? 1 : (R <= 64 ? 2 : 3); }
 
 int pick_warps(int C, int R, int rpt) {
   const int chunks = (R + 32 * rpt - 1) / (32 * rpt);
-  int w = C * chunks;
+  int w = (C * chunks + 1) / 2;          // two tasks per warp, paired heavy + light (snake order)
   if (w > kMaxWarps) w = kMaxWarps;
   if (w < 2) w = 2;
   return w;

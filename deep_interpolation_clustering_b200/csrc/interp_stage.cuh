@@ -82,6 +82,107 @@ __device__ __forceinline__ void warp_pad4(float* key, float* a, float* b, int n,
   __syncwarp();
 }
 
+// Fast path of the canonicalisation.  Returns the observation count if the row already is what
+// the reference pipeline produces - a 0/1 mask that is a left-packed prefix and non-decreasing
+// times on that prefix (p0_data_process.py:44-67) - and -1 otherwise.  One vectorised pass,
+// nothing is moved.  Rows hold Tp (multiple of 4) entries with zero mask beyond T.  One warp.
+__device__ __forceinline__ int warp_canonical_count(const float* rm, const float* rd, int Tp, int lane) {
+  int ok = 1, cnt = 0;
+  for (int t = 4 * lane; t < Tp; t += 128) {
+    const float4 m = *reinterpret_cast<const float4*>(rm + t);
+    const float4 d = *reinterpret_cast<const float4*>(rd + t);
+    const bool last = t + 4 >= Tp;
+    const float mn = last ? 0.f : rm[t + 4];
+    const float dn = last ? 0.f : rd[t + 4];
+    const float mm[5] = {m.x, m.y, m.z, m.w, mn};
+    const float dd[5] = {d.x, d.y, d.z, d.w, dn};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      ok &= (mm[i] == 0.f) | (mm[i] == 1.f);
+      ok &= (mm[i] >= mm[i + 1]);                                   // prefix: never 0 -> 1
+      ok &= (mm[i + 1] == 0.f) | (dd[i] <= dd[i + 1]);              // sorted where both valid
+      cnt += (mm[i] == 1.f);
+    }
+  }
+  ok = __all_sync(0xffffffffu, ok);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  return ok ? cnt : -1;
+}
+
+constexpr float kPadTime = 3.0e18f;   // (kPadTime - r)^2 stays finite and 2^(-a * that) == 0
+
+// Pads rows [n, round_up(n,4)) with entries that contribute exactly nothing.
+__device__ __forceinline__ void warp_pad4_far(float* key, float* a, float* b, int n, int lane) {
+  const int n4 = (n + 3) & ~3;
+  if (lane < n4 - n) {
+    key[n + lane] = kPadTime;
+    a[n + lane] = 0.f;
+    b[n + lane] = 0.f;
+  }
+  __syncwarp();
+}
+
+// First index in sorted key[0..n) with key[i] >= v (lower) / key[i] > v (upper).
+__device__ __forceinline__ int lower_bound_sorted(const float* key, int n, float v) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (key[mid] < v) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+__device__ __forceinline__ int upper_bound_sorted(const float* key, int n, float v) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (key[mid] <= v) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+__device__ __forceinline__ int warp_max_i(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ int warp_min_i(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Per-lane sliding window over the sorted observations of one vital.
+//   A lane owns RPT adjacent grid points [r_first, r_last]; only observations within +-w_out of
+//   them matter (weights below 2^-cut are dropped), and only those within +-w_in feed the
+//   high-pass sums.  Every lane of the warp walks the SAME number of entries (`trip`, multiple
+//   of 4) starting at its own 4-aligned offset `lo`, so there is no divergence and no
+//   union-of-windows penalty; [in0, in1) is the warp-uniform sub-range of iterations that covers
+//   every lane's inner window.
+struct Window {
+  int lo, trip, in0, in1;
+};
+__device__ __forceinline__ Window make_window(const float* key, int n, float r_first, float r_last, float w_out,
+                                              float w_in, bool full) {
+  const int n4 = (n + 3) & ~3;
+  Window w;
+  if (full) {
+    w.lo = 0; w.trip = n4; w.in0 = 0; w.in1 = n4;
+    return w;
+  }
+  int lo = lower_bound_sorted(key, n, r_first - w_out) & ~3;
+  const int hi = upper_bound_sorted(key, n, r_last + w_out);
+  const int ilo = lower_bound_sorted(key, n, r_first - w_in);
+  const int ihi = upper_bound_sorted(key, n, r_last + w_in);
+  w.trip = min(n4, (warp_max_i(hi - lo) + 3) & ~3);
+  lo = min(lo, n4 - w.trip);
+  w.lo = lo;
+  w.in0 = max(0, warp_min_i(ilo - lo)) & ~3;
+  w.in1 = min(w.trip, (warp_max_i(ihi - lo) + 3) & ~3);
+  if (w.in1 < w.in0) w.in1 = w.in0;
+  return w;
+}
+
 // Index of the key nearest to r in sorted key[0..n), n >= 1.
 __device__ __forceinline__ int nearest_sorted(const float* key, int n, float r) {
   int lo = 0, hi = n;
@@ -113,10 +214,10 @@ __device__ __forceinline__ void stage_rows(float* smem_rows, const float* gsrc, 
     }
     mbar_wait(bar, 0);
   } else {
-    const int total = nrows * T;
+    const int total = nrows * Tp;
     for (int i = threadIdx.x; i < total; i += blockDim.x) {
-      const int row = i / T, t = i - row * T;
-      smem_rows[row * Tp + t] = __ldg(gsrc + i);
+      const int row = i / Tp, t = i - row * Tp;
+      smem_rows[i] = t < T ? __ldg(gsrc + row * T + t) : 0.f;     // pad columns: mask 0
     }
     __syncthreads();
   }
