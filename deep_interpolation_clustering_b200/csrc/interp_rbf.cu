@@ -45,15 +45,10 @@ rbf_fwd_kernel(const float* __restrict__ v, const float* __restrict__ x,
   }
   const int64_t b = blockIdx.x;
   const float* vb = v + b * (int64_t)C * R;
-  for (int i = threadIdx.x; i < C * Rp; i += blockDim.x) {
-    const int c = i / Rp, j = i - c * Rp;
-    if (j < R) {
-      const float rj = __ldg(ref_t + j);
-      irregular |= fabsf(rj - (r0 + h * (float)j)) > 0.01f * h;
-      srv[i] = make_float2(rj, __ldg(vb + c * R + j));
-    } else {
-      srv[i] = make_float2(3.0e18f, 0.f);
-    }
+  for (int j = threadIdx.x; j < Rp; j += blockDim.x) {
+    const float rj = j < R ? __ldg(ref_t + j) : 3.0e18f;
+    if (j < R) irregular |= fabsf(rj - (r0 + h * (float)j)) > 0.01f * h;
+    for (int c = 0; c < C; ++c) srv[c * Rp + j] = make_float2(rj, j < R ? __ldg(vb + c * R + j) : 0.f);
   }
   irregular = __syncthreads_or(irregular);
   const float inv_h = 1.0f / h;
@@ -61,39 +56,96 @@ rbf_fwd_kernel(const float* __restrict__ v, const float* __restrict__ x,
   const float* db = x + (b * (int64_t)(4 * C) + 2 * C) * T;   // time plane rows
   float* rb = rec + b * (int64_t)C * T;
   float* nb = inv_norm ? inv_norm + b * (int64_t)C * T : nullptr;
-  for (int i = threadIdx.x; i < C * T; i += blockDim.x) {
-    const int c = i / T;
-    const float m = __ldg(mb + i);
-    float out = 0.f, inv = 0.f;
-    if (m != 0.f) {
-      const float d = __ldg(db + i);
-      const float nb2 = snb[c];
-      const float2* row = srv + c * Rp;
-      // Every lane walks the same number of grid points (swin[c] -> trip), starting at its own
-      // even offset: uniform trip count, no divergence, no union-of-windows penalty.
-      int jlo = 0, trip = Rp;
-      if (!irregular && d >= r0 - 1.0f && d <= rl + 1.0f) {
-        trip = min(Rp, strip[c]);
-        jlo = min(max(0, ((int)floorf((d - r0) * inv_h) - (trip >> 1) + 1) & ~1), Rp - trip);
+
+  // Left-packed 0/1 masks (what the pipeline produces) let the valid observations of all vitals
+  // be dealt evenly to the threads: element e of sum_c n_c -> (vital, observation).  The warp
+  // that scans a vital's mask row also zero-fills the masked tail of its outputs.
+  int* soff = strip + C;                              // [C + 1] prefix sums of the valid counts
+  __shared__ int s_general;
+  if (threadIdx.x == 0) s_general = 0;
+  __syncthreads();
+  {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int c = warp; c < C; c += nwarps) {
+      const float* mrow = mb + c * T;
+      int ok = 1, cnt = 0;
+      for (int t = lane; t < T; t += 32) {
+        const float m = __ldg(mrow + t);
+        const float mn = t + 1 < T ? __ldg(mrow + t + 1) : 0.f;
+        ok &= ((m == 0.f) | (m == 1.f)) & (m >= mn);
+        cnt += (m == 1.f);
       }
-      float N = 0.f, S = 0.f;
-      const float2* rw = row + jlo;
-#pragma unroll 2
-      for (int j = 0; j < trip; j += 2) {
-        const float4 p = *reinterpret_cast<const float4*>(rw + j);   // (r0, v0, r1, v1)
-        const float d0 = d - p.x, d1 = d - p.z;
-        const float e0 = ex2_approx(d0 * d0 * nb2), e1 = ex2_approx(d1 * d1 * nb2);
-        N += e0;
-        S = fmaf(e0, p.y, S);
-        N += e1;
-        S = fmaf(e1, p.w, S);
+      ok = __all_sync(0xffffffffu, ok);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+      if (ok) {
+        for (int t = cnt + lane; t < T; t += 32) {              // masked slots reconstruct to 0
+          rb[c * T + t] = 0.f;
+          if (nb) nb[c * T + t] = 0.f;
+        }
       }
-      // phi = m e  =>  N_ref = m N, sum phi v = m S
-      inv = 1.0f / (m * N + 1e-10f);
-      out = (m * S) * inv * m;                                  // rbf.py:106-107
+      if (lane == 0) {
+        soff[c + 1] = cnt;
+        if (!ok) atomicOr(&s_general, 1);
+      }
     }
-    rb[i] = out;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    soff[0] = 0;
+    for (int c = 0; c < C; ++c) soff[c + 1] += soff[c];
+  }
+  __syncthreads();
+
+  auto readout = [&](int c, int i, float m) {
+    const float d = __ldg(db + i);
+    const float nb2 = snb[c];
+    // Every lane walks the same number of grid points (strip[c] -> trip), starting at its own
+    // even offset: uniform trip count, no divergence, no union-of-windows penalty.
+    int jlo = 0, trip = Rp;
+    if (!irregular && d >= r0 - 1.0f && d <= rl + 1.0f) {
+      trip = min(Rp, strip[c]);
+      jlo = min(max(0, (__float2int_rd((d - r0) * inv_h) - (trip >> 1) + 1) & ~1), Rp - trip);
+    }
+    float N = 0.f, S = 0.f;
+    const float2* rw = srv + c * Rp + jlo;
+#pragma unroll 2
+    for (int j = 0; j < trip; j += 2) {
+      const float4 p = *reinterpret_cast<const float4*>(rw + j);   // (r0, v0, r1, v1)
+      const float d0 = d - p.x, d1 = d - p.z;
+      const float e0 = ex2_approx(d0 * d0 * nb2), e1 = ex2_approx(d1 * d1 * nb2);
+      N += e0;
+      S = fmaf(e0, p.y, S);
+      N += e1;
+      S = fmaf(e1, p.w, S);
+    }
+    // phi = m e  =>  N_ref = m N, sum phi v = m S
+    const float inv = __frcp_rn(fmaf(m, N, 1e-10f));
+    rb[i] = (m * S) * inv * m;                                // rbf.py:106-107
     if (nb) nb[i] = inv;
+  };
+
+  if (!s_general) {
+    const int V = soff[C];
+    for (int e = threadIdx.x; e < V; e += blockDim.x) {
+      int c = 0;
+      while (e >= soff[c + 1]) ++c;
+      readout(c, c * T + (e - soff[c]), 1.0f);
+    }
+  } else {
+    int c = 0, t = threadIdx.x;                                 // (c, t) of element i without dividing
+    while (t >= T) { t -= T; ++c; }
+    for (int i = threadIdx.x; i < C * T; i += blockDim.x) {
+      const float m = __ldg(mb + i);
+      if (m != 0.f) {
+        readout(c, i, m);
+      } else {
+        rb[i] = 0.f;
+        if (nb) nb[i] = 0.f;
+      }
+      t += blockDim.x;
+      while (t >= T) { t -= T; ++c; }
+    }
   }
 }
 
@@ -211,13 +263,13 @@ rbf_bwd_kernel(const float* __restrict__ v, const float* __restrict__ x,
     }
     const float wcut = sqrtf(kRbfCut / b2);
     const Window w = make_window(rd, n, rr[0], rr[RPT - 1], wcut, wcut, false);
-    const float* pd = rd + w.lo;
-    const float* pa = ra + w.lo;
-    const float* ps = ras + w.lo;
+    const int n4 = (n + 3) & ~3;
     for (int t0 = 0; t0 < w.trip; t0 += 4) {
-      const float4 d4 = *reinterpret_cast<const float4*>(pd + t0);
-      const float4 a4 = *reinterpret_cast<const float4*>(pa + t0);
-      const float4 s4 = *reinterpret_cast<const float4*>(ps + t0);
+      const int t = w.base + t0;
+      if ((unsigned)t >= (unsigned)n4) continue;        // chunk off the row (lane at an end of the record)
+      const float4 d4 = *reinterpret_cast<const float4*>(rd + t);
+      const float4 a4 = *reinterpret_cast<const float4*>(ra + t);
+      const float4 s4 = *reinterpret_cast<const float4*>(ras + t);
       const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
       const float aa[4] = {a4.x, a4.y, a4.z, a4.w};
       const float as[4] = {s4.x, s4.y, s4.z, s4.w};
@@ -280,7 +332,7 @@ extern "C" int dic_rbf_fwd(const float* v, const float* x, const float* kernel, 
   DIC_REQUIRE(rec, DIC_ERR_INVALID_ARGUMENT, "null output pointer");
   if (B == 0) return DIC_OK;
   const int Rp = round_up(R, 2);
-  const size_t smem = sizeof(float2) * (size_t)C * Rp + 2 * sizeof(float) * C;
+  const size_t smem = sizeof(float2) * (size_t)C * Rp + sizeof(float) * (3 * (size_t)C + 1);
   DIC_REQUIRE(smem <= (size_t)kMaxSmemBytes, DIC_ERR_UNSUPPORTED,
               "C=%d R=%d needs %zu bytes of shared memory (limit %d)", C, R, smem, kMaxSmemBytes);
   if (smem > 48 * 1024)

@@ -33,11 +33,12 @@ namespace dic {
 namespace {
 
 constexpr int kMaxWarps = 8;
-constexpr float kCut = 34.0f;      // log2 of the dropped weight ratio (2^-34 = 5.8e-11)
+constexpr float kCut = 27.0f;      // log2 of the dropped weight ratio (2^-27 = 7.5e-9; Gaussian tail sum ~1e-8)
 
 struct SciSmem {
-  // dynamic shared memory layout: bar | rows[3][C][Tp] | n_valid[C] | order[C] | part[C*chunks]
+  // dynamic shared memory layout: bar | null chunks | rows[3][C][Tp] | n_valid[C] | order[C] | part[]
   uint64_t* bar;
+  float* nullc;   // [0..3] = kPadTime (a chunk of observations that weigh exactly 0), [4..7] = 0
   float* rows;
   int* n_valid;   // > 0: binary mask; < 0: weighted (|n| entries); 0: all masked
   int* order;     // vitals sorted by descending observation count
@@ -47,7 +48,8 @@ struct SciSmem {
 __device__ __forceinline__ SciSmem sci_carve(unsigned char* base, int C, int Tp) {
   SciSmem s;
   s.bar = reinterpret_cast<uint64_t*>(base);
-  s.rows = reinterpret_cast<float*>(base + 16);
+  s.nullc = reinterpret_cast<float*>(base + 16);
+  s.rows = reinterpret_cast<float*>(base + 48);
   s.n_valid = reinterpret_cast<int*>(s.rows + 3 * C * Tp);
   s.order = s.n_valid + C;
   s.part = reinterpret_cast<float*>(s.order + C);
@@ -55,7 +57,7 @@ __device__ __forceinline__ SciSmem sci_carve(unsigned char* base, int C, int Tp)
 }
 
 static size_t sci_smem_bytes(int C, int Tp, int R) {
-  return 16 + sizeof(float) * (3 * (size_t)C * Tp) + 2 * sizeof(int) * C +
+  return 48 + sizeof(float) * (3 * (size_t)C * Tp) + 2 * sizeof(int) * C +
          sizeof(float) * (size_t)C * ((R + 31) / 32);
 }
 
@@ -64,6 +66,7 @@ static size_t sci_smem_bytes(int C, int Tp, int R) {
 //   by time and padded to a multiple of 4 with null entries; n_valid[c]; order[].
 __device__ __forceinline__ void sci_stage(const SciSmem& s, const float* xb, int C, int T, int Tp,
                                           bool use_tma, bool fold_mask) {
+  if (threadIdx.x < 8) s.nullc[threadIdx.x] = threadIdx.x < 4 ? kPadTime : 0.f;
   stage_rows(s.rows, xb, 3 * C, T, Tp, s.bar, use_tma);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   for (int c = warp; c < C; c += nwarps) {
@@ -105,16 +108,24 @@ template <int RPT, bool WEIGHTED>
 __device__ __forceinline__ void sci_fwd_task(const float* __restrict__ sx, const float* __restrict__ sm,
                                              const float* __restrict__ sd, int n, float alpha, int chunk,
                                              int lane, int c, int C, int R, const float* __restrict__ ref_t,
-                                             float* __restrict__ ub, float* __restrict__ sb) {
+                                             float* __restrict__ ub, float* __restrict__ sb,
+                                             const float* __restrict__ nullc) {
   const float a = alpha * kLog2e, na = -a;
   int ridx[RPT];
   float rr[RPT], nhi[RPT], nlo[RPT], s1[RPT], sy[RPT], s10[RPT], sy10[RPT];
   float nmax = 0.f;
+  bool upk[RPT];
+  int lb[RPT];
 #pragma unroll
   for (int k = 0; k < RPT; ++k) {
     ridx[k] = (chunk * 32 + lane) * RPT + k;
     rr[k] = __ldg(ref_t + min(ridx[k], R - 1));
-    const float dst = sd[nearest_sorted(sd, n, rr[k])] - rr[k];     // delta* = d* - r
+    upk[k] = false;
+  }
+  multi_bound<RPT>(sd, n, rr, upk, lb);         // lb = first observation at or after r
+#pragma unroll
+  for (int k = 0; k < RPT; ++k) {
+    const float dst = nearest_delta(sd, n, lb[k], rr[k]);           // delta* = d* - r
     nhi[k] = dst * dst;
     nlo[k] = fmaf(dst, dst, -nhi[k]);          // exact residual: delta*^2 = nhi + nlo
     nmax = fmaxf(nmax, nhi[k]);
@@ -122,18 +133,18 @@ __device__ __forceinline__ void sci_fwd_task(const float* __restrict__ sx, const
   }
   const Window w = make_window(sd, n, rr[0], rr[RPT - 1], sqrtf(nmax + kCut / a),
                                sqrtf(nmax + kCut / (10.f * a)), WEIGHTED);
-  const float* pd = sd + w.lo;
-  const float* px = sx + w.lo;
-  const float* pm = sm + w.lo;
+  const int n4 = (n + 3) & ~3;
 
   auto body = [&](int t0, bool inner) {
-    const float4 d4 = *reinterpret_cast<const float4*>(pd + t0);
-    const float4 x4 = *reinterpret_cast<const float4*>(px + t0);
+    const int t = w.base + t0;
+    const bool in_row = (unsigned)t < (unsigned)n4;           // chunks off the row weigh nothing
+    const float4 d4 = *reinterpret_cast<const float4*>(in_row ? sd + t : nullc);
+    const float4 x4 = *reinterpret_cast<const float4*>(in_row ? sx + t : nullc + 4);
     const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
     const float xx[4] = {x4.x, x4.y, x4.z, x4.w};
     float mm[4] = {1.f, 1.f, 1.f, 1.f};
     if (WEIGHTED) {
-      const float4 m4 = *reinterpret_cast<const float4*>(pm + t0);
+      const float4 m4 = *reinterpret_cast<const float4*>(sm + t);   // full range: always in the row
       mm[0] = m4.x; mm[1] = m4.y; mm[2] = m4.z; mm[3] = m4.w;
     }
 #pragma unroll
@@ -199,9 +210,9 @@ sci_fwd_kernel(const float* __restrict__ x, const float* __restrict__ kernel,
     const int nv = s.n_valid[c];
     const float alpha = softplus_ref(__ldg(kernel + c));
     if (nv > 0) {
-      sci_fwd_task<RPT, false>(sx, sm, sd, nv, alpha, chunk, lane, c, C, R, ref_t, ub, sb);
+      sci_fwd_task<RPT, false>(sx, sm, sd, nv, alpha, chunk, lane, c, C, R, ref_t, ub, sb, s.nullc);
     } else if (nv < 0) {
-      sci_fwd_task<RPT, true>(sx, sm, sd, -nv, alpha, chunk, lane, c, C, R, ref_t, ub, sb);
+      sci_fwd_task<RPT, true>(sx, sm, sd, -nv, alpha, chunk, lane, c, C, R, ref_t, ub, sb, s.nullc);
     } else {
       // all-masked vital: the reference yields w = -inf, y = y' = NaN (logsumexp of -inf)
 #pragma unroll
@@ -228,17 +239,25 @@ __device__ __forceinline__ float sci_bwd_task(const float* __restrict__ sx, cons
                                               const float* __restrict__ sd, int n, float a, int chunk,
                                               int lane, int c, int C, int R,
                                               const float* __restrict__ ref_t, const float* __restrict__ ub,
-                                              const float* __restrict__ gb, const float* __restrict__ sb) {
+                                              const float* __restrict__ gb, const float* __restrict__ sb,
+                                              const float* __restrict__ nullc) {
   const float na = -a;
   float rr[RPT], nhi[RPT], nlo[RPT], yy[RPT], yy10[RPT], A[RPT], Bc[RPT], A10[RPT], acc[RPT];
   float nmax = 0.f;
+  bool upk[RPT];
+  int lb[RPT];
+#pragma unroll
+  for (int k = 0; k < RPT; ++k) {
+    rr[k] = __ldg(ref_t + min((chunk * 32 + lane) * RPT + k, R - 1));
+    upk[k] = false;
+  }
+  multi_bound<RPT>(sd, n, rr, upk, lb);
 #pragma unroll
   for (int k = 0; k < RPT; ++k) {
     const int r = (chunk * 32 + lane) * RPT + k;
     const bool live = r < R;
     const int rc = min(r, R - 1);
-    rr[k] = __ldg(ref_t + rc);
-    const float dst = sd[nearest_sorted(sd, n, rr[k])] - rr[k];
+    const float dst = nearest_delta(sd, n, lb[k], rr[k]);
     nhi[k] = dst * dst;
     nlo[k] = fmaf(dst, dst, -nhi[k]);
     nmax = fmaxf(nmax, nhi[k]);
@@ -256,18 +275,18 @@ __device__ __forceinline__ float sci_bwd_task(const float* __restrict__ sx, cons
   }
   const Window w = make_window(sd, n, rr[0], rr[RPT - 1], sqrtf(nmax + kCut / a),
                                sqrtf(nmax + kCut / (10.f * a)), WEIGHTED);
-  const float* pd = sd + w.lo;
-  const float* px = sx + w.lo;
-  const float* pm = sm + w.lo;
+  const int n4 = (n + 3) & ~3;
 
   auto body = [&](int t0, bool inner) {
-    const float4 d4 = *reinterpret_cast<const float4*>(pd + t0);
-    const float4 x4 = *reinterpret_cast<const float4*>(px + t0);
+    const int t = w.base + t0;
+    const bool in_row = (unsigned)t < (unsigned)n4;
+    const float4 d4 = *reinterpret_cast<const float4*>(in_row ? sd + t : nullc);
+    const float4 x4 = *reinterpret_cast<const float4*>(in_row ? sx + t : nullc + 4);
     const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
     const float xx[4] = {x4.x, x4.y, x4.z, x4.w};
     float mm[4] = {1.f, 1.f, 1.f, 1.f};
     if (WEIGHTED) {
-      const float4 m4 = *reinterpret_cast<const float4*>(pm + t0);
+      const float4 m4 = *reinterpret_cast<const float4*>(sm + t);
       mm[0] = m4.x; mm[1] = m4.y; mm[2] = m4.z; mm[3] = m4.w;
     }
 #pragma unroll
@@ -328,8 +347,8 @@ sci_bwd_kernel(const float* __restrict__ x, const float* __restrict__ kernel,
     float tot = 0.f;
     if (nv != 0) {   // an all-masked channel contributes nothing (the reference's grad is NaN there)
       const float a = softplus_ref(__ldg(kernel + c)) * kLog2e;
-      tot = nv < 0 ? sci_bwd_task<RPT, true>(sx, sm, sd, -nv, a, chunk, lane, c, C, R, ref_t, ub, gb, sb)
-                   : sci_bwd_task<RPT, false>(sx, sm, sd, nv, a, chunk, lane, c, C, R, ref_t, ub, gb, sb);
+      tot = nv < 0 ? sci_bwd_task<RPT, true>(sx, sm, sd, -nv, a, chunk, lane, c, C, R, ref_t, ub, gb, sb, s.nullc)
+                   : sci_bwd_task<RPT, false>(sx, sm, sd, nv, a, chunk, lane, c, C, R, ref_t, ub, gb, sb, s.nullc);
     }
     if (lane == 0) s.part[c * chunks + chunk] = tot;
   }

@@ -152,35 +152,67 @@ __device__ __forceinline__ int warp_min_i(int v) {
   return v;
 }
 
+// Branch-free binary searches for NV targets at once over sorted key[0..n), n >= 1:
+//   pos[k] = #{ i : key[i] < v[k] }   (lower bound)      when !upper[k]
+//   pos[k] = #{ i : key[i] <= v[k] }  (upper bound)      when  upper[k]
+// The trip count depends only on n (warp-uniform) and the NV probes of a step are independent,
+// so their shared-memory latencies overlap.
+template <int NV>
+__device__ __forceinline__ void multi_bound(const float* key, int n, const float (&v)[NV],
+                                            const bool (&upper)[NV], int (&pos)[NV]) {
+#pragma unroll
+  for (int k = 0; k < NV; ++k) pos[k] = 0;
+  for (int step = 1 << (31 - __clz(n)); step > 0; step >>= 1) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int p = pos[k] + step;
+      const float kv = key[min(p, n) - 1];
+      const bool go = (p <= n) && (upper[k] ? (kv <= v[k]) : (kv < v[k]));
+      pos[k] = go ? p : pos[k];
+    }
+  }
+}
+
 // Per-lane sliding window over the sorted observations of one vital.
 //   A lane owns RPT adjacent grid points [r_first, r_last]; only observations within +-w_out of
 //   them matter (weights below 2^-cut are dropped), and only those within +-w_in feed the
-//   high-pass sums.  Every lane of the warp walks the SAME number of entries (`trip`, multiple
-//   of 4) starting at its own 4-aligned offset `lo`, so there is no divergence and no
-//   union-of-windows penalty; [in0, in1) is the warp-uniform sub-range of iterations that covers
-//   every lane's inner window.
+//   high-pass sums.  Every lane of the warp walks the SAME number of 4-entry chunks (`trip`)
+//   from its own 4-aligned base, and the inner window sits at the SAME iteration range
+//   [in0, in1) for every lane, so there is neither divergence nor a union-of-windows penalty.
+//   A lane near the ends of the record gets a base before the row (or runs past it): those
+//   chunks are redirected to a null chunk (time = kPadTime => weight exactly 0).
 struct Window {
-  int lo, trip, in0, in1;
+  int base, trip, in0, in1;
 };
 __device__ __forceinline__ Window make_window(const float* key, int n, float r_first, float r_last, float w_out,
                                               float w_in, bool full) {
   const int n4 = (n + 3) & ~3;
   Window w;
-  if (full) {
-    w.lo = 0; w.trip = n4; w.in0 = 0; w.in1 = n4;
+  if (full || n == 0) {
+    w.base = 0; w.trip = n4; w.in0 = 0; w.in1 = n4;
     return w;
   }
-  int lo = lower_bound_sorted(key, n, r_first - w_out) & ~3;
-  const int hi = upper_bound_sorted(key, n, r_last + w_out);
-  const int ilo = lower_bound_sorted(key, n, r_first - w_in);
-  const int ihi = upper_bound_sorted(key, n, r_last + w_in);
-  w.trip = min(n4, (warp_max_i(hi - lo) + 3) & ~3);
-  lo = min(lo, n4 - w.trip);
-  w.lo = lo;
-  w.in0 = max(0, warp_min_i(ilo - lo)) & ~3;
-  w.in1 = min(w.trip, (warp_max_i(ihi - lo) + 3) & ~3);
-  if (w.in1 < w.in0) w.in1 = w.in0;
+  const float tv[4] = {r_first - w_out, r_first - w_in, r_last + w_in, r_last + w_out};
+  const bool up[4] = {false, false, true, true};
+  int pos[4];
+  multi_bound<4>(key, n, tv, up, pos);                 // lo <= ilo <= ihi <= hi
+  const int ilo4 = pos[1] & ~3;
+  w.in0 = (warp_max_i(pos[1] - pos[0]) + 3) & ~3;      // entries between outer and inner start
+  const int lin = (warp_max_i(pos[2] - ilo4) + 3) & ~3;
+  const int tail = (warp_max_i(pos[3] - pos[2]) + 3) & ~3;
+  w.in1 = w.in0 + lin;
+  w.trip = w.in1 + tail;
+  w.base = ilo4 - w.in0;
   return w;
+}
+
+// d* - r for the observation nearest to r, given lb = #{i : key[i] < r} in sorted key[0..n), n >= 1.
+__device__ __forceinline__ float nearest_delta(const float* key, int n, int lb, float r) {
+  const float below = key[max(lb, 1) - 1] - r;        // <= 0 when lb >= 1
+  const float above = key[min(lb, n - 1)] - r;        // >= 0 when lb <  n
+  if (lb == 0) return above;
+  if (lb == n) return below;
+  return (-below <= above) ? below : above;
 }
 
 // Index of the key nearest to r in sorted key[0..n), n >= 1.
