@@ -51,7 +51,12 @@ template <typename T> static KmLayout km_layout(int K, int D, int tile) {
   KmLayout L;
   size_t o = 0;
   L.off_c = o;   o += (size_t)K * s16 * 16;
-  L.off_x = o;   o += (size_t)tile * s16 * 16;
+  {   // tile buffer, later reused to fold the per-group register sums: [tile/D groups][K][D]
+    const size_t tile_bytes = (size_t)tile * s16 * 16, fold_bytes = (size_t)tile * K * sizeof(T);
+    L.off_x = o;
+    o += tile_bytes > fold_bytes ? tile_bytes : fold_bytes;
+    o = (o + 15) & ~(size_t)15;
+  }
   L.off_acc = o; o += (size_t)K * D * sizeof(T);
   o = (o + 15) & ~(size_t)15;
   L.off_cn = o;  o += (size_t)K * sizeof(T);
@@ -198,6 +203,202 @@ __global__ void kmeans_assign_kernel(const T* __restrict__ X, const T* __restric
   if (tid == 3) out[(int64_t)K * D + K + 3] = 0.0;
 }
 
+// Fast Lloyd pass for K <= 16 (the reference sweeps K = 2..10 and trains with K = 4): the per-CTA
+// cluster sums live in REGISTERS for the whole kernel (thread = one column of one row group, a
+// warp-uniform switch on the row's label picks the accumulator), tiles are loaded with 128-bit
+// accesses and no per-element division.  One read of X, ~1.1k issue slots per 128-row tile.
+constexpr int kKmTile = 128;
+
+template <typename T, int KR, int NC>
+__global__ void __launch_bounds__(kKmTile)
+kmeans_assign_fast_kernel(const T* __restrict__ X, const T* __restrict__ centers, int32_t* __restrict__ labels,
+                          double* __restrict__ ws, int64_t N, int D, int K, int s16, int flags,
+                          KmLayout L, int want_sums, int vec_ok) {
+  using V = typename Vec16<T>::type;
+  constexpr int PER = Vec16<T>::n;
+  extern __shared__ __align__(16) unsigned char smem[];
+  V* sc = reinterpret_cast<V*>(smem + L.off_c);
+  V* sx = reinterpret_cast<V*>(smem + L.off_x);
+  T* scn = reinterpret_cast<T*>(smem + L.off_cn);
+  int* scnt = reinterpret_cast<int*>(smem + L.off_cnt);
+  int* slab = reinterpret_cast<int*>(smem + L.off_lab);
+  const int tid = threadIdx.x;
+  const int Dp = s16 * PER;
+
+  for (int i = tid; i < K * Dp; i += kKmTile) {
+    const int k = i / Dp, d = i - k * Dp;
+    reinterpret_cast<T*>(sc)[i] = d < D ? centers[(int64_t)k * D + d] : T(0);
+  }
+  for (int i = tid; i < kKmTile * Dp; i += kKmTile) reinterpret_cast<T*>(sx)[i] = T(0);   // pad columns stay 0
+  for (int i = tid; i < K; i += kKmTile) scnt[i] = 0;
+  __syncthreads();
+  for (int k = tid; k < K; k += kKmTile) {
+    T s = T(0);
+    for (int d = 0; d < D; ++d) {
+      const T c = reinterpret_cast<T*>(sc)[k * Dp + d];
+      s += c * c;
+    }
+    scn[k] = s;
+  }
+  __syncthreads();
+
+  // tile-load walk: 16-byte units when the row size allows, else elements; (row, col) advance
+  // incrementally so the loop has no division
+  const bool vec = vec_ok != 0;
+  const int units = vec ? D / PER : D;                 // units per row
+  const int u_r0 = tid / units, u_j0 = tid - u_r0 * units;
+  const int u_dr = kKmTile / units, u_dj = kKmTile - u_dr * units;
+  // phase-2 ownership: column d of row group g (G groups), or NC columns when D > tile
+  const int G = D < kKmTile ? kKmTile / D : 1;
+  const int g = D < kKmTile ? tid / D : 0;
+  const int dcol = D < kKmTile ? tid - g * D : tid;
+  const bool owner = D < kKmTile ? (g < G) : true;
+  T acc[KR][NC];
+#pragma unroll
+  for (int k = 0; k < KR; ++k)
+#pragma unroll
+    for (int c = 0; c < NC; ++c) acc[k][c] = T(0);
+
+  double inertia = 0.0, dist_sum = 0.0;
+  int changed = 0;
+  const int64_t ntiles = (N + kKmTile - 1) / kKmTile;
+  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int64_t row0 = t * kKmTile;
+    const int rows = (int)min((int64_t)kKmTile, N - row0);
+    {
+      int r = u_r0, j = u_j0;
+      if (vec) {
+        const V* src = reinterpret_cast<const V*>(X + row0 * D);
+        for (int i = tid; i < rows * units; i += kKmTile) {
+          sx[r * s16 + j] = src[i];
+          r += u_dr; j += u_dj;
+          if (j >= units) { j -= units; ++r; }
+        }
+      } else {
+        const T* src = X + row0 * D;
+        for (int i = tid; i < rows * units; i += kKmTile) {
+          reinterpret_cast<T*>(sx)[r * Dp + j] = src[i];
+          r += u_dr; j += u_dj;
+          if (j >= units) { j -= units; ++r; }
+        }
+      }
+    }
+    __syncthreads();
+
+    if (tid < rows) {
+      const V* xr = sx + tid * s16;
+      int best = 0;
+      if (flags & DIC_KM_KEEP_LABELS) {
+        best = labels[row0 + tid];
+      } else {
+        T bestd = T(0);
+        for (int kb = 0; kb < K; kb += 4) {
+          const V* c0 = sc + min(kb + 0, K - 1) * s16;
+          const V* c1 = sc + min(kb + 1, K - 1) * s16;
+          const V* c2 = sc + min(kb + 2, K - 1) * s16;
+          const V* c3 = sc + min(kb + 3, K - 1) * s16;
+          T a0 = T(0), a1 = T(0), a2 = T(0), a3 = T(0);
+          for (int j = 0; j < s16; ++j) {
+            const V xv = xr[j];
+            a0 = dot16(xv, c0[j], a0);
+            a1 = dot16(xv, c1[j], a1);
+            a2 = dot16(xv, c2[j], a2);
+            a3 = dot16(xv, c3[j], a3);
+          }
+          const T av[4] = {a0, a1, a2, a3};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int k = kb + i;
+            if (k < K) {
+              const T dk = scn[k] - T(2) * av[i];       // ||c||^2 - 2 x.c  (||x||^2 omitted)
+              if (k == 0 || dk < bestd) {               // strict '<': lowest index wins ties
+                bestd = dk;
+                best = k;
+              }
+            }
+          }
+        }
+        if (flags & DIC_KM_COUNT_CHANGES) changed += (labels[row0 + tid] != best);
+        labels[row0 + tid] = best;
+      }
+      const V* cb = sc + best * s16;
+      T d2 = T(0);
+      for (int j = 0; j < s16; ++j) d2 = sqd16(xr[j], cb[j], d2);
+      inertia += (double)d2;
+      dist_sum += sqrt((double)d2);
+      slab[tid] = best;
+      if (want_sums) atomicAdd(&scnt[best], 1);
+    }
+    __syncthreads();
+    if (want_sums && owner) {
+      for (int r = g; r < rows; r += G) {
+        const int lab = slab[r];
+        T xv[NC];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          const int d = dcol + c * kKmTile;
+          xv[c] = d < D ? reinterpret_cast<const T*>(sx)[r * Dp + d] : T(0);
+        }
+#define DIC_KM_CASE(k_)                                        \
+  case k_:                                                     \
+    if (KR > k_) {                                             \
+      _Pragma("unroll") for (int c = 0; c < NC; ++c) acc[k_ < KR ? k_ : 0][c] += xv[c]; \
+    }                                                          \
+    break;
+        switch (lab) {
+          DIC_KM_CASE(0) DIC_KM_CASE(1) DIC_KM_CASE(2) DIC_KM_CASE(3) DIC_KM_CASE(4) DIC_KM_CASE(5)
+          DIC_KM_CASE(6) DIC_KM_CASE(7) DIC_KM_CASE(8) DIC_KM_CASE(9) DIC_KM_CASE(10) DIC_KM_CASE(11)
+          DIC_KM_CASE(12) DIC_KM_CASE(13) DIC_KM_CASE(14) DIC_KM_CASE(15)
+          default: break;
+        }
+#undef DIC_KM_CASE
+      }
+    }
+    __syncthreads();
+  }
+
+  // per-block partials: [K*D] sums | [K] counts | inertia | changed | dist_sum | 0
+  double* out = ws + (int64_t)blockIdx.x * ((int64_t)K * D + K + 4);
+  if (want_sums) {
+    // fold the G row groups through shared memory (the tile buffer is free now)
+    T* fold = reinterpret_cast<T*>(sx);                  // [G][K][D]
+    if (owner) {
+#pragma unroll
+      for (int k = 0; k < KR; ++k)
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          const int d = dcol + c * kKmTile;
+          if (k < K && d < D) fold[(g * K + k) * D + d] = acc[k][c];
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < K * D; i += kKmTile) {
+      double sum = 0.0;
+      for (int gg = 0; gg < G; ++gg) sum += (double)fold[gg * K * D + i];
+      out[i] = sum;
+    }
+    for (int i = tid; i < K; i += kKmTile) out[(int64_t)K * D + i] = (double)scnt[i];
+    __syncthreads();
+  }
+  double* red = reinterpret_cast<double*>(sx);
+  inertia = warp_sum(inertia);
+  dist_sum = warp_sum(dist_sum);
+  double ch = warp_sum((double)changed);
+  const int warp = tid >> 5, lane = tid & 31;
+  if (lane == 0) {
+    red[warp * 3 + 0] = inertia;
+    red[warp * 3 + 1] = ch;
+    red[warp * 3 + 2] = dist_sum;
+  }
+  __syncthreads();
+  if (tid < 3) {
+    double sum = 0.0;
+    for (int w = 0; w < kKmTile / 32; ++w) sum += red[w * 3 + tid];
+    out[(int64_t)K * D + K + tid] = sum;
+  }
+  if (tid == 3) out[(int64_t)K * D + K + 3] = 0.0;
+}
+
 __global__ void kmeans_finish_kernel(const double* __restrict__ ws, double* __restrict__ sums,
                                      double* __restrict__ counts, double* __restrict__ stats, int nblocks,
                                      int K, int D) {
@@ -213,6 +414,41 @@ __global__ void kmeans_finish_kernel(const double* __restrict__ ws, double* __re
     double s = 0.0;
     for (int b = 0; b < nblocks; ++b) s += ws[b * stride + (int64_t)K * D + K + i];
     stats[i] = s;
+  }
+}
+
+// M-step on device (sklearn/cluster/_k_means_common.pyx:236-260 + _kmeans.py:703-733): new centre =
+// sum / count (an empty cluster keeps its old centre; relocation is the host's rare path),
+// squared centre shift, and a 4-double status [changed labels, sum shift^2, empty clusters,
+// inertia] so the host reads ONE small buffer per iteration.
+template <typename T>
+__global__ void kmeans_update_kernel(const double* __restrict__ sums, const double* __restrict__ counts,
+                                     const double* __restrict__ stats, T* __restrict__ centers,
+                                     double* __restrict__ status, int K, int D) {
+  __shared__ double red[32];
+  double shift2 = 0.0;
+  for (int i = threadIdx.x; i < K * D; i += blockDim.x) {
+    const int k = i / D;
+    const double cnt = counts[k];
+    if (cnt > 0.0) {
+      const T nc = (T)(sums[i] / cnt);
+      const double df = (double)nc - (double)centers[i];
+      shift2 += df * df;
+      centers[i] = nc;
+    }
+  }
+  shift2 = warp_sum(shift2);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = shift2;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
+    int empty = 0;
+    for (int k = 0; k < K; ++k) empty += (counts[k] == 0.0);
+    status[0] = stats[1];
+    status[1] = s;
+    status[2] = (double)empty;
+    status[3] = stats[0];
   }
 }
 
@@ -374,6 +610,34 @@ int launch_assign(const void* X, const void* centers, int32_t* labels, double* s
   const int s16 = row_stride16<T>(D);
   int tile = 128;
   KmLayout L = km_layout<T>(K, D, tile);
+  if (K <= 16 && D <= 4 * kKmTile && L.total <= 100 * 1024) {
+    const int64_t nt = (N + kKmTile - 1) / kKmTile;
+    int nb = km_blocks(K, D);
+    if (nt < nb) nb = (int)nt;
+    if (nb < 1) nb = 1;
+    double* wsd = static_cast<double*>(workspace);
+    const int kr = K <= 4 ? 4 : (K <= 8 ? 8 : 16);
+    const int nc = D <= kKmTile ? 1 : (D <= 2 * kKmTile ? 2 : 4);
+#define DIC_KM_LAUNCH(KR_, NC_)                                                                          \
+  {                                                                                                      \
+    auto kf = kmeans_assign_fast_kernel<T, KR_, NC_>;                                                    \
+    if (L.total > 48 * 1024)                                                                             \
+      DIC_CUDA(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));     \
+    kf<<<nb, kKmTile, L.total, st>>>(static_cast<const T*>(X), static_cast<const T*>(centers), labels,   \
+                                     wsd, N, D, K, s16, flags, L, sums != nullptr,                       \
+                                     (int)(aligned16(X) && D % (16 / (int)sizeof(T)) == 0));             \
+  }
+#define DIC_KM_NC(KR_)                                                                \
+  if (nc == 1) DIC_KM_LAUNCH(KR_, 1) else if (nc == 2) DIC_KM_LAUNCH(KR_, 2) else DIC_KM_LAUNCH(KR_, 4)
+    if (kr == 4) { DIC_KM_NC(4) } else if (kr == 8) { DIC_KM_NC(8) } else { DIC_KM_NC(16) }
+#undef DIC_KM_NC
+#undef DIC_KM_LAUNCH
+    DIC_LAUNCH_CHECK("kmeans_assign_fast_kernel");
+    const int nn = K * D + K + 4;
+    kmeans_finish_kernel<<<(nn + 255) / 256, 256, 0, st>>>(wsd, sums, counts, stats, nb, K, D);
+    DIC_LAUNCH_CHECK("kmeans_finish_kernel");
+    return DIC_OK;
+  }
   while (tile > 32 && L.total > 100 * 1024) {
     tile >>= 1;
     L = km_layout<T>(K, D, tile);
@@ -463,6 +727,20 @@ extern "C" int dic_kmeans_assign(const void* X, const void* centers, int32_t* la
   }
   return dtype == 0 ? launch_assign<float>(X, centers, labels, sums, counts, stats, workspace, N, D, K, flags, st)
                     : launch_assign<double>(X, centers, labels, sums, counts, stats, workspace, N, D, K, flags, st);
+}
+
+extern "C" int dic_kmeans_update(const double* sums, const double* counts, const double* stats, void* centers,
+                                 double* status, int D, int K, int dtype, dic_stream_t stream) {
+  DIC_REQUIRE(sums && counts && stats && centers && status, DIC_ERR_INVALID_ARGUMENT, "null pointer argument");
+  DIC_REQUIRE(D > 0 && K > 0, DIC_ERR_INVALID_ARGUMENT, "bad sizes D=%d K=%d", D, K);
+  DIC_REQUIRE(dtype == 0 || dtype == 1, DIC_ERR_INVALID_ARGUMENT, "dtype must be 0 (float32) or 1 (float64)");
+  cudaStream_t st = as_stream(stream);
+  if (dtype == 0)
+    kmeans_update_kernel<float><<<1, 256, 0, st>>>(sums, counts, stats, static_cast<float*>(centers), status, K, D);
+  else
+    kmeans_update_kernel<double><<<1, 256, 0, st>>>(sums, counts, stats, static_cast<double*>(centers), status, K, D);
+  DIC_LAUNCH_CHECK("kmeans_update_kernel");
+  return DIC_OK;
 }
 
 extern "C" int dic_kmeans_min_d2(const void* X, const void* cands, const void* min_d2, void* min_d2_out,

@@ -95,6 +95,16 @@ class _Device:
         self.sums = torch.empty((K, self.D), dtype=torch.float64, device=self.dev)
         self.counts = torch.empty(K, dtype=torch.float64, device=self.dev)
         self.stats = torch.empty(4, dtype=torch.float64, device=self.dev)
+        self.status = torch.empty(4, dtype=torch.float64, device=self.dev)
+
+    def update(self, centers):
+        """M-step in place on `centers`; returns (changed, shift2, n_empty, inertia) with ONE sync."""
+        with torch.cuda.device(self.dev):
+            _lib.check(_lib.lib().dic_kmeans_update(
+                _lib.ptr(self.sums), _lib.ptr(self.counts), _lib.ptr(self.stats), _lib.ptr(centers),
+                _lib.ptr(self.status), self.D, centers.shape[0], self.dt, _lib.current_stream(self.dev)),
+                "dic_kmeans_update")
+        return self.status.tolist()
 
     def assign(self, centers, flags=0, want_sums=True, labels=None):
         labels = self.labels if labels is None else labels
@@ -260,13 +270,22 @@ class KMeansB200:
             n_iter = i + 1
             st.assign(centers, DIC_KM_COUNT_CHANGES)
             comm.sum_(st.sums, st.counts, st.stats)          # the one exchange step per iteration
-            changed, n_empty = st.stats[1], (st.counts == 0).sum()
-            if int(n_empty) > 0:
-                self._relocate_empty(st, centers, comm)
-            cnt = st.counts.clamp(min=1.0)[:, None]
-            new = torch.where(st.counts[:, None] > 0, st.sums / cnt, centers.to(torch.float64)).to(centers.dtype)
-            shift2 = float(((new - centers).to(torch.float64) ** 2).sum())
-            centers = new
+            if hasattr(st, "update"):
+                old = centers.clone()
+                changed, shift2, n_empty, _ = st.update(centers)        # in place, one host sync
+                if n_empty > 0:                                           # rare: redo the M-step on the host
+                    centers = old
+                    changed = None
+            else:
+                changed = None
+            if changed is None:
+                changed = float(st.stats[1])
+                if int((st.counts == 0).sum()) > 0:
+                    self._relocate_empty(st, centers, comm)
+                cnt = st.counts.clamp(min=1.0)[:, None]
+                new = torch.where(st.counts[:, None] > 0, st.sums / cnt, centers.to(torch.float64)).to(centers.dtype)
+                shift2 = float(((new - centers).to(torch.float64) ** 2).sum())
+                centers = new
             if int(changed) == 0:
                 strict = True
                 break
