@@ -48,13 +48,17 @@ __global__ void colsum_stage1(const float* __restrict__ a, double* __restrict__ 
 __global__ void colsum_stage2(const double* __restrict__ ws, double* __restrict__ out_f64,
                               float* __restrict__ out_f32, const float* __restrict__ scale_by,
                               int nblocks, int cols) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);     // one warp per column
   if (c >= cols) return;
   double t = 0.0;
-  for (int i = 0; i < nblocks; ++i) t += ws[(int64_t)i * cols + c];
-  if (scale_by) t *= (double)scale_by[c];
-  if (out_f64) out_f64[c] = t;
-  if (out_f32) out_f32[c] = (float)t;
+  for (int i = lane; i < nblocks; i += 32) t += ws[(int64_t)i * cols + c];
+  t = warp_sum(t);
+  if (lane == 0) {
+    if (scale_by) t *= (double)scale_by[c];
+    if (out_f64) out_f64[c] = t;
+    if (out_f32) out_f32[c] = (float)t;
+  }
 }
 
 // ---- roofline probes ------------------------------------------------------------------
@@ -126,7 +130,7 @@ int colsum_f32_launch(const float* a, double* out_f64, float* out_f32, const flo
   const int64_t rpb = (rows + nblocks - 1) / nblocks;
   colsum_stage1<<<nblocks, threads, threads * sizeof(double), stream>>>(a, workspace, rows, cols, rpb);
   DIC_LAUNCH_CHECK("colsum_stage1");
-  colsum_stage2<<<(cols + 127) / 128, 128, 0, stream>>>(workspace, out_f64, out_f32, scale_by, nblocks, cols);
+  colsum_stage2<<<(cols + 7) / 8, 256, 0, stream>>>(workspace, out_f64, out_f32, scale_by, nblocks, cols);
   DIC_LAUNCH_CHECK("colsum_stage2");
   return DIC_OK;
 }

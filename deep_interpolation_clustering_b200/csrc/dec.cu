@@ -135,11 +135,13 @@ dec_q_fwd_kernel(const float* __restrict__ z, const float* __restrict__ mu, floa
 
 __global__ void sum_blocks_f64_kernel(const double* __restrict__ ws, double* __restrict__ out, int nblocks,
                                       int cols) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);     // one warp per column
   if (c >= cols) return;
   double t = 0.0;
-  for (int i = 0; i < nblocks; ++i) t += ws[(int64_t)i * cols + c];
-  out[c] = t;
+  for (int i = lane; i < nblocks; i += 32) t += ws[(int64_t)i * cols + c];
+  t = warp_sum(t);
+  if (lane == 0) out[c] = t;
 }
 
 // p from q and the (global) column sum: one thread per row.
@@ -274,22 +276,25 @@ dec_bwd_kernel(const float* __restrict__ z, const float* __restrict__ mu, const 
 __global__ void dec_bwd_finish_kernel(const float* __restrict__ ws, const float* __restrict__ mu,
                                       float* __restrict__ grad_mu, double* __restrict__ kl_sum, int nblocks,
                                       int K, int D) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);     // one warp per element (+1 for kl)
   const int stride = K * D + K + 2;
   if (i < K * D) {
     const int j = i / D;
     double s = 0.0, cs = 0.0;
-    for (int b = 0; b < nblocks; ++b) {
+    for (int b = lane; b < nblocks; b += 32) {
       s += (double)ws[(int64_t)b * stride + i];
       cs += (double)ws[(int64_t)b * stride + K * D + j];
     }
-    grad_mu[i] = (float)(-s + cs * (double)mu[i]);
-  }
-  if (i == 0 && kl_sum) {
+    s = warp_sum(s);
+    cs = warp_sum(cs);
+    if (lane == 0) grad_mu[i] = (float)(-s + cs * (double)mu[i]);
+  } else if (i == K * D && kl_sum) {
     double t = 0.0;
-    for (int b = 0; b < nblocks; ++b)
+    for (int b = lane; b < nblocks; b += 32)
       t += (double)ws[(int64_t)b * stride + K * D + K] + (double)ws[(int64_t)b * stride + K * D + K + 1];
-    *kl_sum = t;
+    t = warp_sum(t);
+    if (lane == 0) *kl_sum = t;
   }
 }
 
@@ -389,7 +394,7 @@ int launch_bwd(int mode, const float* z, const float* mu, const float* grad_q, c
   });
   if (rc) return rc;
   DIC_LAUNCH_CHECK("dec_bwd_kernel");
-  dec_bwd_finish_kernel<<<(K * D + 255) / 256, 256, 0, st>>>(ws, mu, grad_mu, kl_sum, blocks, K, D);
+  dec_bwd_finish_kernel<<<(K * D + 1 + 7) / 8, 256, 0, st>>>(ws, mu, grad_mu, kl_sum, blocks, K, D);
   DIC_LAUNCH_CHECK("dec_bwd_finish_kernel");
   return DIC_OK;
 }
@@ -434,7 +439,7 @@ extern "C" int dic_dec_q_fwd(const float* z, const float* mu, float* q, int32_t*
   if (rc) return rc;
   DIC_LAUNCH_CHECK("dec_q_fwd_kernel");
   if (colsum) {
-    sum_blocks_f64_kernel<<<1, 64, 0, st>>>(ws, colsum, blocks, K);
+    sum_blocks_f64_kernel<<<(K + 7) / 8, 256, 0, st>>>(ws, colsum, blocks, K);
     DIC_LAUNCH_CHECK("sum_blocks_f64_kernel");
   }
   return DIC_OK;

@@ -399,21 +399,23 @@ kmeans_assign_fast_kernel(const T* __restrict__ X, const T* __restrict__ centers
   if (tid == 3) out[(int64_t)K * D + K + 3] = 0.0;
 }
 
+// One warp per output element: lanes stride over the per-block partials (independent loads in
+// flight), then a fixed-order shuffle reduction -> deterministic and latency-tolerant.
 __global__ void kmeans_finish_kernel(const double* __restrict__ ws, double* __restrict__ sums,
                                      double* __restrict__ counts, double* __restrict__ stats, int nblocks,
                                      int K, int D) {
   const int64_t stride = (int64_t)K * D + K + 4;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int nsum = sums ? K * D + K : 0;
-  if (i < nsum) {
-    double s = 0.0;
-    for (int b = 0; b < nblocks; ++b) s += ws[b * stride + i];
-    if (i < K * D) sums[i] = s; else counts[i - K * D] = s;
-  }
-  if (i < 4) {
-    double s = 0.0;
-    for (int b = 0; b < nblocks; ++b) s += ws[b * stride + (int64_t)K * D + K + i];
-    stats[i] = s;
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);     // element of [sums | counts | stats]
+  if (i >= K * D + K + 4) return;
+  if (!sums && i < K * D + K) return;
+  double s = 0.0;
+  for (int b = lane; b < nblocks; b += 32) s += ws[b * stride + i];
+  s = warp_sum(s);
+  if (lane == 0) {
+    if (i < K * D) sums[i] = s;
+    else if (i < K * D + K) counts[i - K * D] = s;
+    else stats[i - K * D - K] = s;
   }
 }
 
@@ -512,11 +514,13 @@ kmeans_min_d2_kernel(const T* __restrict__ X, const T* __restrict__ cands, const
 }
 
 __global__ void sum_blocks_kernel(const double* __restrict__ ws, double* __restrict__ out, int nblocks, int cols) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);     // one warp per column
   if (c >= cols) return;
   double s = 0.0;
-  for (int b = 0; b < nblocks; ++b) s += ws[(int64_t)b * cols + c];
-  out[c] = s;
+  for (int b = lane; b < nblocks; b += 32) s += ws[(int64_t)b * cols + c];
+  s = warp_sum(s);
+  if (lane == 0) out[c] = s;
 }
 
 // ---- pairwise Euclidean distance sum ----------------------------------------------------------
@@ -634,7 +638,7 @@ int launch_assign(const void* X, const void* centers, int32_t* labels, double* s
 #undef DIC_KM_LAUNCH
     DIC_LAUNCH_CHECK("kmeans_assign_fast_kernel");
     const int nn = K * D + K + 4;
-    kmeans_finish_kernel<<<(nn + 255) / 256, 256, 0, st>>>(wsd, sums, counts, stats, nb, K, D);
+    kmeans_finish_kernel<<<(nn + 7) / 8, 256, 0, st>>>(wsd, sums, counts, stats, nb, K, D);
     DIC_LAUNCH_CHECK("kmeans_finish_kernel");
     return DIC_OK;
   }
@@ -656,7 +660,7 @@ int launch_assign(const void* X, const void* centers, int32_t* labels, double* s
                                       N, D, K, s16, flags, L, sums != nullptr);
   DIC_LAUNCH_CHECK("kmeans_assign_kernel");
   const int n = K * D + K + 4;
-  kmeans_finish_kernel<<<(n + 255) / 256, 256, 0, st>>>(ws, sums, counts, stats, blocks, K, D);
+  kmeans_finish_kernel<<<(n + 7) / 8, 256, 0, st>>>(ws, sums, counts, stats, blocks, K, D);
   DIC_LAUNCH_CHECK("kmeans_finish_kernel");
   return DIC_OK;
 }
@@ -676,7 +680,7 @@ int launch_min_d2(const void* X, const void* cands, const void* min_d2, void* mi
                                           static_cast<const T*>(min_d2), static_cast<T*>(min_d2_out), ws, N,
                                           D, L);
   DIC_LAUNCH_CHECK("kmeans_min_d2_kernel");
-  sum_blocks_kernel<<<1, 32, 0, st>>>(ws, pots, blocks, L);
+  sum_blocks_kernel<<<(L + 7) / 8, 256, 0, st>>>(ws, pots, blocks, L);
   DIC_LAUNCH_CHECK("sum_blocks_kernel");
   return DIC_OK;
 }
@@ -690,7 +694,7 @@ int launch_pairwise(const void* X, double* out, void* workspace, int64_t n, int 
   double* ws = static_cast<double*>(workspace);
   pairwise_sum_kernel<T><<<blocks, kPwThreads, 0, st>>>(static_cast<const T*>(X), ws, n, D);
   DIC_LAUNCH_CHECK("pairwise_sum_kernel");
-  sum_blocks_kernel<<<1, 32, 0, st>>>(ws, out, blocks, 1);
+  sum_blocks_kernel<<<1, 256, 0, st>>>(ws, out, blocks, 1);
   DIC_LAUNCH_CHECK("sum_blocks_kernel");
   return DIC_OK;
 }
