@@ -44,7 +44,7 @@ template <typename T> static inline int row_stride16(int D) {
 }
 
 struct KmLayout {
-  size_t off_c, off_cn, off_acc, off_cnt, off_lab, off_x, total;
+  size_t off_c, off_cn, off_acc, off_cnt, off_lab, off_x, off_x2, off_bar, total;
 };
 template <typename T> static KmLayout km_layout(int K, int D, int tile) {
   const int s16 = row_stride16<T>(D);
@@ -63,8 +63,15 @@ template <typename T> static KmLayout km_layout(int K, int D, int tile) {
   o = (o + 15) & ~(size_t)15;
   L.off_cnt = o; o += (size_t)K * sizeof(int);
   L.off_lab = o; o += (size_t)tile * sizeof(int);
+  o = (o + 15) & ~(size_t)15;
+  L.off_bar = o; o += 16;                                   // two mbarriers
+  L.off_x2 = 0;                                             // second tile buffer: see km_add_buffer
   L.total = (o + 15) & ~(size_t)15;
   return L;
+}
+template <typename T> static void km_add_buffer(KmLayout& L, int D, int tile) {
+  L.off_x2 = L.total;
+  L.total += (size_t)tile * row_stride16<T>(D) * 16;
 }
 
 template <typename T>
@@ -218,20 +225,35 @@ kmeans_assign_fast_kernel(const T* __restrict__ X, const T* __restrict__ centers
   constexpr int PER = Vec16<T>::n;
   extern __shared__ __align__(16) unsigned char smem[];
   V* sc = reinterpret_cast<V*>(smem + L.off_c);
-  V* sx = reinterpret_cast<V*>(smem + L.off_x);
+  V* sx0 = reinterpret_cast<V*>(smem + L.off_x);
   T* scn = reinterpret_cast<T*>(smem + L.off_cn);
   int* scnt = reinterpret_cast<int*>(smem + L.off_cnt);
   int* slab = reinterpret_cast<int*>(smem + L.off_lab);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.off_bar);
   const int tid = threadIdx.x;
   const int Dp = s16 * PER;
+  // Tile loads.  Fast path: every thread issues ONE 1-D TMA bulk copy (its row, D*sizeof(T) bytes)
+  // into its padded shared row, completion on an mbarrier; with a second buffer the next tile
+  // streams in while this one is processed.  Fallback: element-wise loads without division.
+  const bool vec = vec_ok != 0;
+  const bool two = vec && L.off_x2 != 0;
+  V* sx1 = two ? reinterpret_cast<V*>(smem + L.off_x2) : sx0;
 
   for (int i = tid; i < K * Dp; i += kKmTile) {
     const int k = i / Dp, d = i - k * Dp;
     reinterpret_cast<T*>(sc)[i] = d < D ? centers[(int64_t)k * D + d] : T(0);
   }
-  for (int i = tid; i < kKmTile * Dp; i += kKmTile) reinterpret_cast<T*>(sx)[i] = T(0);   // pad columns stay 0
+  for (int i = tid; i < kKmTile * Dp; i += kKmTile) {          // pad columns stay 0 for good
+    reinterpret_cast<T*>(sx0)[i] = T(0);
+    if (two) reinterpret_cast<T*>(sx1)[i] = T(0);
+  }
   for (int i = tid; i < K; i += kKmTile) scnt[i] = 0;
+  if (vec && tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+  }
   __syncthreads();
+  if (vec) fence_proxy_async();          // generic-proxy zero fill / barrier init before async-proxy writes
   for (int k = tid; k < K; k += kKmTile) {
     T s = T(0);
     for (int d = 0; d < D; ++d) {
@@ -242,12 +264,17 @@ kmeans_assign_fast_kernel(const T* __restrict__ X, const T* __restrict__ centers
   }
   __syncthreads();
 
-  // tile-load walk: 16-byte units when the row size allows, else elements; (row, col) advance
-  // incrementally so the loop has no division
-  const bool vec = vec_ok != 0;
-  const int units = vec ? D / PER : D;                 // units per row
-  const int u_r0 = tid / units, u_j0 = tid - u_r0 * units;
-  const int u_dr = kKmTile / units, u_dj = kKmTile - u_dr * units;
+  const uint32_t row_bytes = (uint32_t)D * (uint32_t)sizeof(T);
+  const int64_t ntiles = (N + kKmTile - 1) / kKmTile;
+  auto issue = [&](int64_t t, int buf) {
+    const int64_t r0 = t * kKmTile;
+    const int nr = (int)min((int64_t)kKmTile, N - r0);
+    V* dst = buf ? sx1 : sx0;
+    if (tid == 0) mbar_expect_tx(&bars[buf], (uint32_t)nr * row_bytes);
+    if (tid < nr) bulk_g2s(dst + tid * s16, X + (r0 + tid) * D, row_bytes, &bars[buf]);
+  };
+  const int u_r0 = tid / D, u_j0 = tid - u_r0 * D;
+  const int u_dr = kKmTile / D, u_dj = kKmTile - u_dr * D;
   // phase-2 ownership: column d of row group g (G groups), or NC columns when D > tile
   const int G = D < kKmTile ? kKmTile / D : 1;
   const int g = D < kKmTile ? tid / D : 0;
@@ -261,29 +288,27 @@ kmeans_assign_fast_kernel(const T* __restrict__ X, const T* __restrict__ centers
 
   double inertia = 0.0, dist_sum = 0.0;
   int changed = 0;
-  const int64_t ntiles = (N + kKmTile - 1) / kKmTile;
-  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+  if (two && (int64_t)blockIdx.x < ntiles) issue(blockIdx.x, 0);
+  int iter = 0;
+  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++iter) {
     const int64_t row0 = t * kKmTile;
     const int rows = (int)min((int64_t)kKmTile, N - row0);
-    {
+    const int buf = two ? (iter & 1) : 0;
+    V* const sx = buf ? sx1 : sx0;
+    if (vec) {
+      if (!two) issue(t, 0);
+      else if (t + gridDim.x < ntiles) issue(t + gridDim.x, buf ^ 1);     // prefetch the next tile
+      mbar_wait(&bars[buf], two ? (uint32_t)((iter >> 1) & 1) : (uint32_t)(iter & 1));
+    } else {
       int r = u_r0, j = u_j0;
-      if (vec) {
-        const V* src = reinterpret_cast<const V*>(X + row0 * D);
-        for (int i = tid; i < rows * units; i += kKmTile) {
-          sx[r * s16 + j] = src[i];
-          r += u_dr; j += u_dj;
-          if (j >= units) { j -= units; ++r; }
-        }
-      } else {
-        const T* src = X + row0 * D;
-        for (int i = tid; i < rows * units; i += kKmTile) {
-          reinterpret_cast<T*>(sx)[r * Dp + j] = src[i];
-          r += u_dr; j += u_dj;
-          if (j >= units) { j -= units; ++r; }
-        }
+      const T* src = X + row0 * D;
+      for (int i = tid; i < rows * D; i += kKmTile) {
+        reinterpret_cast<T*>(sx)[r * Dp + j] = src[i];
+        r += u_dr; j += u_dj;
+        if (j >= D) { j -= D; ++r; }
       }
+      __syncthreads();
     }
-    __syncthreads();
 
     if (tid < rows) {
       const V* xr = sx + tid * s16;
@@ -354,14 +379,14 @@ kmeans_assign_fast_kernel(const T* __restrict__ X, const T* __restrict__ centers
 #undef DIC_KM_CASE
       }
     }
-    __syncthreads();
+    __syncthreads();     // everyone is done with this buffer (and slab) before it is refilled
   }
 
   // per-block partials: [K*D] sums | [K] counts | inertia | changed | dist_sum | 0
   double* out = ws + (int64_t)blockIdx.x * ((int64_t)K * D + K + 4);
   if (want_sums) {
     // fold the G row groups through shared memory (the tile buffer is free now)
-    T* fold = reinterpret_cast<T*>(sx);                  // [G][K][D]
+    T* fold = reinterpret_cast<T*>(sx0);                 // [G][K][D]
     if (owner) {
 #pragma unroll
       for (int k = 0; k < KR; ++k)
@@ -380,7 +405,7 @@ kmeans_assign_fast_kernel(const T* __restrict__ X, const T* __restrict__ centers
     for (int i = tid; i < K; i += kKmTile) out[(int64_t)K * D + i] = (double)scnt[i];
     __syncthreads();
   }
-  double* red = reinterpret_cast<double*>(sx);
+  double* red = reinterpret_cast<double*>(sx0);
   inertia = warp_sum(inertia);
   dist_sum = warp_sum(dist_sum);
   double ch = warp_sum((double)changed);
@@ -620,6 +645,11 @@ int launch_assign(const void* X, const void* centers, int32_t* labels, double* s
     if (nt < nb) nb = (int)nt;
     if (nb < 1) nb = 1;
     double* wsd = static_cast<double*>(workspace);
+    {
+      KmLayout L2 = L;
+      km_add_buffer<T>(L2, D, kKmTile);
+      if (L2.total <= 72 * 1024) L = L2;          // double-buffer when >= 3 CTAs per SM still fit
+    }
     const int kr = K <= 4 ? 4 : (K <= 8 ? 8 : 16);
     const int nc = D <= kKmTile ? 1 : (D <= 2 * kKmTile ? 2 : 4);
 #define DIC_KM_LAUNCH(KR_, NC_)                                                                          \

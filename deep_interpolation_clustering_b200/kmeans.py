@@ -200,7 +200,8 @@ class KMeansB200:
         K, N = self.n_clusters, st.N
         trials = 2 + int(np.log(K))
         centers = torch.empty((K, st.D), dtype=st.X.dtype, device=st.dev)
-        first = int(rng.choice(n_global, p=np.full(n_global, 1.0 / n_global)))
+        # sklearn: random_state.choice(n, p=uniform) = one random_sample() through a uniform cdf
+        first = min(int(rng.random_sample() * n_global), n_global - 1)
         centers[0] = self._rows(st, comm, torch.tensor([first], device=st.dev), offset)[0]
         closest = torch.empty(N, dtype=st.X.dtype, device=st.dev)
         pot = st.min_d2(centers[0:1], None, closest)
