@@ -13,9 +13,16 @@
 // gives each thread one row against all K centres (centres broadcast from shared memory, 4
 // centres register-blocked), phase 2 re-maps threads to columns and adds the tile into
 // per-CTA [K][D] sums (no atomics on the data path).  HBM-bound: N*D*sizeof(T) bytes/pass.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace dic {
+// tensor-core path (pairwise_tc.cu)
+size_t pairwise_tc_workspace_bytes(int64_t n);
+bool pairwise_tc_supported(const void* X, int D);
+int launch_pairwise_tc(const float* X, double* out, void* workspace, int64_t n, int D, cudaStream_t st);
+
 namespace {
 
 template <typename T> struct Vec16;
@@ -791,8 +798,9 @@ extern "C" int dic_kmeans_min_d2(const void* X, const void* cands, const void* m
 }
 
 extern "C" size_t dic_pairwise_workspace_bytes(int64_t n) {
-  (void)n;
-  return (size_t)kPwBlocks * sizeof(double) + 256;
+  const size_t a = (size_t)kPwBlocks * sizeof(double) + 256;
+  const size_t b = pairwise_tc_workspace_bytes(n < 0 ? 0 : n);
+  return a > b ? a : b;
 }
 
 extern "C" int dic_pairwise_dist_sum(const void* Xc, double* out, void* workspace, int64_t n, int D, int dtype,
@@ -805,6 +813,11 @@ extern "C" int dic_pairwise_dist_sum(const void* Xc, double* out, void* workspac
     DIC_CUDA(cudaMemsetAsync(out, 0, sizeof(double), st));
     return DIC_OK;
   }
+  // float32 clusters of useful size go to the tensor-core kernel (3xTF32, float32-grade dots);
+  // DIC_PAIRWISE_EXACT=1 forces the direct (x_i - x_j)^2 CUDA-core kernel, float64 always uses it.
+  static const bool force_exact = getenv("DIC_PAIRWISE_EXACT") != nullptr;
+  if (dtype == 0 && !force_exact && n >= 512 && pairwise_tc_supported(Xc, D))
+    return launch_pairwise_tc(static_cast<const float*>(Xc), out, workspace, n, D, st);
   return dtype == 0 ? launch_pairwise<float>(Xc, out, workspace, n, D, st)
                     : launch_pairwise<double>(Xc, out, workspace, n, D, st);
 }

@@ -63,8 +63,10 @@ def test_inertia_definitions(golden):
     km = KM(5)
     record("inertia_v1_f32", km.compute_inertia_v1(a, X), g["inertia_v1_f32"], 1e-5, 0)
     record("inertia_v2_f32", km.computer_intertia_v2(a, X), g["inertia_v2_f32"], 1e-5, 0)
-    record("inertia_v1_f64", km.compute_inertia_v1(a, X.astype(np.float64)), g["inertia_v1_f64"], 1e-9, 0)
-    record("inertia_v2_f64", km.computer_intertia_v2(a, X.astype(np.float64)), g["inertia_v2_f64"], 1e-9, 0)
+    kx = KM(5, exact_pairwise=True)             # direct float64 kernel (the default goes to the tensor cores)
+    record("inertia_v1_f64", kx.compute_inertia_v1(a, X.astype(np.float64)), g["inertia_v1_f64"], 1e-9, 0)
+    record("inertia_v2_f64", kx.computer_intertia_v2(a, X.astype(np.float64)), g["inertia_v2_f64"], 1e-9, 0)
+    record("inertia_v1_f64_tc", km.compute_inertia_v1(a, X.astype(np.float64)), g["inertia_v1_f64"], 1e-6, 0)
 
 
 class _FixedInit:
@@ -139,3 +141,20 @@ def test_errors():
         KMeansB200(n_clusters=5).fit(np.zeros((3, 4), np.float32))
     with pytest.raises(ValueError):
         KMeansB200(n_clusters=2, init=np.zeros((3, 4))).fit(np.zeros((10, 4), np.float32))
+
+
+@pytest.mark.parametrize("n,D", [(3000, 64), (1000, 40), (700, 256), (4097, 8)])
+def test_tensor_core_pairwise_matches_exact(n, D):
+    """tcgen05 (3xTF32) pairwise-distance sum vs the direct float64 kernel and numpy."""
+    from deep_interpolation_clustering_b200 import synth
+    from deep_interpolation_clustering_b200.gap import pairwise_dist_sum
+    X = synth.make_blobs(n, D, 3, seed=n)
+    Xd = torch.from_numpy(X).cuda()
+    tc = float(pairwise_dist_sum(Xd))
+    exact = float(pairwise_dist_sum(Xd.double(), exact=True))
+    assert np.isfinite(tc), "tensor-core kernel reported a timeout (NaN)"
+    record(f"pairwise_tc_n{n}_D{D}", tc, exact, 2e-6, 0)
+    if n <= 3000:
+        X64 = X.astype(np.float64)
+        ref = np.sqrt(np.maximum(((X64[:, None, :] - X64[None]) ** 2).sum(2), 0)).sum()
+        record(f"pairwise_exact_n{n}_D{D}", exact, ref, 1e-10, 0)
