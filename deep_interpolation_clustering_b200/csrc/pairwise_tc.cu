@@ -14,8 +14,12 @@
 //   * operands sit in the canonical no-swizzle K-major UMMA layout (8-row x 16-byte core matrices);
 //     the row block of a tile row is kept in shared memory and reused across the tiles of that row.
 //   * upper triangle only: off-diagonal tiles count twice; the diagonal is excluded explicitly.
-//   * the epilogue is the bound (one sqrt per pair): 8 warps read TMEM (warp w -> lanes 32 (w & 3),
-//     columns 64 (w >> 2)), form ni + nj - 2 dot, clamp, sqrt.approx, and keep float64 sums.
+//   * warp-specialised: 4 loader warps stage the next column block while the tensor core multiplies
+//     the current one into one of two TMEM accumulators and 4 epilogue warps drain the other
+//     (tcgen05.ld, ni + nj - 2 dot, clamp, sqrt.approx, float64 sums); mbarriers carry the
+//     stage-free / accumulator-full / accumulator-empty hand-offs.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace dic {
@@ -27,13 +31,17 @@ constexpr int kThreads = 256;
 constexpr int kTileBytes = kTile * kKC * 4;          // 32 KB per operand tile
 constexpr int kChunkStride = kTile * 16;             // bytes between consecutive 16-byte K chunks (LBO)
 constexpr int kGroupStride = 128;                    // bytes between 8-row groups (SBO)
-constexpr uint32_t kTmemCols = 128;
+constexpr uint32_t kTmemCols = 256;       // two 128-column accumulators
 
 struct __align__(16) TcSmem {
-  // operand tiles first (16-byte aligned), then scalars
-  unsigned char a_hi[kTileBytes], a_lo[kTileBytes], b_hi[kTileBytes], b_lo[kTileBytes];
-  float nj[kTile];
-  uint64_t bar;
+  // operand tiles first (16-byte aligned): the row block A (kept across a tile row) and a
+  // double-buffered column block B; then the pipeline state
+  unsigned char a_hi[kTileBytes], a_lo[kTileBytes];
+  unsigned char b_hi[2][kTileBytes], b_lo[2][kTileBytes];
+  float nj[kTile];        // column norms of the tile in the epilogue (owned by the epilogue warps)
+  uint64_t se[2];         // smem stage empty  (tensor core -> loaders,  tcgen05.commit)
+  uint64_t tf[2];         // TMEM accumulator full (tensor core -> epilogue, tcgen05.commit)
+  uint64_t te[2];         // TMEM accumulator empty (epilogue -> MMA issuer, 128 arrivals)
   uint32_t tmem_base;
   int timeout;
 };
@@ -120,21 +128,50 @@ __device__ __forceinline__ float sqrt_approx(float x) {
   return y;
 }
 
-// rows r0.. of X (n x D), K elements [k0, k0 + 64) -> hi / lo operand tiles in the UMMA layout.
-// Consecutive threads take consecutive rows of one 16-byte chunk: shared stores are contiguous
-// (conflict-free); the strided global reads come from L1/L2 (a row block is reused many times).
-__device__ __forceinline__ void load_split_tile(const float* __restrict__ X, int64_t n, int D, int64_t r0, int k0,
-                                                unsigned char* hi, unsigned char* lo) {
-  for (int idx = threadIdx.x; idx < kTile * (kKC / 4); idx += kThreads) {
-    const int c = idx >> 7, r = idx & (kTile - 1);
-    const int64_t gr = r0 + r;
-    const int k = k0 + 4 * c;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (gr < n && k < D) v = __ldg(reinterpret_cast<const float4*>(X + gr * D + k));   // D % 4 == 0
+// rows r0.. of X (n x D), K elements [k0, k0 + 64) -> hi / lo operand tiles in the UMMA layout, in
+// two halves so that the global loads of the NEXT tile are in flight while the current one is
+// converted and multiplied.  128 loader threads, 16 float4 each: a warp step covers 8 rows x 4
+// chunks, so every touched 32-byte sector is fully used and the four 128-byte groups of the
+// shared store are contiguous (4 wavefronts, the minimum for 512 bytes).
+struct TileRegs {
+  float4 v[16];
+};
+__device__ __forceinline__ void tile_fetch(TileRegs& t, const float* __restrict__ X, int64_t n, int D, int64_t r0,
+                                           int k0, int lt) {
+  const int lane = lt & 31, w = lt >> 5;
+  const int rl = lane & 7, cl = lane >> 3;
+  const bool interior = (r0 + kTile <= n) && (k0 + kKC <= D);
+  const float* base = X + (r0 + rl) * D + k0 + 4 * cl;
+  if (interior) {
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int step = w + 4 * u;            // step = rg * 4 + cq
+      t.v[u] = __ldg(reinterpret_cast<const float4*>(base + (int64_t)(step >> 2) * 8 * D + (step & 3) * 16));
+    }
+  } else {
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int step = w + 4 * u;
+      const int64_t gr = r0 + (step >> 2) * 8 + rl;
+      const int k = k0 + (step & 3) * 16 + 4 * cl;
+      t.v[u] = (gr < n && k < D)
+                   ? __ldg(reinterpret_cast<const float4*>(base + (int64_t)(step >> 2) * 8 * D + (step & 3) * 16))
+                   : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+}
+__device__ __forceinline__ void tile_store(const TileRegs& t, unsigned char* hi, unsigned char* lo, int lt) {
+  const int lane = lt & 31, w = lt >> 5;
+  const int rl = lane & 7, cl = lane >> 3;
+#pragma unroll
+  for (int u = 0; u < 16; ++u) {
+    const int step = w + 4 * u;
+    const int rg = step >> 2, c = (step & 3) * 4 + cl;
     float4 h, l;     // hi = rn_tf32(x), lo = rn_tf32(x - hi): round-to-nearest keeps the split unbiased
-    h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
-    l.x = to_tf32(v.x - h.x); l.y = to_tf32(v.y - h.y); l.z = to_tf32(v.z - h.z); l.w = to_tf32(v.w - h.w);
-    const int off = c * kChunkStride + (r >> 3) * kGroupStride + (r & 7) * 16;
+    h.x = to_tf32(t.v[u].x); h.y = to_tf32(t.v[u].y); h.z = to_tf32(t.v[u].z); h.w = to_tf32(t.v[u].w);
+    l.x = to_tf32(t.v[u].x - h.x); l.y = to_tf32(t.v[u].y - h.y);
+    l.z = to_tf32(t.v[u].z - h.z); l.w = to_tf32(t.v[u].w - h.w);
+    const int off = c * kChunkStride + rg * kGroupStride + rl * 16;
     *reinterpret_cast<float4*>(hi + off) = h;
     *reinterpret_cast<float4*>(lo + off) = l;
   }
@@ -153,15 +190,40 @@ __global__ void row_norms_kernel(const float* __restrict__ X, float* __restrict_
   if (lane == 0) norms[row] = s;
 }
 
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void unrank_tile(int64_t t, int64_t nb, int64_t& bi, int64_t& bj) {
+  // row-major enumeration of the upper triangle (bi <= bj)
+  bi = (int64_t)((2.0 * nb + 1.0 - sqrt((2.0 * nb + 1.0) * (2.0 * nb + 1.0) - 8.0 * (double)t)) * 0.5);
+  while (bi * nb - bi * (bi - 1) / 2 > t) --bi;
+  while ((bi + 1) * nb - (bi + 1) * bi / 2 <= t) ++bi;
+  bj = bi + (t - (bi * nb - bi * (bi - 1) / 2));
+}
+
+// Warp-specialised pipeline (one persistent CTA per SM, 8 warps):
+//   warps 4-7  loaders: stage the column block of tile i+1 (split into hi/lo) while the tensor core
+//              works on tile i; thread 128 issues the MMAs of a tile and commits them to two
+//              mbarriers (stage free, accumulator full)
+//   warps 0-3  epilogue: tcgen05.ld the accumulator of tile i (TMEM lanes 32 w .. 32 w + 31), form
+//              the distances and sum them while tile i+1 is being multiplied into the other
+//              accumulator
 __global__ void __launch_bounds__(kThreads, 1)
 pairwise_tc_kernel(const float* __restrict__ X, const float* __restrict__ norms, double* __restrict__ partial,
-                   int64_t n, int D) {
+                   int64_t n, int D, long long* __restrict__ dbg) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   TcSmem& S = *reinterpret_cast<TcSmem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
-    mbar_init(&S.bar, 1);
+    for (int k = 0; k < 2; ++k) {
+      mbar_init(&S.se[k], 1);
+      mbar_init(&S.tf[k], 1);
+      mbar_init(&S.te[k], kTile);
+    }
     S.timeout = 0;
     fence_proxy_async();
   }
@@ -174,72 +236,137 @@ pairwise_tc_kernel(const float* __restrict__ X, const float* __restrict__ norms,
   const int64_t nb = (n + kTile - 1) / kTile;
   const int64_t ntiles = nb * (nb + 1) / 2;
   const int kchunks = (D + kKC - 1) / kKC;
-  const bool keep_a = kchunks == 1;               // the row block stays resident across a tile row
-  int64_t cur_bi = -1;
-  uint32_t phase = 0;
   double total = 0.0;
-  const uint32_t a_hi = smem_u32(S.a_hi), a_lo = smem_u32(S.a_lo), b_hi = smem_u32(S.b_hi), b_lo = smem_u32(S.b_lo);
 
-  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-    // unrank t -> (bi <= bj), row-major over the upper triangle
-    int64_t bi = (int64_t)((2.0 * nb + 1.0 - sqrt((2.0 * nb + 1.0) * (2.0 * nb + 1.0) - 8.0 * (double)t)) * 0.5);
-    while (bi * nb - bi * (bi - 1) / 2 > t) --bi;
-    while ((bi + 1) * nb - (bi + 1) * bi / 2 <= t) ++bi;
-    const int64_t bj = bi + (t - (bi * nb - bi * (bi - 1) / 2));
-    const int64_t i0 = bi * kTile, j0 = bj * kTile;
-
-    for (int kc = 0; kc < kchunks; ++kc) {
-      if (!(keep_a && bi == cur_bi)) load_split_tile(X, n, D, i0, kc * kKC, S.a_hi, S.a_lo);
-      load_split_tile(X, n, D, j0, kc * kKC, S.b_hi, S.b_lo);
-      if (kc == 0 && tid < kTile) S.nj[tid] = (j0 + tid < n) ? __ldg(norms + j0 + tid) : 0.f;
-      fence_proxy_async();            // generic-proxy stores -> visible to the tensor core (async proxy)
-      tc_fence_before();              // previous tile's tcgen05.ld ordered before this tile's MMAs
-      __syncthreads();
-      if (tid == 0) {
+  if (warp >= 4) {
+    // ================= loaders + MMA issuer =================
+    const int lt = tid - 128;
+    const uint32_t a_hi = smem_u32(S.a_hi), a_lo = smem_u32(S.a_lo);
+    const int64_t nstages = ((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x) * kchunks;   // this CTA's stages
+    int64_t cur_bi = -1;
+    TileRegs breg;                 // the column block of the NEXT stage, already on its way from L2
+    {
+      int64_t bi, bj;
+      unrank_tile(blockIdx.x, nb, bi, bj);
+      tile_fetch(breg, X, n, D, bj * kTile, 0, lt);
+    }
+    for (int64_t stage = 0; stage < nstages; ++stage) {
+      const int64_t i = stage / kchunks;                       // running tile count of this CTA
+      const int kc = (int)(stage - i * kchunks);
+      const int64_t t = blockIdx.x + i * gridDim.x;
+      int64_t bi, bj;
+      unrank_tile(t, nb, bi, bj);
+      const int acc = (int)(i & 1), b = (int)(stage & 1);
+      const int u = (int)(stage >> 1);
+      long long c0 = clock64();
+      if (!bar_wait_bounded(&S.se[b], (uint32_t)((u & 1) ^ 1))) S.timeout = 1;   // stage b free again
+      long long c1 = clock64();
+      if (kchunks > 1 || bi != cur_bi) {
+        // the row block is about to change: the MMAs of the previous stage must be done with it
+        if (stage > 0 && !bar_wait_bounded(&S.se[b ^ 1], (uint32_t)(((stage - 1) >> 1) & 1))) S.timeout = 1;
+        TileRegs areg;
+        tile_fetch(areg, X, n, D, bi * kTile, kc * kKC, lt);
+        tile_store(areg, S.a_hi, S.a_lo, lt);
+        cur_bi = bi;
+      }
+      long long c2 = clock64();
+      tile_store(breg, S.b_hi[b], S.b_lo[b], lt);
+      long long c3 = clock64();
+      if (stage + 1 < nstages) {                               // prefetch the next stage's column block
+        const int64_t i2 = (stage + 1) / kchunks;
+        const int kc2 = (int)(stage + 1 - i2 * kchunks);
+        int64_t bi2, bj2;
+        unrank_tile(blockIdx.x + i2 * gridDim.x, nb, bi2, bj2);
+        tile_fetch(breg, X, n, D, bj2 * kTile, kc2 * kKC, lt);
+      }
+      long long c4 = clock64();
+      fence_proxy_async();         // generic-proxy stores -> visible to the tensor core (async proxy)
+      named_bar_sync(1, 128);
+      long long c5 = clock64();
+      if (dbg && lt == 32 && blockIdx.x == 0) {
+        atomicAdd((unsigned long long*)&dbg[0], (unsigned long long)(c1 - c0));   // wait stage free
+        atomicAdd((unsigned long long*)&dbg[1], (unsigned long long)(c2 - c1));   // row block reload
+        atomicAdd((unsigned long long*)&dbg[2], (unsigned long long)(c3 - c2));   // convert + store
+        atomicAdd((unsigned long long*)&dbg[3], (unsigned long long)(c4 - c3));   // prefetch issue
+        atomicAdd((unsigned long long*)&dbg[4], (unsigned long long)(c5 - c4));   // loader barrier
+        atomicAdd((unsigned long long*)&dbg[5], 1ull);
+      }
+      if (lt == 0) {
+        long long d0 = clock64();
+        if (kc == 0) {             // accumulator drained by the epilogue of tile i - 2
+          if (!bar_wait_bounded(&S.te[acc], (uint32_t)(((i >> 1) & 1) ^ 1))) S.timeout = 1;
+        }
+        if (dbg && blockIdx.x == 0) atomicAdd((unsigned long long*)&dbg[6], (unsigned long long)(clock64() - d0));
         tc_fence_after();
+        const uint32_t d_tmem = tmem + (uint32_t)acc * kTile;
+        const uint32_t b_hi = smem_u32(S.b_hi[b]), b_lo = smem_u32(S.b_lo[b]);
 #pragma unroll
         for (int s = 0; s < kKC / 8; ++s) {        // one MMA consumes K = 8 tf32 = two 16-byte chunks
           const uint32_t koff = (uint32_t)s * 2u * kChunkStride;
           const uint64_t dah = make_desc(a_hi + koff), dal = make_desc(a_lo + koff);
           const uint64_t dbh = make_desc(b_hi + koff), dbl = make_desc(b_lo + koff);
-          umma_tf32(tmem, dah, dbh, kIdesc, (kc > 0 || s > 0) ? 1u : 0u);
-          umma_tf32(tmem, dah, dbl, kIdesc, 1u);
-          umma_tf32(tmem, dal, dbh, kIdesc, 1u);
-          umma_tf32(tmem, dal, dbl, kIdesc, 1u);
+          umma_tf32(d_tmem, dah, dbh, kIdesc, (kc > 0 || s > 0) ? 1u : 0u);
+          umma_tf32(d_tmem, dah, dbl, kIdesc, 1u);
+          umma_tf32(d_tmem, dal, dbh, kIdesc, 1u);
+          umma_tf32(d_tmem, dal, dbl, kIdesc, 1u);
         }
-        umma_commit(&S.bar);          // arrives when every MMA above has completed
+        umma_commit(&S.se[b]);                      // stage b reusable once these MMAs have read it
+        if (kc + 1 == kchunks) umma_commit(&S.tf[acc]);   // accumulator complete -> epilogue
+        if (dbg && blockIdx.x == 0) atomicAdd((unsigned long long*)&dbg[7], (unsigned long long)(clock64() - d0));
       }
-      if (!bar_wait_bounded(&S.bar, phase)) S.timeout = 1;
-      phase ^= 1;
+    }
+  } else {
+    // ================= epilogue =================
+    int i = 0;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++i) {
+      int64_t bi, bj;
+      unrank_tile(t, nb, bi, bj);
+      const int acc = i & 1;
+      const int64_t i0 = bi * kTile, j0 = bj * kTile;
+      named_bar_sync(2, 128);                       // previous tile's reads of nj[] are finished
+      S.nj[tid] = (j0 + tid < n) ? __ldg(norms + j0 + tid) : 0.f;
+      const int64_t gi = i0 + tid;                  // TMEM lane = tile row = thread
+      const float ni = gi < n ? __ldg(norms + gi) : 0.f;
+      named_bar_sync(2, 128);
+      long long e0 = clock64();
+      if (!bar_wait_bounded(&S.tf[acc], (uint32_t)((i >> 1) & 1))) S.timeout = 1;
+      long long e1 = clock64();
       tc_fence_after();
-      if (kc + 1 < kchunks) __syncthreads();   // operand tiles are free again
-    }
-    cur_bi = bi;
-
-    // epilogue: warp w reads TMEM lanes 32 (w & 3), columns 64 (w >> 2) .. +63
-    const int row = 32 * (warp & 3) + lane;
-    const int64_t gi = i0 + row;
-    const float ni = gi < n ? __ldg(norms + gi) : 0.f;
-    float tile_sum = 0.f;
+      float tile_sum = 0.f;
+      const bool plain = (bi != bj) && (i0 + kTile <= n) && (j0 + kTile <= n);   // no diagonal, no ragged edge
+#pragma unroll 1
+      for (int h = 0; h < 4; ++h) {
+        const int col0 = 32 * h;
+        uint32_t v[32];
+        tmem_ld32(tmem + ((uint32_t)(32 * warp) << 16) + (uint32_t)(acc * kTile + col0), v);
+        if (plain) {
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int col0 = 64 * (warp >> 2) + 32 * h;
-      uint32_t v[32];
-      tmem_ld32(tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)col0, v);
-      if (gi < n) {
+          for (int c = 0; c < 32; c += 4) {
+            const float4 nj4 = *reinterpret_cast<const float4*>(&S.nj[col0 + c]);
+            tile_sum += sqrt_approx(fmaxf(fmaf(-2.f, __uint_as_float(v[c + 0]), ni + nj4.x), 0.f));
+            tile_sum += sqrt_approx(fmaxf(fmaf(-2.f, __uint_as_float(v[c + 1]), ni + nj4.y), 0.f));
+            tile_sum += sqrt_approx(fmaxf(fmaf(-2.f, __uint_as_float(v[c + 2]), ni + nj4.z), 0.f));
+            tile_sum += sqrt_approx(fmaxf(fmaf(-2.f, __uint_as_float(v[c + 3]), ni + nj4.w), 0.f));
+          }
+        } else if (gi < n) {
+          const int jmax = (int)min((int64_t)32, n - j0 - col0);       // valid columns in this chunk
+          const int jdiag = (int)(gi - j0 - col0);                      // the diagonal, if inside
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          const int64_t gj = j0 + col0 + c;
-          const float d2 = fmaf(-2.f, __uint_as_float(v[c]), ni + S.nj[col0 + c]);
-          const float d = sqrt_approx(fmaxf(d2, 0.f));
-          tile_sum += (gj < n && gj != gi) ? d : 0.f;
+          for (int c = 0; c < 32; ++c) {
+            const float d2 = fmaf(-2.f, __uint_as_float(v[c]), ni + S.nj[col0 + c]);
+            const float d = sqrt_approx(fmaxf(d2, 0.f));
+            tile_sum += (c < jmax && c != jdiag) ? d : 0.f;
+          }
         }
       }
+      tc_fence_before();
+      mbar_arrive(&S.te[acc]);                      // this thread is done with accumulator `acc`
+      if (dbg && tid == 0 && blockIdx.x == 0) {
+        atomicAdd((unsigned long long*)&dbg[8], (unsigned long long)(e1 - e0));          // wait accumulator
+        atomicAdd((unsigned long long*)&dbg[9], (unsigned long long)(clock64() - e1));   // drain + distances
+      }
+      total += (bi == bj) ? (double)tile_sum : 2.0 * (double)tile_sum;
     }
-    total += (bi == bj) ? (double)tile_sum : 2.0 * (double)tile_sum;
-    // every warp is done with TMEM and with nj[] before the next tile overwrites them
-    tc_fence_before();
-    __syncthreads();
   }
 
   __shared__ double red[kThreads / 32];
@@ -250,7 +377,7 @@ pairwise_tc_kernel(const float* __restrict__ X, const float* __restrict__ norms,
   if (tid == 0) {
     double s = 0.0;
     for (int w = 0; w < kThreads / 32; ++w) s += red[w];
-    partial[blockIdx.x] = S.timeout ? __longlong_as_double(0x7ff8000000000000LL) : s;   // NaN = MMA never completed
+    partial[blockIdx.x] = S.timeout ? __longlong_as_double(0x7ff8000000000000LL) : s;   // NaN = pipeline stalled
   }
   if (warp == 0) {
     tc_fence_after();
@@ -289,7 +416,22 @@ int launch_pairwise_tc(const float* X, double* out, void* workspace, int64_t n, 
   if (blocks > 1024) blocks = 1024;
   const size_t smem = sizeof(TcSmem) + 1024;
   DIC_CUDA(cudaFuncSetAttribute(pairwise_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  pairwise_tc_kernel<<<blocks, kThreads, smem, st>>>(X, norms, partial, n, D);
+  long long* dbg = nullptr;
+  if (getenv("DIC_TC_PROFILE")) {          // debug: per-role cycle counters of CTA 0, printed after the run
+    cudaMalloc(&dbg, 16 * sizeof(long long));
+    cudaMemsetAsync(dbg, 0, 16 * sizeof(long long), st);
+  }
+  pairwise_tc_kernel<<<blocks, kThreads, smem, st>>>(X, norms, partial, n, D, dbg);
+  if (dbg) {
+    long long h[16];
+    cudaMemcpyAsync(h, dbg, sizeof(h), cudaMemcpyDeviceToHost, st);
+    cudaStreamSynchronize(st);
+    fprintf(stderr, "[tc profile, CTA 0, %lld stages] loader: wait_stage %lld reload_A %lld store %lld prefetch %lld "
+            "barrier %lld | issuer: wait_acc %lld total %lld | epilogue: wait_full %lld drain %lld (cycles/stage)\n",
+            h[5], h[0] / (h[5] + 1), h[1] / (h[5] + 1), h[2] / (h[5] + 1), h[3] / (h[5] + 1), h[4] / (h[5] + 1),
+            h[6] / (h[5] + 1), h[7] / (h[5] + 1), h[8] / (h[5] + 1), h[9] / (h[5] + 1));
+    cudaFree(dbg);
+  }
   DIC_LAUNCH_CHECK("pairwise_tc_kernel");
   sum_partials_kernel<<<1, 32, 0, st>>>(partial, out, blocks);
   DIC_LAUNCH_CHECK("sum_partials_kernel");
