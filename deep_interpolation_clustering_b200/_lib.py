@@ -26,14 +26,15 @@ SIGNATURES = {
     "dic_last_error": (c_char_p, []),
     "dic_version": (c_int, []),
     "dic_device_info": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
-    "dic_sci_fwd": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, _P]),
+    "dic_sci_fwd": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, c_int64, _P]),
     "dic_interp_bwd_workspace_bytes": (c_size_t, [c_int64, c_int]),
-    "dic_sci_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, _P]),
+    "dic_sci_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, c_int64, _P]),
     "dic_cci_fwd": (c_int, [_P, _P, _P, c_int64, c_int, c_int, _P]),
     "dic_cci_bwd_workspace_bytes": (c_size_t, [c_int64, c_int]),
     "dic_cci_bwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, _P]),
-    "dic_rbf_fwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, _P]),
-    "dic_rbf_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, _P]),
+    "dic_rbf_fwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, c_int64, _P]),
+    "dic_rbf_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, c_int64, _P]),
+    "dic_upload_encounters": (c_int, [_P, _P, c_int64, c_int, c_int, c_int, c_int, _P]),
     "dic_dec_workspace_bytes": (c_size_t, [c_int, c_int]),
     "dic_dec_q_fwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_float, _P]),
     "dic_dec_p": (c_int, [_P, _P, _P, c_int64, c_int, _P]),

@@ -29,7 +29,8 @@ constexpr float kRbfCut = 30.0f;
 __global__ void __launch_bounds__(kRbfFwdThreads)
 rbf_fwd_kernel(const float* __restrict__ v, const float* __restrict__ x,
                const float* __restrict__ kernel, const float* __restrict__ ref_t,
-               float* __restrict__ rec, float* __restrict__ inv_norm, int C, int T, int R, int Rp) {
+               float* __restrict__ rec, float* __restrict__ inv_norm, int C, int T, int R, int Rp,
+               int64_t x_stride) {
   extern __shared__ __align__(16) float smem[];
   float2* srv = reinterpret_cast<float2*>(smem);     // [C][Rp] (r_j, v_cj); pad: (huge, 0) => e = 0
   float* snb = smem + 2 * C * Rp;                     // [C] -beta_c log2(e)
@@ -52,8 +53,8 @@ rbf_fwd_kernel(const float* __restrict__ v, const float* __restrict__ x,
   }
   irregular = __syncthreads_or(irregular);
   const float inv_h = 1.0f / h;
-  const float* mb = x + (b * (int64_t)(4 * C) + C) * T;       // mask plane rows
-  const float* db = x + (b * (int64_t)(4 * C) + 2 * C) * T;   // time plane rows
+  const float* mb = x + b * x_stride + (int64_t)C * T;         // mask plane rows
+  const float* db = x + b * x_stride + (int64_t)2 * C * T;     // time plane rows
   float* rb = rec + b * (int64_t)C * T;
   float* nb = inv_norm ? inv_norm + b * (int64_t)C * T : nullptr;
 
@@ -182,12 +183,12 @@ rbf_bwd_kernel(const float* __restrict__ v, const float* __restrict__ x,
                const float* __restrict__ kernel, const float* __restrict__ ref_t,
                const float* __restrict__ rec, const float* __restrict__ inv_norm,
                const float* __restrict__ grad_rec, float* __restrict__ grad_v,
-               float* __restrict__ partial, int C, int T, int Tp, int R) {
+               float* __restrict__ partial, int C, int T, int Tp, int R, int64_t x_stride) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const RbfSmem s = rbf_carve(smem_raw, C, Tp);
   const int64_t b = blockIdx.x;
-  const float* mb = x + (b * (int64_t)(4 * C) + C) * T;
-  const float* db = x + (b * (int64_t)(4 * C) + 2 * C) * T;
+  const float* mb = x + b * x_stride + (int64_t)C * T;
+  const float* db = x + b * x_stride + (int64_t)2 * C * T;
   const float* rb = rec + b * (int64_t)C * T;
   const float* nb = inv_norm + b * (int64_t)C * T;
   const float* gb = grad_rec + b * (int64_t)C * T;
@@ -311,8 +312,11 @@ __global__ void sigmoid_vec_kernel(const float* __restrict__ kernel, float* __re
 }
 
 int check(const void* v, const void* x, const void* kernel, const void* ref_t, int64_t B, int C,
-          int T, int R) {
+          int T, int R, int64_t& x_stride) {
   DIC_REQUIRE(v && x && kernel && ref_t, DIC_ERR_INVALID_ARGUMENT, "null pointer argument");
+  if (x_stride == 0) x_stride = (int64_t)4 * C * T;
+  DIC_REQUIRE(x_stride >= (int64_t)3 * C * T, DIC_ERR_INVALID_ARGUMENT,
+              "x_stride=%lld is smaller than the 3*C*T live planes of an encounter", (long long)x_stride);
   DIC_REQUIRE(B >= 0 && C > 0 && T > 0 && R > 0, DIC_ERR_INVALID_ARGUMENT,
               "bad sizes B=%lld C=%d T=%d R=%d", (long long)B, C, T, R);
   DIC_REQUIRE(B <= 2147483647LL, DIC_ERR_UNSUPPORTED, "B=%lld exceeds the grid limit", (long long)B);
@@ -326,8 +330,8 @@ using namespace dic;
 
 extern "C" int dic_rbf_fwd(const float* v, const float* x, const float* kernel, const float* ref_t,
                            float* rec, float* inv_norm, int64_t B, int C, int T, int R,
-                           dic_stream_t stream) {
-  int rc = check(v, x, kernel, ref_t, B, C, T, R);
+                           int64_t x_stride, dic_stream_t stream) {
+  int rc = check(v, x, kernel, ref_t, B, C, T, R, x_stride);
   if (rc) return rc;
   DIC_REQUIRE(rec, DIC_ERR_INVALID_ARGUMENT, "null output pointer");
   if (B == 0) return DIC_OK;
@@ -338,7 +342,7 @@ extern "C" int dic_rbf_fwd(const float* v, const float* x, const float* kernel, 
   if (smem > 48 * 1024)
     DIC_CUDA(cudaFuncSetAttribute(rbf_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   rbf_fwd_kernel<<<(unsigned)B, kRbfFwdThreads, smem, as_stream(stream)>>>(v, x, kernel, ref_t, rec,
-                                                                          inv_norm, C, T, R, Rp);
+                                                                          inv_norm, C, T, R, Rp, x_stride);
   DIC_LAUNCH_CHECK("rbf_fwd_kernel");
   return DIC_OK;
 }
@@ -346,8 +350,8 @@ extern "C" int dic_rbf_fwd(const float* v, const float* x, const float* kernel, 
 extern "C" int dic_rbf_bwd(const float* v, const float* x, const float* kernel, const float* ref_t,
                            const float* rec, const float* inv_norm, const float* grad_rec,
                            float* grad_v, float* d_kernel, void* workspace, int64_t B, int C, int T,
-                           int R, dic_stream_t stream) {
-  int rc = check(v, x, kernel, ref_t, B, C, T, R);
+                           int R, int64_t x_stride, dic_stream_t stream) {
+  int rc = check(v, x, kernel, ref_t, B, C, T, R, x_stride);
   if (rc) return rc;
   DIC_REQUIRE(rec && inv_norm && grad_rec && grad_v && d_kernel && workspace,
               DIC_ERR_INVALID_ARGUMENT, "null pointer argument");
@@ -376,7 +380,7 @@ extern "C" int dic_rbf_bwd(const float* v, const float* x, const float* kernel, 
       DIC_CUDA(cudaFuncSetAttribute(rbf_bwd_kernel<RPT_>,                                        \
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
     rbf_bwd_kernel<RPT_><<<(unsigned)B, warps * 32, smem, st>>>(                                 \
-        v, x, kernel, ref_t, rec, inv_norm, grad_rec, grad_v, partial, C, T, Tp, R);             \
+        v, x, kernel, ref_t, rec, inv_norm, grad_rec, grad_v, partial, C, T, Tp, R, x_stride);   \
   }
   if (rpt == 1) DIC_RBF_BWD(1) else if (rpt == 2) DIC_RBF_BWD(2) else DIC_RBF_BWD(3)
 #undef DIC_RBF_BWD

@@ -187,11 +187,11 @@ template <int RPT>
 __global__ void __launch_bounds__(kMaxWarps * 32)
 sci_fwd_kernel(const float* __restrict__ x, const float* __restrict__ kernel,
                const float* __restrict__ ref_t, float* __restrict__ u, float* __restrict__ stats,
-               int C, int T, int Tp, int R, int use_tma) {
+               int C, int T, int Tp, int R, int use_tma, int64_t x_stride) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const SciSmem s = sci_carve(smem_raw, C, Tp);
   const int64_t b = blockIdx.x;
-  sci_stage(s, x + b * (int64_t)(4 * C) * T, C, T, Tp, use_tma != 0, /*fold_mask=*/true);
+  sci_stage(s, x + b * x_stride, C, T, Tp, use_tma != 0, /*fold_mask=*/true);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int chunks = (R + 32 * RPT - 1) / (32 * RPT);
@@ -322,11 +322,11 @@ __global__ void __launch_bounds__(kMaxWarps * 32)
 sci_bwd_kernel(const float* __restrict__ x, const float* __restrict__ kernel,
                const float* __restrict__ ref_t, const float* __restrict__ u,
                const float* __restrict__ stats, const float* __restrict__ grad_u,
-               float* __restrict__ partial, int C, int T, int Tp, int R, int use_tma) {
+               float* __restrict__ partial, int C, int T, int Tp, int R, int use_tma, int64_t x_stride) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const SciSmem s = sci_carve(smem_raw, C, Tp);
   const int64_t b = blockIdx.x;
-  sci_stage(s, x + b * (int64_t)(4 * C) * T, C, T, Tp, use_tma != 0, /*fold_mask=*/false);
+  sci_stage(s, x + b * x_stride, C, T, Tp, use_tma != 0, /*fold_mask=*/false);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int chunks = (R + 32 * RPT - 1) / (32 * RPT);
@@ -386,8 +386,12 @@ int prepare(K kern, size_t smem) {
   return DIC_OK;
 }
 
-int check_common(const void* x, const void* kernel, const void* ref_t, int64_t B, int C, int T, int R) {
+int check_common(const void* x, const void* kernel, const void* ref_t, int64_t B, int C, int T, int R,
+                 int64_t& x_stride) {
   DIC_REQUIRE(x && kernel && ref_t, DIC_ERR_INVALID_ARGUMENT, "null pointer argument");
+  if (x_stride == 0) x_stride = (int64_t)4 * C * T;
+  DIC_REQUIRE(x_stride >= (int64_t)3 * C * T, DIC_ERR_INVALID_ARGUMENT,
+              "x_stride=%lld is smaller than the 3*C*T live planes of an encounter", (long long)x_stride);
   DIC_REQUIRE(B >= 0 && C > 0 && T > 0 && R > 0, DIC_ERR_INVALID_ARGUMENT,
               "bad sizes B=%lld C=%d T=%d R=%d", (long long)B, C, T, R);
   DIC_REQUIRE(B <= 2147483647LL, DIC_ERR_UNSUPPORTED, "B=%lld exceeds the grid limit; split the batch",
@@ -404,15 +408,16 @@ int check_common(const void* x, const void* kernel, const void* ref_t, int64_t B
 using namespace dic;
 
 extern "C" int dic_sci_fwd(const float* x, const float* kernel, const float* ref_t, float* u,
-                           float* stats, int64_t B, int C, int T, int R, dic_stream_t stream) {
-  int rc = check_common(x, kernel, ref_t, B, C, T, R);
+                           float* stats, int64_t B, int C, int T, int R, int64_t x_stride,
+                           dic_stream_t stream) {
+  int rc = check_common(x, kernel, ref_t, B, C, T, R, x_stride);
   if (rc) return rc;
   DIC_REQUIRE(u, DIC_ERR_INVALID_ARGUMENT, "null output pointer");
   if (B == 0) return DIC_OK;
   const int Tp = round_up(T, 4);
   const size_t smem = sci_smem_bytes(C, Tp, R);
   const int use_tma = (Tp == T) && aligned16(x) && ((3LL * C * T * 4) % 16 == 0) &&
-                      (((int64_t)4 * C * T * 4) % 16 == 0);
+                      ((x_stride * 4) % 16 == 0);
   const int rpt = pick_rpt(R);
   const int threads = 32 * pick_warps(C, R, rpt);
   cudaStream_t st = as_stream(stream);
@@ -421,7 +426,7 @@ extern "C" int dic_sci_fwd(const float* x, const float* kernel, const float* ref
     rc = prepare(sci_fwd_kernel<RPT_>, smem);                                               \
     if (rc) return rc;                                                                      \
     sci_fwd_kernel<RPT_><<<(unsigned)B, threads, smem, st>>>(x, kernel, ref_t, u, stats, C, \
-                                                              T, Tp, R, use_tma);           \
+                                                              T, Tp, R, use_tma, x_stride); \
   }
   if (rpt == 1) DIC_SCI_FWD(1) else if (rpt == 2) DIC_SCI_FWD(2) else DIC_SCI_FWD(3)
 #undef DIC_SCI_FWD
@@ -437,8 +442,9 @@ extern "C" size_t dic_interp_bwd_workspace_bytes(int64_t B, int C) {
 
 extern "C" int dic_sci_bwd(const float* x, const float* kernel, const float* ref_t, const float* u,
                            const float* stats, const float* grad_u, float* d_kernel,
-                           void* workspace, int64_t B, int C, int T, int R, dic_stream_t stream) {
-  int rc = check_common(x, kernel, ref_t, B, C, T, R);
+                           void* workspace, int64_t B, int C, int T, int R, int64_t x_stride,
+                           dic_stream_t stream) {
+  int rc = check_common(x, kernel, ref_t, B, C, T, R, x_stride);
   if (rc) return rc;
   DIC_REQUIRE(u && stats && grad_u && d_kernel && workspace, DIC_ERR_INVALID_ARGUMENT,
               "null pointer argument");
@@ -450,7 +456,7 @@ extern "C" int dic_sci_bwd(const float* x, const float* kernel, const float* ref
   const int Tp = round_up(T, 4);
   const size_t smem = sci_smem_bytes(C, Tp, R);
   const int use_tma = (Tp == T) && aligned16(x) && ((3LL * C * T * 4) % 16 == 0) &&
-                      (((int64_t)4 * C * T * 4) % 16 == 0);
+                      ((x_stride * 4) % 16 == 0);
   const int rpt = pick_rpt(R);
   const int threads = 32 * pick_warps(C, R, rpt);
   unsigned char* ws = static_cast<unsigned char*>(workspace);
@@ -464,7 +470,7 @@ extern "C" int dic_sci_bwd(const float* x, const float* kernel, const float* ref
     if (rc) return rc;                                                                         \
     sci_bwd_kernel<RPT_><<<(unsigned)B, threads, smem, st>>>(x, kernel, ref_t, u, stats,       \
                                                               grad_u, partial, C, T, Tp, R,    \
-                                                              use_tma);                        \
+                                                              use_tma, x_stride);              \
   }
   if (rpt == 1) DIC_SCI_BWD(1) else if (rpt == 2) DIC_SCI_BWD(2) else DIC_SCI_BWD(3)
 #undef DIC_SCI_BWD

@@ -11,7 +11,7 @@ import torch
 
 from . import _lib
 
-__all__ = ["sci", "cci", "rbf_readout", "dec_soft_assign", "dec_target_distribution",
+__all__ = ["sci", "cci", "rbf_readout", "upload_encounters", "dec_soft_assign", "dec_target_distribution",
            "dec_assign", "dec_kl_from_colsum", "dec_kl_step", "colsum"]
 
 
@@ -25,23 +25,60 @@ def _require_cuda_f32(t, name):
         raise TypeError(f"{name} must be float32 (got {t.dtype})")
 
 
+def _planes(x, C, name):
+    """x is (B, 4C, T) like the reference's input, or (B, 3C, T) when the never-read hold-out plane
+    (interpolation_layer.py:26-30) was left on the host.  Rows of one encounter must be dense; the
+    batch stride is free (a slice x[:, :3C] of a dense tensor is taken as it is).  Returns x (made
+    dense only if its inner strides are not) and the batch stride in floats."""
+    if x.dim() != 3 or x.shape[1] not in (3 * C, 4 * C):
+        raise ValueError(f"{name} must be (B, {4 * C}, T) (or (B, {3 * C}, T) without the hold-out plane); "
+                         f"got {tuple(x.shape)}")
+    T = x.shape[2]
+    if x.shape[0] > 0 and (x.stride(2) != 1 or x.stride(1) != T or x.stride(0) < 3 * C * T):
+        x = x.contiguous()
+    return x, (x.stride(0) if x.shape[0] > 1 else x.shape[1] * T)
+
+
+def upload_encounters(x_host, out=None, stream=None, device=None):
+    """Host -> device copy of x_host (B, 4C, T) [pin it for an asynchronous copy] that moves only the
+    three live planes [value | mask | time] of every encounter (dic_upload_encounters: one strided
+    DMA, 25 % fewer PCIe bytes).  Returns a (B, 3C, T) CUDA tensor that SingleChannelInterp / RBF
+    accept in place of x."""
+    if x_host.is_cuda or x_host.dtype != torch.float32 or x_host.dim() != 3 or x_host.shape[1] % 4:
+        raise ValueError("x_host must be a float32 host tensor of shape (B, 4*d_dim, T)")
+    if not x_host.is_contiguous():
+        x_host = x_host.contiguous()
+    B, P, T = x_host.shape
+    C = P // 4
+    if out is None:
+        out = torch.empty((B, 3 * C, T), dtype=torch.float32, device=device or "cuda")
+    if tuple(out.shape) != (B, 3 * C, T) or not out.is_contiguous() or not out.is_cuda:
+        raise ValueError(f"out must be a dense CUDA tensor of shape {(B, 3 * C, T)}")
+    st = (stream or torch.cuda.current_stream(out.device)).cuda_stream
+    with torch.cuda.device(out.device):
+        _lib.check(_lib.lib().dic_upload_encounters(_lib.ptr(out), x_host.data_ptr(), B, C, T, P, 3 * C, st),
+                   "dic_upload_encounters")
+    return out
+
+
 def _ws(nbytes, device):
     return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
 
 
 class _SCI(torch.autograd.Function):
-    """dic_sci_fwd / dic_sci_bwd.  x (B,4C,T), kernel (C), ref_t (R) -> u (B,3C,R)."""
+    """dic_sci_fwd / dic_sci_bwd.  x (B,4C|3C,T), kernel (C), ref_t (R) -> u (B,3C,R)."""
 
     @staticmethod
-    def forward(ctx, x, kernel, ref_t):
-        B, C4, T = x.shape
-        C, R = C4 // 4, ref_t.numel()
+    def forward(ctx, x, kernel, ref_t, xs):
+        B, _, T = x.shape
+        C, R = kernel.numel(), ref_t.numel()
+        ctx.xs = xs
         need_grad = ctx.needs_input_grad[1]      # grad mode is off inside forward; ask the ctx
         with torch.cuda.device(x.device):
             u = torch.empty((B, 3 * C, R), dtype=torch.float32, device=x.device)
             stats = torch.empty((B, 2 * C, R), dtype=torch.float32, device=x.device) if need_grad else None
             _lib.check(_lib.lib().dic_sci_fwd(_lib.ptr(x), _lib.ptr(kernel), _lib.ptr(ref_t), _lib.ptr(u),
-                                              _lib.ptr(stats), B, C, T, R, _lib.current_stream(x.device)),
+                                              _lib.ptr(stats), B, C, T, R, xs, _lib.current_stream(x.device)),
                        "dic_sci_fwd")
         if need_grad:
             ctx.save_for_backward(x, kernel, ref_t, u, stats)
@@ -50,27 +87,24 @@ class _SCI(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_u):
         x, kernel, ref_t, u, stats = ctx.saved_tensors
-        B, C4, T = x.shape
-        C, R = C4 // 4, ref_t.numel()
+        B, _, T = x.shape
+        C, R = kernel.numel(), ref_t.numel()
         grad_u = grad_u.contiguous()
         with torch.cuda.device(x.device):
             dk = torch.empty_like(kernel)
             ws = _ws(_lib.lib().dic_interp_bwd_workspace_bytes(B, C), x.device)
             _lib.check(_lib.lib().dic_sci_bwd(_lib.ptr(x), _lib.ptr(kernel), _lib.ptr(ref_t), _lib.ptr(u),
                                               _lib.ptr(stats), _lib.ptr(grad_u), _lib.ptr(dk), _lib.ptr(ws),
-                                              B, C, T, R, _lib.current_stream(x.device)), "dic_sci_bwd")
-        return None, dk, None
+                                              B, C, T, R, ctx.xs, _lib.current_stream(x.device)), "dic_sci_bwd")
+        return None, dk, None, None
 
 
 def sci(x, kernel, ref_t):
     """SingleChannelInterp in planar layout: returns u (B, 3C, R) = rows [y | w | y']."""
     for t, n in ((x, "x"), (kernel, "kernel"), (ref_t, "ref_t")):
         _require_cuda_f32(t, n)
-    if x.dim() != 3 or x.shape[1] % 4 != 0:
-        raise ValueError(f"x must be (B, 4*d_dim, T); got {tuple(x.shape)}")
-    if kernel.numel() * 4 != x.shape[1]:
-        raise ValueError(f"x has {x.shape[1]} planes but kernel has {kernel.numel()} channels")
-    return _SCI.apply(x.contiguous(), kernel.contiguous(), ref_t.contiguous())
+    x, xs = _planes(x, kernel.numel(), "x")
+    return _SCI.apply(x, kernel.contiguous(), ref_t.contiguous(), xs)
 
 
 class _CCI(torch.autograd.Function):
@@ -117,15 +151,16 @@ class _RBF(torch.autograd.Function):
     """dic_rbf_fwd / dic_rbf_bwd.  v (B,C,R), x (B,4C,T) -> rec (B,C,T)."""
 
     @staticmethod
-    def forward(ctx, v, x, kernel, ref_t):
+    def forward(ctx, v, x, kernel, ref_t, xs):
         B, C, R = v.shape
         T = x.shape[2]
+        ctx.xs = xs
         need_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[2]
         with torch.cuda.device(x.device):
             rec = torch.empty((B, C, T), dtype=torch.float32, device=x.device)
             inv = torch.empty_like(rec) if need_grad else None
             _lib.check(_lib.lib().dic_rbf_fwd(_lib.ptr(v), _lib.ptr(x), _lib.ptr(kernel), _lib.ptr(ref_t),
-                                              _lib.ptr(rec), _lib.ptr(inv), B, C, T, R,
+                                              _lib.ptr(rec), _lib.ptr(inv), B, C, T, R, xs,
                                               _lib.current_stream(x.device)), "dic_rbf_fwd")
         if need_grad:
             ctx.save_for_backward(v, x, kernel, ref_t, rec, inv)
@@ -143,20 +178,21 @@ class _RBF(torch.autograd.Function):
             ws = _ws(_lib.lib().dic_interp_bwd_workspace_bytes(B, C), x.device)
             _lib.check(_lib.lib().dic_rbf_bwd(_lib.ptr(v), _lib.ptr(x), _lib.ptr(kernel), _lib.ptr(ref_t),
                                               _lib.ptr(rec), _lib.ptr(inv), _lib.ptr(grad_rec), _lib.ptr(gv),
-                                              _lib.ptr(dk), _lib.ptr(ws), B, C, T, R,
+                                              _lib.ptr(dk), _lib.ptr(ws), B, C, T, R, ctx.xs,
                                               _lib.current_stream(x.device)), "dic_rbf_bwd")
-        return gv, None, dk, None
+        return gv, None, dk, None, None
 
 
 def rbf_readout(v, x, kernel, ref_t):
     """Gaussian RBF read-out of grid values v (B,C,R) at the observation times in x."""
     for t, n in ((v, "interp_data"), (x, "raw_input"), (kernel, "kernel"), (ref_t, "interp_t")):
         _require_cuda_f32(t, n)
-    if x.dim() != 3 or v.dim() != 3 or x.shape[1] != 4 * v.shape[1] or v.shape[0] != x.shape[0]:
+    if x.dim() != 3 or v.dim() != 3 or x.shape[1] not in (3 * v.shape[1], 4 * v.shape[1]) or v.shape[0] != x.shape[0]:
         raise ValueError(f"expected v (B,C,R) and raw_input (B,4C,T); got {tuple(v.shape)}, {tuple(x.shape)}")
     if v.shape[2] != ref_t.numel():
         raise ValueError(f"interp_data has {v.shape[2]} grid points but ref_points is {ref_t.numel()}")
-    return _RBF.apply(v.contiguous(), x.contiguous(), kernel.contiguous(), ref_t.contiguous())
+    x, xs = _planes(x, v.shape[1], "raw_input")
+    return _RBF.apply(v.contiguous(), x, kernel.contiguous(), ref_t.contiguous(), xs)
 
 
 class _DecQ(torch.autograd.Function):

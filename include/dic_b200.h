@@ -19,7 +19,10 @@
  * Planar layouts used across the boundary (the nn.Module mirrors expose the
  * reference's permuted views of these buffers):
  *   x      (B, 4C, T)  planes [value | padding mask | time in hours | hold-out]
- *                       interpolation_layer.py:26-30; the hold-out plane is never read
+ *                       interpolation_layer.py:26-30; the hold-out plane is never read, so every
+ *                       call that takes x also takes x_stride = floats between consecutive
+ *                       encounters (0 = dense 4*C*T; 3*C*T for a buffer that holds only the
+ *                       three live planes, see dic_upload_encounters)
  *   u      (B, 3C, R)  SCI output rows [y (C) | w (C) | y' (C)]; the reference returns
  *                       u.permute(0,2,1), interpolation_layer.py:84-85
  *   cci    (B, 3C, R)  rows [z | exp(w) | y' - z]; interpolation_layer.py:124-126
@@ -64,7 +67,7 @@ int dic_device_info(int* sm_count, int* cc_major, int* cc_minor);
  * Limits: 12*C*round_up(T,4) + 64 bytes of shared memory <= 227 KB.
  */
 int dic_sci_fwd(const float* x, const float* kernel, const float* ref_t, float* u, float* stats,
-                int64_t B, int C, int T, int R, dic_stream_t stream);
+                int64_t B, int C, int T, int R, int64_t x_stride, dic_stream_t stream);
 
 /* Bytes of scratch dic_sci_bwd / dic_rbf_bwd need (per-encounter partials + reduction). */
 size_t dic_interp_bwd_workspace_bytes(int64_t B, int C);
@@ -76,7 +79,7 @@ size_t dic_interp_bwd_workspace_bytes(int64_t B, int C);
  */
 int dic_sci_bwd(const float* x, const float* kernel, const float* ref_t, const float* u,
                 const float* stats, const float* grad_u, float* d_kernel, void* workspace,
-                int64_t B, int C, int T, int R, dic_stream_t stream);
+                int64_t B, int C, int T, int R, int64_t x_stride, dic_stream_t stream);
 
 /* CrossChannelInterp.forward, interpolation_layer.py:99-127.
  *   u (B,3C,R) in, kernel (C,C) in, out (B,3C,R).  Limit: C <= 16.
@@ -97,7 +100,7 @@ int dic_cci_bwd(const float* u, const float* kernel, const float* grad_out, floa
  *   inv_norm (B,C,T) out, may be NULL: 1/(sum_r phi + 1e-10), saved for the backward pass
  */
 int dic_rbf_fwd(const float* v, const float* x, const float* kernel, const float* ref_t,
-                float* rec, float* inv_norm, int64_t B, int C, int T, int R,
+                float* rec, float* inv_norm, int64_t B, int C, int T, int R, int64_t x_stride,
                 dic_stream_t stream);
 
 /* Gradients of dic_rbf_fwd wrt v (flows into compress_fc) and kernel.
@@ -105,8 +108,16 @@ int dic_rbf_fwd(const float* v, const float* x, const float* kernel, const float
  */
 int dic_rbf_bwd(const float* v, const float* x, const float* kernel, const float* ref_t,
                 const float* rec, const float* inv_norm, const float* grad_rec, float* grad_v,
-                float* d_kernel, void* workspace, int64_t B, int C, int T, int R,
+                float* d_kernel, void* workspace, int64_t B, int C, int T, int R, int64_t x_stride,
                 dic_stream_t stream);
+
+/* Host -> device transfer of a batch of encounters as ONE strided DMA that skips the hold-out
+ * plane (a quarter of x; interpolation_layer.py:26-30 never reads it): row b of x_host
+ * (B, host_planes, T) [pinned host memory for an asynchronous copy] lands at
+ * x_dev + b * dev_planes * T; only the first 3*C planes are moved.  host_planes, dev_planes >= 3C.
+ * The device buffer is then passed to the calls above with x_stride = dev_planes * T. */
+int dic_upload_encounters(float* x_dev, const float* x_host, int64_t B, int C, int T,
+                          int host_planes, int dev_planes, dic_stream_t stream);
 
 /* ---- DEC soft assignment ----------------------------------------------------------
  * ClusterAssignment.forward, dec.py:49-63.  z (B,D), mu (K,D) -> q (B,K).

@@ -227,3 +227,33 @@ def test_unsorted_and_weighted_masks_vs_oracle():
     dk64 = interp_oracle.sci_backward(xn.astype(np.float64), p["sci_kernel"].astype(np.float64), rt, C, gs)
     (sci(x) * torch.tensor(gs, device=dev)).sum().backward()
     _check("weighted/d_sci_kernel", sci.kernel.grad, dk64)
+
+
+@pytest.mark.parametrize("case", ["interp_c1", "interp_odd"])
+def test_three_plane_input_is_bit_identical(golden, case):
+    """x without its never-read hold-out plane - uploaded by dic_upload_encounters from the host
+    (B,4C,T) tensor, or a strided slice x[:, :3C] of the dense device tensor - gives bit-identical
+    forward outputs and gradients (interpolation_layer.py:26-30 only reads planes [0, 3C))."""
+    import deep_interpolation_clustering_b200 as dic
+    g = golden(case)
+    dev = torch.device("cuda:0")
+    C = g["x"].shape[1] // 4
+    xh = torch.from_numpy(np.ascontiguousarray(g["x"])).pin_memory()
+    x4 = xh.to(dev)
+    x3 = dic.upload_encounters(xh, device=dev)
+    torch.cuda.synchronize()
+    assert x3.shape == (x4.shape[0], 3 * C, x4.shape[2])
+    assert torch.equal(x3, x4[:, :3 * C])
+    results = []
+    for x in (x4, x3, x4[:, :3 * C]):
+        sci, cci, rbf = _modules(g, dev)
+        v = torch.tensor(g["v"], device=dev, requires_grad=True)
+        c = cci(sci(x))
+        r = rbf(v, x)
+        (c * torch.tensor(g["g_cci"], device=dev)).sum().backward()
+        (r * torch.tensor(g["g_rbf"], device=dev)).sum().backward()
+        results.append([t.detach().clone() for t in (c, r, sci.kernel.grad, cci.kernel.grad, rbf.kernel.grad, v.grad)])
+    for other in results[1:]:
+        for a, b in zip(results[0], other):
+            assert torch.equal(a, b) or (torch.isnan(a) == torch.isnan(b)).all() and torch.equal(
+                torch.nan_to_num(a), torch.nan_to_num(b))

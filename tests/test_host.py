@@ -53,10 +53,10 @@ def test_argument_errors_without_gpu():
     """Validation happens before any CUDA call, so it is testable on a CPU box."""
     from deep_interpolation_clustering_b200 import _lib
     lib = _lib.lib()
-    assert lib.dic_sci_fwd(None, None, None, None, None, 1, 6, 64, 48, None) == _lib.DIC_ERR_INVALID_ARGUMENT
+    assert lib.dic_sci_fwd(None, None, None, None, None, 1, 6, 64, 48, 0, None) == _lib.DIC_ERR_INVALID_ARGUMENT
     assert "null" in _lib.last_error()
     # T so large that one encounter cannot be staged in 227 KB of shared memory
-    assert lib.dic_sci_fwd(16, 16, 16, 16, None, 1, 6, 100000, 48, None) == _lib.DIC_ERR_UNSUPPORTED
+    assert lib.dic_sci_fwd(16, 16, 16, 16, None, 1, 6, 100000, 48, 0, None) == _lib.DIC_ERR_UNSUPPORTED
     assert "shared memory" in _lib.last_error()
     assert lib.dic_cci_fwd(16, 16, 16, 1, 17, 48, None) == _lib.DIC_ERR_UNSUPPORTED
     assert lib.dic_dec_q_fwd(16, 16, 16, None, None, None, 4, 30, 4, 1.0, None) == _lib.DIC_ERR_UNSUPPORTED
