@@ -311,8 +311,16 @@ def device_arm(args, rank, world, local_rank):
             ktab[n]["gex2_per_s"] = round(ex2[n] / 1e9 / (m * 1e-3), 1)
             ktab[n]["mufu_frac"] = round(ex2[n] / (m * 1e-3) / mufu.value, 4)
     dom = max(kms, key=kms.get)
+    traffic = None          # measured DRAM bytes per launch of the dominant kernel (one ncu --set full capture)
+    try:
+        tr = json.load(open(os.path.join(REPO, "profiles", "dram_traffic.json")))
+        if dom in tr["bytes_per_launch"]:
+            traffic = round(tr["bytes_per_launch"][dom] * (B / tr["encounters"]) / 1e9, 3)
+    except Exception:
+        pass
     roofline = {"kernel": dom, "bound": "hbm", "achieved": ktab[dom]["gbps"], "peak": hbm_peak, "unit": "GB/s",
-                "frac": ktab[dom]["hbm_frac"], "traffic": None, "peak_source": peak_src,
+                "frac": ktab[dom]["hbm_frac"], "traffic": traffic, "traffic_unit": "GB per launch (ncu dram bytes, "
+                "profiles/dram_traffic.json)", "peak_source": peak_src,
                 "note": "interpolation kernels are MUFU/issue bound, not HBM bound: see roofline_sfu"}
     roofline_sfu = {"kernel": dom, "bound": "sfu", "unit": "Gex2/s",
                     "achieved": ktab[dom].get("gex2_per_s"), "peak": round(mufu.value / 1e9, 1),

@@ -127,7 +127,7 @@ __device__ __forceinline__ void sci_fwd_task(const float* __restrict__ sx, const
   for (int k = 0; k < RPT; ++k) {
     const float dst = nearest_delta(sd, n, lb[k], rr[k]);           // delta* = d* - r
     nhi[k] = dst * dst;
-    nlo[k] = fmaf(dst, dst, -nhi[k]);          // exact residual: delta*^2 = nhi + nlo
+    nlo[k] = -na * fmaf(dst, dst, -nhi[k]);    // exact residual delta*^2 - nhi, pre-multiplied by a
     nmax = fmaxf(nmax, nhi[k]);
     s1[k] = sy[k] = s10[k] = sy10[k] = 0.f;
   }
@@ -152,8 +152,8 @@ __device__ __forceinline__ void sci_fwd_task(const float* __restrict__ sx, const
 #pragma unroll
       for (int k = 0; k < RPT; ++k) {
         const float dl = dd[j] - rr[k];
-        const float tt = fmaf(dl, dl, -nhi[k]) - nlo[k];      // (d-r)^2 - (d*-r)^2 >= 0
-        const float e = ex2_approx(tt * na);
+        // -a ((d-r)^2 - (d*-r)^2) <= 0: the difference of squares is rounded once, the residual rides in the FMA
+        const float e = ex2_approx(fmaf(fmaf(dl, dl, -nhi[k]), na, nlo[k]));
         s1[k] = WEIGHTED ? fmaf(mm[j], e, s1[k]) : s1[k] + e;
         sy[k] = fmaf(xx[j], e, sy[k]);
         if (inner) {
@@ -259,7 +259,7 @@ __device__ __forceinline__ float sci_bwd_task(const float* __restrict__ sx, cons
     const int rc = min(r, R - 1);
     const float dst = nearest_delta(sd, n, lb[k], rr[k]);
     nhi[k] = dst * dst;
-    nlo[k] = fmaf(dst, dst, -nhi[k]);
+    nlo[k] = -na * fmaf(dst, dst, -nhi[k]);
     nmax = fmaxf(nmax, nhi[k]);
     yy[k] = ub[(0 * C + c) * R + rc];
     yy10[k] = ub[(2 * C + c) * R + rc];
@@ -294,8 +294,7 @@ __device__ __forceinline__ float sci_bwd_task(const float* __restrict__ sx, cons
 #pragma unroll
       for (int k = 0; k < RPT; ++k) {
         const float dl = dd[j] - rr[k];
-        const float tt = fmaf(dl, dl, -nhi[k]) - nlo[k];
-        const float e = ex2_approx(tt * na);
+        const float e = ex2_approx(fmaf(fmaf(dl, dl, -nhi[k]), na, nlo[k]));
         float h = e * fmaf(xx[j] - yy[k], A[k], Bc[k]);
         if (inner) {
           const float e2 = e * e, e4 = e2 * e2, e8 = e4 * e4, e10 = e8 * e2;
