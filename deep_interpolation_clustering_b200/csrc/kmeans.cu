@@ -19,7 +19,7 @@
 
 namespace dic {
 // tensor-core path (pairwise_tc.cu)
-size_t pairwise_tc_workspace_bytes(int64_t n);
+size_t pairwise_tc_workspace_bytes(int64_t n, int D);
 bool pairwise_tc_supported(const void* X, int D);
 int launch_pairwise_tc(const float* X, double* out, void* workspace, int64_t n, int D, cudaStream_t st);
 
@@ -797,9 +797,9 @@ extern "C" int dic_kmeans_min_d2(const void* X, const void* cands, const void* m
                     : launch_min_d2<double>(X, cands, min_d2, min_d2_out, pots, workspace, N, D, L, st);
 }
 
-extern "C" size_t dic_pairwise_workspace_bytes(int64_t n) {
+extern "C" size_t dic_pairwise_workspace_bytes(int64_t n, int D) {
   const size_t a = (size_t)kPwBlocks * sizeof(double) + 256;
-  const size_t b = pairwise_tc_workspace_bytes(n < 0 ? 0 : n);
+  const size_t b = pairwise_tc_workspace_bytes(n < 0 ? 0 : n, D);
   return a > b ? a : b;
 }
 

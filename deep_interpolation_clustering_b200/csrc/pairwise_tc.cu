@@ -7,7 +7,7 @@
 // tile of the Gram matrix X X^T is produced by tcgen05.mma (kind::tf32, accumulator in TMEM), read
 // back with tcgen05.ld and reduced on the fly, so nothing is ever written to memory.
 //
-//   * split TF32: each operand is split in shared memory into hi = rn_tf32(x) and lo = rn_tf32(x - hi)
+//   * split TF32: each operand is split into hi = rn_tf32(x) and lo = rn_tf32(x - hi)
 //     and the tile accumulates hi.hi + hi.lo + lo.hi + lo.lo, which restores float32-grade dot
 //     products (the MMAs are ~3% of the tile time, the epilogue's sqrt is the bound; the caller
 //     centres the cluster first, so ||x||^2 stays small against the distances).
@@ -87,6 +87,33 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         "=r"(v[30]), "=r"(v[31])
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Split form for software pipelining: the load is issued, and the registers may only be read after
+// tmem_ld_wait, which names them as in/out operands so that no use can be scheduled above the wait.
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32"
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15,"
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31},"
+      "[%32];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]),
+        "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]),
+        "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&v)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                 "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]),
+                 "+r"(v[15]), "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]),
+                 "+r"(v[22]), "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]),
+                 "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+               :
+               : "memory");
 }
 
 // Shared-memory matrix descriptor, no swizzle, K-major (cute::UMMA::SmemDescriptor bit layout):
@@ -393,15 +420,404 @@ __global__ void sum_partials_kernel(const double* __restrict__ ws, double* __res
   if (lane == 0) *out = s;
 }
 
+
+// =================================================================================================
+// D <= 64: TMA-fed, A-stationary variant.
+//
+// A one-off pre-pass (pack_split_kernel) writes every 128-row block of X ONCE as split-TF32 operand
+// tiles in the exact shared-memory image the tensor core reads (hi tile | lo tile, 64 KB per block,
+// K padded to 64) plus the row norms.  The main kernel then never touches a float again on its way
+// to the tensor core: one elected thread streams tiles with 1-D TMA bulk copies, one thread issues
+// tcgen05.mma, eight warps drain TMEM.
+//
+//   * supertile = 256 rows (two 128-row blocks: the "row pair", resident in shared memory for a
+//     whole work item, 128 KB) x 128 columns; every column tile that arrives (64 KB) is multiplied
+//     against BOTH row blocks, which halves the L2 -> SM traffic per distance (16 B/clk/SM; a
+//     128-row tile would need 32 of the ~42 B/clk/SM the L2 can deliver chip-wide);
+//   * column tiles arrive as K-halves (32 KB stages, 3 in flight) so that the pipeline fits next to
+//     the resident row pair: 128 + 96 KB of shared memory;
+//   * TMEM holds 2 (double buffer) x 2 (row blocks) accumulators of 128 columns = all 512 columns;
+//   * work items = (row pair p, segment of <= L column tiles), enumerated segment-major so that the
+//     CTAs running at the same time read the same column tiles out of L2, dealt cyclically.
+// =================================================================================================
+namespace tc64 {
+
+constexpr int kBlk = 128;
+constexpr int kTileB = kBlk * 64 * 4;        // 32 KB: one hi or lo operand tile (128 rows x K = 64)
+constexpr int kBlockB = 2 * kTileB;          // 64 KB per packed 128-row block: hi | lo
+constexpr int kHalfB = kTileB / 2;           // 16 KB: one K-half (8 of the 16 sixteen-byte K chunks)
+constexpr int kStages = 3;
+constexpr int kEpiWarps = 8;
+constexpr int kThreads64 = 32 * (2 + kEpiWarps);
+
+struct __align__(128) Smem64 {
+  unsigned char a[2][2][kTileB];             // [row block of the pair][hi | lo]
+  unsigned char b[kStages][2][kHalfB];       // [stage][hi | lo], one K-half of a column tile
+  uint64_t a_full, a_empty, b_full[kStages], b_empty[kStages], acc_full[2], acc_empty[2];
+  double red[kEpiWarps];
+  uint32_t tmem_base;
+  int timeout;
+};
+
+// The sequence of work items of CTA `cta`: segment s covers column tiles [sL, (s+1)L); row pair p takes
+// part in it when 2p < (s+1)L.  Item (s, p) has global index w(s) + p and belongs to CTA (w(s) + p) % G.
+struct ItemIter {
+  int64_t nb, P, S, s, w, p;
+  int L, G, cta;
+  __device__ void init(int64_t nb_, int L_, int G_, int cta_) {
+    nb = nb_; L = L_; G = G_; cta = cta_;
+    P = (nb + 1) / 2;
+    S = (nb + L - 1) / L;
+    s = 0; w = 0;
+    p = first();
+  }
+  __device__ int64_t first() const { return (int64_t)((((cta - w) % G) + G) % G); }
+  __device__ int64_t pmax() const { return min(P - 1, ((s + 1) * L - 1) / 2); }
+  __device__ bool next(int64_t& op, int64_t& j0, int64_t& j1) {
+    while (s < S) {
+      if (p <= pmax()) {
+        op = p;
+        j0 = max(s * L, 2 * p);
+        j1 = min((s + 1) * L, nb);
+        p += G;
+        return true;
+      }
+      w += pmax() + 1;
+      ++s;
+      p = first();
+    }
+    return false;
+  }
+};
+
+// X (n x D, D <= 64, D % 4 == 0) -> packed split-TF32 operand tiles + row norms; rows >= n and K >= D
+// are zero.  One CTA per 128-row block, thread -> (row, 16-byte K chunk): coalesced reads.
+__global__ void __launch_bounds__(256)
+pack_split_kernel(const float* __restrict__ X, unsigned char* __restrict__ packed, float* __restrict__ norms,
+                  int64_t n, int D) {
+  const int64_t blk = blockIdx.x;
+  unsigned char* out = packed + blk * (int64_t)kBlockB;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int idx = it * 256 + threadIdx.x;
+    const int row = idx >> 4, c = idx & 15;
+    const int64_t gr = blk * kBlk + row;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (gr < n && 4 * c < D) v = __ldg(reinterpret_cast<const float4*>(X + gr * D + 4 * c));
+    float4 h, l;
+    h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
+    l.x = to_tf32(v.x - h.x); l.y = to_tf32(v.y - h.y); l.z = to_tf32(v.z - h.z); l.w = to_tf32(v.w - h.w);
+    const int off = c * kChunkStride + (row >> 3) * kGroupStride + (row & 7) * 16;
+    *reinterpret_cast<float4*>(out + off) = h;
+    *reinterpret_cast<float4*>(out + kTileB + off) = l;
+    float s = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, v.w * v.w)));
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (c == 0) norms[gr] = s;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads64, 1)
+pairwise_tc64_kernel(const unsigned char* __restrict__ packed, const float* __restrict__ norms,
+                     double* __restrict__ partial, int64_t n, int L, long long* __restrict__ dbg) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  Smem64& S = *reinterpret_cast<Smem64*>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t nb = (n + kBlk - 1) / kBlk;
+
+  if (tid == 0) {
+    mbar_init(&S.a_full, 1);
+    mbar_init(&S.a_empty, 1);
+    for (int k = 0; k < kStages; ++k) {
+      mbar_init(&S.b_full[k], 1);
+      mbar_init(&S.b_empty[k], 1);
+    }
+    for (int k = 0; k < 2; ++k) {
+      mbar_init(&S.acc_full[k], 1);
+      mbar_init(&S.acc_empty[k], kEpiWarps);
+    }
+    S.timeout = 0;
+    fence_proxy_async();
+  }
+  if (warp == 2) tmem_alloc(&S.tmem_base, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = S.tmem_base;
+  volatile int* timeout = &S.timeout;
+
+  ItemIter it;
+  it.init(nb, L, (int)gridDim.x, (int)blockIdx.x);
+  int64_t p, j0, j1;
+  double total = 0.0;
+
+  if (warp == 0) {
+    // ================= producer: TMA bulk copies =================
+    if (lane == 0) {
+      int64_t item = 0, g = 0;
+      long long pw_a = 0, pw_b = 0;
+      while (it.next(p, j0, j1) && !*timeout) {
+        long long c0 = clock64();
+        if (!bar_wait_bounded(&S.a_empty, (uint32_t)((item & 1) ^ 1))) { *timeout = 1; break; }
+        pw_a += clock64() - c0;
+        mbar_expect_tx(&S.a_full, 2u * kBlockB);
+        const unsigned char* arow = packed + 2 * p * (int64_t)kBlockB;     // blocks 2p, 2p+1 are adjacent
+#pragma unroll
+        for (int q = 0; q < 4; ++q) bulk_g2s(&S.a[0][0][0] + q * kTileB, arow + q * kTileB, kTileB, &S.a_full);
+        for (int64_t bj = j0; bj < j1 && !*timeout; ++bj) {
+          const unsigned char* bcol = packed + bj * (int64_t)kBlockB;
+          for (int kh = 0; kh < 2; ++kh, ++g) {
+            const int slot = (int)(g % kStages);
+            c0 = clock64();
+            if (!bar_wait_bounded(&S.b_empty[slot], (uint32_t)(((g / kStages) & 1) ^ 1))) { *timeout = 1; break; }
+            pw_b += clock64() - c0;
+            mbar_expect_tx(&S.b_full[slot], 2u * kHalfB);
+            bulk_g2s(S.b[slot][0], bcol + kh * kHalfB, kHalfB, &S.b_full[slot]);
+            bulk_g2s(S.b[slot][1], bcol + kTileB + kh * kHalfB, kHalfB, &S.b_full[slot]);
+          }
+        }
+        ++item;
+      }
+      if (dbg && blockIdx.x == 0) { dbg[10] = pw_a; dbg[11] = pw_b; }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      int64_t item = 0, g = 0, t = 0;
+      long long w_a = 0, w_acc = 0, w_b = 0;
+      const long long m0 = clock64();
+      const uint32_t a_base = smem_u32(&S.a[0][0][0]);
+      while (it.next(p, j0, j1) && !*timeout) {
+        long long c0 = clock64();
+        if (!bar_wait_bounded(&S.a_full, (uint32_t)(item & 1))) { *timeout = 1; break; }
+        w_a += clock64() - c0;
+        for (int64_t bj = j0; bj < j1 && !*timeout; ++bj, ++t) {
+          const int buf = (int)(t & 1);
+          c0 = clock64();
+          if (!bar_wait_bounded(&S.acc_empty[buf], (uint32_t)(((t >> 1) & 1) ^ 1))) { *timeout = 1; break; }
+          w_acc += clock64() - c0;
+          for (int kh = 0; kh < 2; ++kh, ++g) {
+            const int slot = (int)(g % kStages);
+            c0 = clock64();
+            if (!bar_wait_bounded(&S.b_full[slot], (uint32_t)((g / kStages) & 1))) { *timeout = 1; break; }
+            w_b += clock64() - c0;
+            tc_fence_after();
+            const uint32_t b_hi = smem_u32(S.b[slot][0]), b_lo = smem_u32(S.b[slot][1]);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const uint32_t d_tmem = tmem + (uint32_t)((buf * 2 + h) * kBlk);
+              const uint32_t a_hi = a_base + (uint32_t)(h * kBlockB), a_lo = a_hi + kTileB;
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {            // one MMA consumes K = 8 tf32 = two 16-byte chunks
+                const uint32_t ka = (uint32_t)((kh * 8 + ks * 2) * kChunkStride);
+                const uint32_t kb = (uint32_t)(ks * 2 * kChunkStride);
+                const uint64_t dah = make_desc(a_hi + ka), dal = make_desc(a_lo + ka);
+                const uint64_t dbh = make_desc(b_hi + kb), dbl = make_desc(b_lo + kb);
+                // 3xTF32: hi.hi + hi.lo + lo.hi; the dropped lo.lo term is < 2^-22 |x||y|, below the
+                // float32 rounding of the norms it is added to
+                umma_tf32(d_tmem, dah, dbh, kIdesc, (kh > 0 || ks > 0) ? 1u : 0u);
+                umma_tf32(d_tmem, dah, dbl, kIdesc, 1u);
+                umma_tf32(d_tmem, dal, dbh, kIdesc, 1u);
+              }
+            }
+            umma_commit(&S.b_empty[slot]);             // stage reusable once these MMAs have read it
+          }
+          umma_commit(&S.acc_full[buf]);               // both accumulators of the supertile complete
+        }
+        umma_commit(&S.a_empty);                       // row pair may be replaced
+        ++item;
+      }
+      if (dbg && blockIdx.x == 0) {
+        dbg[0] = clock64() - m0; dbg[1] = w_a; dbg[2] = w_acc; dbg[3] = w_b; dbg[4] = t; dbg[5] = item;
+      }
+    }
+  } else {
+    // ================= epilogue: 8 warps, (row block h, TMEM lane quarter q) =================
+    const int ew = warp - 2, h = ew >> 2, q = warp & 3;
+    int64_t t = 0;
+    bool dead = false;
+    long long w_full = 0, w_work = 0;
+    while (!dead && it.next(p, j0, j1)) {
+      const int64_t bi = 2 * p + h;
+      const int64_t i0 = bi * kBlk, gi = i0 + 32 * q + lane;
+      const float ni = gi < n ? __ldg(norms + gi) : 0.f;
+      float4 njr[8];                       // norms of the next 32 columns to be processed, prefetched
+#pragma unroll
+      for (int k = 0; k < 8; ++k) njr[k] = __ldg(reinterpret_cast<const float4*>(norms + j0 * kBlk) + k);
+      for (int64_t bj = j0; bj < j1; ++bj, ++t) {
+        const int buf = (int)(t & 1);
+        const int64_t c0 = bj * kBlk;
+        const long long e0 = clock64();
+        if (!bar_wait_bounded(&S.acc_full[buf], (uint32_t)((t >> 1) & 1))) { *timeout = 1; dead = true; break; }
+        const long long e1 = clock64();
+        w_full += e1 - e0;
+        tc_fence_after();
+        float tile_sum = 0.f;
+        const bool active = (bj >= bi) && (i0 < n);
+        const bool plain = active && (bj > bi) && (i0 + kBlk <= n) && (c0 + kBlk <= n);   // no diagonal, no ragged edge
+        const uint32_t taddr = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)((buf * 2 + h) * kBlk);
+        bool released = false;
+        if (plain) {
+          // Software pipeline over the four 32-column chunks: the TMEM load of chunk c+1 and the norms of
+          // chunk c+1 (the first chunk of the NEXT column tile after the last one) are in flight while
+          // chunk c is turned into distances.
+          uint32_t va[32], vb[32];
+          tmem_ld32_issue(taddr, va);
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) {
+            uint32_t(&cur)[32] = (cc & 1) ? vb : va;
+            uint32_t(&nxt)[32] = (cc & 1) ? va : vb;
+            tmem_ld_wait(cur);
+            if (cc < 3) {
+              tmem_ld32_issue(taddr + 32 * (cc + 1), nxt);
+            } else {                     // everything is in registers: hand the accumulators back early
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&S.acc_empty[buf]);
+              released = true;
+            }
+            float4 njc[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) njc[k] = njr[k];
+            const float* nxp = norms + c0 + 32 * (cc + 1);      // cc == 3: chunk 0 of tile bj + 1 (norms is padded)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) njr[k] = __ldg(reinterpret_cast<const float4*>(nxp) + k);
+            float d[32];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              d[4 * k + 0] = fmaxf(fmaf(-2.f, __uint_as_float(cur[4 * k + 0]), ni + njc[k].x), 0.f);
+              d[4 * k + 1] = fmaxf(fmaf(-2.f, __uint_as_float(cur[4 * k + 1]), ni + njc[k].y), 0.f);
+              d[4 * k + 2] = fmaxf(fmaf(-2.f, __uint_as_float(cur[4 * k + 2]), ni + njc[k].z), 0.f);
+              d[4 * k + 3] = fmaxf(fmaf(-2.f, __uint_as_float(cur[4 * k + 3]), ni + njc[k].w), 0.f);
+            }
+#pragma unroll
+            for (int c = 0; c < 32; ++c) d[c] = sqrt_approx(d[c]);
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+            for (int c = 0; c < 32; c += 4) {
+              s0 += d[c];
+              s1 += d[c + 1];
+              s2 += d[c + 2];
+              s3 += d[c + 3];
+            }
+            tile_sum += (s0 + s1) + (s2 + s3);
+          }
+        } else {
+          if (active) {                    // warp-uniform: tcgen05.ld is .sync.aligned (all 32 lanes take part)
+#pragma unroll 1
+            for (int cc = 0; cc < 4; ++cc) {
+              uint32_t v[32];
+              tmem_ld32(taddr + 32 * cc, v);
+              const float* njp = norms + c0 + 32 * cc;
+              const int jmax = gi < n ? (int)min((int64_t)32, n - c0 - 32 * cc) : 0;   // valid columns in this chunk
+              const int jdiag = (int)(gi - c0 - 32 * cc);                     // the diagonal, if inside
+#pragma unroll
+              for (int c = 0; c < 32; ++c) {
+                const float d2 = fmaf(-2.f, __uint_as_float(v[c]), ni + __ldg(njp + c));   // norms is padded
+                const float d = sqrt_approx(fmaxf(d2, 0.f));
+                tile_sum += (c < jmax && c != jdiag) ? d : 0.f;
+              }
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k)      // keep the prefetch invariant: njr = chunk 0 of the next column tile
+            njr[k] = __ldg(reinterpret_cast<const float4*>(norms + c0 + kBlk) + k);
+        }
+        if (!released) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&S.acc_empty[buf]);       // this warp is done with the accumulators
+        }
+        w_work += clock64() - e1;
+        total += (bj == bi) ? (double)tile_sum : 2.0 * (double)tile_sum;
+      }
+    }
+    total = warp_sum(total);
+    if (lane == 0) S.red[ew] = total;
+    if (dbg && blockIdx.x == 0 && lane == 0 && (ew == 0 || ew == 5)) {
+      dbg[6 + 2 * (ew != 0)] = w_full; dbg[7 + 2 * (ew != 0)] = w_work;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (tid == 0) {
+    double s = 0.0;
+    for (int w = 0; w < kEpiWarps; ++w) s += S.red[w];
+    partial[blockIdx.x] = S.timeout ? __longlong_as_double(0x7ff8000000000000LL) : s;   // NaN = pipeline stalled
+  }
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+}  // namespace tc64
+
 }  // namespace
 
-size_t pairwise_tc_workspace_bytes(int64_t n) {
+static int64_t tc64_blocks(int64_t n) { return ((n + tc64::kBlk - 1) / tc64::kBlk + 1) / 2 * 2; }   // even
+
+size_t pairwise_tc_workspace_bytes(int64_t n, int D) {
+  if (D <= 64)   // packed operand tiles | norms (padded) | partials
+    return (size_t)tc64_blocks(n) * (tc64::kBlockB + tc64::kBlk * sizeof(float)) + tc64::kBlk * sizeof(float) +
+           1024 * sizeof(double) + 1024;
   return ((size_t)n * sizeof(float) + 255) / 256 * 256 + 1024 * sizeof(double);
+}
+
+static int launch_pairwise_tc64(const float* X, double* out, void* workspace, int64_t n, int D, cudaStream_t st) {
+  using namespace tc64;
+  const int64_t nblk = tc64_blocks(n), nb = (n + kBlk - 1) / kBlk;
+  unsigned char* packed = static_cast<unsigned char*>(workspace);          // cudaMalloc alignment (>= 256)
+  float* norms = reinterpret_cast<float*>(packed + (size_t)nblk * kBlockB);
+  // norms holds one block more than the packed tiles: the epilogue prefetches one column tile ahead
+  double* partial = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(norms) +
+                                              ((size_t)(nblk + 1) * kBlk * sizeof(float) + 255) / 256 * 256);
+  DIC_CUDA(cudaMemsetAsync(norms + nblk * kBlk, 0, kBlk * sizeof(float), st));
+  pack_split_kernel<<<(unsigned)nblk, 256, 0, st>>>(X, packed, norms, n, D);
+  DIC_LAUNCH_CHECK("pack_split_kernel");
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t P = (nb + 1) / 2;
+  const int64_t supertiles = P * nb - P * (P - 1);           // sum_p (nb - 2p)
+  int64_t L = supertiles / (8 * (int64_t)sms);
+  L = L < 2 ? 2 : (L > 64 ? 64 : L);
+  int64_t items = 0;
+  for (int64_t s = 0; s * L < nb; ++s) items += ((s + 1) * L - 1) / 2 < P - 1 ? ((s + 1) * L - 1) / 2 + 1 : P;
+  int blocks = (int)(items < sms ? items : sms);
+  if (blocks > 1024) blocks = 1024;
+  const size_t smem = sizeof(Smem64) + 1024;
+  DIC_CUDA(cudaFuncSetAttribute(pairwise_tc64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  long long* dbg = nullptr;
+  if (getenv("DIC_TC_PROFILE")) {          // debug: per-role cycle counters of CTA 0, printed after the run
+    cudaMalloc(&dbg, 16 * sizeof(long long));
+    cudaMemsetAsync(dbg, 0, 16 * sizeof(long long), st);
+  }
+  pairwise_tc64_kernel<<<blocks, kThreads64, smem, st>>>(packed, norms, partial, n, (int)L, dbg);
+  if (dbg) {
+    long long h[16];
+    cudaMemcpyAsync(h, dbg, sizeof(h), cudaMemcpyDeviceToHost, st);
+    cudaStreamSynchronize(st);
+    const double T = (double)(h[4] ? h[4] : 1);
+    fprintf(stderr, "[tc64 profile, CTA 0: %lld supertiles, %lld items, L=%lld] MMA thread: total %.0f | wait A %.0f "
+            "acc_empty %.0f B %.0f || epilogue warp 0: wait %.0f work %.0f | warp 5: wait %.0f work %.0f || producer: wait "
+            "a_empty %.0f b_empty %.0f (cycles/supertile)\n",
+            h[4], h[5], (long long)L, h[0] / T, h[1] / T, h[2] / T, h[3] / T, h[6] / T, h[7] / T, h[8] / T, h[9] / T,
+            h[10] / T, h[11] / T);
+    cudaFree(dbg);
+  }
+  DIC_LAUNCH_CHECK("pairwise_tc64_kernel");
+  sum_partials_kernel<<<1, 32, 0, st>>>(partial, out, blocks);
+  DIC_LAUNCH_CHECK("sum_partials_kernel");
+  return DIC_OK;
 }
 
 bool pairwise_tc_supported(const void* X, int D) { return D % 4 == 0 && D >= 4 && aligned16(X); }
 
 int launch_pairwise_tc(const float* X, double* out, void* workspace, int64_t n, int D, cudaStream_t st) {
+  static const bool force_v1 = getenv("DIC_PAIRWISE_TC_V1") != nullptr;      // debug: the register-staged kernel
+  if (D <= 64 && !force_v1) return launch_pairwise_tc64(X, out, workspace, n, D, st);
   float* norms = static_cast<float*>(workspace);
   double* partial = reinterpret_cast<double*>(static_cast<unsigned char*>(workspace) +
                                               ((size_t)n * sizeof(float) + 255) / 256 * 256);

@@ -49,7 +49,7 @@ def pairwise_dist_sum(Xc, exact=False):
     n, D = Xc.shape
     out = torch.empty(1, dtype=torch.float64, device=Xc.device)
     L = _lib.lib()
-    ws = torch.empty(int(L.dic_pairwise_workspace_bytes(n)), dtype=torch.uint8, device=Xc.device)
+    ws = torch.empty(int(L.dic_pairwise_workspace_bytes(n, D)), dtype=torch.uint8, device=Xc.device)
     with torch.cuda.device(Xc.device):
         _lib.check(L.dic_pairwise_dist_sum(_lib.ptr(Xc), _lib.ptr(out), _lib.ptr(ws), n, D, _DT[Xc.dtype],
                                            _lib.current_stream(Xc.device)), "dic_pairwise_dist_sum")

@@ -194,7 +194,7 @@ int dic_kmeans_min_d2(const void* X, const void* cands, const void* min_d2, void
  *   Xc (n,D) rows of one cluster (gathered by the caller), out (1) float64 =
  *   sum_{i,i'} ||x_i - x_i'||  over the FULL n x n matrix (zero diagonal included).
  * The n x n matrix is never materialised.  Limit: D <= 512. */
-size_t dic_pairwise_workspace_bytes(int64_t n);
+size_t dic_pairwise_workspace_bytes(int64_t n, int D);
 int dic_pairwise_dist_sum(const void* Xc, double* out, void* workspace, int64_t n, int D,
                           int dtype, dic_stream_t stream);
 

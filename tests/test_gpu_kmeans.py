@@ -143,7 +143,7 @@ def test_errors():
         KMeansB200(n_clusters=2, init=np.zeros((3, 4))).fit(np.zeros((10, 4), np.float32))
 
 
-@pytest.mark.parametrize("n,D", [(3000, 64), (1000, 40), (700, 256), (4097, 8)])
+@pytest.mark.parametrize("n,D", [(3000, 64), (1000, 40), (700, 256), (4097, 8), (16385, 64), (40000, 48), (513, 4)])
 def test_tensor_core_pairwise_matches_exact(n, D):
     """tcgen05 (3xTF32) pairwise-distance sum vs the direct float64 kernel and numpy."""
     from deep_interpolation_clustering_b200 import synth
