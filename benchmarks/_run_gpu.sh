@@ -1,2 +1,2 @@
 mkdir -p gpurun_out
-DIC_TC_PROFILE=1 timeout 100 python benchmarks/_pw_prof1.py > gpurun_out/pwprof.log 2>&1
+timeout 120 python benchmarks/_km_prof2.py > gpurun_out/kmplain.log 2>&1 && timeout 300 ncu --set full --clock-control none --import-source on -k regex:"kmeans_assign_rw" -s 2 -c 1 -o gpurun_out/prof_km3 python benchmarks/_km_prof2.py > gpurun_out/ncu_km3.log 2>&1

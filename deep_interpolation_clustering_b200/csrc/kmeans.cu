@@ -632,6 +632,239 @@ pairwise_sum_kernel(const T* __restrict__ X, double* __restrict__ ws, int64_t n,
   }
 }
 
+// ---- row-per-half-warp Lloyd pass ------------------------------------------------------------------
+// The streaming form of the E-step + accumulation: NO staging of X in shared memory.  Sixteen lanes own
+// one row (lane l holds elements [l*E, l*E+E) as 16-byte vectors), so one warp-wide 128-bit load covers
+// two adjacent rows and is perfectly coalesced; U = 4 such loads are in flight per warp.  The K dot
+// products are reduced over the 16 lanes with a transposed butterfly (KP/2 + KP/4 + ... shuffles, lane l
+// ends up owning centre l >> (4 - log2 KP)), the arg-min runs over the lanes (strict '<', lowest index on
+// ties, like _k_means_lloyd.pyx), and every half-warp adds its row into ITS OWN [K][D] accumulator in
+// shared memory (no atomics, fixed order => deterministic), folded in float64 at the end.
+//   flags & DIC_KM_NO_INERTIA skips the direct ||x - c||^2 / ||x - c|| sums (not needed inside the loop).
+constexpr int kRwThreads = 256;
+constexpr int kRwHalves = kRwThreads / 16;
+constexpr int kRwUnroll = 4;
+
+template <typename T> struct RwVec;
+template <> struct RwVec<float> { using type = float4; static constexpr int n = 4; };
+template <> struct RwVec<double> { using type = double2; static constexpr int n = 2; };
+
+__device__ __forceinline__ void rw_unpack(const float4& v, float* o) { o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
+__device__ __forceinline__ void rw_unpack(const double2& v, double* o) { o[0] = v.x; o[1] = v.y; }
+__device__ __forceinline__ float4 rw_pack(const float* o) { return make_float4(o[0], o[1], o[2], o[3]); }
+__device__ __forceinline__ double2 rw_pack(const double* o) { return make_double2(o[0], o[1]); }
+__device__ __forceinline__ float rw_inf(float) { return __int_as_float(0x7f800000); }
+__device__ __forceinline__ double rw_inf(double) { return __longlong_as_double(0x7ff0000000000000LL); }
+
+template <typename T, int E, int KP>
+__global__ void __launch_bounds__(kRwThreads)
+kmeans_assign_rw_kernel(const T* __restrict__ X, const T* __restrict__ centers, int32_t* __restrict__ labels,
+                        double* __restrict__ ws, int64_t N, int D, int K, int flags, int want_sums) {
+  using V = typename RwVec<T>::type;
+  constexpr int PER = RwVec<T>::n;          // elements per 16-byte vector
+  constexpr int NV = E / PER;               // vectors per lane
+  constexpr int DP = 16 * E;                // padded row length
+  constexpr int LOGKP = KP == 16 ? 4 : (KP == 8 ? 3 : 2);
+  extern __shared__ __align__(16) unsigned char smem[];
+  T* sc = reinterpret_cast<T*>(smem);                       // [K][DP] centres, zero beyond D
+  T* sacc = sc + K * DP;                                    // [halves][K][DP] per-half-warp cluster sums
+  T* scn = sacc + (want_sums ? kRwHalves * K * DP : 0);     // [KP] ||c||^2
+  int* scnt = reinterpret_cast<int*>(scn + KP);             // [halves][KP] per-half-warp counts
+  double* red = reinterpret_cast<double*>(smem);            // reused at the very end
+  const int tid = threadIdx.x, lane = tid & 31, hl = lane & 15, half = lane >> 4;
+  const int hw = tid >> 4;                                  // half-warp of this CTA
+
+  for (int i = tid; i < K * DP; i += kRwThreads) {
+    const int k = i / DP, d = i - k * DP;
+    sc[i] = d < D ? centers[(int64_t)k * D + d] : T(0);
+  }
+  if (want_sums)
+    for (int i = tid; i < kRwHalves * K * DP; i += kRwThreads) sacc[i] = T(0);
+  for (int i = tid; i < kRwHalves * KP; i += kRwThreads) scnt[i] = 0;
+  __syncthreads();
+  for (int k = tid; k < KP; k += kRwThreads) {
+    T sum = T(0);
+    if (k < K)
+      for (int d = 0; d < D; ++d) sum += sc[k * DP + d] * sc[k * DP + d];
+    scn[k] = sum;
+  }
+  __syncthreads();
+
+  const int k_own0 = hl >> (4 - LOGKP);
+  const T cn_own = k_own0 < K ? scn[k_own0] : rw_inf(T(0));
+  const bool lane_live = hl * E < D;                        // this lane's elements exist (D % PER == 0)
+  const V* scv = reinterpret_cast<const V*>(sc) + hl * NV;
+  V* saccv = reinterpret_cast<V*>(sacc + (int64_t)hw * K * DP) + hl * NV;
+  int* mycnt = scnt + hw * KP;
+  const bool keep = (flags & DIC_KM_KEEP_LABELS) != 0;
+  const bool count_changes = (flags & DIC_KM_COUNT_CHANGES) != 0;
+  const bool want_d2 = (flags & DIC_KM_NO_INERTIA) == 0;
+
+  double inertia = 0.0, dist_sum = 0.0;
+  int changed = 0;
+  const int64_t warps_total = (int64_t)gridDim.x * (kRwThreads / 32);
+  const int64_t warp_g = (int64_t)blockIdx.x * (kRwThreads / 32) + (tid >> 5);
+  const int64_t npairs = (N + 1) / 2;                       // a warp step handles rows 2*pair, 2*pair + 1
+
+  for (int64_t pair0 = warp_g; pair0 < npairs; pair0 += warps_total * kRwUnroll) {
+    V xv[kRwUnroll][NV];
+    int64_t rows[kRwUnroll];
+    int oldl[kRwUnroll];
+#pragma unroll
+    for (int u = 0; u < kRwUnroll; ++u) {
+      const int64_t pair = pair0 + (int64_t)u * warps_total;
+      rows[u] = 2 * pair + half;
+      // the previous label travels with the row (a dependent load per row would serialise the warp)
+      oldl[u] = ((keep || count_changes) && pair < npairs && rows[u] < N) ? labels[rows[u]] : 0;
+      const bool ok = pair < npairs && rows[u] < N && lane_live;
+      const V* src = reinterpret_cast<const V*>(X + (ok ? rows[u] : 0) * D) + hl * NV;
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        T z[PER];
+#pragma unroll
+        for (int e = 0; e < PER; ++e) z[e] = T(0);
+        // a lane's vectors beyond D (ragged D) are zero; D % PER == 0 is guaranteed by the launcher
+        xv[u][v] = (ok && (hl * E + v * PER) < D) ? __ldg(src + v) : rw_pack(z);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kRwUnroll; ++u) {
+      const int64_t pair = pair0 + (int64_t)u * warps_total;
+      if (pair >= npairs) break;                            // warp-uniform
+      const int64_t row = rows[u];
+      const bool row_ok = row < N;                          // uniform per half-warp
+      T x[E];
+#pragma unroll
+      for (int v = 0; v < NV; ++v) rw_unpack(xv[u][v], x + v * PER);
+      int label;
+      if (keep) {
+        label = oldl[u];
+      } else {
+        T dot[KP];
+#pragma unroll
+        for (int k = 0; k < KP; ++k) {
+          dot[k] = T(0);
+          if (k < K) {
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+              T c[PER];
+              rw_unpack(scv[k * (DP / PER) + v], c);
+#pragma unroll
+              for (int e = 0; e < PER; ++e) dot[k] += x[v * PER + e] * c[e];
+            }
+          }
+        }
+        // transposed butterfly over the 16 lanes of the row
+        int nred = KP;
+#pragma unroll
+        for (int off = 8; off >= 1; off >>= 1) {
+          if (nred > 1) {
+            nred >>= 1;
+            const bool up = (hl & off) != 0;
+#pragma unroll
+            for (int i = 0; i < KP / 2; ++i) {
+              if (i < nred) {
+                const T send = up ? dot[i] : dot[i + nred];
+                const T keepv = up ? dot[i + nred] : dot[i];
+                dot[i] = keepv + __shfl_xor_sync(0xffffffffu, send, off);
+              }
+            }
+          } else {
+            dot[0] += __shfl_xor_sync(0xffffffffu, dot[0], off);
+          }
+        }
+        T dk = cn_own - T(2) * dot[0];                      // ||c||^2 - 2 x.c  (||x||^2 omitted); inf for k >= K
+        int kb = k_own0;
+#pragma unroll
+        for (int off = 8; off >= (16 >> LOGKP); off >>= 1) {
+          const T od = __shfl_xor_sync(0xffffffffu, dk, off);
+          const int ok2 = __shfl_xor_sync(0xffffffffu, kb, off);
+          if (od < dk || (od == dk && ok2 < kb)) {          // lowest index wins ties
+            dk = od;
+            kb = ok2;
+          }
+        }
+        label = kb;
+        if (hl == 0 && row_ok) {
+          if (count_changes) changed += (oldl[u] != label);
+          labels[row] = label;
+        }
+      }
+      if (want_d2) {                                        // warp-uniform: the shuffles need all 32 lanes
+        T d2 = T(0);
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          T c[PER];
+          rw_unpack(scv[label * (DP / PER) + v], c);
+#pragma unroll
+          for (int e = 0; e < PER; ++e) {
+            const T df = x[v * PER + e] - c[e];
+            d2 += df * df;
+          }
+        }
+#pragma unroll
+        for (int off = 8; off >= 1; off >>= 1) d2 += __shfl_xor_sync(0xffffffffu, d2, off);
+        if (hl == 0 && row_ok) {
+          inertia += (double)d2;
+          dist_sum += sqrt((double)d2);
+        }
+      }
+      if (row_ok) {
+        if (want_sums) {
+#pragma unroll
+          for (int v = 0; v < NV; ++v) {
+            T a[PER];
+            rw_unpack(saccv[label * (DP / PER) + v], a);
+#pragma unroll
+            for (int e = 0; e < PER; ++e) a[e] += x[v * PER + e];
+            saccv[label * (DP / PER) + v] = rw_pack(a);
+          }
+          if (hl == 0) mycnt[label] += 1;
+        }
+      }
+    }
+  }
+  __syncthreads();
+
+  // per-block partials: [K*D] sums | [K] counts | inertia | changed | dist_sum | 0
+  double* out = ws + (int64_t)blockIdx.x * ((int64_t)K * D + K + 4);
+  if (want_sums) {
+    for (int i = tid; i < K * D; i += kRwThreads) {
+      const int k = i / D, d = i - k * D;
+      double sum = 0.0;
+      for (int h = 0; h < kRwHalves; ++h) sum += (double)sacc[((int64_t)h * K + k) * DP + d];
+      out[i] = sum;
+    }
+    for (int i = tid; i < K; i += kRwThreads) {
+      int c = 0;
+      for (int h = 0; h < kRwHalves; ++h) c += scnt[h * KP + i];
+      out[(int64_t)K * D + i] = (double)c;
+    }
+  }
+  __syncthreads();
+  inertia = warp_sum(inertia);
+  dist_sum = warp_sum(dist_sum);
+  const double ch = warp_sum((double)changed);
+  if (lane == 0) {
+    red[(tid >> 5) * 3 + 0] = inertia;
+    red[(tid >> 5) * 3 + 1] = ch;
+    red[(tid >> 5) * 3 + 2] = dist_sum;
+  }
+  __syncthreads();
+  if (tid < 3) {
+    double sum = 0.0;
+    for (int w = 0; w < kRwThreads / 32; ++w) sum += red[w * 3 + tid];
+    out[(int64_t)K * D + K + tid] = sum;
+  }
+  if (tid == 3) out[(int64_t)K * D + K + 3] = 0.0;
+}
+
+template <typename T>
+size_t rw_smem_bytes(int K, int E, int KP, bool want_sums) {
+  const size_t dp = 16 * (size_t)E;
+  return sizeof(T) * (K * dp + (want_sums ? (size_t)kRwHalves * K * dp : 0) + KP) + sizeof(int) * kRwHalves * KP + 64;
+}
+
 int km_blocks(int K, int D) {
   int64_t per = (int64_t)K * D + K + 4;
   int64_t b = (8LL << 20) / per;
@@ -643,6 +876,50 @@ int km_blocks(int K, int D) {
 template <typename T>
 int launch_assign(const void* X, const void* centers, int32_t* labels, double* sums, double* counts,
                   double* stats, void* workspace, int64_t N, int D, int K, int flags, cudaStream_t st) {
+  // streaming row-per-half-warp kernel: K <= 16, rows of whole 16-byte vectors, <= 16 elements per lane
+  {
+    constexpr int PER = 16 / (int)sizeof(T);
+    const int e_need = (D + 15) / 16;
+    const int E = e_need <= 4 ? 4 : (e_need <= 8 ? 8 : 16);
+    const int KP = K <= 4 ? 4 : (K <= 8 ? 8 : 16);
+    const bool no_rw = getenv("DIC_KMEANS_NO_RW") != nullptr;     // debug: force the tile kernel
+    const size_t smem = rw_smem_bytes<T>(K, E, KP, sums != nullptr);
+    // measured on B200 at 1M x 64 (benchmarks/_km_pass.py): the streaming kernel wins for K <= 8 in float32
+    // (0.15-0.19 ms vs 0.21-0.23 ms per pass) and K <= 4 in float64; beyond that its per-row shuffle
+    // reductions cost more issue slots than the tile kernel's shared-memory staging
+    const bool rw_wins = sizeof(T) == 4 ? K <= 8 : K <= 4;
+    if (!no_rw && rw_wins && D <= 256 && D % PER == 0 && aligned16(X) && smem <= 100 * 1024) {
+      int dev = 0, sms = 148;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      const int per_sm = smem <= 36 * 1024 ? 4 : (smem <= 56 * 1024 ? 3 : 2);      // resident CTAs (8 warps each)
+      int nb = sms * per_sm;
+      const int cap = km_blocks(K, D);                 // the workspace holds this many per-block partials
+      if (nb > cap) nb = cap;
+      const int64_t want = (N + 2 * (kRwThreads / 32) * kRwUnroll - 1) / (2 * (kRwThreads / 32) * kRwUnroll);
+      if (want < nb) nb = (int)want;
+      if (nb < 1) nb = 1;
+      double* wsd = static_cast<double*>(workspace);
+#define DIC_RW_LAUNCH(E_, KP_)                                                                               \
+  {                                                                                                          \
+    auto kf = kmeans_assign_rw_kernel<T, E_, KP_>;                                                           \
+    if (smem > 48 * 1024)                                                                                    \
+      DIC_CUDA(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
+    kf<<<nb, kRwThreads, smem, st>>>(static_cast<const T*>(X), static_cast<const T*>(centers), labels, wsd,  \
+                                     N, D, K, flags, sums != nullptr);                                       \
+  }
+#define DIC_RW_KP(E_)                                                                                        \
+  if (KP == 4) DIC_RW_LAUNCH(E_, 4) else if (KP == 8) DIC_RW_LAUNCH(E_, 8) else DIC_RW_LAUNCH(E_, 16)
+      if (E == 4) { DIC_RW_KP(4) } else if (E == 8) { DIC_RW_KP(8) } else { DIC_RW_KP(16) }
+#undef DIC_RW_KP
+#undef DIC_RW_LAUNCH
+      DIC_LAUNCH_CHECK("kmeans_assign_rw_kernel");
+      const int nn = K * D + K + 4;
+      kmeans_finish_kernel<<<(nn + 7) / 8, 256, 0, st>>>(wsd, sums, counts, stats, nb, K, D);
+      DIC_LAUNCH_CHECK("kmeans_finish_kernel");
+      return DIC_OK;
+    }
+  }
   const int s16 = row_stride16<T>(D);
   int tile = 128;
   KmLayout L = km_layout<T>(K, D, tile);

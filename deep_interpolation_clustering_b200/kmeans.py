@@ -28,6 +28,7 @@ from . import _lib
 _DT = {torch.float32: 0, torch.float64: 1}
 DIC_KM_COUNT_CHANGES = 1
 DIC_KM_KEEP_LABELS = 2
+DIC_KM_NO_INERTIA = 4       # a Lloyd iteration does not need the inertia / distance sums
 
 
 def _check_random_state(seed):
@@ -269,7 +270,7 @@ class KMeansB200:
         n_iter = 0
         for i in range(self.max_iter):
             n_iter = i + 1
-            st.assign(centers, DIC_KM_COUNT_CHANGES)
+            st.assign(centers, DIC_KM_COUNT_CHANGES | DIC_KM_NO_INERTIA)
             comm.sum_(st.sums, st.counts, st.stats)          # the one exchange step per iteration
             if hasattr(st, "update"):
                 old = centers.clone()

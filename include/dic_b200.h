@@ -169,6 +169,7 @@ int dic_dec_kl_fwd_bwd(const float* z, const float* mu, const double* colsum, fl
  */
 #define DIC_KM_COUNT_CHANGES 1
 #define DIC_KM_KEEP_LABELS 2
+#define DIC_KM_NO_INERTIA 4 /* skip stats[0] and stats[2] (a Lloyd iteration does not need them) */
 size_t dic_kmeans_workspace_bytes(int K, int D);
 int dic_kmeans_assign(const void* X, const void* centers, int32_t* labels, double* sums,
                       double* counts, double* stats, void* workspace, int64_t N, int D, int K,
