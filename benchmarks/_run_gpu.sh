@@ -1,2 +1,4 @@
-mkdir -p gpurun_out
-timeout 120 python benchmarks/_km_prof2.py > gpurun_out/kmplain.log 2>&1 && timeout 300 ncu --set full --clock-control none --import-source on -k regex:"kmeans_assign_rw" -s 2 -c 1 -o gpurun_out/prof_km3 python benchmarks/_km_prof2.py > gpurun_out/ncu_km3.log 2>&1
+mkdir -p gpurun_out; rm -f gpurun_out/parity_report.jsonl
+timeout 120 python -m pytest tests/test_gpu_kmeans.py -m gpu -x -q --timeout 100 -k "silhouette or tensor" > gpurun_out/pytest_sil.log 2>&1; echo "exit $?" >> gpurun_out/pytest_sil.log
+timeout 200 python -m pytest tests/test_gpu_kmeans.py tests/test_gpu_interp.py -m gpu -x -q --timeout 100 >> gpurun_out/pytest_sil.log 2>&1; echo "exit $?" >> gpurun_out/pytest_sil.log
+timeout 300 python bench.py --workload c5 --steps 3 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/bench_c5.json 2> gpurun_out/bench_c5.err; echo "exit $?" >> gpurun_out/bench_c5.err

@@ -39,6 +39,8 @@ def main():
     ap.add_argument("--d", type=int, default=64)
     ap.add_argument("--sweep-n", type=int, default=100_000)
     ap.add_argument("--cpu-n", type=int, default=4000)
+    ap.add_argument("--full-refs", type=int, default=0, help="reference sets of the full-size (c4) sweep; 0 = skip")
+    ap.add_argument("--full-ninit", type=int, default=2)
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     out = {"n": args.n, "d": args.d}
@@ -85,6 +87,19 @@ def main():
     out["gap_sweep_s"] = round(time.perf_counter() - t0, 2)
     out["gap_sweep_n"] = args.sweep_n
     out["gap_best_k"] = int(df["gap"].astype(float).idxmax())
+
+    # BASELINE config 4 at full size (N x d, K = 2..10) with a reduced number of reference sets / restarts;
+    # the full 20 x 10 sweep is (21 / (refs + 1)) * (10 / n_init) times this
+    if args.full_refs > 0:
+        km = KM(10, None, [], args.full_ninit, args.full_refs)
+        t0 = time.perf_counter()
+        df = km.compute_gap_internal_metric(KMeansB200(n_init=args.full_ninit), X, k_max=10,
+                                            n_references=args.full_refs, version=1, draw="device")
+        torch.cuda.synchronize()
+        out["c4_sweep_s"] = round(time.perf_counter() - t0, 2)
+        out["c4_sweep_cfg"] = {"n": args.n, "d": args.d, "k": "2..10", "n_references": args.full_refs,
+                               "n_init": args.full_ninit, "draws": "device"}
+        out["c4_best_k"] = int(df["gap"].astype(float).idxmax())
 
     # CPU: the reference's own stack at a size it can run
     from sklearn.cluster import KMeans

@@ -47,6 +47,7 @@ SIGNATURES = {
     "dic_kmeans_min_d2": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, _P]),
     "dic_pairwise_dist_sum": (c_int, [_P, _P, _P, c_int64, c_int, c_int, _P]),
     "dic_pairwise_workspace_bytes": (c_size_t, [c_int64, c_int]),
+    "dic_cluster_rowsums": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, c_int, _P]),
     "dic_colsum_workspace_bytes": (c_size_t, [c_int]),
     "dic_colsum_f32": (c_int, [_P, _P, _P, c_int64, c_int, _P]),
     "dic_probe_mufu": (c_int, [POINTER(c_double), _P]),

@@ -498,7 +498,7 @@ extern "C" int dic_cci_fwd(const float* u, const float* kernel, float* out, int6
     const unsigned grid = (unsigned)((B + kCciWarps - 1) / kCciWarps);
     const size_t tile = (size_t)3 * C * R * 4;
     const size_t smem = 64 + kCciWarps * tile;
-    if (tile % 16 == 0 && aligned16(u) && smem <= 100 * 1024) {
+    if (tile % 16 == 0 && aligned16(u) && smem <= (size_t)kMaxSmemBytes) {
       if (smem > 48 * 1024)
         DIC_CUDA(cudaFuncSetAttribute(cci_fwd_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem));
@@ -534,7 +534,7 @@ extern "C" int dic_cci_bwd(const float* u, const float* kernel, const float* gra
   if (C <= 8) {
     const unsigned grid = (unsigned)((B + kCciWarps - 1) / kCciWarps);
     const size_t tile = (size_t)3 * C * R * 4, smem = 64 + kCciWarps * 2 * tile;
-    if (tile % 16 == 0 && aligned16(u) && aligned16(grad_out) && smem <= 100 * 1024) {
+    if (tile % 16 == 0 && aligned16(u) && aligned16(grad_out) && smem <= (size_t)kMaxSmemBytes) {
       if (smem > 48 * 1024)
         DIC_CUDA(cudaFuncSetAttribute(cci_bwd_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem));

@@ -22,6 +22,8 @@ namespace dic {
 size_t pairwise_tc_workspace_bytes(int64_t n, int D);
 bool pairwise_tc_supported(const void* X, int D);
 int launch_pairwise_tc(const float* X, double* out, void* workspace, int64_t n, int D, cudaStream_t st);
+int launch_cluster_rowsums_tc(const float* X, const int32_t* perm, const int32_t* tile_cluster, double* rowsum,
+                              void* workspace, int64_t n_pad, int D, int K, cudaStream_t st);
 
 namespace {
 
@@ -1078,6 +1080,18 @@ extern "C" size_t dic_pairwise_workspace_bytes(int64_t n, int D) {
   const size_t a = (size_t)kPwBlocks * sizeof(double) + 256;
   const size_t b = pairwise_tc_workspace_bytes(n < 0 ? 0 : n, D);
   return a > b ? a : b;
+}
+
+extern "C" int dic_cluster_rowsums(const float* X, const int32_t* perm, const int32_t* tile_cluster,
+                                   double* rowsum, void* workspace, int64_t n_pad, int D, int K,
+                                   dic_stream_t stream) {
+  DIC_REQUIRE(X && perm && tile_cluster && rowsum && workspace, DIC_ERR_INVALID_ARGUMENT, "null pointer argument");
+  DIC_REQUIRE(n_pad > 0 && n_pad % 128 == 0, DIC_ERR_INVALID_ARGUMENT,
+              "n_pad=%lld must be a positive multiple of 128 (clusters padded to whole tiles)", (long long)n_pad);
+  DIC_REQUIRE(K > 0, DIC_ERR_INVALID_ARGUMENT, "K=%d", K);
+  DIC_REQUIRE(D > 0 && D <= 64 && D % 4 == 0 && aligned16(X), DIC_ERR_UNSUPPORTED,
+              "the tensor-core row-sum kernel needs D <= 64, D %% 4 == 0 and 16-byte aligned rows (got D=%d)", D);
+  return launch_cluster_rowsums_tc(X, perm, tile_cluster, rowsum, workspace, n_pad, D, K, as_stream(stream));
 }
 
 extern "C" int dic_pairwise_dist_sum(const void* Xc, double* out, void* workspace, int64_t n, int D, int dtype,

@@ -464,20 +464,21 @@ struct __align__(128) Smem64 {
 struct ItemIter {
   int64_t nb, P, S, s, w, p;
   int L, G, cta;
-  __device__ void init(int64_t nb_, int L_, int G_, int cta_) {
-    nb = nb_; L = L_; G = G_; cta = cta_;
+  bool full;     // true: the whole nb x nb grid of tiles (row sums); false: the upper triangle (symmetric sum)
+  __device__ void init(int64_t nb_, int L_, int G_, int cta_, bool full_) {
+    nb = nb_; L = L_; G = G_; cta = cta_; full = full_;
     P = (nb + 1) / 2;
     S = (nb + L - 1) / L;
     s = 0; w = 0;
     p = first();
   }
   __device__ int64_t first() const { return (int64_t)((((cta - w) % G) + G) % G); }
-  __device__ int64_t pmax() const { return min(P - 1, ((s + 1) * L - 1) / 2); }
+  __device__ int64_t pmax() const { return full ? P - 1 : min(P - 1, ((s + 1) * L - 1) / 2); }
   __device__ bool next(int64_t& op, int64_t& j0, int64_t& j1) {
     while (s < S) {
       if (p <= pmax()) {
         op = p;
-        j0 = max(s * L, 2 * p);
+        j0 = full ? s * L : max(s * L, 2 * p);
         j1 = min((s + 1) * L, nb);
         p += G;
         return true;
@@ -494,7 +495,7 @@ struct ItemIter {
 // are zero.  One CTA per 128-row block, thread -> (row, 16-byte K chunk): coalesced reads.
 __global__ void __launch_bounds__(256)
 pack_split_kernel(const float* __restrict__ X, unsigned char* __restrict__ packed, float* __restrict__ norms,
-                  int64_t n, int D) {
+                  int64_t n, int D, const int32_t* __restrict__ perm, float pad_norm) {
   const int64_t blk = blockIdx.x;
   unsigned char* out = packed + blk * (int64_t)kBlockB;
 #pragma unroll
@@ -502,8 +503,10 @@ pack_split_kernel(const float* __restrict__ X, unsigned char* __restrict__ packe
     const int idx = it * 256 + threadIdx.x;
     const int row = idx >> 4, c = idx & 15;
     const int64_t gr = blk * kBlk + row;
+    // perm (row-sums mode): packed row gr holds X[perm[gr]], perm < 0 = padding between clusters
+    const int64_t src = gr < n ? (perm ? (int64_t)__ldg(perm + gr) : gr) : -1;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (gr < n && 4 * c < D) v = __ldg(reinterpret_cast<const float4*>(X + gr * D + 4 * c));
+    if (src >= 0 && 4 * c < D) v = __ldg(reinterpret_cast<const float4*>(X + src * D + 4 * c));
     float4 h, l;
     h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
     l.x = to_tf32(v.x - h.x); l.y = to_tf32(v.y - h.y); l.z = to_tf32(v.z - h.z); l.w = to_tf32(v.w - h.w);
@@ -513,13 +516,21 @@ pack_split_kernel(const float* __restrict__ X, unsigned char* __restrict__ packe
     float s = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, v.w * v.w)));
 #pragma unroll
     for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (c == 0) norms[gr] = s;
+    // a padding row gets pad_norm: -inf makes every distance to it exactly 0 (max(-inf, 0) under the sqrt)
+    if (c == 0) norms[gr] = src >= 0 ? s : pad_norm;
   }
 }
 
+// ROWSUMS = false: partial[cta] = this CTA's share of sum_{i,j} ||x_i - x_j|| (upper triangle, doubled).
+// ROWSUMS = true : rows are sorted by cluster and every cluster is padded to whole 128-row tiles (padding
+//                  rows carry norm = -inf => distance 0), tile_cluster[bj] names the cluster of column tile
+//                  bj, and rowsum[i][k] += sum_{j in tile, cluster k} ||x_i - x_j|| over the FULL grid: what
+//                  the silhouette needs (sklearn.metrics.silhouette_samples) without the n x n matrix.
+template <bool ROWSUMS>
 __global__ void __launch_bounds__(kThreads64, 1)
 pairwise_tc64_kernel(const unsigned char* __restrict__ packed, const float* __restrict__ norms,
-                     double* __restrict__ partial, int64_t n, int L, long long* __restrict__ dbg) {
+                     double* __restrict__ partial, int64_t n, int L, long long* __restrict__ dbg,
+                     const int32_t* __restrict__ tile_cluster, double* __restrict__ rowsum, int K) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   Smem64& S = *reinterpret_cast<Smem64*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -547,7 +558,7 @@ pairwise_tc64_kernel(const unsigned char* __restrict__ packed, const float* __re
   volatile int* timeout = &S.timeout;
 
   ItemIter it;
-  it.init(nb, L, (int)gridDim.x, (int)blockIdx.x);
+  it.init(nb, L, (int)gridDim.x, (int)blockIdx.x, ROWSUMS);
   int64_t p, j0, j1;
   double total = 0.0;
 
@@ -644,17 +655,29 @@ pairwise_tc64_kernel(const unsigned char* __restrict__ packed, const float* __re
       float4 njr[8];                       // norms of the next 32 columns to be processed, prefetched
 #pragma unroll
       for (int k = 0; k < 8; ++k) njr[k] = __ldg(reinterpret_cast<const float4*>(norms + j0 * kBlk) + k);
+      int kcur = -1;                       // ROWSUMS: cluster of the column tiles summed into racc so far
+      double racc = 0.0;
       for (int64_t bj = j0; bj < j1; ++bj, ++t) {
         const int buf = (int)(t & 1);
         const int64_t c0 = bj * kBlk;
+        if (ROWSUMS) {
+          const int kc = __ldg(tile_cluster + bj);
+          if (kc != kcur) {
+            if (kcur >= 0 && gi < n) atomicAdd(rowsum + gi * K + kcur, racc);
+            racc = 0.0;
+            kcur = kc;
+          }
+        }
         const long long e0 = clock64();
         if (!bar_wait_bounded(&S.acc_full[buf], (uint32_t)((t >> 1) & 1))) { *timeout = 1; dead = true; break; }
         const long long e1 = clock64();
         w_full += e1 - e0;
         tc_fence_after();
         float tile_sum = 0.f;
-        const bool active = (bj >= bi) && (i0 < n);
-        const bool plain = active && (bj > bi) && (i0 + kBlk <= n) && (c0 + kBlk <= n);   // no diagonal, no ragged edge
+        // ROWSUMS: every tile counts, padding is neutralised by its -inf norm, only the diagonal needs care
+        const bool active = ROWSUMS ? (i0 < n) : ((bj >= bi) && (i0 < n));
+        const bool plain = ROWSUMS ? (active && bj != bi)
+                                   : (active && (bj > bi) && (i0 + kBlk <= n) && (c0 + kBlk <= n));   // no diagonal / ragged edge
         const uint32_t taddr = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)((buf * 2 + h) * kBlk);
         bool released = false;
         if (plain) {
@@ -709,7 +732,7 @@ pairwise_tc64_kernel(const unsigned char* __restrict__ packed, const float* __re
               uint32_t v[32];
               tmem_ld32(taddr + 32 * cc, v);
               const float* njp = norms + c0 + 32 * cc;
-              const int jmax = gi < n ? (int)min((int64_t)32, n - c0 - 32 * cc) : 0;   // valid columns in this chunk
+              const int jmax = gi < n ? (ROWSUMS ? 32 : (int)min((int64_t)32, n - c0 - 32 * cc)) : 0;   // valid columns
               const int jdiag = (int)(gi - c0 - 32 * cc);                     // the diagonal, if inside
 #pragma unroll
               for (int c = 0; c < 32; ++c) {
@@ -729,8 +752,10 @@ pairwise_tc64_kernel(const unsigned char* __restrict__ packed, const float* __re
           if (lane == 0) mbar_arrive(&S.acc_empty[buf]);       // this warp is done with the accumulators
         }
         w_work += clock64() - e1;
-        total += (bj == bi) ? (double)tile_sum : 2.0 * (double)tile_sum;
+        if (ROWSUMS) racc += (double)tile_sum;
+        else total += (bj == bi) ? (double)tile_sum : 2.0 * (double)tile_sum;
       }
+      if (ROWSUMS && kcur >= 0 && gi < n) atomicAdd(rowsum + gi * K + kcur, racc);
     }
     total = warp_sum(total);
     if (lane == 0) S.red[ew] = total;
@@ -745,6 +770,7 @@ pairwise_tc64_kernel(const unsigned char* __restrict__ packed, const float* __re
     double s = 0.0;
     for (int w = 0; w < kEpiWarps; ++w) s += S.red[w];
     partial[blockIdx.x] = S.timeout ? __longlong_as_double(0x7ff8000000000000LL) : s;   // NaN = pipeline stalled
+    if (ROWSUMS && S.timeout) rowsum[0] = __longlong_as_double(0x7ff8000000000000LL);
   }
   if (warp == 2) {
     tc_fence_after();
@@ -765,8 +791,12 @@ size_t pairwise_tc_workspace_bytes(int64_t n, int D) {
   return ((size_t)n * sizeof(float) + 255) / 256 * 256 + 1024 * sizeof(double);
 }
 
-static int launch_pairwise_tc64(const float* X, double* out, void* workspace, int64_t n, int D, cudaStream_t st) {
+// Shared launcher.  rowsum == nullptr: pairwise sum of the n rows of X -> out.  Otherwise: X is read
+// through perm (n = padded row count), rowsum (n, K) is zeroed and filled.
+static int launch_tc64(const float* X, double* out, void* workspace, int64_t n, int D, const int32_t* perm,
+                       const int32_t* tile_cluster, double* rowsum, int K, cudaStream_t st) {
   using namespace tc64;
+  const bool rows_mode = rowsum != nullptr;
   const int64_t nblk = tc64_blocks(n), nb = (n + kBlk - 1) / kBlk;
   unsigned char* packed = static_cast<unsigned char*>(workspace);          // cudaMalloc alignment (>= 256)
   float* norms = reinterpret_cast<float*>(packed + (size_t)nblk * kBlockB);
@@ -774,27 +804,37 @@ static int launch_pairwise_tc64(const float* X, double* out, void* workspace, in
   double* partial = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(norms) +
                                               ((size_t)(nblk + 1) * kBlk * sizeof(float) + 255) / 256 * 256);
   DIC_CUDA(cudaMemsetAsync(norms + nblk * kBlk, 0, kBlk * sizeof(float), st));
-  pack_split_kernel<<<(unsigned)nblk, 256, 0, st>>>(X, packed, norms, n, D);
+  if (rows_mode) DIC_CUDA(cudaMemsetAsync(rowsum, 0, (size_t)n * K * sizeof(double), st));
+  const float pad_norm = rows_mode ? -INFINITY : 0.f;
+  pack_split_kernel<<<(unsigned)nblk, 256, 0, st>>>(X, packed, norms, n, D, perm, pad_norm);
   DIC_LAUNCH_CHECK("pack_split_kernel");
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int64_t P = (nb + 1) / 2;
-  const int64_t supertiles = P * nb - P * (P - 1);           // sum_p (nb - 2p)
+  const int64_t supertiles = rows_mode ? P * nb : P * nb - P * (P - 1);    // full grid | sum_p (nb - 2p)
   int64_t L = supertiles / (8 * (int64_t)sms);
   L = L < 2 ? 2 : (L > 64 ? 64 : L);
   int64_t items = 0;
-  for (int64_t s = 0; s * L < nb; ++s) items += ((s + 1) * L - 1) / 2 < P - 1 ? ((s + 1) * L - 1) / 2 + 1 : P;
+  for (int64_t s = 0; s * L < nb; ++s)
+    items += rows_mode ? P : (((s + 1) * L - 1) / 2 < P - 1 ? ((s + 1) * L - 1) / 2 + 1 : P);
   int blocks = (int)(items < sms ? items : sms);
   if (blocks > 1024) blocks = 1024;
   const size_t smem = sizeof(Smem64) + 1024;
-  DIC_CUDA(cudaFuncSetAttribute(pairwise_tc64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   long long* dbg = nullptr;
   if (getenv("DIC_TC_PROFILE")) {          // debug: per-role cycle counters of CTA 0, printed after the run
     cudaMalloc(&dbg, 16 * sizeof(long long));
     cudaMemsetAsync(dbg, 0, 16 * sizeof(long long), st);
   }
-  pairwise_tc64_kernel<<<blocks, kThreads64, smem, st>>>(packed, norms, partial, n, (int)L, dbg);
+  if (rows_mode) {
+    DIC_CUDA(cudaFuncSetAttribute(pairwise_tc64_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pairwise_tc64_kernel<true><<<blocks, kThreads64, smem, st>>>(packed, norms, partial, n, (int)L, dbg, tile_cluster,
+                                                                 rowsum, K);
+  } else {
+    DIC_CUDA(cudaFuncSetAttribute(pairwise_tc64_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pairwise_tc64_kernel<false><<<blocks, kThreads64, smem, st>>>(packed, norms, partial, n, (int)L, dbg, nullptr,
+                                                                  nullptr, 0);
+  }
   if (dbg) {
     long long h[16];
     cudaMemcpyAsync(h, dbg, sizeof(h), cudaMemcpyDeviceToHost, st);
@@ -808,9 +848,21 @@ static int launch_pairwise_tc64(const float* X, double* out, void* workspace, in
     cudaFree(dbg);
   }
   DIC_LAUNCH_CHECK("pairwise_tc64_kernel");
-  sum_partials_kernel<<<1, 32, 0, st>>>(partial, out, blocks);
-  DIC_LAUNCH_CHECK("sum_partials_kernel");
+  if (!rows_mode) {
+    sum_partials_kernel<<<1, 32, 0, st>>>(partial, out, blocks);
+    DIC_LAUNCH_CHECK("sum_partials_kernel");
+  }
   return DIC_OK;
+}
+
+static int launch_pairwise_tc64(const float* X, double* out, void* workspace, int64_t n, int D, cudaStream_t st) {
+  return launch_tc64(X, out, workspace, n, D, nullptr, nullptr, nullptr, 0, st);
+}
+
+// Row sums by cluster (silhouette): see pairwise_tc64_kernel<true>.  n_pad % 128 == 0.
+int launch_cluster_rowsums_tc(const float* X, const int32_t* perm, const int32_t* tile_cluster, double* rowsum,
+                              void* workspace, int64_t n_pad, int D, int K, cudaStream_t st) {
+  return launch_tc64(X, nullptr, workspace, n_pad, D, perm, tile_cluster, rowsum, K, st);
 }
 
 bool pairwise_tc_supported(const void* X, int D) { return D % 4 == 0 && D >= 4 && aligned16(X); }

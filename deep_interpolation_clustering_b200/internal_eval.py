@@ -2,15 +2,20 @@
 
 Mirror of internal_eval.py:112-147 (same class names, ``metric(x, labels)`` call signature).
 SURVEY.md section 8(f) ranks these as the first "next" row after the hot path.  Status:
-Calinski-Harabasz and Davies-Bouldin are O(N K D) and run as device reductions; Silhouette
-and Dunn are O(N^2) and run as chunked device distance tiles (torch.cdist, library code) -
-a native tiled kernel sharing ``dic_pairwise_dist_sum``'s structure is the planned
-replacement.  Formulas follow sklearn.metrics 1.9.0 (_unsupervised.py).
+Calinski-Harabasz and Davies-Bouldin are O(N K D) and run as device reductions.  Silhouette is
+O(N^2): for D <= 64 its per-row, per-cluster distance sums come from the tcgen05 tile kernel
+(``dic_cluster_rowsums``: rows sorted by cluster, clusters padded to whole 128-row tiles, nothing
+materialised); other shapes and Dunn use chunked device distance tiles (torch.cdist, library code).
+Formulas follow sklearn.metrics 1.9.0 (_unsupervised.py).
 """
 from __future__ import annotations
 
 import numpy as np
 import torch
+
+from . import _lib
+
+TC_MIN_ROWS = 1024     # below this the chunked float64 path is used
 
 
 def _prep(x, labels):
@@ -59,13 +64,60 @@ class DBIndex(object):
 class Sihouette(object):
     """Mean silhouette coefficient (name as upstream).  internal_eval.py:112-122."""
 
-    def __init__(self, chunk=8192):
+    def __init__(self, chunk=8192, native=True):
         self.chunk = chunk
+        self.native = native
+
+    @staticmethod
+    def _finish(per_cluster, own, cnt):
+        """(rows, K) distance sums -> sum of silhouette samples (sklearn _unsupervised.py:silhouette_samples)."""
+        rows = torch.arange(own.numel(), device=own.device)
+        n_own = cnt[own]
+        a = per_cluster[rows, own] / (n_own - 1).clamp(min=1)
+        other = per_cluster / cnt[None, :]
+        other[rows, own] = float("inf")
+        b = other.min(dim=1).values
+        sil = (b - a) / torch.maximum(a, b)
+        sil = torch.where(n_own > 1, sil, torch.zeros_like(sil))         # singleton clusters score 0
+        return torch.nan_to_num(sil).sum()
+
+    @staticmethod
+    def rowsums_native(x32, inv, K):
+        """Per-row per-cluster distance sums (N, K) float64 in the ORIGINAL row order, via dic_cluster_rowsums."""
+        dev = x32.device
+        N, D = x32.shape
+        cnt = torch.bincount(inv, minlength=K)
+        order = torch.argsort(inv, stable=True)
+        start = torch.cumsum(cnt, 0) - cnt                                # first sorted index of each cluster
+        padded = (cnt + 127) // 128 * 128
+        pstart = torch.cumsum(padded, 0) - padded                         # first packed row of each cluster
+        n_pad = int(padded.sum())
+        k_sorted = inv[order]
+        pos = pstart[k_sorted] + (torch.arange(N, device=dev) - start[k_sorted])
+        perm = torch.full((n_pad,), -1, dtype=torch.int32, device=dev)
+        perm[pos] = order.to(torch.int32)
+        tile_cluster = torch.repeat_interleave(torch.arange(K, device=dev, dtype=torch.int32), padded // 128)
+        xc = (x32 - x32.mean(dim=0, keepdim=True)).contiguous()           # distances are translation invariant
+        rowsum = torch.empty((n_pad, K), dtype=torch.float64, device=dev)
+        L = _lib.lib()
+        ws = torch.empty(int(L.dic_pairwise_workspace_bytes(n_pad, D)), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(L.dic_cluster_rowsums(_lib.ptr(xc), _lib.ptr(perm), _lib.ptr(tile_cluster), _lib.ptr(rowsum),
+                                             _lib.ptr(ws), n_pad, D, K, _lib.current_stream(dev)),
+                       "dic_cluster_rowsums")
+        out = torch.empty((N, K), dtype=torch.float64, device=dev)
+        out[order] = rowsum[pos]
+        if bool(torch.isnan(rowsum[0, 0])):
+            raise _lib.DicError("dic_cluster_rowsums: the tensor-core pipeline reported a timeout")
+        return out
 
     def __call__(self, x, labels, *args, **kwargs):
         x, inv, K = _prep(x, labels)
         N = x.shape[0]
         cnt = torch.bincount(inv, minlength=K).to(x.dtype)
+        if self.native and x.is_cuda and N >= TC_MIN_ROWS and x.shape[1] <= 64 and x.shape[1] % 4 == 0:
+            per_cluster = self.rowsums_native(x.to(torch.float32), inv, K)
+            return float(self._finish(per_cluster, inv, cnt) / N)
         onehot = torch.zeros((N, K), dtype=x.dtype, device=x.device)
         onehot[torch.arange(N, device=x.device), inv] = 1.0
         total = torch.zeros((), dtype=x.dtype, device=x.device)

@@ -199,6 +199,18 @@ size_t dic_pairwise_workspace_bytes(int64_t n, int D);
 int dic_pairwise_dist_sum(const void* Xc, double* out, void* workspace, int64_t n, int D,
                           int dtype, dic_stream_t stream);
 
+/* Per-row, per-cluster distance sums - the O(N^2) part of the silhouette coefficient
+ * (internal_eval.py:112-122 -> sklearn.metrics.silhouette_score, called inside the gap loop at
+ * p2_clustering_optK.py:401-405) - on the tensor cores, without the n x n matrix:
+ *   rowsum[i][k] = sum_{j : cluster(j) = k} ||x_perm[i] - x_perm[j]||          (n_pad, K) float64
+ * The caller sorts the rows by cluster and pads every cluster to whole 128-row tiles:
+ *   perm (n_pad) int32: source row of packed row i, -1 = padding (contributes exactly 0);
+ *   tile_cluster (n_pad / 128) int32: cluster of each 128-row tile.
+ * Limits: D <= 64, D % 4 == 0.  workspace: dic_pairwise_workspace_bytes(n_pad, D). */
+int dic_cluster_rowsums(const float* X, const int32_t* perm, const int32_t* tile_cluster,
+                        double* rowsum, void* workspace, int64_t n_pad, int D, int K,
+                        dic_stream_t stream);
+
 /* ---- utilities -------------------------------------------------------------------- */
 /* Deterministic column sums of a (rows, cols) float32 matrix into float64. */
 size_t dic_colsum_workspace_bytes(int cols);

@@ -158,3 +158,36 @@ def test_tensor_core_pairwise_matches_exact(n, D):
         X64 = X.astype(np.float64)
         ref = np.sqrt(np.maximum(((X64[:, None, :] - X64[None]) ** 2).sum(2), 0)).sum()
         record(f"pairwise_exact_n{n}_D{D}", exact, ref, 1e-10, 0)
+
+
+@pytest.mark.parametrize("n,D,K", [(5000, 64, 5), (3001, 20, 7), (20000, 32, 3)])
+def test_silhouette_tensor_core_matches_float64(n, D, K):
+    """dic_cluster_rowsums (tcgen05 row sums by cluster) vs the chunked float64 distance path and sklearn:
+    ragged cluster sizes, a singleton cluster, D < 64."""
+    from deep_interpolation_clustering_b200 import synth
+    from deep_interpolation_clustering_b200.internal_eval import Sihouette
+    X = synth.make_blobs(n, D, K, seed=n + D)
+    rng = np.random.RandomState(n)
+    labels = rng.randint(0, K, size=n)
+    labels[:n // 2] = np.argmin(((X[:n // 2, None, :] - X[None, :K, :]) ** 2).sum(2), axis=1)   # some structure
+    labels[labels == K - 1] = 0
+    labels[7] = K - 1                                                                          # singleton cluster
+    Xd = torch.from_numpy(X).cuda()
+    native = Sihouette(native=True)(Xd, labels)
+    chunked = Sihouette(native=False)(Xd, labels)
+    record(f"silhouette_tc_n{n}_D{D}_K{K}", native, chunked, 1e-5, 1e-7)
+    # the (N, K) sums themselves
+    inv = torch.from_numpy(np.unique(labels, return_inverse=True)[1]).cuda()
+    Kp = int(inv.max()) + 1
+    sums = Sihouette.rowsums_native(Xd, inv, Kp).cpu().numpy()
+    rows = rng.choice(n, size=64, replace=False)
+    X64 = X.astype(np.float64)
+    inv_h = inv.cpu().numpy()
+    ref = np.zeros((64, Kp))
+    for a, i in enumerate(rows):
+        d = np.sqrt(((X64[i] - X64) ** 2).sum(1))
+        ref[a] = np.bincount(inv_h, weights=d, minlength=Kp)
+    record(f"cluster_rowsums_n{n}_D{D}_K{K}", sums[rows], ref, 1e-5, 1e-6)     # float32-grade sums (3xTF32, sqrt.approx)
+    if n <= 5000:
+        from sklearn.metrics import silhouette_score
+        record(f"silhouette_vs_sklearn_n{n}", native, float(silhouette_score(X, labels)), 1e-5, 1e-6)
