@@ -162,8 +162,13 @@ extern "C" size_t dic_colsum_workspace_bytes(int cols) {
 
 extern "C" int dic_colsum_f32(const float* a, double* out, void* workspace, int64_t rows, int cols,
                               dic_stream_t stream) {
-  DIC_REQUIRE(a && out && workspace, DIC_ERR_INVALID_ARGUMENT, "null pointer argument");
+  DIC_REQUIRE((a || rows == 0) && out && workspace, DIC_ERR_INVALID_ARGUMENT, "null pointer argument");
   DIC_REQUIRE(rows >= 0, DIC_ERR_INVALID_ARGUMENT, "rows < 0");
+  if (rows == 0) {
+    DIC_REQUIRE(cols > 0, DIC_ERR_INVALID_ARGUMENT, "cols <= 0");
+    DIC_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * cols, as_stream(stream)));
+    return DIC_OK;
+  }
   return colsum_f32_launch(a, out, nullptr, nullptr, static_cast<double*>(workspace), rows, cols,
                            as_stream(stream));
 }

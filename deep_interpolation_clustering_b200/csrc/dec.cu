@@ -312,7 +312,7 @@ int g_sm_count() {
 constexpr int kDecMaxBlocks = 148 * 8;
 
 int check(const void* z, const void* mu, int64_t B, int D, int K, float alpha) {
-  DIC_REQUIRE(z && mu, DIC_ERR_INVALID_ARGUMENT, "null pointer argument");
+  DIC_REQUIRE((z || B == 0) && mu, DIC_ERR_INVALID_ARGUMENT, "null pointer argument");   // empty batch: z may be NULL
   DIC_REQUIRE(B >= 0 && D > 0 && K > 0, DIC_ERR_INVALID_ARGUMENT, "bad sizes B=%lld D=%d K=%d", (long long)B, D, K);
   DIC_REQUIRE(alpha > 0.f, DIC_ERR_INVALID_ARGUMENT, "alpha must be positive (got %g)", (double)alpha);
   DIC_REQUIRE(K <= 32, DIC_ERR_UNSUPPORTED, "cluster_number <= 32 supported (got %d)", K);
@@ -415,7 +415,7 @@ extern "C" int dic_dec_q_fwd(const float* z, const float* mu, float* q, int32_t*
                              void* workspace, int64_t B, int D, int K, float alpha, dic_stream_t stream) {
   int rc = check(z, mu, B, D, K, alpha);
   if (rc) return rc;
-  DIC_REQUIRE(q, DIC_ERR_INVALID_ARGUMENT, "null output pointer");
+  DIC_REQUIRE(q || B == 0, DIC_ERR_INVALID_ARGUMENT, "null output pointer");
   DIC_REQUIRE(!colsum || workspace, DIC_ERR_INVALID_ARGUMENT, "colsum requested without a workspace");
   cudaStream_t st = as_stream(stream);
   if (B == 0) {
@@ -447,7 +447,7 @@ extern "C" int dic_dec_q_fwd(const float* z, const float* mu, float* q, int32_t*
 
 extern "C" int dic_dec_p(const float* q, const double* colsum, float* p, int64_t B, int K,
                          dic_stream_t stream) {
-  DIC_REQUIRE(q && colsum && p, DIC_ERR_INVALID_ARGUMENT, "null pointer argument");
+  DIC_REQUIRE(((q && p) || B == 0) && colsum, DIC_ERR_INVALID_ARGUMENT, "null pointer argument");
   DIC_REQUIRE(B >= 0 && K > 0, DIC_ERR_INVALID_ARGUMENT, "bad sizes B=%lld K=%d", (long long)B, K);
   DIC_REQUIRE(K <= 64, DIC_ERR_UNSUPPORTED, "cluster_number <= 64 supported (got %d)", K);
   if (B == 0) return DIC_OK;
@@ -461,7 +461,7 @@ extern "C" int dic_dec_q_bwd(const float* z, const float* mu, const float* grad_
                              dic_stream_t stream) {
   int rc = check(z, mu, B, D, K, alpha);
   if (rc) return rc;
-  DIC_REQUIRE(grad_q && grad_mu && workspace, DIC_ERR_INVALID_ARGUMENT, "null pointer argument");
+  DIC_REQUIRE((grad_q || B == 0) && grad_mu && workspace, DIC_ERR_INVALID_ARGUMENT, "null pointer argument");
   DIC_REQUIRE(!grad_z || aligned16(grad_z), DIC_ERR_INVALID_ARGUMENT, "grad_z must be 16-byte aligned");
   cudaStream_t st = as_stream(stream);
   if (B == 0) {

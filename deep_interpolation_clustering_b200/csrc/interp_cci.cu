@@ -474,7 +474,7 @@ cci_bwd_warp_kernel(const float* __restrict__ u, const float* __restrict__ kerne
 }
 
 int check(const void* u, const void* kernel, int64_t B, int C, int R) {
-  DIC_REQUIRE(u && kernel, DIC_ERR_INVALID_ARGUMENT, "null pointer argument");
+  DIC_REQUIRE((u || B == 0) && kernel, DIC_ERR_INVALID_ARGUMENT, "null pointer argument");
   DIC_REQUIRE(B >= 0 && C > 0 && R > 0, DIC_ERR_INVALID_ARGUMENT, "bad sizes B=%lld C=%d R=%d",
               (long long)B, C, R);
   DIC_REQUIRE(C <= 16, DIC_ERR_UNSUPPORTED, "CrossChannelInterp supports d_dim <= 16 (got %d)", C);
@@ -491,7 +491,7 @@ extern "C" int dic_cci_fwd(const float* u, const float* kernel, float* out, int6
                            dic_stream_t stream) {
   int rc = check(u, kernel, B, C, R);
   if (rc) return rc;
-  DIC_REQUIRE(out, DIC_ERR_INVALID_ARGUMENT, "null output pointer");
+  DIC_REQUIRE(out || B == 0, DIC_ERR_INVALID_ARGUMENT, "null output pointer");
   if (B == 0) return DIC_OK;
   cudaStream_t st = as_stream(stream);
   if (C <= 8) {
@@ -521,7 +521,7 @@ extern "C" int dic_cci_bwd(const float* u, const float* kernel, const float* gra
                            dic_stream_t stream) {
   int rc = check(u, kernel, B, C, R);
   if (rc) return rc;
-  DIC_REQUIRE(grad_out && grad_u && d_kernel && workspace, DIC_ERR_INVALID_ARGUMENT,
+  DIC_REQUIRE(((grad_out && grad_u && workspace) || B == 0) && d_kernel, DIC_ERR_INVALID_ARGUMENT,
               "null pointer argument");
   cudaStream_t st = as_stream(stream);
   if (B == 0) {

@@ -313,7 +313,7 @@ __global__ void sigmoid_vec_kernel(const float* __restrict__ kernel, float* __re
 
 int check(const void* v, const void* x, const void* kernel, const void* ref_t, int64_t B, int C,
           int T, int R, int64_t& x_stride) {
-  DIC_REQUIRE(v && x && kernel && ref_t, DIC_ERR_INVALID_ARGUMENT, "null pointer argument");
+  DIC_REQUIRE(((v && x) || B == 0) && kernel && ref_t, DIC_ERR_INVALID_ARGUMENT, "null pointer argument");
   if (x_stride == 0) x_stride = (int64_t)4 * C * T;
   DIC_REQUIRE(x_stride >= (int64_t)3 * C * T, DIC_ERR_INVALID_ARGUMENT,
               "x_stride=%lld is smaller than the 3*C*T live planes of an encounter", (long long)x_stride);
@@ -333,7 +333,7 @@ extern "C" int dic_rbf_fwd(const float* v, const float* x, const float* kernel, 
                            int64_t x_stride, dic_stream_t stream) {
   int rc = check(v, x, kernel, ref_t, B, C, T, R, x_stride);
   if (rc) return rc;
-  DIC_REQUIRE(rec, DIC_ERR_INVALID_ARGUMENT, "null output pointer");
+  DIC_REQUIRE(rec || B == 0, DIC_ERR_INVALID_ARGUMENT, "null output pointer");
   if (B == 0) return DIC_OK;
   const int Rp = round_up(R, 2);
   const size_t smem = sizeof(float2) * (size_t)C * Rp + sizeof(float) * (3 * (size_t)C + 1);
@@ -353,7 +353,7 @@ extern "C" int dic_rbf_bwd(const float* v, const float* x, const float* kernel, 
                            int R, int64_t x_stride, dic_stream_t stream) {
   int rc = check(v, x, kernel, ref_t, B, C, T, R, x_stride);
   if (rc) return rc;
-  DIC_REQUIRE(rec && inv_norm && grad_rec && grad_v && d_kernel && workspace,
+  DIC_REQUIRE(((rec && inv_norm && grad_rec && grad_v && workspace) || B == 0) && d_kernel,
               DIC_ERR_INVALID_ARGUMENT, "null pointer argument");
   cudaStream_t st = as_stream(stream);
   if (B == 0) {

@@ -19,8 +19,8 @@
 //     with (d*-r)^2 = hi + lo carried as an exact two-float: the difference of squares is
 //     rounded once, so the high-pass weight e^10 stays ~30x closer to the float64 truth than the
 //     reference's own float32 evaluation (which subtracts numbers in the hundreds);
-//   * ONE MUFU.EX2 per (t, r): the high-pass weight is e^10 (4 FMULs) because both filters
-//     share the shift;
+//   * both filters share the shift, so the high-pass exponent is 10x the low-pass one: one MUFU.EX2 per
+//     (t, r) in the outer window, a second one (2^(10 arg)) only inside the narrow high-pass window;
 //   * sliding windows: a Gaussian weight below 2^-kCut of the largest one is dropped, so a lane
 //     only walks the observations within +-sqrt(nmin + kCut/a) hours of its grid points, and
 //     only the inner +-sqrt(nmin + kCut/(10a)) feeds the high-pass sums (make_window);
@@ -153,11 +153,14 @@ __device__ __forceinline__ void sci_fwd_task(const float* __restrict__ sx, const
       for (int k = 0; k < RPT; ++k) {
         const float dl = dd[j] - rr[k];
         // -a ((d-r)^2 - (d*-r)^2) <= 0: the difference of squares is rounded once, the residual rides in the FMA
-        const float e = ex2_approx(fmaf(fmaf(dl, dl, -nhi[k]), na, nlo[k]));
+        const float arg = fmaf(fmaf(dl, dl, -nhi[k]), na, nlo[k]);
+        const float e = ex2_approx(arg);
         s1[k] = WEIGHTED ? fmaf(mm[j], e, s1[k]) : s1[k] + e;
         sy[k] = fmaf(xx[j], e, sy[k]);
         if (inner) {
-          const float e2 = e * e, e4 = e2 * e2, e8 = e4 * e4, e10 = e8 * e2;
+          // high-pass weight e^10 = 2^(10 arg): a second MUFU (the XU pipe has the headroom) costs two issue
+          // slots where four squarings cost four, and does not multiply the MUFU's rounding error by ten
+          const float e10 = ex2_approx(10.f * arg);
           s10[k] = WEIGHTED ? fmaf(mm[j], e10, s10[k]) : s10[k] + e10;
           sy10[k] = fmaf(xx[j], e10, sy10[k]);
         }
@@ -294,10 +297,11 @@ __device__ __forceinline__ float sci_bwd_task(const float* __restrict__ sx, cons
 #pragma unroll
       for (int k = 0; k < RPT; ++k) {
         const float dl = dd[j] - rr[k];
-        const float e = ex2_approx(fmaf(fmaf(dl, dl, -nhi[k]), na, nlo[k]));
+        const float arg = fmaf(fmaf(dl, dl, -nhi[k]), na, nlo[k]);
+        const float e = ex2_approx(arg);
         float h = e * fmaf(xx[j] - yy[k], A[k], Bc[k]);
         if (inner) {
-          const float e2 = e * e, e4 = e2 * e2, e8 = e4 * e4, e10 = e8 * e2;
+          const float e10 = ex2_approx(10.f * arg);
           h = fmaf(e10, (xx[j] - yy10[k]) * A10[k], h);
         }
         if (WEIGHTED) h *= mm[j];
@@ -387,7 +391,8 @@ int prepare(K kern, size_t smem) {
 
 int check_common(const void* x, const void* kernel, const void* ref_t, int64_t B, int C, int T, int R,
                  int64_t& x_stride) {
-  DIC_REQUIRE(x && kernel && ref_t, DIC_ERR_INVALID_ARGUMENT, "null pointer argument");
+  // per-batch buffers of an EMPTY batch may be NULL (torch hands out data_ptr() == 0 for empty tensors)
+  DIC_REQUIRE((x || B == 0) && kernel && ref_t, DIC_ERR_INVALID_ARGUMENT, "null pointer argument");
   if (x_stride == 0) x_stride = (int64_t)4 * C * T;
   DIC_REQUIRE(x_stride >= (int64_t)3 * C * T, DIC_ERR_INVALID_ARGUMENT,
               "x_stride=%lld is smaller than the 3*C*T live planes of an encounter", (long long)x_stride);
@@ -411,7 +416,7 @@ extern "C" int dic_sci_fwd(const float* x, const float* kernel, const float* ref
                            dic_stream_t stream) {
   int rc = check_common(x, kernel, ref_t, B, C, T, R, x_stride);
   if (rc) return rc;
-  DIC_REQUIRE(u, DIC_ERR_INVALID_ARGUMENT, "null output pointer");
+  DIC_REQUIRE(u || B == 0, DIC_ERR_INVALID_ARGUMENT, "null output pointer");
   if (B == 0) return DIC_OK;
   const int Tp = round_up(T, 4);
   const size_t smem = sci_smem_bytes(C, Tp, R);
@@ -445,7 +450,7 @@ extern "C" int dic_sci_bwd(const float* x, const float* kernel, const float* ref
                            dic_stream_t stream) {
   int rc = check_common(x, kernel, ref_t, B, C, T, R, x_stride);
   if (rc) return rc;
-  DIC_REQUIRE(u && stats && grad_u && d_kernel && workspace, DIC_ERR_INVALID_ARGUMENT,
+  DIC_REQUIRE(((u && stats && grad_u && workspace) || B == 0) && d_kernel, DIC_ERR_INVALID_ARGUMENT,
               "null pointer argument");
   cudaStream_t st = as_stream(stream);
   if (B == 0) {

@@ -97,3 +97,17 @@ def test_errors():
         ca(torch.zeros(8, 32, device=dev))               # embedding dimension mismatch
     with pytest.raises(RuntimeError):
         ca(torch.zeros(8, 64))                            # CPU tensor
+
+
+def test_empty_batch():
+    """B = 0: empty q / p, zero centre gradients, no launch."""
+    import deep_interpolation_clustering_b200 as dic
+    dev = torch.device("cuda:0")
+    ca = dic.ClusterAssignment(4, 32, 1.0).to(dev)
+    z = torch.zeros((0, 32), device=dev, requires_grad=True)
+    q = ca(z)
+    assert q.shape == (0, 4)
+    p = dic.target_distribution(q)
+    assert p.shape == (0, 4)
+    q.sum().backward()
+    assert float(ca.cluster_centers.grad.abs().sum()) == 0.0

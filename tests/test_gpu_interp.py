@@ -257,3 +257,44 @@ def test_three_plane_input_is_bit_identical(golden, case):
         for a, b in zip(results[0], other):
             assert torch.equal(a, b) or (torch.isnan(a) == torch.isnan(b)).all() and torch.equal(
                 torch.nan_to_num(a), torch.nan_to_num(b))
+
+
+def test_empty_batch_and_extreme_observation_counts():
+    """Edge cases: B = 0 (empty outputs, zero parameter gradients), one observation per vital
+    (the softmax collapses onto it: y = y' = x_0 everywhere), every slot observed (n = T),
+    a duplicated timestamp."""
+    import deep_interpolation_clustering_b200 as dic
+    from deep_interpolation_clustering_b200 import synth
+    from oracle import interp_oracle
+    dev = torch.device("cuda:0")
+    C, T, R, H = 6, 32, 24, 24.0
+    sci = dic.SingleChannelInterp(R, H, C, T, dev)
+    cci = dic.CrossChannelInterp(C, T, dev)
+    rbf = dic.RBF(H, R, C, C, 0.0, dic.basis_func_dict()["gaussian"], dev)
+    rbf.compress_fc = torch.nn.Identity()
+    # B = 0
+    x0 = torch.zeros((0, 4 * C, T), device=dev)
+    v0 = torch.zeros((0, C, R), device=dev, requires_grad=True)
+    out0, rec0 = cci(sci(x0)), rbf(v0, x0)
+    assert out0.shape == (0, R, 3 * C) and rec0.shape == (0, C, T)
+    (out0.sum() + rec0.sum()).backward()
+    for prm in (sci.kernel, cci.kernel, rbf.kernel):
+        assert prm.grad is not None and float(prm.grad.abs().sum()) == 0.0
+    # n_obs = 1 and n_obs = T, against the float64 oracle
+    p = synth.make_interp_params(C, seed=1)
+    rt = interp_oracle.linspace_grid(H, R)
+    for tag, xn in (("one_obs", synth.make_encounters(8, C, T, H, seed=21)),
+                    ("all_obs", synth.make_encounters(8, C, T, H, seed=22, min_obs=T))):
+        if tag == "one_obs":
+            xn[:, C:2 * C, 1:] = 0.0
+            xn[:, :C, 1:] = 0.0
+            xn[:, 2 * C:3 * C, 1:] = 0.0
+        else:
+            xn[:, 2 * C:3 * C, 5] = xn[:, 2 * C:3 * C, 4]          # duplicated timestamp
+        sci.kernel.data = torch.tensor(p["sci_kernel"], device=dev)
+        s64 = interp_oracle.sci_forward(xn.astype(np.float64), p["sci_kernel"].astype(np.float64), rt, C)
+        got = sci(torch.tensor(xn, device=dev))
+        _check_groups(f"edge_{tag}/sci", got, s64, C)
+        if tag == "one_obs":
+            y = got[:, :, :C].detach().cpu().numpy()
+            assert np.array_equal(y, np.broadcast_to(xn[:, None, :C, 0], y.shape))
