@@ -7,11 +7,13 @@ X32 = torch.from_numpy(synth.make_blobs(1_000_000, 64, 5, seed=4)).cuda()
 out = {}
 for name, X in (("f32", X32), ("f64", X32.double())):
     for K in (2, 4, 8, 10, 16):
-        for kern in ("rw", "tile"):
+        for kern in ("tile2", "rw", "tile"):
+            os.environ.pop("DIC_KMEANS_NO_RW", None)
+            os.environ.pop("DIC_KMEANS_NO_TILE2", None)
+            if kern != "tile2":
+                os.environ["DIC_KMEANS_NO_TILE2"] = "1"
             if kern == "tile":
                 os.environ["DIC_KMEANS_NO_RW"] = "1"
-            else:
-                os.environ.pop("DIC_KMEANS_NO_RW", None)
             st = _Device(X, K)
             cen = X[:K].clone().contiguous()
             st.assign(cen, 0)

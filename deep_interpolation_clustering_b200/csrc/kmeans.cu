@@ -634,6 +634,188 @@ pairwise_sum_kernel(const T* __restrict__ X, double* __restrict__ ws, int64_t n,
   }
 }
 
+// ---- specialised tile kernel: rows of exactly S16 sixteen-byte vectors, K <= 16 --------------------------
+// Same structure as kmeans_assign_fast_kernel (128-row tiles, thread = row for the E-step) with everything
+// the compiler needs to unroll known at compile time, and a branch-free M-step:
+//   * rows arrive by per-row 1-D TMA bulk copies into an odd-stride tile (conflict-free 128-bit reads);
+//   * E-step: the row sits in registers (float32) and 4 centres at a time are read as shared-memory
+//     broadcasts: K*D FMAs + K*S16 broadcast loads per row, nothing else in the loop;
+//   * M-step: thread = (row group g, vector column): x += into sacc[g][label][column] in SHARED memory - the
+//     label is an address, not a branch (the register-resident sums of the older kernel cost a 16-way switch
+//     per row); each thread owns its slots, so there are no atomics and the order is fixed (deterministic);
+//   * previous labels are fetched before the tile wait, inertia / distance sums only without NO_INERTIA.
+// Instruction budget at K = 10, float32, D = 64: ~32 issue slots per row (the older kernel: 76).
+constexpr int kT2Rows = 128;
+
+template <typename T, int S16>
+__global__ void __launch_bounds__(kT2Rows)
+kmeans_assign_tile2_kernel(const T* __restrict__ X, const T* __restrict__ centers, int32_t* __restrict__ labels,
+                           double* __restrict__ ws, int64_t N, int K, int flags, int want_sums) {
+  using V = typename Vec16<T>::type;
+  constexpr int PER = Vec16<T>::n;
+  constexpr int D = S16 * PER;
+  constexpr int RS = S16 + 1;                 // odd row stride (in vectors)
+  constexpr int G = kT2Rows / S16;            // row groups of the M-step
+  constexpr bool XREG = sizeof(T) == 4 && S16 <= 16;     // keep the row in registers during the E-step
+  extern __shared__ __align__(16) unsigned char smem[];
+  V* sx = reinterpret_cast<V*>(smem);                         // [128][RS]
+  V* sc = sx + kT2Rows * RS;                                  // [K][S16]
+  V* sacc = sc + K * S16;                                     // [G][K][S16]
+  T* scn = reinterpret_cast<T*>(sacc + (want_sums ? G * K * S16 : 0));   // [16]
+  int* scnt = reinterpret_cast<int*>(scn + 16);               // [G][16]
+  int* slab = scnt + G * 16;                                  // [128]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(slab + kT2Rows);
+  const int tid = threadIdx.x;
+
+  for (int i = tid; i < K * D; i += kT2Rows) reinterpret_cast<T*>(sc)[i] = centers[i];
+  if (want_sums)
+    for (int i = tid; i < G * K * D; i += kT2Rows) reinterpret_cast<T*>(sacc)[i] = T(0);
+  for (int i = tid; i < G * 16; i += kT2Rows) scnt[i] = 0;
+  for (int i = tid; i < kT2Rows * RS * PER; i += kT2Rows) reinterpret_cast<T*>(sx)[i] = T(0);
+  if (tid == 0) mbar_init(bar, 1);
+  __syncthreads();
+  fence_proxy_async();
+  if (tid < 16) {
+    T sum = T(0);
+    if (tid < K)
+      for (int d = 0; d < D; ++d) {
+        const T c = reinterpret_cast<T*>(sc)[tid * D + d];
+        sum += c * c;
+      }
+    scn[tid] = sum;
+  }
+  __syncthreads();
+
+  const bool keep = (flags & DIC_KM_KEEP_LABELS) != 0;
+  const bool count_changes = (flags & DIC_KM_COUNT_CHANGES) != 0;
+  const bool want_d2 = (flags & DIC_KM_NO_INERTIA) == 0;
+  const int g = tid / S16, col = tid - g * S16;
+  const int64_t ntiles = (N + kT2Rows - 1) / kT2Rows;
+  constexpr uint32_t row_bytes = (uint32_t)(D * sizeof(T));
+  double inertia = 0.0, dist_sum = 0.0;
+  int changed = 0, iter = 0;
+
+  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++iter) {
+    const int64_t row0 = t * kT2Rows;
+    const int rows = (int)min((int64_t)kT2Rows, N - row0);
+    if (tid == 0) mbar_expect_tx(bar, (uint32_t)rows * row_bytes);
+    __syncthreads();                          // expect_tx is armed; the previous M-step is done with sx / slab
+    if (tid < rows) bulk_g2s(sx + tid * RS, X + (row0 + tid) * D, row_bytes, bar);
+    int oldl = 0;
+    if ((keep || count_changes) && tid < rows) oldl = labels[row0 + tid];
+    mbar_wait(bar, (uint32_t)(iter & 1));
+
+    if (tid < rows) {
+      const V* xr = sx + tid * RS;
+      V xreg[XREG ? S16 : 1];
+      if (XREG) {
+#pragma unroll
+        for (int j = 0; j < S16; ++j) xreg[j] = xr[j];
+      }
+      int best = oldl;
+      if (!keep) {
+        T bestd = T(0);
+        best = 0;
+        for (int kb = 0; kb < K; kb += 4) {
+          const V* c0 = sc + min(kb + 0, K - 1) * S16;
+          const V* c1 = sc + min(kb + 1, K - 1) * S16;
+          const V* c2 = sc + min(kb + 2, K - 1) * S16;
+          const V* c3 = sc + min(kb + 3, K - 1) * S16;
+          T a0 = T(0), a1 = T(0), a2 = T(0), a3 = T(0);
+#pragma unroll
+          for (int j = 0; j < S16; ++j) {
+            const V xv = XREG ? xreg[j] : xr[j];
+            a0 = dot16(xv, c0[j], a0);
+            a1 = dot16(xv, c1[j], a1);
+            a2 = dot16(xv, c2[j], a2);
+            a3 = dot16(xv, c3[j], a3);
+          }
+          const T av[4] = {a0, a1, a2, a3};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int k = kb + i;
+            if (k < K) {
+              const T dk = scn[k] - T(2) * av[i];       // ||c||^2 - 2 x.c  (||x||^2 omitted)
+              if (k == 0 || dk < bestd) {               // strict '<': lowest index wins ties
+                bestd = dk;
+                best = k;
+              }
+            }
+          }
+        }
+        if (count_changes) changed += (oldl != best);
+        labels[row0 + tid] = best;
+      }
+      if (want_d2) {                          // direct squared distance to the chosen centre
+        const V* cb = sc + best * S16;
+        T d2 = T(0);
+#pragma unroll
+        for (int j = 0; j < S16; ++j) d2 = sqd16(XREG ? xreg[j] : xr[j], cb[j], d2);
+        inertia += (double)d2;
+        dist_sum += sqrt((double)d2);
+      }
+      slab[tid] = best;
+    }
+    if (want_sums) {
+      __syncthreads();
+      for (int r = g; r < rows; r += G) {
+        const int lab = slab[r];
+        const V xv = sx[r * RS + col];
+        V* dst = sacc + (g * K + lab) * S16 + col;
+        V a = *dst;
+        if constexpr (sizeof(T) == 4) {
+          a.x += xv.x; a.y += xv.y; a.z += xv.z; a.w += xv.w;
+        } else {
+          a.x += xv.x; a.y += xv.y;
+        }
+        *dst = a;
+        if (col == 0) scnt[g * 16 + lab] += 1;
+      }
+    }
+  }
+  __syncthreads();
+
+  // per-block partials: [K*D] sums | [K] counts | inertia | changed | dist_sum | 0
+  double* out = ws + (int64_t)blockIdx.x * ((int64_t)K * D + K + 4);
+  if (want_sums) {
+    for (int i = tid; i < K * D; i += kT2Rows) {
+      double sum = 0.0;
+      for (int gg = 0; gg < G; ++gg) sum += (double)reinterpret_cast<const T*>(sacc)[gg * K * D + i];
+      out[i] = sum;
+    }
+    for (int i = tid; i < K; i += kT2Rows) {
+      int c = 0;
+      for (int gg = 0; gg < G; ++gg) c += scnt[gg * 16 + i];
+      out[(int64_t)K * D + i] = (double)c;
+    }
+  }
+  __syncthreads();
+  double* red = reinterpret_cast<double*>(sx);
+  inertia = warp_sum(inertia);
+  dist_sum = warp_sum(dist_sum);
+  const double ch = warp_sum((double)changed);
+  const int warp = tid >> 5, lane = tid & 31;
+  if (lane == 0) {
+    red[warp * 3 + 0] = inertia;
+    red[warp * 3 + 1] = ch;
+    red[warp * 3 + 2] = dist_sum;
+  }
+  __syncthreads();
+  if (tid < 3) {
+    double sum = 0.0;
+    for (int w = 0; w < kT2Rows / 32; ++w) sum += red[w * 3 + tid];
+    out[(int64_t)K * D + K + tid] = sum;
+  }
+  if (tid == 3) out[(int64_t)K * D + K + 3] = 0.0;
+}
+
+template <typename T>
+size_t tile2_smem_bytes(int K, int S16, bool want_sums) {
+  const size_t G = kT2Rows / S16;
+  return 16 * ((size_t)kT2Rows * (S16 + 1) + (size_t)K * S16 + (want_sums ? G * K * S16 : 0)) + 16 * sizeof(T) +
+         sizeof(int) * (G * 16 + kT2Rows) + 16;
+}
+
 // ---- row-per-half-warp Lloyd pass ------------------------------------------------------------------
 // The streaming form of the E-step + accumulation: NO staging of X in shared memory.  Sixteen lanes own
 // one row (lane l holds elements [l*E, l*E+E) as 16-byte vectors), so one warp-wide 128-bit load covers
@@ -878,6 +1060,43 @@ int km_blocks(int K, int D) {
 template <typename T>
 int launch_assign(const void* X, const void* centers, int32_t* labels, double* sums, double* counts,
                   double* stats, void* workspace, int64_t N, int D, int K, int flags, cudaStream_t st) {
+  // specialised tile kernel: rows of exactly 16 or 32 sixteen-byte vectors (D = 64 / 128 float32, 32 / 64 float64)
+  {
+    constexpr int PER = 16 / (int)sizeof(T);
+    const int s16x = D / PER;
+    const bool shape_ok = D % PER == 0 && (s16x == 16 || s16x == 32) && K <= 16 && aligned16(X);
+    const bool no_t2 = getenv("DIC_KMEANS_NO_TILE2") != nullptr;     // debug: force the older kernels
+    const size_t smem = shape_ok ? tile2_smem_bytes<T>(K, s16x, sums != nullptr) : 0;
+    if (shape_ok && !no_t2 && smem <= 110 * 1024) {
+      int dev = 0, sms = 148;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      int per_sm = (int)((size_t)220 * 1024 / (smem + 1024));
+      per_sm = per_sm > 6 ? 6 : (per_sm < 1 ? 1 : per_sm);
+      int nb = sms * per_sm;
+      const int cap = km_blocks(K, D);
+      if (nb > cap) nb = cap;
+      const int64_t nt = (N + kT2Rows - 1) / kT2Rows;
+      if (nt < nb) nb = (int)nt;
+      if (nb < 1) nb = 1;
+      double* wsd = static_cast<double*>(workspace);
+#define DIC_T2_LAUNCH(S16_)                                                                                   \
+  {                                                                                                           \
+    auto kf = kmeans_assign_tile2_kernel<T, S16_>;                                                            \
+    if (smem > 48 * 1024)                                                                                     \
+      DIC_CUDA(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));             \
+    kf<<<nb, kT2Rows, smem, st>>>(static_cast<const T*>(X), static_cast<const T*>(centers), labels, wsd, N, K, \
+                                  flags, sums != nullptr);                                                    \
+  }
+      if (s16x == 16) DIC_T2_LAUNCH(16) else DIC_T2_LAUNCH(32)
+#undef DIC_T2_LAUNCH
+      DIC_LAUNCH_CHECK("kmeans_assign_tile2_kernel");
+      const int nn = K * D + K + 4;
+      kmeans_finish_kernel<<<(nn + 7) / 8, 256, 0, st>>>(wsd, sums, counts, stats, nb, K, D);
+      DIC_LAUNCH_CHECK("kmeans_finish_kernel");
+      return DIC_OK;
+    }
+  }
   // streaming row-per-half-warp kernel: K <= 16, rows of whole 16-byte vectors, <= 16 elements per lane
   {
     constexpr int PER = 16 / (int)sizeof(T);
