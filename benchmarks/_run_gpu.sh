@@ -1,2 +1,3 @@
 mkdir -p gpurun_out
-timeout 120 python benchmarks/_km_prof2.py > gpurun_out/kmplain.log 2>&1 && timeout 300 ncu --set full --clock-control none --import-source on -k regex:"kmeans_assign_tile2" -s 2 -c 4 -o gpurun_out/prof_km4 python benchmarks/_km_prof2.py > gpurun_out/ncu_km4.log 2>&1
+timeout 120 python benchmarks/_km_prof.py > gpurun_out/kmplain.log 2>&1
+timeout 200 python -m pytest tests/test_gpu_kmeans.py -m gpu -x -q --timeout 100 -k "lloyd or plusplus or reloc or gap" > gpurun_out/pytest_km.log 2>&1; echo "exit $?" >> gpurun_out/pytest_km.log

@@ -1043,6 +1043,120 @@ kmeans_assign_rw_kernel(const T* __restrict__ X, const T* __restrict__ centers, 
   if (tid == 3) out[(int64_t)K * D + K + 3] = 0.0;
 }
 
+// k-means++ potentials, streaming form (same row layout as kmeans_assign_rw_kernel): 16 lanes own a row, the
+// L candidate distances are reduced with the transposed butterfly, lane hl ends up owning candidate
+// hl >> (4 - log2 LP) and accumulates its potential in float64.  One read of X (+ min_d2), no staging.
+template <typename T, int E, int LP>
+__global__ void __launch_bounds__(kRwThreads)
+kmeans_min_d2_rw_kernel(const T* __restrict__ X, const T* __restrict__ cands, const T* __restrict__ min_d2,
+                        T* __restrict__ min_d2_out, double* __restrict__ ws, int64_t N, int D, int L) {
+  using V = typename RwVec<T>::type;
+  constexpr int PER = RwVec<T>::n;
+  constexpr int NV = E / PER;
+  constexpr int DP = 16 * E;
+  constexpr int LOGLP = LP == 16 ? 4 : (LP == 4 ? 2 : 0);
+  extern __shared__ __align__(16) unsigned char smem[];
+  T* sc = reinterpret_cast<T*>(smem);                       // [L][DP] candidates, zero beyond D
+  __shared__ double red[kRwThreads / 32][16];
+  const int tid = threadIdx.x, lane = tid & 31, hl = lane & 15, half = lane >> 4;
+  for (int i = tid; i < L * DP; i += kRwThreads) {
+    const int l = i / DP, d = i - l * DP;
+    sc[i] = d < D ? cands[(int64_t)l * D + d] : T(0);
+  }
+  __syncthreads();
+  const int l_own = hl >> (4 - LOGLP);
+  const bool owner = (hl & ((16 >> LOGLP) - 1)) == 0 && l_own < L;    // one lane per (row, candidate)
+  const bool lane_live = hl * E < D;
+  const V* scv = reinterpret_cast<const V*>(sc) + hl * NV;
+  double pot = 0.0;
+  const int64_t warps_total = (int64_t)gridDim.x * (kRwThreads / 32);
+  const int64_t warp_g = (int64_t)blockIdx.x * (kRwThreads / 32) + (tid >> 5);
+  const int64_t npairs = (N + 1) / 2;
+  for (int64_t pair0 = warp_g; pair0 < npairs; pair0 += warps_total * kRwUnroll) {
+    V xv[kRwUnroll][NV];
+    T prev[kRwUnroll];
+    int64_t rows[kRwUnroll];
+#pragma unroll
+    for (int u = 0; u < kRwUnroll; ++u) {
+      const int64_t pair = pair0 + (int64_t)u * warps_total;
+      rows[u] = 2 * pair + half;
+      const bool row_ok = pair < npairs && rows[u] < N;
+      prev[u] = (min_d2 && row_ok) ? min_d2[rows[u]] : rw_inf(T(0));
+      const V* src = reinterpret_cast<const V*>(X + (row_ok ? rows[u] : 0) * D) + hl * NV;
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        T z[PER];
+#pragma unroll
+        for (int e = 0; e < PER; ++e) z[e] = T(0);
+        xv[u][v] = (row_ok && lane_live && (hl * E + v * PER) < D) ? __ldg(src + v) : rw_pack(z);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kRwUnroll; ++u) {
+      const int64_t pair = pair0 + (int64_t)u * warps_total;
+      if (pair >= npairs) break;                            // warp-uniform
+      T x[E];
+#pragma unroll
+      for (int v = 0; v < NV; ++v) rw_unpack(xv[u][v], x + v * PER);
+      T part[LP];
+#pragma unroll
+      for (int l = 0; l < LP; ++l) {
+        part[l] = T(0);
+        if (l < L) {
+#pragma unroll
+          for (int v = 0; v < NV; ++v) {
+            T c[PER];
+            rw_unpack(scv[l * (DP / PER) + v], c);
+#pragma unroll
+            for (int e = 0; e < PER; ++e) {
+              const T df = x[v * PER + e] - c[e];
+              part[l] += df * df;
+            }
+          }
+        }
+      }
+      int nred = LP;
+#pragma unroll
+      for (int off = 8; off >= 1; off >>= 1) {
+        if (nred > 1) {
+          nred >>= 1;
+          const bool up = (hl & off) != 0;
+#pragma unroll
+          for (int i = 0; i < (LP > 1 ? LP / 2 : 1); ++i) {
+            if (i < nred) {
+              const T send = up ? part[i] : part[i + nred];
+              const T keepv = up ? part[i + nred] : part[i];
+              part[i] = keepv + __shfl_xor_sync(0xffffffffu, send, off);
+            }
+          }
+        } else {
+          part[0] += __shfl_xor_sync(0xffffffffu, part[0], off);
+        }
+      }
+      T v = part[0];
+      if (prev[u] < v) v = prev[u];
+      if (owner && rows[u] < N) {
+        pot += (double)v;
+        if (min_d2_out && l_own == 0) min_d2_out[rows[u]] = v;
+      }
+    }
+  }
+  // lanes that own candidate l: fixed-order sum over the block
+  if (lane < 16) {
+#pragma unroll
+    for (int l = 0; l < 16; ++l) red[tid >> 5][l] = 0.0;
+  }
+  __syncwarp();
+  const double both = pot + __shfl_xor_sync(0xffffffffu, pot, 16);      // the two rows of the warp step
+  if (half == 0 && owner) red[tid >> 5][l_own] = both;
+  __syncthreads();
+  if (tid < L) {
+    double sum = 0.0;
+    for (int w = 0; w < kRwThreads / 32; ++w) sum += red[w][tid];
+    ws[(int64_t)blockIdx.x * L + tid] = sum;
+  }
+}
+
 template <typename T>
 size_t rw_smem_bytes(int K, int E, int KP, bool want_sums) {
   const size_t dp = 16 * (size_t)E;
@@ -1203,6 +1317,38 @@ int launch_assign(const void* X, const void* centers, int32_t* labels, double* s
 template <typename T>
 int launch_min_d2(const void* X, const void* cands, const void* min_d2, void* min_d2_out, double* pots,
                   void* workspace, int64_t N, int D, int L, cudaStream_t st) {
+  {   // streaming half-warp-per-row kernel: rows of whole 16-byte vectors, <= 16 elements per lane
+    constexpr int PER = 16 / (int)sizeof(T);
+    const int e_need = (D + 15) / 16;
+    const int E = e_need <= 4 ? 4 : (e_need <= 8 ? 8 : 16);
+    const bool no_rw = getenv("DIC_KMEANS_NO_RW") != nullptr;
+    if (!no_rw && D <= 256 && D % PER == 0 && aligned16(X) && L <= 16) {
+      const size_t smem_rw = (size_t)L * 16 * E * sizeof(T);
+      int dev = 0, sms = 148;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      int blocks = sms * 4;
+      if (blocks > kPotBlocks) blocks = kPotBlocks;
+      const int64_t want = (N + 2 * (kRwThreads / 32) * kRwUnroll - 1) / (2 * (kRwThreads / 32) * kRwUnroll);
+      if (want < blocks) blocks = (int)want;
+      if (blocks < 1) blocks = 1;
+      double* wsd = static_cast<double*>(workspace);
+      const int LP = L == 1 ? 1 : (L <= 4 ? 4 : 16);
+#define DIC_MD_LAUNCH(E_, LP_)                                                                                 \
+  kmeans_min_d2_rw_kernel<T, E_, LP_><<<blocks, kRwThreads, smem_rw, st>>>(                                    \
+      static_cast<const T*>(X), static_cast<const T*>(cands), static_cast<const T*>(min_d2),                   \
+      static_cast<T*>(min_d2_out), wsd, N, D, L);
+#define DIC_MD_LP(E_)                                                                                          \
+  if (LP == 1) { DIC_MD_LAUNCH(E_, 1) } else if (LP == 4) { DIC_MD_LAUNCH(E_, 4) } else { DIC_MD_LAUNCH(E_, 16) }
+      if (E == 4) { DIC_MD_LP(4) } else if (E == 8) { DIC_MD_LP(8) } else { DIC_MD_LP(16) }
+#undef DIC_MD_LP
+#undef DIC_MD_LAUNCH
+      DIC_LAUNCH_CHECK("kmeans_min_d2_rw_kernel");
+      sum_blocks_kernel<<<(L + 7) / 8, 256, 0, st>>>(wsd, pots, blocks, L);
+      DIC_LAUNCH_CHECK("sum_blocks_kernel");
+      return DIC_OK;
+    }
+  }
   const size_t smem = (size_t)L * D * sizeof(T);
   auto kern = kmeans_min_d2_kernel<T>;
   if (smem > 48 * 1024)

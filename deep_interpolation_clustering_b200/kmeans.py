@@ -208,8 +208,12 @@ class KMeansB200:
         pot = st.min_d2(centers[0:1], None, closest)
         comm.sum_(pot)
         pot = pot[0]
+        # sklearn draws random_state.uniform(size=trials) once per centre; the stream does not depend on the
+        # data, so the (K-1) x trials numbers are drawn here in the same order and uploaded ONCE
+        draws = torch.from_numpy(np.stack([rng.uniform(size=trials) for _ in range(1, K)])
+                                 if K > 1 else np.zeros((0, trials))).to(st.dev)
         for c in range(1, K):
-            rv = torch.from_numpy(rng.uniform(size=trials)).to(st.dev) * pot
+            rv = draws[c - 1] * pot
             cum = torch.cumsum(closest.to(torch.float64), 0)
             if comm.on:      # global cumulative sum = local one + the totals of the lower ranks
                 totals = comm.gather(cum[-1:] if N else cum.new_zeros(1)).flatten()
