@@ -1,3 +1,2 @@
 mkdir -p gpurun_out
-timeout 120 python benchmarks/_km_prof.py > gpurun_out/kmplain.log 2>&1
-timeout 200 python -m pytest tests/test_gpu_kmeans.py -m gpu -x -q --timeout 100 -k "lloyd or plusplus or reloc or gap" > gpurun_out/pytest_km.log 2>&1; echo "exit $?" >> gpurun_out/pytest_km.log
+timeout 300 python -m pytest tests/test_final_labels.py -m gpu -x -q --timeout 100 > gpurun_out/pytest_final.log 2>&1; echo "exit $?" >> gpurun_out/pytest_final.log
