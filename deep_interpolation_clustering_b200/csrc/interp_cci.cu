@@ -264,8 +264,12 @@ cci_bwd_kernel(const float* __restrict__ u, const float* __restrict__ kernel,
 // data path.  HBM-bound: ~1.1k warp instructions per encounter against 20.7 KB of traffic.
 constexpr int kCciWarps = 4;
 
-__device__ __forceinline__ void softmax_c8(const float* __restrict__ wrow /*ub + C*R + r*/, int C, int R,
+// CT > 0: the channel count is a compile-time constant (the reference's 6 vitals): the padded-to-8 loops and
+// their `c < C` predicates fold away (36 instead of 64 MACs per 6x6 product, ...).  CT = 0: runtime C <= 8.
+template <int CT>
+__device__ __forceinline__ void softmax_c8(const float* __restrict__ wrow /*ub + C*R + r*/, int C_rt, int R,
                                            float (&w)[8], float (&what)[8]) {
+  const int C = CT ? CT : C_rt;
   float wmax = -INFINITY;
 #pragma unroll
   for (int c = 0; c < 8; ++c)
@@ -308,10 +312,11 @@ __device__ __forceinline__ const float* warp_tile_load(unsigned char* smem, int 
   return tile;
 }
 
-template <bool TILE>
+template <bool TILE, int CT>
 __global__ void __launch_bounds__(kCciWarps * 32)
 cci_fwd_warp_kernel(const float* __restrict__ u, const float* __restrict__ kernel, float* __restrict__ out,
-                    int64_t B, int C, int R) {
+                    int64_t B, int C_rt, int R) {
+  const int C = CT ? CT : C_rt;
   extern __shared__ __align__(128) unsigned char dyn_smem[];
   __shared__ float sK[64];
   for (int i = threadIdx.x; i < C * C; i += blockDim.x) sK[i] = __ldg(kernel + i);
@@ -336,7 +341,7 @@ cci_fwd_warp_kernel(const float* __restrict__ u, const float* __restrict__ kerne
     if (c < C) ybar[c] = warp_sum(ybar[c]) * invR;
   for (int r = lane; r < R; r += 32) {
     float w[8], a[8];
-    softmax_c8(ub + C * R + r, C, R, w, a);
+    softmax_c8<CT>(ub + C * R + r, C, R, w, a);
 #pragma unroll
     for (int c = 0; c < 8; ++c)
       if (c < C) {
@@ -357,11 +362,12 @@ cci_fwd_warp_kernel(const float* __restrict__ u, const float* __restrict__ kerne
   }
 }
 
-template <bool TILE>
+template <bool TILE, int CT>
 __global__ void __launch_bounds__(kCciWarps * 32)
 cci_bwd_warp_kernel(const float* __restrict__ u, const float* __restrict__ kernel,
                     const float* __restrict__ grad_out, float* __restrict__ grad_u,
-                    float* __restrict__ partial /*(B, C*C)*/, int64_t B, int C, int R) {
+                    float* __restrict__ partial /*(B, C*C)*/, int64_t B, int C_rt, int R) {
+  const int C = CT ? CT : C_rt;
   extern __shared__ __align__(128) unsigned char dyn_smem[];
   __shared__ float sK[64];
   for (int i = threadIdx.x; i < C * C; i += blockDim.x) sK[i] = __ldg(kernel + i);
@@ -398,7 +404,7 @@ cci_bwd_warp_kernel(const float* __restrict__ u, const float* __restrict__ kerne
   for (int i = 0; i < 16; ++i) means[i] = 0.f;
   for (int r = lane; r < R; r += 32) {
     float w[8], what[8], gzt[8];
-    softmax_c8(ub + C * R + r, C, R, w, what);
+    softmax_c8<CT>(ub + C * R + r, C, R, w, what);
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
       gzt[c] = 0.f;
@@ -445,7 +451,7 @@ cci_bwd_warp_kernel(const float* __restrict__ u, const float* __restrict__ kerne
   // pass B: the gradients (rows are L1/L2 hot)
   for (int r = lane; r < R; r += 32) {
     float w[8], what[8], gzt[8], t[8], uu[8];
-    softmax_c8(ub + C * R + r, C, R, w, what);
+    softmax_c8<CT>(ub + C * R + r, C, R, w, what);
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
       gzt[c] = 0.f;
@@ -499,12 +505,12 @@ extern "C" int dic_cci_fwd(const float* u, const float* kernel, float* out, int6
     const size_t tile = (size_t)3 * C * R * 4;
     const size_t smem = 64 + kCciWarps * tile;
     if (tile % 16 == 0 && aligned16(u) && smem <= (size_t)kMaxSmemBytes) {
+      auto kf = C == 6 ? cci_fwd_warp_kernel<true, 6> : cci_fwd_warp_kernel<true, 0>;
       if (smem > 48 * 1024)
-        DIC_CUDA(cudaFuncSetAttribute(cci_fwd_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)smem));
-      cci_fwd_warp_kernel<true><<<grid, kCciWarps * 32, smem, st>>>(u, kernel, out, B, C, R);
+        DIC_CUDA(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      kf<<<grid, kCciWarps * 32, smem, st>>>(u, kernel, out, B, C, R);
     } else
-      cci_fwd_warp_kernel<false><<<grid, kCciWarps * 32, 0, st>>>(u, kernel, out, B, C, R);
+      cci_fwd_warp_kernel<false, 0><<<grid, kCciWarps * 32, 0, st>>>(u, kernel, out, B, C, R);
   } else cci_fwd_kernel<16><<<(unsigned)B, kCciThreads, 0, st>>>(u, kernel, out, C, R);
   DIC_LAUNCH_CHECK("cci_fwd_kernel");
   return DIC_OK;
@@ -535,12 +541,12 @@ extern "C" int dic_cci_bwd(const float* u, const float* kernel, const float* gra
     const unsigned grid = (unsigned)((B + kCciWarps - 1) / kCciWarps);
     const size_t tile = (size_t)3 * C * R * 4, smem = 64 + kCciWarps * 2 * tile;
     if (tile % 16 == 0 && aligned16(u) && aligned16(grad_out) && smem <= (size_t)kMaxSmemBytes) {
+      auto kf = C == 6 ? cci_bwd_warp_kernel<true, 6> : cci_bwd_warp_kernel<true, 0>;
       if (smem > 48 * 1024)
-        DIC_CUDA(cudaFuncSetAttribute(cci_bwd_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)smem));
-      cci_bwd_warp_kernel<true><<<grid, kCciWarps * 32, smem, st>>>(u, kernel, grad_out, grad_u, partial, B, C, R);
+        DIC_CUDA(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      kf<<<grid, kCciWarps * 32, smem, st>>>(u, kernel, grad_out, grad_u, partial, B, C, R);
     } else {
-      cci_bwd_warp_kernel<false><<<grid, kCciWarps * 32, 0, st>>>(u, kernel, grad_out, grad_u, partial, B, C, R);
+      cci_bwd_warp_kernel<false, 0><<<grid, kCciWarps * 32, 0, st>>>(u, kernel, grad_out, grad_u, partial, B, C, R);
     }
   } else
     cci_bwd_kernel<16><<<(unsigned)B, kCciThreads, 0, st>>>(u, kernel, grad_out, grad_u, partial, C, R);
