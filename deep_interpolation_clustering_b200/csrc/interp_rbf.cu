@@ -32,24 +32,26 @@ rbf_fwd_kernel(const float* __restrict__ v, const float* __restrict__ x,
                float* __restrict__ rec, float* __restrict__ inv_norm, int C, int T, int R, int Rp,
                int64_t x_stride) {
   extern __shared__ __align__(16) float smem[];
-  float2* srv = reinterpret_cast<float2*>(smem);     // [C][Rp] (r_j, v_cj); pad: (huge, 0) => e = 0
-  float* snb = smem + 2 * C * Rp;                     // [C] -beta_c log2(e)
+  float2* srv = reinterpret_cast<float2*>(smem);     // [C][Rp] (s_c r_j, v_cj); pad: (huge, 0) => e = 0
+  float* snb = smem + 2 * C * Rp;                     // [C] s_c = sqrt(beta_c log2 e): coordinates are pre-scaled so
+                                                      //     that the exponent is just -(s d - s r)^2 (one FMUL)
   int* strip = reinterpret_cast<int*>(snb + C);       // [C] grid points per window (even)
   const float r0 = __ldg(ref_t), rl = __ldg(ref_t + R - 1);
   const float h = R > 1 ? (rl - r0) / (float)(R - 1) : 1.0f;
   int irregular = !(h > 0.f);
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const float b2 = softplus_ref(__ldg(kernel + c)) * kLog2e;
-    snb[c] = -b2;
+    snb[c] = sqrtf(b2);
     // window = +-sqrt(cut / (beta log2 e)) hours -> grid points, +2 points of slack each side
     strip[c] = (2 * ((int)ceilf(sqrtf(kRbfCut / b2) / h) + 2) + 1) & ~1;
   }
+  __syncthreads();
   const int64_t b = blockIdx.x;
   const float* vb = v + b * (int64_t)C * R;
   for (int j = threadIdx.x; j < Rp; j += blockDim.x) {
-    const float rj = j < R ? __ldg(ref_t + j) : 3.0e18f;
+    const float rj = j < R ? __ldg(ref_t + j) : 3.0e18f;      // (3e18 s)^2 stays finite, 2^-that == 0
     if (j < R) irregular |= fabsf(rj - (r0 + h * (float)j)) > 0.01f * h;
-    for (int c = 0; c < C; ++c) srv[c * Rp + j] = make_float2(rj, j < R ? __ldg(vb + c * R + j) : 0.f);
+    for (int c = 0; c < C; ++c) srv[c * Rp + j] = make_float2(rj * snb[c], j < R ? __ldg(vb + c * R + j) : 0.f);
   }
   irregular = __syncthreads_or(irregular);
   const float inv_h = 1.0f / h;
@@ -100,7 +102,7 @@ rbf_fwd_kernel(const float* __restrict__ v, const float* __restrict__ x,
 
   auto readout = [&](int c, int i, float m) {
     const float d = __ldg(db + i);
-    const float nb2 = snb[c];
+    const float ds = d * snb[c];
     // Every lane walks the same number of grid points (strip[c] -> trip), starting at its own
     // even offset: uniform trip count, no divergence, no union-of-windows penalty.
     int jlo = 0, trip = Rp;
@@ -113,8 +115,8 @@ rbf_fwd_kernel(const float* __restrict__ v, const float* __restrict__ x,
 #pragma unroll 2
     for (int j = 0; j < trip; j += 2) {
       const float4 p = *reinterpret_cast<const float4*>(rw + j);   // (r0, v0, r1, v1)
-      const float d0 = d - p.x, d1 = d - p.z;
-      const float e0 = ex2_approx(d0 * d0 * nb2), e1 = ex2_approx(d1 * d1 * nb2);
+      const float d0 = ds - p.x, d1 = ds - p.z;
+      const float e0 = ex2_approx(-(d0 * d0)), e1 = ex2_approx(-(d1 * d1));
       N += e0;
       S = fmaf(e0, p.y, S);
       N += e1;
@@ -152,7 +154,7 @@ rbf_fwd_kernel(const float* __restrict__ v, const float* __restrict__ x,
 
 struct RbfSmem {
   uint64_t* bar;
-  float* rows;     // [3][C][Tp]: d | a' = m^2 g invN | a'S = m g invN rec
+  float* rows;     // [3][C][Tp]: mask, then a' = m^2 g invN | s d (scaled time) | a'S = m g invN rec
   int* n_valid;    // [C]
   int* order;      // [C] vitals by descending count
   float* part;     // [C * ceil(R/32)]
@@ -183,25 +185,19 @@ rbf_bwd_kernel(const float* __restrict__ v, const float* __restrict__ x,
                const float* __restrict__ kernel, const float* __restrict__ ref_t,
                const float* __restrict__ rec, const float* __restrict__ inv_norm,
                const float* __restrict__ grad_rec, float* __restrict__ grad_v,
-               float* __restrict__ partial, int C, int T, int Tp, int R, int64_t x_stride) {
+               float* __restrict__ partial, int C, int T, int Tp, int R, int64_t x_stride, int use_tma) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const RbfSmem s = rbf_carve(smem_raw, C, Tp);
   const int64_t b = blockIdx.x;
   const float* mb = x + b * x_stride + (int64_t)C * T;
-  const float* db = x + b * x_stride + (int64_t)2 * C * T;
   const float* rb = rec + b * (int64_t)C * T;
   const float* nb = inv_norm + b * (int64_t)C * T;
   const float* gb = grad_rec + b * (int64_t)C * T;
-  float* sd = s.rows;                 // times
-  float* sa = s.rows + C * Tp;        // mask first, then a'
+  float* sa = s.rows;                 // mask first, then a'
+  float* sd = s.rows + C * Tp;        // times, scaled by s_c = sqrt(beta_c log2 e) once the row is canonical
   float* sas = s.rows + 2 * C * Tp;   // a'S
-  for (int i = threadIdx.x; i < C * Tp; i += blockDim.x) {
-    const int c = i / Tp, t = i - c * Tp;
-    const bool in = t < T;
-    sd[i] = in ? __ldg(db + c * T + t) : 0.f;
-    sa[i] = in ? __ldg(mb + c * T + t) : 0.f;
-  }
-  __syncthreads();
+  // the mask and time planes of one encounter are adjacent: ONE bulk copy of 2*C*T floats
+  stage_rows(s.rows, mb, 2 * C, T, Tp, s.bar, use_tma != 0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   for (int c = warp; c < C; c += nwarps) {
     float* rd = sd + c * Tp;
@@ -221,6 +217,11 @@ rbf_bwd_kernel(const float* __restrict__ v, const float* __restrict__ x,
       warp_sort3(rd, ra, ras, n, lane);
     }
     warp_pad4_far(rd, ra, ras, n, lane);
+    {   // pre-scale the (sorted) times: the exponent becomes -(s d - s r)^2, one FMUL per pair
+      const float sc = sqrtf(softplus_ref(__ldg(kernel + c)) * kLog2e);
+      const int n4 = (n + 3) & ~3;
+      for (int t = lane; t < n4; t += 32) rd[t] *= sc;        // pad entries stay huge and finite
+    }
     if (lane == 0) s.n_valid[c] = n;
   }
   __syncthreads();
@@ -251,22 +252,31 @@ rbf_bwd_kernel(const float* __restrict__ v, const float* __restrict__ x,
     const float* ras = sas + c * Tp;
     const int n = s.n_valid[c];
     const float b2 = softplus_ref(__ldg(kernel + c)) * kLog2e;
-    const float nb2 = -b2;
+    const float sc = sqrtf(b2);
     int ridx[RPT];
     float rr[RPT], vv[RPT], dv[RPT], acc[RPT];
 #pragma unroll
     for (int k = 0; k < RPT; ++k) {
       ridx[k] = (chunk * 32 + lane) * RPT + k;
       const int rc = min(ridx[k], R - 1);
-      rr[k] = __ldg(ref_t + rc);
+      rr[k] = __ldg(ref_t + rc) * sc;                         // scaled like the staged times
       vv[k] = __ldg(vb + c * R + rc);
       dv[k] = acc[k] = 0.f;
     }
-    const float wcut = sqrtf(kRbfCut / b2);
-    const Window w = make_window(rd, n, rr[0], rr[RPT - 1], wcut, wcut, false);
+    // one window [r_first - w, r_last + w] in scaled units (w = sqrt(cut)), two searches, uniform trip
     const int n4 = (n + 3) & ~3;
-    for (int t0 = 0; t0 < w.trip; t0 += 4) {
-      const int t = w.base + t0;
+    int wbase = 0, wtrip = n4;
+    if (n > 0) {
+      const float wcut = sqrtf(kRbfCut);
+      const float tv[2] = {rr[0] - wcut, rr[RPT - 1] + wcut};
+      const bool up[2] = {false, true};
+      int pos[2];
+      multi_bound<2>(rd, n, tv, up, pos);
+      wbase = pos[0] & ~3;
+      wtrip = (warp_max_i(pos[1] - wbase) + 3) & ~3;
+    }
+    for (int t0 = 0; t0 < wtrip; t0 += 4) {
+      const int t = wbase + t0;
       if ((unsigned)t >= (unsigned)n4) continue;        // chunk off the row (lane at an end of the record)
       const float4 d4 = *reinterpret_cast<const float4*>(rd + t);
       const float4 a4 = *reinterpret_cast<const float4*>(ra + t);
@@ -279,11 +289,11 @@ rbf_bwd_kernel(const float* __restrict__ v, const float* __restrict__ x,
 #pragma unroll
         for (int k = 0; k < RPT; ++k) {
           const float dl = dd[j] - rr[k];
-          const float n2 = dl * dl;
-          const float e = ex2_approx(n2 * nb2);
+          const float arg = -(dl * dl);                         // = -beta log2(e) (d - r)^2
+          const float e = ex2_approx(arg);
           dv[k] = fmaf(e, aa[j], dv[k]);
           const float tt = fmaf(aa[j], vv[k], -as[j]);
-          acc[k] = fmaf(e * n2, tt, acc[k]);
+          acc[k] = fmaf(e * arg, tt, acc[k]);                   // sum of -b2 n e (...): rescaled below
         }
       }
     }
@@ -295,7 +305,7 @@ rbf_bwd_kernel(const float* __restrict__ v, const float* __restrict__ x,
         tot += acc[k];
       }
     }
-    tot = warp_sum(tot);
+    tot = warp_sum(tot) * (-1.0f / b2);                        // back to sum n e (a' v - a'S)
     if (lane == 0) s.part[c * chunks + chunk] = tot;
   }
   __syncthreads();
@@ -365,6 +375,7 @@ extern "C" int dic_rbf_bwd(const float* v, const float* x, const float* kernel, 
   DIC_REQUIRE(smem <= (size_t)kMaxSmemBytes, DIC_ERR_UNSUPPORTED,
               "C=%d T=%d needs %zu bytes of shared memory per encounter (limit %d)", C, T, smem,
               kMaxSmemBytes);
+  const int use_tma = (Tp == T) && aligned16(x) && ((x_stride * 4) % 16 == 0) && (((int64_t)C * T * 4) % 16 == 0);
   const int rpt = R <= 32 ? 1 : (R <= 64 ? 2 : 3);
   const int chunks = (R + 32 * rpt - 1) / (32 * rpt);
   int warps = (C * chunks + 1) / 2;      // two tasks per warp, paired heavy + light (snake order)
@@ -380,7 +391,8 @@ extern "C" int dic_rbf_bwd(const float* v, const float* x, const float* kernel, 
       DIC_CUDA(cudaFuncSetAttribute(rbf_bwd_kernel<RPT_>,                                        \
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
     rbf_bwd_kernel<RPT_><<<(unsigned)B, warps * 32, smem, st>>>(                                 \
-        v, x, kernel, ref_t, rec, inv_norm, grad_rec, grad_v, partial, C, T, Tp, R, x_stride);   \
+        v, x, kernel, ref_t, rec, inv_norm, grad_rec, grad_v, partial, C, T, Tp, R, x_stride,    \
+        use_tma);                                                                                \
   }
   if (rpt == 1) DIC_RBF_BWD(1) else if (rpt == 2) DIC_RBF_BWD(2) else DIC_RBF_BWD(3)
 #undef DIC_RBF_BWD
