@@ -1,3 +1,7 @@
 mkdir -p gpurun_out; rm -f gpurun_out/parity_report.jsonl
-timeout 300 python -m pytest tests/test_gpu_interp.py -m gpu -x -q --timeout 100 > gpurun_out/pytest_interp.log 2>&1; echo "exit $?" >> gpurun_out/pytest_interp.log
-timeout 300 python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/bench9.json 2> gpurun_out/bench9.err; echo "exit $?" >> gpurun_out/bench9.err
+timeout 900 python -m pytest tests -m gpu -x -q --timeout 200 > gpurun_out/pytest_gpu.log 2>&1; echo "exit $?" >> gpurun_out/pytest_gpu.log
+timeout 900 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "exit $?" >> gpurun_out/smoke.log
+timeout 900 python bench.py > gpurun_out/bench10.json 2> gpurun_out/bench10.err; echo "exit $?" >> gpurun_out/bench10.err
+timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref2.json 2> gpurun_out/bench_ref2.err
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches2.csv python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --encounters 131072 > gpurun_out/ncu_launch.log 2>&1; echo "exit $?" >> gpurun_out/ncu_launch.log
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"sci_fwd_kernel|sci_bwd_kernel|rbf_fwd_kernel|rbf_bwd_kernel|cci_fwd_warp|cci_bwd_warp" -s 6 -c 6 -o gpurun_out/prof_v6 python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/ncu6.log 2>&1; echo "exit $?" >> gpurun_out/ncu6.log

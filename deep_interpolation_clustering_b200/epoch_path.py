@@ -72,7 +72,9 @@ def init_cluster_centers(hidden, cluster_number, mode="kmeans", n_init=20, rando
     if mode == "kmeans":
         km = KMeansB200(n_clusters=cluster_number, n_init=n_init, random_state=random_state)
         pred = km.fit_predict(x)
-        centers = torch.as_tensor(np.asarray(km.cluster_centers_), dtype=torch.float).to(x.device).clone().requires_grad_(True)
+        cc = km.cluster_centers_                 # tensor when fitted on a tensor, ndarray otherwise (sklearn contract)
+        cc = cc.detach() if isinstance(cc, torch.Tensor) else torch.from_numpy(np.asarray(cc))
+        centers = cc.to(device=x.device, dtype=torch.float).clone().requires_grad_(True)
         return pred, centers, km
     if mode == "random":
         rng = np.random if rng is None else rng
