@@ -1,7 +1,4 @@
-mkdir -p gpurun_out; rm -f gpurun_out/parity_report.jsonl
-timeout 900 python -m pytest tests -m gpu -x -q --timeout 200 > gpurun_out/pytest_gpu.log 2>&1; echo "exit $?" >> gpurun_out/pytest_gpu.log
-timeout 900 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "exit $?" >> gpurun_out/smoke.log
-timeout 900 python bench.py > gpurun_out/bench10.json 2> gpurun_out/bench10.err; echo "exit $?" >> gpurun_out/bench10.err
-timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref2.json 2> gpurun_out/bench_ref2.err
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches2.csv python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --encounters 131072 > gpurun_out/ncu_launch.log 2>&1; echo "exit $?" >> gpurun_out/ncu_launch.log
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"sci_fwd_kernel|sci_bwd_kernel|rbf_fwd_kernel|rbf_bwd_kernel|cci_fwd_warp|cci_bwd_warp" -s 6 -c 6 -o gpurun_out/prof_v6 python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/ncu6.log 2>&1; echo "exit $?" >> gpurun_out/ncu6.log
+mkdir -p gpurun_out
+timeout 300 python -m pytest tests/test_final_labels.py -m gpu -x -q --timeout 100 > gpurun_out/pytest_final.log 2>&1; echo "exit $?" >> gpurun_out/pytest_final.log
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 3 --warmup 3 > gpurun_out/bench_N2.json 2> gpurun_out/bench_N2.err; echo "exit $?" >> gpurun_out/bench_N2.err
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 1 --warmup 1 > gpurun_out/bench_ref_N2.json 2> gpurun_out/bench_ref_N2.err; echo "exit $?" >> gpurun_out/bench_ref_N2.err
