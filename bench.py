@@ -322,11 +322,12 @@ def device_arm(args, rank, world, local_rank):
             ktab[n]["gex2_per_s"] = round(ex2[n] / 1e9 / (m * 1e-3), 1)
             ktab[n]["mufu_frac"] = round(ex2[n] / (m * 1e-3) / mufu.value, 4)
     dom = max(kms, key=kms.get)
-    traffic = None          # measured DRAM bytes per launch of the dominant kernel (one ncu --set full capture)
+    traffic, ncu_pipes = None, None   # from ONE committed ncu --set full capture: DRAM bytes per launch, pipe utilisation
     try:
         tr = json.load(open(os.path.join(REPO, "profiles", "dram_traffic.json")))
         if dom in tr["bytes_per_launch"] and args.workload == "c2":
             traffic = round(tr["bytes_per_launch"][dom] * (B / tr["encounters"]) / 1e9, 3)
+            ncu_pipes = tr.get("pipes", {}).get(dom)
     except Exception:
         pass
     roofline = {"kernel": dom, "bound": "hbm", "achieved": ktab[dom]["gbps"], "peak": hbm_peak, "unit": "GB/s",
@@ -337,6 +338,7 @@ def device_arm(args, rank, world, local_rank):
                     "achieved": ktab[dom].get("gex2_per_s"), "peak": round(mufu.value / 1e9, 1),
                     "frac": ktab[dom].get("mufu_frac"), "ffma_peak_gops": round(ffma.value / 1e9, 1),
                     "peak_source": "dic_probe_mufu: ex2.approx-only kernel timed in this run",
+                    "ncu": ncu_pipes,
                     "note": "algorithmic exps = 2 per (valid obs, ref point) for SCI (low+high pass), 1 for RBF; "
                             "the kernels skip pairs whose weight is below 2^-27..2^-30 of the largest and evaluate the "
                             "high-pass exponential only inside its narrow window, so frac may exceed 1 (ncu: issue "
