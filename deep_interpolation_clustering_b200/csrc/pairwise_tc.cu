@@ -445,14 +445,16 @@ namespace tc64 {
 constexpr int kBlk = 128;
 constexpr int kTileB = kBlk * 64 * 4;        // 32 KB: one hi or lo operand tile (128 rows x K = 64)
 constexpr int kBlockB = 2 * kTileB;          // 64 KB per packed 128-row block: hi | lo
-constexpr int kHalfB = kTileB / 2;           // 16 KB: one K-half (8 of the 16 sixteen-byte K chunks)
-constexpr int kStages = 3;
+constexpr int kKParts = 2;                   // a column tile arrives in kKParts K-slices (one pipeline stage each);
+                                             // measured: 4 slices (6 x 16 KB stages) are 10 % SLOWER (smaller bulk copies)
+constexpr int kHalfB = kTileB / kKParts;     // bytes of one K-slice of a hi (or lo) tile: 16 / kKParts K chunks
+constexpr int kStages = 96 * 1024 / (2 * kHalfB);   // 96 KB of stages next to the resident 128 KB row pair
 constexpr int kEpiWarps = 8;
 constexpr int kThreads64 = 32 * (2 + kEpiWarps);
 
 struct __align__(128) Smem64 {
   unsigned char a[2][2][kTileB];             // [row block of the pair][hi | lo]
-  unsigned char b[kStages][2][kHalfB];       // [stage][hi | lo], one K-half of a column tile
+  unsigned char b[kStages][2][kHalfB];       // [stage][hi | lo], one K-slice of a column tile
   uint64_t a_full, a_empty, b_full[kStages], b_empty[kStages], acc_full[2], acc_empty[2];
   double red[kEpiWarps];
   uint32_t tmem_base;
@@ -577,7 +579,7 @@ pairwise_tc64_kernel(const unsigned char* __restrict__ packed, const float* __re
         for (int q = 0; q < 4; ++q) bulk_g2s(&S.a[0][0][0] + q * kTileB, arow + q * kTileB, kTileB, &S.a_full);
         for (int64_t bj = j0; bj < j1 && !*timeout; ++bj) {
           const unsigned char* bcol = packed + bj * (int64_t)kBlockB;
-          for (int kh = 0; kh < 2; ++kh, ++g) {
+          for (int kh = 0; kh < kKParts; ++kh, ++g) {
             const int slot = (int)(g % kStages);
             c0 = clock64();
             if (!bar_wait_bounded(&S.b_empty[slot], (uint32_t)(((g / kStages) & 1) ^ 1))) { *timeout = 1; break; }
@@ -607,7 +609,7 @@ pairwise_tc64_kernel(const unsigned char* __restrict__ packed, const float* __re
           c0 = clock64();
           if (!bar_wait_bounded(&S.acc_empty[buf], (uint32_t)(((t >> 1) & 1) ^ 1))) { *timeout = 1; break; }
           w_acc += clock64() - c0;
-          for (int kh = 0; kh < 2; ++kh, ++g) {
+          for (int kh = 0; kh < kKParts; ++kh, ++g) {
             const int slot = (int)(g % kStages);
             c0 = clock64();
             if (!bar_wait_bounded(&S.b_full[slot], (uint32_t)((g / kStages) & 1))) { *timeout = 1; break; }
@@ -619,8 +621,8 @@ pairwise_tc64_kernel(const unsigned char* __restrict__ packed, const float* __re
               const uint32_t d_tmem = tmem + (uint32_t)((buf * 2 + h) * kBlk);
               const uint32_t a_hi = a_base + (uint32_t)(h * kBlockB), a_lo = a_hi + kTileB;
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks) {            // one MMA consumes K = 8 tf32 = two 16-byte chunks
-                const uint32_t ka = (uint32_t)((kh * 8 + ks * 2) * kChunkStride);
+              for (int ks = 0; ks < 8 / kKParts; ++ks) {  // one MMA consumes K = 8 tf32 = two 16-byte chunks
+                const uint32_t ka = (uint32_t)((kh * (16 / kKParts) + ks * 2) * kChunkStride);
                 const uint32_t kb = (uint32_t)(ks * 2 * kChunkStride);
                 const uint64_t dah = make_desc(a_hi + ka), dal = make_desc(a_lo + ka);
                 const uint64_t dbh = make_desc(b_hi + kb), dbl = make_desc(b_lo + kb);
