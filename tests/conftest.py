@@ -15,6 +15,16 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+def pytest_sessionstart(session):
+    """Build libdic_b200.so when it is missing or older than its sources (the .so is git-ignored; nvcc
+    cross-compiles without a GPU).  A failed build is reported by the tests that need the library."""
+    try:
+        from deep_interpolation_clustering_b200 import build as _build
+        _build.build()
+    except Exception as e:          # noqa: BLE001
+        sys.stderr.write(f"[conftest] could not build libdic_b200.so: {e}\n")
+
+
 def pytest_collection_modifyitems(config, items):
     try:
         import torch
