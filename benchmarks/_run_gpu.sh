@@ -1,4 +1,3 @@
 mkdir -p gpurun_out
-DIC_TC_PROFILE=1 timeout 100 python benchmarks/_pw_prof1.py > gpurun_out/pwprof.log 2>&1
-timeout 60 python -m pytest tests/test_gpu_kmeans.py -m gpu -x -q --timeout 50 -k "tensor or silhouette" > gpurun_out/pytest_tc.log 2>&1; echo "exit $?" >> gpurun_out/pytest_tc.log
-timeout 100 python benchmarks/_pw_prof.py > gpurun_out/pwplain.log 2>&1; echo "exit $?" >> gpurun_out/pwplain.log
+timeout 300 python -m pytest tests/test_gpu_kmeans.py tests/test_final_labels.py -m gpu -x -q --timeout 100 > gpurun_out/pytest_km.log 2>&1; echo "exit $?" >> gpurun_out/pytest_km.log
+timeout 200 python benchmarks/_sweep_prof.py > gpurun_out/sweep_prof.log 2>&1

@@ -462,8 +462,17 @@ __global__ void kmeans_update_kernel(const double* __restrict__ sums, const doub
                                      const double* __restrict__ stats, T* __restrict__ centers,
                                      double* __restrict__ status, int K, int D) {
   __shared__ double red[32];
+  __shared__ int s_empty;
+  if (threadIdx.x == 0) {
+    int e = 0;
+    for (int k = 0; k < K; ++k) e += (counts[k] == 0.0);
+    s_empty = e;
+  }
+  __syncthreads();
+  // an empty cluster is the host's (rare) relocation path: leave the centres exactly as they are
+  const bool frozen = s_empty > 0;
   double shift2 = 0.0;
-  for (int i = threadIdx.x; i < K * D; i += blockDim.x) {
+  for (int i = threadIdx.x; i < K * D && !frozen; i += blockDim.x) {
     const int k = i / D;
     const double cnt = counts[k];
     if (cnt > 0.0) {
@@ -479,11 +488,9 @@ __global__ void kmeans_update_kernel(const double* __restrict__ sums, const doub
   if (threadIdx.x == 0) {
     double s = 0.0;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
-    int empty = 0;
-    for (int k = 0; k < K; ++k) empty += (counts[k] == 0.0);
     status[0] = stats[1];
     status[1] = s;
-    status[2] = (double)empty;
+    status[2] = (double)s_empty;
     status[3] = stats[0];
   }
 }
@@ -1426,6 +1433,15 @@ extern "C" int dic_kmeans_update(const double* sums, const double* counts, const
     kmeans_update_kernel<double><<<1, 256, 0, st>>>(sums, counts, stats, static_cast<double*>(centers), status, K, D);
   DIC_LAUNCH_CHECK("kmeans_update_kernel");
   return DIC_OK;
+}
+
+extern "C" int dic_kmeans_lloyd_step(const void* X, void* centers, int32_t* labels, double* sums, double* counts,
+                                     double* stats, double* status, void* workspace, int64_t N, int D, int K,
+                                     int dtype, int flags, dic_stream_t stream) {
+  DIC_REQUIRE(sums && counts && status, DIC_ERR_INVALID_ARGUMENT, "null pointer argument");
+  int rc = dic_kmeans_assign(X, centers, labels, sums, counts, stats, workspace, N, D, K, dtype, flags, stream);
+  if (rc) return rc;
+  return dic_kmeans_update(sums, counts, stats, centers, status, D, K, dtype, stream);
 }
 
 extern "C" int dic_kmeans_min_d2(const void* X, const void* cands, const void* min_d2, void* min_d2_out,

@@ -97,6 +97,26 @@ class _Device:
         self.counts = torch.empty(K, dtype=torch.float64, device=self.dev)
         self.stats = torch.empty(4, dtype=torch.float64, device=self.dev)
         self.status = torch.empty(4, dtype=torch.float64, device=self.dev)
+        self._step_args = None
+
+    def lloyd_step(self, centers, flags):
+        """One Lloyd iteration (E-step + M-step in place on `centers`) in ONE C call with ONE host sync;
+        returns (changed, shift2, n_empty, inertia).  If a cluster came out empty the centres are untouched."""
+        key = centers.data_ptr()
+        if self._step_args is None or self._step_args[0] != key:
+            L = _lib.lib()
+            self._step_args = (key, L.dic_kmeans_lloyd_step,
+                               (_lib.ptr(self.X), key, _lib.ptr(self.labels), _lib.ptr(self.sums), _lib.ptr(self.counts),
+                                _lib.ptr(self.stats), _lib.ptr(self.status), _lib.ptr(self.ws), self.N, self.D,
+                                centers.shape[0], self.dt), _lib.current_stream(self.dev))
+        _, fn, args, stream = self._step_args
+        if torch.cuda.current_device() == self.dev.index:
+            rc = fn(*args, flags, stream)
+        else:
+            with torch.cuda.device(self.dev):
+                rc = fn(*args, flags, stream)
+        _lib.check(rc, "dic_kmeans_lloyd_step")
+        return self.status.tolist()
 
     def update(self, centers):
         """M-step in place on `centers`; returns (changed, shift2, n_empty, inertia) with ONE sync."""
@@ -274,16 +294,19 @@ class KMeansB200:
         n_iter = 0
         for i in range(self.max_iter):
             n_iter = i + 1
-            st.assign(centers, DIC_KM_COUNT_CHANGES | DIC_KM_NO_INERTIA)
-            comm.sum_(st.sums, st.counts, st.stats)          # the one exchange step per iteration
-            if hasattr(st, "update"):
-                old = centers.clone()
-                changed, shift2, n_empty, _ = st.update(centers)        # in place, one host sync
-                if n_empty > 0:                                           # rare: redo the M-step on the host
-                    centers = old
+            if not comm.on and hasattr(st, "lloyd_step"):
+                changed, shift2, n_empty, _ = st.lloyd_step(centers, DIC_KM_COUNT_CHANGES | DIC_KM_NO_INERTIA)
+                if n_empty > 0:                  # rare: the centres were left untouched, redo the M-step on the host
                     changed = None
             else:
-                changed = None
+                st.assign(centers, DIC_KM_COUNT_CHANGES | DIC_KM_NO_INERTIA)
+                comm.sum_(st.sums, st.counts, st.stats)          # the one exchange step per iteration
+                if hasattr(st, "update"):
+                    changed, shift2, n_empty, _ = st.update(centers)    # in place, one host sync
+                    if n_empty > 0:
+                        changed = None
+                else:
+                    changed = None
             if changed is None:
                 changed = float(st.stats[1])
                 if int((st.counts == 0).sum()) > 0:

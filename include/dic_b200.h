@@ -176,11 +176,17 @@ int dic_kmeans_assign(const void* X, const void* centers, int32_t* labels, doubl
                       int dtype, int flags, dic_stream_t stream);
 
 /* M-step (sklearn/cluster/_k_means_common.pyx:236-260, _kmeans.py:703-733): centers (K,D, dtype)
- * in/out <- sums / counts for non-empty clusters (empty ones keep their centre: relocation is
- * the caller's rare path); status (4) float64 out = [labels changed (stats[1]), sum of squared
+ * in/out <- sums / counts; if ANY cluster is empty the centres are left untouched (relocation is
+ * the caller's rare path: it redoes the M-step); status (4) float64 out = [labels changed (stats[1]), sum of squared
  * centre shifts, number of empty clusters, inertia (stats[0])] - one small read per iteration. */
 int dic_kmeans_update(const double* sums, const double* counts, const double* stats, void* centers,
                       double* status, int D, int K, int dtype, dic_stream_t stream);
+
+/* One whole Lloyd iteration in one call: dic_kmeans_assign followed by dic_kmeans_update on the same
+ * stream (single-process use: a sharded fit all-reduces sums / counts / stats between the two). */
+int dic_kmeans_lloyd_step(const void* X, void* centers, int32_t* labels, double* sums, double* counts,
+                          double* stats, double* status, void* workspace, int64_t N, int D, int K,
+                          int dtype, int flags, dic_stream_t stream);
 
 /* k-means++ potentials (sklearn/cluster/_kmeans.py:224-281): for each of L candidate centres
  *   pots[l] = sum_i min(min_d2[i], ||x_i - cand_l||^2)          (float64, L <= 16)
