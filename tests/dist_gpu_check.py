@@ -1,0 +1,108 @@
+"""Multi-GPU (NCCL) parity of the sharded hot path against the single-GPU result.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+        --master-port 29533 tests/dist_gpu_check.py
+
+Every rank computes the FULL problem on its own GPU (the single-process truth) and its SHARD through the
+sharded entry points; the shard results must reproduce the matching rows / the global
+reductions: interpolation parameter gradients (one packed all-reduce), DEC target distribution and fused KL step
+(global column sum, global 'batchmean'), k-means (labels bit-exact, centres, inertia).  Prints one JSON line on
+rank 0 and exits non-zero on any mismatch.  Run by tests/test_gpu_multi.py when >= 2 GPUs are visible.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+
+import deep_interpolation_clustering_b200 as dic                                  # noqa: E402
+from deep_interpolation_clustering_b200 import functional as F_, parallel, synth  # noqa: E402
+from deep_interpolation_clustering_b200.kmeans import KMeansB200                   # noqa: E402
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    report = {}
+
+    # ---- interpolation: gradients of the sharded batch == gradients of the whole batch ----------------------
+    B, C, T, R, H = 4096, 6, 64, 48, 24.0
+    xn = synth.make_encounters(B, C, T, H, seed=0)
+    p = synth.make_interp_params(C, seed=1)
+    rng = np.random.RandomState(2)
+    vn = rng.normal(size=(B, C, R)).astype(np.float32)
+    gn = rng.normal(size=(B, R, 3 * C)).astype(np.float32)
+
+    def run(sl):
+        sci = dic.SingleChannelInterp(R, H, C, T, dev)
+        cci = dic.CrossChannelInterp(C, T, dev)
+        rbf = dic.RBF(H, R, C, C, 0.0, dic.basis_func_dict()["gaussian"], dev)
+        rbf.compress_fc = torch.nn.Identity()
+        sci.kernel.data = torch.tensor(p["sci_kernel"], device=dev)
+        cci.kernel.data = torch.tensor(p["cci_kernel"], device=dev)
+        rbf.kernel.data = torch.tensor(p["rbf_kernel"], device=dev)
+        x = torch.tensor(xn[sl], device=dev)
+        v = torch.tensor(vn[sl], device=dev)
+        out = cci(sci(x))
+        rec = rbf(v, x)
+        ((out * torch.tensor(gn[sl], device=dev)).sum() + (rec ** 2).sum()).backward()
+        return [sci.kernel, cci.kernel, rbf.kernel]
+
+    full = run(slice(0, B))
+    lo, hi = parallel.shard_range(B, rank, world)
+    mine = run(slice(lo, hi))
+    parallel.allreduce_gradients(mine)
+    for name, a, b in zip(("d_sci", "d_cci", "d_rbf"), full, mine):
+        err = float(((a.grad - b.grad).abs() / (a.grad.abs() + 1e-3 * a.grad.abs().max())).max())
+        report[name] = err
+        assert err < 2e-5, (name, err)          # different float32 summation order only
+
+    # ---- DEC: global target distribution and fused KL step ---------------------------------------------------
+    N, D, K = 20000, 64, 4
+    zn, mun = synth.make_latents(N, D, K, seed=3)
+    z, mu = torch.tensor(zn, device=dev), torch.tensor(mun, device=dev)
+    ref = F_.dec_kl_step(z, mu, 1.0, weight=10.0)
+    lo, hi = parallel.shard_range(N, rank, world)
+    sh = parallel.sharded_dec_kl_step(z[lo:hi].contiguous(), mu, 1.0, weight=10.0)
+    assert torch.equal(sh["labels"], ref["labels"][lo:hi])
+    report["dec_p"] = float((sh["p"] - ref["p"][lo:hi]).abs().max())
+    report["dec_kl"] = float((sh["kl"] - ref["kl"]).abs().max() / ref["kl"].abs().max())
+    report["dec_dmu"] = float((sh["grad_mu"] - ref["grad_mu"]).abs().max() / ref["grad_mu"].abs().max())
+    report["dec_dz"] = float((sh["grad_z"] - ref["grad_z"][lo:hi]).abs().max() / ref["grad_z"].abs().max())
+    assert report["dec_p"] < 1e-6 and report["dec_kl"] < 1e-6 and report["dec_dmu"] < 1e-5 and report["dec_dz"] < 1e-5, report
+    q = F_.dec_soft_assign(z, mu, 1.0).detach()
+    p_full = F_.dec_target_distribution(q)
+    p_sh = parallel.sharded_target_distribution(q[lo:hi].contiguous())
+    report["target_p"] = float((p_sh - p_full[lo:hi]).abs().max())
+    assert report["target_p"] < 1e-6
+
+    # ---- k-means: sharded fit == single-process fit ----------------------------------------------------------
+    for dtype in (np.float32, np.float64):
+        X = synth.make_blobs(30001, 64, 5, seed=4).astype(dtype)          # odd size: ragged shards
+        single = KMeansB200(n_clusters=5, n_init=2, random_state=7, device=dev).fit(X)
+        lo, hi = parallel.shard_range(X.shape[0], rank, world)
+        shard = KMeansB200(n_clusters=5, n_init=2, random_state=7, device=dev, sharded=True).fit(X[lo:hi])
+        assert np.array_equal(shard.labels_, single.labels_[lo:hi]), "sharded k-means labels differ"
+        tag = "f32" if dtype == np.float32 else "f64"
+        report[f"km_{tag}_centers"] = float(np.abs(shard.cluster_centers_ - single.cluster_centers_).max())
+        report[f"km_{tag}_inertia"] = abs(shard.inertia_ - single.inertia_) / single.inertia_
+        assert report[f"km_{tag}_centers"] < (1e-5 if dtype == np.float32 else 1e-10), report
+        assert report[f"km_{tag}_inertia"] < (1e-6 if dtype == np.float32 else 1e-12), report
+        assert shard.n_iter_ == single.n_iter_
+
+    dist.barrier()
+    if rank == 0:
+        print(json.dumps({"world": world, "ok": True, **{k: float(f"{v:.3e}") for k, v in report.items()}}), flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
