@@ -22,11 +22,14 @@
 //   * both filters share the shift, so the high-pass exponent is 10x the low-pass one: one MUFU.EX2 per
 //     (t, r) in the outer window, a second one (2^(10 arg)) only inside the narrow high-pass window;
 //   * sliding windows: a Gaussian weight below 2^-kCut of the largest one is dropped, so a lane
-//     only walks the observations within +-sqrt(nmin + kCut/a) hours of its grid points, and
-//     only the inner +-sqrt(nmin + kCut/(10a)) feeds the high-pass sums (make_window);
+//     only walks the observations within +-sqrt(nmin + kCut/a) hours of its grid points for the
+//     low-pass sums, and in a second, short loop those within +-sqrt(nmin + kCut/(10a)) for the
+//     high-pass sums (make_window2: one warp-uniform trip count per loop);
 //   * accumulators stay in registers, each lane owns RPT ADJACENT grid points, observations are
 //     read as 128-bit shared loads; vitals are dealt to warps heaviest-first in snake order so
 //     the warps of a CTA finish together.
+#include <type_traits>
+
 #include "interp_stage.cuh"
 
 namespace dic {
@@ -131,12 +134,18 @@ __device__ __forceinline__ void sci_fwd_task(const float* __restrict__ sx, const
     nmax = fmaxf(nmax, nhi[k]);
     s1[k] = sy[k] = s10[k] = sy10[k] = 0.f;
   }
-  const Window w = make_window(sd, n, rr[0], rr[RPT - 1], sqrtf(nmax + kCut / a),
-                               sqrtf(nmax + kCut / (10.f * a)), WEIGHTED);
+  const Window2 w = make_window2(sd, n, rr[0], rr[RPT - 1], sqrtf(nmax + kCut / a),
+                                 sqrtf(nmax + kCut / (10.f * a)), WEIGHTED);
   const int n4 = (n + 3) & ~3;
+  const float na10 = 10.f * na;
+  float nlo10[RPT];
+#pragma unroll
+  for (int k = 0; k < RPT; ++k) nlo10[k] = 10.f * nlo[k];
 
-  auto body = [&](int t0, bool inner) {
-    const int t = w.base + t0;
+  // HIGH = false: low-pass sums over the outer window; HIGH = true: high-pass sums (exponent x 10, same shift)
+  // over the inner window.  One MUFU.EX2 per pair in either loop.
+  auto body = [&](int t, auto high) {
+    constexpr bool HIGH = decltype(high)::value;
     const bool in_row = (unsigned)t < (unsigned)n4;           // chunks off the row weigh nothing
     const float4 d4 = *reinterpret_cast<const float4*>(in_row ? sd + t : nullc);
     const float4 x4 = *reinterpret_cast<const float4*>(in_row ? sx + t : nullc + 4);
@@ -153,24 +162,19 @@ __device__ __forceinline__ void sci_fwd_task(const float* __restrict__ sx, const
       for (int k = 0; k < RPT; ++k) {
         const float dl = dd[j] - rr[k];
         // -a ((d-r)^2 - (d*-r)^2) <= 0: the difference of squares is rounded once, the residual rides in the FMA
-        const float arg = fmaf(fmaf(dl, dl, -nhi[k]), na, nlo[k]);
-        const float e = ex2_approx(arg);
-        s1[k] = WEIGHTED ? fmaf(mm[j], e, s1[k]) : s1[k] + e;
-        sy[k] = fmaf(xx[j], e, sy[k]);
-        if (inner) {
-          // high-pass weight e^10 = 2^(10 arg): a second MUFU (the XU pipe has the headroom) costs two issue
-          // slots where four squarings cost four, and does not multiply the MUFU's rounding error by ten
-          const float e10 = ex2_approx(10.f * arg);
-          s10[k] = WEIGHTED ? fmaf(mm[j], e10, s10[k]) : s10[k] + e10;
-          sy10[k] = fmaf(xx[j], e10, sy10[k]);
+        const float e = ex2_approx(fmaf(fmaf(dl, dl, -nhi[k]), HIGH ? na10 : na, HIGH ? nlo10[k] : nlo[k]));
+        if (HIGH) {
+          s10[k] = WEIGHTED ? fmaf(mm[j], e, s10[k]) : s10[k] + e;
+          sy10[k] = fmaf(xx[j], e, sy10[k]);
+        } else {
+          s1[k] = WEIGHTED ? fmaf(mm[j], e, s1[k]) : s1[k] + e;
+          sy[k] = fmaf(xx[j], e, sy[k]);
         }
       }
     }
   };
-  int t0 = 0;
-  for (; t0 < w.in0; t0 += 4) body(t0, false);
-  for (; t0 < w.in1; t0 += 4) body(t0, true);
-  for (; t0 < w.trip; t0 += 4) body(t0, false);
+  for (int t0 = 0; t0 < w.ot; t0 += 4) body(w.ob + t0, std::false_type{});
+  for (int t0 = 0; t0 < w.it; t0 += 4) body(w.ib + t0, std::true_type{});
 
 #pragma unroll
   for (int k = 0; k < RPT; ++k) {
@@ -276,12 +280,18 @@ __device__ __forceinline__ float sci_bwd_task(const float* __restrict__ sx, cons
     A10[k] = gy10 * i10;
     acc[k] = 0.f;
   }
-  const Window w = make_window(sd, n, rr[0], rr[RPT - 1], sqrtf(nmax + kCut / a),
-                               sqrtf(nmax + kCut / (10.f * a)), WEIGHTED);
+  const Window2 w = make_window2(sd, n, rr[0], rr[RPT - 1], sqrtf(nmax + kCut / a),
+                                 sqrtf(nmax + kCut / (10.f * a)), WEIGHTED);
   const int n4 = (n + 3) & ~3;
+  const float na10 = 10.f * na;
+  float nlo10[RPT];
+#pragma unroll
+  for (int k = 0; k < RPT; ++k) nlo10[k] = 10.f * nlo[k];
 
-  auto body = [&](int t0, bool inner) {
-    const int t = w.base + t0;
+  // HIGH = false: the low-pass / intensity terms over the outer window; HIGH = true: the high-pass term over
+  // the inner window (exponent x 10, same shift).  One MUFU.EX2 per pair in either loop.
+  auto body = [&](int t, auto high) {
+    constexpr bool HIGH = decltype(high)::value;
     const bool in_row = (unsigned)t < (unsigned)n4;
     const float4 d4 = *reinterpret_cast<const float4*>(in_row ? sd + t : nullc);
     const float4 x4 = *reinterpret_cast<const float4*>(in_row ? sx + t : nullc + 4);
@@ -297,22 +307,15 @@ __device__ __forceinline__ float sci_bwd_task(const float* __restrict__ sx, cons
 #pragma unroll
       for (int k = 0; k < RPT; ++k) {
         const float dl = dd[j] - rr[k];
-        const float arg = fmaf(fmaf(dl, dl, -nhi[k]), na, nlo[k]);
-        const float e = ex2_approx(arg);
-        float h = e * fmaf(xx[j] - yy[k], A[k], Bc[k]);
-        if (inner) {
-          const float e10 = ex2_approx(10.f * arg);
-          h = fmaf(e10, (xx[j] - yy10[k]) * A10[k], h);
-        }
+        const float e = ex2_approx(fmaf(fmaf(dl, dl, -nhi[k]), HIGH ? na10 : na, HIGH ? nlo10[k] : nlo[k]));
+        float h = HIGH ? e * ((xx[j] - yy10[k]) * A10[k]) : e * fmaf(xx[j] - yy[k], A[k], Bc[k]);
         if (WEIGHTED) h *= mm[j];
         acc[k] = fmaf(dl * dl, h, acc[k]);                    // n_tr = (d_t - r)^2
       }
     }
   };
-  int t0 = 0;
-  for (; t0 < w.in0; t0 += 4) body(t0, false);
-  for (; t0 < w.in1; t0 += 4) body(t0, true);
-  for (; t0 < w.trip; t0 += 4) body(t0, false);
+  for (int t0 = 0; t0 < w.ot; t0 += 4) body(w.ob + t0, std::false_type{});
+  for (int t0 = 0; t0 < w.it; t0 += 4) body(w.ib + t0, std::true_type{});
 
   float tot = 0.f;
 #pragma unroll

@@ -206,6 +206,32 @@ __device__ __forceinline__ Window make_window(const float* key, int n, float r_f
   return w;
 }
 
+// Two independent windows for the two filters (interp_sci.cu): the low-pass sums walk [ob, ob + ot) and the
+// high-pass sums walk [ib, ib + it) in a second, much shorter loop.  Each window costs ONE warp maximum
+// (uniform trip from per-lane 4-aligned bases); with a shared loop the three segments outer-left | inner |
+// outer-right each paid their own maximum over the lanes plus their own round-up to whole chunks.
+struct Window2 {
+  int ob, ot, ib, it;
+};
+__device__ __forceinline__ Window2 make_window2(const float* key, int n, float r_first, float r_last, float w_out,
+                                                float w_in, bool full) {
+  const int n4 = (n + 3) & ~3;
+  Window2 w;
+  if (full || n == 0) {
+    w.ob = 0; w.ot = n4; w.ib = 0; w.it = n4;
+    return w;
+  }
+  const float tv[4] = {r_first - w_out, r_first - w_in, r_last + w_in, r_last + w_out};
+  const bool up[4] = {false, false, true, true};
+  int pos[4];
+  multi_bound<4>(key, n, tv, up, pos);                 // lo <= ilo <= ihi <= hi
+  w.ob = pos[0] & ~3;
+  w.ib = pos[1] & ~3;
+  w.ot = (warp_max_i(pos[3] - w.ob) + 3) & ~3;
+  w.it = (warp_max_i(pos[2] - w.ib) + 3) & ~3;
+  return w;
+}
+
 // d* - r for the observation nearest to r, given lb = #{i : key[i] < r} in sorted key[0..n), n >= 1.
 __device__ __forceinline__ float nearest_delta(const float* key, int n, int lb, float r) {
   const float below = key[max(lb, 1) - 1] - r;        // <= 0 when lb >= 1
