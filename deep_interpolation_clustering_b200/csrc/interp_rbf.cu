@@ -12,6 +12,8 @@
 // row (r_j, v_j) is read as shared-memory broadcasts; one MUFU.EX2 per (t, r).
 // Backward: the reduction for grad_v runs over observations, so the encounter is staged
 // like SCI (interp_stage.cuh) and each lane owns RPT grid points.
+#include <stdlib.h>
+
 #include "interp_stage.cuh"
 
 namespace dic {
@@ -26,7 +28,7 @@ constexpr int kMaxWarps = 8;
 // span, and non-uniform grids, take the full range.
 constexpr float kRbfCut = 30.0f;
 
-__global__ void __launch_bounds__(kRbfFwdThreads)
+__global__ void __launch_bounds__(kRbfFwdThreads, 6)
 rbf_fwd_kernel(const float* __restrict__ v, const float* __restrict__ x,
                const float* __restrict__ kernel, const float* __restrict__ ref_t,
                float* __restrict__ rec, float* __restrict__ inv_norm, int C, int T, int R, int Rp,
@@ -148,6 +150,163 @@ rbf_fwd_kernel(const float* __restrict__ v, const float* __restrict__ x,
       }
       t += blockDim.x;
       while (t >= T) { t -= T; ++c; }
+    }
+  }
+}
+
+// ---- forward, warp-task form -------------------------------------------------------------------------
+// The element-dealing kernel above pays ~120 issue slots per observation around a ~320-slot loop (vital
+// search, window arithmetic, scattered loads and stores) and a prologue of dependent global loads behind six
+// block barriers.  Here the encounter's mask + time planes and its grid values arrive by TMA bulk copies
+// while the parameters are computed, and the work is cut into TASKS of 32 consecutive observations of one
+// vital: within a task the vital, its window length and its (s r_j, v_j) row are warp-uniform, every lane
+// reads its observation from shared memory and the 32 results leave as one coalesced store.  Tasks are dealt
+// round-robin to the warps (about 27 tasks for 4 warps at c2).
+constexpr int kRbfFwd2Warps = 4;
+
+struct RbfFwd2Smem {
+  uint64_t* bar;
+  float* planes;    // [2][C][Tp]: mask | time
+  float* sv;        // [C][R] grid values
+  float2* srv;      // [C][Rp] (s_c r_j, v_cj), pad (huge, 0)
+  float* ssc;       // [C] s_c = sqrt(beta_c log2 e)
+  int* strip;       // [C] grid points per window (even)
+  int* nval;        // [C] observation slots to visit: the prefix length, or T for a general mask
+  int* tbase;       // [C + 1] prefix sums of the task counts
+};
+__host__ __device__ inline size_t rbf_fwd2_offsets(int C, int Tp, int R, int Rp, size_t (&off)[8]) {
+  size_t o = 16;
+  off[0] = o; o += sizeof(float) * 2 * (size_t)C * Tp;
+  off[1] = o; o += (sizeof(float) * (size_t)C * R + 15) / 16 * 16;
+  off[2] = o; o += sizeof(float2) * (size_t)C * Rp;
+  off[3] = o; o += sizeof(float) * C;
+  off[4] = o; o += sizeof(int) * C;
+  off[5] = o; o += sizeof(int) * C;
+  off[6] = o; o += sizeof(int) * (C + 1);
+  return (o + 15) / 16 * 16;
+}
+__device__ __forceinline__ RbfFwd2Smem rbf_fwd2_carve(unsigned char* base, int C, int Tp, int R, int Rp) {
+  size_t off[8];
+  rbf_fwd2_offsets(C, Tp, R, Rp, off);
+  RbfFwd2Smem s;
+  s.bar = reinterpret_cast<uint64_t*>(base);
+  s.planes = reinterpret_cast<float*>(base + off[0]);
+  s.sv = reinterpret_cast<float*>(base + off[1]);
+  s.srv = reinterpret_cast<float2*>(base + off[2]);
+  s.ssc = reinterpret_cast<float*>(base + off[3]);
+  s.strip = reinterpret_cast<int*>(base + off[4]);
+  s.nval = reinterpret_cast<int*>(base + off[5]);
+  s.tbase = reinterpret_cast<int*>(base + off[6]);
+  return s;
+}
+
+__global__ void __launch_bounds__(kRbfFwd2Warps * 32)
+rbf_fwd2_kernel(const float* __restrict__ v, const float* __restrict__ x, const float* __restrict__ kernel,
+                const float* __restrict__ ref_t, float* __restrict__ rec, float* __restrict__ inv_norm, int C,
+                int T, int Tp, int R, int Rp, int64_t x_stride, int use_tma) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const RbfFwd2Smem s = rbf_fwd2_carve(smem_raw, C, Tp, R, Rp);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t b = blockIdx.x;
+  const float* mb = x + b * x_stride + (int64_t)C * T;         // mask plane, followed by the time plane
+  const float* vb = v + b * (int64_t)C * R;
+  float* rb = rec + b * (int64_t)C * T;
+  float* nb = inv_norm ? inv_norm + b * (int64_t)C * T : nullptr;
+
+  if (use_tma && tid == 0) {                                   // both copies are in flight during the set-up below
+    mbar_init(s.bar, 1);
+    fence_proxy_async();
+    const uint32_t pb = (uint32_t)(2 * C * T) * 4u, vbytes = (uint32_t)(C * R) * 4u;
+    mbar_expect_tx(s.bar, pb + vbytes);
+    bulk_g2s(s.planes, mb, pb, s.bar);
+    bulk_g2s(s.sv, vb, vbytes, s.bar);
+  }
+  const float r0 = __ldg(ref_t), rl = __ldg(ref_t + R - 1);
+  const float h = R > 1 ? (rl - r0) / (float)(R - 1) : 1.0f;
+  int irregular = !(h > 0.f);
+  for (int c = tid; c < C; c += blockDim.x) {
+    const float b2 = softplus_ref(__ldg(kernel + c)) * kLog2e;
+    s.ssc[c] = sqrtf(b2);
+    s.strip[c] = (2 * ((int)ceilf(sqrtf(kRbfCut / b2) / h) + 2) + 1) & ~1;   // window + 2 points of slack per side
+  }
+  for (int j = tid; j < R; j += blockDim.x) irregular |= fabsf(__ldg(ref_t + j) - (r0 + h * (float)j)) > 0.01f * h;
+  if (!use_tma) {
+    for (int i = tid; i < 2 * C * Tp; i += blockDim.x) {
+      const int row = i / Tp, t = i - row * Tp;
+      s.planes[i] = t < T ? __ldg(mb + row * T + t) : 0.f;
+    }
+    for (int i = tid; i < C * R; i += blockDim.x) s.sv[i] = __ldg(vb + i);
+  }
+  irregular = __syncthreads_or(irregular);                     // also publishes ssc / strip / the mbarrier
+  if (use_tma) mbar_wait(s.bar, 0);
+
+  const float* smask = s.planes;
+  const float* stime = s.planes + C * Tp;
+  for (int i = tid; i < C * Rp; i += blockDim.x) {             // (s_c r_j, v_cj) rows
+    const int c = i / Rp, j = i - c * Rp;
+    s.srv[i] = j < R ? make_float2(__ldg(ref_t + j) * s.ssc[c], s.sv[c * R + j]) : make_float2(3.0e18f, 0.f);
+  }
+  for (int c = warp; c < C; c += kRbfFwd2Warps) {              // prefix masks: visit [0, n) and zero the tail
+    const float* mrow = smask + c * Tp;
+    int ok = 1, cnt = 0;
+    for (int t = lane; t < T; t += 32) {
+      const float m = mrow[t];
+      const float mn = t + 1 < T ? mrow[t + 1] : 0.f;
+      ok &= ((m == 0.f) | (m == 1.f)) & (m >= mn);
+      cnt += (m == 1.f);
+    }
+    ok = __all_sync(0xffffffffu, ok);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    const int n = ok ? cnt : T;                                // general mask: every slot is visited
+    for (int t = n + lane; t < T; t += 32) {
+      rb[c * T + t] = 0.f;
+      if (nb) nb[c * T + t] = 0.f;
+    }
+    if (lane == 0) s.nval[c] = n;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    s.tbase[0] = 0;
+    for (int c = 0; c < C; ++c) s.tbase[c + 1] = s.tbase[c] + (s.nval[c] + 31) / 32;
+  }
+  __syncthreads();
+
+  const float inv_h = 1.0f / h;
+  const int ntask = s.tbase[C];
+  int c = 0;
+  for (int k = warp; k < ntask; k += kRbfFwd2Warps) {
+    while (k >= s.tbase[c + 1]) ++c;                           // warp-uniform, monotone in k
+    const int t = (k - s.tbase[c]) * 32 + lane;
+    const int n = s.nval[c];
+    const bool live = t < n;
+    const int tc = live ? t : n - 1;                           // idle lanes shadow the last observation
+    const float m = smask[c * Tp + tc];
+    const float d = stime[c * Tp + tc];
+    const float ds = d * s.ssc[c];
+    // every lane walks the same number of grid points from its own even offset
+    int trip = min(Rp, s.strip[c]);
+    const bool wide = irregular || !(d >= r0 - 1.0f && d <= rl + 1.0f);
+    if (__any_sync(0xffffffffu, wide && live && m != 0.f)) trip = Rp;      // rare: the whole row for this task
+    const int jlo = trip == Rp ? 0
+                               : min(max(0, (__float2int_rd((d - r0) * inv_h) - (trip >> 1) + 1) & ~1), Rp - trip);
+    float N = 0.f, S = 0.f;
+    const float2* rw = s.srv + c * Rp + jlo;
+#pragma unroll 2
+    for (int j = 0; j < trip; j += 2) {
+      const float4 p = *reinterpret_cast<const float4*>(rw + j);   // (s r0, v0, s r1, v1)
+      const float d0 = ds - p.x, d1 = ds - p.z;
+      const float e0 = ex2_approx(-(d0 * d0)), e1 = ex2_approx(-(d1 * d1));
+      N += e0;
+      S = fmaf(e0, p.y, S);
+      N += e1;
+      S = fmaf(e1, p.w, S);
+    }
+    if (live) {
+      // phi = m e  =>  N_ref = m N, sum phi v = m S; a masked slot of a general row reconstructs to 0
+      const float inv = m != 0.f ? __frcp_rn(fmaf(m, N, 1e-10f)) : 0.f;
+      rb[c * T + t] = (m * S) * inv * m;                        // rbf.py:106-107
+      if (nb) nb[c * T + t] = inv;
     }
   }
 }
@@ -346,6 +505,22 @@ extern "C" int dic_rbf_fwd(const float* v, const float* x, const float* kernel, 
   DIC_REQUIRE(rec || B == 0, DIC_ERR_INVALID_ARGUMENT, "null output pointer");
   if (B == 0) return DIC_OK;
   const int Rp = round_up(R, 2);
+  {   // warp-task kernel (TMA-staged planes): the default
+    const int Tp = round_up(T, 4);
+    size_t off[8];
+    const size_t smem2 = rbf_fwd2_offsets(C, Tp, R, Rp, off);
+    static const bool v1 = getenv("DIC_RBF_FWD_V1") != nullptr;          // debug: the element-dealing kernel
+    if (!v1 && smem2 <= (size_t)kMaxSmemBytes) {
+      const int use_tma = (Tp == T) && aligned16(x) && aligned16(v) && ((x_stride * 4) % 16 == 0) &&
+                          (((int64_t)C * T * 4) % 16 == 0) && (((int64_t)C * R * 4) % 16 == 0);
+      if (smem2 > 48 * 1024)
+        DIC_CUDA(cudaFuncSetAttribute(rbf_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+      rbf_fwd2_kernel<<<(unsigned)B, kRbfFwd2Warps * 32, smem2, as_stream(stream)>>>(
+          v, x, kernel, ref_t, rec, inv_norm, C, T, Tp, R, Rp, x_stride, use_tma);
+      DIC_LAUNCH_CHECK("rbf_fwd2_kernel");
+      return DIC_OK;
+    }
+  }
   const size_t smem = sizeof(float2) * (size_t)C * Rp + sizeof(float) * (3 * (size_t)C + 1);
   DIC_REQUIRE(smem <= (size_t)kMaxSmemBytes, DIC_ERR_UNSUPPORTED,
               "C=%d R=%d needs %zu bytes of shared memory (limit %d)", C, R, smem, kMaxSmemBytes);
