@@ -43,6 +43,10 @@ CFG_NAME = "c2: interp fwd+bwd + DEC assign, 1M enc x 6 vitals x <=256 obs, 96 r
 WORKLOADS = {
     "c1": dict(T=64, R=48, K=4, B=1000, name="c1: interp fwd+bwd + DEC assign, 1,000 enc x 6 vitals x <=64 obs, 48 ref points"),
     "c2": dict(T=256, R=96, K=4, B=1_000_000, name=CFG_NAME),
+    # c3 = c2 with the whole DEC step of the joint-clustering loop: q (+labels, column sum), then ONE fused kernel
+    # for p, the KL sum and the closed-form gradients dz, dmu (clustering_interp.py:186,205-207)
+    "c3": dict(T=256, R=96, K=4, B=1_000_000, dec_kl=True,
+               name="c3: interp fwd+bwd + DEC q/p/KL fwd+bwd, K=4, 1M enc x 6 vitals x <=256 obs, 96 ref points"),
     "c5": dict(T=1024, R=192, K=16, B=131_072,
                name="c5 (stress shape): interp fwd+bwd + DEC assign, 6 vitals x <=1024 obs, 192 ref points, K=16, "
                     "one 131,072-encounter shard of the 10M per step"),
@@ -164,9 +168,10 @@ class HotPath:
     """Preallocated buffers + direct C-ABI calls for one shard (no allocation in the timed loop)."""
 
     # launches of OUR kernels behind each C-ABI call (kernel + reductions)
-    LAUNCHES = dict(sci_fwd=1, cci_fwd=1, cci_bwd=3, sci_bwd=4, rbf_fwd=1, rbf_bwd=4, dec_q=2, dec_p=1)
+    LAUNCHES = dict(sci_fwd=1, cci_fwd=1, cci_bwd=3, sci_bwd=4, rbf_fwd=1, rbf_bwd=4, dec_q=2, dec_p=1, dec_kl=2)
 
-    def __init__(self, B, dev, seed):
+    def __init__(self, B, dev, seed, dec_kl=False):
+        self.dec_kl = dec_kl
         import torch
         from deep_interpolation_clustering_b200 import _lib, synth
         self.t, self.L, self._lib, self.B, self.dev = torch, _lib.lib(), _lib, B, dev
@@ -198,6 +203,10 @@ class HotPath:
         self.ws_i = torch.empty(int(self.L.dic_interp_bwd_workspace_bytes(B, C)), dtype=torch.uint8, device=dev)
         self.ws_c = torch.empty(int(self.L.dic_cci_bwd_workspace_bytes(B, C)), dtype=torch.uint8, device=dev)
         self.ws_d = torch.empty(int(self.L.dic_dec_workspace_bytes(K_CLUST, D_LAT)), dtype=torch.uint8, device=dev)
+        if dec_kl:
+            self.g_z = torch.empty_like(self.z)
+            self.g_mu = torch.empty_like(self.mu)
+            self.kl = torch.empty(1, dtype=torch.float64, device=dev)
         self.n_valid = float(self.x[:, C:2 * C].sum())
 
     def kernels(self, st):
@@ -205,6 +214,11 @@ class HotPath:
         L, P, B = self.L, self._lib.ptr, self.B
         chk = self._lib.check
         gs, gc, gr = self.grads[:C], self.grads[C:C + C * C], self.grads[C + C * C:]
+        tail = [("dec_p", lambda: chk(L.dic_dec_p(P(self.q), P(self.colsum), P(self.p), B, K_CLUST, st), "dec_p"))]
+        if self.dec_kl:      # p, KL sum and the gradients dz, dmu in one kernel; scale = weight 10 / B (p3_clustering_main.py:85)
+            tail = [("dec_kl", lambda: chk(L.dic_dec_kl_fwd_bwd(P(self.z), P(self.mu), P(self.colsum), P(self.p), P(self.kl),
+                                                                 P(self.g_z), P(self.g_mu), P(self.ws_d), B, D_LAT, K_CLUST,
+                                                                 1.0, 10.0 / B, st), "dec_kl"))]
         return [
             ("sci_fwd", lambda: chk(L.dic_sci_fwd(P(self.x), P(self.k_sci), P(self.ref_t), P(self.u), P(self.stats),
                                                   B, C, T, R, 0, st), "sci_fwd")),
@@ -220,8 +234,7 @@ class HotPath:
                                                   B, C, T, R, 0, st), "rbf_bwd")),
             ("dec_q", lambda: chk(L.dic_dec_q_fwd(P(self.z), P(self.mu), P(self.q), P(self.labels), P(self.colsum),
                                                   P(self.ws_d), B, D_LAT, K_CLUST, 1.0, st), "dec_q")),
-            ("dec_p", lambda: chk(L.dic_dec_p(P(self.q), P(self.colsum), P(self.p), B, K_CLUST, st), "dec_p")),
-        ]
+        ] + tail
 
     def algorithmic(self):
         """Algorithmic HBM bytes and MUFU exps per launch (split per kernel)."""
@@ -229,7 +242,8 @@ class HotPath:
         ct, cr = C * T * 4.0, C * R * 4.0
         byt = dict(sci_fwd=3 * ct + 3 * cr + 2 * cr, cci_fwd=6 * cr, cci_bwd=9 * cr,
                    sci_bwd=3 * ct + 3 * cr + 2 * cr + 3 * cr, rbf_fwd=2 * ct + cr + 2 * ct,
-                   rbf_bwd=2 * ct + 3 * ct + cr + cr, dec_q=D_LAT * 4.0 + K_CLUST * 4.0 + 4.0, dec_p=2 * K_CLUST * 4.0)
+                   rbf_bwd=2 * ct + 3 * ct + cr + cr, dec_q=D_LAT * 4.0 + K_CLUST * 4.0 + 4.0, dec_p=2 * K_CLUST * 4.0,
+                   dec_kl=2 * D_LAT * 4.0 + K_CLUST * 4.0)
         ex2 = dict(sci_fwd=2 * nv * R, sci_bwd=2 * nv * R, rbf_fwd=nv * R, rbf_bwd=nv * R)
         return {k: v * B for k, v in byt.items()}, ex2
 
@@ -243,18 +257,20 @@ def device_arm(args, rank, world, local_rank):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B = args.encounters
-    hp = HotPath(B, dev, seed=1000 * rank)
+    hp = HotPath(B, dev, seed=1000 * rank, dec_kl=bool(WORKLOADS[args.workload].get("dec_kl")))
     stream = torch.cuda.current_stream(dev)
     st = stream.cuda_stream
     kernels = hp.kernels(st)
 
     def step():
         for name, fn in kernels:
-            if name == "dec_p" and world > 1:
+            if name in ("dec_p", "dec_kl") and world > 1:
                 dist.all_reduce(hp.colsum)               # f_j over the global batch (dec.py:73)
             fn()
         if world > 1:
             dist.all_reduce(hp.grads)                    # parameter gradients of the sharded batch
+            if hp.dec_kl:
+                dist.all_reduce(hp.g_mu)                 # centre gradients (K x D floats)
 
     def barrier():
         if world > 1:
@@ -358,7 +374,7 @@ def device_arm(args, rank, world, local_rank):
                    "parallelism": f"encounter-sharded x{world}",
                    "l2": f"inputs ({B * 4 * C * T * 4 / 1e9:.1f} GB/GPU) " + ("exceed L2" if B * 4 * C * T * 4 > 2.5e8 else
                                                                            "fit L2: flushed by the other kernels' buffers")},
-        "clocks": clocks, "gpu_launches": args.steps * sum(HotPath.LAUNCHES.values()),
+        "clocks": clocks, "gpu_launches": args.steps * sum(HotPath.LAUNCHES[n] for n, _ in kernels),
         "kernels": ktab, "roofline": roofline, "roofline_sfu": roofline_sfu, "e2e": e2e,
     }
     if not args.no_cpu_baseline:

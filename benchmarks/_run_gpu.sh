@@ -1,3 +1,3 @@
-mkdir -p gpurun_out; rm -f gpurun_out/parity_report.jsonl
-timeout 300 python -m pytest tests/test_gpu_interp.py -m gpu -x -q --timeout 100 > gpurun_out/pytest_interp.log 2>&1; echo "exit $?" >> gpurun_out/pytest_interp.log
-timeout 300 python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/bench11.json 2> gpurun_out/bench11.err; echo "exit $?" >> gpurun_out/bench11.err
+mkdir -p gpurun_out
+timeout 300 python bench.py --workload c3 --steps 3 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/bench_c3.json 2> gpurun_out/bench_c3.err; echo "exit $?" >> gpurun_out/bench_c3.err
+timeout 300 python bench.py --workload c1 --steps 3 --warmup 3 --no-e2e > gpurun_out/bench_c1.json 2> gpurun_out/bench_c1.err; echo "exit $?" >> gpurun_out/bench_c1.err
