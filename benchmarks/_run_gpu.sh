@@ -1,3 +1,5 @@
 mkdir -p gpurun_out
-timeout 300 python bench.py --workload c3 --steps 3 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/bench_c3.json 2> gpurun_out/bench_c3.err; echo "exit $?" >> gpurun_out/bench_c3.err
-timeout 300 python bench.py --workload c1 --steps 3 --warmup 3 --no-e2e > gpurun_out/bench_c1.json 2> gpurun_out/bench_c1.err; echo "exit $?" >> gpurun_out/bench_c1.err
+timeout 120 python benchmarks/_km_prof.py 2>&1 | head -3 > gpurun_out/km_hc_on.log
+DIC_KMEANS_NO_HC=1 timeout 120 python benchmarks/_km_prof.py 2>&1 | head -3 > gpurun_out/km_hc_off.log
+timeout 120 python benchmarks/_km_prof_small.py 2>&1 | head -3 >> gpurun_out/km_hc_on.log
+DIC_KMEANS_NO_HC=1 timeout 120 python benchmarks/_km_prof_small.py 2>&1 | head -3 >> gpurun_out/km_hc_off.log
