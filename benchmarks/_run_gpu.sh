@@ -1,2 +1,2 @@
 mkdir -p gpurun_out
-timeout 200 python benchmarks/_dbg_sweep.py > gpurun_out/dbg_sweep.log 2>&1
+timeout 300 python -m pytest tests/test_gpu_kmeans.py -m gpu -q --timeout 100 -k "dispatch" > gpurun_out/pytest_disp.log 2>&1; echo "exit $?" >> gpurun_out/pytest_disp.log

@@ -191,3 +191,26 @@ def test_silhouette_tensor_core_matches_float64(n, D, K):
     if n <= 5000:
         from sklearn.metrics import silhouette_score
         record(f"silhouette_vs_sklearn_n{n}", native, float(silhouette_score(X, labels)), 1e-5, 1e-6)
+
+
+@pytest.mark.parametrize("dtag,D,K", [("f32", 64, 3), ("f32", 64, 10), ("f32", 64, 16), ("f64", 64, 4), ("f64", 64, 10),
+                                      ("f32", 128, 5), ("f64", 32, 6), ("f32", 100, 7), ("f64", 100, 3),
+                                      ("f32", 200, 4), ("f32", 300, 5), ("f32", 64, 20)])
+def test_lloyd_kernel_dispatch_matches_sklearn(dtag, D, K):
+    """Every Lloyd kernel (specialised tile kernel: rows of 16 / 32 vectors; streaming row kernel; generic tile
+    kernels) against scikit-learn run here on the same data and the same initial centres."""
+    from sklearn.cluster import KMeans
+    from deep_interpolation_clustering_b200 import synth
+    from deep_interpolation_clustering_b200.kmeans import KMeansB200
+    dt = np.float32 if dtag == "f32" else np.float64
+    X = synth.make_blobs(3001, D, 6, seed=D + K).astype(dt)
+    init = X[:K].copy()
+    ref = KMeans(n_clusters=K, init=init, n_init=1).fit(X)
+    km = KMeansB200(n_clusters=K, init=init, n_init=1).fit(X)
+    tag = f"dispatch_{dtag}_D{D}_K{K}"
+    _labels_equal_mod_ties(tag + "_labels", km.labels_, ref.labels_, X, ref.cluster_centers_)
+    assert km.n_iter_ == ref.n_iter_
+    record(tag + "_centers", km.cluster_centers_, ref.cluster_centers_, 1e-5, 1e-5)
+    record(tag + "_inertia", km.inertia_, ref.inertia_, 1e-5, 0)
+    Xv = synth.make_blobs(777, D, 6, seed=D + K + 1).astype(dt)
+    _labels_equal_mod_ties(tag + "_predict", km.predict(Xv), ref.predict(Xv), Xv, ref.cluster_centers_)
