@@ -292,7 +292,7 @@ rbf_fwd2_kernel(const float* __restrict__ v, const float* __restrict__ x, const 
                                : min(max(0, (__float2int_rd((d - r0) * inv_h) - (trip >> 1) + 1) & ~1), Rp - trip);
     float N = 0.f, S = 0.f;
     const float2* rw = s.srv + c * Rp + jlo;
-#pragma unroll 2
+#pragma unroll 4
     for (int j = 0; j < trip; j += 2) {
       const float4 p = *reinterpret_cast<const float4*>(rw + j);   // (s r0, v0, s r1, v1)
       const float d0 = ds - p.x, d1 = ds - p.z;
