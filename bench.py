@@ -185,7 +185,7 @@ class HotPath:
         self.k_rbf = torch.tensor(p["rbf_kernel"], **f32)
         self.ref_t = torch.linspace(0, HOURS, R).to(dev)
         self.u = torch.empty((B, 3 * C, R), **f32)
-        self.stats = torch.empty((B, 2 * C, R), **f32)
+        self.stats = torch.empty((B, 3 * C, R), **f32)          # gradient-moment rows [U1 | U0 | U1']
         self.out = torch.empty((B, 3 * C, R), **f32)
         self.g_out = torch.randn((B, 3 * C, R), generator=g, **f32)
         self.g_u = torch.empty((B, 3 * C, R), **f32)
@@ -240,11 +240,11 @@ class HotPath:
         """Algorithmic HBM bytes and MUFU exps per launch (split per kernel)."""
         B, nv = self.B, self.n_valid
         ct, cr = C * T * 4.0, C * R * 4.0
-        byt = dict(sci_fwd=3 * ct + 3 * cr + 2 * cr, cci_fwd=6 * cr, cci_bwd=9 * cr,
-                   sci_bwd=3 * ct + 3 * cr + 2 * cr + 3 * cr, rbf_fwd=2 * ct + cr + 2 * ct,
+        byt = dict(sci_fwd=3 * ct + 3 * cr + 3 * cr, cci_fwd=6 * cr, cci_bwd=9 * cr,
+                   sci_bwd=3 * cr + 3 * cr, rbf_fwd=2 * ct + cr + 2 * ct,
                    rbf_bwd=2 * ct + 3 * ct + cr + cr, dec_q=D_LAT * 4.0 + K_CLUST * 4.0 + 4.0, dec_p=2 * K_CLUST * 4.0,
                    dec_kl=2 * D_LAT * 4.0 + K_CLUST * 4.0)
-        ex2 = dict(sci_fwd=2 * nv * R, sci_bwd=2 * nv * R, rbf_fwd=nv * R, rbf_bwd=nv * R)
+        ex2 = dict(sci_fwd=2 * nv * R, rbf_fwd=nv * R, rbf_bwd=nv * R)     # sci_bwd no longer sweeps the observations
         return {k: v * B for k, v in byt.items()}, ex2
 
 

@@ -1,4 +1,3 @@
-mkdir -p gpurun_out
-DIC_KMEANS_T2_DB=1 timeout 300 python -m pytest tests/test_gpu_kmeans.py -m gpu -x -q --timeout 100 -k "lloyd or dispatch or config4" > gpurun_out/pytest_km.log 2>&1; echo "exit $?" >> gpurun_out/pytest_km.log
-timeout 300 python benchmarks/_km_pass.py > gpurun_out/km_pass_sb.json 2> gpurun_out/km_pass_sb.err
-DIC_KMEANS_T2_DB=1 timeout 300 python benchmarks/_km_pass.py > gpurun_out/km_pass_db.json 2> gpurun_out/km_pass_db.err
+mkdir -p gpurun_out; rm -f gpurun_out/parity_report.jsonl
+timeout 300 python -m pytest tests/test_gpu_interp.py -m gpu -q --timeout 100 > gpurun_out/pytest_interp.log 2>&1; echo "exit $?" >> gpurun_out/pytest_interp.log
+timeout 300 python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/bench14.json 2> gpurun_out/bench14.err; echo "exit $?" >> gpurun_out/bench14.err

@@ -107,7 +107,19 @@ __device__ __forceinline__ int snake_task(int round, int warp, int nwarps) {
   return round * nwarps + ((round & 1) ? (nwarps - 1 - warp) : warp);
 }
 
-template <int RPT, bool WEIGHTED>
+// Forward task.  Per filter it accumulates S = sum e and SY = sum e x (y = SY / S) and, when the backward pass
+// will run (MOM), the two moments that carry the whole kernel gradient:
+//     Q0 = sum t e,  Q1 = sum t e x,   t = (d - r)^2 - (d* - r)^2 >= 0   (the shifted squared distance)
+// With n_t = t + (d* - r)^2:
+//     sum_t n_t e_t (x_t - y) = Q1 - y Q0 + (d* - r)^2 (SY - y S) = Q1 - y Q0        (SY - y S == 0 by definition)
+//     sum_t n_t e_t           = Q0 + (d* - r)^2 S
+// so d alpha needs no second sweep over the observations (Appendix A.1):
+//     d alpha_c = - sum_r [ gy U1 + gw U0 + gy' U1' ],  U1 = (Q1 - y Q0)/S,  U0 = Q0/S + (d*-r)^2,
+//                                                       U1' = 10 (Q1' - y' Q0')/S'
+// The three U rows are what `stats` holds.  The term that made a direct sum of n e (x A - y A) cancel
+// catastrophically when one observation dominates - (d*-r)^2 sum e (x - y) - is the one that vanishes
+// analytically here and is never formed; the dominant observation itself has t = 0.
+template <int RPT, bool WEIGHTED, bool MOM>
 __device__ __forceinline__ void sci_fwd_task(const float* __restrict__ sx, const float* __restrict__ sm,
                                              const float* __restrict__ sd, int n, float alpha, int chunk,
                                              int lane, int c, int C, int R, const float* __restrict__ ref_t,
@@ -115,7 +127,7 @@ __device__ __forceinline__ void sci_fwd_task(const float* __restrict__ sx, const
                                              const float* __restrict__ nullc) {
   const float a = alpha * kLog2e, na = -a;
   int ridx[RPT];
-  float rr[RPT], nhi[RPT], nlo[RPT], s1[RPT], sy[RPT], s10[RPT], sy10[RPT];
+  float rr[RPT], nhi[RPT], nlo[RPT];
   float nmax = 0.f;
   bool upk[RPT];
   int lb[RPT];
@@ -128,69 +140,87 @@ __device__ __forceinline__ void sci_fwd_task(const float* __restrict__ sx, const
   multi_bound<RPT>(sd, n, rr, upk, lb);         // lb = first observation at or after r
 #pragma unroll
   for (int k = 0; k < RPT; ++k) {
-    const float dst = nearest_delta(sd, n, lb[k], rr[k]);           // delta* = d* - r
+    const int is = nearest_index(sd, n, lb[k], rr[k]);
+    const float dst = sd[is] - rr[k];                                // delta* = d* - r
     nhi[k] = dst * dst;
     nlo[k] = -na * fmaf(dst, dst, -nhi[k]);    // exact residual delta*^2 - nhi, pre-multiplied by a
     nmax = fmaxf(nmax, nhi[k]);
-    s1[k] = sy[k] = s10[k] = sy10[k] = 0.f;
   }
   const Window2 w = make_window2(sd, n, rr[0], rr[RPT - 1], sqrtf(nmax + kCut / a),
                                  sqrtf(nmax + kCut / (10.f * a)), WEIGHTED);
   const int n4 = (n + 3) & ~3;
-  const float na10 = 10.f * na;
-  float nlo10[RPT];
-#pragma unroll
-  for (int k = 0; k < RPT; ++k) nlo10[k] = 10.f * nlo[k];
 
-  // HIGH = false: low-pass sums over the outer window; HIGH = true: high-pass sums (exponent x 10, same shift)
-  // over the inner window.  One MUFU.EX2 per pair in either loop.
-  auto body = [&](int t, auto high) {
+  // One filter: HIGH = false walks the outer window with exponent -a t, HIGH = true the inner window with -10 a t
+  // (same shift).  One MUFU.EX2 per pair.
+  auto filter = [&](auto high, float (&S)[RPT], float (&SC)[RPT], float (&Q0)[RPT], float (&Q1)[RPT]) {
     constexpr bool HIGH = decltype(high)::value;
-    const bool in_row = (unsigned)t < (unsigned)n4;           // chunks off the row weigh nothing
-    const float4 d4 = *reinterpret_cast<const float4*>(in_row ? sd + t : nullc);
-    const float4 x4 = *reinterpret_cast<const float4*>(in_row ? sx + t : nullc + 4);
-    const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
-    const float xx[4] = {x4.x, x4.y, x4.z, x4.w};
-    float mm[4] = {1.f, 1.f, 1.f, 1.f};
-    if (WEIGHTED) {
-      const float4 m4 = *reinterpret_cast<const float4*>(sm + t);   // full range: always in the row
-      mm[0] = m4.x; mm[1] = m4.y; mm[2] = m4.z; mm[3] = m4.w;
+    const float nak = HIGH ? 10.f * na : na;
+    float nlk[RPT];
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) {
+      nlk[k] = HIGH ? 10.f * nlo[k] : nlo[k];
+      S[k] = SC[k] = Q0[k] = Q1[k] = 0.f;
     }
+    const int base = HIGH ? w.ib : w.ob, trip = HIGH ? w.it : w.ot;
+    for (int t0 = 0; t0 < trip; t0 += 4) {
+      const int t = base + t0;
+      const bool in_row = (unsigned)t < (unsigned)n4;           // chunks off the row weigh nothing
+      const float4 d4 = *reinterpret_cast<const float4*>(in_row ? sd + t : nullc);
+      const float4 x4 = *reinterpret_cast<const float4*>(in_row ? sx + t : nullc + 4);
+      const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
+      const float xx[4] = {x4.x, x4.y, x4.z, x4.w};
+      float mm[4] = {1.f, 1.f, 1.f, 1.f};
+      if (WEIGHTED) {
+        const float4 m4 = *reinterpret_cast<const float4*>(sm + t);   // full range: always in the row
+        mm[0] = m4.x; mm[1] = m4.y; mm[2] = m4.z; mm[3] = m4.w;
+      }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < 4; ++j) {
 #pragma unroll
-      for (int k = 0; k < RPT; ++k) {
-        const float dl = dd[j] - rr[k];
-        // -a ((d-r)^2 - (d*-r)^2) <= 0: the difference of squares is rounded once, the residual rides in the FMA
-        const float e = ex2_approx(fmaf(fmaf(dl, dl, -nhi[k]), HIGH ? na10 : na, HIGH ? nlo10[k] : nlo[k]));
-        if (HIGH) {
-          s10[k] = WEIGHTED ? fmaf(mm[j], e, s10[k]) : s10[k] + e;
-          sy10[k] = fmaf(xx[j], e, sy10[k]);
-        } else {
-          s1[k] = WEIGHTED ? fmaf(mm[j], e, s1[k]) : s1[k] + e;
-          sy[k] = fmaf(xx[j], e, sy[k]);
+        for (int k = 0; k < RPT; ++k) {
+          const float dl = dd[j] - rr[k];
+          const float t1 = fmaf(dl, dl, -nhi[k]);              // (d-r)^2 - (d*-r)^2, rounded once
+          const float e = ex2_approx(fmaf(t1, nak, nlk[k]));   // the residual of the shift rides in the FMA
+          // rows with fractional weights hold x m, and the weight of the pair is m e
+          S[k] = WEIGHTED ? fmaf(mm[j], e, S[k]) : S[k] + e;
+          SC[k] = fmaf(e, xx[j], SC[k]);
+          if (MOM) {
+            const float te = t1 * e;
+            Q0[k] = WEIGHTED ? fmaf(mm[j], te, Q0[k]) : Q0[k] + te;
+            Q1[k] = fmaf(te, xx[j], Q1[k]);
+          }
         }
       }
     }
   };
-  for (int t0 = 0; t0 < w.ot; t0 += 4) body(w.ob + t0, std::false_type{});
-  for (int t0 = 0; t0 < w.it; t0 += 4) body(w.ib + t0, std::true_type{});
 
+  float S[RPT], SC[RPT], Q0[RPT], Q1[RPT];
+  filter(std::false_type{}, S, SC, Q0, Q1);
 #pragma unroll
   for (int k = 0; k < RPT; ++k) {
     if (ridx[k] < R) {
-      ub[(0 * C + c) * R + ridx[k]] = sy[k] / s1[k];
-      ub[(1 * C + c) * R + ridx[k]] = logf(s1[k]) - alpha * nhi[k];
-      ub[(2 * C + c) * R + ridx[k]] = sy10[k] / s10[k];
-      if (sb) {
-        sb[(0 * C + c) * R + ridx[k]] = s1[k];
-        sb[(1 * C + c) * R + ridx[k]] = s10[k];
+      const float inv = 1.0f / S[k], yc = SC[k] * inv;
+      ub[(0 * C + c) * R + ridx[k]] = yc;
+      ub[(1 * C + c) * R + ridx[k]] = logf(S[k]) - alpha * nhi[k];
+      if (MOM) {
+        sb[(0 * C + c) * R + ridx[k]] = fmaf(-yc, Q0[k], Q1[k]) * inv;          // U1
+        sb[(1 * C + c) * R + ridx[k]] = fmaf(Q0[k], inv, nhi[k]);               // U0 >= 0
       }
+    }
+  }
+  filter(std::true_type{}, S, SC, Q0, Q1);
+#pragma unroll
+  for (int k = 0; k < RPT; ++k) {
+    if (ridx[k] < R) {
+      const float inv = 1.0f / S[k], yc = SC[k] * inv;
+      ub[(2 * C + c) * R + ridx[k]] = yc;
+      if (MOM) sb[(2 * C + c) * R + ridx[k]] = 10.f * fmaf(-yc, Q0[k], Q1[k]) * inv;   // U1'
     }
   }
 }
 
-template <int RPT>
+// MOM: also produce the three gradient-moment rows (stats (B, 3C, R) = [U1 | U0 | U1']) for dic_sci_bwd.
+template <int RPT, bool MOM>
 __global__ void __launch_bounds__(kMaxWarps * 32)
 sci_fwd_kernel(const float* __restrict__ x, const float* __restrict__ kernel,
                const float* __restrict__ ref_t, float* __restrict__ u, float* __restrict__ stats,
@@ -204,7 +234,7 @@ sci_fwd_kernel(const float* __restrict__ x, const float* __restrict__ kernel,
   const int chunks = (R + 32 * RPT - 1) / (32 * RPT);
   const int ntasks = C * chunks;
   float* ub = u + b * (int64_t)(3 * C) * R;
-  float* sb = stats ? stats + b * (int64_t)(2 * C) * R : nullptr;
+  float* sb = MOM ? stats + b * (int64_t)(3 * C) * R : nullptr;
 
   for (int round = 0;; ++round) {
     const int task = snake_task(round, warp, nwarps);
@@ -217,9 +247,9 @@ sci_fwd_kernel(const float* __restrict__ x, const float* __restrict__ kernel,
     const int nv = s.n_valid[c];
     const float alpha = softplus_ref(__ldg(kernel + c));
     if (nv > 0) {
-      sci_fwd_task<RPT, false>(sx, sm, sd, nv, alpha, chunk, lane, c, C, R, ref_t, ub, sb, s.nullc);
+      sci_fwd_task<RPT, false, MOM>(sx, sm, sd, nv, alpha, chunk, lane, c, C, R, ref_t, ub, sb, s.nullc);
     } else if (nv < 0) {
-      sci_fwd_task<RPT, true>(sx, sm, sd, -nv, alpha, chunk, lane, c, C, R, ref_t, ub, sb, s.nullc);
+      sci_fwd_task<RPT, true, MOM>(sx, sm, sd, -nv, alpha, chunk, lane, c, C, R, ref_t, ub, sb, s.nullc);
     } else {
       // all-masked vital: the reference yields w = -inf, y = y' = NaN (logsumexp of -inf)
 #pragma unroll
@@ -229,143 +259,42 @@ sci_fwd_kernel(const float* __restrict__ x, const float* __restrict__ kernel,
           ub[(0 * C + c) * R + r] = __int_as_float(0x7fc00000);
           ub[(1 * C + c) * R + r] = -INFINITY;
           ub[(2 * C + c) * R + r] = __int_as_float(0x7fc00000);
-          if (sb) sb[(0 * C + c) * R + r] = sb[(1 * C + c) * R + r] = 0.f;
+          if (MOM) {        // U0 < 0 marks "no contribution" (the reference's gradient is NaN there; U0 >= 0 otherwise)
+            sb[(0 * C + c) * R + r] = 0.f;
+            sb[(1 * C + c) * R + r] = -1.f;
+            sb[(2 * C + c) * R + r] = 0.f;
+          }
         }
       }
     }
   }
 }
 
-// Backward: d/d alpha_c = sum_{t,r} -n_tr (ds_t + 10 ds'_t)   (Appendix A.1), with
-//   ds_t  = m e   ((x - y ) A  + B),  A  = gy /S1,  B = gw/S1
-//   ds'_t = m e10 ((x - y') A')    ,  A' = gy'/S10
-// and n_tr = (d_t - r)^2.  (x - y) is formed first: when one observation dominates, y ~ x_t and
-// x A - y A would cancel catastrophically (measured 9e-5 relative on d kernel; 5e-6 this way).
-template <int RPT, bool WEIGHTED>
-__device__ __forceinline__ float sci_bwd_task(const float* __restrict__ sx, const float* __restrict__ sm,
-                                              const float* __restrict__ sd, int n, float a, int chunk,
-                                              int lane, int c, int C, int R,
-                                              const float* __restrict__ ref_t, const float* __restrict__ ub,
-                                              const float* __restrict__ gb, const float* __restrict__ sb,
-                                              const float* __restrict__ nullc) {
-  const float na = -a;
-  float rr[RPT], nhi[RPT], nlo[RPT], yy[RPT], yy10[RPT], A[RPT], Bc[RPT], A10[RPT], acc[RPT];
-  float nmax = 0.f;
-  bool upk[RPT];
-  int lb[RPT];
-#pragma unroll
-  for (int k = 0; k < RPT; ++k) {
-    rr[k] = __ldg(ref_t + min((chunk * 32 + lane) * RPT + k, R - 1));
-    upk[k] = false;
-  }
-  multi_bound<RPT>(sd, n, rr, upk, lb);
-#pragma unroll
-  for (int k = 0; k < RPT; ++k) {
-    const int r = (chunk * 32 + lane) * RPT + k;
-    const bool live = r < R;
-    const int rc = min(r, R - 1);
-    const float dst = nearest_delta(sd, n, lb[k], rr[k]);
-    nhi[k] = dst * dst;
-    nlo[k] = -na * fmaf(dst, dst, -nhi[k]);
-    nmax = fmaxf(nmax, nhi[k]);
-    yy[k] = ub[(0 * C + c) * R + rc];
-    yy10[k] = ub[(2 * C + c) * R + rc];
-    const float gy = live ? gb[(0 * C + c) * R + rc] : 0.f;
-    const float gw = live ? gb[(1 * C + c) * R + rc] : 0.f;
-    const float gy10 = live ? gb[(2 * C + c) * R + rc] : 0.f;
-    const float i1 = 1.0f / sb[(0 * C + c) * R + rc];
-    const float i10 = 10.0f / sb[(1 * C + c) * R + rc];
-    A[k] = gy * i1;
-    Bc[k] = gw * i1;
-    A10[k] = gy10 * i10;
-    acc[k] = 0.f;
-  }
-  const Window2 w = make_window2(sd, n, rr[0], rr[RPT - 1], sqrtf(nmax + kCut / a),
-                                 sqrtf(nmax + kCut / (10.f * a)), WEIGHTED);
-  const int n4 = (n + 3) & ~3;
-  const float na10 = 10.f * na;
-  float nlo10[RPT];
-#pragma unroll
-  for (int k = 0; k < RPT; ++k) nlo10[k] = 10.f * nlo[k];
+// Backward: d alpha_c = - sum_r [ gy U1 + gw U0 + gy' U1' ] from the moment rows the forward pass saved
+// (see sci_fwd_task): one read of stats and grad_u, no second sweep over the observations.  One warp per
+// encounter, lanes stride over the grid points of each vital (coalesced rows), fixed-order shuffle reduction.
+constexpr int kSciBwdWarps = 8;
 
-  // HIGH = false: the low-pass / intensity terms over the outer window; HIGH = true: the high-pass term over
-  // the inner window (exponent x 10, same shift).  One MUFU.EX2 per pair in either loop.
-  auto body = [&](int t, auto high) {
-    constexpr bool HIGH = decltype(high)::value;
-    const bool in_row = (unsigned)t < (unsigned)n4;
-    const float4 d4 = *reinterpret_cast<const float4*>(in_row ? sd + t : nullc);
-    const float4 x4 = *reinterpret_cast<const float4*>(in_row ? sx + t : nullc + 4);
-    const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
-    const float xx[4] = {x4.x, x4.y, x4.z, x4.w};
-    float mm[4] = {1.f, 1.f, 1.f, 1.f};
-    if (WEIGHTED) {
-      const float4 m4 = *reinterpret_cast<const float4*>(sm + t);
-      mm[0] = m4.x; mm[1] = m4.y; mm[2] = m4.z; mm[3] = m4.w;
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-#pragma unroll
-      for (int k = 0; k < RPT; ++k) {
-        const float dl = dd[j] - rr[k];
-        const float e = ex2_approx(fmaf(fmaf(dl, dl, -nhi[k]), HIGH ? na10 : na, HIGH ? nlo10[k] : nlo[k]));
-        float h = HIGH ? e * ((xx[j] - yy10[k]) * A10[k]) : e * fmaf(xx[j] - yy[k], A[k], Bc[k]);
-        if (WEIGHTED) h *= mm[j];
-        acc[k] = fmaf(dl * dl, h, acc[k]);                    // n_tr = (d_t - r)^2
+__global__ void __launch_bounds__(kSciBwdWarps * 32)
+sci_bwd_kernel(const float* __restrict__ stats, const float* __restrict__ grad_u, float* __restrict__ partial,
+               int64_t B, int C, int R) {
+  const int lane = threadIdx.x & 31;
+  const int64_t b = (int64_t)blockIdx.x * kSciBwdWarps + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const float* sb = stats + b * (int64_t)(3 * C) * R;
+  const float* gb = grad_u + b * (int64_t)(3 * C) * R;
+  for (int c = 0; c < C; ++c) {
+    float acc = 0.f;
+    for (int r = lane; r < R; r += 32) {
+      const float u0 = __ldg(sb + (1 * C + c) * R + r);
+      if (u0 >= 0.f) {      // an all-masked vital contributes nothing (its upstream gradients may be NaN)
+        acc = fmaf(__ldg(gb + (0 * C + c) * R + r), __ldg(sb + (0 * C + c) * R + r), acc);
+        acc = fmaf(__ldg(gb + (1 * C + c) * R + r), u0, acc);
+        acc = fmaf(__ldg(gb + (2 * C + c) * R + r), __ldg(sb + (2 * C + c) * R + r), acc);
       }
     }
-  };
-  for (int t0 = 0; t0 < w.ot; t0 += 4) body(w.ob + t0, std::false_type{});
-  for (int t0 = 0; t0 < w.it; t0 += 4) body(w.ib + t0, std::true_type{});
-
-  float tot = 0.f;
-#pragma unroll
-  for (int k = 0; k < RPT; ++k) tot += acc[k];
-  return warp_sum(tot);
-}
-
-// 4 x 256 threads per SM => <= 64 registers: 10 resident CTAs of 3 warps at c2 (measured: 27.7 -> 26.8 ms;
-// a 56-register build for 12 CTAs was not faster)
-template <int RPT>
-__global__ void __launch_bounds__(kMaxWarps * 32, 4)
-sci_bwd_kernel(const float* __restrict__ x, const float* __restrict__ kernel,
-               const float* __restrict__ ref_t, const float* __restrict__ u,
-               const float* __restrict__ stats, const float* __restrict__ grad_u,
-               float* __restrict__ partial, int C, int T, int Tp, int R, int use_tma, int64_t x_stride) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  const SciSmem s = sci_carve(smem_raw, C, Tp);
-  const int64_t b = blockIdx.x;
-  sci_stage(s, x + b * x_stride, C, T, Tp, use_tma != 0, /*fold_mask=*/false);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  const int chunks = (R + 32 * RPT - 1) / (32 * RPT);
-  const int ntasks = C * chunks;
-  const float* ub = u + b * (int64_t)(3 * C) * R;
-  const float* gb = grad_u + b * (int64_t)(3 * C) * R;
-  const float* sb = stats + b * (int64_t)(2 * C) * R;
-
-  for (int round = 0;; ++round) {
-    const int task = snake_task(round, warp, nwarps);
-    if (round * nwarps >= ntasks) break;
-    if (task >= ntasks) continue;
-    const int c = s.order[task / chunks], chunk = task % chunks;
-    const float* sx = s.rows + (0 * C + c) * Tp;
-    const float* sm = s.rows + (1 * C + c) * Tp;
-    const float* sd = s.rows + (2 * C + c) * Tp;
-    const int nv = s.n_valid[c];
-    float tot = 0.f;
-    if (nv != 0) {   // an all-masked channel contributes nothing (the reference's grad is NaN there)
-      const float a = softplus_ref(__ldg(kernel + c)) * kLog2e;
-      tot = nv < 0 ? sci_bwd_task<RPT, true>(sx, sm, sd, -nv, a, chunk, lane, c, C, R, ref_t, ub, gb, sb, s.nullc)
-                   : sci_bwd_task<RPT, false>(sx, sm, sd, nv, a, chunk, lane, c, C, R, ref_t, ub, gb, sb, s.nullc);
-    }
-    if (lane == 0) s.part[c * chunks + chunk] = tot;
-  }
-  __syncthreads();
-  // chunks of one vital are summed in a fixed order -> deterministic partials
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float t = 0.f;
-    for (int k = 0; k < chunks; ++k) t += s.part[c * chunks + k];
-    partial[b * C + c] = -t;
+    acc = warp_sum(acc);
+    if (lane == 0) partial[b * C + c] = -acc;
   }
 }
 
@@ -430,14 +359,17 @@ extern "C" int dic_sci_fwd(const float* x, const float* kernel, const float* ref
   const int rpt = pick_rpt(R);
   const int threads = 32 * pick_warps(C, R, rpt);
   cudaStream_t st = as_stream(stream);
-#define DIC_SCI_FWD(RPT_)                                                                   \
-  {                                                                                         \
-    rc = prepare(sci_fwd_kernel<RPT_>, smem);                                               \
-    if (rc) return rc;                                                                      \
-    sci_fwd_kernel<RPT_><<<(unsigned)B, threads, smem, st>>>(x, kernel, ref_t, u, stats, C, \
-                                                              T, Tp, R, use_tma, x_stride); \
+#define DIC_SCI_FWD_(RPT_, MOM_)                                                                        \
+  {                                                                                                     \
+    rc = prepare(sci_fwd_kernel<RPT_, MOM_>, smem);                                                     \
+    if (rc) return rc;                                                                                  \
+    sci_fwd_kernel<RPT_, MOM_><<<(unsigned)B, threads, smem, st>>>(x, kernel, ref_t, u, stats, C, T, Tp, \
+                                                                    R, use_tma, x_stride);              \
   }
-  if (rpt == 1) DIC_SCI_FWD(1) else if (rpt == 2) DIC_SCI_FWD(2) else DIC_SCI_FWD(3)
+#define DIC_SCI_FWD(RPT_) \
+  if (stats) DIC_SCI_FWD_(RPT_, true) else DIC_SCI_FWD_(RPT_, false)
+  if (rpt == 1) { DIC_SCI_FWD(1) } else if (rpt == 2) { DIC_SCI_FWD(2) } else { DIC_SCI_FWD(3) }
+#undef DIC_SCI_FWD_
 #undef DIC_SCI_FWD
   DIC_LAUNCH_CHECK("sci_fwd_kernel");
   return DIC_OK;
@@ -453,36 +385,25 @@ extern "C" int dic_sci_bwd(const float* x, const float* kernel, const float* ref
                            const float* stats, const float* grad_u, float* d_kernel,
                            void* workspace, int64_t B, int C, int T, int R, int64_t x_stride,
                            dic_stream_t stream) {
-  int rc = check_common(x, kernel, ref_t, B, C, T, R, x_stride);
-  if (rc) return rc;
-  DIC_REQUIRE(((u && stats && grad_u && workspace) || B == 0) && d_kernel, DIC_ERR_INVALID_ARGUMENT,
-              "null pointer argument");
+  // x, ref_t and u are part of the signature for symmetry with dic_sci_fwd; the gradient is a function of the
+  // saved moment rows and the upstream gradient alone, so they are not read (and may be NULL)
+  (void)x; (void)ref_t; (void)u; (void)x_stride;
+  DIC_REQUIRE(kernel && d_kernel, DIC_ERR_INVALID_ARGUMENT, "null pointer argument");
+  DIC_REQUIRE(B >= 0 && C > 0 && T > 0 && R > 0, DIC_ERR_INVALID_ARGUMENT, "bad sizes B=%lld C=%d T=%d R=%d",
+              (long long)B, C, T, R);
+  DIC_REQUIRE((stats && grad_u && workspace) || B == 0, DIC_ERR_INVALID_ARGUMENT, "null pointer argument");
   cudaStream_t st = as_stream(stream);
   if (B == 0) {
     DIC_CUDA(cudaMemsetAsync(d_kernel, 0, sizeof(float) * C, st));
     return DIC_OK;
   }
-  const int Tp = round_up(T, 4);
-  const size_t smem = sci_smem_bytes(C, Tp, R);
-  const int use_tma = (Tp == T) && aligned16(x) && ((3LL * C * T * 4) % 16 == 0) &&
-                      ((x_stride * 4) % 16 == 0);
-  const int rpt = pick_rpt(R);
-  const int threads = 32 * pick_warps(C, R, rpt);
   unsigned char* ws = static_cast<unsigned char*>(workspace);
   float* partial = reinterpret_cast<float*>(ws);
   size_t off = ((size_t)B * C * sizeof(float) + 255) / 256 * 256;
   double* red = reinterpret_cast<double*>(ws + off);
   float* sig = reinterpret_cast<float*>(ws + off + (size_t)kColsumBlocks * C * sizeof(double));
-#define DIC_SCI_BWD(RPT_)                                                                      \
-  {                                                                                            \
-    rc = prepare(sci_bwd_kernel<RPT_>, smem);                                                  \
-    if (rc) return rc;                                                                         \
-    sci_bwd_kernel<RPT_><<<(unsigned)B, threads, smem, st>>>(x, kernel, ref_t, u, stats,       \
-                                                              grad_u, partial, C, T, Tp, R,    \
-                                                              use_tma, x_stride);              \
-  }
-  if (rpt == 1) DIC_SCI_BWD(1) else if (rpt == 2) DIC_SCI_BWD(2) else DIC_SCI_BWD(3)
-#undef DIC_SCI_BWD
+  sci_bwd_kernel<<<(unsigned)((B + kSciBwdWarps - 1) / kSciBwdWarps), kSciBwdWarps * 32, 0, st>>>(stats, grad_u, partial,
+                                                                                                  B, C, R);
   DIC_LAUNCH_CHECK("sci_bwd_kernel");
   sigmoid_vec_kernel<<<(C + 127) / 128, 128, 0, st>>>(kernel, sig, C);
   DIC_LAUNCH_CHECK("sigmoid_vec_kernel");

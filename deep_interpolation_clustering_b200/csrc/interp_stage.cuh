@@ -241,6 +241,14 @@ __device__ __forceinline__ float nearest_delta(const float* key, int n, int lb, 
   return (-below <= above) ? below : above;
 }
 
+// Index of the observation nearest to r, given lb = #{i : key[i] < r} in sorted key[0..n), n >= 1 (ties: the earlier).
+__device__ __forceinline__ int nearest_index(const float* key, int n, int lb, float r) {
+  const int ib = max(lb, 1) - 1, ia = min(lb, n - 1);
+  if (lb == 0) return ia;
+  if (lb == n) return ib;
+  return (r - key[ib] <= key[ia] - r) ? ib : ia;
+}
+
 // Index of the key nearest to r in sorted key[0..n), n >= 1.
 __device__ __forceinline__ int nearest_sorted(const float* key, int n, float r) {
   int lo = 0, hi = n;

@@ -76,7 +76,7 @@ class _SCI(torch.autograd.Function):
         need_grad = ctx.needs_input_grad[1]      # grad mode is off inside forward; ask the ctx
         with torch.cuda.device(x.device):
             u = torch.empty((B, 3 * C, R), dtype=torch.float32, device=x.device)
-            stats = torch.empty((B, 2 * C, R), dtype=torch.float32, device=x.device) if need_grad else None
+            stats = torch.empty((B, 3 * C, R), dtype=torch.float32, device=x.device) if need_grad else None
             _lib.check(_lib.lib().dic_sci_fwd(_lib.ptr(x), _lib.ptr(kernel), _lib.ptr(ref_t), _lib.ptr(u),
                                               _lib.ptr(stats), B, C, T, R, xs, _lib.current_stream(x.device)),
                        "dic_sci_fwd")

@@ -62,8 +62,9 @@ int dic_device_info(int* sm_count, int* cc_major, int* cc_minor);
  *   kernel (C)  raw parameter; alpha = log(1+exp(kernel)) is applied inside (:51)
  *   ref_t  (R)  reference grid, torch.linspace(0, H, R) (:41)
  *   u      (B,3C,R) out
- *   stats  (B,2C,R) out, may be NULL: shifted partition sums [sum e | sum e^10] that the
- *          backward pass re-uses (saved-for-backward state, 8CR bytes per encounter)
+ *   stats  (B,3C,R) out, may be NULL: the three gradient-moment rows [U1 | U0 | U1'] from which
+ *          dic_sci_bwd forms d kernel without a second sweep over the observations (saved-for-backward
+ *          state, 12CR bytes per encounter; U0 < 0 marks an all-masked vital)
  * Limits: 12*C*round_up(T,4) + 64 bytes of shared memory <= 227 KB.
  */
 int dic_sci_fwd(const float* x, const float* kernel, const float* ref_t, float* u, float* stats,
@@ -74,7 +75,8 @@ size_t dic_interp_bwd_workspace_bytes(int64_t B, int C);
 
 /* Gradient of dic_sci_fwd wrt `kernel` (what autograd produces for
  * interpolation_layer.py:51-83).  grad_u (B,3C,R) is the upstream gradient in planar
- * layout.  No input gradient is produced.
+ * layout.  No input gradient is produced.  Only kernel, stats and grad_u are
+ * read: d alpha_c = - sum_{b,r} (gy U1 + gw U0 + gy' U1'); x, ref_t and u may be NULL.
  *   d_kernel (C) out (overwritten, deterministic two-stage reduction)
  */
 int dic_sci_bwd(const float* x, const float* kernel, const float* ref_t, const float* u,
