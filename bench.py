@@ -363,7 +363,7 @@ def device_arm(args, rank, world, local_rank):
                     "note": "algorithmic exps = 2 per (valid obs, ref point) for SCI (low+high pass), 1 for RBF; "
                             "the kernels skip pairs whose weight is below 2^-27..2^-30 of the largest and evaluate the "
                             "high-pass exponential only inside its narrow window, so frac may exceed 1 (ncu: issue "
-                            "slots 80-92 % busy, XU pipe 48-64 %, FMA pipe 47-53 %)"}
+                            "slots 82-90 % busy, XU pipe 46-65 %, FMA pipe 47-54 %)"}
 
     line = {
         "metric": "encounters/s (interp fwd+bwd + DEC assign)", "value": round(value, 1), "unit": "encounters/s",
