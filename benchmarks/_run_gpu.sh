@@ -1,4 +1,3 @@
-mkdir -p gpurun_out
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus 8 --steps 3 --warmup 3 > gpurun_out/bench_N8.json 2> gpurun_out/bench_N8.err; echo "exit $?" >> gpurun_out/bench_N8.err
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29542 bench.py --gpus 4 --steps 3 --warmup 3 --no-e2e > gpurun_out/bench_N4.json 2> gpurun_out/bench_N4.err; echo "exit $?" >> gpurun_out/bench_N4.err
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29543 bench.py --gpus 2 --steps 3 --warmup 3 > gpurun_out/bench_N2.json 2> gpurun_out/bench_N2.err; echo "exit $?" >> gpurun_out/bench_N2.err
+mkdir -p gpurun_out; rm -f gpurun_out/parity_report.jsonl
+timeout 300 python -m pytest tests/test_gpu_interp.py -m gpu -q --timeout 100 > gpurun_out/pytest_interp.log 2>&1; echo "exit $?" >> gpurun_out/pytest_interp.log
+timeout 300 python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/bench16.json 2> gpurun_out/bench16.err; echo "exit $?" >> gpurun_out/bench16.err

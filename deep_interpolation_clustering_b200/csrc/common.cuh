@@ -55,6 +55,40 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// ---- packed float32 x 2 arithmetic (sm_100: FFMA2 / FADD2 / FMUL2) ---------------------------------------
+// One instruction issues two float32 operations on an aligned register pair.  The FMA pipe does not get wider
+// (measured: 32 TFMA/s either way, benchmarks/probes/ffma2_probe.cu) but the sweep loops are ISSUE bound with
+// the FMA pipe ~50 % busy, so halving the issue slots of their arithmetic is what moves them.
+typedef unsigned long long f2_t;     // .x in the low word, .y in the high word
+__device__ __forceinline__ f2_t pack2(float lo, float hi) {
+  f2_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f2_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f2_t fma2(f2_t a, f2_t b, f2_t c) {
+  f2_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f2_t add2(f2_t a, f2_t b) {
+  f2_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f2_t mul2(f2_t a, f2_t b) {
+  f2_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ float sum2(f2_t v) {
+  float lo, hi;
+  unpack2(v, lo, hi);
+  return lo + hi;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -368,7 +368,7 @@ rbf_bwd_kernel(const float* __restrict__ v, const float* __restrict__ x,
       const float m = ra[t];
       const float gi = __ldg(gb + c * T + t) * __ldg(nb + c * T + t) * m;
       ra[t] = gi * m;
-      ras[t] = gi * __ldg(rb + c * T + t);
+      ras[t] = -gi * __ldg(rb + c * T + t);              // stored NEGATED: the loop forms a' v - a'S with one FMA
     }
     __syncwarp();
     if (n < 0) {   // general rows: keep entries that carry gradient (a' != 0), sort by time
@@ -434,27 +434,40 @@ rbf_bwd_kernel(const float* __restrict__ v, const float* __restrict__ x,
       wbase = pos[0] & ~3;
       wtrip = (warp_max_i(pos[1] - wbase) + 3) & ~3;
     }
+    // packed float32x2 over pairs of consecutive observations (two aligned register pairs per 128-bit load)
+    f2_t nrr2[RPT], vv2[RPT], dv2[RPT], acc2[RPT];
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) {
+      nrr2[k] = pack2(-rr[k], -rr[k]);
+      vv2[k] = pack2(vv[k], vv[k]);
+      dv2[k] = acc2[k] = pack2(0.f, 0.f);
+    }
     for (int t0 = 0; t0 < wtrip; t0 += 4) {
       const int t = wbase + t0;
       if ((unsigned)t >= (unsigned)n4) continue;        // chunk off the row (lane at an end of the record)
-      const float4 d4 = *reinterpret_cast<const float4*>(rd + t);
-      const float4 a4 = *reinterpret_cast<const float4*>(ra + t);
-      const float4 s4 = *reinterpret_cast<const float4*>(ras + t);
-      const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
-      const float aa[4] = {a4.x, a4.y, a4.z, a4.w};
-      const float as[4] = {s4.x, s4.y, s4.z, s4.w};
+      const ulonglong2 d4 = *reinterpret_cast<const ulonglong2*>(rd + t);
+      const ulonglong2 a4 = *reinterpret_cast<const ulonglong2*>(ra + t);
+      const ulonglong2 s4 = *reinterpret_cast<const ulonglong2*>(ras + t);      // -a'S
+      const f2_t dd[2] = {d4.x, d4.y}, aa[2] = {a4.x, a4.y}, ns[2] = {s4.x, s4.y};
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < 2; ++j) {
 #pragma unroll
         for (int k = 0; k < RPT; ++k) {
-          const float dl = dd[j] - rr[k];
-          const float arg = -(dl * dl);                         // = -beta log2(e) (d - r)^2
-          const float e = ex2_approx(arg);
-          dv[k] = fmaf(e, aa[j], dv[k]);
-          const float tt = fmaf(aa[j], vv[k], -as[j]);
-          acc[k] = fmaf(e * arg, tt, acc[k]);                   // sum of -b2 n e (...): rescaled below
+          const f2_t dl = add2(dd[j], nrr2[k]);
+          const f2_t n2 = mul2(dl, dl);                          // beta log2(e) (d - r)^2
+          float n0, n1;
+          unpack2(n2, n0, n1);
+          const f2_t e = pack2(ex2_approx(-n0), ex2_approx(-n1));
+          dv2[k] = fma2(e, aa[j], dv2[k]);
+          const f2_t tt = fma2(aa[j], vv2[k], ns[j]);
+          acc2[k] = fma2(mul2(e, n2), tt, acc2[k]);              // sum of +b2 n e (...): rescaled below
         }
       }
+    }
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) {
+      dv[k] = sum2(dv2[k]);
+      acc[k] = sum2(acc2[k]);
     }
     float tot = 0.f;
 #pragma unroll
@@ -464,7 +477,7 @@ rbf_bwd_kernel(const float* __restrict__ v, const float* __restrict__ x,
         tot += acc[k];
       }
     }
-    tot = warp_sum(tot) * (-1.0f / b2);                        // back to sum n e (a' v - a'S)
+    tot = warp_sum(tot) * (1.0f / b2);                         // back to sum n e (a' v - a'S)
     if (lane == 0) s.part[c * chunks + chunk] = tot;
   }
   __syncthreads();

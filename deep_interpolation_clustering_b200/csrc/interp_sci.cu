@@ -152,45 +152,60 @@ __device__ __forceinline__ void sci_fwd_task(const float* __restrict__ sx, const
 
   // One filter: HIGH = false walks the outer window with exponent -a t, HIGH = true the inner window with -10 a t
   // (same shift).  One MUFU.EX2 per pair.
+  // Packed float32x2 arithmetic over pairs of consecutive observations (two aligned register pairs per 128-bit
+  // load): the loop is issue bound, and FFMA2 / FADD2 / FMUL2 halve the issue slots of its arithmetic.
   auto filter = [&](auto high, float (&S)[RPT], float (&SC)[RPT], float (&Q0)[RPT], float (&Q1)[RPT]) {
     constexpr bool HIGH = decltype(high)::value;
     const float nak = HIGH ? 10.f * na : na;
-    float nlk[RPT];
+    const f2_t nak2 = pack2(nak, nak);
+    f2_t nrr2[RPT], nnhi2[RPT], nlk2[RPT], S2[RPT], SC2[RPT], Q02[RPT], Q12[RPT];
 #pragma unroll
     for (int k = 0; k < RPT; ++k) {
-      nlk[k] = HIGH ? 10.f * nlo[k] : nlo[k];
-      S[k] = SC[k] = Q0[k] = Q1[k] = 0.f;
+      const float nl = HIGH ? 10.f * nlo[k] : nlo[k];
+      nrr2[k] = pack2(-rr[k], -rr[k]);
+      nnhi2[k] = pack2(-nhi[k], -nhi[k]);
+      nlk2[k] = pack2(nl, nl);
+      S2[k] = SC2[k] = Q02[k] = Q12[k] = pack2(0.f, 0.f);
     }
     const int base = HIGH ? w.ib : w.ob, trip = HIGH ? w.it : w.ot;
     for (int t0 = 0; t0 < trip; t0 += 4) {
       const int t = base + t0;
       const bool in_row = (unsigned)t < (unsigned)n4;           // chunks off the row weigh nothing
-      const float4 d4 = *reinterpret_cast<const float4*>(in_row ? sd + t : nullc);
-      const float4 x4 = *reinterpret_cast<const float4*>(in_row ? sx + t : nullc + 4);
-      const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
-      const float xx[4] = {x4.x, x4.y, x4.z, x4.w};
-      float mm[4] = {1.f, 1.f, 1.f, 1.f};
+      const ulonglong2 d4 = *reinterpret_cast<const ulonglong2*>(in_row ? sd + t : nullc);
+      const ulonglong2 x4 = *reinterpret_cast<const ulonglong2*>(in_row ? sx + t : nullc + 4);
+      const f2_t dd[2] = {d4.x, d4.y}, xx[2] = {x4.x, x4.y};
+      f2_t mm[2] = {0, 0};
       if (WEIGHTED) {
-        const float4 m4 = *reinterpret_cast<const float4*>(sm + t);   // full range: always in the row
-        mm[0] = m4.x; mm[1] = m4.y; mm[2] = m4.z; mm[3] = m4.w;
+        const ulonglong2 m4 = *reinterpret_cast<const ulonglong2*>(sm + t);   // full range: always in the row
+        mm[0] = m4.x; mm[1] = m4.y;
       }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < 2; ++j) {
 #pragma unroll
         for (int k = 0; k < RPT; ++k) {
-          const float dl = dd[j] - rr[k];
-          const float t1 = fmaf(dl, dl, -nhi[k]);              // (d-r)^2 - (d*-r)^2, rounded once
-          const float e = ex2_approx(fmaf(t1, nak, nlk[k]));   // the residual of the shift rides in the FMA
+          const f2_t dl = add2(dd[j], nrr2[k]);
+          const f2_t t1 = fma2(dl, dl, nnhi2[k]);                // (d-r)^2 - (d*-r)^2, rounded once
+          const f2_t arg = fma2(t1, nak2, nlk2[k]);              // the residual of the shift rides in the FMA
+          float a0, a1;
+          unpack2(arg, a0, a1);
+          const f2_t e = pack2(ex2_approx(a0), ex2_approx(a1));
           // rows with fractional weights hold x m, and the weight of the pair is m e
-          S[k] = WEIGHTED ? fmaf(mm[j], e, S[k]) : S[k] + e;
-          SC[k] = fmaf(e, xx[j], SC[k]);
+          S2[k] = WEIGHTED ? fma2(mm[j], e, S2[k]) : add2(S2[k], e);
+          SC2[k] = fma2(e, xx[j], SC2[k]);
           if (MOM) {
-            const float te = t1 * e;
-            Q0[k] = WEIGHTED ? fmaf(mm[j], te, Q0[k]) : Q0[k] + te;
-            Q1[k] = fmaf(te, xx[j], Q1[k]);
+            const f2_t te = mul2(t1, e);
+            Q02[k] = WEIGHTED ? fma2(mm[j], te, Q02[k]) : add2(Q02[k], te);
+            Q12[k] = fma2(te, xx[j], Q12[k]);
           }
         }
       }
+    }
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) {
+      S[k] = sum2(S2[k]);
+      SC[k] = sum2(SC2[k]);
+      Q0[k] = MOM ? sum2(Q02[k]) : 0.f;
+      Q1[k] = MOM ? sum2(Q12[k]) : 0.f;
     }
   };
 
@@ -221,7 +236,7 @@ __device__ __forceinline__ void sci_fwd_task(const float* __restrict__ sx, const
 
 // MOM: also produce the three gradient-moment rows (stats (B, 3C, R) = [U1 | U0 | U1']) for dic_sci_bwd.
 template <int RPT, bool MOM>
-__global__ void __launch_bounds__(kMaxWarps * 32)
+__global__ void __launch_bounds__(kMaxWarps * 32)          // (a 64-register cap spills and measures slower)
 sci_fwd_kernel(const float* __restrict__ x, const float* __restrict__ kernel,
                const float* __restrict__ ref_t, float* __restrict__ u, float* __restrict__ stats,
                int C, int T, int Tp, int R, int use_tma, int64_t x_stride) {
