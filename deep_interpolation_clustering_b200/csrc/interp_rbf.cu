@@ -242,9 +242,13 @@ rbf_fwd2_kernel(const float* __restrict__ v, const float* __restrict__ x, const 
 
   const float* smask = s.planes;
   const float* stime = s.planes + C * Tp;
-  for (int i = tid; i < C * Rp; i += blockDim.x) {             // (s_c r_j, v_cj) rows
-    const int c = i / Rp, j = i - c * Rp;
-    s.srv[i] = j < R ? make_float2(__ldg(ref_t + j) * s.ssc[c], s.sv[c * R + j]) : make_float2(3.0e18f, 0.f);
+  // rows of (-s_c r_j, -s_c r_j+1, v_cj, v_cj+1) per pair of grid points: two aligned register pairs per 128-bit
+  // load for the packed float32x2 loop below; a pad point sits at -(3e18 s) with value 0 => weight exactly 0
+  for (int i = tid; i < C * (Rp / 2); i += blockDim.x) {
+    const int c = i / (Rp / 2), j = 2 * (i - c * (Rp / 2));
+    const float sc = s.ssc[c];
+    const float ra = -__ldg(ref_t + j) * sc, rb2 = j + 1 < R ? -__ldg(ref_t + j + 1) * sc : -3.0e18f * sc;
+    reinterpret_cast<float4*>(s.srv)[i] = make_float4(ra, rb2, s.sv[c * R + j], j + 1 < R ? s.sv[c * R + j + 1] : 0.f);
   }
   for (int c = warp; c < C; c += kRbfFwd2Warps) {              // prefix masks: visit [0, n) and zero the tail
     const float* mrow = smask + c * Tp;
@@ -290,18 +294,21 @@ rbf_fwd2_kernel(const float* __restrict__ v, const float* __restrict__ x, const 
     if (__any_sync(0xffffffffu, wide && live && m != 0.f)) trip = Rp;      // rare: the whole row for this task
     const int jlo = trip == Rp ? 0
                                : min(max(0, (__float2int_rd((d - r0) * inv_h) - (trip >> 1) + 1) & ~1), Rp - trip);
-    float N = 0.f, S = 0.f;
-    const float2* rw = s.srv + c * Rp + jlo;
+    f2_t N2 = pack2(0.f, 0.f), S2 = N2;
+    const f2_t ds2 = pack2(ds, ds);
+    const ulonglong2* rw = reinterpret_cast<const ulonglong2*>(s.srv) + c * (Rp / 2) + (jlo >> 1);
 #pragma unroll 4
-    for (int j = 0; j < trip; j += 2) {
-      const float4 p = *reinterpret_cast<const float4*>(rw + j);   // (s r0, v0, s r1, v1)
-      const float d0 = ds - p.x, d1 = ds - p.z;
-      const float e0 = ex2_approx(-(d0 * d0)), e1 = ex2_approx(-(d1 * d1));
-      N += e0;
-      S = fmaf(e0, p.y, S);
-      N += e1;
-      S = fmaf(e1, p.w, S);
+    for (int j = 0; j < (trip >> 1); ++j) {
+      const ulonglong2 p = rw[j];                                  // (-s r0, -s r1) | (v0, v1)
+      const f2_t dl = add2(ds2, p.x);
+      const f2_t n2 = mul2(dl, dl);
+      float n0, n1;
+      unpack2(n2, n0, n1);
+      const f2_t e = pack2(ex2_approx(-n0), ex2_approx(-n1));
+      N2 = add2(N2, e);
+      S2 = fma2(e, p.y, S2);
     }
+    const float N = sum2(N2), S = sum2(S2);
     if (live) {
       // phi = m e  =>  N_ref = m N, sum phi v = m S; a masked slot of a general row reconstructs to 0
       const float inv = m != 0.f ? __frcp_rn(fmaf(m, N, 1e-10f)) : 0.f;
