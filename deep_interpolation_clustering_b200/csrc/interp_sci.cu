@@ -168,6 +168,7 @@ __device__ __forceinline__ void sci_fwd_task(const float* __restrict__ sx, const
       S2[k] = SC2[k] = Q02[k] = Q12[k] = pack2(0.f, 0.f);
     }
     const int base = HIGH ? w.ib : w.ob, trip = HIGH ? w.it : w.ot;
+#pragma unroll 2
     for (int t0 = 0; t0 < trip; t0 += 4) {
       const int t = base + t0;
       const bool in_row = (unsigned)t < (unsigned)n4;           // chunks off the row weigh nothing
