@@ -363,7 +363,8 @@ def device_arm(args, rank, world, local_rank):
                     "note": "algorithmic exps = 2 per (valid obs, ref point) for SCI (low+high pass), 1 for RBF; "
                             "the kernels skip pairs whose weight is below 2^-27..2^-30 of the largest and evaluate the "
                             "high-pass exponential only inside its narrow window, so frac may exceed 1 (ncu: issue "
-                            "slots 82-90 % busy, XU pipe 46-65 %, FMA pipe 47-54 %)"}
+                            "slots 65-82 % busy, XU pipe 49-69 %, FMA pipe 52 %; on EXECUTED exponentials the sweeps run at ~52 % of "
+                            "the MUFU peak)"}
 
     line = {
         "metric": "encounters/s (interp fwd+bwd + DEC assign)", "value": round(value, 1), "unit": "encounters/s",
