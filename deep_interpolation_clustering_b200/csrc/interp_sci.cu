@@ -293,12 +293,33 @@ constexpr int kSciBwdWarps = 8;
 
 __global__ void __launch_bounds__(kSciBwdWarps * 32)
 sci_bwd_kernel(const float* __restrict__ stats, const float* __restrict__ grad_u, float* __restrict__ partial,
-               int64_t B, int C, int R) {
+               int64_t B, int C, int R, int vec4) {
   const int lane = threadIdx.x & 31;
   const int64_t b = (int64_t)blockIdx.x * kSciBwdWarps + (threadIdx.x >> 5);
   if (b >= B) return;
   const float* sb = stats + b * (int64_t)(3 * C) * R;
   const float* gb = grad_u + b * (int64_t)(3 * C) * R;
+  if (vec4) {      // R % 4 == 0 and 16-byte aligned bases: 128-bit loads, all six rows of a vital in flight at once
+    const int R4 = R >> 2;
+    for (int c = 0; c < C; ++c) {
+      float acc = 0.f;
+      for (int i = lane; i < R4; i += 32) {
+        const float4 u1 = __ldg(reinterpret_cast<const float4*>(sb + (0 * C + c) * R) + i);
+        const float4 u0 = __ldg(reinterpret_cast<const float4*>(sb + (1 * C + c) * R) + i);
+        const float4 u2 = __ldg(reinterpret_cast<const float4*>(sb + (2 * C + c) * R) + i);
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gb + (0 * C + c) * R) + i);
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gb + (1 * C + c) * R) + i);
+        const float4 g2 = __ldg(reinterpret_cast<const float4*>(gb + (2 * C + c) * R) + i);
+        if (u0.x >= 0.f) acc = fmaf(g0.x, u1.x, fmaf(g1.x, u0.x, fmaf(g2.x, u2.x, acc)));
+        if (u0.y >= 0.f) acc = fmaf(g0.y, u1.y, fmaf(g1.y, u0.y, fmaf(g2.y, u2.y, acc)));
+        if (u0.z >= 0.f) acc = fmaf(g0.z, u1.z, fmaf(g1.z, u0.z, fmaf(g2.z, u2.z, acc)));
+        if (u0.w >= 0.f) acc = fmaf(g0.w, u1.w, fmaf(g1.w, u0.w, fmaf(g2.w, u2.w, acc)));
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) partial[b * C + c] = -acc;
+    }
+    return;
+  }
   for (int c = 0; c < C; ++c) {
     float acc = 0.f;
     for (int r = lane; r < R; r += 32) {
@@ -418,8 +439,9 @@ extern "C" int dic_sci_bwd(const float* x, const float* kernel, const float* ref
   size_t off = ((size_t)B * C * sizeof(float) + 255) / 256 * 256;
   double* red = reinterpret_cast<double*>(ws + off);
   float* sig = reinterpret_cast<float*>(ws + off + (size_t)kColsumBlocks * C * sizeof(double));
+  const int vec4 = (R % 4 == 0) && aligned16(stats) && aligned16(grad_u);
   sci_bwd_kernel<<<(unsigned)((B + kSciBwdWarps - 1) / kSciBwdWarps), kSciBwdWarps * 32, 0, st>>>(stats, grad_u, partial,
-                                                                                                  B, C, R);
+                                                                                                  B, C, R, vec4);
   DIC_LAUNCH_CHECK("sci_bwd_kernel");
   sigmoid_vec_kernel<<<(C + 127) / 128, 128, 0, st>>>(kernel, sig, C);
   DIC_LAUNCH_CHECK("sigmoid_vec_kernel");
