@@ -354,3 +354,29 @@ def test_shape_sweep_vs_oracle(B, C, T, R):
     _check(f"{tag}/d_sci_kernel", sci.kernel.grad, dks64)
     _check(f"{tag}/dv", v.grad, dv64)
     _check(f"{tag}/d_rbf_kernel", rbf.kernel.grad, dkr64)
+
+
+def test_allmasked_vital_contributes_zero_gradient(golden):
+    """Backward with a finite upstream gradient: an all-masked vital (NaN / -inf outputs, the reference's gradient is
+    NaN there) contributes exactly nothing to d kernel; the other vitals match the float64 oracle."""
+    from deep_interpolation_clustering_b200 import functional as F_
+    from oracle import interp_oracle as O
+    g = golden("interp_allmasked")
+    dev = torch.device("cuda:0")
+    xn = g["x"]
+    C, R, H = xn.shape[1] // 4, int(g["R"]), float(g["hours"])
+    masked = [(b, c) for b in range(xn.shape[0]) for c in range(C) if xn[b, C + c].sum() == 0]
+    assert masked, "fixture must contain an all-masked vital"
+    k = torch.tensor(g["sci_kernel"], device=dev, requires_grad=True)
+    rt = torch.linspace(0, H, R).to(dev)
+    u = F_.sci(torch.tensor(xn, device=dev), k, rt)                     # planar (B, 3C, R)
+    gu = np.random.RandomState(0).normal(size=tuple(u.shape)).astype(np.float32)
+    u.backward(torch.tensor(gu, device=dev))
+    assert torch.isfinite(k.grad).all()
+    # oracle on a copy where the all-masked vitals get one dummy observation and a ZERO upstream gradient
+    x2, g2 = xn.astype(np.float64).copy(), gu.astype(np.float64).copy()
+    for b, c in masked:
+        x2[b, C + c, 0] = 1.0
+        g2[b, [c, C + c, 2 * C + c], :] = 0.0
+    want = O.sci_backward(x2, g["sci_kernel"].astype(np.float64), O.linspace_grid(H, R), C, g2.transpose(0, 2, 1))
+    _check("allmasked/d_sci_kernel", k.grad, want)
