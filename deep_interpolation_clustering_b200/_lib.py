@@ -45,6 +45,8 @@ SIGNATURES = {
     "dic_kmeans_assign": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, c_int, _P]),
     "dic_kmeans_update": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P]),
     "dic_kmeans_lloyd_step": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, c_int, _P]),
+    "dic_kmeans_lloyd_run": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, c_int, c_int,
+                                     c_double, _P]),
     "dic_kmeans_min_d2": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, _P]),
     "dic_pairwise_dist_sum": (c_int, [_P, _P, _P, c_int64, c_int, c_int, _P]),
     "dic_pairwise_workspace_bytes": (c_size_t, [c_int64, c_int]),

@@ -86,7 +86,9 @@ template <typename T> static void km_add_buffer(KmLayout& L, int D, int tile) {
 template <typename T>
 __global__ void kmeans_assign_kernel(const T* __restrict__ X, const T* __restrict__ centers,
                                      int32_t* __restrict__ labels, double* __restrict__ ws, int64_t N, int D,
-                                     int K, int s16, int flags, KmLayout L, int want_sums) {
+                                     int K, int s16, int flags, KmLayout L, int want_sums,
+                                     const double* __restrict__ done) {
+  if (done && *done != 0.0) return;     // a batched Lloyd run has stopped: nothing left to do (see dic_kmeans_lloyd_run)
   using V = typename Vec16<T>::type;
   constexpr int PER = Vec16<T>::n;
   extern __shared__ __align__(16) unsigned char smem[];
@@ -229,7 +231,8 @@ template <typename T, int KR, int NC>
 __global__ void __launch_bounds__(kKmTile)
 kmeans_assign_fast_kernel(const T* __restrict__ X, const T* __restrict__ centers, int32_t* __restrict__ labels,
                           double* __restrict__ ws, int64_t N, int D, int K, int s16, int flags,
-                          KmLayout L, int want_sums, int vec_ok) {
+                          KmLayout L, int want_sums, int vec_ok, const double* __restrict__ done) {
+  if (done && *done != 0.0) return;
   using V = typename Vec16<T>::type;
   constexpr int PER = Vec16<T>::n;
   extern __shared__ __align__(16) unsigned char smem[];
@@ -437,7 +440,8 @@ kmeans_assign_fast_kernel(const T* __restrict__ X, const T* __restrict__ centers
 // flight), then a fixed-order shuffle reduction -> deterministic and latency-tolerant.
 __global__ void kmeans_finish_kernel(const double* __restrict__ ws, double* __restrict__ sums,
                                      double* __restrict__ counts, double* __restrict__ stats, int nblocks,
-                                     int K, int D) {
+                                     int K, int D, const double* __restrict__ done) {
+  if (done && *done != 0.0) return;
   const int64_t stride = (int64_t)K * D + K + 4;
   const int lane = threadIdx.x & 31;
   const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);     // element of [sums | counts | stats]
@@ -457,10 +461,15 @@ __global__ void kmeans_finish_kernel(const double* __restrict__ ws, double* __re
 // sum / count (an empty cluster keeps its old centre; relocation is the host's rare path),
 // squared centre shift, and a 4-double status [changed labels, sum shift^2, empty clusters,
 // inertia] so the host reads ONE small buffer per iteration.
+// run != 0 (dic_kmeans_lloyd_run): status has 8 doubles; status[4] is the stop flag every kernel of the batch
+// checks first (1 = converged, 2 = an empty cluster needs the host), status[5] counts the iterations done,
+// status[6] = 1 for strict convergence (no label changed), and the stopping rule of _kmeans.py:700-733 is applied
+// here with tolerance `tol`.
 template <typename T>
 __global__ void kmeans_update_kernel(const double* __restrict__ sums, const double* __restrict__ counts,
                                      const double* __restrict__ stats, T* __restrict__ centers,
-                                     double* __restrict__ status, int K, int D) {
+                                     double* __restrict__ status, int K, int D, int run, double tol) {
+  if (run && status[4] != 0.0) return;
   __shared__ double red[32];
   __shared__ int s_empty;
   if (threadIdx.x == 0) {
@@ -492,6 +501,12 @@ __global__ void kmeans_update_kernel(const double* __restrict__ sums, const doub
     status[1] = s;
     status[2] = (double)s_empty;
     status[3] = stats[0];
+    if (run) {
+      status[5] += 1.0;
+      if (s_empty > 0) status[4] = 2.0;
+      else if (stats[1] == 0.0) { status[4] = 1.0; status[6] = 1.0; }
+      else if (s <= tol) status[4] = 1.0;
+    }
   }
 }
 
@@ -657,7 +672,9 @@ constexpr int kT2Rows = 128;
 template <typename T, int S16>
 __global__ void __launch_bounds__(kT2Rows)
 kmeans_assign_tile2_kernel(const T* __restrict__ X, const T* __restrict__ centers, int32_t* __restrict__ labels,
-                           double* __restrict__ ws, int64_t N, int K, int flags, int want_sums) {
+                           double* __restrict__ ws, int64_t N, int K, int flags, int want_sums,
+                           const double* __restrict__ done) {
+  if (done && *done != 0.0) return;
   using V = typename Vec16<T>::type;
   constexpr int PER = Vec16<T>::n;
   constexpr int D = S16 * PER;
@@ -850,7 +867,9 @@ __device__ __forceinline__ double rw_inf(double) { return __longlong_as_double(0
 template <typename T, int E, int KP>
 __global__ void __launch_bounds__(kRwThreads)
 kmeans_assign_rw_kernel(const T* __restrict__ X, const T* __restrict__ centers, int32_t* __restrict__ labels,
-                        double* __restrict__ ws, int64_t N, int D, int K, int flags, int want_sums) {
+                        double* __restrict__ ws, int64_t N, int D, int K, int flags, int want_sums,
+                        const double* __restrict__ done) {
+  if (done && *done != 0.0) return;
   using V = typename RwVec<T>::type;
   constexpr int PER = RwVec<T>::n;          // elements per 16-byte vector
   constexpr int NV = E / PER;               // vectors per lane
@@ -1180,7 +1199,8 @@ int km_blocks(int K, int D) {
 
 template <typename T>
 int launch_assign(const void* X, const void* centers, int32_t* labels, double* sums, double* counts,
-                  double* stats, void* workspace, int64_t N, int D, int K, int flags, cudaStream_t st) {
+                  double* stats, void* workspace, int64_t N, int D, int K, int flags, cudaStream_t st,
+                  const double* done = nullptr) {
   // specialised tile kernel: rows of exactly 16 or 32 sixteen-byte vectors (D = 64 / 128 float32, 32 / 64 float64)
   {
     constexpr int PER = 16 / (int)sizeof(T);
@@ -1207,13 +1227,13 @@ int launch_assign(const void* X, const void* centers, int32_t* labels, double* s
     if (smem > 48 * 1024)                                                                                     \
       DIC_CUDA(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));             \
     kf<<<nb, kT2Rows, smem, st>>>(static_cast<const T*>(X), static_cast<const T*>(centers), labels, wsd, N, K, \
-                                  flags, sums != nullptr);                                                    \
+                                  flags, sums != nullptr, done);                                              \
   }
       if (s16x == 16) DIC_T2_LAUNCH(16) else DIC_T2_LAUNCH(32)
 #undef DIC_T2_LAUNCH
       DIC_LAUNCH_CHECK("kmeans_assign_tile2_kernel");
       const int nn = K * D + K + 4;
-      kmeans_finish_kernel<<<(nn + 7) / 8, 256, 0, st>>>(wsd, sums, counts, stats, nb, K, D);
+      kmeans_finish_kernel<<<(nn + 7) / 8, 256, 0, st>>>(wsd, sums, counts, stats, nb, K, D, done);
       DIC_LAUNCH_CHECK("kmeans_finish_kernel");
       return DIC_OK;
     }
@@ -1248,7 +1268,7 @@ int launch_assign(const void* X, const void* centers, int32_t* labels, double* s
     if (smem > 48 * 1024)                                                                                    \
       DIC_CUDA(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
     kf<<<nb, kRwThreads, smem, st>>>(static_cast<const T*>(X), static_cast<const T*>(centers), labels, wsd,  \
-                                     N, D, K, flags, sums != nullptr);                                       \
+                                     N, D, K, flags, sums != nullptr, done);                                 \
   }
 #define DIC_RW_KP(E_)                                                                                        \
   if (KP == 4) DIC_RW_LAUNCH(E_, 4) else if (KP == 8) DIC_RW_LAUNCH(E_, 8) else DIC_RW_LAUNCH(E_, 16)
@@ -1257,7 +1277,7 @@ int launch_assign(const void* X, const void* centers, int32_t* labels, double* s
 #undef DIC_RW_LAUNCH
       DIC_LAUNCH_CHECK("kmeans_assign_rw_kernel");
       const int nn = K * D + K + 4;
-      kmeans_finish_kernel<<<(nn + 7) / 8, 256, 0, st>>>(wsd, sums, counts, stats, nb, K, D);
+      kmeans_finish_kernel<<<(nn + 7) / 8, 256, 0, st>>>(wsd, sums, counts, stats, nb, K, D, done);
       DIC_LAUNCH_CHECK("kmeans_finish_kernel");
       return DIC_OK;
     }
@@ -1285,7 +1305,7 @@ int launch_assign(const void* X, const void* centers, int32_t* labels, double* s
       DIC_CUDA(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));     \
     kf<<<nb, kKmTile, L.total, st>>>(static_cast<const T*>(X), static_cast<const T*>(centers), labels,   \
                                      wsd, N, D, K, s16, flags, L, sums != nullptr,                       \
-                                     (int)(aligned16(X) && D % (16 / (int)sizeof(T)) == 0));             \
+                                     (int)(aligned16(X) && D % (16 / (int)sizeof(T)) == 0), done);       \
   }
 #define DIC_KM_NC(KR_)                                                                \
   if (nc == 1) DIC_KM_LAUNCH(KR_, 1) else if (nc == 2) DIC_KM_LAUNCH(KR_, 2) else DIC_KM_LAUNCH(KR_, 4)
@@ -1294,7 +1314,7 @@ int launch_assign(const void* X, const void* centers, int32_t* labels, double* s
 #undef DIC_KM_LAUNCH
     DIC_LAUNCH_CHECK("kmeans_assign_fast_kernel");
     const int nn = K * D + K + 4;
-    kmeans_finish_kernel<<<(nn + 7) / 8, 256, 0, st>>>(wsd, sums, counts, stats, nb, K, D);
+    kmeans_finish_kernel<<<(nn + 7) / 8, 256, 0, st>>>(wsd, sums, counts, stats, nb, K, D, done);
     DIC_LAUNCH_CHECK("kmeans_finish_kernel");
     return DIC_OK;
   }
@@ -1313,10 +1333,10 @@ int launch_assign(const void* X, const void* centers, int32_t* labels, double* s
   if (blocks < 1) blocks = 1;
   double* ws = static_cast<double*>(workspace);
   kern<<<blocks, tile, L.total, st>>>(static_cast<const T*>(X), static_cast<const T*>(centers), labels, ws,
-                                      N, D, K, s16, flags, L, sums != nullptr);
+                                      N, D, K, s16, flags, L, sums != nullptr, done);
   DIC_LAUNCH_CHECK("kmeans_assign_kernel");
   const int n = K * D + K + 4;
-  kmeans_finish_kernel<<<(n + 7) / 8, 256, 0, st>>>(ws, sums, counts, stats, blocks, K, D);
+  kmeans_finish_kernel<<<(n + 7) / 8, 256, 0, st>>>(ws, sums, counts, stats, blocks, K, D, done);
   DIC_LAUNCH_CHECK("kmeans_finish_kernel");
   return DIC_OK;
 }
@@ -1428,9 +1448,9 @@ extern "C" int dic_kmeans_update(const double* sums, const double* counts, const
   DIC_REQUIRE(dtype == 0 || dtype == 1, DIC_ERR_INVALID_ARGUMENT, "dtype must be 0 (float32) or 1 (float64)");
   cudaStream_t st = as_stream(stream);
   if (dtype == 0)
-    kmeans_update_kernel<float><<<1, 256, 0, st>>>(sums, counts, stats, static_cast<float*>(centers), status, K, D);
+    kmeans_update_kernel<float><<<1, 256, 0, st>>>(sums, counts, stats, static_cast<float*>(centers), status, K, D, 0, 0.0);
   else
-    kmeans_update_kernel<double><<<1, 256, 0, st>>>(sums, counts, stats, static_cast<double*>(centers), status, K, D);
+    kmeans_update_kernel<double><<<1, 256, 0, st>>>(sums, counts, stats, static_cast<double*>(centers), status, K, D, 0, 0.0);
   DIC_LAUNCH_CHECK("kmeans_update_kernel");
   return DIC_OK;
 }
@@ -1442,6 +1462,30 @@ extern "C" int dic_kmeans_lloyd_step(const void* X, void* centers, int32_t* labe
   int rc = dic_kmeans_assign(X, centers, labels, sums, counts, stats, workspace, N, D, K, dtype, flags, stream);
   if (rc) return rc;
   return dic_kmeans_update(sums, counts, stats, centers, status, D, K, dtype, stream);
+}
+
+extern "C" int dic_kmeans_lloyd_run(const void* X, void* centers, int32_t* labels, double* sums, double* counts,
+                                    double* stats, double* status8, void* workspace, int64_t N, int D, int K,
+                                    int dtype, int flags, int n_steps, double tol, dic_stream_t stream) {
+  DIC_REQUIRE(X && centers && labels && sums && counts && stats && status8 && workspace, DIC_ERR_INVALID_ARGUMENT,
+              "null pointer argument");
+  DIC_REQUIRE(N > 0 && D > 0 && K > 0 && n_steps > 0, DIC_ERR_INVALID_ARGUMENT, "bad sizes N=%lld D=%d K=%d steps=%d",
+              (long long)N, D, K, n_steps);
+  DIC_REQUIRE(K <= 64 && D <= 512, DIC_ERR_UNSUPPORTED, "k-means supports K <= 64, D <= 512 (got K=%d D=%d)", K, D);
+  DIC_REQUIRE(dtype == 0 || dtype == 1, DIC_ERR_INVALID_ARGUMENT, "dtype must be 0 (float32) or 1 (float64)");
+  cudaStream_t st = as_stream(stream);
+  const double* done = status8 + 4;
+  for (int i = 0; i < n_steps; ++i) {
+    int rc = dtype == 0 ? launch_assign<float>(X, centers, labels, sums, counts, stats, workspace, N, D, K, flags, st, done)
+                        : launch_assign<double>(X, centers, labels, sums, counts, stats, workspace, N, D, K, flags, st, done);
+    if (rc) return rc;
+    if (dtype == 0)
+      kmeans_update_kernel<float><<<1, 256, 0, st>>>(sums, counts, stats, static_cast<float*>(centers), status8, K, D, 1, tol);
+    else
+      kmeans_update_kernel<double><<<1, 256, 0, st>>>(sums, counts, stats, static_cast<double*>(centers), status8, K, D, 1, tol);
+    DIC_LAUNCH_CHECK("kmeans_update_kernel");
+  }
+  return DIC_OK;
 }
 
 extern "C" int dic_kmeans_min_d2(const void* X, const void* cands, const void* min_d2, void* min_d2_out,

@@ -18,6 +18,7 @@ centre-shift stopping, a final E-step when not strictly converged, best of n_ini
 from __future__ import annotations
 
 import numbers
+import os
 
 import numpy as np
 import torch
@@ -98,6 +99,8 @@ class _Device:
         self.stats = torch.empty(4, dtype=torch.float64, device=self.dev)
         self.status = torch.empty(4, dtype=torch.float64, device=self.dev)
         self._step_args = None
+        self._run_args = None
+        self.status8 = None
 
     def lloyd_step(self, centers, flags):
         """One Lloyd iteration (E-step + M-step in place on `centers`) in ONE C call with ONE host sync;
@@ -117,6 +120,27 @@ class _Device:
                 rc = fn(*args, flags, stream)
         _lib.check(rc, "dic_kmeans_lloyd_step")
         return self.status.tolist()
+
+    def lloyd_run(self, centers, flags, n_steps, tol):
+        """Up to n_steps Lloyd iterations enqueued back to back with the stopping rule on the device
+        (dic_kmeans_lloyd_run); ONE host sync.  Returns status8 = [changed, shift2, n_empty, inertia, stop flag,
+        iterations so far, strict, -]."""
+        key = centers.data_ptr()
+        if self._run_args is None or self._run_args[0] != key:
+            if self.status8 is None:
+                self.status8 = torch.zeros(8, dtype=torch.float64, device=self.dev)
+            self._run_args = (key, _lib.lib().dic_kmeans_lloyd_run,
+                              (_lib.ptr(self.X), key, _lib.ptr(self.labels), _lib.ptr(self.sums), _lib.ptr(self.counts),
+                               _lib.ptr(self.stats), _lib.ptr(self.status8), _lib.ptr(self.ws), self.N, self.D,
+                               centers.shape[0], self.dt), _lib.current_stream(self.dev))
+        _, fn, args, stream = self._run_args
+        if torch.cuda.current_device() == self.dev.index:
+            rc = fn(*args, flags, int(n_steps), float(tol), stream)
+        else:
+            with torch.cuda.device(self.dev):
+                rc = fn(*args, flags, int(n_steps), float(tol), stream)
+        _lib.check(rc, "dic_kmeans_lloyd_run")
+        return self.status8.tolist()
 
     def update(self, centers):
         """M-step in place on `centers`; returns (changed, shift2, n_empty, inertia) with ONE sync."""
@@ -287,8 +311,51 @@ class KMeansB200:
             st.counts[new_id] = 1
             st.counts[old_id] -= 1
 
+    LLOYD_BATCH = 8      # iterations enqueued per host synchronisation
+
+    def _lloyd_batched(self, st, centers, tol_eff, comm):
+        """_lloyd with the iterations enqueued LLOYD_BATCH at a time and the stopping rule evaluated on the device
+        (dic_kmeans_lloyd_run): the kernels of a batch that follow the stopping iteration return at once, so labels,
+        sums and centres are exactly those of the per-iteration loop.  An empty cluster (rare) stops the batch with
+        the centres untouched; relocation and that iteration's M-step then run on the host path and the run resumes."""
+        st.labels.fill_(-1)
+        if st.status8 is not None:
+            st.status8.zero_()
+        strict = False
+        it = 0
+        while it < self.max_iter:
+            status = st.lloyd_run(centers, DIC_KM_COUNT_CHANGES | DIC_KM_NO_INERTIA, min(self.LLOYD_BATCH, self.max_iter - it),
+                                  tol_eff)
+            it = int(status[5])
+            flag = int(status[4])
+            if flag == 1:
+                strict = status[6] == 1.0
+                break
+            if flag == 2:                                        # the iteration `it` left an empty cluster
+                changed = float(st.stats[1])
+                self._relocate_empty(st, centers, comm)
+                cnt = st.counts.clamp(min=1.0)[:, None]
+                new = torch.where(st.counts[:, None] > 0, st.sums / cnt, centers.to(torch.float64)).to(centers.dtype)
+                shift2 = float(((new - centers).to(torch.float64) ** 2).sum())
+                centers.copy_(new)                               # in place: the cached kernel arguments stay valid
+                if int(changed) == 0:
+                    strict = True
+                    break
+                if shift2 <= tol_eff:
+                    break
+                st.status8[4:5].zero_()                         # resume; [5] keeps counting
+        n_iter = it
+        if strict:
+            st.assign(centers, DIC_KM_KEEP_LABELS, want_sums=False)
+        else:
+            st.assign(centers, 0, want_sums=False)
+        inertia = float(st.stats[0])
+        return st.labels.clone(), inertia, centers, n_iter
+
     def _lloyd(self, st, centers, tol_eff, comm):
         """One run of sklearn/cluster/_kmeans.py:630-757."""
+        if not comm.on and hasattr(st, "lloyd_run") and os.environ.get("DIC_KMEANS_NO_BATCH") is None:
+            return self._lloyd_batched(st, centers, tol_eff, comm)
         st.labels.fill_(-1)
         strict = False
         n_iter = 0

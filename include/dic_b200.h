@@ -190,6 +190,18 @@ int dic_kmeans_lloyd_step(const void* X, void* centers, int32_t* labels, double*
                           double* stats, double* status, void* workspace, int64_t N, int D, int K,
                           int dtype, int flags, dic_stream_t stream);
 
+/* Up to n_steps Lloyd iterations enqueued back to back with a device-side stopping rule, so that the host
+ * synchronises once per batch instead of once per iteration (at N <= 1e5 the per-iteration round trip is most of
+ * the time).  status8 (8 doubles, zero status8[4..7] before the first batch of a run):
+ *   [0..3] as dic_kmeans_update, [4] stop flag (0 = running, 1 = converged, 2 = a cluster came out empty: the
+ *   centres were left untouched, the caller relocates and resumes), [5] iterations executed so far,
+ *   [6] 1 if the run stopped because no label changed (strict convergence, _kmeans.py:700-712), [7] unused.
+ * Once the flag is set every remaining kernel of the batch returns at once: labels, sums and centres are those
+ * of the stopping iteration.  tol is the absolute tolerance on the squared centre shift (_kmeans.py:285-293). */
+int dic_kmeans_lloyd_run(const void* X, void* centers, int32_t* labels, double* sums, double* counts,
+                         double* stats, double* status8, void* workspace, int64_t N, int D, int K, int dtype,
+                         int flags, int n_steps, double tol, dic_stream_t stream);
+
 /* k-means++ potentials (sklearn/cluster/_kmeans.py:224-281): for each of L candidate centres
  *   pots[l] = sum_i min(min_d2[i], ||x_i - cand_l||^2)          (float64, L <= 16)
  * min_d2 (N, same dtype as X) may be NULL (treated as +inf: first centre).  If
