@@ -20,6 +20,7 @@ import torch
 
 from . import _lib
 from . import internal_eval
+from . import parallel
 from .kmeans import KMeansB200, _DT
 
 
@@ -59,8 +60,11 @@ def pairwise_dist_sum(Xc, exact=False):
 class KM(object):
     """p2_clustering_optK.py:226-410 (constructor signature kept; plots are out of scope)."""
 
-    def __init__(self, k_max, out_path=None, internal_metrics=(), n_init=10, gap_b=10, exact_pairwise=False):
+    def __init__(self, k_max, out_path=None, internal_metrics=(), n_init=10, gap_b=10, exact_pairwise=False,
+                 _pairwise=None, _device=None):
         self.exact_pairwise = exact_pairwise
+        self._pairwise = _pairwise          # test hooks (gloo tests on CPU): distance-sum stand-in and its device
+        self._dev = _device
         self.k_max = k_max
         self.out_path = os.path.join(out_path, "plot") if out_path else None
         if self.out_path:
@@ -77,12 +81,13 @@ class KM(object):
 
     # ---- the two "inertia" definitions ---------------------------------------------------------
     def _cluster_sums(self, a, X):
-        Xd = _as_device(X)
+        Xd = _as_device(X, self._dev)
         ad = torch.as_tensor(np.asarray(a) if not isinstance(a, torch.Tensor) else a).to(Xd.device)
+        pw = self._pairwise or pairwise_dist_sum
         out = []
         for c in torch.unique(ad).tolist():                      # np.unique(a): sorted labels present
             Xc = Xd[ad == c]
-            out.append((pairwise_dist_sum(Xc, exact=self.exact_pairwise), Xc.shape[0]))
+            out.append((pw(Xc, exact=self.exact_pairwise), Xc.shape[0]))
         return out
 
     def compute_inertia_v1(self, a, X):
@@ -95,11 +100,19 @@ class KM(object):
         return float(sum(float(s) / (2 * n) for s, n in self._cluster_sums(a, X)))
 
     # ---- gap statistic -----------------------------------------------------------------------
-    def compute_gap_internal_metric(self, clustering, data, k_max=5, n_references=5, version=2, draw=None):
+    def compute_gap_internal_metric(self, clustering, data, k_max=5, n_references=5, version=2, draw=None,
+                                    group=None, task_parallel=None, seed=0):
+        """``group`` / ``task_parallel=True``: the (k, reference set) fits of the sweep are independent, so they are
+        dealt round-robin to the ranks of ``group`` (every rank holds the whole data matrix, SURVEY 8e "task-parallel
+        at c4") and ONE all-reduce of the (k, reference) table of inertias ends the sweep.  Reference set (k, j) is
+        then drawn from its own generator seeded by (seed, k, j), so the table does not depend on the world size
+        (give ``clustering`` an integer ``random_state`` for the same property of its k-means++ draws)."""
         import pandas as pd
         data = np.asarray(data) if not isinstance(data, torch.Tensor) else data.cpu().numpy()
         if len(data.shape) == 1:
             data = data.reshape(-1, 1)
+        if task_parallel or (task_parallel is None and group is not None):
+            return self._gap_task_parallel(clustering, data, k_max, n_references, version, draw, group, seed)
         # draw: None = np.random.random_sample like the reference (:370; host RNG, exact stream parity);
         # "device" = uniform float64 draws generated on the GPU (same distribution, no 8*N*D-byte host
         # generation + upload per reference set - at 1M x 64 that is 0.5 s of host time 180 times)
@@ -110,7 +123,7 @@ class KM(object):
         data_rng = data.max() - data_min                                             # :360
         k_rng = range(2, k_max + 1)
         vals = pd.DataFrame(index=k_rng, columns=["k", "gap", "ref", "act", "ref_s"] + self.internal_metrics_names)
-        data_dev = _as_device(data)
+        data_dev = _as_device(data, self._dev)
         for k in k_rng:
             local_inertia = []
             clustering.n_clusters = k                                                # :367
@@ -132,6 +145,61 @@ class KM(object):
             a_host = assignments.cpu().numpy() if isinstance(assignments, torch.Tensor) else np.asarray(assignments)
             metric_values = [m(data_dev, a_host) for m in self.internal_metrics]     # :401-405
             vals.loc[k] = [k, gap, ref, act, ref_s] + metric_values
+        return vals
+
+    def _gap_task_parallel(self, clustering, data, k_max, n_references, version, draw, group, seed):
+        """The sweep above as a flat list of (k, j) tasks, j < n_references a reference set and j = n_references the
+        data itself (with its internal metrics), dealt round-robin to the ranks; see compute_gap_internal_metric."""
+        import pandas as pd
+        import torch.distributed as dist
+        rank, ws = parallel.world(group)
+        device_draws = isinstance(draw, str) and draw == "device"
+        inertia = self.compute_inertia_v1 if version == 1 else self.computer_intertia_v2
+        data_min = data.min()
+        data_rng = data.max() - data_min
+        k_rng = range(2, k_max + 1)
+        n_m = len(self.internal_metrics)
+        table = np.zeros((len(k_rng), n_references + 1 + n_m), dtype=np.float64)
+        data_dev = _as_device(data, self._dev)
+        on_dev = _accepts_tensor(clustering)
+        task = 0
+        for ki, k in enumerate(k_rng):
+            for j in range(n_references + 1):
+                mine = task % ws == rank
+                task += 1
+                if not mine:
+                    continue
+                clustering.n_clusters = k
+                if j == n_references:
+                    a = clustering.fit_predict(data_dev if on_dev else data)
+                    table[ki, j] = inertia(a, data_dev)
+                    a_host = a.cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+                    table[ki, j + 1:] = [m(data_dev, a_host) for m in self.internal_metrics]
+                    continue
+                task_seed = (int(seed) * 1000003 + k * 1009 + j) % (2 ** 31)
+                if device_draws and on_dev:
+                    gen = torch.Generator(device=data_dev.device).manual_seed(task_seed)
+                    ref_dev = torch.rand(data.shape, dtype=torch.float64, device=data_dev.device, generator=gen) \
+                        * float(data_rng) + float(data_min)
+                    reference = None
+                else:
+                    sample = np.random.RandomState(task_seed).random_sample if (draw is None or device_draws) else draw
+                    reference = sample(data.shape) * data_rng + data_min
+                    ref_dev = _as_device(reference, self._dev)
+                a = clustering.fit_predict(ref_dev if on_dev else reference)
+                table[ki, j] = inertia(a, ref_dev)
+        if ws > 1:
+            nccl = dist.get_backend(group) == "nccl"
+            buf = torch.from_numpy(table).to(data_dev.device) if nccl else torch.from_numpy(table)
+            dist.all_reduce(buf, group=group)                    # every cell was written by exactly one rank
+            table = buf.cpu().numpy()
+        vals = pd.DataFrame(index=k_rng, columns=["k", "gap", "ref", "act", "ref_s"] + self.internal_metrics_names)
+        for ki, k in enumerate(k_rng):
+            logs = np.log(table[ki, :n_references])
+            ref = np.mean(logs)
+            ref_s = np.sqrt(1 + 1 / n_references) * np.std(logs)
+            act = np.log(table[ki, n_references])
+            vals.loc[k] = [k, ref - act, ref, act, ref_s] + list(table[ki, n_references + 1:])
         return vals
 
     # ---- elbow ---------------------------------------------------------------------------------

@@ -98,6 +98,20 @@ def main():
         assert report[f"km_{tag}_inertia"] < (1e-6 if dtype == np.float32 else 1e-12), report
         assert shard.n_iter_ == single.n_iter_
 
+    # ---- gap sweep: (k, reference set) tasks dealt to the ranks == the same tasks on one GPU -----------------
+    from deep_interpolation_clustering_b200.gap import KM
+    Xg = synth.make_blobs(20000, 64, 4, seed=6).astype(np.float32)
+    args = dict(k_max=6, n_references=3, version=1, draw="device", seed=5)
+    solo = [dist.new_group([r]) for r in range(world)][rank]         # a world of one: every task on this GPU
+    one = KM(6, internal_metrics=["Calinski-Harabasz"]).compute_gap_internal_metric(
+        KMeansB200(n_init=3, random_state=9, device=dev), Xg, group=solo, **args)
+    many = KM(6, internal_metrics=["Calinski-Harabasz"]).compute_gap_internal_metric(
+        KMeansB200(n_init=3, random_state=9, device=dev), Xg, group=dist.group.WORLD, **args)
+    a, b = one.astype(float).to_numpy(), many.astype(float).to_numpy()
+    report["gap_tasks_max_diff"] = float(np.abs(a - b).max())
+    assert np.allclose(a, b, rtol=1e-12, atol=0), (a, b)
+    assert int(many["k"][many["gap"].astype(float).idxmax()]) == 4
+
     dist.barrier()
     if rank == 0:
         print(json.dumps({"world": world, "ok": True, **{k: float(f"{v:.3e}") for k, v in report.items()}}), flush=True)

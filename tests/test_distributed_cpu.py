@@ -232,3 +232,33 @@ def test_sharded_relocation_and_kmeanspp(golden):
     single = KMeansB200(n_clusters=5, n_init=2, random_state=11, _backend=_CpuBackend).fit(X)
     assert np.isclose(single.inertia_, res[0][2], rtol=1e-9)
     assert np.array_equal(np.concatenate([res[r][0] for r in range(WORLD)]), single.labels_)
+
+
+def _cdist_sum(Xc, exact=False):
+    return torch.cdist(Xc.double(), Xc.double()).sum().reshape(1)
+
+
+def _gap_sweep(group_mode):
+    from deep_interpolation_clustering_b200.gap import KM
+    from deep_interpolation_clustering_b200.kmeans import KMeansB200
+    from deep_interpolation_clustering_b200 import synth
+    X = synth.make_blobs(240, 8, 3, seed=5).astype(np.float32)
+    km = KM(5, _pairwise=_cdist_sum, _device=torch.device("cpu"))
+    clustering = KMeansB200(n_init=2, random_state=3, _backend=_CpuBackend)
+    df = km.compute_gap_internal_metric(clustering, X, k_max=5, n_references=3, version=1, seed=7, **group_mode)
+    return df.astype(float).to_numpy()
+
+
+def _t_gap_tasks(rank):
+    return _gap_sweep({"group": dist.group.WORLD})
+
+
+def test_task_parallel_gap_sweep_equals_single_process():
+    """The (k, reference set) fits dealt round-robin to two ranks + one all-reduce of the inertia table give the
+    single-process table exactly (per-task seeded reference draws, SURVEY 8e 'task-parallel at c4')."""
+    res = _run(_t_gap_tasks)
+    single = _gap_sweep({"task_parallel": True})
+    assert np.isfinite(single).all() and single.shape == (4, 5)
+    for r in range(WORLD):
+        assert np.array_equal(res[r], single)
+    assert int(single[np.argmax(single[:, 1]), 0]) == 3          # three blobs: the gap picks K = 3
