@@ -49,6 +49,7 @@ SIGNATURES = {
                                      c_double, _P]),
     "dic_kmeans_min_d2": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, _P]),
     "dic_pairwise_dist_sum": (c_int, [_P, _P, _P, c_int64, c_int, c_int, _P]),
+    "dic_pairwise_dist_sum_part": (c_int, [_P, _P, _P, c_int64, c_int, c_int, c_int, c_int, _P]),
     "dic_pairwise_workspace_bytes": (c_size_t, [c_int64, c_int]),
     "dic_cluster_rowsums": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, c_int, _P]),
     "dic_colsum_workspace_bytes": (c_size_t, [c_int]),

@@ -21,7 +21,8 @@ namespace dic {
 // tensor-core path (pairwise_tc.cu)
 size_t pairwise_tc_workspace_bytes(int64_t n, int D);
 bool pairwise_tc_supported(const void* X, int D);
-int launch_pairwise_tc(const float* X, double* out, void* workspace, int64_t n, int D, cudaStream_t st);
+int launch_pairwise_tc(const float* X, double* out, void* workspace, int64_t n, int D, cudaStream_t st, int part,
+                       int n_parts);
 int launch_cluster_rowsums_tc(const float* X, const int32_t* perm, const int32_t* tile_cluster, double* rowsum,
                               void* workspace, int64_t n_pad, int D, int K, cudaStream_t st);
 
@@ -590,7 +591,7 @@ constexpr int kPwBlocks = 148 * 4;
 
 template <typename T>
 __global__ void __launch_bounds__(kPwThreads)
-pairwise_sum_kernel(const T* __restrict__ X, double* __restrict__ ws, int64_t n, int D) {
+pairwise_sum_kernel(const T* __restrict__ X, double* __restrict__ ws, int64_t n, int D, int part, int n_parts) {
   __shared__ T sa[kPwChunk][kPwTile + 1];   // [d][row]: rows of the i-tile, transposed
   __shared__ T sb[kPwChunk][kPwTile + 1];
   const int tid = threadIdx.x;
@@ -598,7 +599,8 @@ pairwise_sum_kernel(const T* __restrict__ X, double* __restrict__ ws, int64_t n,
   const int64_t nb = (n + kPwTile - 1) / kPwTile;
   const int64_t ntiles = nb * (nb + 1) / 2;
   double total = 0.0;
-  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+  // stripe `part` of `n_parts` (multi-GPU): tiles part, part + n_parts, ... of this CTA's sequence
+  for (int64_t t = (int64_t)blockIdx.x * n_parts + part; t < ntiles; t += (int64_t)gridDim.x * n_parts) {
     // unrank t -> (bi <= bj) in the upper triangle, row-major
     int64_t bi = (int64_t)((2.0 * nb + 1.0 - sqrt((2.0 * nb + 1.0) * (2.0 * nb + 1.0) - 8.0 * (double)t)) * 0.5);
     while (bi * nb - bi * (bi - 1) / 2 > t) --bi;
@@ -1394,13 +1396,14 @@ int launch_min_d2(const void* X, const void* cands, const void* min_d2, void* mi
 }
 
 template <typename T>
-int launch_pairwise(const void* X, double* out, void* workspace, int64_t n, int D, cudaStream_t st) {
+int launch_pairwise(const void* X, double* out, void* workspace, int64_t n, int D, cudaStream_t st, int part,
+                    int n_parts) {
   const int64_t nb = (n + kPwTile - 1) / kPwTile;
   const int64_t ntiles = nb * (nb + 1) / 2;
   int blocks = (int)(ntiles < kPwBlocks ? ntiles : kPwBlocks);
   if (blocks < 1) blocks = 1;
   double* ws = static_cast<double*>(workspace);
-  pairwise_sum_kernel<T><<<blocks, kPwThreads, 0, st>>>(static_cast<const T*>(X), ws, n, D);
+  pairwise_sum_kernel<T><<<blocks, kPwThreads, 0, st>>>(static_cast<const T*>(X), ws, n, D, part, n_parts);
   DIC_LAUNCH_CHECK("pairwise_sum_kernel");
   sum_blocks_kernel<<<1, 256, 0, st>>>(ws, out, blocks, 1);
   DIC_LAUNCH_CHECK("sum_blocks_kernel");
@@ -1519,11 +1522,13 @@ extern "C" int dic_cluster_rowsums(const float* X, const int32_t* perm, const in
   return launch_cluster_rowsums_tc(X, perm, tile_cluster, rowsum, workspace, n_pad, D, K, as_stream(stream));
 }
 
-extern "C" int dic_pairwise_dist_sum(const void* Xc, double* out, void* workspace, int64_t n, int D, int dtype,
-                                     dic_stream_t stream) {
+static int pairwise_dist_sum_impl(const void* Xc, double* out, void* workspace, int64_t n, int D, int dtype, int part,
+                                  int n_parts, dic_stream_t stream) {
   DIC_REQUIRE(Xc && out && workspace, DIC_ERR_INVALID_ARGUMENT, "null pointer argument");
   DIC_REQUIRE(n >= 0 && D > 0, DIC_ERR_INVALID_ARGUMENT, "bad sizes n=%lld D=%d", (long long)n, D);
   DIC_REQUIRE(dtype == 0 || dtype == 1, DIC_ERR_INVALID_ARGUMENT, "dtype must be 0 (float32) or 1 (float64)");
+  DIC_REQUIRE(n_parts >= 1 && n_parts <= 1024 && part >= 0 && part < n_parts, DIC_ERR_INVALID_ARGUMENT,
+              "bad stripe %d of %d", part, n_parts);
   cudaStream_t st = as_stream(stream);
   if (n == 0) {
     DIC_CUDA(cudaMemsetAsync(out, 0, sizeof(double), st));
@@ -1533,7 +1538,17 @@ extern "C" int dic_pairwise_dist_sum(const void* Xc, double* out, void* workspac
   // DIC_PAIRWISE_EXACT=1 forces the direct (x_i - x_j)^2 CUDA-core kernel, float64 always uses it.
   static const bool force_exact = getenv("DIC_PAIRWISE_EXACT") != nullptr;
   if (dtype == 0 && !force_exact && n >= 512 && pairwise_tc_supported(Xc, D))
-    return launch_pairwise_tc(static_cast<const float*>(Xc), out, workspace, n, D, st);
-  return dtype == 0 ? launch_pairwise<float>(Xc, out, workspace, n, D, st)
-                    : launch_pairwise<double>(Xc, out, workspace, n, D, st);
+    return launch_pairwise_tc(static_cast<const float*>(Xc), out, workspace, n, D, st, part, n_parts);
+  return dtype == 0 ? launch_pairwise<float>(Xc, out, workspace, n, D, st, part, n_parts)
+                    : launch_pairwise<double>(Xc, out, workspace, n, D, st, part, n_parts);
+}
+
+extern "C" int dic_pairwise_dist_sum(const void* Xc, double* out, void* workspace, int64_t n, int D, int dtype,
+                                     dic_stream_t stream) {
+  return pairwise_dist_sum_impl(Xc, out, workspace, n, D, dtype, 0, 1, stream);
+}
+
+extern "C" int dic_pairwise_dist_sum_part(const void* Xc, double* out, void* workspace, int64_t n, int D, int dtype,
+                                          int part, int n_parts, dic_stream_t stream) {
+  return pairwise_dist_sum_impl(Xc, out, workspace, n, D, dtype, part, n_parts, stream);
 }

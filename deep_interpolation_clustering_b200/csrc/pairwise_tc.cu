@@ -240,7 +240,7 @@ __device__ __forceinline__ void unrank_tile(int64_t t, int64_t nb, int64_t& bi, 
 //              accumulator
 __global__ void __launch_bounds__(kThreads, 1)
 pairwise_tc_kernel(const float* __restrict__ X, const float* __restrict__ norms, double* __restrict__ partial,
-                   int64_t n, int D, long long* __restrict__ dbg) {
+                   int64_t n, int D, long long* __restrict__ dbg, int part, int n_parts) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   TcSmem& S = *reinterpret_cast<TcSmem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -264,23 +264,25 @@ pairwise_tc_kernel(const float* __restrict__ X, const float* __restrict__ norms,
   const int64_t ntiles = nb * (nb + 1) / 2;
   const int kchunks = (D + kKC - 1) / kKC;
   double total = 0.0;
+  // stripe `part` of `n_parts` (multi-GPU): this CTA acts as CTA vcta of a grid of vgrid CTAs
+  const int64_t vcta = (int64_t)blockIdx.x * n_parts + part, vgrid = (int64_t)gridDim.x * n_parts;
 
   if (warp >= 4) {
     // ================= loaders + MMA issuer =================
     const int lt = tid - 128;
     const uint32_t a_hi = smem_u32(S.a_hi), a_lo = smem_u32(S.a_lo);
-    const int64_t nstages = ((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x) * kchunks;   // this CTA's stages
+    const int64_t nstages = vcta < ntiles ? ((ntiles - vcta + vgrid - 1) / vgrid) * kchunks : 0;   // this CTA's stages
     int64_t cur_bi = -1;
     TileRegs breg;                 // the column block of the NEXT stage, already on its way from L2
-    {
+    if (nstages > 0) {
       int64_t bi, bj;
-      unrank_tile(blockIdx.x, nb, bi, bj);
+      unrank_tile(vcta, nb, bi, bj);
       tile_fetch(breg, X, n, D, bj * kTile, 0, lt);
     }
     for (int64_t stage = 0; stage < nstages; ++stage) {
       const int64_t i = stage / kchunks;                       // running tile count of this CTA
       const int kc = (int)(stage - i * kchunks);
-      const int64_t t = blockIdx.x + i * gridDim.x;
+      const int64_t t = vcta + i * vgrid;
       int64_t bi, bj;
       unrank_tile(t, nb, bi, bj);
       const int acc = (int)(i & 1), b = (int)(stage & 1);
@@ -303,7 +305,7 @@ pairwise_tc_kernel(const float* __restrict__ X, const float* __restrict__ norms,
         const int64_t i2 = (stage + 1) / kchunks;
         const int kc2 = (int)(stage + 1 - i2 * kchunks);
         int64_t bi2, bj2;
-        unrank_tile(blockIdx.x + i2 * gridDim.x, nb, bi2, bj2);
+        unrank_tile(vcta + i2 * vgrid, nb, bi2, bj2);
         tile_fetch(breg, X, n, D, bj2 * kTile, kc2 * kKC, lt);
       }
       long long c4 = clock64();
@@ -345,7 +347,7 @@ pairwise_tc_kernel(const float* __restrict__ X, const float* __restrict__ norms,
   } else {
     // ================= epilogue =================
     int i = 0;
-    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++i) {
+    for (int64_t t = vcta; t < ntiles; t += vgrid, ++i) {
       int64_t bi, bj;
       unrank_tile(t, nb, bi, bj);
       const int acc = i & 1;
@@ -532,7 +534,8 @@ template <bool ROWSUMS>
 __global__ void __launch_bounds__(kThreads64, 1)
 pairwise_tc64_kernel(const unsigned char* __restrict__ packed, const float* __restrict__ norms,
                      double* __restrict__ partial, int64_t n, int L, long long* __restrict__ dbg,
-                     const int32_t* __restrict__ tile_cluster, double* __restrict__ rowsum, int K) {
+                     const int32_t* __restrict__ tile_cluster, double* __restrict__ rowsum, int K, int part,
+                     int n_parts) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   Smem64& S = *reinterpret_cast<Smem64*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -560,7 +563,9 @@ pairwise_tc64_kernel(const unsigned char* __restrict__ packed, const float* __re
   volatile int* timeout = &S.timeout;
 
   ItemIter it;
-  it.init(nb, L, (int)gridDim.x, (int)blockIdx.x, ROWSUMS);
+  // stripe `part` of `n_parts` (multi-GPU): this CTA takes the items of CTA blockIdx.x * n_parts + part of a grid
+  // n_parts times as large, so the stripes of all parts tile the item list exactly once
+  it.init(nb, L, (int)gridDim.x * n_parts, (int)blockIdx.x * n_parts + part, ROWSUMS);
   int64_t p, j0, j1;
   double total = 0.0;
 
@@ -796,7 +801,8 @@ size_t pairwise_tc_workspace_bytes(int64_t n, int D) {
 // Shared launcher.  rowsum == nullptr: pairwise sum of the n rows of X -> out.  Otherwise: X is read
 // through perm (n = padded row count), rowsum (n, K) is zeroed and filled.
 static int launch_tc64(const float* X, double* out, void* workspace, int64_t n, int D, const int32_t* perm,
-                       const int32_t* tile_cluster, double* rowsum, int K, cudaStream_t st) {
+                       const int32_t* tile_cluster, double* rowsum, int K, cudaStream_t st, int part = 0,
+                       int n_parts = 1) {
   using namespace tc64;
   const bool rows_mode = rowsum != nullptr;
   const int64_t nblk = tc64_blocks(n), nb = (n + kBlk - 1) / kBlk;
@@ -820,7 +826,8 @@ static int launch_tc64(const float* X, double* out, void* workspace, int64_t n, 
   int64_t items = 0;
   for (int64_t s = 0; s * L < nb; ++s)
     items += rows_mode ? P : (((s + 1) * L - 1) / 2 < P - 1 ? ((s + 1) * L - 1) / 2 + 1 : P);
-  int blocks = (int)(items < sms ? items : sms);
+  const int64_t my_items = items / n_parts > 0 ? items / n_parts : 1;
+  int blocks = (int)(my_items < sms ? my_items : sms);
   if (blocks > 1024) blocks = 1024;
   const size_t smem = sizeof(Smem64) + 1024;
   long long* dbg = nullptr;
@@ -831,11 +838,11 @@ static int launch_tc64(const float* X, double* out, void* workspace, int64_t n, 
   if (rows_mode) {
     DIC_CUDA(cudaFuncSetAttribute(pairwise_tc64_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     pairwise_tc64_kernel<true><<<blocks, kThreads64, smem, st>>>(packed, norms, partial, n, (int)L, dbg, tile_cluster,
-                                                                 rowsum, K);
+                                                                 rowsum, K, part, n_parts);
   } else {
     DIC_CUDA(cudaFuncSetAttribute(pairwise_tc64_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     pairwise_tc64_kernel<false><<<blocks, kThreads64, smem, st>>>(packed, norms, partial, n, (int)L, dbg, nullptr,
-                                                                  nullptr, 0);
+                                                                  nullptr, 0, part, n_parts);
   }
   if (dbg) {
     long long h[16];
@@ -857,8 +864,9 @@ static int launch_tc64(const float* X, double* out, void* workspace, int64_t n, 
   return DIC_OK;
 }
 
-static int launch_pairwise_tc64(const float* X, double* out, void* workspace, int64_t n, int D, cudaStream_t st) {
-  return launch_tc64(X, out, workspace, n, D, nullptr, nullptr, nullptr, 0, st);
+static int launch_pairwise_tc64(const float* X, double* out, void* workspace, int64_t n, int D, cudaStream_t st,
+                                int part, int n_parts) {
+  return launch_tc64(X, out, workspace, n, D, nullptr, nullptr, nullptr, 0, st, part, n_parts);
 }
 
 // Row sums by cluster (silhouette): see pairwise_tc64_kernel<true>.  n_pad % 128 == 0.
@@ -869,9 +877,10 @@ int launch_cluster_rowsums_tc(const float* X, const int32_t* perm, const int32_t
 
 bool pairwise_tc_supported(const void* X, int D) { return D % 4 == 0 && D >= 4 && aligned16(X); }
 
-int launch_pairwise_tc(const float* X, double* out, void* workspace, int64_t n, int D, cudaStream_t st) {
+int launch_pairwise_tc(const float* X, double* out, void* workspace, int64_t n, int D, cudaStream_t st, int part,
+                       int n_parts) {
   static const bool force_v1 = getenv("DIC_PAIRWISE_TC_V1") != nullptr;      // debug: the register-staged kernel
-  if (D <= 64 && !force_v1) return launch_pairwise_tc64(X, out, workspace, n, D, st);
+  if (D <= 64 && !force_v1) return launch_pairwise_tc64(X, out, workspace, n, D, st, part, n_parts);
   float* norms = static_cast<float*>(workspace);
   double* partial = reinterpret_cast<double*>(static_cast<unsigned char*>(workspace) +
                                               ((size_t)n * sizeof(float) + 255) / 256 * 256);
@@ -882,7 +891,8 @@ int launch_pairwise_tc(const float* X, double* out, void* workspace, int64_t n, 
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int64_t nb = (n + kTile - 1) / kTile;
   const int64_t ntiles = nb * (nb + 1) / 2;
-  int blocks = (int)(ntiles < sms ? ntiles : sms);
+  const int64_t my_tiles = ntiles / n_parts > 0 ? ntiles / n_parts : 1;
+  int blocks = (int)(my_tiles < sms ? my_tiles : sms);
   if (blocks > 1024) blocks = 1024;
   const size_t smem = sizeof(TcSmem) + 1024;
   DIC_CUDA(cudaFuncSetAttribute(pairwise_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -891,7 +901,7 @@ int launch_pairwise_tc(const float* X, double* out, void* workspace, int64_t n, 
     cudaMalloc(&dbg, 16 * sizeof(long long));
     cudaMemsetAsync(dbg, 0, 16 * sizeof(long long), st);
   }
-  pairwise_tc_kernel<<<blocks, kThreads, smem, st>>>(X, norms, partial, n, D, dbg);
+  pairwise_tc_kernel<<<blocks, kThreads, smem, st>>>(X, norms, partial, n, D, dbg, part, n_parts);
   if (dbg) {
     long long h[16];
     cudaMemcpyAsync(h, dbg, sizeof(h), cudaMemcpyDeviceToHost, st);

@@ -21,7 +21,7 @@ import torch
 from . import _lib
 from . import internal_eval
 from . import parallel
-from .kmeans import KMeansB200, _DT
+from .kmeans import KMeansB200, _Comm, _DT
 
 
 def _as_device(X, device=None):
@@ -57,14 +57,33 @@ def pairwise_dist_sum(Xc, exact=False):
     return out
 
 
+def pairwise_dist_sum_part(Xc, part, n_parts, exact=False):
+    """Stripe `part` of `n_parts` of pairwise_dist_sum(Xc): Xc holds ALL rows of the cluster (identical on every
+    rank), the stripes tile the kernel's tile list once, so the n_parts results add up to the full sum."""
+    if not exact and Xc.shape[0] >= TC_MIN_ROWS and Xc.shape[1] % 4 == 0:
+        Xc = (Xc - Xc.mean(dim=0, keepdim=True)).to(torch.float32)
+    Xc = Xc.contiguous()
+    n, D = Xc.shape
+    out = torch.empty(1, dtype=torch.float64, device=Xc.device)
+    L = _lib.lib()
+    ws = torch.empty(int(L.dic_pairwise_workspace_bytes(n, D)), dtype=torch.uint8, device=Xc.device)
+    with torch.cuda.device(Xc.device):
+        _lib.check(L.dic_pairwise_dist_sum_part(_lib.ptr(Xc), _lib.ptr(out), _lib.ptr(ws), n, D, _DT[Xc.dtype],
+                                                int(part), int(n_parts), _lib.current_stream(Xc.device)),
+                   "dic_pairwise_dist_sum_part")
+    return out
+
+
 class KM(object):
     """p2_clustering_optK.py:226-410 (constructor signature kept; plots are out of scope)."""
 
     def __init__(self, k_max, out_path=None, internal_metrics=(), n_init=10, gap_b=10, exact_pairwise=False,
-                 _pairwise=None, _device=None):
+                 _pairwise=None, _device=None, _pairwise_part=None):
         self.exact_pairwise = exact_pairwise
-        self._pairwise = _pairwise          # test hooks (gloo tests on CPU): distance-sum stand-in and its device
+        self._pairwise = _pairwise          # test hooks (gloo tests on CPU): distance-sum stand-ins and their device
+        self._pairwise_part = _pairwise_part
         self._dev = _device
+        self._comm = None                   # set while a row-sharded sweep runs
         self.k_max = k_max
         self.out_path = os.path.join(out_path, "plot") if out_path else None
         if self.out_path:
@@ -81,6 +100,8 @@ class KM(object):
 
     # ---- the two "inertia" definitions ---------------------------------------------------------
     def _cluster_sums(self, a, X):
+        if self._comm is not None and self._comm.on:
+            return self._cluster_sums_sharded(a, X, self._comm)
         Xd = _as_device(X, self._dev)
         ad = torch.as_tensor(np.asarray(a) if not isinstance(a, torch.Tensor) else a).to(Xd.device)
         pw = self._pairwise or pairwise_dist_sum
@@ -89,6 +110,30 @@ class KM(object):
             Xc = Xd[ad == c]
             out.append((pw(Xc, exact=self.exact_pairwise), Xc.shape[0]))
         return out
+
+    def _cluster_sums_sharded(self, a, X, comm):
+        """_cluster_sums for rows sharded over the ranks of `comm` (pairwise inertia): the rows of one
+        cluster are all-gathered (padded to the largest shard), every rank evaluates its stripe of the tile list
+        (dic_pairwise_dist_sum_part) and ONE all-reduce of the K per-cluster sums ends the evaluation."""
+        Xd = _as_device(X, self._dev)
+        ad = torch.as_tensor(np.asarray(a) if not isinstance(a, torch.Tensor) else a).to(Xd.device).long()
+        top = torch.tensor([int(ad.max()) + 1 if ad.numel() else 0], dtype=torch.int64, device=Xd.device)
+        K = int(comm.gather(top).max())
+        counts = comm.gather(torch.bincount(ad, minlength=K)).cpu()          # (ranks, K)
+        total = counts.sum(0)
+        pw = self._pairwise_part or pairwise_dist_sum_part
+        sums = torch.zeros(K, dtype=torch.float64, device=Xd.device)
+        for c in range(K):
+            if int(total[c]) == 0:
+                continue
+            mine = Xd[ad == c]
+            pad = torch.zeros((int(counts[:, c].max()), Xd.shape[1]), dtype=Xd.dtype, device=Xd.device)
+            pad[:mine.shape[0]] = mine
+            parts = comm.gather(pad)
+            Xc = torch.cat([parts[r, :int(counts[r, c])] for r in range(comm.size)])
+            sums[c:c + 1] = pw(Xc, comm.rank, comm.size, exact=self.exact_pairwise)
+        comm.sum_(sums)
+        return [(sums[c], int(total[c])) for c in range(K) if int(total[c]) > 0]
 
     def compute_inertia_v1(self, a, X):
         """mean_c [ mean of the full n_c x n_c distance matrix ]   (:334-342)."""
@@ -101,8 +146,12 @@ class KM(object):
 
     # ---- gap statistic -----------------------------------------------------------------------
     def compute_gap_internal_metric(self, clustering, data, k_max=5, n_references=5, version=2, draw=None,
-                                    group=None, task_parallel=None, seed=0):
-        """``group`` / ``task_parallel=True``: the (k, reference set) fits of the sweep are independent, so they are
+                                    group=None, task_parallel=None, seed=0, row_sharded=False):
+        """``row_sharded=True``: ``data`` holds this rank's ROWS only and ``clustering`` is a
+        ``KMeansB200(sharded=True, process_group=group)``; the data range is all-reduced, every rank draws its own rows
+        of each reference set, the fits exchange one packed all-reduce per Lloyd iteration and the pairwise inertia
+        runs in stripes (_cluster_sums_sharded) - the mode for matrices beyond one GPU (SURVEY 8e "row-shard at c5").
+        ``group`` / ``task_parallel=True``: the (k, reference set) fits of the sweep are independent, so they are
         dealt round-robin to the ranks of ``group`` (every rank holds the whole data matrix, SURVEY 8e "task-parallel
         at c4") and ONE all-reduce of the (k, reference) table of inertias ends the sweep.  Reference set (k, j) is
         then drawn from its own generator seeded by (seed, k, j), so the table does not depend on the world size
@@ -111,6 +160,8 @@ class KM(object):
         data = np.asarray(data) if not isinstance(data, torch.Tensor) else data.cpu().numpy()
         if len(data.shape) == 1:
             data = data.reshape(-1, 1)
+        if row_sharded:
+            return self._gap_row_sharded(clustering, data, k_max, n_references, version, draw, group, seed)
         if task_parallel or (task_parallel is None and group is not None):
             return self._gap_task_parallel(clustering, data, k_max, n_references, version, draw, group, seed)
         # draw: None = np.random.random_sample like the reference (:370; host RNG, exact stream parity);
@@ -134,7 +185,7 @@ class KM(object):
                     reference = None
                 else:
                     reference = draw(data.shape) * data_rng + data_min               # :370 (float64)
-                    ref_dev = _as_device(reference)
+                    ref_dev = _as_device(reference, self._dev)
                 assignments = clustering.fit_predict(ref_dev if _accepts_tensor(clustering) else reference)
                 local_inertia.append(inertia(assignments, ref_dev))
             ref = np.mean(np.log(local_inertia))                                     # :374
@@ -200,6 +251,51 @@ class KM(object):
             ref_s = np.sqrt(1 + 1 / n_references) * np.std(logs)
             act = np.log(table[ki, n_references])
             vals.loc[k] = [k, ref - act, ref, act, ref_s] + list(table[ki, n_references + 1:])
+        return vals
+
+    def _gap_row_sharded(self, clustering, data, k_max, n_references, version, draw, group, seed):
+        import pandas as pd
+        import torch.distributed as dist
+        if self.internal_metrics:
+            raise NotImplementedError("internal metrics are not available for a row-sharded sweep")
+        comm = _Comm(group)
+        device_draws = isinstance(draw, str) and draw == "device"
+        inertia = self.compute_inertia_v1 if version == 1 else self.computer_intertia_v2
+        data_dev = _as_device(data, self._dev)
+        lohi = torch.tensor([float(data.min()), -float(data.max())], dtype=torch.float64, device=data_dev.device)
+        if comm.on:
+            dist.all_reduce(lohi, op=dist.ReduceOp.MIN, group=group)
+        data_min = data.dtype.type(float(lohi[0]))                                  # :360 over ALL rows, in the
+        data_rng = data.dtype.type(float(-lohi[1])) - data_min                      # data's own arithmetic
+        k_rng = range(2, k_max + 1)
+        vals = pd.DataFrame(index=k_rng, columns=["k", "gap", "ref", "act", "ref_s"])
+        on_dev = _accepts_tensor(clustering)
+        self._comm = comm
+        try:
+            for k in k_rng:
+                local_inertia = []
+                clustering.n_clusters = k
+                for j in range(n_references):
+                    task_seed = ((int(seed) * 1000003 + k * 1009 + j) * 1031 + comm.rank) % (2 ** 31)
+                    if device_draws and on_dev:
+                        gen = torch.Generator(device=data_dev.device).manual_seed(task_seed)
+                        ref_dev = torch.rand(data.shape, dtype=torch.float64, device=data_dev.device, generator=gen) \
+                            * float(data_rng) + float(data_min)
+                        reference = None
+                    else:
+                        sample = np.random.RandomState(task_seed).random_sample if (draw is None or device_draws) \
+                            else draw
+                        reference = sample(data.shape) * data_rng + data_min
+                        ref_dev = _as_device(reference, self._dev)
+                    a = clustering.fit_predict(ref_dev if on_dev else reference)
+                    local_inertia.append(inertia(a, ref_dev))
+                ref = np.mean(np.log(local_inertia))
+                ref_s = np.sqrt(1 + 1 / n_references) * np.std(np.log(local_inertia))
+                a = clustering.fit_predict(data_dev if on_dev else data)
+                act = np.log(inertia(a, data_dev))
+                vals.loc[k] = [k, ref - act, ref, act, ref_s]
+        finally:
+            self._comm = None
         return vals
 
     # ---- elbow ---------------------------------------------------------------------------------

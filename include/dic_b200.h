@@ -218,6 +218,11 @@ int dic_kmeans_min_d2(const void* X, const void* cands, const void* min_d2, void
 size_t dic_pairwise_workspace_bytes(int64_t n, int D);
 int dic_pairwise_dist_sum(const void* Xc, double* out, void* workspace, int64_t n, int D,
                           int dtype, dic_stream_t stream);
+/* Stripe `part` of `n_parts` of the same sum (pairwise inertia on several GPUs): every
+ * rank holds all n rows of the cluster (all-gathered by the caller) and evaluates the tiles
+ * part, part + n_parts, ... of the tile list; the n_parts results add up to dic_pairwise_dist_sum's. */
+int dic_pairwise_dist_sum_part(const void* Xc, double* out, void* workspace, int64_t n, int D,
+                               int dtype, int part, int n_parts, dic_stream_t stream);
 
 /* Per-row, per-cluster distance sums - the O(N^2) part of the silhouette coefficient
  * (internal_eval.py:112-122 -> sklearn.metrics.silhouette_score, called inside the gap loop at

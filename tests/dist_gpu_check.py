@@ -112,6 +112,28 @@ def main():
     assert np.allclose(a, b, rtol=1e-12, atol=0), (a, b)
     assert int(many["k"][many["gap"].astype(float).idxmax()]) == 4
 
+    # ---- gap sweep, rows sharded: sharded fits + striped pairwise inertia == the whole matrix on one GPU ----
+    class Sliced:                                  # t-th call -> rows [lo, hi) of the t-th pre-drawn uniform matrix
+        def __init__(self, U, lo, hi):
+            self.U, self.lo, self.hi, self.t = U, lo, hi, 0
+
+        def __call__(self, shape):
+            self.t += 1
+            return self.U[self.t - 1][self.lo:self.hi]
+
+    Xr = synth.make_blobs(6001, 64, 3, seed=8).astype(np.float32)
+    U = np.random.RandomState(4).random_sample((3 * 2,) + Xr.shape)
+    lo, hi = parallel.shard_range(Xr.shape[0], rank, world)
+    whole = KM(4).compute_gap_internal_metric(KMeansB200(n_init=2, random_state=5, device=dev), Xr, k_max=4,
+                                              n_references=2, version=1, draw=Sliced(U, 0, Xr.shape[0]),
+                                              task_parallel=False)
+    rows = KM(4).compute_gap_internal_metric(KMeansB200(n_init=2, random_state=5, device=dev, sharded=True),
+                                             Xr[lo:hi], k_max=4, n_references=2, version=1, draw=Sliced(U, lo, hi),
+                                             row_sharded=True, group=dist.group.WORLD)
+    a, b = whole.astype(float).to_numpy(), rows.astype(float).to_numpy()
+    report["gap_rows_max_rel_diff"] = float((np.abs(a - b) / np.maximum(np.abs(a), 1e-12)).max())
+    assert np.allclose(a, b, rtol=1e-5, atol=1e-6), (a, b)
+
     dist.barrier()
     if rank == 0:
         print(json.dumps({"world": world, "ok": True, **{k: float(f"{v:.3e}") for k, v in report.items()}}), flush=True)

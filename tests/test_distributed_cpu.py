@@ -262,3 +262,50 @@ def test_task_parallel_gap_sweep_equals_single_process():
     for r in range(WORLD):
         assert np.array_equal(res[r], single)
     assert int(single[np.argmax(single[:, 1]), 0]) == 3          # three blobs: the gap picks K = 3
+
+
+def _cdist_sum_part(Xc, part, n_parts, exact=False):
+    return torch.cdist(Xc[part::n_parts].double(), Xc.double()).sum().reshape(1)
+
+
+class _SlicedDraws:
+    """draw(shape) stand-in: the t-th call returns rows [lo, hi) of the t-th pre-generated uniform matrix."""
+
+    def __init__(self, U, lo, hi):
+        self.U, self.lo, self.hi, self.t = U, lo, hi, 0
+
+    def __call__(self, shape):
+        out = self.U[self.t][self.lo:self.hi]
+        self.t += 1
+        assert out.shape == tuple(shape)
+        return out
+
+
+def _gap_rows(rank, world):
+    from deep_interpolation_clustering_b200 import parallel, synth
+    from deep_interpolation_clustering_b200.gap import KM
+    from deep_interpolation_clustering_b200.kmeans import KMeansB200
+    X = synth.make_blobs(301, 8, 3, seed=5).astype(np.float32)                # odd size: ragged shards
+    U = np.random.RandomState(3).random_sample((3 * 2,) + X.shape)
+    lo, hi = parallel.shard_range(X.shape[0], rank, world) if world > 1 else (0, X.shape[0])
+    km = KM(4, _pairwise=_cdist_sum, _pairwise_part=_cdist_sum_part, _device=torch.device("cpu"))
+    clustering = KMeansB200(n_init=2, random_state=3, sharded=world > 1, _backend=_CpuBackend)
+    df = km.compute_gap_internal_metric(clustering, X[lo:hi], k_max=4, n_references=2, version=1,
+                                        draw=_SlicedDraws(U, lo, hi), row_sharded=world > 1,
+                                        group=dist.group.WORLD if world > 1 else None,
+                                        task_parallel=False)
+    return df.astype(float).to_numpy()
+
+
+def _t_gap_rows(rank):
+    return _gap_rows(rank, WORLD)
+
+
+def test_row_sharded_gap_sweep_equals_single_process():
+    """Rows of the data and of every reference set sharded over two ranks: sharded k-means fits + striped pairwise
+    inertia (all-gather of a cluster's rows, stripes of the tile list, one all-reduce) give the single-process table."""
+    res = _run(_t_gap_rows)
+    single = _gap_rows(0, 1)
+    assert np.isfinite(single).all()
+    for r in range(WORLD):
+        assert np.allclose(res[r], single, rtol=1e-9, atol=1e-12), (res[r], single)

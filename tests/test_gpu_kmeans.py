@@ -160,6 +160,25 @@ def test_tensor_core_pairwise_matches_exact(n, D):
         record(f"pairwise_exact_n{n}_D{D}", exact, ref, 1e-10, 0)
 
 
+@pytest.mark.parametrize("n,D,dtype", [(600, 64, "f32"), (16385, 64, "f32"), (5000, 32, "f32"), (3000, 256, "f32"),
+                                       (700, 100, "f32"), (900, 64, "f64"), (300, 16, "f32")])
+@pytest.mark.parametrize("n_parts", [2, 3, 8])
+def test_pairwise_stripes_add_up(n, D, dtype, n_parts):
+    """dic_pairwise_dist_sum_part: the stripes of the tile list (one per rank of a row-sharded sweep) tile it exactly
+    once on every kernel - TMA-fed tcgen05 (D <= 64), register-staged tcgen05 (D > 64), CUDA cores (float64, odd D,
+    small n) - including stripes that own no tile at all (n = 300 / 600 with 8 parts)."""
+    from deep_interpolation_clustering_b200 import synth
+    from deep_interpolation_clustering_b200.gap import pairwise_dist_sum, pairwise_dist_sum_part
+    X = synth.make_blobs(n, D, 3, seed=n + D)
+    Xd = torch.from_numpy(X).cuda().to(torch.float32 if dtype == "f32" else torch.float64)
+    full = float(pairwise_dist_sum(Xd))
+    parts = [float(pairwise_dist_sum_part(Xd, r, n_parts)) for r in range(n_parts)]
+    assert all(np.isfinite(v) and v >= 0 for v in parts), parts
+    if n >= 3000:
+        assert min(parts) > 0.5 * full / n_parts, "unbalanced stripes"
+    record(f"pairwise_parts_n{n}_D{D}_{dtype}_p{n_parts}", sum(parts), full, 1e-9, 0)
+
+
 @pytest.mark.parametrize("n,D,K", [(5000, 64, 5), (3001, 20, 7), (20000, 32, 3)])
 def test_silhouette_tensor_core_matches_float64(n, D, K):
     """dic_cluster_rowsums (tcgen05 row sums by cluster) vs the chunked float64 distance path and sklearn:
