@@ -1534,7 +1534,7 @@ static int pairwise_dist_sum_impl(const void* Xc, double* out, void* workspace, 
     DIC_CUDA(cudaMemsetAsync(out, 0, sizeof(double), st));
     return DIC_OK;
   }
-  // float32 clusters of useful size go to the tensor-core kernel (3xTF32, float32-grade dots);
+  // float32 clusters of useful size go to the tensor-core kernel (split float16 / TF32 operands, float32-grade dots);
   // DIC_PAIRWISE_EXACT=1 forces the direct (x_i - x_j)^2 CUDA-core kernel, float64 always uses it.
   static const bool force_exact = getenv("DIC_PAIRWISE_EXACT") != nullptr;
   if (dtype == 0 && !force_exact && n >= 512 && pairwise_tc_supported(Xc, D))

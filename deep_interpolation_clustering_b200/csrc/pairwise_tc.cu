@@ -18,6 +18,7 @@
 //     the current one into one of two TMEM accumulators and 4 epilogue warps drain the other
 //     (tcgen05.ld, ni + nj - 2 dot, clamp, sqrt.approx, float64 sums); mbarriers carry the
 //     stage-free / accumulator-full / accumulator-empty hand-offs.
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -66,6 +67,18 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
       ".reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+      : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, M = 128, N = 128, K = 16 (f16 operands, f32 accumulate), single CTA
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t"
       "}\n" ::"r"(tmem_d),
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
       : "memory");
@@ -127,6 +140,10 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
 // at [7,10)/[10,13), both K-major, N >> 3 at [17,23), M >> 4 at [24,29).
 constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTile >> 3) << 17) |
                             ((uint32_t)(kTile >> 4) << 24);
+
+// The same with a/b format F16 (0): kind::f16, K = 16 per instruction.
+constexpr uint32_t kIdescF16 = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(kTile >> 3) << 17) |
+                               ((uint32_t)(kTile >> 4) << 24);
 
 __device__ __forceinline__ bool bar_wait_bounded(uint64_t* bar, uint32_t phase) {
   for (int spin = 0; spin < (1 << 22); ++spin) {
@@ -426,18 +443,18 @@ __global__ void sum_partials_kernel(const double* __restrict__ ws, double* __res
 // =================================================================================================
 // D <= 64: TMA-fed, A-stationary variant.
 //
-// A one-off pre-pass (pack_split_kernel) writes every 128-row block of X ONCE as split-TF32 operand
-// tiles in the exact shared-memory image the tensor core reads (hi tile | lo tile, 64 KB per block,
-// K padded to 64) plus the row norms.  The main kernel then never touches a float again on its way
-// to the tensor core: one elected thread streams tiles with 1-D TMA bulk copies, one thread issues
-// tcgen05.mma, eight warps drain TMEM.
+// A one-off pre-pass (absmax_kernel + pack_split_kernel) writes every 128-row block of X ONCE as split
+// float16 operand tiles (x scaled by a power of two so that max |x| lies in [2^13, 2^14); hi = rn_f16,
+// lo = rn_f16(x - hi): the same 2 x 11 significand bits as split TF32 at half the bytes and twice the K per
+// MMA) in the exact shared-memory image the tensor core reads (hi tile | lo tile, 32 KB per block, K padded
+// to 64) plus the row norms.  The main kernel then never touches a float again on its way to the tensor
+// core: one elected thread streams tiles with 1-D TMA bulk copies, one thread issues tcgen05.mma
+// (kind::f16), eight warps drain TMEM.
 //
 //   * supertile = 256 rows (two 128-row blocks: the "row pair", resident in shared memory for a
-//     whole work item, 128 KB) x 128 columns; every column tile that arrives (64 KB) is multiplied
-//     against BOTH row blocks, which halves the L2 -> SM traffic per distance (16 B/clk/SM; a
-//     128-row tile would need 32 of the ~42 B/clk/SM the L2 can deliver chip-wide);
-//   * column tiles arrive as K-halves (32 KB stages, 3 in flight) so that the pipeline fits next to
-//     the resident row pair: 128 + 96 KB of shared memory;
+//     whole work item, 64 KB) x 128 columns; every column tile that arrives (32 KB) is multiplied
+//     against BOTH row blocks, which halves the L2 -> SM traffic per distance;
+//   * column tiles arrive whole (32 KB stages, 4 in flight): 64 + 128 KB of shared memory;
 //   * TMEM holds 2 (double buffer) x 2 (row blocks) accumulators of 128 columns = all 512 columns;
 //   * work items = (row pair p, segment of <= L column tiles), enumerated segment-major so that the
 //     CTAs running at the same time read the same column tiles out of L2, dealt cyclically.
@@ -445,12 +462,13 @@ __global__ void sum_partials_kernel(const double* __restrict__ ws, double* __res
 namespace tc64 {
 
 constexpr int kBlk = 128;
-constexpr int kTileB = kBlk * 64 * 4;        // 32 KB: one hi or lo operand tile (128 rows x K = 64)
-constexpr int kBlockB = 2 * kTileB;          // 64 KB per packed 128-row block: hi | lo
-constexpr int kKParts = 2;                   // a column tile arrives in kKParts K-slices (one pipeline stage each);
-                                             // measured: 4 slices (6 x 16 KB stages) are 10 % SLOWER (smaller bulk copies)
-constexpr int kHalfB = kTileB / kKParts;     // bytes of one K-slice of a hi (or lo) tile: 16 / kKParts K chunks
-constexpr int kStages = 96 * 1024 / (2 * kHalfB);   // 96 KB of stages next to the resident 128 KB row pair
+constexpr int kTileB = kBlk * 64 * 2;        // 16 KB: one hi or lo operand tile (128 rows x K = 64 halves)
+constexpr int kBlockB = 2 * kTileB;          // 32 KB per packed 128-row block: hi | lo
+constexpr int kKChunks = 8;                  // 16-byte K chunks (8 halves) per row
+constexpr int kKParts = 1;                   // a column tile arrives in kKParts K-slices (one pipeline stage each);
+                                             // measured with float32 tiles: smaller bulk copies are slower
+constexpr int kHalfB = kTileB / kKParts;     // bytes of one K-slice of a hi (or lo) tile
+constexpr int kStages = 128 * 1024 / (2 * kHalfB);  // 128 KB of stages next to the resident 64 KB row pair
 constexpr int kEpiWarps = 8;
 constexpr int kThreads64 = 32 * (2 + kEpiWarps);
 
@@ -495,31 +513,80 @@ struct ItemIter {
   }
 };
 
-// X (n x D, D <= 64, D % 4 == 0) -> packed split-TF32 operand tiles + row norms; rows >= n and K >= D
-// are zero.  One CTA per 128-row block, thread -> (row, 16-byte K chunk): coalesced reads.
+// Power-of-two scale that puts max |x| into [2^13, 2^14): the two-term float16 split below then keeps 22 bits of
+// every element whose magnitude is within 2^-11 of the largest (smaller ones lose nothing that matters: the error
+// of a dot product is relative to |x||y|).  absmax_bits = bit pattern of max |x| (non-negative floats order like
+// unsigned integers).
+__device__ __forceinline__ float f16_scale(unsigned bits, float* inv) {
+  int e = bits ? (int)((bits >> 23) & 0xffu) - 127 : 13;       // floor(log2 max|x|); all-zero data: scale 1
+  e = max(-100, min(100, e));
+  *inv = __uint_as_float((uint32_t)(e - 13 + 127) << 23);
+  return __uint_as_float((uint32_t)(13 - e + 127) << 23);
+}
+
+// thread -> (row, 16-byte chunk of 8 halves) of a 128-row block, shared by the two pre-pass kernels
+__device__ __forceinline__ void load_row_chunk(const float* __restrict__ X, int64_t src, int D, int c, float (&v)[8]) {
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+  if (src >= 0 && 8 * c < D) a = __ldg(reinterpret_cast<const float4*>(X + src * D + 8 * c));
+  if (src >= 0 && 8 * c + 4 < D) b = __ldg(reinterpret_cast<const float4*>(X + src * D + 8 * c + 4));
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+
+__global__ void __launch_bounds__(256)
+absmax_kernel(const float* __restrict__ X, unsigned* __restrict__ absmax_bits, int64_t n, int D,
+              const int32_t* __restrict__ perm) {
+  const int64_t blk = blockIdx.x;
+  float m = 0.f;
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int idx = it * 256 + threadIdx.x;
+    const int row = idx >> 3, c = idx & 7;
+    const int64_t gr = blk * kBlk + row;
+    const int64_t src = gr < n ? (perm ? (int64_t)__ldg(perm + gr) : gr) : -1;
+    float v[8];
+    load_row_chunk(X, src, D, c, v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) m = fmaxf(m, fabsf(v[k]));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(absmax_bits, __float_as_uint(m));
+}
+
+// X (n x D, D <= 64, D % 4 == 0) -> packed split-float16 operand tiles (hi = rn_f16(s x), lo = rn_f16(s x - hi)) +
+// row norms of s x; rows >= n and K >= D are zero.  One CTA per 128-row block, thread -> (row, 16-byte K chunk).
 __global__ void __launch_bounds__(256)
 pack_split_kernel(const float* __restrict__ X, unsigned char* __restrict__ packed, float* __restrict__ norms,
-                  int64_t n, int D, const int32_t* __restrict__ perm, float pad_norm) {
+                  int64_t n, int D, const int32_t* __restrict__ perm, float pad_norm,
+                  const unsigned* __restrict__ absmax_bits) {
   const int64_t blk = blockIdx.x;
   unsigned char* out = packed + blk * (int64_t)kBlockB;
+  float inv;
+  const float scale = f16_scale(__ldg(absmax_bits), &inv);
 #pragma unroll
-  for (int it = 0; it < 8; ++it) {
+  for (int it = 0; it < 4; ++it) {
     const int idx = it * 256 + threadIdx.x;
-    const int row = idx >> 4, c = idx & 15;
+    const int row = idx >> 3, c = idx & 7;
     const int64_t gr = blk * kBlk + row;
     // perm (row-sums mode): packed row gr holds X[perm[gr]], perm < 0 = padding between clusters
     const int64_t src = gr < n ? (perm ? (int64_t)__ldg(perm + gr) : gr) : -1;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (src >= 0 && 4 * c < D) v = __ldg(reinterpret_cast<const float4*>(X + src * D + 4 * c));
-    float4 h, l;
-    h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
-    l.x = to_tf32(v.x - h.x); l.y = to_tf32(v.y - h.y); l.z = to_tf32(v.z - h.z); l.w = to_tf32(v.w - h.w);
-    const int off = c * kChunkStride + (row >> 3) * kGroupStride + (row & 7) * 16;
-    *reinterpret_cast<float4*>(out + off) = h;
-    *reinterpret_cast<float4*>(out + kTileB + off) = l;
-    float s = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, v.w * v.w)));
+    float v[8];
+    load_row_chunk(X, src, D, c, v);
+    __half2 h[4], l[4];
+    float s = 0.f;
 #pragma unroll
-    for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    for (int k = 0; k < 4; ++k) {
+      const float x0 = v[2 * k] * scale, x1 = v[2 * k + 1] * scale;          // power of two: exact
+      const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
+      h[k] = __halves2half2(h0, h1);
+      l[k] = __halves2half2(__float2half_rn(x0 - __half2float(h0)), __float2half_rn(x1 - __half2float(h1)));
+      s = fmaf(x0, x0, fmaf(x1, x1, s));
+    }
+    const int off = c * kChunkStride + (row >> 3) * kGroupStride + (row & 7) * 16;
+    *reinterpret_cast<uint4*>(out + off) = *reinterpret_cast<const uint4*>(h);
+    *reinterpret_cast<uint4*>(out + kTileB + off) = *reinterpret_cast<const uint4*>(l);
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     // a padding row gets pad_norm: -inf makes every distance to it exactly 0 (max(-inf, 0) under the sqrt)
     if (c == 0) norms[gr] = src >= 0 ? s : pad_norm;
   }
@@ -535,7 +602,7 @@ __global__ void __launch_bounds__(kThreads64, 1)
 pairwise_tc64_kernel(const unsigned char* __restrict__ packed, const float* __restrict__ norms,
                      double* __restrict__ partial, int64_t n, int L, long long* __restrict__ dbg,
                      const int32_t* __restrict__ tile_cluster, double* __restrict__ rowsum, int K, int part,
-                     int n_parts) {
+                     int n_parts, const unsigned* __restrict__ absmax_bits) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   Smem64& S = *reinterpret_cast<Smem64*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -561,6 +628,8 @@ pairwise_tc64_kernel(const unsigned char* __restrict__ packed, const float* __re
   tc_fence_after();
   const uint32_t tmem = S.tmem_base;
   volatile int* timeout = &S.timeout;
+  float inv_scale;                        // distances come out in units of the packed (scaled) data
+  f16_scale(__ldg(absmax_bits), &inv_scale);
 
   ItemIter it;
   // stripe `part` of `n_parts` (multi-GPU): this CTA takes the items of CTA blockIdx.x * n_parts + part of a grid
@@ -626,16 +695,17 @@ pairwise_tc64_kernel(const unsigned char* __restrict__ packed, const float* __re
               const uint32_t d_tmem = tmem + (uint32_t)((buf * 2 + h) * kBlk);
               const uint32_t a_hi = a_base + (uint32_t)(h * kBlockB), a_lo = a_hi + kTileB;
 #pragma unroll
-              for (int ks = 0; ks < 8 / kKParts; ++ks) {  // one MMA consumes K = 8 tf32 = two 16-byte chunks
-                const uint32_t ka = (uint32_t)((kh * (16 / kKParts) + ks * 2) * kChunkStride);
+              for (int ks = 0; ks < kKChunks / 2 / kKParts; ++ks) {  // one MMA consumes K = 16 halves = two 16-byte chunks
+                const uint32_t ka = (uint32_t)((kh * (kKChunks / kKParts) + ks * 2) * kChunkStride);
                 const uint32_t kb = (uint32_t)(ks * 2 * kChunkStride);
                 const uint64_t dah = make_desc(a_hi + ka), dal = make_desc(a_lo + ka);
                 const uint64_t dbh = make_desc(b_hi + kb), dbl = make_desc(b_lo + kb);
-                // 3xTF32: hi.hi + hi.lo + lo.hi; the dropped lo.lo term is < 2^-22 |x||y|, below the
+                // split float16 (same 11-bit significands as TF32, twice the K per instruction and half the
+                // operand bytes): hi.hi + hi.lo + lo.hi; the dropped lo.lo term is < 2^-22 |x||y|, below the
                 // float32 rounding of the norms it is added to
-                umma_tf32(d_tmem, dah, dbh, kIdesc, (kh > 0 || ks > 0) ? 1u : 0u);
-                umma_tf32(d_tmem, dah, dbl, kIdesc, 1u);
-                umma_tf32(d_tmem, dal, dbh, kIdesc, 1u);
+                umma_f16(d_tmem, dah, dbh, kIdescF16, (kh > 0 || ks > 0) ? 1u : 0u);
+                umma_f16(d_tmem, dah, dbl, kIdescF16, 1u);
+                umma_f16(d_tmem, dal, dbh, kIdescF16, 1u);
               }
             }
             umma_commit(&S.b_empty[slot]);             // stage reusable once these MMAs have read it
@@ -670,7 +740,7 @@ pairwise_tc64_kernel(const unsigned char* __restrict__ packed, const float* __re
         if (ROWSUMS) {
           const int kc = __ldg(tile_cluster + bj);
           if (kc != kcur) {
-            if (kcur >= 0 && gi < n) atomicAdd(rowsum + gi * K + kcur, racc);
+            if (kcur >= 0 && gi < n) atomicAdd(rowsum + gi * K + kcur, racc * (double)inv_scale);
             racc = 0.0;
             kcur = kc;
           }
@@ -762,7 +832,7 @@ pairwise_tc64_kernel(const unsigned char* __restrict__ packed, const float* __re
         if (ROWSUMS) racc += (double)tile_sum;
         else total += (bj == bi) ? (double)tile_sum : 2.0 * (double)tile_sum;
       }
-      if (ROWSUMS && kcur >= 0 && gi < n) atomicAdd(rowsum + gi * K + kcur, racc);
+      if (ROWSUMS && kcur >= 0 && gi < n) atomicAdd(rowsum + gi * K + kcur, racc * (double)inv_scale);
     }
     total = warp_sum(total);
     if (lane == 0) S.red[ew] = total;
@@ -776,7 +846,7 @@ pairwise_tc64_kernel(const unsigned char* __restrict__ packed, const float* __re
   if (tid == 0) {
     double s = 0.0;
     for (int w = 0; w < kEpiWarps; ++w) s += S.red[w];
-    partial[blockIdx.x] = S.timeout ? __longlong_as_double(0x7ff8000000000000LL) : s;   // NaN = pipeline stalled
+    partial[blockIdx.x] = S.timeout ? __longlong_as_double(0x7ff8000000000000LL) : s * (double)inv_scale;   // NaN = stalled
     if (ROWSUMS && S.timeout) rowsum[0] = __longlong_as_double(0x7ff8000000000000LL);
   }
   if (warp == 2) {
@@ -794,7 +864,7 @@ static int64_t tc64_blocks(int64_t n) { return ((n + tc64::kBlk - 1) / tc64::kBl
 size_t pairwise_tc_workspace_bytes(int64_t n, int D) {
   if (D <= 64)   // packed operand tiles | norms (padded) | partials
     return (size_t)tc64_blocks(n) * (tc64::kBlockB + tc64::kBlk * sizeof(float)) + tc64::kBlk * sizeof(float) +
-           1024 * sizeof(double) + 1024;
+           1024 * sizeof(double) + 256 + 1024;
   return ((size_t)n * sizeof(float) + 255) / 256 * 256 + 1024 * sizeof(double);
 }
 
@@ -811,10 +881,14 @@ static int launch_tc64(const float* X, double* out, void* workspace, int64_t n, 
   // norms holds one block more than the packed tiles: the epilogue prefetches one column tile ahead
   double* partial = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(norms) +
                                               ((size_t)(nblk + 1) * kBlk * sizeof(float) + 255) / 256 * 256);
+  unsigned* absmax = reinterpret_cast<unsigned*>(partial + 1024);
   DIC_CUDA(cudaMemsetAsync(norms + nblk * kBlk, 0, kBlk * sizeof(float), st));
+  DIC_CUDA(cudaMemsetAsync(absmax, 0, sizeof(unsigned), st));
   if (rows_mode) DIC_CUDA(cudaMemsetAsync(rowsum, 0, (size_t)n * K * sizeof(double), st));
   const float pad_norm = rows_mode ? -INFINITY : 0.f;
-  pack_split_kernel<<<(unsigned)nblk, 256, 0, st>>>(X, packed, norms, n, D, perm, pad_norm);
+  absmax_kernel<<<(unsigned)nblk, 256, 0, st>>>(X, absmax, n, D, perm);
+  DIC_LAUNCH_CHECK("absmax_kernel");
+  pack_split_kernel<<<(unsigned)nblk, 256, 0, st>>>(X, packed, norms, n, D, perm, pad_norm, absmax);
   DIC_LAUNCH_CHECK("pack_split_kernel");
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -838,11 +912,11 @@ static int launch_tc64(const float* X, double* out, void* workspace, int64_t n, 
   if (rows_mode) {
     DIC_CUDA(cudaFuncSetAttribute(pairwise_tc64_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     pairwise_tc64_kernel<true><<<blocks, kThreads64, smem, st>>>(packed, norms, partial, n, (int)L, dbg, tile_cluster,
-                                                                 rowsum, K, part, n_parts);
+                                                                 rowsum, K, part, n_parts, absmax);
   } else {
     DIC_CUDA(cudaFuncSetAttribute(pairwise_tc64_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     pairwise_tc64_kernel<false><<<blocks, kThreads64, smem, st>>>(packed, norms, partial, n, (int)L, dbg, nullptr,
-                                                                  nullptr, 0, part, n_parts);
+                                                                  nullptr, 0, part, n_parts, absmax);
   }
   if (dbg) {
     long long h[16];

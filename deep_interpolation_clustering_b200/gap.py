@@ -41,7 +41,7 @@ def pairwise_dist_sum(Xc, exact=False):
     """sum over the full n x n Euclidean distance matrix of the rows of Xc (device tensor).
 
     Clusters of >= 512 rows are centred (distances are translation invariant) and evaluated in
-    float32 on the tensor cores (tcgen05, 3xTF32: float32-grade dot products, ~1e-7 relative on
+    float32 on the tensor cores (tcgen05, split-operand products: float32-grade dot products, ~1e-7 relative on
     the sum); ``exact=True`` keeps the input dtype and the direct (x_i - x_j)^2 kernel.
     """
     if not exact and Xc.shape[0] >= TC_MIN_ROWS and Xc.shape[1] % 4 == 0:
