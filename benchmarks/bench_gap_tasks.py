@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--refs", type=int, default=4)
     ap.add_argument("--ninit", type=int, default=2)
     ap.add_argument("--kmax", type=int, default=10)
+    ap.add_argument("--draw", default="device", choices=["device", "device32"])
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -44,7 +45,7 @@ def main():
 
     def sweep():
         return km.compute_gap_internal_metric(KMeansB200(n_init=args.ninit, random_state=1, device=dev), X,
-                                              k_max=args.kmax, n_references=args.refs, version=1, draw="device",
+                                              k_max=args.kmax, n_references=args.refs, version=1, draw=args.draw,
                                               task_parallel=True, group=dist.group.WORLD if world > 1 else None)
     km_small = KM(3, None, [], 1, 1)                                  # warm-up: allocator, NCCL communicator
     km_small.compute_gap_internal_metric(KMeansB200(n_init=1, random_state=1, device=dev), X[:50000], k_max=3,
@@ -64,7 +65,7 @@ def main():
     if rank == 0:
         best = int(df["k"][df["gap"].astype(float).idxmax()])
         print(json.dumps({"workload": "c4 gap sweep, tasks dealt to the GPUs", "n": args.n, "d": args.d,
-                          "k": f"2..{args.kmax}", "n_references": args.refs, "n_init": args.ninit, "n_gpus": world,
+                          "k": f"2..{args.kmax}", "n_references": args.refs, "n_init": args.ninit, "draw": args.draw, "n_gpus": world,
                           "sweep_s": round(float(dt), 3), "best_k": best,
                           "gap": [round(float(g), 5) for g in df["gap"]]}), flush=True)
     if world > 1:

@@ -166,8 +166,11 @@ class KM(object):
             return self._gap_task_parallel(clustering, data, k_max, n_references, version, draw, group, seed)
         # draw: None = np.random.random_sample like the reference (:370; host RNG, exact stream parity);
         # "device" = uniform float64 draws generated on the GPU (same distribution, no 8*N*D-byte host
-        # generation + upload per reference set - at 1M x 64 that is 0.5 s of host time 180 times)
-        device_draws = isinstance(draw, str) and draw == "device"
+        # generation + upload per reference set - at 1M x 64 that is 0.5 s of host time 180 times);
+        # "device32" = the same in float32 (the reference's float64 draws make sklearn - and the Lloyd kernels here -
+        # iterate in float64 on the reference sets although the data is float32; opt-in, half the bytes per pass)
+        device_draws = isinstance(draw, str) and draw in ("device", "device32")
+        ref_dtype = torch.float32 if draw == "device32" else torch.float64
         draw = np.random.random_sample if (draw is None or device_draws) else draw
         inertia = self.compute_inertia_v1 if version == 1 else self.computer_intertia_v2
         data_min = data.min()
@@ -180,7 +183,7 @@ class KM(object):
             clustering.n_clusters = k                                                # :367
             for _ in range(n_references):
                 if device_draws and _accepts_tensor(clustering):
-                    ref_dev = torch.rand(data.shape, dtype=torch.float64, device=data_dev.device) * float(data_rng) \
+                    ref_dev = torch.rand(data.shape, dtype=ref_dtype, device=data_dev.device) * float(data_rng) \
                         + float(data_min)
                     reference = None
                 else:
@@ -204,7 +207,8 @@ class KM(object):
         import pandas as pd
         import torch.distributed as dist
         rank, ws = parallel.world(group)
-        device_draws = isinstance(draw, str) and draw == "device"
+        device_draws = isinstance(draw, str) and draw in ("device", "device32")
+        ref_dtype = torch.float32 if draw == "device32" else torch.float64
         inertia = self.compute_inertia_v1 if version == 1 else self.computer_intertia_v2
         data_min = data.min()
         data_rng = data.max() - data_min
@@ -230,7 +234,7 @@ class KM(object):
                 task_seed = (int(seed) * 1000003 + k * 1009 + j) % (2 ** 31)
                 if device_draws and on_dev:
                     gen = torch.Generator(device=data_dev.device).manual_seed(task_seed)
-                    ref_dev = torch.rand(data.shape, dtype=torch.float64, device=data_dev.device, generator=gen) \
+                    ref_dev = torch.rand(data.shape, dtype=ref_dtype, device=data_dev.device, generator=gen) \
                         * float(data_rng) + float(data_min)
                     reference = None
                 else:
@@ -259,7 +263,8 @@ class KM(object):
         if self.internal_metrics:
             raise NotImplementedError("internal metrics are not available for a row-sharded sweep")
         comm = _Comm(group)
-        device_draws = isinstance(draw, str) and draw == "device"
+        device_draws = isinstance(draw, str) and draw in ("device", "device32")
+        ref_dtype = torch.float32 if draw == "device32" else torch.float64
         inertia = self.compute_inertia_v1 if version == 1 else self.computer_intertia_v2
         data_dev = _as_device(data, self._dev)
         lohi = torch.tensor([float(data.min()), -float(data.max())], dtype=torch.float64, device=data_dev.device)
@@ -279,7 +284,7 @@ class KM(object):
                     task_seed = ((int(seed) * 1000003 + k * 1009 + j) * 1031 + comm.rank) % (2 ** 31)
                     if device_draws and on_dev:
                         gen = torch.Generator(device=data_dev.device).manual_seed(task_seed)
-                        ref_dev = torch.rand(data.shape, dtype=torch.float64, device=data_dev.device, generator=gen) \
+                        ref_dev = torch.rand(data.shape, dtype=ref_dtype, device=data_dev.device, generator=gen) \
                             * float(data_rng) + float(data_min)
                         reference = None
                     else:

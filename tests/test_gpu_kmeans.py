@@ -135,6 +135,26 @@ def test_config4_size_properties():
     assert frac < 1e-3, frac
 
 
+@pytest.mark.parametrize("draw", ["device", "device32"])
+def test_gap_sweep_device_draws_and_task_mode(draw):
+    """Reference sets drawn on the GPU (float64 like the reference's np.random draws, or float32 opt-in): the gap
+    statistic flattens at the number of blobs, the per-task seeded sweep is reproducible, and float32 draws move the
+    reference term by no more than its own spread."""
+    from deep_interpolation_clustering_b200 import synth
+    from deep_interpolation_clustering_b200.gap import KM
+    from deep_interpolation_clustering_b200.kmeans import KMeansB200
+    X = synth.make_blobs(6000, 64, 4, seed=12).astype(np.float32)
+    def sweep(d):
+        return KM(6).compute_gap_internal_metric(KMeansB200(n_init=2, random_state=2), X, k_max=6, n_references=3,
+                                                 version=1, draw=d, task_parallel=True, seed=1).astype(float)
+    a, b = sweep(draw), sweep(draw)
+    assert np.array_equal(a.to_numpy(), b.to_numpy())
+    assert a["gap"][4] - a["gap"][3] > 10 * abs(a["gap"][5] - a["gap"][4])      # the gap flattens at the 4 blobs
+    ref64 = sweep("device")
+    assert np.allclose(a["ref"], ref64["ref"], atol=5e-3)
+    assert np.allclose(a["act"], ref64["act"], rtol=1e-6)
+
+
 def test_errors():
     from deep_interpolation_clustering_b200.kmeans import KMeansB200
     with pytest.raises(ValueError):
