@@ -83,6 +83,19 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
       : "memory");
 }
+// One lane of a converged warp (cute::elect_one_sync): code under `if (elect_one())` is single-thread by construction.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "elect.sync _|P1, %1;\n\t"
+      "@P1 mov.s32 %0, 1;\n\t"
+      "}\n"
+      : "+r"(pred)
+      : "r"(0xffffffffu));
+  return pred != 0;
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
@@ -605,7 +618,9 @@ pairwise_tc64_kernel(const unsigned char* __restrict__ packed, const float* __re
                      int n_parts, const unsigned* __restrict__ absmax_bits) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   Smem64& S = *reinterpret_cast<Smem64*>(smem_raw);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // the warp index through a shuffle: the compiler then knows that the role branches below are warp-uniform
+  // (cutlass::canonical_warp_idx_sync), which is what lets the MMA operands live in uniform registers
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
   const int64_t nb = (n + kBlk - 1) / kBlk;
 
   if (tid == 0) {
@@ -669,30 +684,44 @@ pairwise_tc64_kernel(const unsigned char* __restrict__ packed, const float* __re
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
-    if (lane == 0) {
+    // The WHOLE warp runs the loop in uniform control flow and only the tcgen05 instructions themselves sit under
+    // `if (elect_one())`: descriptors and addresses are then computed on the uniform datapath and the three MMAs
+    // of a K step issue back to back.  (With the loop inside `if (lane == 0)` every UTCHMMA operand went through
+    // an ELECT / R2UR.BROADCAST waterfall: 96 clk per MMA issued against ~53 clk of tensor-pipe time.)
+    {
+      const bool leader = lane == 0;
+      // redux.sync results are uniform by construction: the compiler cannot know that a shared-memory load is
+      const uint32_t tmem_u = __reduce_or_sync(0xffffffffu, tmem);
+      auto stalled = [&]() { return __reduce_or_sync(0xffffffffu, (unsigned)*timeout) != 0u; };
       int64_t item = 0, g = 0, t = 0;
       long long w_a = 0, w_acc = 0, w_b = 0;
       const long long m0 = clock64();
       const uint32_t a_base = smem_u32(&S.a[0][0][0]);
-      while (it.next(p, j0, j1) && !*timeout) {
+      while (it.next(p, j0, j1) && !stalled()) {
         long long c0 = clock64();
-        if (!bar_wait_bounded(&S.a_full, (uint32_t)(item & 1))) { *timeout = 1; break; }
+        if (!__all_sync(0xffffffffu, bar_wait_bounded(&S.a_full, (uint32_t)(item & 1)))) { *timeout = 1; break; }
         w_a += clock64() - c0;
-        for (int64_t bj = j0; bj < j1 && !*timeout; ++bj, ++t) {
-          const int buf = (int)(t & 1);
+        for (int64_t bj = j0; bj < j1 && !stalled(); ++bj, ++t) {
+          const int buf = (int)__reduce_or_sync(0xffffffffu, (unsigned)(t & 1));          // uniform (see tmem_u)
           c0 = clock64();
-          if (!bar_wait_bounded(&S.acc_empty[buf], (uint32_t)(((t >> 1) & 1) ^ 1))) { *timeout = 1; break; }
+          if (!__all_sync(0xffffffffu, bar_wait_bounded(&S.acc_empty[buf], (uint32_t)(((t >> 1) & 1) ^ 1)))) {
+            *timeout = 1;
+            break;
+          }
           w_acc += clock64() - c0;
           for (int kh = 0; kh < kKParts; ++kh, ++g) {
-            const int slot = (int)(g % kStages);
+            const int slot = (int)__reduce_or_sync(0xffffffffu, (unsigned)(g % kStages));   // uniform
             c0 = clock64();
-            if (!bar_wait_bounded(&S.b_full[slot], (uint32_t)((g / kStages) & 1))) { *timeout = 1; break; }
+            if (!__all_sync(0xffffffffu, bar_wait_bounded(&S.b_full[slot], (uint32_t)((g / kStages) & 1)))) {
+              *timeout = 1;
+              break;
+            }
             w_b += clock64() - c0;
             tc_fence_after();
             const uint32_t b_hi = smem_u32(S.b[slot][0]), b_lo = smem_u32(S.b[slot][1]);
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-              const uint32_t d_tmem = tmem + (uint32_t)((buf * 2 + h) * kBlk);
+              const uint32_t d_tmem = tmem_u + (uint32_t)((buf * 2 + h) * kBlk);
               const uint32_t a_hi = a_base + (uint32_t)(h * kBlockB), a_lo = a_hi + kTileB;
 #pragma unroll
               for (int ks = 0; ks < kKChunks / 2 / kKParts; ++ks) {  // one MMA consumes K = 16 halves = two 16-byte chunks
@@ -703,19 +732,21 @@ pairwise_tc64_kernel(const unsigned char* __restrict__ packed, const float* __re
                 // split float16 (same 11-bit significands as TF32, twice the K per instruction and half the
                 // operand bytes): hi.hi + hi.lo + lo.hi; the dropped lo.lo term is < 2^-22 |x||y|, below the
                 // float32 rounding of the norms it is added to
-                umma_f16(d_tmem, dah, dbh, kIdescF16, (kh > 0 || ks > 0) ? 1u : 0u);
-                umma_f16(d_tmem, dah, dbl, kIdescF16, 1u);
-                umma_f16(d_tmem, dal, dbh, kIdescF16, 1u);
+                if (elect_one()) {
+                  umma_f16(d_tmem, dah, dbh, kIdescF16, (kh > 0 || ks > 0) ? 1u : 0u);
+                  umma_f16(d_tmem, dah, dbl, kIdescF16, 1u);
+                  umma_f16(d_tmem, dal, dbh, kIdescF16, 1u);
+                }
               }
             }
-            umma_commit(&S.b_empty[slot]);             // stage reusable once these MMAs have read it
+            if (elect_one()) umma_commit(&S.b_empty[slot]);   // stage reusable once these MMAs have read it
           }
-          umma_commit(&S.acc_full[buf]);               // both accumulators of the supertile complete
+          if (elect_one()) umma_commit(&S.acc_full[buf]);     // both accumulators of the supertile complete
         }
-        umma_commit(&S.a_empty);                       // row pair may be replaced
+        if (elect_one()) umma_commit(&S.a_empty);             // row pair may be replaced
         ++item;
       }
-      if (dbg && blockIdx.x == 0) {
+      if (dbg && blockIdx.x == 0 && leader) {
         dbg[0] = clock64() - m0; dbg[1] = w_a; dbg[2] = w_acc; dbg[3] = w_b; dbg[4] = t; dbg[5] = item;
       }
     }
@@ -725,6 +756,7 @@ pairwise_tc64_kernel(const unsigned char* __restrict__ packed, const float* __re
     int64_t t = 0;
     bool dead = false;
     long long w_full = 0, w_work = 0;
+    const long long ep0 = clock64();
     while (!dead && it.next(p, j0, j1)) {
       const int64_t bi = 2 * p + h;
       const int64_t i0 = bi * kBlk, gi = i0 + 32 * q + lane;
@@ -733,15 +765,25 @@ pairwise_tc64_kernel(const unsigned char* __restrict__ packed, const float* __re
 #pragma unroll
       for (int k = 0; k < 8; ++k) njr[k] = __ldg(reinterpret_cast<const float4*>(norms + j0 * kBlk) + k);
       int kcur = -1;                       // ROWSUMS: cluster of the column tiles summed into racc so far
-      double racc = 0.0;
+      // Tile sums are collected in a float32 two-sum (value + rounding error, exact to ~2^-48) and turned into
+      // float64 once per item / cluster run: a DADD per tile cost 16 % of this loop's stall samples (ncu).
+      float acc_hi = 0.f, acc_lo = 0.f;
+      auto acc_add = [&](float v) {
+        const float sum = acc_hi + v;
+        const float bb = sum - acc_hi;
+        acc_lo += (acc_hi - (sum - bb)) + (v - bb);
+        acc_hi = sum;
+      };
       for (int64_t bj = j0; bj < j1; ++bj, ++t) {
         const int buf = (int)(t & 1);
         const int64_t c0 = bj * kBlk;
         if (ROWSUMS) {
           const int kc = __ldg(tile_cluster + bj);
           if (kc != kcur) {
-            if (kcur >= 0 && gi < n) atomicAdd(rowsum + gi * K + kcur, racc * (double)inv_scale);
-            racc = 0.0;
+            if (kcur >= 0 && gi < n)
+              atomicAdd(rowsum + gi * K + kcur, ((double)acc_hi + (double)acc_lo) * (double)inv_scale);
+            acc_hi = 0.f;
+            acc_lo = 0.f;
             kcur = kc;
           }
         }
@@ -791,6 +833,7 @@ pairwise_tc64_kernel(const unsigned char* __restrict__ packed, const float* __re
               d[4 * k + 3] = fmaxf(fmaf(-2.f, __uint_as_float(cur[4 * k + 3]), ni + njc[k].w), 0.f);
             }
 #pragma unroll
+            // (x * rsqrt(x) instead of sqrt.approx was measured: no change - the SFU is not what bounds this loop)
             for (int c = 0; c < 32; ++c) d[c] = sqrt_approx(d[c]);
             float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
@@ -829,15 +872,20 @@ pairwise_tc64_kernel(const unsigned char* __restrict__ packed, const float* __re
           if (lane == 0) mbar_arrive(&S.acc_empty[buf]);       // this warp is done with the accumulators
         }
         w_work += clock64() - e1;
-        if (ROWSUMS) racc += (double)tile_sum;
-        else total += (bj == bi) ? (double)tile_sum : 2.0 * (double)tile_sum;
+        acc_add((ROWSUMS || bj == bi) ? tile_sum : 2.f * tile_sum);
       }
-      if (ROWSUMS && kcur >= 0 && gi < n) atomicAdd(rowsum + gi * K + kcur, racc * (double)inv_scale);
+      if (ROWSUMS) {
+        if (kcur >= 0 && gi < n)
+          atomicAdd(rowsum + gi * K + kcur, ((double)acc_hi + (double)acc_lo) * (double)inv_scale);
+      } else {
+        total += (double)acc_hi + (double)acc_lo;
+      }
     }
     total = warp_sum(total);
     if (lane == 0) S.red[ew] = total;
     if (dbg && blockIdx.x == 0 && lane == 0 && (ew == 0 || ew == 5)) {
       dbg[6 + 2 * (ew != 0)] = w_full; dbg[7 + 2 * (ew != 0)] = w_work;
+      if (ew == 0) { dbg[12] = clock64() - ep0; dbg[13] = t; }
     }
   }
 
@@ -925,9 +973,9 @@ static int launch_tc64(const float* X, double* out, void* workspace, int64_t n, 
     const double T = (double)(h[4] ? h[4] : 1);
     fprintf(stderr, "[tc64 profile, CTA 0: %lld supertiles, %lld items, L=%lld] MMA thread: total %.0f | wait A %.0f "
             "acc_empty %.0f B %.0f || epilogue warp 0: wait %.0f work %.0f | warp 5: wait %.0f work %.0f || producer: wait "
-            "a_empty %.0f b_empty %.0f (cycles/supertile)\n",
+            "a_empty %.0f b_empty %.0f | epilogue warp 0 loop total %.0f over %lld tiles (cycles/supertile)\n",
             h[4], h[5], (long long)L, h[0] / T, h[1] / T, h[2] / T, h[3] / T, h[6] / T, h[7] / T, h[8] / T, h[9] / T,
-            h[10] / T, h[11] / T);
+            h[10] / T, h[11] / T, h[12] / T, h[13]);
     cudaFree(dbg);
   }
   DIC_LAUNCH_CHECK("pairwise_tc64_kernel");
