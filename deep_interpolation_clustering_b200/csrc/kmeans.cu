@@ -1517,8 +1517,8 @@ extern "C" int dic_cluster_rowsums(const float* X, const int32_t* perm, const in
   DIC_REQUIRE(n_pad > 0 && n_pad % 128 == 0, DIC_ERR_INVALID_ARGUMENT,
               "n_pad=%lld must be a positive multiple of 128 (clusters padded to whole tiles)", (long long)n_pad);
   DIC_REQUIRE(K > 0, DIC_ERR_INVALID_ARGUMENT, "K=%d", K);
-  DIC_REQUIRE(D > 0 && D <= 64 && D % 4 == 0 && aligned16(X), DIC_ERR_UNSUPPORTED,
-              "the tensor-core row-sum kernel needs D <= 64, D %% 4 == 0 and 16-byte aligned rows (got D=%d)", D);
+  DIC_REQUIRE(D > 0 && D <= 256 && D % 4 == 0 && aligned16(X), DIC_ERR_UNSUPPORTED,
+              "the tensor-core row-sum kernel needs D <= 256, D %% 4 == 0 and 16-byte aligned rows (got D=%d)", D);
   return launch_cluster_rowsums_tc(X, perm, tile_cluster, rowsum, workspace, n_pad, D, K, as_stream(stream));
 }
 

@@ -377,6 +377,7 @@ pairwise_tc_kernel(const float* __restrict__ X, const float* __restrict__ norms,
   } else {
     // ================= epilogue =================
     int i = 0;
+    float acc_hi = 0.f, acc_lo = 0.f;
     for (int64_t t = vcta; t < ntiles; t += vgrid, ++i) {
       int64_t bi, bj;
       unrank_tile(t, nb, bi, bj);
@@ -424,8 +425,15 @@ pairwise_tc_kernel(const float* __restrict__ X, const float* __restrict__ norms,
         atomicAdd((unsigned long long*)&dbg[8], (unsigned long long)(e1 - e0));          // wait accumulator
         atomicAdd((unsigned long long*)&dbg[9], (unsigned long long)(clock64() - e1));   // drain + distances
       }
-      total += (bi == bj) ? (double)tile_sum : 2.0 * (double)tile_sum;
+      {                                             // float32 two-sum: no float64 arithmetic per tile
+        const float v = (bi == bj) ? tile_sum : 2.f * tile_sum;
+        const float sum = acc_hi + v;
+        const float bb = sum - acc_hi;
+        acc_lo += (acc_hi - (sum - bb)) + (v - bb);
+        acc_hi = sum;
+      }
     }
+    total = (double)acc_hi + (double)acc_lo;
   }
 
   __shared__ double red[kThreads / 32];
@@ -475,45 +483,53 @@ __global__ void sum_partials_kernel(const double* __restrict__ ws, double* __res
 namespace tc64 {
 
 constexpr int kBlk = 128;
-constexpr int kTileB = kBlk * 64 * 2;        // 16 KB: one hi or lo operand tile (128 rows x K = 64 halves)
-constexpr int kBlockB = 2 * kTileB;          // 32 KB per packed 128-row block: hi | lo
-constexpr int kKChunks = 8;                  // 16-byte K chunks (8 halves) per row
-constexpr int kKParts = 1;                   // a column tile arrives in kKParts K-slices (one pipeline stage each);
-                                             // measured with float32 tiles: smaller bulk copies are slower
-constexpr int kHalfB = kTileB / kKParts;     // bytes of one K-slice of a hi (or lo) tile
-constexpr int kStages = 128 * 1024 / (2 * kHalfB);  // 128 KB of stages next to the resident 64 KB row pair
+constexpr int kTileB = kBlk * 64 * 2;        // 16 KB: one hi or lo operand tile (128 rows x 64 halves of K)
+constexpr int kChunkB = 2 * kTileB;          // 32 KB: hi | lo of one 64-wide K chunk of a 128-row block
+constexpr int kKSteps = 4;                   // MMAs (K = 16 halves = two 16-byte chunks) per 64-wide K chunk
 constexpr int kEpiWarps = 8;
 constexpr int kThreads64 = 32 * (2 + kEpiWarps);
 
+// NK = 64-wide K chunks per row (D <= 64 NK), NH = 128-row blocks resident per work item.  <1,2>: the layout
+// described above.  <2,2> (D <= 128): 128 KB resident + 3 stages.  <4,1> (D <= 256): ONE row block resident
+// (128 KB), 3 stages, the eight epilogue warps split the 128 columns of its accumulator in halves.
+template <int NK, int NH>
+struct Cfg {
+  static constexpr int kStages = NK == 1 ? 4 : 3;          // 32 KB stages: one K chunk of a column tile each
+  static constexpr int kBlockB = NK * kChunkB;             // bytes of one packed 128-row block
+};
+
+template <int NK, int NH>
 struct __align__(128) Smem64 {
-  unsigned char a[2][2][kTileB];             // [row block of the pair][hi | lo]
-  unsigned char b[kStages][2][kHalfB];       // [stage][hi | lo], one K-slice of a column tile
+  static constexpr int kStages = Cfg<NK, NH>::kStages;
+  unsigned char a[NH][NK][2][kTileB];        // [row block of the item][K chunk][hi | lo]
+  unsigned char b[kStages][2][kTileB];       // [stage][hi | lo], one K chunk of a column tile
   uint64_t a_full, a_empty, b_full[kStages], b_empty[kStages], acc_full[2], acc_empty[2];
   double red[kEpiWarps];
   uint32_t tmem_base;
   int timeout;
 };
 
-// The sequence of work items of CTA `cta`: segment s covers column tiles [sL, (s+1)L); row pair p takes
-// part in it when 2p < (s+1)L.  Item (s, p) has global index w(s) + p and belongs to CTA (w(s) + p) % G.
+// The sequence of work items of CTA `cta`: segment s covers column tiles [sL, (s+1)L); row group p (nh row
+// blocks) takes part in it when nh p < (s+1)L.  Item (s, p) has global index w(s) + p and belongs to CTA
+// (w(s) + p) % G.
 struct ItemIter {
   int64_t nb, P, S, s, w, p;
-  int L, G, cta;
+  int L, G, cta, nh;
   bool full;     // true: the whole nb x nb grid of tiles (row sums); false: the upper triangle (symmetric sum)
-  __device__ void init(int64_t nb_, int L_, int G_, int cta_, bool full_) {
-    nb = nb_; L = L_; G = G_; cta = cta_; full = full_;
-    P = (nb + 1) / 2;
+  __device__ void init(int64_t nb_, int L_, int G_, int cta_, bool full_, int nh_) {
+    nb = nb_; L = L_; G = G_; cta = cta_; full = full_; nh = nh_;
+    P = (nb + nh - 1) / nh;
     S = (nb + L - 1) / L;
     s = 0; w = 0;
     p = first();
   }
   __device__ int64_t first() const { return (int64_t)((((cta - w) % G) + G) % G); }
-  __device__ int64_t pmax() const { return full ? P - 1 : min(P - 1, ((s + 1) * L - 1) / 2); }
+  __device__ int64_t pmax() const { return full ? P - 1 : min(P - 1, ((s + 1) * L - 1) / nh); }
   __device__ bool next(int64_t& op, int64_t& j0, int64_t& j1) {
     while (s < S) {
       if (p <= pmax()) {
         op = p;
-        j0 = full ? s * L : max(s * L, 2 * p);
+        j0 = full ? s * L : max(s * L, (int64_t)nh * p);
         j1 = min((s + 1) * L, nb);
         p += G;
         return true;
@@ -545,15 +561,16 @@ __device__ __forceinline__ void load_row_chunk(const float* __restrict__ X, int6
   v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
 
+template <int NK>
 __global__ void __launch_bounds__(256)
 absmax_kernel(const float* __restrict__ X, unsigned* __restrict__ absmax_bits, int64_t n, int D,
               const int32_t* __restrict__ perm) {
   const int64_t blk = blockIdx.x;
   float m = 0.f;
 #pragma unroll
-  for (int it = 0; it < 4; ++it) {
+  for (int it = 0; it < 4 * NK; ++it) {
     const int idx = it * 256 + threadIdx.x;
-    const int row = idx >> 3, c = idx & 7;
+    const int row = idx / (8 * NK), c = idx % (8 * NK);
     const int64_t gr = blk * kBlk + row;
     const int64_t src = gr < n ? (perm ? (int64_t)__ldg(perm + gr) : gr) : -1;
     float v[8];
@@ -566,20 +583,22 @@ absmax_kernel(const float* __restrict__ X, unsigned* __restrict__ absmax_bits, i
   if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(absmax_bits, __float_as_uint(m));
 }
 
-// X (n x D, D <= 64, D % 4 == 0) -> packed split-float16 operand tiles (hi = rn_f16(s x), lo = rn_f16(s x - hi)) +
-// row norms of s x; rows >= n and K >= D are zero.  One CTA per 128-row block, thread -> (row, 16-byte K chunk).
+// X (n x D, D <= 64 NK, D % 4 == 0) -> packed split-float16 operand tiles (hi = rn_f16(s x), lo = rn_f16(s x - hi);
+// per 128-row block NK images [hi | lo] of 64-wide K chunks) + row norms of s x; rows >= n and K >= D are zero.
+// One CTA per 128-row block, thread -> (row, 16-byte K chunk); the 8 NK chunks of a row sit in adjacent lanes.
+template <int NK>
 __global__ void __launch_bounds__(256)
 pack_split_kernel(const float* __restrict__ X, unsigned char* __restrict__ packed, float* __restrict__ norms,
                   int64_t n, int D, const int32_t* __restrict__ perm, float pad_norm,
                   const unsigned* __restrict__ absmax_bits) {
   const int64_t blk = blockIdx.x;
-  unsigned char* out = packed + blk * (int64_t)kBlockB;
+  unsigned char* out = packed + blk * (int64_t)(NK * kChunkB);
   float inv;
   const float scale = f16_scale(__ldg(absmax_bits), &inv);
 #pragma unroll
-  for (int it = 0; it < 4; ++it) {
+  for (int it = 0; it < 4 * NK; ++it) {
     const int idx = it * 256 + threadIdx.x;
-    const int row = idx >> 3, c = idx & 7;
+    const int row = idx / (8 * NK), c = idx % (8 * NK);
     const int64_t gr = blk * kBlk + row;
     // perm (row-sums mode): packed row gr holds X[perm[gr]], perm < 0 = padding between clusters
     const int64_t src = gr < n ? (perm ? (int64_t)__ldg(perm + gr) : gr) : -1;
@@ -595,11 +614,11 @@ pack_split_kernel(const float* __restrict__ X, unsigned char* __restrict__ packe
       l[k] = __halves2half2(__float2half_rn(x0 - __half2float(h0)), __float2half_rn(x1 - __half2float(h1)));
       s = fmaf(x0, x0, fmaf(x1, x1, s));
     }
-    const int off = c * kChunkStride + (row >> 3) * kGroupStride + (row & 7) * 16;
+    const int off = (c >> 3) * kChunkB + (c & 7) * kChunkStride + (row >> 3) * kGroupStride + (row & 7) * 16;
     *reinterpret_cast<uint4*>(out + off) = *reinterpret_cast<const uint4*>(h);
     *reinterpret_cast<uint4*>(out + kTileB + off) = *reinterpret_cast<const uint4*>(l);
 #pragma unroll
-    for (int o = 4; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    for (int o = 4 * NK; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     // a padding row gets pad_norm: -inf makes every distance to it exactly 0 (max(-inf, 0) under the sqrt)
     if (c == 0) norms[gr] = src >= 0 ? s : pad_norm;
   }
@@ -610,14 +629,17 @@ pack_split_kernel(const float* __restrict__ X, unsigned char* __restrict__ packe
 //                  rows carry norm = -inf => distance 0), tile_cluster[bj] names the cluster of column tile
 //                  bj, and rowsum[i][k] += sum_{j in tile, cluster k} ||x_i - x_j|| over the FULL grid: what
 //                  the silhouette needs (sklearn.metrics.silhouette_samples) without the n x n matrix.
-template <bool ROWSUMS>
+template <bool ROWSUMS, int NK, int NH>
 __global__ void __launch_bounds__(kThreads64, 1)
 pairwise_tc64_kernel(const unsigned char* __restrict__ packed, const float* __restrict__ norms,
                      double* __restrict__ partial, int64_t n, int L, long long* __restrict__ dbg,
                      const int32_t* __restrict__ tile_cluster, double* __restrict__ rowsum, int K, int part,
                      int n_parts, const unsigned* __restrict__ absmax_bits) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  Smem64& S = *reinterpret_cast<Smem64*>(smem_raw);
+  using SmemT = Smem64<NK, NH>;
+  constexpr int kStages = SmemT::kStages;
+  constexpr int kBlockB = NK * kChunkB;
+  SmemT& S = *reinterpret_cast<SmemT*>(smem_raw);
   // the warp index through a shuffle: the compiler then knows that the role branches below are warp-uniform
   // (cutlass::canonical_warp_idx_sync), which is what lets the MMA operands live in uniform registers
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
@@ -649,7 +671,7 @@ pairwise_tc64_kernel(const unsigned char* __restrict__ packed, const float* __re
   ItemIter it;
   // stripe `part` of `n_parts` (multi-GPU): this CTA takes the items of CTA blockIdx.x * n_parts + part of a grid
   // n_parts times as large, so the stripes of all parts tile the item list exactly once
-  it.init(nb, L, (int)gridDim.x * n_parts, (int)blockIdx.x * n_parts + part, ROWSUMS);
+  it.init(nb, L, (int)gridDim.x * n_parts, (int)blockIdx.x * n_parts + part, ROWSUMS, NH);
   int64_t p, j0, j1;
   double total = 0.0;
 
@@ -662,20 +684,21 @@ pairwise_tc64_kernel(const unsigned char* __restrict__ packed, const float* __re
         long long c0 = clock64();
         if (!bar_wait_bounded(&S.a_empty, (uint32_t)((item & 1) ^ 1))) { *timeout = 1; break; }
         pw_a += clock64() - c0;
-        mbar_expect_tx(&S.a_full, 2u * kBlockB);
-        const unsigned char* arow = packed + 2 * p * (int64_t)kBlockB;     // blocks 2p, 2p+1 are adjacent
+        mbar_expect_tx(&S.a_full, (uint32_t)(NH * kBlockB));
+        const unsigned char* arow = packed + NH * p * (int64_t)kBlockB;    // the NH blocks of the item are adjacent
 #pragma unroll
-        for (int q = 0; q < 4; ++q) bulk_g2s(&S.a[0][0][0] + q * kTileB, arow + q * kTileB, kTileB, &S.a_full);
+        for (int q = 0; q < 2 * NH * NK; ++q)
+          bulk_g2s(&S.a[0][0][0][0] + q * kTileB, arow + q * kTileB, kTileB, &S.a_full);
         for (int64_t bj = j0; bj < j1 && !*timeout; ++bj) {
           const unsigned char* bcol = packed + bj * (int64_t)kBlockB;
-          for (int kh = 0; kh < kKParts; ++kh, ++g) {
+          for (int kc = 0; kc < NK; ++kc, ++g) {
             const int slot = (int)(g % kStages);
             c0 = clock64();
             if (!bar_wait_bounded(&S.b_empty[slot], (uint32_t)(((g / kStages) & 1) ^ 1))) { *timeout = 1; break; }
             pw_b += clock64() - c0;
-            mbar_expect_tx(&S.b_full[slot], 2u * kHalfB);
-            bulk_g2s(S.b[slot][0], bcol + kh * kHalfB, kHalfB, &S.b_full[slot]);
-            bulk_g2s(S.b[slot][1], bcol + kTileB + kh * kHalfB, kHalfB, &S.b_full[slot]);
+            mbar_expect_tx(&S.b_full[slot], (uint32_t)kChunkB);
+            bulk_g2s(S.b[slot][0], bcol + kc * kChunkB, kTileB, &S.b_full[slot]);
+            bulk_g2s(S.b[slot][1], bcol + kc * kChunkB + kTileB, kTileB, &S.b_full[slot]);
           }
         }
         ++item;
@@ -696,7 +719,7 @@ pairwise_tc64_kernel(const unsigned char* __restrict__ packed, const float* __re
       int64_t item = 0, g = 0, t = 0;
       long long w_a = 0, w_acc = 0, w_b = 0;
       const long long m0 = clock64();
-      const uint32_t a_base = smem_u32(&S.a[0][0][0]);
+      const uint32_t a_base = smem_u32(&S.a[0][0][0][0]);
       while (it.next(p, j0, j1) && !stalled()) {
         long long c0 = clock64();
         if (!__all_sync(0xffffffffu, bar_wait_bounded(&S.a_full, (uint32_t)(item & 1)))) { *timeout = 1; break; }
@@ -709,7 +732,7 @@ pairwise_tc64_kernel(const unsigned char* __restrict__ packed, const float* __re
             break;
           }
           w_acc += clock64() - c0;
-          for (int kh = 0; kh < kKParts; ++kh, ++g) {
+          for (int kc = 0; kc < NK; ++kc, ++g) {
             const int slot = (int)__reduce_or_sync(0xffffffffu, (unsigned)(g % kStages));   // uniform
             c0 = clock64();
             if (!__all_sync(0xffffffffu, bar_wait_bounded(&S.b_full[slot], (uint32_t)((g / kStages) & 1)))) {
@@ -720,20 +743,20 @@ pairwise_tc64_kernel(const unsigned char* __restrict__ packed, const float* __re
             tc_fence_after();
             const uint32_t b_hi = smem_u32(S.b[slot][0]), b_lo = smem_u32(S.b[slot][1]);
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const uint32_t d_tmem = tmem_u + (uint32_t)((buf * 2 + h) * kBlk);
-              const uint32_t a_hi = a_base + (uint32_t)(h * kBlockB), a_lo = a_hi + kTileB;
+            for (int h = 0; h < NH; ++h) {
+              const uint32_t d_tmem = tmem_u + (uint32_t)((buf * NH + h) * kBlk);
+              const uint32_t a_hi = a_base + (uint32_t)(h * kBlockB) + (uint32_t)kc * (uint32_t)kChunkB;
+              const uint32_t a_lo = a_hi + kTileB;
 #pragma unroll
-              for (int ks = 0; ks < kKChunks / 2 / kKParts; ++ks) {  // one MMA consumes K = 16 halves = two 16-byte chunks
-                const uint32_t ka = (uint32_t)((kh * (kKChunks / kKParts) + ks * 2) * kChunkStride);
-                const uint32_t kb = (uint32_t)(ks * 2 * kChunkStride);
-                const uint64_t dah = make_desc(a_hi + ka), dal = make_desc(a_lo + ka);
-                const uint64_t dbh = make_desc(b_hi + kb), dbl = make_desc(b_lo + kb);
+              for (int ks = 0; ks < kKSteps; ++ks) {      // one MMA consumes K = 16 halves = two 16-byte chunks
+                const uint32_t kk = (uint32_t)(ks * 2 * kChunkStride);
+                const uint64_t dah = make_desc(a_hi + kk), dal = make_desc(a_lo + kk);
+                const uint64_t dbh = make_desc(b_hi + kk), dbl = make_desc(b_lo + kk);
                 // split float16 (same 11-bit significands as TF32, twice the K per instruction and half the
                 // operand bytes): hi.hi + hi.lo + lo.hi; the dropped lo.lo term is < 2^-22 |x||y|, below the
                 // float32 rounding of the norms it is added to
                 if (elect_one()) {
-                  umma_f16(d_tmem, dah, dbh, kIdescF16, (kh > 0 || ks > 0) ? 1u : 0u);
+                  umma_f16(d_tmem, dah, dbh, kIdescF16, (kc > 0 || ks > 0) ? 1u : 0u);
                   umma_f16(d_tmem, dah, dbl, kIdescF16, 1u);
                   umma_f16(d_tmem, dal, dbh, kIdescF16, 1u);
                 }
@@ -741,9 +764,9 @@ pairwise_tc64_kernel(const unsigned char* __restrict__ packed, const float* __re
             }
             if (elect_one()) umma_commit(&S.b_empty[slot]);   // stage reusable once these MMAs have read it
           }
-          if (elect_one()) umma_commit(&S.acc_full[buf]);     // both accumulators of the supertile complete
+          if (elect_one()) umma_commit(&S.acc_full[buf]);     // the NH accumulators of the supertile are complete
         }
-        if (elect_one()) umma_commit(&S.a_empty);             // row pair may be replaced
+        if (elect_one()) umma_commit(&S.a_empty);             // the resident row blocks may be replaced
         ++item;
       }
       if (dbg && blockIdx.x == 0 && leader) {
@@ -751,19 +774,23 @@ pairwise_tc64_kernel(const unsigned char* __restrict__ packed, const float* __re
       }
     }
   } else {
-    // ================= epilogue: 8 warps, (row block h, TMEM lane quarter q) =================
-    const int ew = warp - 2, h = ew >> 2, q = warp & 3;
+    // ================= epilogue: 8 warps, (row block h | column half, TMEM lane quarter q) =================
+    // NH = 2: warps 0-3 drain row block 0, warps 4-7 row block 1, all 128 columns (CC = 4 chunks of 32).
+    // NH = 1: both sets drain the one row block, columns [0, 64) and [64, 128) (CC = 2 chunks from chunk cbeg).
+    constexpr int CC = NH == 2 ? 4 : 2;
+    const int ew = warp - 2, q = warp & 3;
+    const int h = NH == 2 ? ew >> 2 : 0, cbeg = NH == 2 ? 0 : 2 * (ew >> 2);
     int64_t t = 0;
     bool dead = false;
     long long w_full = 0, w_work = 0;
     const long long ep0 = clock64();
     while (!dead && it.next(p, j0, j1)) {
-      const int64_t bi = 2 * p + h;
+      const int64_t bi = NH * p + h;
       const int64_t i0 = bi * kBlk, gi = i0 + 32 * q + lane;
       const float ni = gi < n ? __ldg(norms + gi) : 0.f;
       float4 njr[8];                       // norms of the next 32 columns to be processed, prefetched
 #pragma unroll
-      for (int k = 0; k < 8; ++k) njr[k] = __ldg(reinterpret_cast<const float4*>(norms + j0 * kBlk) + k);
+      for (int k = 0; k < 8; ++k) njr[k] = __ldg(reinterpret_cast<const float4*>(norms + j0 * kBlk + 32 * cbeg) + k);
       int kcur = -1;                       // ROWSUMS: cluster of the column tiles summed into racc so far
       // Tile sums are collected in a float32 two-sum (value + rounding error, exact to ~2^-48) and turned into
       // float64 once per item / cluster run: a DADD per tile cost 16 % of this loop's stall samples (ncu).
@@ -797,20 +824,20 @@ pairwise_tc64_kernel(const unsigned char* __restrict__ packed, const float* __re
         const bool active = ROWSUMS ? (i0 < n) : ((bj >= bi) && (i0 < n));
         const bool plain = ROWSUMS ? (active && bj != bi)
                                    : (active && (bj > bi) && (i0 + kBlk <= n) && (c0 + kBlk <= n));   // no diagonal / ragged edge
-        const uint32_t taddr = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)((buf * 2 + h) * kBlk);
+        const uint32_t taddr = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)((buf * NH + h) * kBlk + 32 * cbeg);
         bool released = false;
         if (plain) {
-          // Software pipeline over the four 32-column chunks: the TMEM load of chunk c+1 and the norms of
+          // Software pipeline over the CC 32-column chunks: the TMEM load of chunk c+1 and the norms of
           // chunk c+1 (the first chunk of the NEXT column tile after the last one) are in flight while
           // chunk c is turned into distances.
           uint32_t va[32], vb[32];
           tmem_ld32_issue(taddr, va);
 #pragma unroll
-          for (int cc = 0; cc < 4; ++cc) {
+          for (int cc = 0; cc < CC; ++cc) {
             uint32_t(&cur)[32] = (cc & 1) ? vb : va;
             uint32_t(&nxt)[32] = (cc & 1) ? va : vb;
             tmem_ld_wait(cur);
-            if (cc < 3) {
+            if (cc < CC - 1) {
               tmem_ld32_issue(taddr + 32 * (cc + 1), nxt);
             } else {                     // everything is in registers: hand the accumulators back early
               tc_fence_before();
@@ -821,7 +848,8 @@ pairwise_tc64_kernel(const unsigned char* __restrict__ packed, const float* __re
             float4 njc[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) njc[k] = njr[k];
-            const float* nxp = norms + c0 + 32 * (cc + 1);      // cc == 3: chunk 0 of tile bj + 1 (norms is padded)
+            // the chunk after the last one is this warp's first chunk of tile bj + 1 (norms is padded)
+            const float* nxp = norms + c0 + 32 * cbeg + (cc + 1 < CC ? 32 * (cc + 1) : kBlk);
 #pragma unroll
             for (int k = 0; k < 8; ++k) njr[k] = __ldg(reinterpret_cast<const float4*>(nxp) + k);
             float d[32];
@@ -848,12 +876,13 @@ pairwise_tc64_kernel(const unsigned char* __restrict__ packed, const float* __re
         } else {
           if (active) {                    // warp-uniform: tcgen05.ld is .sync.aligned (all 32 lanes take part)
 #pragma unroll 1
-            for (int cc = 0; cc < 4; ++cc) {
+            for (int cc = 0; cc < CC; ++cc) {
               uint32_t v[32];
               tmem_ld32(taddr + 32 * cc, v);
-              const float* njp = norms + c0 + 32 * cc;
-              const int jmax = gi < n ? (ROWSUMS ? 32 : (int)min((int64_t)32, n - c0 - 32 * cc)) : 0;   // valid columns
-              const int jdiag = (int)(gi - c0 - 32 * cc);                     // the diagonal, if inside
+              const int64_t col0 = c0 + 32 * (cbeg + cc);
+              const float* njp = norms + col0;
+              const int jmax = gi < n ? (ROWSUMS ? 32 : (int)min((int64_t)32, n - col0)) : 0;   // valid columns
+              const int jdiag = (int)(gi - col0);                             // the diagonal, if inside
 #pragma unroll
               for (int c = 0; c < 32; ++c) {
                 const float d2 = fmaf(-2.f, __uint_as_float(v[c]), ni + __ldg(njp + c));   // norms is padded
@@ -864,7 +893,7 @@ pairwise_tc64_kernel(const unsigned char* __restrict__ packed, const float* __re
           }
 #pragma unroll
           for (int k = 0; k < 8; ++k)      // keep the prefetch invariant: njr = chunk 0 of the next column tile
-            njr[k] = __ldg(reinterpret_cast<const float4*>(norms + c0 + kBlk) + k);
+            njr[k] = __ldg(reinterpret_cast<const float4*>(norms + c0 + kBlk + 32 * cbeg) + k);
         }
         if (!released) {
           tc_fence_before();
@@ -908,20 +937,25 @@ pairwise_tc64_kernel(const unsigned char* __restrict__ packed, const float* __re
 }  // namespace
 
 static int64_t tc64_blocks(int64_t n) { return ((n + tc64::kBlk - 1) / tc64::kBlk + 1) / 2 * 2; }   // even
+static int tc64_nk(int D) { return D <= 64 ? 1 : (D <= 128 ? 2 : 4); }   // 64-wide K chunks per row (K zero-padded)
+constexpr int kTc64MaxD = 256;
 
 size_t pairwise_tc_workspace_bytes(int64_t n, int D) {
-  if (D <= 64)   // packed operand tiles | norms (padded) | partials
-    return (size_t)tc64_blocks(n) * (tc64::kBlockB + tc64::kBlk * sizeof(float)) + tc64::kBlk * sizeof(float) +
-           1024 * sizeof(double) + 256 + 1024;
-  return ((size_t)n * sizeof(float) + 255) / 256 * 256 + 1024 * sizeof(double);
+  const size_t v1 = ((size_t)n * sizeof(float) + 255) / 256 * 256 + 1024 * sizeof(double);
+  if (D > kTc64MaxD) return v1;
+  // packed operand tiles | norms (padded) | partials | scale
+  const size_t v2 = (size_t)tc64_blocks(n) * ((size_t)tc64_nk(D) * tc64::kChunkB + tc64::kBlk * sizeof(float)) +
+                    tc64::kBlk * sizeof(float) + 1024 * sizeof(double) + 256 + 1024;
+  return v2 > v1 ? v2 : v1;
 }
 
 // Shared launcher.  rowsum == nullptr: pairwise sum of the n rows of X -> out.  Otherwise: X is read
 // through perm (n = padded row count), rowsum (n, K) is zeroed and filled.
-static int launch_tc64(const float* X, double* out, void* workspace, int64_t n, int D, const int32_t* perm,
-                       const int32_t* tile_cluster, double* rowsum, int K, cudaStream_t st, int part = 0,
-                       int n_parts = 1) {
+template <int NK, int NH>
+static int launch_tc64_t(const float* X, double* out, void* workspace, int64_t n, int D, const int32_t* perm,
+                         const int32_t* tile_cluster, double* rowsum, int K, cudaStream_t st, int part, int n_parts) {
   using namespace tc64;
+  constexpr int kBlockB = NK * kChunkB;
   const bool rows_mode = rowsum != nullptr;
   const int64_t nblk = tc64_blocks(n), nb = (n + kBlk - 1) / kBlk;
   unsigned char* packed = static_cast<unsigned char*>(workspace);          // cudaMalloc alignment (>= 256)
@@ -934,48 +968,51 @@ static int launch_tc64(const float* X, double* out, void* workspace, int64_t n, 
   DIC_CUDA(cudaMemsetAsync(absmax, 0, sizeof(unsigned), st));
   if (rows_mode) DIC_CUDA(cudaMemsetAsync(rowsum, 0, (size_t)n * K * sizeof(double), st));
   const float pad_norm = rows_mode ? -INFINITY : 0.f;
-  absmax_kernel<<<(unsigned)nblk, 256, 0, st>>>(X, absmax, n, D, perm);
+  absmax_kernel<NK><<<(unsigned)nblk, 256, 0, st>>>(X, absmax, n, D, perm);
   DIC_LAUNCH_CHECK("absmax_kernel");
-  pack_split_kernel<<<(unsigned)nblk, 256, 0, st>>>(X, packed, norms, n, D, perm, pad_norm, absmax);
+  pack_split_kernel<NK><<<(unsigned)nblk, 256, 0, st>>>(X, packed, norms, n, D, perm, pad_norm, absmax);
   DIC_LAUNCH_CHECK("pack_split_kernel");
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int64_t P = (nb + 1) / 2;
-  const int64_t supertiles = rows_mode ? P * nb : P * nb - P * (P - 1);    // full grid | sum_p (nb - 2p)
+  const int64_t P = (nb + NH - 1) / NH;
+  const int64_t supertiles = rows_mode ? P * nb : P * nb - NH * P * (P - 1) / 2;   // full grid | sum_p (nb - NH p)
   int64_t L = supertiles / (8 * (int64_t)sms);
   L = L < 2 ? 2 : (L > 64 ? 64 : L);
   int64_t items = 0;
   for (int64_t s = 0; s * L < nb; ++s)
-    items += rows_mode ? P : (((s + 1) * L - 1) / 2 < P - 1 ? ((s + 1) * L - 1) / 2 + 1 : P);
+    items += rows_mode ? P : (((s + 1) * L - 1) / NH < P - 1 ? ((s + 1) * L - 1) / NH + 1 : P);
   const int64_t my_items = items / n_parts > 0 ? items / n_parts : 1;
   int blocks = (int)(my_items < sms ? my_items : sms);
   if (blocks > 1024) blocks = 1024;
-  const size_t smem = sizeof(Smem64) + 1024;
+  const size_t smem = sizeof(Smem64<NK, NH>) + 1024;
   long long* dbg = nullptr;
   if (getenv("DIC_TC_PROFILE")) {          // debug: per-role cycle counters of CTA 0, printed after the run
     cudaMalloc(&dbg, 16 * sizeof(long long));
     cudaMemsetAsync(dbg, 0, 16 * sizeof(long long), st);
   }
   if (rows_mode) {
-    DIC_CUDA(cudaFuncSetAttribute(pairwise_tc64_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    pairwise_tc64_kernel<true><<<blocks, kThreads64, smem, st>>>(packed, norms, partial, n, (int)L, dbg, tile_cluster,
-                                                                 rowsum, K, part, n_parts, absmax);
+    auto kern = pairwise_tc64_kernel<true, NK, NH>;
+    DIC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<blocks, kThreads64, smem, st>>>(packed, norms, partial, n, (int)L, dbg, tile_cluster, rowsum, K, part,
+                                           n_parts, absmax);
   } else {
-    DIC_CUDA(cudaFuncSetAttribute(pairwise_tc64_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    pairwise_tc64_kernel<false><<<blocks, kThreads64, smem, st>>>(packed, norms, partial, n, (int)L, dbg, nullptr,
-                                                                  nullptr, 0, part, n_parts, absmax);
+    auto kern = pairwise_tc64_kernel<false, NK, NH>;
+    DIC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<blocks, kThreads64, smem, st>>>(packed, norms, partial, n, (int)L, dbg, nullptr, nullptr, 0, part, n_parts,
+                                           absmax);
   }
   if (dbg) {
     long long h[16];
     cudaMemcpyAsync(h, dbg, sizeof(h), cudaMemcpyDeviceToHost, st);
     cudaStreamSynchronize(st);
     const double T = (double)(h[4] ? h[4] : 1);
-    fprintf(stderr, "[tc64 profile, CTA 0: %lld supertiles, %lld items, L=%lld] MMA thread: total %.0f | wait A %.0f "
-            "acc_empty %.0f B %.0f || epilogue warp 0: wait %.0f work %.0f | warp 5: wait %.0f work %.0f || producer: wait "
-            "a_empty %.0f b_empty %.0f | epilogue warp 0 loop total %.0f over %lld tiles (cycles/supertile)\n",
-            h[4], h[5], (long long)L, h[0] / T, h[1] / T, h[2] / T, h[3] / T, h[6] / T, h[7] / T, h[8] / T, h[9] / T,
-            h[10] / T, h[11] / T, h[12] / T, h[13]);
+    fprintf(stderr, "[tc64 profile <NK=%d,NH=%d>, CTA 0: %lld supertiles, %lld items, L=%lld] MMA thread: total %.0f | "
+            "wait A %.0f acc_empty %.0f B %.0f || epilogue warp 0: wait %.0f work %.0f | warp 5: wait %.0f work %.0f || "
+            "producer: wait a_empty %.0f b_empty %.0f | epilogue warp 0 loop total %.0f over %lld tiles "
+            "(cycles/supertile)\n",
+            NK, NH, h[4], h[5], (long long)L, h[0] / T, h[1] / T, h[2] / T, h[3] / T, h[6] / T, h[7] / T, h[8] / T,
+            h[9] / T, h[10] / T, h[11] / T, h[12] / T, h[13]);
     cudaFree(dbg);
   }
   DIC_LAUNCH_CHECK("pairwise_tc64_kernel");
@@ -984,6 +1021,16 @@ static int launch_tc64(const float* X, double* out, void* workspace, int64_t n, 
     DIC_LAUNCH_CHECK("sum_partials_kernel");
   }
   return DIC_OK;
+}
+
+static int launch_tc64(const float* X, double* out, void* workspace, int64_t n, int D, const int32_t* perm,
+                       const int32_t* tile_cluster, double* rowsum, int K, cudaStream_t st, int part = 0,
+                       int n_parts = 1) {
+  switch (tc64_nk(D)) {
+    case 1: return launch_tc64_t<1, 2>(X, out, workspace, n, D, perm, tile_cluster, rowsum, K, st, part, n_parts);
+    case 2: return launch_tc64_t<2, 2>(X, out, workspace, n, D, perm, tile_cluster, rowsum, K, st, part, n_parts);
+    default: return launch_tc64_t<4, 1>(X, out, workspace, n, D, perm, tile_cluster, rowsum, K, st, part, n_parts);
+  }
 }
 
 static int launch_pairwise_tc64(const float* X, double* out, void* workspace, int64_t n, int D, cudaStream_t st,
@@ -1002,7 +1049,7 @@ bool pairwise_tc_supported(const void* X, int D) { return D % 4 == 0 && D >= 4 &
 int launch_pairwise_tc(const float* X, double* out, void* workspace, int64_t n, int D, cudaStream_t st, int part,
                        int n_parts) {
   static const bool force_v1 = getenv("DIC_PAIRWISE_TC_V1") != nullptr;      // debug: the register-staged kernel
-  if (D <= 64 && !force_v1) return launch_pairwise_tc64(X, out, workspace, n, D, st, part, n_parts);
+  if (D <= kTc64MaxD && !force_v1) return launch_pairwise_tc64(X, out, workspace, n, D, st, part, n_parts);
   float* norms = static_cast<float*>(workspace);
   double* partial = reinterpret_cast<double*>(static_cast<unsigned char*>(workspace) +
                                               ((size_t)n * sizeof(float) + 255) / 256 * 256);

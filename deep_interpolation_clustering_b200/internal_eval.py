@@ -3,7 +3,7 @@
 Mirror of internal_eval.py:112-147 (same class names, ``metric(x, labels)`` call signature).
 SURVEY.md section 8(f) ranks these as the first "next" row after the hot path.  Status:
 Calinski-Harabasz and Davies-Bouldin are O(N K D) and run as device reductions.  Silhouette is
-O(N^2): for D <= 64 its per-row, per-cluster distance sums come from the tcgen05 tile kernel
+O(N^2): for D <= 256 its per-row, per-cluster distance sums come from the tcgen05 tile kernel
 (``dic_cluster_rowsums``: rows sorted by cluster, clusters padded to whole 128-row tiles, nothing
 materialised); other shapes and Dunn use chunked device distance tiles (torch.cdist, library code).
 Formulas follow sklearn.metrics 1.9.0 (_unsupervised.py).
@@ -115,7 +115,7 @@ class Sihouette(object):
         x, inv, K = _prep(x, labels)
         N = x.shape[0]
         cnt = torch.bincount(inv, minlength=K).to(x.dtype)
-        if self.native and x.is_cuda and N >= TC_MIN_ROWS and x.shape[1] <= 64 and x.shape[1] % 4 == 0:
+        if self.native and x.is_cuda and N >= TC_MIN_ROWS and x.shape[1] <= 256 and x.shape[1] % 4 == 0:
             per_cluster = self.rowsums_native(x.to(torch.float32), inv, K)
             return float(self._finish(per_cluster, inv, cnt) / N)
         onehot = torch.zeros((N, K), dtype=x.dtype, device=x.device)

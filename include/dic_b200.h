@@ -231,7 +231,7 @@ int dic_pairwise_dist_sum_part(const void* Xc, double* out, void* workspace, int
  * The caller sorts the rows by cluster and pads every cluster to whole 128-row tiles:
  *   perm (n_pad) int32: source row of packed row i, -1 = padding (contributes exactly 0);
  *   tile_cluster (n_pad / 128) int32: cluster of each 128-row tile.
- * Limits: D <= 64, D % 4 == 0.  workspace: dic_pairwise_workspace_bytes(n_pad, D). */
+ * Limits: D <= 256, D % 4 == 0.  workspace: dic_pairwise_workspace_bytes(n_pad, D). */
 int dic_cluster_rowsums(const float* X, const int32_t* perm, const int32_t* tile_cluster,
                         double* rowsum, void* workspace, int64_t n_pad, int D, int K,
                         dic_stream_t stream);

@@ -163,7 +163,8 @@ def test_errors():
         KMeansB200(n_clusters=2, init=np.zeros((3, 4))).fit(np.zeros((10, 4), np.float32))
 
 
-@pytest.mark.parametrize("n,D", [(3000, 64), (1000, 40), (700, 256), (4097, 8), (16385, 64), (40000, 48), (513, 4)])
+@pytest.mark.parametrize("n,D", [(3000, 64), (1000, 40), (700, 256), (4097, 8), (16385, 64), (40000, 48), (513, 4),
+                                 (16385, 256), (9000, 128), (5001, 100), (2000, 192), (3000, 300)])
 def test_tensor_core_pairwise_matches_exact(n, D):
     """tcgen05 (3xTF32) pairwise-distance sum vs the direct float64 kernel and numpy."""
     from deep_interpolation_clustering_b200 import synth
@@ -199,7 +200,8 @@ def test_pairwise_stripes_add_up(n, D, dtype, n_parts):
     record(f"pairwise_parts_n{n}_D{D}_{dtype}_p{n_parts}", sum(parts), full, 1e-9, 0)
 
 
-@pytest.mark.parametrize("n,D,K", [(5000, 64, 5), (3001, 20, 7), (20000, 32, 3)])
+@pytest.mark.parametrize("n,D,K", [(5000, 64, 5), (3001, 20, 7), (20000, 32, 3), (4000, 256, 4), (2500, 128, 3),
+                                   (3000, 100, 5)])
 def test_silhouette_tensor_core_matches_float64(n, D, K):
     """dic_cluster_rowsums (tcgen05 row sums by cluster) vs the chunked float64 distance path and sklearn:
     ragged cluster sizes, a singleton cluster, D < 64."""
@@ -226,7 +228,10 @@ def test_silhouette_tensor_core_matches_float64(n, D, K):
     for a, i in enumerate(rows):
         d = np.sqrt(((X64[i] - X64) ** 2).sum(1))
         ref[a] = np.bincount(inv_h, weights=d, minlength=Kp)
-    record(f"cluster_rowsums_n{n}_D{D}_K{K}", sums[rows], ref, 1e-5, 1e-6)     # float32-grade sums (3xTF32, sqrt.approx)
+    # float32-grade sums (split operands, float32 accumulation in the tensor core, sqrt.approx).  Intra-blob distances
+    # are differences of large norms (|x|^2 ~ 17 D against d^2 ~ 2 D here) and the accumulator's error grows with the
+    # number of products, so the raw sums get 3e-5 above D = 64; the silhouette itself stays within 1e-5 (above).
+    record(f"cluster_rowsums_n{n}_D{D}_K{K}", sums[rows], ref, 1e-5 if D <= 64 else 3e-5, 1e-6)
     if n <= 5000:
         from sklearn.metrics import silhouette_score
         record(f"silhouette_vs_sklearn_n{n}", native, float(silhouette_score(X, labels)), 1e-5, 1e-6)
