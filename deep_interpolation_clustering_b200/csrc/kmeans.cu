@@ -1203,14 +1203,16 @@ template <typename T>
 int launch_assign(const void* X, const void* centers, int32_t* labels, double* sums, double* counts,
                   double* stats, void* workspace, int64_t N, int D, int K, int flags, cudaStream_t st,
                   const double* done = nullptr) {
-  // specialised tile kernel: rows of exactly 16 or 32 sixteen-byte vectors (D = 64 / 128 float32, 32 / 64 float64)
+  // specialised tile kernel: rows of exactly 16, 32 or 64 sixteen-byte vectors (D = 64 / 128 / 256 float32,
+  // 32 / 64 / 128 float64).  64 vectors (the reference's latent width, D = 256) leave room for ONE resident CTA per
+  // SM only, still 9x the general kernel that served this shape before (3.6 ms per pass at 500k x 256, K = 10).
   {
     constexpr int PER = 16 / (int)sizeof(T);
     const int s16x = D / PER;
-    const bool shape_ok = D % PER == 0 && (s16x == 16 || s16x == 32) && K <= 16 && aligned16(X);
+    const bool shape_ok = D % PER == 0 && (s16x == 16 || s16x == 32 || s16x == 64) && K <= 16 && aligned16(X);
     const bool no_t2 = getenv("DIC_KMEANS_NO_TILE2") != nullptr;     // debug: force the older kernels
     const size_t smem = shape_ok ? tile2_smem_bytes<T>(K, s16x, sums != nullptr) : 0;
-    if (shape_ok && !no_t2 && smem <= 110 * 1024) {
+    if (shape_ok && !no_t2 && smem <= (s16x == 64 ? 200 : 110) * 1024) {
       int dev = 0, sms = 148;
       cudaGetDevice(&dev);
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -1231,7 +1233,7 @@ int launch_assign(const void* X, const void* centers, int32_t* labels, double* s
     kf<<<nb, kT2Rows, smem, st>>>(static_cast<const T*>(X), static_cast<const T*>(centers), labels, wsd, N, K, \
                                   flags, sums != nullptr, done);                                              \
   }
-      if (s16x == 16) DIC_T2_LAUNCH(16) else DIC_T2_LAUNCH(32)
+      if (s16x == 16) DIC_T2_LAUNCH(16) else if (s16x == 32) DIC_T2_LAUNCH(32) else DIC_T2_LAUNCH(64)
 #undef DIC_T2_LAUNCH
       DIC_LAUNCH_CHECK("kmeans_assign_tile2_kernel");
       const int nn = K * D + K + 4;

@@ -239,7 +239,8 @@ def test_silhouette_tensor_core_matches_float64(n, D, K):
 
 @pytest.mark.parametrize("dtag,D,K", [("f32", 64, 3), ("f32", 64, 10), ("f32", 64, 16), ("f64", 64, 4), ("f64", 64, 10),
                                       ("f32", 128, 5), ("f64", 32, 6), ("f32", 100, 7), ("f64", 100, 3),
-                                      ("f32", 200, 4), ("f32", 300, 5), ("f32", 64, 20)])
+                                      ("f32", 200, 4), ("f32", 300, 5), ("f32", 64, 20), ("f32", 256, 4), ("f32", 256, 10),
+                                      ("f32", 256, 16), ("f64", 128, 6), ("f64", 128, 12)])
 def test_lloyd_kernel_dispatch_matches_sklearn(dtag, D, K):
     """Every Lloyd kernel (specialised tile kernel: rows of 16 / 32 vectors; streaming row kernel; generic tile
     kernels) against scikit-learn run here on the same data and the same initial centres.  The comparison is made
