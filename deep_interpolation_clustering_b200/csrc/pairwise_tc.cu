@@ -3,21 +3,25 @@
 // This is the one genuinely dense contraction on the hot path: the "inertia" of
 // KM.compute_inertia_v1 / computer_intertia_v2 (p2_clustering_optK.py:334-351) sums
 // ||x_i - x_j|| over the full n_c x n_c matrix of every cluster.  The reference materialises that
-// matrix (sklearn pairwise_distances: ||x||^2 + ||y||^2 - 2 x.y, clamp, sqrt); here a 128 x 128
-// tile of the Gram matrix X X^T is produced by tcgen05.mma (kind::tf32, accumulator in TMEM), read
-// back with tcgen05.ld and reduced on the fly, so nothing is ever written to memory.
+// matrix (sklearn pairwise_distances: ||x||^2 + ||y||^2 - 2 x.y, clamp, sqrt); here 128 x 128 tiles of
+// the Gram matrix X X^T come out of tcgen05.mma (accumulator in TMEM), are read back with tcgen05.ld and
+// reduced on the fly, so nothing is ever written to memory.  Two kernels:
 //
-//   * split TF32: each operand is split into hi = rn_tf32(x) and lo = rn_tf32(x - hi)
-//     and the tile accumulates hi.hi + hi.lo + lo.hi + lo.lo, which restores float32-grade dot
-//     products (the MMAs are ~3% of the tile time, the epilogue's sqrt is the bound; the caller
-//     centres the cluster first, so ||x||^2 stays small against the distances).
-//   * operands sit in the canonical no-swizzle K-major UMMA layout (8-row x 16-byte core matrices);
-//     the row block of a tile row is kept in shared memory and reused across the tiles of that row.
+//   * D <= 256: tc64::pairwise_tc64_kernel (second half of this file) - a pre-pass packs the rows ONCE as split
+//     float16 operand tiles (kind::f16), TMA bulk copies feed them, one warp issues, eight warps drain; also
+//     the silhouette's per-row, per-cluster sums (ROWSUMS).
+//   * D > 256: pairwise_tc_kernel (first half) - the earlier register-staged design on split TF32
+//     (kind::tf32): 4 loader warps convert and store the next column block while the tensor core multiplies
+//     the current one into one of two TMEM accumulators and 4 epilogue warps drain the other.
+//
+// Common to both:
+//   * split operands: each element is hi + lo with 11-bit significands and the tile accumulates
+//     hi.hi + hi.lo + lo.hi (+ lo.lo in the TF32 kernel), which restores float32-grade dot products; the
+//     caller centres the cluster first, so ||x||^2 stays small against the distances.
+//   * operands sit in the canonical no-swizzle K-major UMMA layout (8-row x 16-byte core matrices).
 //   * upper triangle only: off-diagonal tiles count twice; the diagonal is excluded explicitly.
-//   * warp-specialised: 4 loader warps stage the next column block while the tensor core multiplies
-//     the current one into one of two TMEM accumulators and 4 epilogue warps drain the other
-//     (tcgen05.ld, ni + nj - 2 dot, clamp, sqrt.approx, float64 sums); mbarriers carry the
-//     stage-free / accumulator-full / accumulator-empty hand-offs.
+//   * epilogue: ni + nj - 2 dot, clamp, sqrt.approx, float32 two-sum per thread, float64 across threads;
+//     mbarriers carry the stage-free / accumulator-full / accumulator-empty hand-offs, all waits bounded.
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
