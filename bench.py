@@ -63,6 +63,8 @@ def parse():
     ap.add_argument("--encounters", type=int, default=0, help="encounters per GPU per step (0 = the workload's)")
     ap.add_argument("--e2e-encounters", type=int, default=262_144)
     ap.add_argument("--e2e-chunk", type=int, default=32_768)
+    ap.add_argument("--e2e-upload", default="packed", choices=["packed", "dense"],
+                    help="host format of x in the e2e arm: ragged/packed rows (default) or the dense planes")
     ap.add_argument("--cpu-sample", type=int, default=256, help="encounters in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -418,7 +420,16 @@ def e2e_arm(args, hp, dev, world):
     from deep_interpolation_clustering_b200 import functional as F_
     Bc = min(args.e2e_chunk, hp.B)
     n_chunks = max(1, min(args.e2e_encounters, hp.B) // Bc)
-    host = [hp.x[i * Bc:(i + 1) * Bc].cpu().pin_memory() for i in range(min(2, n_chunks))]
+    from deep_interpolation_clustering_b200 import PackedEncounters, PackedStaging
+    packed_mode = args.e2e_upload == "packed"
+    host = [hp.x[i * Bc:(i + 1) * Bc].cpu() for i in range(min(2, n_chunks))]
+    if packed_mode:      # packed once per data set, outside the timed region (what p0_data_process.py's rows already are)
+        host = [PackedEncounters.from_dense(h) for h in host]
+        staging = [PackedStaging(C, Bc, max(h.floats() for h in host), dev) for _ in range(2)]
+        chunk_bytes = [h.nbytes() for h in host]
+    else:
+        host = [h.pin_memory() for h in host]
+        chunk_bytes = [Bc * 3 * C * T * 4 for _ in host]
     dbuf = [torch.empty((Bc, 3 * C, T), dtype=torch.float32, device=dev) for _ in range(2)]   # live planes only
     sci = dic.SingleChannelInterp(R, HOURS, C, T, dev)
     cci = dic.CrossChannelInterp(C, T, dev)
@@ -433,12 +444,18 @@ def e2e_arm(args, hp, dev, world):
     ready = [torch.cuda.Event() for _ in range(2)]
     free = [torch.cuda.Event() for _ in range(2)]
 
+    def upload(k, slot):
+        if packed_mode:
+            staging[slot].upload(host[k], 0, Bc, out=dbuf[slot], stream=copy_stream)
+        else:
+            F_.upload_encounters(host[k], out=dbuf[slot], stream=copy_stream)
+
     def step():
         for p_ in params:
             p_.grad = None
         loss_acc = torch.zeros((), device=dev)
         with torch.cuda.stream(copy_stream):
-            F_.upload_encounters(host[0], out=dbuf[0], stream=copy_stream)
+            upload(0, 0)
             ready[0].record(copy_stream)
         for i in range(n_chunks):
             cur = i & 1
@@ -446,7 +463,7 @@ def e2e_arm(args, hp, dev, world):
                 with torch.cuda.stream(copy_stream):
                     if i >= 1:
                         copy_stream.wait_event(free[cur ^ 1])
-                    F_.upload_encounters(host[(i + 1) % len(host)], out=dbuf[cur ^ 1], stream=copy_stream)
+                    upload((i + 1) % len(host), cur ^ 1)
                     ready[cur ^ 1].record(copy_stream)
             main.wait_event(ready[cur])
             x = dbuf[cur]
@@ -488,11 +505,17 @@ def e2e_arm(args, hp, dev, world):
     per_step = float(t_ms) / n
     enc = n_chunks * Bc
     return {"value": round(world * enc / (per_step * 1e-3), 1), "unit": "encounters/s",
-            "h2d_bytes_per_step": int(enc * 3 * C * T * 4), "d2h_bytes_per_step": int(enc * 4 + host_out.numel() * 4),
+            "h2d_bytes_per_step": int(sum(chunk_bytes[i % len(host)] for i in range(n_chunks))), "d2h_bytes_per_step": int(enc * 4 + host_out.numel() * 4),
             "encounters_per_step_per_gpu": enc, "chunk": Bc, "ms_per_step": round(per_step, 3),
-            "path": "pinned host x (B,4C,T) -> upload_encounters (one strided DMA of the 3 live planes per chunk, copy "
-                    "stream, double buffered) -> SingleChannelInterp/CrossChannelInterp/RBF "
-                    "modules (autograd fwd+bwd) + dec_kl_step -> D2H labels, loss, parameter grads"}
+            "upload": args.e2e_upload,
+            "path": ("pinned host PackedEncounters (ragged rows: valid prefix of value/time + one count per vital, packed "
+                     "once per data set outside the timed region) -> PackedStaging.upload (3 contiguous H2D copies + "
+                     "device-side expansion to dense planes per chunk, copy stream, double buffered)" if packed_mode else
+                     "pinned host x (B,4C,T) -> upload_encounters (one strided DMA of the 3 live planes per chunk, copy "
+                     "stream, double buffered)") +
+                    " -> SingleChannelInterp/CrossChannelInterp/RBF modules (autograd fwd+bwd; RBF.compress_fc = Identity, "
+                    "v and the latents z stay device-resident: the metric's step has no encoder) + dec_kl_step -> D2H labels, "
+                    "loss, parameter grads"}
 
 
 def main():

@@ -35,6 +35,9 @@ SIGNATURES = {
     "dic_rbf_fwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, c_int64, _P]),
     "dic_rbf_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, c_int64, _P]),
     "dic_upload_encounters": (c_int, [_P, _P, c_int64, c_int, c_int, c_int, c_int, _P]),
+    "dic_pack_encounters_host": (c_int64, [_P, c_int64, c_int, c_int, c_int, _P, _P, _P, c_int64, POINTER(c_int)]),
+    "dic_upload_encounters_packed": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, _P]),
+    "dic_expand_encounters": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int, c_int, _P]),
     "dic_dec_workspace_bytes": (c_size_t, [c_int, c_int]),
     "dic_dec_q_fwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_float, _P]),
     "dic_dec_p": (c_int, [_P, _P, _P, c_int64, c_int, _P]),

@@ -173,20 +173,6 @@ extern "C" int dic_colsum_f32(const float* a, double* out, void* workspace, int6
                            as_stream(stream));
 }
 
-extern "C" int dic_upload_encounters(float* x_dev, const float* x_host, int64_t B, int C, int T,
-                                     int host_planes, int dev_planes, dic_stream_t stream) {
-  DIC_REQUIRE(x_dev && x_host, DIC_ERR_INVALID_ARGUMENT, "null pointer argument");
-  DIC_REQUIRE(B >= 0 && C > 0 && T > 0, DIC_ERR_INVALID_ARGUMENT, "bad sizes B=%lld C=%d T=%d", (long long)B, C, T);
-  DIC_REQUIRE(host_planes >= 3 * C && dev_planes >= 3 * C, DIC_ERR_INVALID_ARGUMENT,
-              "an encounter has 3*C live planes: host_planes=%d dev_planes=%d C=%d", host_planes, dev_planes, C);
-  if (B == 0) return DIC_OK;
-  // one strided DMA: B rows of 3*C*T floats (value | mask | time); the hold-out plane stays on the host
-  DIC_CUDA(cudaMemcpy2DAsync(x_dev, (size_t)dev_planes * T * sizeof(float), x_host,
-                             (size_t)host_planes * T * sizeof(float), (size_t)3 * C * T * sizeof(float),
-                             (size_t)B, cudaMemcpyHostToDevice, as_stream(stream)));
-  return DIC_OK;
-}
-
 extern "C" int dic_probe_mufu(double* ex2_per_second_host, dic_stream_t stream) {
   DIC_REQUIRE(ex2_per_second_host, DIC_ERR_INVALID_ARGUMENT, "null pointer argument");
   return run_probe(probe_mufu_kernel, ex2_per_second_host, as_stream(stream));

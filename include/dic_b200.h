@@ -121,6 +121,39 @@ int dic_rbf_bwd(const float* v, const float* x, const float* kernel, const float
 int dic_upload_encounters(float* x_dev, const float* x_host, int64_t B, int C, int T,
                           int host_planes, int dev_planes, dic_stream_t stream);
 
+/* ---- ragged (packed) encounters ---------------------------------------------------------
+ * The pipeline's rows are left-packed (p0_data_process.py:44-67: observations first, zero padding after), so the
+ * dense planes the trainer ships (pretrain_trainer.py:132-136) are on average half padding and the mask plane of a
+ * row is one integer.  The packed form keeps, per (encounter b, vital c), only the valid prefix:
+ *   n_obs   (B, C) int32    prefix length
+ *   enc_off (B + 1) int64   float offset of encounter b in `packed` (multiples of 4: rows are 16-byte aligned)
+ *   packed                  for b, for c: [ value[0..n4) | time[0..n4) ], n4 = round_up(n_obs[b,c], 4); pad slots
+ *                           hold value 0 and time 3e18 (an observation whose Gaussian weight is exactly 0)
+ * ~6.2 KB instead of 18.4 KB per encounter at c2 (C = 6, T = 256, mean 128.5 observations).
+ *
+ * dic_pack_encounters_host: HOST function (no device work).  Reads x_host (B, host_planes, T) float32, fills
+ * n_obs_host and enc_off_host, and - when packed_host is not NULL - the packed rows (capacity in floats).  Returns
+ * the number of floats the packed rows take (call once with packed_host = NULL to size the buffer), or a negative
+ * dic_status: DIC_ERR_UNSUPPORTED when a mask is not a left-packed 0/1 prefix (general masks take the dense
+ * upload).  *all_sorted (may be NULL) is set to 1 when every row's times are non-decreasing on its prefix.  C <= 16. */
+int64_t dic_pack_encounters_host(const float* x_host, int64_t B, int C, int T, int host_planes,
+                                 int32_t* n_obs_host, int64_t* enc_off_host, float* packed_host,
+                                 int64_t capacity, int* all_sorted);
+
+/* Host -> device copy of encounters [b0, b0 + B) of a packed set: pass n_obs_host + b0*C and enc_off_host + b0
+ * (B + 1 entries are read; packed_host is the BASE of the packed rows, the slice is located through enc_off_host).
+ * Three contiguous asynchronous copies (pin the host arrays); packed_dev needs enc_off_host[B] - enc_off_host[0]
+ * floats and 16-byte alignment.  Offsets stay absolute: consumers subtract enc_off_dev[0]. */
+int dic_upload_encounters_packed(const float* packed_host, const int32_t* n_obs_host, const int64_t* enc_off_host,
+                                 float* packed_dev, int32_t* n_obs_dev, int64_t* enc_off_dev, int64_t B, int C,
+                                 dic_stream_t stream);
+
+/* Device-side expansion of packed encounters into the dense planes [value | mask | time] of x_dev
+ * (B, dev_planes, T), dev_planes >= 3C (planes beyond 3C are left untouched): the buffer every dic_* call above
+ * takes with x_stride = dev_planes * T.  Bit-identical to what dic_upload_encounters delivers for the same rows. */
+int dic_expand_encounters(const float* packed_dev, const int32_t* n_obs_dev, const int64_t* enc_off_dev,
+                          float* x_dev, int64_t B, int C, int T, int dev_planes, dic_stream_t stream);
+
 /* ---- DEC soft assignment ----------------------------------------------------------
  * ClusterAssignment.forward, dec.py:49-63.  z (B,D), mu (K,D) -> q (B,K).
  *   labels (B) int32 out, may be NULL: argmax_j q (clustering_trainer.py:473-484)
