@@ -59,7 +59,10 @@ def build(force=False, verbose=False):
         obj = os.path.join(BUILD, src.replace(".cu", ".o"))
         path = os.path.join(CSRC, src)
         if force or _stale(obj, [path] + deps):
-            cmd = [nvcc] + NVCC_FLAGS + ["-I", INCLUDE, "-I", CSRC, "-c", path, "-o", obj]
+            # NVCC_EXTRA: extra compile flags for a BENCHMARK build (e.g. -DDIC_TC_PROFILE, benchmarks/README.md);
+            # a build-time switch of this script, not something the library reads
+            cmd = [nvcc] + NVCC_FLAGS + os.environ.get("NVCC_EXTRA", "").split() + \
+                ["-I", INCLUDE, "-I", CSRC, "-c", path, "-o", obj]
             if verbose:
                 cmd[1:1] = ["-Xptxas", "-v"]
             r = subprocess.run(cmd, capture_output=True, text=True)

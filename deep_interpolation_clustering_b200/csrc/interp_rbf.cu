@@ -8,18 +8,15 @@
 // The reduction runs over the reference grid (the transpose of SCI).  There is no
 // softmax shift in the reference (plain exp, absolute epsilon), so none is applied here.
 //
-// Forward: one CTA per encounter, one thread per (vital, observation); the vital's grid
-// row (r_j, v_j) is read as shared-memory broadcasts; one MUFU.EX2 per (t, r).
+// Forward: one CTA per encounter, warp tasks of 32 consecutive observations of one vital; each lane walks a
+// uniform-length window of the vital's grid row (s r_j, v_j) in shared memory; one MUFU.EX2 per (t, r).
 // Backward: the reduction for grad_v runs over observations, so the encounter is staged
 // like SCI (interp_stage.cuh) and each lane owns RPT grid points.
-#include <stdlib.h>
-
 #include "interp_stage.cuh"
 
 namespace dic {
 namespace {
 
-constexpr int kRbfFwdThreads = 256;
 constexpr int kMaxWarps = 8;
 
 // Window cut-off: a (t, r) pair whose basis value is below 2^-kRbfCut (9e-10) is skipped.  The
@@ -28,137 +25,9 @@ constexpr int kMaxWarps = 8;
 // span, and non-uniform grids, take the full range.
 constexpr float kRbfCut = 30.0f;
 
-__global__ void __launch_bounds__(kRbfFwdThreads, 6)
-rbf_fwd_kernel(const float* __restrict__ v, const float* __restrict__ x,
-               const float* __restrict__ kernel, const float* __restrict__ ref_t,
-               float* __restrict__ rec, float* __restrict__ inv_norm, int C, int T, int R, int Rp,
-               int64_t x_stride) {
-  extern __shared__ __align__(16) float smem[];
-  float2* srv = reinterpret_cast<float2*>(smem);     // [C][Rp] (s_c r_j, v_cj); pad: (huge, 0) => e = 0
-  float* snb = smem + 2 * C * Rp;                     // [C] s_c = sqrt(beta_c log2 e): coordinates are pre-scaled so
-                                                      //     that the exponent is just -(s d - s r)^2 (one FMUL)
-  int* strip = reinterpret_cast<int*>(snb + C);       // [C] grid points per window (even)
-  const float r0 = __ldg(ref_t), rl = __ldg(ref_t + R - 1);
-  const float h = R > 1 ? (rl - r0) / (float)(R - 1) : 1.0f;
-  int irregular = !(h > 0.f);
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const float b2 = softplus_ref(__ldg(kernel + c)) * kLog2e;
-    snb[c] = sqrtf(b2);
-    // window = +-sqrt(cut / (beta log2 e)) hours -> grid points, +2 points of slack each side
-    strip[c] = (2 * ((int)ceilf(sqrtf(kRbfCut / b2) / h) + 2) + 1) & ~1;
-  }
-  __syncthreads();
-  const int64_t b = blockIdx.x;
-  const float* vb = v + b * (int64_t)C * R;
-  for (int j = threadIdx.x; j < Rp; j += blockDim.x) {
-    const float rj = j < R ? __ldg(ref_t + j) : 3.0e18f;      // (3e18 s)^2 stays finite, 2^-that == 0
-    if (j < R) irregular |= fabsf(rj - (r0 + h * (float)j)) > 0.01f * h;
-    for (int c = 0; c < C; ++c) srv[c * Rp + j] = make_float2(rj * snb[c], j < R ? __ldg(vb + c * R + j) : 0.f);
-  }
-  irregular = __syncthreads_or(irregular);
-  const float inv_h = 1.0f / h;
-  const float* mb = x + b * x_stride + (int64_t)C * T;         // mask plane rows
-  const float* db = x + b * x_stride + (int64_t)2 * C * T;     // time plane rows
-  float* rb = rec + b * (int64_t)C * T;
-  float* nb = inv_norm ? inv_norm + b * (int64_t)C * T : nullptr;
-
-  // Left-packed 0/1 masks (what the pipeline produces) let the valid observations of all vitals
-  // be dealt evenly to the threads: element e of sum_c n_c -> (vital, observation).  The warp
-  // that scans a vital's mask row also zero-fills the masked tail of its outputs.
-  int* soff = strip + C;                              // [C + 1] prefix sums of the valid counts
-  __shared__ int s_general;
-  if (threadIdx.x == 0) s_general = 0;
-  __syncthreads();
-  {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    for (int c = warp; c < C; c += nwarps) {
-      const float* mrow = mb + c * T;
-      int ok = 1, cnt = 0;
-      for (int t = lane; t < T; t += 32) {
-        const float m = __ldg(mrow + t);
-        const float mn = t + 1 < T ? __ldg(mrow + t + 1) : 0.f;
-        ok &= ((m == 0.f) | (m == 1.f)) & (m >= mn);
-        cnt += (m == 1.f);
-      }
-      ok = __all_sync(0xffffffffu, ok);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-      if (ok) {
-        for (int t = cnt + lane; t < T; t += 32) {              // masked slots reconstruct to 0
-          rb[c * T + t] = 0.f;
-          if (nb) nb[c * T + t] = 0.f;
-        }
-      }
-      if (lane == 0) {
-        soff[c + 1] = cnt;
-        if (!ok) atomicOr(&s_general, 1);
-      }
-    }
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    soff[0] = 0;
-    for (int c = 0; c < C; ++c) soff[c + 1] += soff[c];
-  }
-  __syncthreads();
-
-  auto readout = [&](int c, int i, float m) {
-    const float d = __ldg(db + i);
-    const float ds = d * snb[c];
-    // Every lane walks the same number of grid points (strip[c] -> trip), starting at its own
-    // even offset: uniform trip count, no divergence, no union-of-windows penalty.
-    int jlo = 0, trip = Rp;
-    if (!irregular && d >= r0 - 1.0f && d <= rl + 1.0f) {
-      trip = min(Rp, strip[c]);
-      jlo = min(max(0, (__float2int_rd((d - r0) * inv_h) - (trip >> 1) + 1) & ~1), Rp - trip);
-    }
-    float N = 0.f, S = 0.f;
-    const float2* rw = srv + c * Rp + jlo;
-#pragma unroll 2
-    for (int j = 0; j < trip; j += 2) {
-      const float4 p = *reinterpret_cast<const float4*>(rw + j);   // (r0, v0, r1, v1)
-      const float d0 = ds - p.x, d1 = ds - p.z;
-      const float e0 = ex2_approx(-(d0 * d0)), e1 = ex2_approx(-(d1 * d1));
-      N += e0;
-      S = fmaf(e0, p.y, S);
-      N += e1;
-      S = fmaf(e1, p.w, S);
-    }
-    // phi = m e  =>  N_ref = m N, sum phi v = m S
-    const float inv = __frcp_rn(fmaf(m, N, 1e-10f));
-    rb[i] = (m * S) * inv * m;                                // rbf.py:106-107
-    if (nb) nb[i] = inv;
-  };
-
-  if (!s_general) {
-    const int V = soff[C];
-    for (int e = threadIdx.x; e < V; e += blockDim.x) {
-      int c = 0;
-      while (e >= soff[c + 1]) ++c;
-      readout(c, c * T + (e - soff[c]), 1.0f);
-    }
-  } else {
-    int c = 0, t = threadIdx.x;                                 // (c, t) of element i without dividing
-    while (t >= T) { t -= T; ++c; }
-    for (int i = threadIdx.x; i < C * T; i += blockDim.x) {
-      const float m = __ldg(mb + i);
-      if (m != 0.f) {
-        readout(c, i, m);
-      } else {
-        rb[i] = 0.f;
-        if (nb) nb[i] = 0.f;
-      }
-      t += blockDim.x;
-      while (t >= T) { t -= T; ++c; }
-    }
-  }
-}
-
 // ---- forward, warp-task form -------------------------------------------------------------------------
-// The element-dealing kernel above pays ~120 issue slots per observation around a ~320-slot loop (vital
-// search, window arithmetic, scattered loads and stores) and a prologue of dependent global loads behind six
-// block barriers.  Here the encounter's mask + time planes and its grid values arrive by TMA bulk copies
-// while the parameters are computed, and the work is cut into TASKS of 32 consecutive observations of one
+// The encounter's mask + time planes and its grid values arrive by TMA bulk copies while the parameters are
+// computed, and the work is cut into TASKS of 32 consecutive observations of one
 // vital: within a task the vital, its window length and its (s r_j, v_j) row are warp-uniform, every lane
 // reads its observation from shared memory and the 32 results leave as one coalesced store.  Tasks are dealt
 // round-robin to the warps (about 27 tasks for 4 warps at c2).
@@ -525,30 +394,18 @@ extern "C" int dic_rbf_fwd(const float* v, const float* x, const float* kernel, 
   DIC_REQUIRE(rec || B == 0, DIC_ERR_INVALID_ARGUMENT, "null output pointer");
   if (B == 0) return DIC_OK;
   const int Rp = round_up(R, 2);
-  {   // warp-task kernel (TMA-staged planes): the default
-    const int Tp = round_up(T, 4);
-    size_t off[8];
-    const size_t smem2 = rbf_fwd2_offsets(C, Tp, R, Rp, off);
-    static const bool v1 = getenv("DIC_RBF_FWD_V1") != nullptr;          // debug: the element-dealing kernel
-    if (!v1 && smem2 <= (size_t)kMaxSmemBytes) {
-      const int use_tma = (Tp == T) && aligned16(x) && aligned16(v) && ((x_stride * 4) % 16 == 0) &&
-                          (((int64_t)C * T * 4) % 16 == 0) && (((int64_t)C * R * 4) % 16 == 0);
-      if (smem2 > 48 * 1024)
-        DIC_CUDA(cudaFuncSetAttribute(rbf_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-      rbf_fwd2_kernel<<<(unsigned)B, kRbfFwd2Warps * 32, smem2, as_stream(stream)>>>(
-          v, x, kernel, ref_t, rec, inv_norm, C, T, Tp, R, Rp, x_stride, use_tma);
-      DIC_LAUNCH_CHECK("rbf_fwd2_kernel");
-      return DIC_OK;
-    }
-  }
-  const size_t smem = sizeof(float2) * (size_t)C * Rp + sizeof(float) * (3 * (size_t)C + 1);
-  DIC_REQUIRE(smem <= (size_t)kMaxSmemBytes, DIC_ERR_UNSUPPORTED,
-              "C=%d R=%d needs %zu bytes of shared memory (limit %d)", C, R, smem, kMaxSmemBytes);
-  if (smem > 48 * 1024)
-    DIC_CUDA(cudaFuncSetAttribute(rbf_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  rbf_fwd_kernel<<<(unsigned)B, kRbfFwdThreads, smem, as_stream(stream)>>>(v, x, kernel, ref_t, rec,
-                                                                          inv_norm, C, T, R, Rp, x_stride);
-  DIC_LAUNCH_CHECK("rbf_fwd_kernel");
+  const int Tp = round_up(T, 4);
+  size_t off[8];
+  const size_t smem2 = rbf_fwd2_offsets(C, Tp, R, Rp, off);
+  DIC_REQUIRE(smem2 <= (size_t)kMaxSmemBytes, DIC_ERR_UNSUPPORTED,
+              "C=%d T=%d R=%d needs %zu bytes of shared memory per encounter (limit %d)", C, T, R, smem2, kMaxSmemBytes);
+  const int use_tma = (Tp == T) && aligned16(x) && aligned16(v) && ((x_stride * 4) % 16 == 0) &&
+                      (((int64_t)C * T * 4) % 16 == 0) && (((int64_t)C * R * 4) % 16 == 0);
+  if (smem2 > 48 * 1024)
+    DIC_CUDA(cudaFuncSetAttribute(rbf_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+  rbf_fwd2_kernel<<<(unsigned)B, kRbfFwd2Warps * 32, smem2, as_stream(stream)>>>(
+      v, x, kernel, ref_t, rec, inv_norm, C, T, Tp, R, Rp, x_stride, use_tma);
+  DIC_LAUNCH_CHECK("rbf_fwd2_kernel");
   return DIC_OK;
 }
 

@@ -13,7 +13,6 @@
 // gives each thread one row against all K centres (centres broadcast from shared memory, 4
 // centres register-blocked), phase 2 re-maps threads to columns and adds the tile into
 // per-CTA [K][D] sums (no atomics on the data path).  HBM-bound: N*D*sizeof(T) bytes/pass.
-#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -518,8 +517,8 @@ constexpr int kPotBlocks = 148 * 4;
 
 template <typename T>
 __global__ void __launch_bounds__(kPotThreads)
-kmeans_min_d2_kernel(const T* __restrict__ X, const T* __restrict__ cands, const T* __restrict__ min_d2,
-                     T* __restrict__ min_d2_out, double* __restrict__ ws, int64_t N, int D, int L) {
+kmeans_min_d2_kernel(const T* __restrict__ X, const T* __restrict__ cands, const T* min_d2,
+                     T* min_d2_out /* may alias min_d2: in place */, double* __restrict__ ws, int64_t N, int D, int L) {
   extern __shared__ __align__(16) unsigned char smem[];
   T* sc = reinterpret_cast<T*>(smem);                  // [L][D]
   for (int i = threadIdx.x; i < L * D; i += blockDim.x) sc[i] = cands[i];
@@ -1076,8 +1075,8 @@ kmeans_assign_rw_kernel(const T* __restrict__ X, const T* __restrict__ centers, 
 // hl >> (4 - log2 LP) and accumulates its potential in float64.  One read of X (+ min_d2), no staging.
 template <typename T, int E, int LP>
 __global__ void __launch_bounds__(kRwThreads)
-kmeans_min_d2_rw_kernel(const T* __restrict__ X, const T* __restrict__ cands, const T* __restrict__ min_d2,
-                        T* __restrict__ min_d2_out, double* __restrict__ ws, int64_t N, int D, int L) {
+kmeans_min_d2_rw_kernel(const T* __restrict__ X, const T* __restrict__ cands, const T* min_d2,
+                        T* min_d2_out /* may alias min_d2: in place */, double* __restrict__ ws, int64_t N, int D, int L) {
   using V = typename RwVec<T>::type;
   constexpr int PER = RwVec<T>::n;
   constexpr int NV = E / PER;
@@ -1203,6 +1202,10 @@ template <typename T>
 int launch_assign(const void* X, const void* centers, int32_t* labels, double* sums, double* counts,
                   double* stats, void* workspace, int64_t N, int D, int K, int flags, cudaStream_t st,
                   const double* done = nullptr) {
+  // bits 8..11 of flags: 0 = pick by shape and measured cost; 1..4 = that kernel or DIC_ERR_UNSUPPORTED (parity tests
+  // and benchmarks address every kernel through the ABI; nothing here reads the environment)
+  const int which = (flags >> 8) & 15;
+  DIC_REQUIRE(which <= 4, DIC_ERR_INVALID_ARGUMENT, "DIC_KM_KERNEL(%d): unknown kernel", which);
   // specialised tile kernel: rows of exactly 16, 32 or 64 sixteen-byte vectors (D = 64 / 128 / 256 float32,
   // 32 / 64 / 128 float64).  64 vectors (the reference's latent width, D = 256) leave room for ONE resident CTA per
   // SM only, still 9x the general kernel that served this shape before (3.6 ms per pass at 500k x 256, K = 10).
@@ -1210,9 +1213,11 @@ int launch_assign(const void* X, const void* centers, int32_t* labels, double* s
     constexpr int PER = 16 / (int)sizeof(T);
     const int s16x = D / PER;
     const bool shape_ok = D % PER == 0 && (s16x == 16 || s16x == 32 || s16x == 64) && K <= 16 && aligned16(X);
-    const bool no_t2 = getenv("DIC_KMEANS_NO_TILE2") != nullptr;     // debug: force the older kernels
     const size_t smem = shape_ok ? tile2_smem_bytes<T>(K, s16x, sums != nullptr) : 0;
-    if (shape_ok && !no_t2 && smem <= (s16x == 64 ? 200 : 110) * 1024) {
+    const bool fits = shape_ok && smem <= (s16x == 64 ? 200 : 110) * 1024;
+    DIC_REQUIRE(fits || which != 1, DIC_ERR_UNSUPPORTED, "DIC_KM_KERNEL(1): the specialised tile kernel does not cover "
+                "K=%d D=%d", K, D);
+    if (fits && (which == 0 || which == 1)) {
       int dev = 0, sms = 148;
       cudaGetDevice(&dev);
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -1248,13 +1253,15 @@ int launch_assign(const void* X, const void* centers, int32_t* labels, double* s
     const int e_need = (D + 15) / 16;
     const int E = e_need <= 4 ? 4 : (e_need <= 8 ? 8 : 16);
     const int KP = K <= 4 ? 4 : (K <= 8 ? 8 : 16);
-    const bool no_rw = getenv("DIC_KMEANS_NO_RW") != nullptr;     // debug: force the tile kernel
     const size_t smem = rw_smem_bytes<T>(K, E, KP, sums != nullptr);
     // measured on B200 at 1M x 64 (benchmarks/_km_pass.py): the streaming kernel wins for K <= 8 in float32
     // (0.15-0.19 ms vs 0.21-0.23 ms per pass) and K <= 4 in float64; beyond that its per-row shuffle
     // reductions cost more issue slots than the tile kernel's shared-memory staging
     const bool rw_wins = sizeof(T) == 4 ? K <= 8 : K <= 4;
-    if (!no_rw && rw_wins && D <= 256 && D % PER == 0 && aligned16(X) && smem <= 100 * 1024) {
+    const bool rw_ok = K <= 16 && D <= 256 && D % PER == 0 && aligned16(X) && smem <= 100 * 1024;
+    DIC_REQUIRE(rw_ok || which != 2, DIC_ERR_UNSUPPORTED, "DIC_KM_KERNEL(2): the streaming kernel does not cover K=%d D=%d",
+                K, D);
+    if (rw_ok && ((which == 0 && rw_wins) || which == 2)) {
       int dev = 0, sms = 148;
       cudaGetDevice(&dev);
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -1289,7 +1296,10 @@ int launch_assign(const void* X, const void* centers, int32_t* labels, double* s
   const int s16 = row_stride16<T>(D);
   int tile = 128;
   KmLayout L = km_layout<T>(K, D, tile);
-  if (K <= 16 && D <= 4 * kKmTile && L.total <= 100 * 1024) {
+  const bool fast_ok = K <= 16 && D <= 4 * kKmTile && L.total <= 100 * 1024;
+  DIC_REQUIRE(fast_ok || which != 3, DIC_ERR_UNSUPPORTED, "DIC_KM_KERNEL(3): the generic tile kernel does not cover "
+              "K=%d D=%d", K, D);
+  if (fast_ok && which != 4) {
     const int64_t nt = (N + kKmTile - 1) / kKmTile;
     int nb = km_blocks(K, D);
     if (nt < nb) nb = (int)nt;
@@ -1352,8 +1362,7 @@ int launch_min_d2(const void* X, const void* cands, const void* min_d2, void* mi
     constexpr int PER = 16 / (int)sizeof(T);
     const int e_need = (D + 15) / 16;
     const int E = e_need <= 4 ? 4 : (e_need <= 8 ? 8 : 16);
-    const bool no_rw = getenv("DIC_KMEANS_NO_RW") != nullptr;
-    if (!no_rw && D <= 256 && D % PER == 0 && aligned16(X) && L <= 16) {
+    if (D <= 256 && D % PER == 0 && aligned16(X) && L <= 16) {
       const size_t smem_rw = (size_t)L * 16 * E * sizeof(T);
       int dev = 0, sms = 148;
       cudaGetDevice(&dev);
@@ -1419,7 +1428,13 @@ using namespace dic;
 
 extern "C" size_t dic_kmeans_workspace_bytes(int K, int D) {
   if (K <= 0 || D <= 0) return 0;
-  size_t a = (size_t)km_blocks(K, D) * ((size_t)K * D + K + 4) * sizeof(double);
+  // the block count shrinks as K grows, so the product is not monotone in K: a buffer sized for K must also serve
+  // every smaller K' (a gap sweep reuses one buffer for K = 2..k_max)
+  size_t a = 0;
+  for (int k = 1; k <= K; ++k) {
+    const size_t ak = (size_t)km_blocks(k, D) * ((size_t)k * D + k + 4) * sizeof(double);
+    a = ak > a ? ak : a;
+  }
   size_t b = (size_t)kPotBlocks * kMaxCands * sizeof(double);
   return (a > b ? a : b) + 256;
 }
@@ -1528,6 +1543,8 @@ static int pairwise_dist_sum_impl(const void* Xc, double* out, void* workspace, 
                                   int n_parts, dic_stream_t stream) {
   DIC_REQUIRE(Xc && out && workspace, DIC_ERR_INVALID_ARGUMENT, "null pointer argument");
   DIC_REQUIRE(n >= 0 && D > 0, DIC_ERR_INVALID_ARGUMENT, "bad sizes n=%lld D=%d", (long long)n, D);
+  const bool force_exact = (dtype & DIC_PAIRWISE_EXACT) != 0;
+  dtype &= ~DIC_PAIRWISE_EXACT;
   DIC_REQUIRE(dtype == 0 || dtype == 1, DIC_ERR_INVALID_ARGUMENT, "dtype must be 0 (float32) or 1 (float64)");
   DIC_REQUIRE(n_parts >= 1 && n_parts <= 1024 && part >= 0 && part < n_parts, DIC_ERR_INVALID_ARGUMENT,
               "bad stripe %d of %d", part, n_parts);
@@ -1536,9 +1553,9 @@ static int pairwise_dist_sum_impl(const void* Xc, double* out, void* workspace, 
     DIC_CUDA(cudaMemsetAsync(out, 0, sizeof(double), st));
     return DIC_OK;
   }
-  // float32 clusters of useful size go to the tensor-core kernel (split float16 / TF32 operands, float32-grade dots);
-  // DIC_PAIRWISE_EXACT=1 forces the direct (x_i - x_j)^2 CUDA-core kernel, float64 always uses it.
-  static const bool force_exact = getenv("DIC_PAIRWISE_EXACT") != nullptr;
+  // float32 clusters of useful size go to the tensor-core kernel (split float16 / TF32 operands, float32-grade dots; the
+  // caller centres the cluster); dtype | DIC_PAIRWISE_EXACT forces the direct (x_i - x_j)^2 CUDA-core kernel in the
+  // data's own precision, float64 always uses it.
   if (dtype == 0 && !force_exact && n >= 512 && pairwise_tc_supported(Xc, D))
     return launch_pairwise_tc(static_cast<const float*>(Xc), out, workspace, n, D, st, part, n_parts);
   return dtype == 0 ? launch_pairwise<float>(Xc, out, workspace, n, D, st, part, n_parts)

@@ -23,9 +23,17 @@
 //   * epilogue: ni + nj - 2 dot, clamp, sqrt.approx, float32 two-sum per thread, float64 across threads;
 //     mbarriers carry the stage-free / accumulator-full / accumulator-empty hand-offs, all waits bounded.
 #include <cuda_fp16.h>
-#include <stdlib.h>
 
 #include "common.cuh"
+
+// Per-role cycle counters (clock64 around every mbarrier wait of CTA 0) exist only in the benchmark build:
+//   NVCC_EXTRA=-DDIC_TC_PROFILE python -m deep_interpolation_clustering_b200.build --force   (benchmarks/README.md)
+// The product library carries none of it: no counters in the pipeline loops, no allocation, sync or output in a call.
+#ifdef DIC_TC_PROFILE
+#define DIC_PROF(...) __VA_ARGS__
+#else
+#define DIC_PROF(...)
+#endif
 
 namespace dic {
 namespace {
@@ -274,7 +282,7 @@ __device__ __forceinline__ void unrank_tile(int64_t t, int64_t nb, int64_t& bi, 
 //              accumulator
 __global__ void __launch_bounds__(kThreads, 1)
 pairwise_tc_kernel(const float* __restrict__ X, const float* __restrict__ norms, double* __restrict__ partial,
-                   int64_t n, int D, long long* __restrict__ dbg, int part, int n_parts) {
+                   int64_t n, int D, DIC_PROF(long long* __restrict__ dbg,) int part, int n_parts) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   TcSmem& S = *reinterpret_cast<TcSmem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -321,9 +329,9 @@ pairwise_tc_kernel(const float* __restrict__ X, const float* __restrict__ norms,
       unrank_tile(t, nb, bi, bj);
       const int acc = (int)(i & 1), b = (int)(stage & 1);
       const int u = (int)(stage >> 1);
-      long long c0 = clock64();
+      DIC_PROF(long long c0 = clock64();)
       if (!bar_wait_bounded(&S.se[b], (uint32_t)((u & 1) ^ 1))) S.timeout = 1;   // stage b free again
-      long long c1 = clock64();
+      DIC_PROF(long long c1 = clock64();)
       if (kchunks > 1 || bi != cur_bi) {
         // the row block is about to change: the MMAs of the previous stage must be done with it
         if (stage > 0 && !bar_wait_bounded(&S.se[b ^ 1], (uint32_t)(((stage - 1) >> 1) & 1))) S.timeout = 1;
@@ -332,9 +340,9 @@ pairwise_tc_kernel(const float* __restrict__ X, const float* __restrict__ norms,
         tile_store(areg, S.a_hi, S.a_lo, lt);
         cur_bi = bi;
       }
-      long long c2 = clock64();
+      DIC_PROF(long long c2 = clock64();)
       tile_store(breg, S.b_hi[b], S.b_lo[b], lt);
-      long long c3 = clock64();
+      DIC_PROF(long long c3 = clock64();)
       if (stage + 1 < nstages) {                               // prefetch the next stage's column block
         const int64_t i2 = (stage + 1) / kchunks;
         const int kc2 = (int)(stage + 1 - i2 * kchunks);
@@ -342,10 +350,11 @@ pairwise_tc_kernel(const float* __restrict__ X, const float* __restrict__ norms,
         unrank_tile(vcta + i2 * vgrid, nb, bi2, bj2);
         tile_fetch(breg, X, n, D, bj2 * kTile, kc2 * kKC, lt);
       }
-      long long c4 = clock64();
+      DIC_PROF(long long c4 = clock64();)
       fence_proxy_async();         // generic-proxy stores -> visible to the tensor core (async proxy)
       named_bar_sync(1, 128);
-      long long c5 = clock64();
+      DIC_PROF(long long c5 = clock64();)
+#ifdef DIC_TC_PROFILE
       if (dbg && lt == 32 && blockIdx.x == 0) {
         atomicAdd((unsigned long long*)&dbg[0], (unsigned long long)(c1 - c0));   // wait stage free
         atomicAdd((unsigned long long*)&dbg[1], (unsigned long long)(c2 - c1));   // row block reload
@@ -354,12 +363,15 @@ pairwise_tc_kernel(const float* __restrict__ X, const float* __restrict__ norms,
         atomicAdd((unsigned long long*)&dbg[4], (unsigned long long)(c5 - c4));   // loader barrier
         atomicAdd((unsigned long long*)&dbg[5], 1ull);
       }
+#endif
       if (lt == 0) {
-        long long d0 = clock64();
+        DIC_PROF(long long d0 = clock64();)
         if (kc == 0) {             // accumulator drained by the epilogue of tile i - 2
           if (!bar_wait_bounded(&S.te[acc], (uint32_t)(((i >> 1) & 1) ^ 1))) S.timeout = 1;
         }
+#ifdef DIC_TC_PROFILE
         if (dbg && blockIdx.x == 0) atomicAdd((unsigned long long*)&dbg[6], (unsigned long long)(clock64() - d0));
+#endif
         tc_fence_after();
         const uint32_t d_tmem = tmem + (uint32_t)acc * kTile;
         const uint32_t b_hi = smem_u32(S.b_hi[b]), b_lo = smem_u32(S.b_lo[b]);
@@ -375,7 +387,9 @@ pairwise_tc_kernel(const float* __restrict__ X, const float* __restrict__ norms,
         }
         umma_commit(&S.se[b]);                      // stage b reusable once these MMAs have read it
         if (kc + 1 == kchunks) umma_commit(&S.tf[acc]);   // accumulator complete -> epilogue
+#ifdef DIC_TC_PROFILE
         if (dbg && blockIdx.x == 0) atomicAdd((unsigned long long*)&dbg[7], (unsigned long long)(clock64() - d0));
+#endif
       }
     }
   } else {
@@ -392,9 +406,9 @@ pairwise_tc_kernel(const float* __restrict__ X, const float* __restrict__ norms,
       const int64_t gi = i0 + tid;                  // TMEM lane = tile row = thread
       const float ni = gi < n ? __ldg(norms + gi) : 0.f;
       named_bar_sync(2, 128);
-      long long e0 = clock64();
+      DIC_PROF(long long e0 = clock64();)
       if (!bar_wait_bounded(&S.tf[acc], (uint32_t)((i >> 1) & 1))) S.timeout = 1;
-      long long e1 = clock64();
+      DIC_PROF(long long e1 = clock64();)
       tc_fence_after();
       float tile_sum = 0.f;
       const bool plain = (bi != bj) && (i0 + kTile <= n) && (j0 + kTile <= n);   // no diagonal, no ragged edge
@@ -425,10 +439,12 @@ pairwise_tc_kernel(const float* __restrict__ X, const float* __restrict__ norms,
       }
       tc_fence_before();
       mbar_arrive(&S.te[acc]);                      // this thread is done with accumulator `acc`
+#ifdef DIC_TC_PROFILE
       if (dbg && tid == 0 && blockIdx.x == 0) {
         atomicAdd((unsigned long long*)&dbg[8], (unsigned long long)(e1 - e0));          // wait accumulator
         atomicAdd((unsigned long long*)&dbg[9], (unsigned long long)(clock64() - e1));   // drain + distances
       }
+#endif
       {                                             // float32 two-sum: no float64 arithmetic per tile
         const float v = (bi == bj) ? tile_sum : 2.f * tile_sum;
         const float sum = acc_hi + v;
@@ -636,7 +652,7 @@ pack_split_kernel(const float* __restrict__ X, unsigned char* __restrict__ packe
 template <bool ROWSUMS, int NK, int NH>
 __global__ void __launch_bounds__(kThreads64, 1)
 pairwise_tc64_kernel(const unsigned char* __restrict__ packed, const float* __restrict__ norms,
-                     double* __restrict__ partial, int64_t n, int L, long long* __restrict__ dbg,
+                     double* __restrict__ partial, int64_t n, int L, DIC_PROF(long long* __restrict__ dbg,)
                      const int32_t* __restrict__ tile_cluster, double* __restrict__ rowsum, int K, int part,
                      int n_parts, const unsigned* __restrict__ absmax_bits) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -683,11 +699,11 @@ pairwise_tc64_kernel(const unsigned char* __restrict__ packed, const float* __re
     // ================= producer: TMA bulk copies =================
     if (lane == 0) {
       int64_t item = 0, g = 0;
-      long long pw_a = 0, pw_b = 0;
+      DIC_PROF(long long pw_a = 0, pw_b = 0;)
       while (it.next(p, j0, j1) && !*timeout) {
-        long long c0 = clock64();
+        DIC_PROF(long long c0 = clock64();)
         if (!bar_wait_bounded(&S.a_empty, (uint32_t)((item & 1) ^ 1))) { *timeout = 1; break; }
-        pw_a += clock64() - c0;
+        DIC_PROF(pw_a += clock64() - c0;)
         mbar_expect_tx(&S.a_full, (uint32_t)(NH * kBlockB));
         const unsigned char* arow = packed + NH * p * (int64_t)kBlockB;    // the NH blocks of the item are adjacent
 #pragma unroll
@@ -697,9 +713,9 @@ pairwise_tc64_kernel(const unsigned char* __restrict__ packed, const float* __re
           const unsigned char* bcol = packed + bj * (int64_t)kBlockB;
           for (int kc = 0; kc < NK; ++kc, ++g) {
             const int slot = (int)(g % kStages);
-            c0 = clock64();
+            DIC_PROF(c0 = clock64();)
             if (!bar_wait_bounded(&S.b_empty[slot], (uint32_t)(((g / kStages) & 1) ^ 1))) { *timeout = 1; break; }
-            pw_b += clock64() - c0;
+            DIC_PROF(pw_b += clock64() - c0;)
             mbar_expect_tx(&S.b_full[slot], (uint32_t)kChunkB);
             bulk_g2s(S.b[slot][0], bcol + kc * kChunkB, kTileB, &S.b_full[slot]);
             bulk_g2s(S.b[slot][1], bcol + kc * kChunkB + kTileB, kTileB, &S.b_full[slot]);
@@ -707,7 +723,9 @@ pairwise_tc64_kernel(const unsigned char* __restrict__ packed, const float* __re
         }
         ++item;
       }
+#ifdef DIC_TC_PROFILE
       if (dbg && blockIdx.x == 0) { dbg[10] = pw_a; dbg[11] = pw_b; }
+#endif
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
@@ -716,34 +734,34 @@ pairwise_tc64_kernel(const unsigned char* __restrict__ packed, const float* __re
     // of a K step issue back to back.  (With the loop inside `if (lane == 0)` every UTCHMMA operand went through
     // an ELECT / R2UR.BROADCAST waterfall: 96 clk per MMA issued against ~53 clk of tensor-pipe time.)
     {
-      const bool leader = lane == 0;
+      DIC_PROF(const bool leader = lane == 0;)
       // redux.sync results are uniform by construction: the compiler cannot know that a shared-memory load is
       const uint32_t tmem_u = __reduce_or_sync(0xffffffffu, tmem);
       auto stalled = [&]() { return __reduce_or_sync(0xffffffffu, (unsigned)*timeout) != 0u; };
       int64_t item = 0, g = 0, t = 0;
-      long long w_a = 0, w_acc = 0, w_b = 0;
-      const long long m0 = clock64();
+      DIC_PROF(long long w_a = 0, w_acc = 0, w_b = 0;)
+      DIC_PROF(const long long m0 = clock64();)
       const uint32_t a_base = smem_u32(&S.a[0][0][0][0]);
       while (it.next(p, j0, j1) && !stalled()) {
-        long long c0 = clock64();
+        DIC_PROF(long long c0 = clock64();)
         if (!__all_sync(0xffffffffu, bar_wait_bounded(&S.a_full, (uint32_t)(item & 1)))) { *timeout = 1; break; }
-        w_a += clock64() - c0;
+        DIC_PROF(w_a += clock64() - c0;)
         for (int64_t bj = j0; bj < j1 && !stalled(); ++bj, ++t) {
           const int buf = (int)__reduce_or_sync(0xffffffffu, (unsigned)(t & 1));          // uniform (see tmem_u)
-          c0 = clock64();
+          DIC_PROF(c0 = clock64();)
           if (!__all_sync(0xffffffffu, bar_wait_bounded(&S.acc_empty[buf], (uint32_t)(((t >> 1) & 1) ^ 1)))) {
             *timeout = 1;
             break;
           }
-          w_acc += clock64() - c0;
+          DIC_PROF(w_acc += clock64() - c0;)
           for (int kc = 0; kc < NK; ++kc, ++g) {
             const int slot = (int)__reduce_or_sync(0xffffffffu, (unsigned)(g % kStages));   // uniform
-            c0 = clock64();
+            DIC_PROF(c0 = clock64();)
             if (!__all_sync(0xffffffffu, bar_wait_bounded(&S.b_full[slot], (uint32_t)((g / kStages) & 1)))) {
               *timeout = 1;
               break;
             }
-            w_b += clock64() - c0;
+            DIC_PROF(w_b += clock64() - c0;)
             tc_fence_after();
             const uint32_t b_hi = smem_u32(S.b[slot][0]), b_lo = smem_u32(S.b[slot][1]);
 #pragma unroll
@@ -773,9 +791,11 @@ pairwise_tc64_kernel(const unsigned char* __restrict__ packed, const float* __re
         if (elect_one()) umma_commit(&S.a_empty);             // the resident row blocks may be replaced
         ++item;
       }
+#ifdef DIC_TC_PROFILE
       if (dbg && blockIdx.x == 0 && leader) {
         dbg[0] = clock64() - m0; dbg[1] = w_a; dbg[2] = w_acc; dbg[3] = w_b; dbg[4] = t; dbg[5] = item;
       }
+#endif
     }
   } else {
     // ================= epilogue: 8 warps, (row block h | column half, TMEM lane quarter q) =================
@@ -786,8 +806,8 @@ pairwise_tc64_kernel(const unsigned char* __restrict__ packed, const float* __re
     const int h = NH == 2 ? ew >> 2 : 0, cbeg = NH == 2 ? 0 : 2 * (ew >> 2);
     int64_t t = 0;
     bool dead = false;
-    long long w_full = 0, w_work = 0;
-    const long long ep0 = clock64();
+    DIC_PROF(long long w_full = 0, w_work = 0;)
+    DIC_PROF(const long long ep0 = clock64();)
     while (!dead && it.next(p, j0, j1)) {
       const int64_t bi = NH * p + h;
       const int64_t i0 = bi * kBlk, gi = i0 + 32 * q + lane;
@@ -818,10 +838,10 @@ pairwise_tc64_kernel(const unsigned char* __restrict__ packed, const float* __re
             kcur = kc;
           }
         }
-        const long long e0 = clock64();
+        DIC_PROF(const long long e0 = clock64();)
         if (!bar_wait_bounded(&S.acc_full[buf], (uint32_t)((t >> 1) & 1))) { *timeout = 1; dead = true; break; }
-        const long long e1 = clock64();
-        w_full += e1 - e0;
+        DIC_PROF(const long long e1 = clock64();)
+        DIC_PROF(w_full += e1 - e0;)
         tc_fence_after();
         float tile_sum = 0.f;
         // ROWSUMS: every tile counts, padding is neutralised by its -inf norm, only the diagonal needs care
@@ -904,7 +924,7 @@ pairwise_tc64_kernel(const unsigned char* __restrict__ packed, const float* __re
           __syncwarp();
           if (lane == 0) mbar_arrive(&S.acc_empty[buf]);       // this warp is done with the accumulators
         }
-        w_work += clock64() - e1;
+        DIC_PROF(w_work += clock64() - e1;)
         acc_add((ROWSUMS || bj == bi) ? tile_sum : 2.f * tile_sum);
       }
       if (ROWSUMS) {
@@ -916,10 +936,12 @@ pairwise_tc64_kernel(const unsigned char* __restrict__ packed, const float* __re
     }
     total = warp_sum(total);
     if (lane == 0) S.red[ew] = total;
+#ifdef DIC_TC_PROFILE
     if (dbg && blockIdx.x == 0 && lane == 0 && (ew == 0 || ew == 5)) {
       dbg[6 + 2 * (ew != 0)] = w_full; dbg[7 + 2 * (ew != 0)] = w_work;
       if (ew == 0) { dbg[12] = clock64() - ep0; dbg[13] = t; }
     }
+#endif
   }
 
   tc_fence_before();
@@ -990,22 +1012,23 @@ static int launch_tc64_t(const float* X, double* out, void* workspace, int64_t n
   int blocks = (int)(my_items < sms ? my_items : sms);
   if (blocks > 1024) blocks = 1024;
   const size_t smem = sizeof(Smem64<NK, NH>) + 1024;
+#ifdef DIC_TC_PROFILE      // benchmark build only: per-role cycle counters of CTA 0, printed after the run
   long long* dbg = nullptr;
-  if (getenv("DIC_TC_PROFILE")) {          // debug: per-role cycle counters of CTA 0, printed after the run
     cudaMalloc(&dbg, 16 * sizeof(long long));
     cudaMemsetAsync(dbg, 0, 16 * sizeof(long long), st);
-  }
+#endif
   if (rows_mode) {
     auto kern = pairwise_tc64_kernel<true, NK, NH>;
     DIC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<blocks, kThreads64, smem, st>>>(packed, norms, partial, n, (int)L, dbg, tile_cluster, rowsum, K, part,
+    kern<<<blocks, kThreads64, smem, st>>>(packed, norms, partial, n, (int)L, DIC_PROF(dbg,) tile_cluster, rowsum, K, part,
                                            n_parts, absmax);
   } else {
     auto kern = pairwise_tc64_kernel<false, NK, NH>;
     DIC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<blocks, kThreads64, smem, st>>>(packed, norms, partial, n, (int)L, dbg, nullptr, nullptr, 0, part, n_parts,
+    kern<<<blocks, kThreads64, smem, st>>>(packed, norms, partial, n, (int)L, DIC_PROF(dbg,) nullptr, nullptr, 0, part, n_parts,
                                            absmax);
   }
+#ifdef DIC_TC_PROFILE
   if (dbg) {
     long long h[16];
     cudaMemcpyAsync(h, dbg, sizeof(h), cudaMemcpyDeviceToHost, st);
@@ -1019,6 +1042,7 @@ static int launch_tc64_t(const float* X, double* out, void* workspace, int64_t n
             h[9] / T, h[10] / T, h[11] / T, h[12] / T, h[13]);
     cudaFree(dbg);
   }
+#endif
   DIC_LAUNCH_CHECK("pairwise_tc64_kernel");
   if (!rows_mode) {
     sum_partials_kernel<<<1, 32, 0, st>>>(partial, out, blocks);
@@ -1052,8 +1076,7 @@ bool pairwise_tc_supported(const void* X, int D) { return D % 4 == 0 && D >= 4 &
 
 int launch_pairwise_tc(const float* X, double* out, void* workspace, int64_t n, int D, cudaStream_t st, int part,
                        int n_parts) {
-  static const bool force_v1 = getenv("DIC_PAIRWISE_TC_V1") != nullptr;      // debug: the register-staged kernel
-  if (D <= kTc64MaxD && !force_v1) return launch_pairwise_tc64(X, out, workspace, n, D, st, part, n_parts);
+  if (D <= kTc64MaxD) return launch_pairwise_tc64(X, out, workspace, n, D, st, part, n_parts);
   float* norms = static_cast<float*>(workspace);
   double* partial = reinterpret_cast<double*>(static_cast<unsigned char*>(workspace) +
                                               ((size_t)n * sizeof(float) + 255) / 256 * 256);
@@ -1069,12 +1092,13 @@ int launch_pairwise_tc(const float* X, double* out, void* workspace, int64_t n, 
   if (blocks > 1024) blocks = 1024;
   const size_t smem = sizeof(TcSmem) + 1024;
   DIC_CUDA(cudaFuncSetAttribute(pairwise_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+#ifdef DIC_TC_PROFILE      // benchmark build only: per-role cycle counters of CTA 0, printed after the run
   long long* dbg = nullptr;
-  if (getenv("DIC_TC_PROFILE")) {          // debug: per-role cycle counters of CTA 0, printed after the run
     cudaMalloc(&dbg, 16 * sizeof(long long));
     cudaMemsetAsync(dbg, 0, 16 * sizeof(long long), st);
-  }
-  pairwise_tc_kernel<<<blocks, kThreads, smem, st>>>(X, norms, partial, n, D, dbg, part, n_parts);
+#endif
+  pairwise_tc_kernel<<<blocks, kThreads, smem, st>>>(X, norms, partial, n, D, DIC_PROF(dbg,) part, n_parts);
+#ifdef DIC_TC_PROFILE
   if (dbg) {
     long long h[16];
     cudaMemcpyAsync(h, dbg, sizeof(h), cudaMemcpyDeviceToHost, st);
@@ -1085,6 +1109,7 @@ int launch_pairwise_tc(const float* X, double* out, void* workspace, int64_t n, 
             h[6] / (h[5] + 1), h[7] / (h[5] + 1), h[8] / (h[5] + 1), h[9] / (h[5] + 1));
     cudaFree(dbg);
   }
+#endif
   DIC_LAUNCH_CHECK("pairwise_tc_kernel");
   sum_partials_kernel<<<1, 32, 0, st>>>(partial, out, blocks);
   DIC_LAUNCH_CHECK("sum_partials_kernel");

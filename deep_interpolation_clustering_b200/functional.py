@@ -25,6 +25,15 @@ def _require_cuda_f32(t, name):
         raise TypeError(f"{name} must be float32 (got {t.dtype})")
 
 
+def _no_input_grad(x, name):
+    """The interpolation operators produce no gradient with respect to the observation tensor: no caller of the
+    reference needs one (the trainers never set requires_grad on the batch; the reference's own mask-plane gradient
+    is NaN).  Fail loudly rather than hand autograd a silent None."""
+    if x.requires_grad:
+        raise RuntimeError(f"{name}.requires_grad is set, but the B200 interpolation operators are differentiable with "
+                           f"respect to their parameters (and the RBF grid values) only; pass {name}.detach()")
+
+
 def _planes(x, C, name):
     """x is (B, 4C, T) like the reference's input, or (B, 3C, T) when the never-read hold-out plane
     (interpolation_layer.py:26-30) was left on the host.  Rows of one encounter must be dense; the
@@ -103,6 +112,7 @@ def sci(x, kernel, ref_t):
     """SingleChannelInterp in planar layout: returns u (B, 3C, R) = rows [y | w | y']."""
     for t, n in ((x, "x"), (kernel, "kernel"), (ref_t, "ref_t")):
         _require_cuda_f32(t, n)
+    _no_input_grad(x, "x")
     x, xs = _planes(x, kernel.numel(), "x")
     return _SCI.apply(x, kernel.contiguous(), ref_t.contiguous(), xs)
 
@@ -191,6 +201,7 @@ def rbf_readout(v, x, kernel, ref_t):
         raise ValueError(f"expected v (B,C,R) and raw_input (B,4C,T); got {tuple(v.shape)}, {tuple(x.shape)}")
     if v.shape[2] != ref_t.numel():
         raise ValueError(f"interp_data has {v.shape[2]} grid points but ref_points is {ref_t.numel()}")
+    _no_input_grad(x, "raw_input")
     x, xs = _planes(x, v.shape[1], "raw_input")
     return _RBF.apply(v.contiguous(), x, kernel.contiguous(), ref_t.contiguous(), xs)
 

@@ -35,43 +35,58 @@ def _as_device(X, device=None):
 
 
 TC_MIN_ROWS = 512      # below this the exact CUDA-core kernel is used and the dtype is preserved
+DIC_PAIRWISE_EXACT = 16  # include/dic_b200.h: OR-ed into dtype, forces the direct (x_i - x_j)^2 kernel
 
 
-def pairwise_dist_sum(Xc, exact=False):
-    """sum over the full n x n Euclidean distance matrix of the rows of Xc (device tensor).
+def _pairwise_call(fn_name, Xc, exact, out, ws, extra=()):
+    """Shared body of pairwise_dist_sum / pairwise_dist_sum_part.  Asynchronous: the NaN the tensor-core kernels
+    write when their pipeline stalls is checked by the caller when it reads the value (check_pairwise_sums)."""
+    if not exact and Xc.shape[0] >= TC_MIN_ROWS and Xc.shape[1] % 4 == 0:
+        # distances are translation invariant; the Gram-form tensor-core kernel wants ||x||^2 small against them
+        Xc = (Xc - Xc.mean(dim=0, keepdim=True)).to(torch.float32)
+    Xc = Xc.contiguous()
+    if Xc.data_ptr() % 16:
+        Xc = Xc.clone()
+    n, D = Xc.shape
+    if out is None:
+        out = torch.empty(1, dtype=torch.float64, device=Xc.device)
+    L = _lib.lib()
+    need = int(L.dic_pairwise_workspace_bytes(n, D))
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(need, dtype=torch.uint8, device=Xc.device)
+    dt = _DT[Xc.dtype] | (DIC_PAIRWISE_EXACT if exact else 0)
+    with torch.cuda.device(Xc.device):
+        _lib.check(getattr(L, fn_name)(_lib.ptr(Xc), _lib.ptr(out), _lib.ptr(ws), n, D, dt, *extra,
+                                       _lib.current_stream(Xc.device)), fn_name)
+    return out
+
+
+def check_pairwise_sums(values, what="dic_pairwise_dist_sum"):
+    """values: host floats read back from the kernels.  NaN is the kernels' 'pipeline stalled' sentinel
+    (pairwise_tc.cu: every mbarrier wait is bounded) - raise instead of letting it reach the gap table."""
+    for v in values:
+        if v != v:
+            raise _lib.DicError(f"{what}: the tensor-core pipeline reported a stalled mbarrier hand-off (NaN result); "
+                                "the launch did not complete its tile list")
+    return values
+
+
+def pairwise_dist_sum(Xc, exact=False, out=None, ws=None):
+    """sum over the full n x n Euclidean distance matrix of the rows of Xc (device tensor) -> (1,) float64 tensor.
 
     Clusters of >= 512 rows are centred (distances are translation invariant) and evaluated in
     float32 on the tensor cores (tcgen05, split-operand products: float32-grade dot products, ~1e-7 relative on
-    the sum); ``exact=True`` keeps the input dtype and the direct (x_i - x_j)^2 kernel.
+    the sum); ``exact=True`` keeps the input dtype and ALWAYS takes the direct (x_i - x_j)^2 CUDA-core kernel
+    (dtype | DIC_PAIRWISE_EXACT), whatever the cluster size.  ``out`` (1-element float64 view) and ``ws`` (byte
+    workspace) let a sweep reuse its buffers.
     """
-    if not exact and Xc.shape[0] >= TC_MIN_ROWS and Xc.shape[1] % 4 == 0:
-        Xc = (Xc - Xc.mean(dim=0, keepdim=True)).to(torch.float32)
-    Xc = Xc.contiguous()
-    n, D = Xc.shape
-    out = torch.empty(1, dtype=torch.float64, device=Xc.device)
-    L = _lib.lib()
-    ws = torch.empty(int(L.dic_pairwise_workspace_bytes(n, D)), dtype=torch.uint8, device=Xc.device)
-    with torch.cuda.device(Xc.device):
-        _lib.check(L.dic_pairwise_dist_sum(_lib.ptr(Xc), _lib.ptr(out), _lib.ptr(ws), n, D, _DT[Xc.dtype],
-                                           _lib.current_stream(Xc.device)), "dic_pairwise_dist_sum")
-    return out
+    return _pairwise_call("dic_pairwise_dist_sum", Xc, exact, out, ws)
 
 
-def pairwise_dist_sum_part(Xc, part, n_parts, exact=False):
+def pairwise_dist_sum_part(Xc, part, n_parts, exact=False, out=None, ws=None):
     """Stripe `part` of `n_parts` of pairwise_dist_sum(Xc): Xc holds ALL rows of the cluster (identical on every
     rank), the stripes tile the kernel's tile list once, so the n_parts results add up to the full sum."""
-    if not exact and Xc.shape[0] >= TC_MIN_ROWS and Xc.shape[1] % 4 == 0:
-        Xc = (Xc - Xc.mean(dim=0, keepdim=True)).to(torch.float32)
-    Xc = Xc.contiguous()
-    n, D = Xc.shape
-    out = torch.empty(1, dtype=torch.float64, device=Xc.device)
-    L = _lib.lib()
-    ws = torch.empty(int(L.dic_pairwise_workspace_bytes(n, D)), dtype=torch.uint8, device=Xc.device)
-    with torch.cuda.device(Xc.device):
-        _lib.check(L.dic_pairwise_dist_sum_part(_lib.ptr(Xc), _lib.ptr(out), _lib.ptr(ws), n, D, _DT[Xc.dtype],
-                                                int(part), int(n_parts), _lib.current_stream(Xc.device)),
-                   "dic_pairwise_dist_sum_part")
-    return out
+    return _pairwise_call("dic_pairwise_dist_sum_part", Xc, exact, out, ws, (int(part), int(n_parts)))
 
 
 class KM(object):
@@ -84,6 +99,7 @@ class KM(object):
         self._pairwise_part = _pairwise_part
         self._dev = _device
         self._comm = None                   # set while a row-sharded sweep runs
+        self._ws = None                     # pairwise workspace, reused across the evaluations of a sweep
         self.k_max = k_max
         self.out_path = os.path.join(out_path, "plot") if out_path else None
         if self.out_path:
@@ -100,16 +116,36 @@ class KM(object):
 
     # ---- the two "inertia" definitions ---------------------------------------------------------
     def _cluster_sums(self, a, X):
+        """[(sum of the full n_c x n_c distance matrix, n_c)] for the labels present in `a` (np.unique order).
+        The rows are sorted by label ONCE (one stable argsort + one gather), the per-cluster launches share one
+        workspace and write into one (K,) buffer, and the host reads that buffer once: two synchronisations per
+        evaluation instead of two per cluster."""
         if self._comm is not None and self._comm.on:
             return self._cluster_sums_sharded(a, X, self._comm)
         Xd = _as_device(X, self._dev)
-        ad = torch.as_tensor(np.asarray(a) if not isinstance(a, torch.Tensor) else a).to(Xd.device)
+        ad = torch.as_tensor(np.asarray(a) if not isinstance(a, torch.Tensor) else a).to(Xd.device).long()
+        if ad.numel() == 0:
+            return []
+        order = torch.argsort(ad, stable=True)
+        Xs = Xd[order]
+        counts = torch.bincount(ad).tolist()                     # sync 1: cluster sizes
         pw = self._pairwise or pairwise_dist_sum
-        out = []
-        for c in torch.unique(ad).tolist():                      # np.unique(a): sorted labels present
-            Xc = Xd[ad == c]
-            out.append((pw(Xc, exact=self.exact_pairwise), Xc.shape[0]))
-        return out
+        sums = torch.zeros(len(counts), dtype=torch.float64, device=Xd.device)
+        if self._pairwise is None:
+            need = int(_lib.lib().dic_pairwise_workspace_bytes(max(counts), Xd.shape[1]))
+            if self._ws is None or self._ws.numel() < need or self._ws.device != Xd.device:
+                self._ws = torch.empty(need, dtype=torch.uint8, device=Xd.device)
+        off = 0
+        for c, n in enumerate(counts):
+            if n:
+                Xc = Xs[off:off + n]
+                if self._pairwise is None:
+                    pw(Xc, exact=self.exact_pairwise, out=sums[c:c + 1], ws=self._ws)
+                else:
+                    sums[c:c + 1] = pw(Xc, exact=self.exact_pairwise)
+                off += n
+        host = check_pairwise_sums(sums.tolist())                # sync 2: the K sums
+        return [(host[c], n) for c, n in enumerate(counts) if n]
 
     def _cluster_sums_sharded(self, a, X, comm):
         """_cluster_sums for rows sharded over the ranks of `comm` (pairwise inertia): the rows of one
@@ -132,8 +168,11 @@ class KM(object):
             parts = comm.gather(pad)
             Xc = torch.cat([parts[r, :int(counts[r, c])] for r in range(comm.size)])
             sums[c:c + 1] = pw(Xc, comm.rank, comm.size, exact=self.exact_pairwise)
+        if bool(torch.isnan(sums).any()):          # a stalled pipeline must not ride through the all-reduce as NaN
+            check_pairwise_sums([float("nan")], "dic_pairwise_dist_sum_part")
         comm.sum_(sums)
-        return [(sums[c], int(total[c])) for c in range(K) if int(total[c]) > 0]
+        host = sums.tolist()
+        return [(host[c], int(total[c])) for c in range(K) if int(total[c]) > 0]
 
     def compute_inertia_v1(self, a, X):
         """mean_c [ mean of the full n_c x n_c distance matrix ]   (:334-342)."""

@@ -18,7 +18,6 @@ centre-shift stopping, a final E-step when not strictly converged, best of n_ini
 from __future__ import annotations
 
 import numbers
-import os
 
 import numpy as np
 import torch
@@ -197,6 +196,7 @@ class KMeansB200:
         self.sharded = sharded or process_group is not None
         self.process_group = process_group
         self._backend = _backend            # test hook: a CPU stand-in for _Device (gloo tests)
+        self.batched = True                 # eight Lloyd iterations per host sync (dic_kmeans_lloyd_run); False = one
 
     # ---- helpers ---------------------------------------------------------------------------
     def _device(self):
@@ -354,7 +354,7 @@ class KMeansB200:
 
     def _lloyd(self, st, centers, tol_eff, comm):
         """One run of sklearn/cluster/_kmeans.py:630-757."""
-        if not comm.on and hasattr(st, "lloyd_run") and os.environ.get("DIC_KMEANS_NO_BATCH") is None:
+        if not comm.on and hasattr(st, "lloyd_run") and self.batched:
             return self._lloyd_batched(st, centers, tol_eff, comm)
         st.labels.fill_(-1)
         strict = False

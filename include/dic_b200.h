@@ -205,6 +205,11 @@ int dic_dec_kl_fwd_bwd(const float* z, const float* mu, const double* colsum, fl
 #define DIC_KM_COUNT_CHANGES 1
 #define DIC_KM_KEEP_LABELS 2
 #define DIC_KM_NO_INERTIA 4 /* skip stats[0] and stats[2] (a Lloyd iteration does not need them) */
+/* Kernel selector in bits 8..11 of `flags` (parity tests and benchmarks address every kernel through the ABI; the
+ * library reads no environment variables): 0 = chosen by shape and measured cost, 1 = specialised tile kernel,
+ * 2 = streaming half-warp-per-row, 3 = generic tile kernel, 4 = general kernel; a kernel that does not cover the
+ * shape answers DIC_ERR_UNSUPPORTED. */
+#define DIC_KM_KERNEL(k) ((k) << 8)
 size_t dic_kmeans_workspace_bytes(int K, int D);
 int dic_kmeans_assign(const void* X, const void* centers, int32_t* labels, double* sums,
                       double* counts, double* stats, void* workspace, int64_t N, int D, int K,
@@ -247,7 +252,10 @@ int dic_kmeans_min_d2(const void* X, const void* cands, const void* min_d2, void
  * KM.compute_inertia_v1 / computer_intertia_v2, p2_clustering_optK.py:334-351:
  *   Xc (n,D) rows of one cluster (gathered by the caller), out (1) float64 =
  *   sum_{i,i'} ||x_i - x_i'||  over the FULL n x n matrix (zero diagonal included).
- * The n x n matrix is never materialised.  Limit: D <= 512. */
+ * The n x n matrix is never materialised.  Limit: D <= 512.
+ * dtype | DIC_PAIRWISE_EXACT: always the direct (x_i - x_j)^2 CUDA-core kernel in the data's own precision (float32
+ * clusters of >= 512 rows otherwise take the tensor-core Gram form, which expects a centred cluster). */
+#define DIC_PAIRWISE_EXACT 16
 size_t dic_pairwise_workspace_bytes(int64_t n, int D);
 int dic_pairwise_dist_sum(const void* Xc, double* out, void* workspace, int64_t n, int D,
                           int dtype, dic_stream_t stream);

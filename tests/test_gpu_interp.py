@@ -380,3 +380,22 @@ def test_allmasked_vital_contributes_zero_gradient(golden):
         g2[b, [c, C + c, 2 * C + c], :] = 0.0
     want = O.sci_backward(x2, g["sci_kernel"].astype(np.float64), O.linspace_grid(H, R), C, g2.transpose(0, 2, 1))
     _check("allmasked/d_sci_kernel", k.grad, want)
+
+
+def test_observation_tensor_gradient_is_refused_loudly():
+    """The operators are differentiable wrt their parameters (and the RBF grid values) only; an x that requires grad
+    must raise instead of receiving a silent None (the reference's own mask-plane gradient is NaN, Appendix A.1)."""
+    import deep_interpolation_clustering_b200 as dic
+    from deep_interpolation_clustering_b200 import synth
+    dev = torch.device("cuda:0")
+    x = torch.tensor(synth.make_encounters(4, 6, 32, 24.0, seed=0), device=dev, requires_grad=True)
+    sci = dic.SingleChannelInterp(24, 24.0, 6, 32, dev)
+    rbf = dic.RBF(24.0, 24, 6, 6, 0.0, dic.basis_func_dict()["gaussian"], dev)
+    rbf.compress_fc = torch.nn.Identity()
+    with pytest.raises(RuntimeError, match="requires_grad"):
+        sci(x)
+    with pytest.raises(RuntimeError, match="requires_grad"):
+        rbf(torch.zeros((4, 6, 24), device=dev), x)
+    # a frozen kernel with a plain input still runs (no saved state, no backward)
+    sci.kernel.requires_grad_(False)
+    assert sci(x.detach()).shape == (4, 24, 18)

@@ -268,3 +268,64 @@ def test_lloyd_kernel_dispatch_matches_sklearn(dtag, D, K):
         record(tag + "_centers", km.cluster_centers_, ref.cluster_centers_, 1e-5, 1e-5)
         record(tag + "_inertia", km.inertia_, ref.inertia_, 1e-5, 0)
         _labels_equal_mod_ties(tag + "_predict", km.predict(Xv), ref.predict(Xv), Xv, ref.cluster_centers_)
+
+
+def test_exact_pairwise_is_honoured_for_float32_clusters():
+    """KM(exact_pairwise=True) / pairwise_dist_sum(exact=True): float32 clusters of >= 512 rows must take the direct
+    (x_i - x_j)^2 kernel (dtype | DIC_PAIRWISE_EXACT), not the Gram-form tensor-core kernel on UNCENTRED rows.  With a
+    mean offset of 1e3 the Gram form in float32 loses the distances entirely; the direct form does not care."""
+    from deep_interpolation_clustering_b200 import synth
+    from deep_interpolation_clustering_b200.gap import KM, pairwise_dist_sum
+    X = (synth.make_blobs(2000, 64, 3, seed=11) + 1000.0).astype(np.float32)
+    Xd = torch.from_numpy(X).cuda()
+    truth = float(pairwise_dist_sum(Xd.double(), exact=True))
+    X64 = X.astype(np.float64)
+    ref = np.sqrt(np.maximum(((X64[:, None, :] - X64[None]) ** 2).sum(2), 0)).sum()
+    record("pairwise_exact_f64_offset", truth, ref, 1e-10, 0)
+    record("pairwise_exact_f32_offset", float(pairwise_dist_sum(Xd, exact=True)), truth, 2e-6, 0)
+    record("pairwise_default_f32_offset", float(pairwise_dist_sum(Xd)), truth, 2e-6, 0)     # centred by the wrapper
+    a = np.arange(2000) % 2
+    v_exact = KM(5, exact_pairwise=True).compute_inertia_v1(a, X)
+    v_ref = np.mean([np.sqrt(np.maximum(((X64[a == c][:, None] - X64[a == c][None]) ** 2).sum(2), 0)).mean()
+                     for c in (0, 1)])
+    record("inertia_v1_exact_f32_offset", v_exact, v_ref, 2e-6, 0)
+
+
+def test_stalled_pipeline_sentinel_raises():
+    from deep_interpolation_clustering_b200 import _lib
+    from deep_interpolation_clustering_b200.gap import check_pairwise_sums
+    assert check_pairwise_sums([1.0, 0.0]) == [1.0, 0.0]
+    with pytest.raises(_lib.DicError, match="stalled"):
+        check_pairwise_sums([1.0, float("nan")])
+
+
+@pytest.mark.parametrize("dtag,D,K", [("f32", 64, 4), ("f32", 64, 10), ("f64", 64, 4), ("f32", 256, 10), ("f32", 128, 16),
+                                      ("f32", 100, 7), ("f64", 32, 12)])
+def test_every_lloyd_kernel_through_the_abi_selector(dtag, D, K):
+    """DIC_KM_KERNEL(k) in the flags addresses each Lloyd kernel explicitly (no environment switches): all of them must
+    produce the labels, sums and counts of the general kernel; a kernel that does not cover the shape says so."""
+    from deep_interpolation_clustering_b200 import synth
+    from deep_interpolation_clustering_b200.kmeans import _Device
+    dt = torch.float32 if dtag == "f32" else torch.float64
+    X = torch.from_numpy(synth.make_blobs(20011, D, 6, seed=D + K)).cuda().to(dt)
+    cen = X[:K].clone().contiguous()
+    out = {}
+    for sel in (4, 0, 1, 2, 3):
+        st = _Device(X, K)
+        try:
+            st.assign(cen, sel << 8)
+        except ValueError as e:
+            assert "does not cover" in str(e)
+            continue
+        out[sel] = (st.labels.cpu().numpy().copy(), st.sums.cpu().numpy().copy(), st.counts.cpu().numpy().copy(),
+                    st.stats.cpu().numpy().copy())
+    assert 4 in out and 0 in out and len(out) >= 3
+    lab, sums, counts, stats = out[4]
+    for sel, (l2, s2, c2, t2) in out.items():
+        _labels_equal_mod_ties(f"selector{sel}", l2, lab, X.cpu().numpy(), cen.cpu().numpy())
+        if np.array_equal(l2, lab):
+            np.testing.assert_allclose(s2, sums, rtol=1e-12, atol=1e-9)
+            np.testing.assert_array_equal(c2, counts)
+            np.testing.assert_allclose(t2[0], stats[0], rtol=1e-6)
+    with pytest.raises(ValueError):
+        _Device(X, K).assign(cen, 9 << 8)
