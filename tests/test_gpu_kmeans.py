@@ -324,7 +324,8 @@ def test_every_lloyd_kernel_through_the_abi_selector(dtag, D, K):
     for sel, (l2, s2, c2, t2) in out.items():
         _labels_equal_mod_ties(f"selector{sel}", l2, lab, X.cpu().numpy(), cen.cpu().numpy())
         if np.array_equal(l2, lab):
-            np.testing.assert_allclose(s2, sums, rtol=1e-12, atol=1e-9)
+            # float32 kernels add a tile's rows in float32 before the float64 partials: 1e-6-grade agreement
+            np.testing.assert_allclose(s2, sums, rtol=2e-6, atol=2e-6 * float(np.abs(sums).max()))
             np.testing.assert_array_equal(c2, counts)
             np.testing.assert_allclose(t2[0], stats[0], rtol=1e-6)
     with pytest.raises(ValueError):
