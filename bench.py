@@ -47,6 +47,10 @@ WORKLOADS = {
     # for p, the KL sum and the closed-form gradients dz, dmu (clustering_interp.py:186,205-207)
     "c3": dict(T=256, R=96, K=4, B=1_000_000, dec_kl=True,
                name="c3: interp fwd+bwd + DEC q/p/KL fwd+bwd, K=4, 1M enc x 6 vitals x <=256 obs, 96 ref points"),
+    # c4 = the K-selection sweep of p2 AS WRITTEN (p2_clustering_optK.py:33,36,37,353-410): K = 2..10, 20 reference draws,
+    # n_init = 10 on a 1M x 64 latent matrix; one step = one whole sweep (c4_arm below; not an interp workload)
+    "c4": dict(T=256, R=96, K=10, B=1_000_000, sweep=True,
+               name="c4: gap-statistic k-means sweep K=2..10, 20 reference draws, n_init=10, 1M x 64-d latents (p2 path)"),
     "c5": dict(T=1024, R=192, K=16, B=131_072,
                name="c5 (stress shape): interp fwd+bwd + DEC assign, 6 vitals x <=1024 obs, 192 ref points, K=16, "
                     "one 131,072-encounter shard of the 10M per step"),
@@ -67,6 +71,14 @@ def parse():
                     help="host format of x in the e2e arm: ragged/packed rows (default) or the dense planes")
     ap.add_argument("--cpu-sample", type=int, default=256, help="encounters in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--c4-dim", type=int, default=64)
+    ap.add_argument("--c4-kmax", type=int, default=10)
+    ap.add_argument("--c4-refs", type=int, default=20)
+    ap.add_argument("--c4-ninit", type=int, default=10)
+    ap.add_argument("--c4-draw", default="device", choices=["device", "device32", "host"],
+                    help="reference sets: float64 uniform draws generated on the GPU (default; the reference draws float64 "
+                         "on the host, :370), float32 device draws, or numpy host draws uploaded per set")
+    ap.add_argument("--c4-cpu-n", type=int, default=1500, help="rows of the CPU-baseline sweep (n x n matrices)")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
 
@@ -390,6 +402,193 @@ def device_arm(args, rank, world, local_rank):
     return line
 
 
+# ----------------------------------------------------------------------------------------------
+# c4: the K-selection sweep of p2 (gap statistic), task-parallel over the ranks
+# ----------------------------------------------------------------------------------------------
+def c4_cpu_arm(n_rows, dim, k_max, refs, n_init):
+    """The reference's algorithm (oracle/kmeans_oracle.gap_statistic = KM.compute_gap_internal_metric restated, with
+    scikit-learn's KMeans as the estimator exactly like p2_clustering_optK.py:284) on a matrix small enough for its
+    n_c x n_c distance matrices.  Returns (rows/s, seconds, cores)."""
+    import numpy as np
+    from sklearn.cluster import KMeans
+    from deep_interpolation_clustering_b200 import synth
+    from oracle import kmeans_oracle
+    X = synth.make_blobs(n_rows, dim, 5, seed=4)
+    np.random.seed(123)
+    t0 = time.perf_counter()
+    kmeans_oracle.gap_statistic(lambda k, data: KMeans(n_clusters=k, n_init=n_init).fit_predict(data), X, k_max=k_max,
+                                n_references=refs, version=1)
+    dt = time.perf_counter() - t0
+    return n_rows / dt, dt, os.cpu_count() or 1
+
+
+def c4_arm(args, rank, world, local_rank):
+    """One step = one gap-statistic sweep as p2 runs it (K = 2..k_max, `refs` reference draws, n_init restarts, version
+    1 inertia) through KM.compute_gap_internal_metric + KMeansB200.  Every rank holds the whole matrix (256 MB) and takes
+    the (k, reference set) fits round-robin; ONE all-reduce of the inertia table ends the sweep."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from deep_interpolation_clustering_b200 import _lib
+    from deep_interpolation_clustering_b200.gap import KM, pairwise_dist_sum
+    from deep_interpolation_clustering_b200.kmeans import KMeansB200, _Device
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    N, D = args.encounters, args.c4_dim
+    g = torch.Generator(device=dev).manual_seed(4)                   # the same matrix on every rank
+    centres = 4.0 * torch.randn((5, D), generator=g, device=dev)
+    lab = torch.randint(0, 5, (N,), generator=g, device=dev)
+    X = (centres[lab] + torch.randn((N, D), generator=g, device=dev)).contiguous()     # SURVEY 8d: blobs, sigma 1
+    draw = None if args.c4_draw == "host" else args.c4_draw
+    group = dist.group.WORLD if world > 1 else None
+
+    def sweep(data, k_max, refs, n_init, timers=None):
+        km = KM(k_max, None, [], n_init, refs)
+        km.timers = timers
+        df = km.compute_gap_internal_metric(KMeansB200(n_init=n_init, random_state=0), data, k_max=k_max,
+                                            n_references=refs, version=1, draw=draw, group=group, task_parallel=True,
+                                            seed=0)
+        torch.cuda.synchronize(dev)
+        return df
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    warm = max(args.warmup, 3)
+    for _ in range(warm):                                            # every kernel and shape class once, cheaply
+        sweep(X, min(args.c4_kmax, 3), 1, 1)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    stream = torch.cuda.current_stream(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    timers = {}
+    e0.record(stream)
+    for i in range(args.steps):
+        df = sweep(X, args.c4_kmax, args.c4_refs, args.c4_ninit)
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    t_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t_ms) / args.steps
+
+    # e2e: the call p2 makes - a HOST float32 ndarray in, a DataFrame out (H2D of the matrix and of nothing else;
+    # D2H of the labels for the internal metrics' interface and of the K sums per evaluation)
+    e2e = None
+    if not args.no_e2e:
+        Xh = X.cpu().numpy()
+        barrier()
+        t0 = time.perf_counter()
+        df_h = sweep(Xh, args.c4_kmax, args.c4_refs, args.c4_ninit)
+        barrier()
+        wall = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(wall, op=dist.ReduceOp.MAX)
+        same = bool(np.allclose(df_h.astype(float).values, df.astype(float).values, rtol=1e-9, atol=0))
+        e2e = {"value": round(N / float(wall), 1), "unit": "rows/s", "seconds_per_sweep": round(float(wall), 3),
+               "h2d_bytes_per_step": int(N * D * 4 * world), "d2h_bytes_per_step": int(8 * 9 * (args.c4_refs + 1) * 10),
+               "same_table_as_device_input": same,
+               "path": "KM.compute_gap_internal_metric(KMeansB200(n_init), X_host float32 ndarray, k_max, n_references, "
+                       "version=1) -> pandas DataFrame: the signature of p2_clustering_optK.py:353; H2D of the matrix inside "
+                       "the timed region, reference sets drawn on the device"}
+
+    # phase breakdown (synchronised timers; a separate, reduced sweep so that the timed sweeps run asynchronously)
+    sweep(X, args.c4_kmax, 2, 2, timers)
+    # kernel rooflines, live: one Lloyd pass (K = 10, the dtype the reference sets have) and the pairwise inertia
+    L = _lib.lib()
+    ref_dtype = torch.float32 if args.c4_draw == "device32" else torch.float64
+    kern = {}
+    for name, Xk in (("lloyd_pass_data_f32", X), ("lloyd_pass_refs", X.to(ref_dtype))):
+        st = _Device(Xk, 10)
+        cen = Xk[:10].clone().contiguous()
+        st.assign(cen, 0)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(20):
+            st.assign(cen, 1 | 4)
+        b.record(stream)
+        b.synchronize()
+        ms = a.elapsed_time(b) / 20
+        nbytes = N * D * Xk.element_size() + N * 4
+        kern[name] = {"ms": round(ms, 4), "dtype": str(Xk.dtype).replace("torch.", ""), "algorithmic_gb": round(nbytes / 1e9, 4),
+                      "gbps": round(nbytes / 1e9 / (ms * 1e-3), 1)}
+        del st
+    n_pw = min(N, 262_144)
+    Xc = X[:n_pw].contiguous()
+    pairwise_dist_sum(Xc)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(stream)
+    for _ in range(3):
+        s_pw = pairwise_dist_sum(Xc)
+    b.record(stream)
+    b.synchronize()
+    ms = a.elapsed_time(b) / 3
+    pairs = n_pw * (n_pw - 1) / 2
+    kern["pairwise_inertia"] = {"ms": round(ms, 3), "rows": n_pw, "unordered_pairs_per_s": round(pairs / (ms * 1e-3), 1),
+                                "tflops_dense_equiv": round(3 * 2 * pairs * 2 * D / (ms * 1e-3) / 1e12, 2),
+                                "note": "3 split-float16 MMAs per product (hi.hi + hi.lo + lo.hi), upper triangle only; "
+                                        "one sqrt per pair in the epilogue"}
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return None
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    for k in ("lloyd_pass_data_f32", "lloyd_pass_refs"):
+        kern[k]["hbm_frac"] = round(kern[k]["gbps"] / hbm_peak, 4)
+    fits = 9 * (args.c4_refs + 1) * args.c4_ninit if args.c4_kmax == 10 else (args.c4_kmax - 1) * (args.c4_refs + 1) * args.c4_ninit
+    phase = {k: (round(v, 3) if isinstance(v, float) else v) for k, v in timers.items()}
+    fit_s = timers.get("fit_ref", 0) + timers.get("fit_data", 0)
+    pw_s = timers.get("inertia_ref", 0) + timers.get("inertia_data", 0)
+    dom = "lloyd_pass_refs" if fit_s >= pw_s else "pairwise_inertia"
+    if dom == "lloyd_pass_refs":
+        roofline = {"kernel": "kmeans_assign (one Lloyd pass over a reference set, K=10)", "bound": "hbm",
+                    "achieved": kern[dom]["gbps"], "peak": hbm_peak, "unit": "GB/s", "frac": kern[dom]["hbm_frac"], "traffic": None,
+                    "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"}
+    else:
+        tf_peak = float(peaks.get("bf16_tflops", 1650.0))
+        roofline = {"kernel": "pairwise_tc64 (tcgen05 kind::f16, 3 split products per pair)", "bound": "tensor",
+                    "achieved": kern[dom]["tflops_dense_equiv"], "peak": tf_peak, "unit": "TFLOP/s",
+                    "frac": round(kern[dom]["tflops_dense_equiv"] / tf_peak, 4), "traffic": None,
+                    "peak_source": "MEASURED_PEAKS.json (cuBLAS bf16)" if "bf16_tflops" in peaks else "fallback"}
+    line = {
+        "metric": "latent rows/s through one gap-statistic sweep (K=2..10, 20 reference draws, n_init=10)",
+        "value": round(N / (ms_per_step * 1e-3), 1), "unit": "rows/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
+        "ms_per_step": round(ms_per_step, 1), "seconds_per_sweep": round(ms_per_step / 1e3, 3), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32 data / " + ("f32" if args.c4_draw == "device32" else "f64") + " reference sets",
+        "data": "synthetic",
+        "config": {"workload": CFG_NAME, "rows": N, "dim": D, "k": f"2..{args.c4_kmax}", "n_references": args.c4_refs,
+                   "n_init": args.c4_ninit, "kmeans_fits_per_sweep": fits, "pairwise_evaluations_per_sweep": (args.c4_kmax - 1) * (args.c4_refs + 1),
+                   "draws": args.c4_draw, "parallelism": f"task-parallel x{world} ((k, reference set) fits dealt round-robin, data replicated)",
+                   "warmup_steps": f"{warm} reduced sweeps (K=2..3, 1 reference set, n_init=1): every kernel class warm",
+                   "l2": "each matrix (256-512 MB) exceeds L2 (126 MB)"},
+        "clocks": clocks, "gpu_launches": "not counted: data-dependent (Lloyd iterations until convergence; ~2-3 launches each)",
+        "kernels": kern, "phases_reduced_sweep_2refs_ninit2": phase, "roofline": roofline, "e2e": e2e,
+        "gap_table": {str(int(k)): round(float(v), 6) for k, v in zip(df["k"], df["gap"])},
+        "best_k": int(df["gap"].astype(float).idxmax()),
+    }
+    if not args.no_cpu_baseline:
+        v, dt, cores = c4_cpu_arm(args.c4_cpu_n, D, args.c4_kmax, args.c4_refs, args.c4_ninit)
+        line["cpu_baseline"] = {"value": round(v, 2), "unit": "rows/s", "cores": cores, "kind": "port",
+                                "sample": f"the same sweep (K=2..{args.c4_kmax}, {args.c4_refs} draws, n_init={args.c4_ninit}) on "
+                                          f"{args.c4_cpu_n} rows x {D}: oracle/kmeans_oracle.gap_statistic (the reference's routine "
+                                          f"restated) over scikit-learn KMeans, {dt:.1f} s; the reference's n_c x n_c distance "
+                                          "matrices make N = 1M infeasible on any host (terabytes)"}
+    if world > 1:
+        dist.destroy_process_group()
+    return line
+
+
 def bind_to_gpu_numa(index):
     """Pin this process to the CPUs NVML reports as local to GPU `index` BEFORE the pinned host buffers are
     allocated and first touched, so that their pages live on the GPU's NUMA node (with 8 ranks streaming from
@@ -532,6 +731,20 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference" and w.get("sweep"):
+        if rank != 0:
+            return
+        v, dt, cores = c4_cpu_arm(args.c4_cpu_n, args.c4_dim, args.c4_kmax, args.c4_refs, args.c4_ninit)
+        print(json.dumps({"impl": "reference", "metric": "latent rows/s through one gap-statistic sweep (K=2..10, 20 reference "
+                          "draws, n_init=10)", "value": round(v, 2), "unit": "rows/s", "n_gpus": args.gpus, "steps": 1, "warmup": 0,
+                          "ms_per_step": round(dt * 1e3, 1), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                          "dtype": "f32 data / f64 reference sets", "data": "synthetic",
+                          "config": {"workload": CFG_NAME, "rows": args.c4_cpu_n, "dim": args.c4_dim},
+                          "cpu_baseline": {"value": round(v, 2), "unit": "rows/s", "cores": cores, "kind": "port",
+                                           "sample": f"{args.c4_cpu_n} rows (the n_c x n_c matrices cap the reference)"},
+                          "e2e": {"value": round(v, 2), "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "gpu_launches": 0}), flush=True)
+        return
     if args.impl == "reference":
         if rank != 0:
             return
@@ -554,7 +767,12 @@ def main():
         return
     if world != args.gpus and world == 1 and args.gpus > 1:
         sys.stderr.write(f"--gpus {args.gpus} needs torchrun with {args.gpus} ranks; running 1 rank\n")
-    line = device_arm(args, rank, world, local_rank)
+    if w.get("sweep"):
+        if args.steps == 5:            # the default step count is for the interp workloads; one sweep is ~1 minute
+            args.steps = 1
+        line = c4_arm(args, rank, world, local_rank)
+    else:
+        line = device_arm(args, rank, world, local_rank)
     if line is not None:
         print(json.dumps(line), flush=True)
 

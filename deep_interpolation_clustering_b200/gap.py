@@ -26,12 +26,24 @@ from .kmeans import KMeansB200, _Comm, _DT
 
 def _as_device(X, device=None):
     if isinstance(X, torch.Tensor):
+        if not X.is_cuda and device is None and torch.cuda.is_available():
+            X = X.cuda()
         return X.contiguous()
     X = np.asarray(X)
     if X.dtype not in (np.float32, np.float64):
         X = X.astype(np.float64)
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
     return torch.from_numpy(np.ascontiguousarray(X)).to(dev)
+
+
+def _data_range(data):
+    """(min, max - min) of the data matrix as numpy scalars in the data's own dtype: p2_clustering_optK.py:360
+    (`data.min()`, `data.max() - data.min()` on the float32 feature matrix)."""
+    if isinstance(data, torch.Tensor):
+        mn, mx = data.min().cpu().numpy()[()], data.max().cpu().numpy()[()]
+    else:
+        mn, mx = data.min(), data.max()
+    return mn, mx - mn
 
 
 TC_MIN_ROWS = 512      # below this the exact CUDA-core kernel is used and the dtype is preserved
@@ -100,6 +112,7 @@ class KM(object):
         self._dev = _device
         self._comm = None                   # set while a row-sharded sweep runs
         self._ws = None                     # pairwise workspace, reused across the evaluations of a sweep
+        self.timers = None                  # set to {} to collect per-phase seconds of a task-parallel sweep (bench.py)
         self.k_max = k_max
         self.out_path = os.path.join(out_path, "plot") if out_path else None
         if self.out_path:
@@ -113,6 +126,19 @@ class KM(object):
         table = {"Dunn_Index": internal_eval.DunnIndex, "Sihouette": internal_eval.Sihouette,
                  "Davies-Bouldin_Index": internal_eval.DBIndex, "Calinski-Harabasz": internal_eval.CHIndex}
         return [table[name]() for name in self.internal_metrics_names]
+
+    def _timed(self, key, fn, *args):
+        """fn(*args); with self.timers set, bracketed by device synchronisations and accumulated under `key`."""
+        if self.timers is None:
+            return fn(*args)
+        import time
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out = fn(*args)
+        torch.cuda.synchronize()
+        self.timers[key] = self.timers.get(key, 0.0) + time.perf_counter() - t0
+        self.timers[key + "_calls"] = self.timers.get(key + "_calls", 0) + 1
+        return out
 
     # ---- the two "inertia" definitions ---------------------------------------------------------
     def _cluster_sums(self, a, X):
@@ -196,7 +222,9 @@ class KM(object):
         then drawn from its own generator seeded by (seed, k, j), so the table does not depend on the world size
         (give ``clustering`` an integer ``random_state`` for the same property of its k-means++ draws)."""
         import pandas as pd
-        data = np.asarray(data) if not isinstance(data, torch.Tensor) else data.cpu().numpy()
+        if not (isinstance(data, torch.Tensor) and data.is_cuda and _accepts_tensor(clustering)):
+            # host arrays as the reference passes them; a CUDA tensor stays where it is for a device estimator
+            data = np.asarray(data) if not isinstance(data, torch.Tensor) else data.cpu().numpy()
         if len(data.shape) == 1:
             data = data.reshape(-1, 1)
         if row_sharded:
@@ -212,8 +240,7 @@ class KM(object):
         ref_dtype = torch.float32 if draw == "device32" else torch.float64
         draw = np.random.random_sample if (draw is None or device_draws) else draw
         inertia = self.compute_inertia_v1 if version == 1 else self.computer_intertia_v2
-        data_min = data.min()
-        data_rng = data.max() - data_min                                             # :360
+        data_min, data_rng = _data_range(data)                                       # :360
         k_rng = range(2, k_max + 1)
         vals = pd.DataFrame(index=k_rng, columns=["k", "gap", "ref", "act", "ref_s"] + self.internal_metrics_names)
         data_dev = _as_device(data, self._dev)
@@ -249,8 +276,7 @@ class KM(object):
         device_draws = isinstance(draw, str) and draw in ("device", "device32")
         ref_dtype = torch.float32 if draw == "device32" else torch.float64
         inertia = self.compute_inertia_v1 if version == 1 else self.computer_intertia_v2
-        data_min = data.min()
-        data_rng = data.max() - data_min
+        data_min, data_rng = _data_range(data)
         k_rng = range(2, k_max + 1)
         n_m = len(self.internal_metrics)
         table = np.zeros((len(k_rng), n_references + 1 + n_m), dtype=np.float64)
@@ -265,23 +291,25 @@ class KM(object):
                     continue
                 clustering.n_clusters = k
                 if j == n_references:
-                    a = clustering.fit_predict(data_dev if on_dev else data)
-                    table[ki, j] = inertia(a, data_dev)
+                    a = self._timed("fit_data", clustering.fit_predict, data_dev if on_dev else data)
+                    table[ki, j] = self._timed("inertia_data", inertia, a, data_dev)
                     a_host = a.cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
-                    table[ki, j + 1:] = [m(data_dev, a_host) for m in self.internal_metrics]
+                    table[ki, j + 1:] = [self._timed("metrics", m, data_dev, a_host) for m in self.internal_metrics]
                     continue
                 task_seed = (int(seed) * 1000003 + k * 1009 + j) % (2 ** 31)
                 if device_draws and on_dev:
-                    gen = torch.Generator(device=data_dev.device).manual_seed(task_seed)
-                    ref_dev = torch.rand(data.shape, dtype=ref_dtype, device=data_dev.device, generator=gen) \
-                        * float(data_rng) + float(data_min)
+                    def draw_dev():
+                        gen = torch.Generator(device=data_dev.device).manual_seed(task_seed)
+                        return torch.rand(data.shape, dtype=ref_dtype, device=data_dev.device, generator=gen) \
+                            * float(data_rng) + float(data_min)
+                    ref_dev = self._timed("draw", draw_dev)
                     reference = None
                 else:
                     sample = np.random.RandomState(task_seed).random_sample if (draw is None or device_draws) else draw
                     reference = sample(data.shape) * data_rng + data_min
                     ref_dev = _as_device(reference, self._dev)
-                a = clustering.fit_predict(ref_dev if on_dev else reference)
-                table[ki, j] = inertia(a, ref_dev)
+                a = self._timed("fit_ref", clustering.fit_predict, ref_dev if on_dev else reference)
+                table[ki, j] = self._timed("inertia_ref", inertia, a, ref_dev)
         if ws > 1:
             nccl = dist.get_backend(group) == "nccl"
             buf = torch.from_numpy(table).to(data_dev.device) if nccl else torch.from_numpy(table)
@@ -309,8 +337,9 @@ class KM(object):
         lohi = torch.tensor([float(data.min()), -float(data.max())], dtype=torch.float64, device=data_dev.device)
         if comm.on:
             dist.all_reduce(lohi, op=dist.ReduceOp.MIN, group=group)
-        data_min = data.dtype.type(float(lohi[0]))                                  # :360 over ALL rows, in the
-        data_rng = data.dtype.type(float(-lohi[1])) - data_min                      # data's own arithmetic
+        np_t = np.float32 if (data.dtype in (np.float32, torch.float32)) else np.float64
+        data_min = np_t(float(lohi[0]))                                             # :360 over ALL rows, in the
+        data_rng = np_t(float(-lohi[1])) - data_min                                 # data's own arithmetic
         k_rng = range(2, k_max + 1)
         vals = pd.DataFrame(index=k_rng, columns=["k", "gap", "ref", "act", "ref_s"])
         on_dev = _accepts_tensor(clustering)
@@ -359,7 +388,12 @@ class KM(object):
         results = {}
         for method in select_opt_k:
             if method == "elbow":
-                results["elbow"] = self.elbow(train_feat, valid_feat)
+                tr, va = self.elbow(train_feat, valid_feat)
+                results["elbow"] = (tr, va)
+                if self.out_path:      # the numbers behind {train,valid}_elbow.png (:266-274), one row per k
+                    import pandas as pd
+                    pd.DataFrame({"k": list(range(2, self.k_max + 1)), "train_distortion": tr,
+                                  "valid_distortion": va}).to_csv(os.path.join(self.out_path, "elbow.csv"), index=False)
             elif method == "gap_sts":
                 df = self.compute_gap_internal_metric(KMeansB200(n_init=self.n_init), train_feat, self.k_max,
                                                       n_references=self.gap_b, version=1).astype(float)
