@@ -649,21 +649,31 @@ def e2e_arm(args, hp, dev, world):
         else:
             F_.upload_encounters(host[k], out=dbuf[slot], stream=copy_stream)
 
+    # The uploads run as ONE continuous prefetch stream, like a data loader with one batch of look-ahead: while chunk
+    # g is computed, chunk g + 1 is on the wire - also across a step boundary (the first chunk of step s + 1 travels
+    # while the last chunk of step s is computed and its results are read back).
+    state = {"next": 0}        # global index of the next chunk to upload; chunk g lives in slot g & 1
+
+    def prefetch():
+        g = state["next"]
+        slot = g & 1
+        with torch.cuda.stream(copy_stream):
+            if g >= 2:
+                copy_stream.wait_event(free[slot])        # the compute that last read this slot is done
+            upload(g % len(host), slot)
+            ready[slot].record(copy_stream)
+        state["next"] = g + 1
+
     def step():
         for p_ in params:
             p_.grad = None
         loss_acc = torch.zeros((), device=dev)
-        with torch.cuda.stream(copy_stream):
-            upload(0, 0)
-            ready[0].record(copy_stream)
         for i in range(n_chunks):
-            cur = i & 1
-            if i + 1 < n_chunks:
-                with torch.cuda.stream(copy_stream):
-                    if i >= 1:
-                        copy_stream.wait_event(free[cur ^ 1])
-                    upload((i + 1) % len(host), cur ^ 1)
-                    ready[cur ^ 1].record(copy_stream)
+            if state["next"] == 0:
+                prefetch()                                 # very first chunk of the run
+            g = state["next"] - 1
+            cur = g & 1
+            prefetch()                                     # chunk g + 1 (possibly the next step's first)
             main.wait_event(ready[cur])
             x = dbuf[cur]
             sl = slice(i * Bc, (i + 1) * Bc)
@@ -709,7 +719,8 @@ def e2e_arm(args, hp, dev, world):
             "upload": args.e2e_upload,
             "path": ("pinned host PackedEncounters (ragged rows: valid prefix of value/time + one count per vital, packed "
                      "once per data set outside the timed region) -> PackedStaging.upload (3 contiguous H2D copies + "
-                     "device-side expansion to dense planes per chunk, copy stream, double buffered)" if packed_mode else
+                     "device-side expansion to dense planes per chunk, copy stream, double buffered, one chunk of look-ahead "
+                     "also across step boundaries)" if packed_mode else
                      "pinned host x (B,4C,T) -> upload_encounters (one strided DMA of the 3 live planes per chunk, copy "
                      "stream, double buffered)") +
                     " -> SingleChannelInterp/CrossChannelInterp/RBF modules (autograd fwd+bwd; RBF.compress_fc = Identity, "
