@@ -25,6 +25,11 @@ int launch_pairwise_tc(const float* X, double* out, void* workspace, int64_t n, 
 int launch_cluster_rowsums_tc(const float* X, const int32_t* perm, const int32_t* tile_cluster, double* rowsum,
                               void* workspace, int64_t n_pad, int D, int K, cudaStream_t st);
 
+// kmeans_tc.cu
+bool kmeans_tc_covers(const void* X, int D, int K, int flags);
+int launch_kmeans_assign_tc(const float* X, const float* centers, int32_t* labels, double* ws, int64_t N, int D, int K,
+                            int flags, int want_sums, const double* done, int max_blocks, int* nb_out, cudaStream_t st);
+
 namespace {
 
 template <typename T> struct Vec16;
@@ -1198,6 +1203,9 @@ int km_blocks(int K, int D) {
   return (int)b;
 }
 
+// Where the tensor-core pass beats the CUDA-core kernels (measured, benchmarks/_km_pass.py).
+static bool kmeans_tc_wins(int D, int K) { return false && D >= 64 && K >= 1; }
+
 template <typename T>
 int launch_assign(const void* X, const void* centers, int32_t* labels, double* sums, double* counts,
                   double* stats, void* workspace, int64_t N, int D, int K, int flags, cudaStream_t st,
@@ -1205,7 +1213,27 @@ int launch_assign(const void* X, const void* centers, int32_t* labels, double* s
   // bits 8..11 of flags: 0 = pick by shape and measured cost; 1..4 = that kernel or DIC_ERR_UNSUPPORTED (parity tests
   // and benchmarks address every kernel through the ABI; nothing here reads the environment)
   const int which = (flags >> 8) & 15;
-  DIC_REQUIRE(which <= 4, DIC_ERR_INVALID_ARGUMENT, "DIC_KM_KERNEL(%d): unknown kernel", which);
+  DIC_REQUIRE(which <= 5, DIC_ERR_INVALID_ARGUMENT, "DIC_KM_KERNEL(%d): unknown kernel", which);
+  // tensor-core E-step (kmeans_tc.cu): float32 rows of 64 / 128 / 256 elements in the Lloyd-loop form of the pass
+  if constexpr (sizeof(T) == 4) {
+    const bool tc_ok = kmeans_tc_covers(X, D, K, flags);
+    DIC_REQUIRE(tc_ok || which != 5, DIC_ERR_UNSUPPORTED, "DIC_KM_KERNEL(5): the tensor-core pass covers float32, D in "
+                "{64,128,256}, K <= 16 with DIC_KM_NO_INERTIA and without DIC_KM_KEEP_LABELS (got D=%d K=%d flags=%d)", D, K,
+                flags & 255);
+    if (tc_ok && (which == 5 || (which == 0 && kmeans_tc_wins(D, K)))) {
+      double* wsd = static_cast<double*>(workspace);
+      int nb = 0;
+      int rc = launch_kmeans_assign_tc(static_cast<const float*>(X), static_cast<const float*>(centers), labels, wsd, N, D, K,
+                                       flags, sums != nullptr, done, km_blocks(K, D), &nb, st);
+      if (rc) return rc;
+      const int nn = K * D + K + 4;
+      kmeans_finish_kernel<<<(nn + 7) / 8, 256, 0, st>>>(wsd, sums, counts, stats, nb, K, D, done);
+      DIC_LAUNCH_CHECK("kmeans_finish_kernel");
+      return DIC_OK;
+    }
+  } else {
+    DIC_REQUIRE(which != 5, DIC_ERR_UNSUPPORTED, "DIC_KM_KERNEL(5): the tensor-core pass is float32 only");
+  }
   // specialised tile kernel: rows of exactly 16, 32 or 64 sixteen-byte vectors (D = 64 / 128 / 256 float32,
   // 32 / 64 / 128 float64).  64 vectors (the reference's latent width, D = 256) leave room for ONE resident CTA per
   // SM only, still 9x the general kernel that served this shape before (3.6 ms per pass at 500k x 256, K = 10).

@@ -301,36 +301,75 @@ def test_stalled_pipeline_sentinel_raises():
 
 
 @pytest.mark.parametrize("dtag,D,K", [("f32", 64, 4), ("f32", 64, 10), ("f64", 64, 4), ("f32", 256, 10), ("f32", 128, 16),
-                                      ("f32", 100, 7), ("f64", 32, 12)])
-def test_every_lloyd_kernel_through_the_abi_selector(dtag, D, K):
-    """DIC_KM_KERNEL(k) in the flags addresses each Lloyd kernel explicitly (no environment switches): all of them must
-    produce the labels, sums and counts of the general kernel; a kernel that does not cover the shape says so."""
+                                      ("f32", 100, 7), ("f64", 32, 12), ("f32", 64, 16), ("f32", 256, 4), ("f32", 128, 2),
+                                      ("f32", 256, 16), ("f32", 64, 1)])
+@pytest.mark.parametrize("n", [20011, 128, 77])
+def test_every_lloyd_kernel_through_the_abi_selector(dtag, D, K, n):
+    """DIC_KM_KERNEL(k) in the flags addresses each Lloyd kernel explicitly (no environment switches): all of them -
+    CUDA-core kernels 1-4 and the tcgen05 E-step kernel 5 - must produce the labels, sums, counts and changed-label
+    count of the general kernel in the Lloyd-loop form of the pass; a kernel that does not cover the shape says so."""
     from deep_interpolation_clustering_b200 import synth
     from deep_interpolation_clustering_b200.kmeans import _Device
     dt = torch.float32 if dtag == "f32" else torch.float64
-    X = torch.from_numpy(synth.make_blobs(20011, D, 6, seed=D + K)).cuda().to(dt)
+    X = torch.from_numpy(synth.make_blobs(n, D, 6, seed=D + K)).cuda().to(dt)
     cen = X[:K].clone().contiguous()
+    prev = torch.from_numpy(np.random.RandomState(n).randint(0, K, size=n).astype(np.int32)).cuda()
     out = {}
-    for sel in (4, 0, 1, 2, 3):
+    base = 1 | 4                                     # DIC_KM_COUNT_CHANGES | DIC_KM_NO_INERTIA: what a Lloyd iteration passes
+    for sel in (4, 0, 1, 2, 3, 5):
         st = _Device(X, K)
+        st.labels.copy_(prev)
         try:
-            st.assign(cen, sel << 8)
+            st.assign(cen, base | sel << 8)
         except ValueError as e:
-            assert "does not cover" in str(e)
+            assert "does not cover" in str(e) or "covers" in str(e) or "float32 only" in str(e), str(e)
             continue
         out[sel] = (st.labels.cpu().numpy().copy(), st.sums.cpu().numpy().copy(), st.counts.cpu().numpy().copy(),
                     st.stats.cpu().numpy().copy())
     assert 4 in out and 0 in out and len(out) >= 3
+    if dtag == "f32" and D in (64, 128, 256):
+        assert 5 in out, "the tensor-core pass must cover this shape"
     lab, sums, counts, stats = out[4]
     for sel, (l2, s2, c2, t2) in out.items():
         _labels_equal_mod_ties(f"selector{sel}", l2, lab, X.cpu().numpy(), cen.cpu().numpy())
+        assert np.isfinite(s2).all() and np.isfinite(t2).all(), f"kernel {sel}: stalled pipeline sentinel"
+        assert c2.sum() == n
         if np.array_equal(l2, lab):
             # float32 kernels add a tile's rows in float32 before the float64 partials: 1e-6-grade agreement
             np.testing.assert_allclose(s2, sums, rtol=2e-6, atol=2e-6 * float(np.abs(sums).max()))
             np.testing.assert_array_equal(c2, counts)
-            np.testing.assert_allclose(t2[0], stats[0], rtol=1e-6)
+            assert t2[1] == stats[1], f"kernel {sel}: changed-label count {t2[1]} vs {stats[1]}"
     with pytest.raises(ValueError):
         _Device(X, K).assign(cen, 9 << 8)
+
+
+def test_tensor_core_lloyd_pass_inside_a_fit_matches_sklearn(monkeypatch):
+    """A whole fit with every Lloyd iteration forced onto the tcgen05 pass (DIC_KM_KERNEL(5)) against scikit-learn with
+    the same initial centres: labels mod near-ties, centres, inertia, iteration count (D = 64 and the real latent 256)."""
+    import warnings
+    from sklearn.cluster import KMeans
+    from deep_interpolation_clustering_b200 import synth
+    from deep_interpolation_clustering_b200 import kmeans as km_mod
+    orig = km_mod._Device.lloyd_run
+
+    def forced(self, centers, flags, n_steps, tol):
+        return orig(self, centers, flags | 5 << 8, n_steps, tol)
+    monkeypatch.setattr(km_mod._Device, "lloyd_run", forced)
+    for D, K in ((64, 10), (256, 4), (128, 7)):
+        X = synth.make_blobs(30011, D, 5, seed=D)
+        init = X[:K].copy()
+        for iters in (1, 3):
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                ref = KMeans(n_clusters=K, init=init, n_init=1, max_iter=iters, tol=0.0).fit(X)
+            km = km_mod.KMeansB200(n_clusters=K, init=init, n_init=1, max_iter=iters, tol=0.0).fit(X)
+            tag = f"tc_fit_D{D}_K{K}_it{iters}"
+            # float32-grade dots on both sides (sklearn: a float32 GEMM): rows whose float64 margin is below a few 1e-5
+            # are decided by rounding (measured worst: 1.1e-5, one row of 30,011)
+            _labels_equal_mod_ties(tag, km.labels_, ref.labels_, X, ref.cluster_centers_, tie=5e-5, max_frac=1e-3)
+            assert km.n_iter_ == ref.n_iter_
+            record(tag + "_centers", km.cluster_centers_, ref.cluster_centers_, 1e-5, 1e-5)
+            record(tag + "_inertia", km.inertia_, ref.inertia_, 1e-5, 0)
 
 
 def test_config4_size_lloyd_matches_sklearn_with_fixed_init():
