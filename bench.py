@@ -80,6 +80,7 @@ def parse():
                          "on the host, :370), float32 device draws, or numpy host draws uploaded per set")
     ap.add_argument("--c4-cpu-n", type=int, default=1500, help="rows of the CPU-baseline sweep (n x n matrices)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the multi-GPU result checks printed as `parity` (N > 1)")
     return ap.parse_args()
 
 
@@ -310,6 +311,20 @@ def device_arm(args, rank, world, local_rank):
     ms_per_step = float(t_ms) / args.steps
     value = world * B / (ms_per_step * 1e-3)
 
+    # launches of OUR kernels in one step, COUNTED (CUPTI through torch.profiler, names in namespace dic::) on one
+    # extra step outside the timed region; the static per-call table is only the fallback when CUPTI is unavailable
+    launches_per_step, launches_how = sum(HotPath.LAUNCHES[n] for n, _ in kernels), "table (CUPTI unavailable)"
+    try:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            step()
+            torch.cuda.synchronize(dev)
+        counted = sum(e.count for e in prof.key_averages() if "dic::" in e.key)
+        if counted > 0:
+            launches_per_step, launches_how = int(counted), "counted with CUPTI (kernels named dic::*) on one step"
+    except Exception:       # noqa: BLE001
+        pass
+
     # per-kernel durations (CUDA events on the launching stream), for the roofline objects
     per = {n: [] for n, _ in kernels}
     for _ in range(3):
@@ -330,6 +345,20 @@ def device_arm(args, rank, world, local_rank):
             e2e["host_numa_binding"] = prev_affinity is not None
         if prev_affinity is not None:
             os.sched_setaffinity(0, prev_affinity)        # the CPU baseline below uses all host cores again
+
+    # result checks at this world size (sharded gradients, DEC p/KL, k-means, gap sweeps vs the single-GPU truth), so
+    # that a scaling record carries parity and not only speed (deep_interpolation_clustering_b200/dist_check.py)
+    parity = None
+    if world > 1 and not args.no_parity:
+        from deep_interpolation_clustering_b200 import dist_check
+        try:
+            rep = dist_check.run(rank, world, dev)
+            parity = {"world": world, "ok": True, **{k: float(f"{v:.3e}") for k, v in rep.items()}}
+        except AssertionError as e:          # noqa: PERF203
+            parity = {"world": world, "ok": False, "error": str(e)[:300]}
+        ok = torch.tensor([1.0 if parity["ok"] else 0.0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        parity["all_ranks_ok"] = bool(ok.item() == 1.0)
 
     if rank != 0:
         if world > 1:
@@ -357,28 +386,51 @@ def device_arm(args, rank, world, local_rank):
             ktab[n]["gex2_per_s"] = round(ex2[n] / 1e9 / (m * 1e-3), 1)
             ktab[n]["mufu_frac"] = round(ex2[n] / (m * 1e-3) / mufu.value, 4)
     dom = max(kms, key=kms.get)
-    traffic, ncu_pipes = None, None   # from ONE committed ncu --set full capture: DRAM bytes per launch, pipe utilisation
+    # DRAM traffic, executed MUFU count and pipe utilisation come from ONE ncu --set full capture of this step
+    # (benchmarks/capture_traffic.py -> profiles/dram_traffic.json), tied to the SHA-256 of the kernel sources it was
+    # measured on: if the tree has changed since, the numbers are refused (null + a note), never printed stale.
+    traffic, ncu_k, traffic_note = None, None, "no capture (profiles/dram_traffic.json missing)"
     try:
+        from deep_interpolation_clustering_b200.build import sources_sha256
         tr = json.load(open(os.path.join(REPO, "profiles", "dram_traffic.json")))
-        if dom in tr["bytes_per_launch"] and args.workload == "c2":
-            traffic = round(tr["bytes_per_launch"][dom] * (B / tr["encounters"]) / 1e9, 3)
-            ncu_pipes = tr.get("pipes", {}).get(dom)
-    except Exception:
-        pass
+        if tr.get("sources_sha256") != sources_sha256():
+            traffic_note = "refused: profiles/dram_traffic.json was captured on different kernel sources (stale)"
+        elif args.workload not in ("c2", "c3"):
+            traffic_note = "capture is of the c2 shape"
+        elif dom in tr["kernels"]:
+            ncu_k = tr["kernels"][dom]
+            traffic = round(ncu_k["bytes_per_launch"] * (B / tr["encounters"]) / 1e9, 3)
+            traffic_note = f"ncu dram__bytes_read+write of one launch at {tr['encounters']} encounters, scaled to {B}"
+    except Exception as e:       # noqa: BLE001
+        traffic_note = f"no capture ({type(e).__name__})"
     roofline = {"kernel": dom, "bound": "hbm", "achieved": ktab[dom]["gbps"], "peak": hbm_peak, "unit": "GB/s",
-                "frac": ktab[dom]["hbm_frac"], "traffic": traffic, "traffic_unit": "GB per launch (ncu dram bytes, "
-                "profiles/dram_traffic.json)", "peak_source": peak_src,
-                "note": "interpolation kernels are MUFU/issue bound, not HBM bound: see roofline_sfu"}
+                "frac": ktab[dom]["hbm_frac"], "traffic": traffic, "traffic_unit": "GB per launch", "traffic_note": traffic_note,
+                "peak_source": peak_src,
+                "note": "the interpolation sweeps are MUFU / issue bound, not HBM bound: see roofline_sfu and roofline_issue"}
+    # SFU view on EXECUTED exponentials: the kernels skip pairs whose weight is below 2^-27..2^-30 of the largest and
+    # evaluate the high-pass exponential only inside its narrow window, so the algorithmic count (2 per pair for SCI,
+    # 1 for RBF) is not what runs; executed = ncu sm__inst_executed_pipe_xu (warp instructions) x 32 lanes.
+    exec_ex2 = None
+    if ncu_k and ncu_k.get("xu_warp_inst"):
+        exec_ex2 = ncu_k["xu_warp_inst"] * 32.0 * (B / tr["encounters"])
     roofline_sfu = {"kernel": dom, "bound": "sfu", "unit": "Gex2/s",
-                    "achieved": ktab[dom].get("gex2_per_s"), "peak": round(mufu.value / 1e9, 1),
-                    "frac": ktab[dom].get("mufu_frac"), "ffma_peak_gops": round(ffma.value / 1e9, 1),
+                    "achieved": round(exec_ex2 / 1e9 / (kms[dom] * 1e-3), 1) if exec_ex2 else None,
+                    "peak": round(mufu.value / 1e9, 1),
+                    "frac": round(exec_ex2 / (kms[dom] * 1e-3) / mufu.value, 4) if exec_ex2 else None,
+                    "algorithmic_gex2_per_s": ktab[dom].get("gex2_per_s"),
+                    "algorithmic_over_peak": ktab[dom].get("mufu_frac"),
+                    "ffma_peak_gops": round(ffma.value / 1e9, 1),
                     "peak_source": "dic_probe_mufu: ex2.approx-only kernel timed in this run",
-                    "ncu": ncu_pipes,
-                    "note": "algorithmic exps = 2 per (valid obs, ref point) for SCI (low+high pass), 1 for RBF; "
-                            "the kernels skip pairs whose weight is below 2^-27..2^-30 of the largest and evaluate the "
-                            "high-pass exponential only inside its narrow window, so frac may exceed 1 (ncu: issue "
-                            "slots 65-82 % busy, XU pipe 49-69 %, FMA pipe 52 %; on EXECUTED exponentials the sweeps run at ~52 % of "
-                            "the MUFU peak)"}
+                    "note": "frac = EXECUTED MUFU lane-operations per second (ncu XU-pipe instruction count of the capture x 32 / "
+                            "this run's kernel time) over the probe's rate; algorithmic_over_peak counts every (observation, "
+                            "grid point) exponential of the reference and may exceed 1 because skipped pairs are not executed"}
+    roofline_issue = {"kernel": dom, "bound": "issue", "unit": "% of issue slots",
+                      "achieved": ncu_k.get("issue_active_pct") if ncu_k else None, "peak": 100.0,
+                      "frac": round(ncu_k["issue_active_pct"] / 100.0, 4) if ncu_k and ncu_k.get("issue_active_pct") else None,
+                      "xu_pipe_pct": ncu_k.get("xu_pipe_pct") if ncu_k else None,
+                      "fma_pipe_pct": ncu_k.get("fma_pipe_pct") if ncu_k else None,
+                      "shared_bank_conflict_share": round(ncu_k["shared_bank_conflict_share"], 4) if ncu_k else None,
+                      "source": traffic_note}
 
     line = {
         "metric": "encounters/s (interp fwd+bwd + DEC assign)", "value": round(value, 1), "unit": "encounters/s",
@@ -389,9 +441,12 @@ def device_arm(args, rank, world, local_rank):
                    "parallelism": f"encounter-sharded x{world}",
                    "l2": f"inputs ({B * 4 * C * T * 4 / 1e9:.1f} GB/GPU) " + ("exceed L2" if B * 4 * C * T * 4 > 2.5e8 else
                                                                            "fit L2: flushed by the other kernels' buffers")},
-        "clocks": clocks, "gpu_launches": args.steps * sum(HotPath.LAUNCHES[n] for n, _ in kernels),
-        "kernels": ktab, "roofline": roofline, "roofline_sfu": roofline_sfu, "e2e": e2e,
+        "clocks": clocks, "gpu_launches": args.steps * launches_per_step, "gpu_launches_per_step": launches_per_step,
+        "gpu_launches_how": launches_how,
+        "kernels": ktab, "roofline": roofline, "roofline_sfu": roofline_sfu, "roofline_issue": roofline_issue, "e2e": e2e,
     }
+    if parity is not None:
+        line["parity"] = parity
     if not args.no_cpu_baseline:
         v, dt, cores = cpu_arm(args.cpu_sample, 2, 1)
         line["cpu_baseline"] = {"value": round(v, 1), "unit": "encounters/s", "cores": cores, "kind": "port",

@@ -42,6 +42,18 @@ def _deps():
     return hdrs
 
 
+def sources_sha256():
+    """SHA-256 over the kernel sources and the public header (sorted by name): what a measured profile is tied to."""
+    import hashlib
+    h = hashlib.sha256()
+    files = sorted([os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))] +
+                   [os.path.join(INCLUDE, f) for f in os.listdir(INCLUDE)])
+    for f in files:
+        h.update(os.path.basename(f).encode())
+        h.update(open(f, "rb").read())
+    return h.hexdigest()
+
+
 def _stale(target, sources):
     if not os.path.exists(target):
         return True

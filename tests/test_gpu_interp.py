@@ -13,7 +13,7 @@ from gpu_util import RTOL_GRID, record, scale_atol
 
 pytestmark = pytest.mark.gpu
 
-CASES = ["interp_c1", "interp_c2", "interp_c5", "interp_smoke", "interp_odd", "interp_dense"]
+CASES = ["interp_c1", "interp_c2", "interp_c5", "interp_smoke", "interp_odd", "interp_dense", "interp_kernels"]
 
 
 def _modules(g, dev):

@@ -9,7 +9,7 @@ import pytest
 
 from oracle import dec_oracle, interp_oracle, kmeans_oracle
 
-INTERP_CASES = ["interp_c1", "interp_c2", "interp_c5", "interp_smoke", "interp_odd", "interp_dense"]
+INTERP_CASES = ["interp_c1", "interp_c2", "interp_c5", "interp_smoke", "interp_odd", "interp_dense", "interp_kernels"]
 DEC_CASES = ["dec_k4", "dec_k16", "dec_alpha2", "dec_k10"]
 
 
