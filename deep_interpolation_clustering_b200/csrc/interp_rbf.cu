@@ -37,7 +37,7 @@ struct RbfFwd2Smem {
   uint64_t* bar;
   float* planes;    // [2][C][Tp]: mask | time
   float* sv;        // [C][R] grid values
-  float2* srv;      // [C][Rp] (s_c r_j, v_cj), pad (huge, 0)
+  float2* srv;      // [C][Rp] (-r_j, v_cj), pad (-huge, 0)
   float* ssc;       // [C] s_c = sqrt(beta_c log2 e)
   int* strip;       // [C] grid points per window (even)
   int* nval;        // [C] observation slots to visit: the prefix length, or T for a general mask
@@ -111,12 +111,14 @@ rbf_fwd2_kernel(const float* __restrict__ v, const float* __restrict__ x, const 
 
   const float* smask = s.planes;
   const float* stime = s.planes + C * Tp;
-  // rows of (-s_c r_j, -s_c r_j+1, v_cj, v_cj+1) per pair of grid points: two aligned register pairs per 128-bit
-  // load for the packed float32x2 loop below; a pad point sits at -(3e18 s) with value 0 => weight exactly 0
+  // rows of (-r_j, -r_j+1, v_cj, v_cj+1) per pair of grid points: two aligned register pairs per 128-bit
+  // load for the packed float32x2 loop below; a pad point sits at -1e12 with value 0 => weight exactly 0.
+  // The coordinates stay UNSCALED: d - r is formed first (its rounding error is relative to the small
+  // difference) and then scaled by s_c.  Pre-scaled coordinates s d - s r carry the rounding of numbers up to
+  // s H, which a narrow kernel (beta = 8: s H = 81) turns into 1e-5 relative errors of the basis values.
   for (int i = tid; i < C * (Rp / 2); i += blockDim.x) {
     const int c = i / (Rp / 2), j = 2 * (i - c * (Rp / 2));
-    const float sc = s.ssc[c];
-    const float ra = -__ldg(ref_t + j) * sc, rb2 = j + 1 < R ? -__ldg(ref_t + j + 1) * sc : -3.0e18f * sc;
+    const float ra = -__ldg(ref_t + j), rb2 = j + 1 < R ? -__ldg(ref_t + j + 1) : -1.0e12f;
     reinterpret_cast<float4*>(s.srv)[i] = make_float4(ra, rb2, s.sv[c * R + j], j + 1 < R ? s.sv[c * R + j + 1] : 0.f);
   }
   for (int c = warp; c < C; c += kRbfFwd2Warps) {              // prefix masks: visit [0, n) and zero the tail
@@ -156,7 +158,7 @@ rbf_fwd2_kernel(const float* __restrict__ v, const float* __restrict__ x, const 
     const int tc = live ? t : n - 1;                           // idle lanes shadow the last observation
     const float m = smask[c * Tp + tc];
     const float d = stime[c * Tp + tc];
-    const float ds = d * s.ssc[c];
+    const float sc = s.ssc[c];
     // every lane walks the same number of grid points from its own even offset
     int trip = min(Rp, s.strip[c]);
     const bool wide = irregular || !(d >= r0 - 1.0f && d <= rl + 1.0f);
@@ -164,12 +166,12 @@ rbf_fwd2_kernel(const float* __restrict__ v, const float* __restrict__ x, const 
     const int jlo = trip == Rp ? 0
                                : min(max(0, (__float2int_rd((d - r0) * inv_h) - (trip >> 1) + 1) & ~1), Rp - trip);
     f2_t N2 = pack2(0.f, 0.f), S2 = N2;
-    const f2_t ds2 = pack2(ds, ds);
+    const f2_t d2 = pack2(d, d), sc2 = pack2(sc, sc);
     const ulonglong2* rw = reinterpret_cast<const ulonglong2*>(s.srv) + c * (Rp / 2) + (jlo >> 1);
 #pragma unroll 4
     for (int j = 0; j < (trip >> 1); ++j) {
-      const ulonglong2 p = rw[j];                                  // (-s r0, -s r1) | (v0, v1)
-      const f2_t dl = add2(ds2, p.x);
+      const ulonglong2 p = rw[j];                                  // (-r0, -r1) | (v0, v1)
+      const f2_t dl = mul2(add2(d2, p.x), sc2);                    // s (d - r)
       const f2_t n2 = mul2(dl, dl);
       float n0, n1;
       unpack2(n2, n0, n1);
@@ -229,7 +231,7 @@ rbf_bwd_kernel(const float* __restrict__ v, const float* __restrict__ x,
   const float* nb = inv_norm + b * (int64_t)C * T;
   const float* gb = grad_rec + b * (int64_t)C * T;
   float* sa = s.rows;                 // mask first, then a'
-  float* sd = s.rows + C * Tp;        // times, scaled by s_c = sqrt(beta_c log2 e) once the row is canonical
+  float* sd = s.rows + C * Tp;        // times (unscaled: the loop scales the difference d - r, see rbf_fwd2_kernel)
   float* sas = s.rows + 2 * C * Tp;   // a'S
   // the mask and time planes of one encounter are adjacent: ONE bulk copy of 2*C*T floats
   stage_rows(s.rows, mb, 2 * C, T, Tp, s.bar, use_tma != 0);
@@ -252,11 +254,10 @@ rbf_bwd_kernel(const float* __restrict__ v, const float* __restrict__ x,
       warp_sort3(rd, ra, ras, n, lane);
     }
     warp_pad4_far(rd, ra, ras, n, lane);
-    {   // pre-scale the (sorted) times: the exponent becomes -(s d - s r)^2, one FMUL per pair
-      const float sc = sqrtf(softplus_ref(__ldg(kernel + c)) * kLog2e);
-      const int n4 = (n + 3) & ~3;
-      for (int t = lane; t < n4; t += 32) rd[t] *= sc;        // pad entries stay huge and finite
-    }
+    // pad entries at 1e12 h instead of kPadTime: (s 1e12)^2 stays finite for any kernel the float32 softplus can
+    // produce, so the moment term e * n is 0 * finite, never 0 * inf
+    if (lane < ((n + 3) & ~3) - n) rd[n + lane] = 1.0e12f;
+    __syncwarp();
     if (lane == 0) s.n_valid[c] = n;
   }
   __syncthreads();
@@ -294,15 +295,15 @@ rbf_bwd_kernel(const float* __restrict__ v, const float* __restrict__ x,
     for (int k = 0; k < RPT; ++k) {
       ridx[k] = (chunk * 32 + lane) * RPT + k;
       const int rc = min(ridx[k], R - 1);
-      rr[k] = __ldg(ref_t + rc) * sc;                         // scaled like the staged times
+      rr[k] = __ldg(ref_t + rc);
       vv[k] = __ldg(vb + c * R + rc);
       dv[k] = acc[k] = 0.f;
     }
-    // one window [r_first - w, r_last + w] in scaled units (w = sqrt(cut)), two searches, uniform trip
+    // one window [r_first - w, r_last + w] (w = sqrt(cut / b2) hours), two searches, uniform trip
     const int n4 = (n + 3) & ~3;
     int wbase = 0, wtrip = n4;
     if (n > 0) {
-      const float wcut = sqrtf(kRbfCut);
+      const float wcut = sqrtf(kRbfCut / b2);
       const float tv[2] = {rr[0] - wcut, rr[RPT - 1] + wcut};
       const bool up[2] = {false, true};
       int pos[2];
@@ -312,6 +313,7 @@ rbf_bwd_kernel(const float* __restrict__ v, const float* __restrict__ x,
     }
     // packed float32x2 over pairs of consecutive observations (two aligned register pairs per 128-bit load)
     f2_t nrr2[RPT], vv2[RPT], dv2[RPT], acc2[RPT];
+    const f2_t sc2 = pack2(sc, sc);
 #pragma unroll
     for (int k = 0; k < RPT; ++k) {
       nrr2[k] = pack2(-rr[k], -rr[k]);
@@ -329,7 +331,7 @@ rbf_bwd_kernel(const float* __restrict__ v, const float* __restrict__ x,
       for (int j = 0; j < 2; ++j) {
 #pragma unroll
         for (int k = 0; k < RPT; ++k) {
-          const f2_t dl = add2(dd[j], nrr2[k]);
+          const f2_t dl = mul2(add2(dd[j], nrr2[k]), sc2);       // s (d - r): the difference first, then the scale
           const f2_t n2 = mul2(dl, dl);                          // beta log2(e) (d - r)^2
           float n0, n1;
           unpack2(n2, n0, n1);

@@ -27,6 +27,27 @@ def _labels_equal_mod_ties(name, got, want, X, centers, tie=1e-5, max_frac=1.0):
     assert np.all(margin < tie), f"{name}: {bad.size} label mismatches, worst margin {margin.max():.3e}"
 
 
+def _centres_close_mod_flips(name, km, ref, X, rtol=1e-5):
+    """Centres after several Lloyd iterations, with the near-tie rows accounted for: a row that sklearn's float32 GEMM
+    and the kernel assign to different clusters (a documented near-tie, checked by _labels_equal_mod_ties) moves the two
+    centres involved by (x - c) / n_k.  The per-cluster bound is therefore
+        1e-5 (1 + |c|)  +  2 * flips_k * max_i |x_i - c_k|_inf / n_k
+    with flips_k counted on the final labels (the E-steps inside the loop are not observable from outside; the factor 2
+    covers them).  Without flips this is the plain 1e-5 check."""
+    X64 = np.asarray(X, np.float64)
+    got, want = np.asarray(km.cluster_centers_, np.float64), np.asarray(ref.cluster_centers_, np.float64)
+    bad = km.labels_ != ref.labels_
+    worst = 0.0
+    for k in range(want.shape[0]):
+        members = ref.labels_ == k
+        n_k = max(int(members.sum()), 1)
+        flips = int((bad & (members | (km.labels_ == k))).sum())
+        spread = float(np.abs(X64[members] - want[k]).max()) if members.any() else 0.0
+        lim = rtol * (1.0 + np.abs(want[k])) + 2.0 * flips * spread / n_k
+        worst = max(worst, float((np.abs(got[k] - want[k]) / lim).max()))
+    record(name, worst, 0.0, 0.0, 1.0)        # logged as a ratio to the bound (<= 1 passes)
+
+
 @pytest.mark.parametrize("dtag", ["f32", "f64"])
 @pytest.mark.parametrize("k", [2, 4, 7])
 def test_lloyd_matches_sklearn(golden, dtag, k):
@@ -365,17 +386,21 @@ def test_tensor_core_lloyd_pass_inside_a_fit_matches_sklearn(monkeypatch):
             km = km_mod.KMeansB200(n_clusters=K, init=init, n_init=1, max_iter=iters, tol=0.0).fit(X)
             tag = f"tc_fit_D{D}_K{K}_it{iters}"
             # float32-grade dots on both sides (sklearn: a float32 GEMM): rows whose float64 margin is below a few 1e-5
-            # are decided by rounding (measured worst: 1.1e-5, one row of 30,011)
-            _labels_equal_mod_ties(tag, km.labels_, ref.labels_, X, ref.cluster_centers_, tie=5e-5, max_frac=1e-3)
+            # are decided by rounding (measured worst: 1.1e-5, one row of 30,011).  After the first iteration a flipped
+            # row has moved two centres by |x - c| / n_k ~ 3e-3 (n_k ~ 3,000 here), which shifts every squared distance
+            # to them by ~2 |x - c| 3e-3: the near-tie band of the LATER E-steps is ~1e-3 of the distance.
+            _labels_equal_mod_ties(tag, km.labels_, ref.labels_, X, ref.cluster_centers_,
+                                   tie=5e-5 if iters == 1 else 2e-3, max_frac=1e-3)
             assert km.n_iter_ == ref.n_iter_
-            record(tag + "_centers", km.cluster_centers_, ref.cluster_centers_, 1e-5, 1e-5)
+            _centres_close_mod_flips(tag + "_centers", km, ref, X)
             record(tag + "_inertia", km.inertia_, ref.inertia_, 1e-5, 0)
 
 
 def test_config4_size_lloyd_matches_sklearn_with_fixed_init():
     """BASELINE config 4 size (1M x 64, K = 10): three Lloyd iterations from the same initial centres against
     scikit-learn run here on the host (sklearn/cluster/_k_means_lloyd.pyx:196-213 decides ties): labels equal except
-    documented near-ties, centres and inertia to 1e-5.
+    documented near-ties, inertia to 1e-5, centres to 1e-5 plus the displacement the near-tie rows themselves cause
+    (_centres_close_mod_flips: 189 rows assigned differently move a centre of ~10^5 rows by up to ~4e-4).
 
     Near-tie bound at this size: sklearn decides a float32 row by ||c||^2 - 2 x.c evaluated in float32 (a 64-term dot
     product of magnitude ~10^3, i.e. ~1e-4 absolute noise on squared distances of ~60-100), so rows whose float64
@@ -393,5 +418,5 @@ def test_config4_size_lloyd_matches_sklearn_with_fixed_init():
     km = KMeansB200(n_clusters=10, init=init, n_init=1, max_iter=3, tol=0.0).fit(X)
     _labels_equal_mod_ties("c4_1M_labels", km.labels_, ref.labels_, X, ref.cluster_centers_, tie=2e-4, max_frac=1e-3)
     assert km.n_iter_ == ref.n_iter_
-    record("c4_1M_centers", km.cluster_centers_, ref.cluster_centers_, 1e-5, 1e-5)
+    _centres_close_mod_flips("c4_1M_centers", km, ref, X)
     record("c4_1M_inertia", km.inertia_, ref.inertia_, 1e-5, 0)
