@@ -36,19 +36,21 @@ namespace dic {
 namespace {
 
 constexpr int kMaxWarps = 8;
-constexpr float kCut = 27.0f;      // log2 of the dropped weight ratio (2^-27 = 7.5e-9; Gaussian tail sum ~1e-8)
+constexpr float kCut = 24.0f;      // log2 of the dropped weight ratio: the dropped tail is < 2e-8 of S and < 5e-7 of the moment sums
 
 struct SciSmem {
-  // dynamic shared memory layout: bar | null chunks | rows[3][C][Tp] | n_valid[C] | order[C] | part[]
+  // dynamic shared memory layout: bar | null chunks | rows[3][C][Tp] | n_valid[C] | order[C] | part[] | vpar | lbtab
   uint64_t* bar;
   float* nullc;   // [0..3] = kPadTime (a chunk of observations that weigh exactly 0), [4..7] = 0
   float* rows;
   int* n_valid;   // > 0: binary mask; < 0: weighted (|n| entries); 0: all masked
   int* order;     // vitals sorted by descending observation count
   float* part;
+  float* vpar;    // [C][4] per-vital constants: alpha, a = alpha log2 e, kCut / a, kCut / (10 a)
+  int* lbtab;     // [C][R + 1]: lbtab[c][j] = #{t : d_t < r_j} (j < R), lbtab[c][R] = n  (forward kernel only)
 };
 
-__device__ __forceinline__ SciSmem sci_carve(unsigned char* base, int C, int Tp) {
+__device__ __forceinline__ SciSmem sci_carve(unsigned char* base, int C, int Tp, int R) {
   SciSmem s;
   s.bar = reinterpret_cast<uint64_t*>(base);
   s.nullc = reinterpret_cast<float*>(base + 16);
@@ -56,22 +58,42 @@ __device__ __forceinline__ SciSmem sci_carve(unsigned char* base, int C, int Tp)
   s.n_valid = reinterpret_cast<int*>(s.rows + 3 * C * Tp);
   s.order = s.n_valid + C;
   s.part = reinterpret_cast<float*>(s.order + C);
+  s.vpar = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(s.part + C * ((R + 31) / 32)) + 15) & ~(uintptr_t)15);
+  s.lbtab = reinterpret_cast<int*>(s.vpar + 4 * C);
   return s;
 }
 
 static size_t sci_smem_bytes(int C, int Tp, int R) {
   return 48 + sizeof(float) * (3 * (size_t)C * Tp) + 2 * sizeof(int) * C +
-         sizeof(float) * (size_t)C * ((R + 31) / 32);
+         sizeof(float) * (size_t)C * ((R + 31) / 32) + 16 + sizeof(float) * 4 * C + sizeof(int) * (size_t)C * (R + 1);
 }
 
 // Stage + canonicalise one encounter.  After return (CTA-synchronised):
-//   rows[0][c] = m*x (forward) or x (backward), rows[1][c] = m, rows[2][c] = d, compacted, sorted
-//   by time and padded to a multiple of 4 with null entries; n_valid[c]; order[].
-__device__ __forceinline__ void sci_stage(const SciSmem& s, const float* xb, int C, int T, int Tp,
-                                          bool use_tma, bool fold_mask) {
+//   rows[0][c] = m*x, rows[1][c] = m, rows[2][c] = d, compacted, sorted by time and padded to a multiple of 4 with
+//   null entries; n_valid[c]; order[]; vpar[c] (per-vital constants, computed ONCE per encounter while the bulk copy
+//   is in flight); lbtab[c][j] = #{t : d_t < r_j} for every grid point (the binary searches of the whole encounter,
+//   done by the warp that canonicalised the row) - the tasks read the nearest observation AND their window bounds
+//   from this table.  Returns true when the grid is uniform (ref_t[j] = r0 + j h within 1 % of h).
+template <int RPT>
+__device__ __forceinline__ bool sci_stage(const SciSmem& s, const float* xb, const float* __restrict__ kernel,
+                                          const float* __restrict__ ref_t, int C, int T, int Tp, int R, bool use_tma) {
   if (threadIdx.x < 8) s.nullc[threadIdx.x] = threadIdx.x < 4 ? kPadTime : 0.f;
-  stage_rows(s.rows, xb, 3 * C, T, Tp, s.bar, use_tma);
+  stage_rows_issue(s.rows, xb, 3 * C, T, Tp, s.bar, use_tma);
+  // ---- overlapped with the copy: per-vital constants, regularity of the grid ----
+  if (threadIdx.x < C) {
+    const float alpha = softplus_ref(__ldg(kernel + threadIdx.x));
+    const float a = alpha * kLog2e;
+    reinterpret_cast<float4*>(s.vpar)[threadIdx.x] = make_float4(alpha, a, kCut / a, kCut / (10.f * a));
+  }
+  const float r0 = __ldg(ref_t), rl = __ldg(ref_t + R - 1);
+  const float h = R > 1 ? (rl - r0) / (float)(R - 1) : 1.0f;
+  int irregular = !(h > 0.f);
+  for (int j = threadIdx.x; j < R; j += blockDim.x)
+    irregular |= fabsf(__ldg(ref_t + j) - (r0 + h * (float)j)) > 0.01f * h;
+  stage_rows_wait(s.bar, use_tma);
+
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int chunks = (R + 32 * RPT - 1) / (32 * RPT);
   for (int c = warp; c < C; c += nwarps) {
     float* sx = s.rows + (0 * C + c) * Tp;
     float* sm = s.rows + (1 * C + c) * Tp;
@@ -79,15 +101,35 @@ __device__ __forceinline__ void sci_stage(const SciSmem& s, const float* xb, int
     int n = warp_canonical_count(sm, sd, Tp, lane);
     int weighted = 0;
     if (n < 0) {   // general rows: drop masked entries, sort by time, detect fractional weights
-      n = warp_compact3(sx, sm, sd, T, lane, fold_mask);
+      n = warp_compact3(sx, sm, sd, T, lane, /*fold_mask=*/true);
       warp_sort3(sd, sx, sm, n, lane);
       for (int t = lane; t < n; t += 32) weighted |= (sm[t] != 1.0f);
       weighted = __any_sync(0xffffffffu, weighted);
     }
     warp_pad4_far(sd, sx, sm, n, lane);
     if (lane == 0) s.n_valid[c] = weighted ? -n : n;
+    int* tab = s.lbtab + c * (R + 1);
+    if (n > 0) {
+      for (int ch = 0; ch < chunks; ++ch) {
+        float rr[RPT];
+        bool upk[RPT];
+        int lb[RPT];
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) {
+          rr[k] = __ldg(ref_t + min((ch * 32 + lane) * RPT + k, R - 1));
+          upk[k] = false;
+        }
+        multi_bound<RPT>(sd, n, rr, upk, lb);
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) {
+          const int j = (ch * 32 + lane) * RPT + k;
+          if (j < R) tab[j] = lb[k];
+        }
+      }
+    }
+    if (lane == 0) tab[R] = n;
   }
-  __syncthreads();
+  irregular = __syncthreads_or(irregular);
   if (threadIdx.x == 0) {   // insertion sort of C indices by descending count (C is ~6)
     for (int c = 0; c < C; ++c) {
       const int key = abs(s.n_valid[c]);
@@ -100,11 +142,24 @@ __device__ __forceinline__ void sci_stage(const SciSmem& s, const float* xb, int
     }
   }
   __syncthreads();
+  return !irregular;
 }
 
 // Task k of `ntasks` (heaviest vital first) in snake order over the warps.
 __device__ __forceinline__ int snake_task(int round, int warp, int nwarps) {
   return round * nwarps + ((round & 1) ? (nwarps - 1 - warp) : warp);
+}
+
+// Window bounds from the per-vital table of lower bounds (uniform grid): the observations within +-w of the lane's
+// grid points [r_first, r_last] lie between the grid points that bracket r_first - w and r_last + w, so four table
+// reads replace four 8-step binary searches; the bracket is at most one grid step (~1 observation) wider per side,
+// which the 4-entry chunk rounding mostly absorbs.
+__device__ __forceinline__ void table_range(const int* __restrict__ tab, int n, int R, float lo, float hi, float r0,
+                                            float inv_h, int& start, int& end) {
+  const float f0 = (lo - r0) * inv_h - 0.02f, f1 = (hi - r0) * inv_h + 0.02f;     // 0.02: the grid's 1 % tolerance
+  start = f0 < 0.f ? 0 : tab[min(__float2int_rd(f0), R)];               // #{d < r_j}, r_j <= lo
+  const int j1 = __float2int_ru(f1) + 1;                                // #{d < r_(j+1)} >= #{d <= hi}
+  end = j1 >= R ? n : tab[max(j1, 0)];
 }
 
 // Forward task.  Per filter it accumulates S = sum e and SY = sum e x (y = SY / S) and, when the backward pass
@@ -121,33 +176,42 @@ __device__ __forceinline__ int snake_task(int round, int warp, int nwarps) {
 // analytically here and is never formed; the dominant observation itself has t = 0.
 template <int RPT, bool WEIGHTED, bool MOM>
 __device__ __forceinline__ void sci_fwd_task(const float* __restrict__ sx, const float* __restrict__ sm,
-                                             const float* __restrict__ sd, int n, float alpha, int chunk,
+                                             const float* __restrict__ sd, int n, const float4 par, int chunk,
                                              int lane, int c, int C, int R, const float* __restrict__ ref_t,
                                              float* __restrict__ ub, float* __restrict__ sb,
-                                             const float* __restrict__ nullc) {
-  const float a = alpha * kLog2e, na = -a;
+                                             const float* __restrict__ nullc, const int* __restrict__ tab,
+                                             bool regular, float r0, float inv_h) {
+  const float alpha = par.x, a = par.y, na = -a;
   int ridx[RPT];
   float rr[RPT], nhi[RPT], nlo[RPT];
   float nmax = 0.f;
-  bool upk[RPT];
-  int lb[RPT];
 #pragma unroll
   for (int k = 0; k < RPT; ++k) {
     ridx[k] = (chunk * 32 + lane) * RPT + k;
-    rr[k] = __ldg(ref_t + min(ridx[k], R - 1));
-    upk[k] = false;
-  }
-  multi_bound<RPT>(sd, n, rr, upk, lb);         // lb = first observation at or after r
-#pragma unroll
-  for (int k = 0; k < RPT; ++k) {
-    const int is = nearest_index(sd, n, lb[k], rr[k]);
+    const int rc = min(ridx[k], R - 1);
+    rr[k] = __ldg(ref_t + rc);
+    const int is = nearest_index(sd, n, tab[rc], rr[k]);               // tab[rc] = first observation at or after r
     const float dst = sd[is] - rr[k];                                // delta* = d* - r
     nhi[k] = dst * dst;
     nlo[k] = -na * fmaf(dst, dst, -nhi[k]);    // exact residual delta*^2 - nhi, pre-multiplied by a
     nmax = fmaxf(nmax, nhi[k]);
   }
-  const Window2 w = make_window2(sd, n, rr[0], rr[RPT - 1], sqrtf(nmax + kCut / a),
-                                 sqrtf(nmax + kCut / (10.f * a)), WEIGHTED);
+  Window2 w;
+  const float wo = sqrtf(nmax + par.z), wi = sqrtf(nmax + par.w);
+  if (WEIGHTED) {
+    w.ob = w.ib = 0;
+    w.ot = w.it = (n + 3) & ~3;
+  } else if (regular) {
+    int so, eo, si, ei;
+    table_range(tab, n, R, rr[0] - wo, rr[RPT - 1] + wo, r0, inv_h, so, eo);
+    table_range(tab, n, R, rr[0] - wi, rr[RPT - 1] + wi, r0, inv_h, si, ei);
+    w.ob = so & ~3;
+    w.ib = si & ~3;
+    w.ot = (warp_max_i(eo - w.ob) + 3) & ~3;
+    w.it = (warp_max_i(ei - w.ib) + 3) & ~3;
+  } else {
+    w = make_window2(sd, n, rr[0], rr[RPT - 1], wo, wi, false);
+  }
   const int n4 = (n + 3) & ~3;
 
   // One filter: HIGH = false walks the outer window with exponent -a t, HIGH = true the inner window with -10 a t
@@ -215,9 +279,10 @@ __device__ __forceinline__ void sci_fwd_task(const float* __restrict__ sx, const
 #pragma unroll
   for (int k = 0; k < RPT; ++k) {
     if (ridx[k] < R) {
-      const float inv = 1.0f / S[k], yc = SC[k] * inv;
+      const float inv = __frcp_rn(S[k]), yc = SC[k] * inv;
       ub[(0 * C + c) * R + ridx[k]] = yc;
-      ub[(1 * C + c) * R + ridx[k]] = logf(S[k]) - alpha * nhi[k];
+      // log S through MUFU.LG2 (absolute error ~2e-7 on log S <= ~6; w itself is -alpha n_min + log S)
+      ub[(1 * C + c) * R + ridx[k]] = fmaf(__log2f(S[k]), kLn2, -alpha * nhi[k]);
       if (MOM) {
         sb[(0 * C + c) * R + ridx[k]] = fmaf(-yc, Q0[k], Q1[k]) * inv;          // U1
         sb[(1 * C + c) * R + ridx[k]] = fmaf(Q0[k], inv, nhi[k]);               // U0 >= 0
@@ -228,7 +293,7 @@ __device__ __forceinline__ void sci_fwd_task(const float* __restrict__ sx, const
 #pragma unroll
   for (int k = 0; k < RPT; ++k) {
     if (ridx[k] < R) {
-      const float inv = 1.0f / S[k], yc = SC[k] * inv;
+      const float inv = __frcp_rn(S[k]), yc = SC[k] * inv;
       ub[(2 * C + c) * R + ridx[k]] = yc;
       if (MOM) sb[(2 * C + c) * R + ridx[k]] = 10.f * fmaf(-yc, Q0[k], Q1[k]) * inv;   // U1'
     }
@@ -242,30 +307,36 @@ sci_fwd_kernel(const float* __restrict__ x, const float* __restrict__ kernel,
                const float* __restrict__ ref_t, float* __restrict__ u, float* __restrict__ stats,
                int C, int T, int Tp, int R, int use_tma, int64_t x_stride) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const SciSmem s = sci_carve(smem_raw, C, Tp);
+  const SciSmem s = sci_carve(smem_raw, C, Tp, R);
   const int64_t b = blockIdx.x;
-  sci_stage(s, x + b * x_stride, C, T, Tp, use_tma != 0, /*fold_mask=*/true);
+  const bool regular = sci_stage<RPT>(s, x + b * x_stride, kernel, ref_t, C, T, Tp, R, use_tma != 0);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int chunks = (R + 32 * RPT - 1) / (32 * RPT);
   const int ntasks = C * chunks;
   float* ub = u + b * (int64_t)(3 * C) * R;
   float* sb = MOM ? stats + b * (int64_t)(3 * C) * R : nullptr;
+  const float r0 = __ldg(ref_t);
+  const float inv_h = R > 1 ? (float)(R - 1) / (__ldg(ref_t + R - 1) - r0) : 1.0f;
 
   for (int round = 0;; ++round) {
     const int task = snake_task(round, warp, nwarps);
     if (round * nwarps >= ntasks) break;
     if (task >= ntasks) continue;
-    const int c = s.order[task / chunks], chunk = task % chunks;
+    const int vi = chunks == 1 ? task : task / chunks, chunk = chunks == 1 ? 0 : task - vi * chunks;
+    const int c = s.order[vi];
     const float* sx = s.rows + (0 * C + c) * Tp;
     const float* sm = s.rows + (1 * C + c) * Tp;
     const float* sd = s.rows + (2 * C + c) * Tp;
     const int nv = s.n_valid[c];
-    const float alpha = softplus_ref(__ldg(kernel + c));
+    const float4 par = reinterpret_cast<const float4*>(s.vpar)[c];
+    const int* tab = s.lbtab + c * (R + 1);
     if (nv > 0) {
-      sci_fwd_task<RPT, false, MOM>(sx, sm, sd, nv, alpha, chunk, lane, c, C, R, ref_t, ub, sb, s.nullc);
+      sci_fwd_task<RPT, false, MOM>(sx, sm, sd, nv, par, chunk, lane, c, C, R, ref_t, ub, sb, s.nullc, tab, regular,
+                                    r0, inv_h);
     } else if (nv < 0) {
-      sci_fwd_task<RPT, true, MOM>(sx, sm, sd, -nv, alpha, chunk, lane, c, C, R, ref_t, ub, sb, s.nullc);
+      sci_fwd_task<RPT, true, MOM>(sx, sm, sd, -nv, par, chunk, lane, c, C, R, ref_t, ub, sb, s.nullc, tab, regular,
+                                   r0, inv_h);
     } else {
       // all-masked vital: the reference yields w = -inf, y = y' = NaN (logsumexp of -inf)
 #pragma unroll

@@ -289,4 +289,29 @@ __device__ __forceinline__ void stage_rows(float* smem_rows, const float* gsrc, 
   }
 }
 
+// The same in two halves, so that per-encounter set-up work can run while the bulk copy is in flight:
+// stage_rows_issue (all threads; returns at once on the TMA path) ... independent work ... stage_rows_wait.
+__device__ __forceinline__ void stage_rows_issue(float* smem_rows, const float* gsrc, int nrows, int T, int Tp,
+                                                 uint64_t* bar, bool use_tma) {
+  if (use_tma) {
+    if (threadIdx.x == 0) {
+      mbar_init(bar, 1);
+      fence_proxy_async();
+      const uint32_t bytes = static_cast<uint32_t>(nrows) * T * 4u;
+      mbar_expect_tx(bar, bytes);
+      bulk_g2s(smem_rows, gsrc, bytes, bar);
+    }
+  } else {
+    const int total = nrows * Tp;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+      const int row = i / Tp, t = i - row * Tp;
+      smem_rows[i] = t < T ? __ldg(gsrc + row * T + t) : 0.f;     // pad columns: mask 0
+    }
+  }
+}
+__device__ __forceinline__ void stage_rows_wait(uint64_t* bar, bool use_tma) {
+  __syncthreads();                 // publishes the mbarrier's initialisation / the plain loads
+  if (use_tma) mbar_wait(bar, 0);
+}
+
 }  // namespace dic
