@@ -55,6 +55,9 @@ SIGNATURES = {
     "dic_pairwise_dist_sum_part": (c_int, [_P, _P, _P, c_int64, c_int, c_int, c_int, c_int, _P]),
     "dic_pairwise_workspace_bytes": (c_size_t, [c_int64, c_int]),
     "dic_cluster_rowsums": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, c_int, _P]),
+    "dic_cluster_scatter_workspace_bytes": (c_size_t, [c_int]),
+    "dic_cluster_scatter": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, _P]),
+    "dic_dunn_minmax": (c_int, [_P, _P, _P, c_int64, c_int, c_int, c_int, _P]),
     "dic_colsum_workspace_bytes": (c_size_t, [c_int]),
     "dic_colsum_f32": (c_int, [_P, _P, _P, c_int64, c_int, _P]),
     "dic_probe_mufu": (c_int, [POINTER(c_double), _P]),

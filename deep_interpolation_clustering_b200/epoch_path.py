@@ -24,17 +24,31 @@ from .kmeans import KMeansB200
 class EpochFeatures:
     """Device-side replacement for the ob_pred_lst / merge_ob_pred pair (clustering_trainer.py:409-416,486-493)
     restricted to what the clustering loop consumes: the latent ``hidden`` and, optionally, the soft
-    assignment of each batch.  Preallocates (capacity, D) once; ``append`` is a device copy."""
+    assignment of each batch.  Preallocates (capacity, D) once; ``append`` is a device copy.
+    ``capacity=None``: grows by doubling (a data loader without ``len``)."""
 
     def __init__(self, capacity, dim, device, n_clusters=None):
+        self.growable = capacity is None
+        capacity = 4096 if capacity is None else capacity
         self.hidden = torch.empty((capacity, dim), dtype=torch.float32, device=device)
         self.q = torch.empty((capacity, n_clusters), dtype=torch.float32, device=device) if n_clusters else None
         self.n = 0
 
+    def _grow(self, need):
+        cap = max(2 * self.hidden.shape[0], need)
+        for name in ("hidden", "q"):
+            old = getattr(self, name)
+            if old is not None:
+                new = torch.empty((cap, old.shape[1]), dtype=old.dtype, device=old.device)
+                new[:self.n].copy_(old[:self.n])
+                setattr(self, name, new)
+
     def append(self, hidden, q=None):
         b = hidden.shape[0]
         if self.n + b > self.hidden.shape[0]:
-            raise ValueError(f"EpochFeatures capacity {self.hidden.shape[0]} exceeded")
+            if not self.growable:
+                raise ValueError(f"EpochFeatures capacity {self.hidden.shape[0]} exceeded")
+            self._grow(self.n + b)
         self.hidden[self.n:self.n + b].copy_(hidden.detach(), non_blocking=True)
         if q is not None and self.q is not None:
             self.q[self.n:self.n + b].copy_(q.detach(), non_blocking=True)

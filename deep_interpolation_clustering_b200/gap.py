@@ -327,8 +327,6 @@ class KM(object):
     def _gap_row_sharded(self, clustering, data, k_max, n_references, version, draw, group, seed):
         import pandas as pd
         import torch.distributed as dist
-        if self.internal_metrics:
-            raise NotImplementedError("internal metrics are not available for a row-sharded sweep")
         comm = _Comm(group)
         device_draws = isinstance(draw, str) and draw in ("device", "device32")
         ref_dtype = torch.float32 if draw == "device32" else torch.float64
@@ -341,7 +339,7 @@ class KM(object):
         data_min = np_t(float(lohi[0]))                                             # :360 over ALL rows, in the
         data_rng = np_t(float(-lohi[1])) - data_min                                 # data's own arithmetic
         k_rng = range(2, k_max + 1)
-        vals = pd.DataFrame(index=k_rng, columns=["k", "gap", "ref", "act", "ref_s"])
+        vals = pd.DataFrame(index=k_rng, columns=["k", "gap", "ref", "act", "ref_s"] + self.internal_metrics_names)
         on_dev = _accepts_tensor(clustering)
         self._comm = comm
         try:
@@ -366,7 +364,9 @@ class KM(object):
                 ref_s = np.sqrt(1 + 1 / n_references) * np.std(np.log(local_inertia))
                 a = clustering.fit_predict(data_dev if on_dev else data)
                 act = np.log(inertia(a, data_dev))
-                vals.loc[k] = [k, ref - act, ref, act, ref_s]
+                # :401-405 on the sharded rows: CH / DB all-reduce K-sized statistics, the O(N^2) scores gather the rows
+                metric_values = [m(data_dev, a, group=group) for m in self.internal_metrics]
+                vals.loc[k] = [k, ref - act, ref, act, ref_s] + metric_values
         finally:
             self._comm = None
         return vals

@@ -277,6 +277,26 @@ int dic_cluster_rowsums(const float* X, const int32_t* perm, const int32_t* tile
                         double* rowsum, void* workspace, int64_t n_pad, int D, int K,
                         dic_stream_t stream);
 
+/* Per-cluster dispersion for Calinski-Harabasz / Davies-Bouldin (internal_eval.py:125-147 -> sklearn.metrics
+ * calinski_harabasz_score / davies_bouldin_score, called inside the gap loop at p2_clustering_optK.py:401-405):
+ *   out (K,2) float64:  out[k][0] = sum_{label(i)=k} ||x_i - c_k||,  out[k][1] = sum_{label(i)=k} ||x_i - c_k||^2
+ * in one pass over X (N,D) with labels (N) int32 in [0,K) and centers (K,D) of the data's dtype (the per-cluster
+ * means: dic_kmeans_assign with DIC_KM_KEEP_LABELS yields their sums / counts).  Deterministic.  K <= 64.
+ * workspace: dic_cluster_scatter_workspace_bytes(K). */
+size_t dic_cluster_scatter_workspace_bytes(int K);
+int dic_cluster_scatter(const void* X, const int32_t* labels, const void* centers, double* out,
+                        void* workspace, int64_t N, int D, int K, int dtype, dic_stream_t stream);
+
+/* The O(N^2) part of the Dunn index (internal_eval.py:15-109, "nearest" inter-cluster distances over the
+ * "farthest" diameter):
+ *   out[a*K + b] (a < b) = min over x_i in cluster a, x_j in cluster b of ||x_i - x_j||   (+inf: no such pair;
+ *                          entries with a >= b stay +inf)      - the reference's cluster_distances matrix (:37-53)
+ *   out[K*K]             = max over pairs with equal labels of ||x_i - x_j||               (0 if none; :77-81)
+ * from 64 x 64 distance tiles, upper triangle only; the n x n matrix the reference builds (euclidean_distances,
+ * internal_eval.py:103) is never materialised.  labels (N) int32 in [0, K), K <= 32; dtype as above. */
+int dic_dunn_minmax(const void* X, const int32_t* labels, double* out, int64_t N, int D, int K, int dtype,
+                    dic_stream_t stream);
+
 /* ---- utilities -------------------------------------------------------------------- */
 /* Deterministic column sums of a (rows, cols) float32 matrix into float64. */
 size_t dic_colsum_workspace_bytes(int cols);

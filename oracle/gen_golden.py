@@ -263,18 +263,46 @@ def gen_kmeans(ref, outdir):
     np.savez_compressed(os.path.join(outdir, "gap.npz"), **res)
 
 
+def gen_internal_eval(ref, outdir):
+    """The four cluster-validity metrics of internal_eval.py:15-147 through the reference's own classes (Dunn's
+    pure-Python double loop limits the size): blobs, a k-means labelling, and a second data set with duplicated rows
+    (zero inter-cluster distances, which internal_eval.py:104 skips through ``nonzero()``)."""
+    from sklearn.cluster import KMeans
+    from deep_interpolation_clustering_b200 import synth
+    out = {}
+    X = synth.make_blobs(700, 16, 4, seed=21)
+    lab = KMeans(n_clusters=5, init=X[:5].copy(), n_init=1).fit_predict(X)
+    Xd = synth.make_blobs(240, 8, 3, seed=22)
+    labd = KMeans(n_clusters=3, init=Xd[:3].copy(), n_init=1).fit_predict(Xd)
+    src = np.nonzero(labd[:200] == 0)[0][:12]           # 12 rows of cluster 0 ...
+    Xd[200:212] = Xd[src]                               # ... duplicated exactly ...
+    labd[200:206] = 1                                   # ... 6 copies filed under cluster 1 (the pair (0,1) then has a
+    labd[206:212] = 0                                   # zero nearest distance and drops out), 6 under cluster 0
+    for tag, (A, a) in (("blobs", (X, lab)), ("dups", (Xd, labd))):
+        out[tag + "_X"], out[tag + "_labels"] = A, a.astype(np.int64)
+        out[tag + "_dunn"] = np.float64(ref.internal_eval.DunnIndex()(A, a))
+        out[tag + "_silhouette"] = np.float64(ref.internal_eval.Sihouette()(A, a))
+        out[tag + "_ch"] = np.float64(ref.internal_eval.CHIndex()(A, a))
+        out[tag + "_db"] = np.float64(ref.internal_eval.DBIndex()(A, a))
+    np.savez_compressed(os.path.join(outdir, "internal_eval.npz"), **out)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(REPO, "tests", "golden"))
     ap.add_argument("--only", nargs="*", help="regenerate only these interpolation fixtures (leaves the others untouched)")
+    ap.add_argument("--internal-eval-only", action="store_true", help="regenerate only internal_eval.npz")
     args = ap.parse_args()
     os.makedirs(args.out, exist_ok=True)
     ref = import_reference()
-    gen_interp(ref, args.out, args.only)
-    if not args.only:
+    if not args.internal_eval_only:
+        gen_interp(ref, args.out, args.only)
+    if not args.only and not args.internal_eval_only:
         gen_rbf_module(ref, args.out)
         gen_dec(ref, args.out)
         gen_kmeans(ref, args.out)
+    if not args.only:
+        gen_internal_eval(ref, args.out)
     import torch, sklearn, scipy
     manifest = dict(reference=REFERENCE, torch=torch.__version__, numpy=np.__version__,
                     sklearn=sklearn.__version__, scipy=scipy.__version__,

@@ -219,3 +219,57 @@ def gap_statistic(fit_predict, data, k_max=5, n_references=5, version=1, draw=No
         rows.append((k, ref - act, ref, act, ref_s))
     cols = list(zip(*rows))
     return {n: np.array(c) for n, c in zip(("k", "gap", "ref", "act", "ref_s"), cols)}
+
+
+# ---- cluster-validity metrics of the gap loop (internal_eval.py) -------------------------------------------------
+def dunn_index(x, labels):
+    """DunnIndex.__call__, internal_eval.py:83-109: nearest-point distance of every pair of clusters (:37-53; the
+    K x K matrix starts at +inf off the diagonal), zero entries dropped through ``nonzero()`` (:106), over the largest
+    "farthest" diameter (:77-81).  Vectorised restatement of the reference's pure-Python double loops; distances are
+    sklearn's euclidean_distances (float32 input evaluated through the float64 Gram form, :103)."""
+    x = np.asarray(x)
+    labels = np.asarray(labels)
+    d = pairwise_euclidean(x)
+    ks = np.unique(labels)
+    ic = []
+    diam = 0.0
+    for i, a in enumerate(ks):
+        ma = labels == a
+        if ma.sum() > 1:
+            diam = max(diam, float(d[np.ix_(ma, ma)].max()))
+        for b in ks[i + 1:]:
+            ic.append(float(d[np.ix_(ma, labels == b)].min()))
+    ic = np.array([v for v in ic if v != 0.0])
+    if ic.size == 0:
+        raise ValueError("min() iterable argument is empty")
+    return float(ic.min() / diam)
+
+
+def calinski_harabasz(x, labels):
+    """CHIndex, internal_eval.py:125-135 -> sklearn.metrics.calinski_harabasz_score (_unsupervised.py): float64."""
+    x = np.asarray(x, np.float64)
+    labels = np.asarray(labels)
+    ks = np.unique(labels)
+    mean = x.mean(0)
+    extra = intra = 0.0
+    for k in ks:
+        xk = x[labels == k]
+        ck = xk.mean(0)
+        extra += len(xk) * ((ck - mean) ** 2).sum()
+        intra += ((xk - ck) ** 2).sum()
+    n, K = x.shape[0], len(ks)
+    return 1.0 if intra == 0.0 else float(extra * (n - K) / (intra * (K - 1.0)))
+
+
+def davies_bouldin(x, labels):
+    """DBIndex, internal_eval.py:138-147 -> sklearn.metrics.davies_bouldin_score."""
+    x = np.asarray(x, np.float64)
+    labels = np.asarray(labels)
+    ks = np.unique(labels)
+    cen = np.stack([x[labels == k].mean(0) for k in ks])
+    s = np.array([np.sqrt(((x[labels == k] - cen[i]) ** 2).sum(1)).mean() for i, k in enumerate(ks)])
+    cd = np.sqrt(((cen[:, None] - cen[None]) ** 2).sum(2))
+    if np.allclose(s, 0) or np.allclose(cd, 0):
+        return 0.0
+    cd[cd == 0] = np.inf
+    return float(np.max((s[:, None] + s[None, :]) / cd, axis=1).mean())

@@ -174,3 +174,83 @@ def test_dropin_makes_reference_models_use_b200_operators():
                 sys.modules.pop(k, None)
             else:
                 sys.modules[k] = v
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="reference checkout not present")
+def test_patch_trainer_routes_the_real_trainer_class_through_epoch_path():
+    """dropin.patch_trainer on the reference's own clustering_trainer.TrainerCluster (unchanged upstream file):
+    generate_pred_cluster (clustering_trainer.py:473-484) and merge_ob_pred (:486-493) of the patched class return what
+    the reference's methods return on the same batches, with the epoch's latents accumulated by the forward hook."""
+    from deep_interpolation_clustering_b200 import dropin
+    from deep_interpolation_clustering_b200.kmeans import KMeansB200
+
+    def stub(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        return m
+
+    names = ("tensorflow", "warmup_scheduler", "tensorboardX", "utils", "clustering_trainer", "clustering_interp",
+             "interpolation_layer", "rbf", "dec", "info", "dataloader")
+    saved = {k: sys.modules.get(k) for k in names}
+    sys.modules.setdefault("tensorflow", stub("tensorflow", random=types.SimpleNamespace(set_seed=lambda s: None)))
+    sys.modules.setdefault("warmup_scheduler", stub("warmup_scheduler", GradualWarmupScheduler=object))
+    sys.modules.setdefault("tensorboardX", stub("tensorboardX", SummaryWriter=object))
+    sys.path.insert(0, REFERENCE)
+    cwd = os.getcwd()
+    os.chdir("/tmp")
+    try:
+        for k in ("clustering_trainer", "clustering_interp", "interpolation_layer", "rbf", "dec"):
+            sys.modules.pop(k, None)
+        import clustering_trainer as ct
+        ref_generate = ct.TrainerCluster.generate_pred_cluster
+        ref_merge = ct.TrainerCluster.merge_ob_pred
+
+        class Model(torch.nn.Module):                       # (hidden, rec_ob, aux_pred_dict) like clustering_interp.Net
+            def forward(self, x):
+                q = torch.softmax(x[:, :4] * 3.0, dim=1)
+                return x * 2.0, x, {"cluster_pred": q, "cluster_label": q.detach()}
+
+        rng = np.random.RandomState(0)
+        batches = [torch.from_numpy(rng.normal(size=(n, 8)).astype(np.float32)) for n in (5, 7, 3)]
+
+        def fake_eval(self, scope, dl, denoise=False):      # the data path of eval_one_epoch (:285-422), nothing else
+            lst = []
+            for b in dl:
+                hidden, rec, aux = self.model(b)
+                d = {"encounter_id": [f"e{i}" for i in range(b.shape[0])], "ob": b.numpy(),
+                     "hidden": hidden.detach().cpu().numpy(), "rec_ob": rec.detach().cpu().numpy()}
+                d.update({k: v.detach().cpu().numpy() for k, v in aux.items()})
+                lst.append(d)
+            return {"scope": scope}, lst
+
+        ct.TrainerCluster.eval_one_epoch = fake_eval
+        ref_tr = object.__new__(ct.TrainerCluster)
+        ref_tr.model = Model()
+        prev = np.array([0, 1, 2, 3, 0, 1, 2, 3, 0, 1, 2, 3, 0, 1, 2])
+        want_first = ref_generate(ref_tr, "valid", batches, None)
+        want = ref_generate(ref_tr, "valid", batches, prev)
+        want_merged = ref_merge(ref_tr, fake_eval(ref_tr, "valid", batches)[1])
+
+        cls = dropin.patch_trainer(ct)
+        assert ct.KMeans is KMeansB200 and cls is ct.TrainerCluster
+        tr = object.__new__(cls)
+        tr.model = Model()
+        got_first = tr.generate_pred_cluster("valid", batches, None)
+        got = tr.generate_pred_cluster("valid", batches, prev)
+        assert got_first[0] == want_first[0] == 1.0
+        assert got[0] == want[0] and np.array_equal(got[1], want[1]) and got[2] == want[2]
+        feats = tr.dic_epoch_features
+        assert feats.n == 15 and torch.equal(feats.features(), torch.cat(batches) * 2.0)
+        merged = tr.merge_ob_pred(tr.eval_one_epoch("valid", batches)[1])
+        assert sorted(merged) == sorted(want_merged)
+        for k, v in want_merged.items():
+            assert np.array_equal(merged[k], v), k
+            assert merged[k].dtype == v.dtype or v.dtype.kind in "US", k
+    finally:
+        os.chdir(cwd)
+        sys.path.remove(REFERENCE)
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v

@@ -201,3 +201,16 @@ def test_ref_port_dec(golden):
     _close(loss.numpy(), g["kl"], 1e-5, 1e-8, "kl")
     _close(z.grad.numpy(), g["dz_kl"], 1e-4, 1e-8, "dz")
     _close(mu.grad.numpy(), g["dmu_kl"], 1e-4, 1e-7, "dmu")
+
+
+@pytest.mark.parametrize("tag", ["blobs", "dups"])
+def test_internal_metrics_oracle_matches_reference(golden, tag):
+    """Dunn / Calinski-Harabasz / Davies-Bouldin restatements against the values the reference's own classes gave
+    (internal_eval.py:15-147; fixture internal_eval.npz from oracle/gen_golden.py, incl. the duplicated-row case
+    where a touching pair of clusters drops out of the Dunn minimum)."""
+    g = golden("internal_eval")
+    X, lab = g[tag + "_X"], g[tag + "_labels"]
+    np.testing.assert_allclose(kmeans_oracle.dunn_index(X, lab), float(g[tag + "_dunn"]), rtol=1e-6)
+    # sklearn evaluates float32 input partly in float32 (centroid distances): float32-rounding agreement
+    np.testing.assert_allclose(kmeans_oracle.calinski_harabasz(X, lab), float(g[tag + "_ch"]), rtol=1e-6)
+    np.testing.assert_allclose(kmeans_oracle.davies_bouldin(X, lab), float(g[tag + "_db"]), rtol=1e-6)
