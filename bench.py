@@ -80,6 +80,8 @@ def parse():
                          "on the host, :370), float32 device draws, or numpy host draws uploaded per set")
     ap.add_argument("--c4-cpu-n", type=int, default=1500, help="rows of the CPU-baseline sweep (n x n matrices)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true",
+                    help="skip the short c3 / c4 / c5 runs printed as `other_configs` next to the c2 line")
     ap.add_argument("--no-parity", action="store_true", help="skip the multi-GPU result checks printed as `parity` (N > 1)")
     return ap.parse_args()
 
@@ -88,12 +90,15 @@ def parse():
 # CPU arm (reference algorithm on host cores)
 # ----------------------------------------------------------------------------------------------
 def cpu_arm(sample, steps, warmup):
-    """Times oracle/ref_port (the reference's ATen-level algorithm) on `sample` encounters of the
-    c2 shape + the DEC step on the same number of latents.  Returns encounters/s."""
+    """Times the reference's CPU implementation of the step on `sample` encounters of the workload's shape + the DEC
+    step on the same number of latents.  With the reference's own modules staged under baseline/_ref
+    (oracle/make_ref.py; built by __graft_entry__.build() where /root/reference exists) these ARE the unmodified
+    upstream classes (kind "reference"); otherwise oracle/ref_port (the same ATen-level algorithm restated, kind
+    "port").  Returns (encounters/s, seconds per step, threads, kind)."""
     import numpy as np
     import torch
     from deep_interpolation_clustering_b200 import synth
-    from oracle import ref_port
+    from oracle import make_ref, ref_port
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     x = torch.from_numpy(synth.make_encounters(sample, C, T, HOURS, seed=0))
@@ -103,18 +108,39 @@ def cpu_arm(sample, steps, warmup):
     g = torch.from_numpy(rng.normal(size=(sample, R, 3 * C)).astype(np.float32))
     zn, mun = synth.make_latents(sample, D_LAT, K_CLUST, seed=3)
     z = torch.from_numpy(zn).requires_grad_(True)
-    mu = torch.from_numpy(mun).requires_grad_(True)
-    sci, cci, rbf = ref_port.SingleChannelInterp(R, HOURS, C), ref_port.CrossChannelInterp(C), \
-        ref_port.RBFReadout(R, HOURS, C)
+    ref = make_ref.import_reference()
+    if ref is not None:
+        kind, cpu = "reference", torch.device("cpu")
+        sci = ref.interpolation_layer.SingleChannelInterp(R, HOURS, C, T, cpu)          # interpolation_layer.py:14
+        cci = ref.interpolation_layer.CrossChannelInterp(C, T, cpu)                     # :90
+        rbf = ref.rbf.RBF(HOURS, R, C, C, 0.0, ref.rbf.basis_func_dict()["gaussian"], cpu)   # rbf.py:38
+        rbf.compress_fc = torch.nn.Identity()      # the metric's step has no encoder: v is the read-out's input
+        ca = ref.dec.ClusterAssignment(K_CLUST, D_LAT, 1.0, torch.from_numpy(mun))      # dec.py:14
+        mu = ca.cluster_centers
+
+        def step():
+            for t in (sci.kernel, cci.kernel, rbf.kernel, v, z, mu):
+                t.grad = None
+            out = cci(sci(x))
+            rec = rbf(v, x)
+            (((out * g).sum() / x.shape[0]) + ref_port.masked_mse(x, rec, C)).backward()
+            q = ca(z)
+            pt = ref.dec.target_distribution(q).detach()
+            torch.nn.functional.kl_div(q.log(), pt, reduction="batchmean").backward()   # clustering_interp.py:205-207
+    else:
+        kind = "port"
+        mu = torch.from_numpy(mun).requires_grad_(True)
+        sci, cci, rbf = ref_port.SingleChannelInterp(R, HOURS, C), ref_port.CrossChannelInterp(C), \
+            ref_port.RBFReadout(R, HOURS, C)
+
+        def step():
+            for t in (sci.kernel, cci.kernel, rbf.kernel, v, z, mu):
+                t.grad = None
+            ref_port.interp_step(sci, cci, rbf, x, v, g)
+            ref_port.dec_step(z, mu, 1.0)
     sci.kernel.data = torch.from_numpy(p["sci_kernel"])
     cci.kernel.data = torch.from_numpy(p["cci_kernel"])
     rbf.kernel.data = torch.from_numpy(p["rbf_kernel"])
-
-    def step():
-        for t in (sci.kernel, cci.kernel, rbf.kernel, v, z, mu):
-            t.grad = None
-        ref_port.interp_step(sci, cci, rbf, x, v, g)
-        ref_port.dec_step(z, mu, 1.0)
 
     for _ in range(warmup):
         step()
@@ -122,7 +148,7 @@ def cpu_arm(sample, steps, warmup):
     for _ in range(steps):
         step()
     dt = (time.perf_counter() - t0) / steps
-    return sample / dt, dt, cores
+    return sample / dt, dt, cores, kind
 
 
 # ----------------------------------------------------------------------------------------------
@@ -263,6 +289,114 @@ class HotPath:
         return {k: v * B for k, v in byt.items()}, ex2
 
 
+def make_step(hp, kernels, world):
+    """One pass of the hot path over the shard `hp` (the order of the module docstring), with the path's own
+    exchange steps when the encounters are sharded over `world` ranks."""
+    import torch.distributed as dist
+
+    def step():
+        for name, fn in kernels:
+            if name in ("dec_p", "dec_kl") and world > 1:
+                dist.all_reduce(hp.colsum)               # f_j over the global batch (dec.py:73)
+            fn()
+        if world > 1:
+            dist.all_reduce(hp.grads)                    # parameter gradients of the sharded batch
+            if hp.dec_kl:
+                dist.all_reduce(hp.g_mu)                 # centre gradients (K x D floats)
+    return step
+
+
+def other_configs(args, rank, world, dev):
+    """The other BASELINE.json configurations next to the headline line, each as a SHORT device-timed run at this world
+    size so that every configuration has a driver-visible number (the full-size runs are `--workload c3|c4|c5`):
+      c3  the joint-clustering step (c2 + the fused DEC p / KL / gradient kernel) on 262,144 encounters per GPU;
+      c5  the stress shape (T = 1024, R = 192, K = 16) on one 32,768-encounter shard per GPU (10M encounters are
+          processed shard by shard: generation on the device, nothing larger ever resident);
+      c4  the gap-statistic sweep on the full 1M x 64 matrix, K = 2..10, REDUCED to 2 reference draws and n_init = 2
+          (the sweep as written - 20 draws, n_init = 10 - is `--workload c4`: profiles/r02_c4_*.json)."""
+    global T, R, K_CLUST
+    import torch
+    import torch.distributed as dist
+    saved = (T, R, K_CLUST)
+    out = {}
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed_hot_path(B, dec_kl, steps=3):
+        hp = HotPath(B, dev, seed=1000 * rank + 17, dec_kl=dec_kl)
+        stream = torch.cuda.current_stream(dev)
+        step = make_step(hp, hp.kernels(stream.cuda_stream), world)
+        for _ in range(3):
+            step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            step()
+        e1.record(stream)
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        nv = hp.n_valid / (B * C)
+        del hp, step
+        torch.cuda.empty_cache()
+        return float(t), nv
+
+    try:
+        for tag in ("c3", "c5"):
+            w = WORKLOADS[tag]
+            T, R, K_CLUST = w["T"], w["R"], w["K"]
+            B = 262_144 if tag == "c3" else 32_768
+            ms, nv = timed_hot_path(B, bool(w.get("dec_kl")))
+            out[tag] = {"value": round(world * B / (ms * 1e-3), 1), "unit": "encounters/s", "ms_per_step": round(ms, 3),
+                        "encounters_per_gpu_per_step": B, "n_gpus": world, "scaling": "weak", "steps": 3, "warmup": 3,
+                        "config": {"workload": w["name"], "max_obs": T, "ref_points": R, "clusters": K_CLUST,
+                                   "mean_valid_obs": round(nv, 2)}}
+    finally:
+        T, R, K_CLUST = saved
+    # c4 (reduced draws / restarts, full matrix), task-parallel over the ranks
+    from deep_interpolation_clustering_b200.gap import KM
+    from deep_interpolation_clustering_b200.kmeans import KMeansB200
+    N, D = 1_000_000, 64
+    g = torch.Generator(device=dev).manual_seed(4)
+    centres = 4.0 * torch.randn((5, D), generator=g, device=dev)
+    X = (centres[torch.randint(0, 5, (N,), generator=g, device=dev)] + torch.randn((N, D), generator=g, device=dev)).contiguous()
+    group = dist.group.WORLD if world > 1 else None
+
+    def sweep(k_max, refs, n_init):
+        df = KM(k_max, None, [], n_init, refs).compute_gap_internal_metric(
+            KMeansB200(n_init=n_init, random_state=0), X, k_max=k_max, n_references=refs, version=1, draw="device",
+            group=group, task_parallel=True, seed=0)
+        torch.cuda.synchronize(dev)
+        return df
+
+    for _ in range(2):
+        sweep(3, 1, 1)
+    barrier()
+    t0 = time.perf_counter()
+    df = sweep(10, 2, 2)
+    barrier()
+    wall = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(wall, op=dist.ReduceOp.MAX)
+    out["c4_reduced"] = {"value": round(N / float(wall), 1), "unit": "rows/s", "seconds_per_sweep": round(float(wall), 3),
+                         "n_gpus": world, "scaling": "strong", "steps": 1, "warmup": 2,
+                         "config": {"workload": "c4 REDUCED: gap-statistic k-means sweep K=2..10 on 1M x 64-d latents with 2 "
+                                                "reference draws and n_init=2 (as written: 20 draws, n_init=10 = "
+                                                "`bench.py --workload c4`)",
+                                    "rows": N, "dim": D, "k": "2..10", "n_references": 2, "n_init": 2,
+                                    "kmeans_fits_per_sweep": 9 * 3 * 2, "pairwise_evaluations_per_sweep": 27,
+                                    "parallelism": f"task-parallel x{world}"},
+                         "best_k": int(df["gap"].astype(float).idxmax())}
+    del X
+    torch.cuda.empty_cache()
+    return out
+
+
 def device_arm(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -276,16 +410,7 @@ def device_arm(args, rank, world, local_rank):
     stream = torch.cuda.current_stream(dev)
     st = stream.cuda_stream
     kernels = hp.kernels(st)
-
-    def step():
-        for name, fn in kernels:
-            if name in ("dec_p", "dec_kl") and world > 1:
-                dist.all_reduce(hp.colsum)               # f_j over the global batch (dec.py:73)
-            fn()
-        if world > 1:
-            dist.all_reduce(hp.grads)                    # parameter gradients of the sharded batch
-            if hp.dec_kl:
-                dist.all_reduce(hp.g_mu)                 # centre gradients (K x D floats)
+    step = make_step(hp, kernels, world)
 
     def barrier():
         if world > 1:
@@ -360,6 +485,17 @@ def device_arm(args, rank, world, local_rank):
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         parity["all_ranks_ok"] = bool(ok.item() == 1.0)
 
+    byt, ex2 = hp.algorithmic()
+    n_valid_mean = hp.n_valid / (B * C)
+    others = None
+    if args.workload == "c2" and not args.no_other_configs:
+        del step, kernels, hp
+        torch.cuda.empty_cache()
+        try:
+            others = other_configs(args, rank, world, dev)
+        except Exception as e:       # noqa: BLE001 - the headline line must not be lost to a side run
+            others = {"error": f"{type(e).__name__}: {e}"[:300]}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -376,7 +512,6 @@ def device_arm(args, rank, world, local_rank):
     _lib.check(_lib.lib().dic_probe_mufu(ctypes.byref(mufu), st), "probe_mufu")
     ffma = ctypes.c_double()
     _lib.check(_lib.lib().dic_probe_ffma(ctypes.byref(ffma), st), "probe_ffma")
-    byt, ex2 = hp.algorithmic()
     ktab = {}
     for n, m in kms.items():
         ktab[n] = {"ms": round(m, 4), "share": round(m / sum(kms.values()), 4),
@@ -437,7 +572,7 @@ def device_arm(args, rank, world, local_rank):
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": CFG_NAME, "encounters_per_gpu": B, "vitals": C, "max_obs": T, "ref_points": R,
-                   "hours": HOURS, "latent_dim": D_LAT, "clusters": K_CLUST, "mean_valid_obs": round(hp.n_valid / (B * C), 2),
+                   "hours": HOURS, "latent_dim": D_LAT, "clusters": K_CLUST, "mean_valid_obs": round(n_valid_mean, 2),
                    "parallelism": f"encounter-sharded x{world}",
                    "l2": f"inputs ({B * 4 * C * T * 4 / 1e9:.1f} GB/GPU) " + ("exceed L2" if B * 4 * C * T * 4 > 2.5e8 else
                                                                            "fit L2: flushed by the other kernels' buffers")},
@@ -447,11 +582,15 @@ def device_arm(args, rank, world, local_rank):
     }
     if parity is not None:
         line["parity"] = parity
+    if others is not None:
+        line["other_configs"] = others
     if not args.no_cpu_baseline:
-        v, dt, cores = cpu_arm(args.cpu_sample, 2, 1)
-        line["cpu_baseline"] = {"value": round(v, 1), "unit": "encounters/s", "cores": cores, "kind": "port",
-                                "sample": f"{args.cpu_sample} encounters of the c2 shape + {args.cpu_sample} latents, "
-                                          f"oracle/ref_port.py (torch CPU autograd), {dt:.2f} s/step"}
+        v, dt, cores, kind = cpu_arm(args.cpu_sample, 2, 1)
+        how = "the reference's own modules staged in baseline/_ref (oracle/make_ref.py)" if kind == "reference" \
+            else "oracle/ref_port.py (the reference's algorithm restated; no staged reference on this box)"
+        line["cpu_baseline"] = {"value": round(v, 1), "unit": "encounters/s", "cores": cores, "kind": kind,
+                                "sample": f"{args.cpu_sample} encounters of this workload's shape + {args.cpu_sample} "
+                                          f"latents, torch CPU autograd through {how}, {dt:.2f} s/step"}
     if world > 1:
         dist.destroy_process_group()
     return line
@@ -461,20 +600,28 @@ def device_arm(args, rank, world, local_rank):
 # c4: the K-selection sweep of p2 (gap statistic), task-parallel over the ranks
 # ----------------------------------------------------------------------------------------------
 def c4_cpu_arm(n_rows, dim, k_max, refs, n_init):
-    """The reference's algorithm (oracle/kmeans_oracle.gap_statistic = KM.compute_gap_internal_metric restated, with
-    scikit-learn's KMeans as the estimator exactly like p2_clustering_optK.py:284) on a matrix small enough for its
-    n_c x n_c distance matrices.  Returns (rows/s, seconds, cores)."""
+    """The reference's sweep on a matrix small enough for its n_c x n_c distance matrices: the staged reference's own
+    KM.compute_gap_internal_metric (p2_clustering_optK.py:353-410, kind "reference") over scikit-learn's KMeans exactly
+    like :284, or - without a staged reference - oracle/kmeans_oracle.gap_statistic, the same routine restated (kind
+    "port").  Returns (rows/s, seconds, cores, kind)."""
     import numpy as np
     from sklearn.cluster import KMeans
     from deep_interpolation_clustering_b200 import synth
-    from oracle import kmeans_oracle
+    from oracle import kmeans_oracle, make_ref
     X = synth.make_blobs(n_rows, dim, 5, seed=4)
     np.random.seed(123)
+    ref = make_ref.import_reference(p2=True)
     t0 = time.perf_counter()
-    kmeans_oracle.gap_statistic(lambda k, data: KMeans(n_clusters=k, n_init=n_init).fit_predict(data), X, k_max=k_max,
-                                n_references=refs, version=1)
+    if ref is not None:
+        kind = "reference"
+        km = ref.p2.KM(k_max, "/tmp/dic_bench_p2", [], n_init, refs)
+        km.compute_gap_internal_metric(KMeans(n_init=n_init), X, k_max=k_max, n_references=refs, version=1)
+    else:
+        kind = "port"
+        kmeans_oracle.gap_statistic(lambda k, data: KMeans(n_clusters=k, n_init=n_init).fit_predict(data), X,
+                                    k_max=k_max, n_references=refs, version=1)
     dt = time.perf_counter() - t0
-    return n_rows / dt, dt, os.cpu_count() or 1
+    return n_rows / dt, dt, os.cpu_count() or 1, kind
 
 
 def c4_arm(args, rank, world, local_rank):
@@ -633,12 +780,13 @@ def c4_arm(args, rank, world, local_rank):
         "best_k": int(df["gap"].astype(float).idxmax()),
     }
     if not args.no_cpu_baseline:
-        v, dt, cores = c4_cpu_arm(args.c4_cpu_n, D, args.c4_kmax, args.c4_refs, args.c4_ninit)
-        line["cpu_baseline"] = {"value": round(v, 2), "unit": "rows/s", "cores": cores, "kind": "port",
+        v, dt, cores, kind = c4_cpu_arm(args.c4_cpu_n, D, args.c4_kmax, args.c4_refs, args.c4_ninit)
+        how = "the staged reference's own KM.compute_gap_internal_metric (baseline/_ref)" if kind == "reference" \
+            else "oracle/kmeans_oracle.gap_statistic (the reference's routine restated)"
+        line["cpu_baseline"] = {"value": round(v, 2), "unit": "rows/s", "cores": cores, "kind": kind,
                                 "sample": f"the same sweep (K=2..{args.c4_kmax}, {args.c4_refs} draws, n_init={args.c4_ninit}) on "
-                                          f"{args.c4_cpu_n} rows x {D}: oracle/kmeans_oracle.gap_statistic (the reference's routine "
-                                          f"restated) over scikit-learn KMeans, {dt:.1f} s; the reference's n_c x n_c distance "
-                                          "matrices make N = 1M infeasible on any host (terabytes)"}
+                                          f"{args.c4_cpu_n} rows x {D}: {how} over scikit-learn KMeans, {dt:.1f} s; the "
+                                          "reference's n_c x n_c distance matrices make N = 1M infeasible on any host (terabytes)"}
     if world > 1:
         dist.destroy_process_group()
     return line
@@ -800,13 +948,13 @@ def main():
     if args.impl == "reference" and w.get("sweep"):
         if rank != 0:
             return
-        v, dt, cores = c4_cpu_arm(args.c4_cpu_n, args.c4_dim, args.c4_kmax, args.c4_refs, args.c4_ninit)
+        v, dt, cores, kind = c4_cpu_arm(args.c4_cpu_n, args.c4_dim, args.c4_kmax, args.c4_refs, args.c4_ninit)
         print(json.dumps({"impl": "reference", "metric": "latent rows/s through one gap-statistic sweep (K=2..10, 20 reference "
                           "draws, n_init=10)", "value": round(v, 2), "unit": "rows/s", "n_gpus": args.gpus, "steps": 1, "warmup": 0,
                           "ms_per_step": round(dt * 1e3, 1), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                           "dtype": "f32 data / f64 reference sets", "data": "synthetic",
                           "config": {"workload": CFG_NAME, "rows": args.c4_cpu_n, "dim": args.c4_dim},
-                          "cpu_baseline": {"value": round(v, 2), "unit": "rows/s", "cores": cores, "kind": "port",
+                          "cpu_baseline": {"value": round(v, 2), "unit": "rows/s", "cores": cores, "kind": kind,
                                            "sample": f"{args.c4_cpu_n} rows (the n_c x n_c matrices cap the reference)"},
                           "e2e": {"value": round(v, 2), "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                           "gpu_launches": 0}), flush=True)
@@ -815,18 +963,20 @@ def main():
         if rank != 0:
             return
         steps, warmup = max(1, args.steps), max(1, min(args.warmup, 2))
-        v, dt, cores = cpu_arm(args.cpu_sample, steps, warmup)
+        v, dt, cores, kind = cpu_arm(args.cpu_sample, steps, warmup)
         line = {"impl": "reference", "metric": "encounters/s (interp fwd+bwd + DEC assign)", "value": round(v, 1),
                 "unit": "encounters/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
                 "ms_per_step": round(dt * 1e3, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
                 "config": {"workload": CFG_NAME, "vitals": C, "max_obs": T, "ref_points": R, "hours": HOURS,
                            "latent_dim": D_LAT, "clusters": K_CLUST},
-                "cpu_baseline": {"value": round(v, 1), "unit": "encounters/s", "cores": cores, "kind": "port",
-                                 "sample": f"each step = {args.cpu_sample} encounters of the c2 shape (bounded sample; the "
-                                           "reference's (B,C,T,R) temporaries cap its batch) through oracle/ref_port.py, the "
-                                           "torch-CPU restatement of the reference (the reference itself is Python and does not "
-                                           "travel to the GPU box)"},
+                "cpu_baseline": {"value": round(v, 1), "unit": "encounters/s", "cores": cores, "kind": kind,
+                                 "sample": f"each step = {args.cpu_sample} encounters of this workload's shape (bounded sample; "
+                                           "the reference's (B,C,T,R) temporaries cap its batch) through " +
+                                           ("the reference's own unmodified modules (interpolation_layer.py, rbf.py, dec.py) "
+                                            "staged in baseline/_ref by oracle/make_ref.py" if kind == "reference" else
+                                            "oracle/ref_port.py, the torch-CPU restatement of the reference (no staged "
+                                            "reference on this box)")},
                 "e2e": {"value": round(v, 1), "unit": "encounters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         print(json.dumps(line), flush=True)

@@ -27,7 +27,7 @@ def _labels_equal_mod_ties(name, got, want, X, centers, tie=1e-5, max_frac=1.0):
     assert np.all(margin < tie), f"{name}: {bad.size} label mismatches, worst margin {margin.max():.3e}"
 
 
-def _centres_close_mod_flips(name, km, ref, X, rtol=1e-5):
+def _centres_close_mod_flips(name, km, ref, X, rtol=1e-5, init=None, tie=5e-5):
     """Centres after several Lloyd iterations, with the near-tie rows accounted for: a row that sklearn's float32 GEMM
     and the kernel assign to different clusters (a documented near-tie, checked by _labels_equal_mod_ties) moves the two
     centres involved by (x - c) / n_k.  The per-cluster bound is therefore
@@ -37,6 +37,10 @@ def _centres_close_mod_flips(name, km, ref, X, rtol=1e-5):
     X64 = np.asarray(X, np.float64)
     got, want = np.asarray(km.cluster_centers_, np.float64), np.asarray(ref.cluster_centers_, np.float64)
     bad = km.labels_ != ref.labels_
+    if init is not None:      # one-iteration fits: the rows the E-step on `init` could have decided either way
+        d = ((X64[:, None, :] - np.asarray(init, np.float64)[None]) ** 2).sum(2)
+        d.sort(axis=1)
+        bad = bad | ((d[:, 1] - d[:, 0]) < tie * np.maximum(d[:, 0], 1e-30))
     worst = 0.0
     for k in range(want.shape[0]):
         members = ref.labels_ == k
@@ -390,10 +394,13 @@ def test_tensor_core_lloyd_pass_inside_a_fit_matches_sklearn(monkeypatch):
             km = km_mod.KMeansB200(n_clusters=K, init=cur, n_init=1, max_iter=1, tol=0.0).fit(X)
             tag = f"tc_fit_D{D}_K{K}_it{it}"
             # float32-grade dots on both sides (sklearn: a float32 GEMM): rows whose float64 margin is below a few 1e-5
-            # are decided by rounding (measured worst: 1.1e-5, one row of 30,011)
-            _labels_equal_mod_ties(tag, km.labels_, ref.labels_, X, ref.cluster_centers_, tie=5e-5, max_frac=1e-3)
+            # are decided by rounding.  labels_ of a one-iteration fit are the E-step on the NEW centres, and those
+            # already carry the near-tie rows of the iteration's own E-step (one flipped row moves two centres by
+            # |x - c| / n_k ~ 3e-3 here), so the band for labels_ is ~1e-3 of the distance; the kernel's own E-step
+            # parity at fixed centres (5e-5 band) is test_every_lloyd_kernel_through_the_abi_selector.
+            _labels_equal_mod_ties(tag, km.labels_, ref.labels_, X, ref.cluster_centers_, tie=2e-3, max_frac=1e-3)
             assert km.n_iter_ == ref.n_iter_
-            _centres_close_mod_flips(tag + "_centers", km, ref, X)
+            _centres_close_mod_flips(tag + "_centers", km, ref, X, init=cur)
             record(tag + "_inertia", km.inertia_, ref.inertia_, 1e-5, 0)
             cur = ref.cluster_centers_.copy()
 
