@@ -22,7 +22,7 @@ INCLUDE = os.path.join(REPO, "include")
 OUT = os.path.join(HERE, "libdic_b200.so")
 BUILD = os.path.join(CSRC, "build")
 
-SOURCES = ["api.cu", "upload.cu", "interp_sci.cu", "interp_cci.cu", "interp_rbf.cu", "dec.cu", "kmeans.cu", "kmeans_tc.cu", "pairwise_tc.cu", "cluster_eval.cu"]
+SOURCES = ["api.cu", "upload.cu", "interp_sci.cu", "interp_cci.cu", "interp_rbf.cu", "dec.cu", "kmeans.cu", "kmeans_tc.cu", "pairwise_tc.cu", "cluster_eval.cu", "lstm.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",

@@ -119,3 +119,15 @@ def patch_trainer(module, class_name="TrainerCluster"):
     cls._dic_patched = True
     cls._dic_orig = {"eval_one_epoch": orig_eval}
     return cls
+
+
+def patch_lstm(module):
+    """Rebind ``EncoderRNN`` / ``DecoderRNN`` of an imported ``pretrain_interp`` / ``clustering_interp`` module
+    (pretrain_interp.py:14-41) to the B200 mirrors (lstm.py): ``Net.__init__`` looks the names up in its module at
+    call time, so Nets built afterwards run their BiLSTMs on the persistent tcgen05 kernel; the ``encoder.lstm.*`` /
+    ``decoder.lstm.*`` state-dict keys are unchanged."""
+    from . import lstm
+    for name in ("EncoderRNN", "DecoderRNN"):
+        if hasattr(module, name):
+            setattr(module, name, getattr(lstm, name))
+    return module

@@ -297,6 +297,31 @@ int dic_cluster_scatter(const void* X, const int32_t* labels, const void* center
 int dic_dunn_minmax(const void* X, const int32_t* labels, double* out, int64_t N, int D, int K, int dtype,
                     dic_stream_t stream);
 
+/* ---- bidirectional LSTM either side of the interpolation network ------------------------------
+ * Replaces the recurrence of nn.LSTM(input, 128, num_layers=1, bidirectional=True) in EncoderRNN / DecoderRNN
+ * (pretrain_interp.py:14-41, clustering_interp.py likewise); float32 semantics of torch.nn.LSTM, gate order i|f|g|o.
+ *
+ * dic_lstm_pack_whh: weight_hh_l0 and weight_hh_l0_reverse (512,128 each) -> the shared-memory image of the tensor-core
+ *   operand (fp16 hi + lo halves of the power-of-two-scaled weights, per direction and per 32-unit slice) followed by the
+ *   two inverse scales; `packed` holds dic_lstm_packed_bytes() bytes.  Call again whenever the weights change.
+ * dic_lstm_fwd: all R steps of both directions in ONE persistent kernel (4-CTA clusters, W_hh resident in shared memory,
+ *   h exchanged through distributed shared memory, tcgen05 MMAs with TMEM accumulators).
+ *   pre  (R,B,1024): W_ih x_t + b_ih + b_hh of both directions (a library GEMM of the caller), columns ordered
+ *        [direction][slice q = 0..3][half = 0,1][gate i,f,g,o][16 units]  <->  hidden unit 32 q + 16 half + u
+ *   h0, c0 (2,B,128) or NULL (zeros); out (R,B,256) = [forward | reverse]; hn, cn (2,B,128);
+ *   save (2,R,B,5,128) or NULL: i, f, g, o, c_t of every step for the backward pass.  hidden must be 128.
+ * dic_lstm_bwd_step: the gate-gradient algebra of ONE backward step of one direction (closed form of autograd on the
+ *   cell): da (B,512) = d a_t in gate order i|f|g|o, dc_rec (B,128) in/out; save_t (B,5,128) the step's saved row,
+ *   c_prev (row stride c_prev_stride) the previous cell state or NULL (zeros), gh_out (row stride gh_stride) the upstream
+ *   gradient of this direction's h_t or NULL, dh_rec (B,128) the recurrent gradient d a_(t+1) W_hh (a library GEMM). */
+size_t dic_lstm_packed_bytes(void);
+int dic_lstm_pack_whh(const float* w_hh, const float* w_hh_reverse, void* packed, dic_stream_t stream);
+int dic_lstm_fwd(const float* pre, const void* packed, const float* h0, const float* c0, float* out, float* hn,
+                 float* cn, float* save, int R, int64_t B, int hidden, dic_stream_t stream);
+int dic_lstm_bwd_step(const float* save_t, const float* c_prev, int64_t c_prev_stride, const float* gh_out,
+                      int64_t gh_stride, const float* dh_rec, float* dc_rec, float* da, int64_t B, int hidden,
+                      dic_stream_t stream);
+
 /* ---- utilities -------------------------------------------------------------------- */
 /* Deterministic column sums of a (rows, cols) float32 matrix into float64. */
 size_t dic_colsum_workspace_bytes(int cols);
