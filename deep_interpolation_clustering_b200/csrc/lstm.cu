@@ -63,7 +63,11 @@ __device__ __forceinline__ void st_cluster_v4(uint32_t addr, uint4 v) {
   asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
                : "memory");
 }
-__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// generic-proxy writes to (distributed) shared memory -> visible to the tensor core's async-proxy reads.  The
+// unqualified fence.proxy.async also orders GLOBAL memory and costs microseconds per step here.
+__device__ __forceinline__ void fence_proxy_async_cluster() {
+  asm volatile("fence.proxy.async.shared::cluster;" ::: "memory");
+}
 
 // tcgen05.ld 32 lanes x 32 bit x 8 columns, issue only (tcgen05.wait::ld by the caller once all pieces are in flight)
 __device__ __forceinline__ void tmem_ld8_issue(uint32_t taddr, uint32_t (&v)[8]) {
@@ -82,16 +86,22 @@ __device__ __forceinline__ void tmem_wait4x8(uint32_t (&a)[8], uint32_t (&b)[8],
                : "memory");
 }
 
-// sigmoid / tanh with float32-grade accuracy from MUFU.EX2 + a correctly rounded reciprocal (tanh.approx has 2^-11)
-__device__ __forceinline__ float sigmoid_acc(float x) { return __frcp_rn(1.0f + ex2_approx(-kLog2e * x)); }
+// sigmoid / tanh with float32-grade accuracy from MUFU.EX2 + MUFU.RCP (each ~1 ulp; tanh.approx has only 2^-11),
+// branch free: the epilogue is MUFU bound (10 per hidden unit and step), so everything else has to stay off the
+// critical path - an if / else per activation cost 25 % of the kernel's instructions as BSSY / BRA / BSYNC.
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sigmoid_acc(float x) { return rcp_approx(1.0f + ex2_approx(-kLog2e * x)); }
 __device__ __forceinline__ float tanh_acc(float x) {
   const float ax = fabsf(x);
-  if (ax < 0.04f) {                      // odd series: 1 - e^(-2x) would cancel; |error| < 2e-9 here
-    const float x2 = x * x;
-    return x * fmaf(x2, fmaf(x2, 0.13333334f, -0.33333334f), 1.0f);
-  }
+  const float x2 = x * x;
+  const float small = x * fmaf(x2, fmaf(x2, 0.13333334f, -0.33333334f), 1.0f);   // |x| < 0.04: error < 2e-9 (no cancellation)
   const float t = ex2_approx(-2.0f * kLog2e * ax);
-  return copysignf((1.0f - t) * __frcp_rn(1.0f + t), x);
+  const float big = copysignf((1.0f - t) * rcp_approx(1.0f + t), x);
+  return ax < 0.04f ? small : big;
 }
 
 // 8 floats -> 8 fp16 "hi" and 8 fp16 "lo" (residual), one 16-byte K chunk each
@@ -199,7 +209,7 @@ lstm_fwd_kernel(const float* __restrict__ pre, const unsigned char* __restrict__
 #pragma unroll
   for (int u = 0; u < 16; ++u) c[u] = (c0 && live) ? __ldg(c0 + ((int64_t)dir * B + b) * kH + j0 + u) : 0.f;
   const float inv_s = __ldg(inv_scale + dir);
-  fence_proxy_async_all();
+  fence_proxy_async_cluster();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -231,6 +241,7 @@ lstm_fwd_kernel(const float* __restrict__ pre, const unsigned char* __restrict__
     }
     // ---- a_t (recurrent part) = h_(t-1) W_hh^T on the tensor core ----
     if (warp == 0) {
+      fence_proxy_async();                          // the peers' h slices (acquired by the cluster barrier) -> async proxy
       tc_fence_after();
       if (elect_one()) {
         const uint32_t a_hi = sa_u + (uint32_t)buf * 2u * kTileB, a_lo = a_hi + kTileB;
@@ -309,7 +320,7 @@ lstm_fwd_kernel(const float* __restrict__ pre, const unsigned char* __restrict__
         st_cluster_v4(base + kTileB + kLbo, lo1);
       }
     }
-    fence_proxy_async_all();
+    fence_proxy_async_cluster();
     cluster_arrive();
     // ---- the layer output (overlaps the barrier latency) ----
     if (live) {
@@ -319,7 +330,6 @@ lstm_fwd_kernel(const float* __restrict__ pre, const unsigned char* __restrict__
     }
     __syncwarp();
     cluster_wait();                                  // all four slices of h_t have landed in every A buffer
-    fence_proxy_async_all();
   }
   if (live) {
     float* hp = hn + ((int64_t)dir * B + b) * kH + j0;
