@@ -51,6 +51,12 @@ WORKLOADS = {
     # n_init = 10 on a 1M x 64 latent matrix; one step = one whole sweep (c4_arm below; not an interp workload)
     "c4": dict(T=256, R=96, K=10, B=1_000_000, sweep=True,
                name="c4: gap-statistic k-means sweep K=2..10, 20 reference draws, n_init=10, 1M x 64-d latents (p2 path)"),
+    # p1 = one training step of the WHOLE pretrain network: the unmodified pretrain_interp.Net of the staged
+    # reference on top of the B200 mirrors - SCI -> CCI -> BiLSTM encoder -> BiLSTM decoder -> compress_fc -> RBF read-out,
+    # masked reconstruction MSE, backward through everything, Adam step (p1_arm below)
+    "p1": dict(T=256, R=96, K=4, B=16_384, net=True,
+               name="p1: full pretrain Net step (interp + BiLSTM encoder/decoder + compress_fc + RBF read-out, fwd+bwd+Adam), "
+                    "6 vitals x <=256 obs, 96 ref points, 16,384 encounters per GPU per step"),
     "c5": dict(T=1024, R=192, K=16, B=131_072,
                name="c5 (stress shape): interp fwd+bwd + DEC assign, 6 vitals x <=1024 obs, 192 ref points, K=16, "
                     "one 131,072-encounter shard of the 10M per step"),
@@ -792,6 +798,184 @@ def c4_arm(args, rank, world, local_rank):
     return line
 
 
+# ----------------------------------------------------------------------------------------------
+# p1: one training step of the whole pretrain network
+# ----------------------------------------------------------------------------------------------
+def _net_args():
+    import types
+    return types.SimpleNamespace(num_variables=C, num_timestamps=T, ref_points=R, hours_from_admission=HOURS, dropout=0.2,
+                                 aux_tasks={}, fake_detection=False, triple_margin=0., cluster_number=K_CLUST)
+
+
+def p1_cpu_arm(sample, steps=2):
+    """The staged reference's own pretrain_interp.Net (unmodified, its own operators, torch CPU) on `sample` encounters:
+    forward, rec_loss (:169-175), backward, Adam step.  Returns (encounters/s, seconds per step, cores, kind)."""
+    import torch
+    from deep_interpolation_clustering_b200 import synth
+    from oracle import make_ref
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    mod = make_ref.import_net_module("pretrain_interp", b200=False)
+    if mod is None:
+        return None
+    net = mod.Net(_net_args(), torch.device("cpu")).train()
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3)
+    x = torch.from_numpy(synth.make_encounters(sample, C, T, HOURS, seed=0))
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        hidden, rec, _ = net(x)
+        loss = net.rec_loss(x[:, :C], rec, x[:, C:2 * C])["loss"]
+        loss.backward()
+        opt.step()
+
+    step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return sample / dt, dt, cores, "reference"
+
+
+def p1_arm(args, rank, world, local_rank):
+    """One step = forward + rec_loss + backward + Adam of the unmodified pretrain_interp.Net (staged reference file) built
+    on the B200 mirrors, on B encounters per GPU; gradients all-reduced over the ranks (data parallel)."""
+    import torch
+    import torch.distributed as dist
+    from deep_interpolation_clustering_b200 import synth
+    from deep_interpolation_clustering_b200.packed import PackedEncounters, PackedStaging
+    from oracle import make_ref
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    mod = make_ref.import_net_module("pretrain_interp", b200=True)
+    if mod is None:
+        raise SystemExit("--workload p1 needs the staged reference (python oracle/make_ref.py where /root/reference exists)")
+    B = args.encounters
+    torch.manual_seed(0)
+    net = mod.Net(_net_args(), dev).to(dev).train()
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3)
+    x = synth.make_encounters_device(B, C, T, HOURS, 5.0, 1000 * rank, dev)
+    params = [p for p in net.parameters()]
+
+    def step(xb):
+        opt.zero_grad(set_to_none=True)
+        hidden, rec, _ = net(xb)
+        loss = net.rec_loss(xb[:, :C], rec, xb[:, C:2 * C])["loss"]
+        loss.backward()
+        if world > 1:
+            flat = torch.cat([p.grad.reshape(-1) for p in params])
+            dist.all_reduce(flat)
+            flat /= world
+            off = 0
+            for p in params:
+                p.grad.copy_(flat[off:off + p.numel()].view_as(p))
+                off += p.numel()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        step(x)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    stream = torch.cuda.current_stream(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        loss = step(x)
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    t_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t_ms) / args.steps
+
+    # kernel shares of one step (CUPTI): our kernels (dic::*) vs library kernels
+    shares, launches = {}, 0
+    try:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            step(x)
+            torch.cuda.synchronize(dev)
+        tot = sum(e.device_time_total for e in prof.key_averages()) or 1.0
+        for e in sorted(prof.key_averages(), key=lambda e: -e.device_time_total)[:12]:
+            shares[e.key[:70]] = {"ms": round(e.device_time_total / 1e3, 3), "share": round(e.device_time_total / tot, 4),
+                                  "launches": e.count}
+        launches = int(sum(e.count for e in prof.key_averages() if "dic::" in e.key))
+    except Exception:       # noqa: BLE001
+        pass
+
+    # e2e: pinned host batch (packed ragged rows) -> upload -> the same step -> loss back on the host
+    e2e = None
+    if not args.no_e2e:
+        host = x.cpu()
+        pk = PackedEncounters.from_dense(host)
+        staging = PackedStaging.for_chunks(pk, B, dev)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            xb = staging.upload(pk, 0, B)
+            lv = float(step(xb))
+        barrier()
+        wall = torch.tensor([(time.perf_counter() - t0) / args.steps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(wall, op=dist.ReduceOp.MAX)
+        e2e = {"value": round(world * B / float(wall), 1), "unit": "encounters/s", "ms_per_step": round(float(wall) * 1e3, 3),
+               "h2d_bytes_per_step": int(pk.nbytes(0, B)) * world, "d2h_bytes_per_step": 4 * world, "loss": lv,
+               "path": "pinned host PackedEncounters -> PackedStaging.upload -> pretrain_interp.Net (unmodified staged "
+                       "reference file on the B200 mirrors incl. the BiLSTMs) fwd + rec_loss + bwd + Adam -> loss to the host"}
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return None
+    line = {
+        "metric": "encounters/s (full pretrain Net step: interp + BiLSTM enc/dec + read-out, fwd+bwd+Adam)",
+        "value": round(world * B / (ms_per_step * 1e-3), 1), "unit": "encounters/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": CFG_NAME, "encounters_per_gpu": B, "vitals": C, "max_obs": T, "ref_points": R,
+                   "parameters": int(sum(p.numel() for p in params)), "parallelism": f"data-parallel x{world}",
+                   "l2": f"activations ({B * R * 1024 * 4 / 1e9:.1f} GB of gate pre-activations alone) exceed L2"},
+        "clocks": clocks, "gpu_launches": launches * args.steps, "gpu_launches_per_step": launches,
+        "kernels": shares, "loss": float(loss), "e2e": e2e,
+    }
+    k = next((v for n, v in shares.items() if "lstm_fwd_kernel" in n), None)
+    if k:
+        # the recurrence: 2 B R 2 x 128 x 512 algorithmic flops per forward launch, two launches (encoder, decoder) per step
+        flops = 2.0 * B * R * 2 * 128 * 512 * k["launches"]
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
+        except Exception:       # noqa: BLE001
+            pass
+        peak = float(peaks.get("bf16_tflops", 1653.3))
+        line["roofline"] = {"kernel": "lstm_fwd_kernel (persistent BiLSTM recurrence)", "bound": "tensor",
+                            "achieved": round(flops / (k["ms"] * 1e-3) / 1e12, 2), "peak": peak, "unit": "TFLOP/s",
+                            "frac": round(flops / (k["ms"] * 1e-3) / 1e12 / peak, 4), "traffic": None,
+                            "note": "algorithmic float32 flops of h W_hh^T; the kernel issues 3 fp16 MMAs per product (split "
+                                    "operands) and its step time is set by the MUFU-bound gate epilogue and the cluster "
+                                    "barrier, not by the tensor pipe (profiles/r02_ncu_lstm_fwd_summary.txt)"}
+    if not args.no_cpu_baseline:
+        r = p1_cpu_arm(min(args.cpu_sample, 64))
+        if r is not None:
+            v, dt, cores, kind = r
+            line["cpu_baseline"] = {"value": round(v, 1), "unit": "encounters/s", "cores": cores, "kind": kind,
+                                    "sample": f"{min(args.cpu_sample, 64)} encounters through the staged reference's own "
+                                              f"pretrain_interp.Net on its own operators (torch CPU), fwd + rec_loss + bwd + "
+                                              f"Adam, {dt:.2f} s/step"}
+    if world > 1:
+        dist.destroy_process_group()
+    return line
+
+
 def bind_to_gpu_numa(index):
     """Pin this process to the CPUs NVML reports as local to GPU `index` BEFORE the pinned host buffers are
     allocated and first touched, so that their pages live on the GPU's NUMA node (with 8 ranks streaming from
@@ -983,7 +1167,9 @@ def main():
         return
     if world != args.gpus and world == 1 and args.gpus > 1:
         sys.stderr.write(f"--gpus {args.gpus} needs torchrun with {args.gpus} ranks; running 1 rank\n")
-    if w.get("sweep"):
+    if w.get("net"):
+        line = p1_arm(args, rank, world, local_rank)
+    elif w.get("sweep"):
         if args.steps == 5:            # the default step count is for the interp workloads; one sweep is ~1 minute
             args.steps = 1
         line = c4_arm(args, rank, world, local_rank)

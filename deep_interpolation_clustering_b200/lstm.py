@@ -6,7 +6,9 @@ The reference wraps ``nn.LSTM(input, 128, num_layers=1, bidirectional=True)`` in
 (``weight_ih_l0 (512, I)``, ``weight_hh_l0 (512, 128)``, ``bias_ih_l0``, ``bias_hh_l0`` and the ``_reverse`` set), so
 ``encoder.lstm.*`` / ``decoder.lstm.*`` checkpoints load unchanged, and computes
 
-  * the input projection of all steps and both directions as ONE library GEMM (``torch.addmm``, float32),
+  * the input projection of all steps and both directions as ONE library GEMM (``torch.addmm``, plain float32: a
+    split-TF32 evaluation through the library's tensor-core GEMMs was measured 3x faster but 3-8x less accurate - their
+    accumulation is not round-to-nearest - and fell outside the 1e-5 parity, profiles/r02_lstm_notes.txt),
   * the recurrence of all R steps in ONE persistent sm_100a kernel (``dic_lstm_fwd``: 4-CTA clusters, W_hh resident
     in shared memory, h exchanged over distributed shared memory, tcgen05 MMAs on split-fp16 operands),
   * the backward recurrence with one fused gate-gradient kernel per step (``dic_lstm_bwd_step``) and library GEMMs

@@ -39,6 +39,7 @@ def stage(verbose=True):
 def import_reference(p2=False):
     """Import the staged reference modules (stubbing the optional imports the container lacks).
     Returns a namespace or None when nothing is staged.  p2=True also imports p2_clustering_optK (class KM)."""
+    import importlib.machinery
     import types
     if not os.path.exists(os.path.join(DEST, "interpolation_layer.py")):
         return None
@@ -46,6 +47,7 @@ def import_reference(p2=False):
     def stub(name, **attrs):
         if name not in sys.modules:
             m = types.ModuleType(name)
+            m.__spec__ = importlib.machinery.ModuleSpec(name, None)      # torch._dynamo probes find_spec("tensorflow")
             m.__dict__.update(attrs)
             sys.modules[name] = m
         return sys.modules[name]
@@ -76,6 +78,43 @@ def import_reference(p2=False):
         sys.path[:] = saved_path
         sys.argv[:] = saved_argv
         sys.modules.update(shadow)
+
+
+def import_net_module(name="pretrain_interp", b200=False):
+    """The staged reference's `pretrain_interp` / `clustering_interp` module.  b200=False: on the reference's own
+    operators (the CPU arm).  b200=True: the same unmodified file on top of the B200 mirrors (dropin.install +
+    dropin.patch_lstm) - what a user of the reference runs after switching.  Returns None when nothing is staged."""
+    import importlib
+    import importlib.machinery
+    import types
+    if not os.path.exists(os.path.join(DEST, name + ".py")):
+        return None
+
+    def stub(modname, **attrs):
+        if modname not in sys.modules:
+            m = types.ModuleType(modname)
+            m.__spec__ = importlib.machinery.ModuleSpec(modname, None)
+            m.__dict__.update(attrs)
+            sys.modules[modname] = m
+
+    stub("tensorflow", random=types.SimpleNamespace(set_seed=lambda s: None))
+    stub("warmup_scheduler", GradualWarmupScheduler=object)
+    for k in (name, "interpolation_layer", "rbf", "dec", "utils", "info"):
+        sys.modules.pop(k, None)
+    sys.path.insert(0, DEST)
+    try:
+        if b200:
+            from deep_interpolation_clustering_b200 import dropin
+            dropin.install()
+            mod = importlib.import_module(name)
+            dropin.patch_lstm(mod)
+        else:
+            mod = importlib.import_module(name)
+        return mod
+    finally:
+        sys.path.remove(DEST)
+        for k in (name, "interpolation_layer", "rbf", "dec", "utils", "info"):
+            sys.modules.pop(k, None)
 
 
 if __name__ == "__main__":

@@ -24,11 +24,12 @@ C, T, R, H, NH, K = 6, 32, 24, 24.0, 16, 3
 class _Net(nn.Module):
     """Mirror of pretrain_interp.Net.forward (:138-142) around whatever operator modules it is given."""
 
-    def __init__(self, sci, cci, rbf, assign):
+    def __init__(self, sci, cci, rbf, assign, nh=NH, lstm=None):
         super().__init__()
         self.sci, self.cci, self.rbf, self.assign = sci, cci, rbf, assign
-        self.encoder = nn.LSTM(3 * C, NH, bidirectional=True)
-        self.decoder = nn.LSTM(2 * NH, NH, bidirectional=True)
+        lstm = lstm or (lambda i, h: nn.LSTM(i, h, bidirectional=True))
+        self.encoder = lstm(3 * C, nh)
+        self.decoder = lstm(2 * nh, nh)
 
     def forward(self, x):
         u = self.cci(self.sci(x)).permute(1, 0, 2)                 # (R, B, 3C), as the LSTM wants it
@@ -48,6 +49,17 @@ def _loss(x, hidden, rec, q_fn, p_fn):
 
 
 def test_chained_network_step_matches_float64_reference_operators(monkeypatch):
+    _chained_step(monkeypatch, NH, None)
+
+
+def test_chained_network_with_the_b200_bilstm_matches_float64_reference(monkeypatch):
+    """The same step with the encoder / decoder LSTMs on the persistent tcgen05 kernel (lstm.BiLSTMB200, hidden 128 as in
+    pretrain_interp.py:95-112): every operator between the observations and the loss is now this package's."""
+    from deep_interpolation_clustering_b200.lstm import BiLSTMB200
+    _chained_step(monkeypatch, 128, lambda i, h: BiLSTMB200(i, h))
+
+
+def _chained_step(monkeypatch, NH, b200_lstm):
     import deep_interpolation_clustering_b200 as dic
     from deep_interpolation_clustering_b200 import synth
     from oracle import ref_port
@@ -70,13 +82,13 @@ def test_chained_network_step_matches_float64_reference_operators(monkeypatch):
     with torch.no_grad():
         cci.kernel.add_(torch.from_numpy(0.1 * rng.standard_normal((C, C)).astype(np.float32)).to(cci.kernel.device))
         ca.cluster_centers.copy_(torch.from_numpy(0.3 * rng.standard_normal((K, 2 * NH)).astype(np.float32)))
-    ours = _Net(sci, cci, rbf, ca)
+    ours = _Net(sci, cci, rbf, ca, NH, b200_lstm)
 
     # the truth: oracle operators, same weights, float64 on the CPU
     o_sci = ref_port.SingleChannelInterp(R, H, C)
     o_cci = ref_port.CrossChannelInterp(C)
     o_rbf = ref_port.RBFReadout(R, H, C, compress=copy.deepcopy(rbf.compress_fc.module.model).cpu())
-    truth = _Net(o_sci, o_cci, o_rbf, None)
+    truth = _Net(o_sci, o_cci, o_rbf, None, NH)
     with torch.no_grad():
         o_sci.kernel.copy_(sci.kernel)
         o_cci.kernel.copy_(cci.kernel)
