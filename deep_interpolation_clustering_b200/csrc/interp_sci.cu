@@ -36,6 +36,7 @@ namespace dic {
 namespace {
 
 constexpr int kMaxWarps = 8;
+constexpr float kExactAbove = 12.0f;   // ak (d* - r)^2 above which a filter evaluates its exponents in float64 (sci_fwd_task)
 constexpr float kCut = 24.0f;      // log2 of the dropped weight ratio: the dropped tail is < 2e-8 of S and < 5e-7 of the moment sums
 
 struct SciSmem {
@@ -183,7 +184,7 @@ __device__ __forceinline__ void sci_fwd_task(const float* __restrict__ sx, const
                                              bool regular, float r0, float inv_h) {
   const float alpha = par.x, a = par.y, na = -a;
   int ridx[RPT];
-  float rr[RPT], nhi[RPT], nlo[RPT];
+  float rr[RPT], nhi[RPT], dstar[RPT], dst[RPT];
   float nmax = 0.f;
 #pragma unroll
   for (int k = 0; k < RPT; ++k) {
@@ -191,9 +192,9 @@ __device__ __forceinline__ void sci_fwd_task(const float* __restrict__ sx, const
     const int rc = min(ridx[k], R - 1);
     rr[k] = __ldg(ref_t + rc);
     const int is = nearest_index(sd, n, tab[rc], rr[k]);               // tab[rc] = first observation at or after r
-    const float dst = sd[is] - rr[k];                                // delta* = d* - r
-    nhi[k] = dst * dst;
-    nlo[k] = -na * fmaf(dst, dst, -nhi[k]);    // exact residual delta*^2 - nhi, pre-multiplied by a
+    dstar[k] = sd[is];
+    dst[k] = dstar[k] - rr[k];                                       // delta* = d* - r
+    nhi[k] = dst[k] * dst[k];
     nmax = fmaxf(nmax, nhi[k]);
   }
   Window2 w;
@@ -216,19 +217,25 @@ __device__ __forceinline__ void sci_fwd_task(const float* __restrict__ sx, const
 
   // One filter: HIGH = false walks the outer window with exponent -a t, HIGH = true the inner window with -10 a t
   // (same shift).  One MUFU.EX2 per pair.
+  // The shifted squared distance t = (d - r)^2 - (d* - r)^2 is formed as a PRODUCT, t = (d - d*) ((d - d*) + 2 (d* - r)):
+  // d - d* is exact or rounded relative to itself, so t carries ~2e-7 relative error wherever the grid point lies.  (The
+  // difference of squares fma(d - r, d - r, -(d* - r)^2) inherits the absolute rounding of d - r times 2 |d - r|: for a
+  // sparse vital whose nearest observations are 8 h from the grid point that is 1.5e-5 on t and, times 10 alpha, 5e-5 on
+  // the high-pass output - found on the 4,096-encounter c2 slice, tests/test_gpu_interp.py.)  The exponent comes out in
+  // the same three packed instructions: dd = d - d*, q = fma(dd, -ak, -ak 2 (d* - r)), arg = dd q = -ak t.
   // Packed float32x2 arithmetic over pairs of consecutive observations (two aligned register pairs per 128-bit
   // load): the loop is issue bound, and FFMA2 / FADD2 / FMUL2 halve the issue slots of its arithmetic.
+  // The moments are accumulated on arg = -ak t (Q0 = sum arg e, Q1 = sum arg e x) and divided by -ak in the finish.
   auto filter = [&](auto high, float (&S)[RPT], float (&SC)[RPT], float (&Q0)[RPT], float (&Q1)[RPT]) {
     constexpr bool HIGH = decltype(high)::value;
     const float nak = HIGH ? 10.f * na : na;
     const f2_t nak2 = pack2(nak, nak);
-    f2_t nrr2[RPT], nnhi2[RPT], nlk2[RPT], S2[RPT], SC2[RPT], Q02[RPT], Q12[RPT];
+    f2_t nds2[RPT], nck2[RPT], S2[RPT], SC2[RPT], Q02[RPT], Q12[RPT];
 #pragma unroll
     for (int k = 0; k < RPT; ++k) {
-      const float nl = HIGH ? 10.f * nlo[k] : nlo[k];
-      nrr2[k] = pack2(-rr[k], -rr[k]);
-      nnhi2[k] = pack2(-nhi[k], -nhi[k]);
-      nlk2[k] = pack2(nl, nl);
+      const float nc = nak * (2.f * dst[k]);
+      nds2[k] = pack2(-dstar[k], -dstar[k]);
+      nck2[k] = pack2(nc, nc);
       S2[k] = SC2[k] = Q02[k] = Q12[k] = pack2(0.f, 0.f);
     }
     const int base = HIGH ? w.ib : w.ob, trip = HIGH ? w.it : w.ot;
@@ -248,9 +255,9 @@ __device__ __forceinline__ void sci_fwd_task(const float* __restrict__ sx, const
       for (int j = 0; j < 2; ++j) {
 #pragma unroll
         for (int k = 0; k < RPT; ++k) {
-          const f2_t dl = add2(dd[j], nrr2[k]);
-          const f2_t t1 = fma2(dl, dl, nnhi2[k]);                // (d-r)^2 - (d*-r)^2, rounded once
-          const f2_t arg = fma2(t1, nak2, nlk2[k]);              // the residual of the shift rides in the FMA
+          const f2_t dl = add2(dd[j], nds2[k]);                  // d - d*
+          const f2_t q = fma2(dl, nak2, nck2[k]);                // -ak ((d - d*) + 2 (d* - r))
+          const f2_t arg = mul2(dl, q);                          // -ak ((d - r)^2 - (d* - r)^2)
           float a0, a1;
           unpack2(arg, a0, a1);
           const f2_t e = pack2(ex2_approx(a0), ex2_approx(a1));
@@ -258,7 +265,7 @@ __device__ __forceinline__ void sci_fwd_task(const float* __restrict__ sx, const
           S2[k] = WEIGHTED ? fma2(mm[j], e, S2[k]) : add2(S2[k], e);
           SC2[k] = fma2(e, xx[j], SC2[k]);
           if (MOM) {
-            const f2_t te = mul2(t1, e);
+            const f2_t te = mul2(arg, e);
             Q02[k] = WEIGHTED ? fma2(mm[j], te, Q02[k]) : add2(Q02[k], te);
             Q12[k] = fma2(te, xx[j], Q12[k]);
           }
@@ -274,8 +281,60 @@ __device__ __forceinline__ void sci_fwd_task(const float* __restrict__ sx, const
     }
   };
 
+  // The same sums with the shifted squared distance evaluated in float64, for lanes whose NEAREST observation is far
+  // from the grid point (sparse vitals, gaps of hours).  There float32 cannot hold t: an observation at the same distance
+  // on the other side of the grid point has weight ~1 and t = (d - d*) (d + d* - 2 r) with a factor that cancels to the
+  // rounding of d - r itself, ~ulp(d* - r) |d - d*| = 1e-6 on t at 3 h, 5e-6 at 8 h, times 10 alpha on the high-pass
+  // exponent (measured: 4e-5 / 5e-5 on y' against the float64 reference, c1 and the 4,096-encounter c2 slice).  The float32
+  // error of the exponent is bounded by 2.4e-7 ak max (d* - r)^2, so a filter keeps the packed float32 loop while
+  // ak max (d* - r)^2 <= 12 (3e-6 on the exponent; ak = a or 10 a): for the low-pass sums that is a nearest observation
+  // within ~2.9 h, for the high-pass sums within ~0.9 h.  A warp without a far lane never enters this loop, and the rows
+  // that do are the short ones (measured cost at c2: +3 % of the kernel).
+  const bool far_low = !WEIGHTED && a * nmax > kExactAbove, far_high = !WEIGHTED && 10.f * a * nmax > kExactAbove;
+  const bool any_far_low = __any_sync(0xffffffffu, far_low), any_far_high = __any_sync(0xffffffffu, far_high);
+  auto filter_exact = [&](auto high, float (&S)[RPT], float (&SC)[RPT], float (&Q0)[RPT], float (&Q1)[RPT]) {
+    constexpr bool HIGH = decltype(high)::value;
+    const bool far = HIGH ? far_high : far_low;
+    const double nakd = HIGH ? 10.0 * (double)na : (double)na;
+    double v2[RPT], rd[RPT];
+    float s_[RPT], sc_[RPT], q0_[RPT], q1_[RPT];
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) {
+      rd[k] = (double)rr[k];
+      const double v = (double)dstar[k] - rd[k];
+      v2[k] = v * v;
+      s_[k] = sc_[k] = q0_[k] = q1_[k] = 0.f;
+    }
+    const int base = HIGH ? w.ib : w.ob, trip = HIGH ? w.it : w.ot;
+    if (far) {
+      for (int t = max(base, 0); t < min(base + trip, n); ++t) {
+        const double d = (double)sd[t];
+        const float x = sx[t];
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) {
+          const double u = d - rd[k];
+          const float arg = (float)(nakd * fma(u, u, -v2[k]));
+          const float e = ex2_approx(arg);
+          s_[k] += e;
+          sc_[k] = fmaf(e, x, sc_[k]);
+          if (MOM) {
+            const float te = arg * e;
+            q0_[k] += te;
+            q1_[k] = fmaf(te, x, q1_[k]);
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < RPT; ++k) {
+        S[k] = s_[k]; SC[k] = sc_[k]; Q0[k] = q0_[k]; Q1[k] = q1_[k];
+      }
+    }
+  };
+
   float S[RPT], SC[RPT], Q0[RPT], Q1[RPT];
+  const float inv_na = __frcp_rn(na);
   filter(std::false_type{}, S, SC, Q0, Q1);
+  if (any_far_low) filter_exact(std::false_type{}, S, SC, Q0, Q1);
 #pragma unroll
   for (int k = 0; k < RPT; ++k) {
     if (ridx[k] < R) {
@@ -283,19 +342,21 @@ __device__ __forceinline__ void sci_fwd_task(const float* __restrict__ sx, const
       ub[(0 * C + c) * R + ridx[k]] = yc;
       // log S through MUFU.LG2 (absolute error ~2e-7 on log S <= ~6; w itself is -alpha n_min + log S)
       ub[(1 * C + c) * R + ridx[k]] = fmaf(__log2f(S[k]), kLn2, -alpha * nhi[k]);
-      if (MOM) {
-        sb[(0 * C + c) * R + ridx[k]] = fmaf(-yc, Q0[k], Q1[k]) * inv;          // U1
-        sb[(1 * C + c) * R + ridx[k]] = fmaf(Q0[k], inv, nhi[k]);               // U0 >= 0
+      if (MOM) {          // the sums are over arg = -a t: back to t with 1 / (-a)
+        const float invt = inv * inv_na;
+        sb[(0 * C + c) * R + ridx[k]] = fmaf(-yc, Q0[k], Q1[k]) * invt;         // U1
+        sb[(1 * C + c) * R + ridx[k]] = fmaxf(fmaf(Q0[k], invt, nhi[k]), 0.f);  // U0 >= 0
       }
     }
   }
   filter(std::true_type{}, S, SC, Q0, Q1);
+  if (any_far_high) filter_exact(std::true_type{}, S, SC, Q0, Q1);
 #pragma unroll
   for (int k = 0; k < RPT; ++k) {
     if (ridx[k] < R) {
       const float inv = __frcp_rn(S[k]), yc = SC[k] * inv;
       ub[(2 * C + c) * R + ridx[k]] = yc;
-      if (MOM) sb[(2 * C + c) * R + ridx[k]] = 10.f * fmaf(-yc, Q0[k], Q1[k]) * inv;   // U1'
+      if (MOM) sb[(2 * C + c) * R + ridx[k]] = fmaf(-yc, Q0[k], Q1[k]) * inv * inv_na;   // U1' = 10 (..) / (-10 a S')
     }
   }
 }

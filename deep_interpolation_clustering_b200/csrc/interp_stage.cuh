@@ -110,7 +110,7 @@ __device__ __forceinline__ int warp_canonical_count(const float* rm, const float
   return ok ? cnt : -1;
 }
 
-constexpr float kPadTime = 3.0e18f;   // (kPadTime - r)^2 stays finite and 2^(-a * that) == 0
+constexpr float kPadTime = 1.0e12f;   // a (kPadTime - d*)^2 stays finite for any kernel (no 0 * inf in the moments) and 2^(-that) == 0
 
 // Pads rows [n, round_up(n,4)) with entries that contribute exactly nothing.
 __device__ __forceinline__ void warp_pad4_far(float* key, float* a, float* b, int n, int lane) {

@@ -14,7 +14,7 @@
 namespace dic {
 
 constexpr int kPackedMaxC = 16;
-constexpr float kPackedPadTime = 3.0e18f;   // == kPadTime (interp_stage.cuh)
+constexpr float kPackedPadTime = 3.0e18f;   // a far-away time; the expansion writes 0 in the dense planes, whose kernels pad on their own
 
 __host__ __device__ inline int packed_round4(int n) { return (n + 3) & ~3; }
 

@@ -399,3 +399,62 @@ def test_observation_tensor_gradient_is_refused_loudly():
     # a frozen kernel with a plain input still runs (no saved state, no backward)
     sci.kernel.requires_grad_(False)
     assert sci(x.detach()).shape == (4, 24, 18)
+
+
+def test_config2_slice_of_4096_encounters_vs_the_staged_reference_in_float64():
+    """"c2 B = 1M, T = 256, R = 96 (oracle checks a 4,096-row slice)".  The first 4,096 encounters of the c2
+    generator through the kernels against the REFERENCE'S OWN modules (interpolation_layer.py, rbf.py as staged in
+    baseline/_ref by oracle/make_ref.py - it travels with the tree) run in float64 on the host in chunks of 128:
+    every output element and the three parameter gradients."""
+    from deep_interpolation_clustering_b200 import synth
+    import deep_interpolation_clustering_b200 as dic
+    from oracle import make_ref
+    ref = make_ref.import_reference()
+    if ref is None:
+        pytest.skip("no staged reference (python oracle/make_ref.py where /root/reference exists)")
+    dev, cpu = torch.device("cuda:0"), torch.device("cpu")
+    B, C, T, R, H = 4096, 6, 256, 96, 24.0
+    xn = synth.make_encounters(B, C, T, H, seed=0)
+    p = synth.make_interp_params(C, seed=1)
+    rng = np.random.RandomState(2)
+    vn = rng.normal(size=(B, C, R)).astype(np.float32)
+    gc = rng.normal(size=(B, R, 3 * C)).astype(np.float32)
+    gr = rng.normal(size=(B, C, T)).astype(np.float32)
+
+    r_sci = ref.interpolation_layer.SingleChannelInterp(R, H, C, T, cpu).double()
+    r_cci = ref.interpolation_layer.CrossChannelInterp(C, T, cpu).double()
+    r_rbf = ref.rbf.RBF(H, R, C, C, 0.0, ref.rbf.basis_func_dict()["gaussian"], cpu)
+    r_rbf.compress_fc = torch.nn.Identity()
+    r_rbf = r_rbf.double()
+    r_rbf.interp_t = r_rbf.interp_t.double()
+    with torch.no_grad():
+        r_sci.kernel.copy_(torch.from_numpy(p["sci_kernel"]).double())
+        r_cci.kernel.copy_(torch.from_numpy(p["cci_kernel"]).double())
+        r_rbf.kernel.copy_(torch.from_numpy(p["rbf_kernel"]).double())
+    c64, rec64 = [], []
+    torch.set_num_threads(max(1, (torch.get_num_threads())))
+    for i in range(0, B, 128):
+        xb = torch.from_numpy(xn[i:i + 128]).double()
+        out = r_cci(r_sci(xb))
+        rec = r_rbf(torch.from_numpy(vn[i:i + 128]).double(), xb)
+        ((out * torch.from_numpy(gc[i:i + 128]).double()).sum() + (rec * torch.from_numpy(gr[i:i + 128]).double()).sum()).backward()
+        c64.append(out.detach().numpy())
+        rec64.append(rec.detach().numpy())
+    c64, rec64 = np.concatenate(c64), np.concatenate(rec64)
+
+    sci = dic.SingleChannelInterp(R, H, C, T, dev)
+    cci = dic.CrossChannelInterp(C, T, dev)
+    rbf = dic.RBF(H, R, C, C, 0.0, dic.basis_func_dict()["gaussian"], dev)
+    rbf.compress_fc = torch.nn.Identity()
+    sci.kernel.data = torch.tensor(p["sci_kernel"], device=dev)
+    cci.kernel.data = torch.tensor(p["cci_kernel"], device=dev)
+    rbf.kernel.data = torch.tensor(p["rbf_kernel"], device=dev)
+    x = torch.tensor(xn, device=dev)
+    c = cci(sci(x))
+    rec = rbf(torch.tensor(vn, device=dev), x)
+    ((c * torch.tensor(gc, device=dev)).sum() + (rec * torch.tensor(gr, device=dev)).sum()).backward()
+    _check_groups("c2_slice4096/cci_out", c, c64, C)
+    _check("c2_slice4096/rbf_out", rec, rec64)
+    _check("c2_slice4096/d_sci_kernel", sci.kernel.grad, r_sci.kernel.grad.numpy())
+    _check("c2_slice4096/d_cci_kernel", cci.kernel.grad, r_cci.kernel.grad.numpy())
+    _check("c2_slice4096/d_rbf_kernel", rbf.kernel.grad, r_rbf.kernel.grad.numpy())
