@@ -9,7 +9,7 @@ irregular observations in 24 h, 96 reference points, per GPU (weak scaling: ever
 its own 1M-encounter shard), plus the DEC q/p assignment of one 256-d latent per encounter
 (K = 4).  One step = one pass of the whole hot path over the shard:
 
-    SCI fwd -> CCI fwd -> CCI bwd -> SCI bwd -> RBF fwd -> RBF bwd -> DEC q (+labels, column sum)
+    SCI fwd -> CCI fwd -> CCI+SCI bwd (one kernel) -> RBF fwd -> RBF bwd -> DEC q (+labels, column sum)
     -> all-reduce(column sum) -> DEC p -> all-reduce(parameter gradients)
 
 `value`  : whole-job encounters/s, inputs resident in HBM, CUDA-event timed, max over ranks.
@@ -215,7 +215,7 @@ class HotPath:
     """Preallocated buffers + direct C-ABI calls for one shard (no allocation in the timed loop)."""
 
     # launches of OUR kernels behind each C-ABI call (kernel + reductions)
-    LAUNCHES = dict(sci_fwd=1, cci_fwd=1, cci_bwd=3, sci_bwd=4, rbf_fwd=1, rbf_bwd=4, dec_q=2, dec_p=1, dec_kl=2)
+    LAUNCHES = dict(sci_fwd=1, cci_fwd=1, cci_sci_bwd=6, rbf_fwd=1, rbf_bwd=4, dec_q=2, dec_p=1, dec_kl=2)
 
     def __init__(self, B, dev, seed, dec_kl=False):
         self.dec_kl = dec_kl
@@ -235,7 +235,6 @@ class HotPath:
         self.stats = torch.empty((B, 3 * C, R), **f32)          # gradient-moment rows [U1 | U0 | U1']
         self.out = torch.empty((B, 3 * C, R), **f32)
         self.g_out = torch.randn((B, 3 * C, R), generator=g, **f32)
-        self.g_u = torch.empty((B, 3 * C, R), **f32)
         self.v = torch.randn((B, C, R), generator=g, **f32)
         self.rec = torch.empty((B, C, T), **f32)
         self.inv = torch.empty((B, C, T), **f32)
@@ -248,7 +247,7 @@ class HotPath:
         self.colsum = torch.empty(K_CLUST, dtype=torch.float64, device=dev)
         self.grads = torch.empty(C + C * C + C, **f32)          # packed [d sci.kernel | d cci.kernel | d rbf.kernel]
         self.ws_i = torch.empty(int(self.L.dic_interp_bwd_workspace_bytes(B, C)), dtype=torch.uint8, device=dev)
-        self.ws_c = torch.empty(int(self.L.dic_cci_bwd_workspace_bytes(B, C)), dtype=torch.uint8, device=dev)
+        self.ws_c = torch.empty(int(self.L.dic_cci_sci_bwd_workspace_bytes(B, C)), dtype=torch.uint8, device=dev)
         self.ws_d = torch.empty(int(self.L.dic_dec_workspace_bytes(K_CLUST, D_LAT)), dtype=torch.uint8, device=dev)
         if dec_kl:
             self.g_z = torch.empty_like(self.z)
@@ -270,10 +269,10 @@ class HotPath:
             ("sci_fwd", lambda: chk(L.dic_sci_fwd(P(self.x), P(self.k_sci), P(self.ref_t), P(self.u), P(self.stats),
                                                   B, C, T, R, 0, st), "sci_fwd")),
             ("cci_fwd", lambda: chk(L.dic_cci_fwd(P(self.u), P(self.k_cci), P(self.out), B, C, R, st), "cci_fwd")),
-            ("cci_bwd", lambda: chk(L.dic_cci_bwd(P(self.u), P(self.k_cci), P(self.g_out), P(self.g_u), P(gc),
-                                                  P(self.ws_c), B, C, R, st), "cci_bwd")),
-            ("sci_bwd", lambda: chk(L.dic_sci_bwd(P(self.x), P(self.k_sci), P(self.ref_t), P(self.u), P(self.stats),
-                                                  P(self.g_u), P(gs), P(self.ws_i), B, C, T, R, 0, st), "sci_bwd")),
+            # CCI backward with the SCI backward folded in: the gradient of the SCI output never reaches HBM
+            ("cci_sci_bwd", lambda: chk(L.dic_cci_sci_bwd(P(self.u), P(self.k_cci), P(self.k_sci), P(self.stats),
+                                                          P(self.g_out), P(gc), P(gs), P(self.ws_c), B, C, R, st),
+                                        "cci_sci_bwd")),
             ("rbf_fwd", lambda: chk(L.dic_rbf_fwd(P(self.v), P(self.x), P(self.k_rbf), P(self.ref_t), P(self.rec),
                                                   P(self.inv), B, C, T, R, 0, st), "rbf_fwd")),
             ("rbf_bwd", lambda: chk(L.dic_rbf_bwd(P(self.v), P(self.x), P(self.k_rbf), P(self.ref_t), P(self.rec),
@@ -287,8 +286,8 @@ class HotPath:
         """Algorithmic HBM bytes and MUFU exps per launch (split per kernel)."""
         B, nv = self.B, self.n_valid
         ct, cr = C * T * 4.0, C * R * 4.0
-        byt = dict(sci_fwd=3 * ct + 3 * cr + 3 * cr, cci_fwd=6 * cr, cci_bwd=9 * cr,
-                   sci_bwd=3 * cr + 3 * cr, rbf_fwd=2 * ct + cr + 2 * ct,
+        byt = dict(sci_fwd=3 * ct + 3 * cr + 3 * cr, cci_fwd=6 * cr, cci_sci_bwd=9 * cr,      # u, grad_out, stats in
+                   rbf_fwd=2 * ct + cr + 2 * ct,
                    rbf_bwd=2 * ct + 3 * ct + cr + cr, dec_q=D_LAT * 4.0 + K_CLUST * 4.0 + 4.0, dec_p=2 * K_CLUST * 4.0,
                    dec_kl=2 * D_LAT * 4.0 + K_CLUST * 4.0)
         ex2 = dict(sci_fwd=2 * nv * R, rbf_fwd=nv * R, rbf_bwd=nv * R)     # sci_bwd no longer sweeps the observations

@@ -31,6 +31,8 @@ SIGNATURES = {
     "dic_sci_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, c_int64, _P]),
     "dic_cci_fwd": (c_int, [_P, _P, _P, c_int64, c_int, c_int, _P]),
     "dic_cci_bwd_workspace_bytes": (c_size_t, [c_int64, c_int]),
+    "dic_cci_sci_bwd_workspace_bytes": (c_size_t, [c_int64, c_int]),
+    "dic_cci_sci_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, _P]),
     "dic_cci_bwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, _P]),
     "dic_rbf_fwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, c_int64, _P]),
     "dic_rbf_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, c_int64, _P]),

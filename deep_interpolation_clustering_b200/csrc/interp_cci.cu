@@ -295,7 +295,8 @@ __device__ __forceinline__ void softmax_c8(const float* __restrict__ wrow /*ub +
 // bulk copies on a per-warp mbarrier: the loads of all warps of all resident CTAs are in flight
 // at once (>= 100 KB per SM), which is what an HBM-bound kernel with this little work needs.
 __device__ __forceinline__ const float* warp_tile_load(unsigned char* smem, int warp, int lane, int ntiles,
-                                                       const float* g0, const float* g1, uint32_t bytes) {
+                                                       const float* g0, const float* g1, uint32_t bytes,
+                                                       const float* g2 = nullptr) {
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem) + warp;
   float* tile = reinterpret_cast<float*>(smem + 64 + (size_t)warp * ntiles * bytes);
   if (lane == 0) {
@@ -307,6 +308,7 @@ __device__ __forceinline__ const float* warp_tile_load(unsigned char* smem, int 
     mbar_expect_tx(bar, bytes * ntiles);
     bulk_g2s(tile, g0, bytes, bar);
     if (ntiles > 1) bulk_g2s(reinterpret_cast<unsigned char*>(tile) + bytes, g1, bytes, bar);
+    if (ntiles > 2) bulk_g2s(reinterpret_cast<unsigned char*>(tile) + 2 * bytes, g2, bytes, bar);
   }
   mbar_wait(bar, 0);
   return tile;
@@ -362,11 +364,15 @@ cci_fwd_warp_kernel(const float* __restrict__ u, const float* __restrict__ kerne
   }
 }
 
-template <bool TILE, int CT>
+// FUSE: the SCI backward folded in (dic_cci_sci_bwd).  The gradient with respect to the SCI output is consumed where it
+// is produced - d alpha_c = - sum_r [ gy U1 + gw U0 + gy' U1' ] against the moment rows `stats` the forward pass saved
+// (interp_sci.cu) - instead of making a round trip through HBM as grad_u (13.8 KB per encounter written, then read).
+template <bool TILE, int CT, bool FUSE>
 __global__ void __launch_bounds__(kCciWarps * 32)
 cci_bwd_warp_kernel(const float* __restrict__ u, const float* __restrict__ kernel,
                     const float* __restrict__ grad_out, float* __restrict__ grad_u,
-                    float* __restrict__ partial /*(B, C*C)*/, int64_t B, int C_rt, int R) {
+                    float* __restrict__ partial /*(B, C*C)*/, const float* __restrict__ stats,
+                    float* __restrict__ sci_partial /*(B, C)*/, int64_t B, int C_rt, int R) {
   const int C = CT ? CT : C_rt;
   extern __shared__ __align__(128) unsigned char dyn_smem[];
   __shared__ float sK[64];
@@ -377,11 +383,13 @@ cci_bwd_warp_kernel(const float* __restrict__ u, const float* __restrict__ kerne
   if (b >= B) return;
   const float* ub = u + b * (int64_t)(3 * C) * R;
   const float* gb = grad_out + b * (int64_t)(3 * C) * R;
-  if (TILE) {
-    ub = warp_tile_load(dyn_smem, threadIdx.x >> 5, lane, 2, ub, gb, (uint32_t)(3 * C * R) * 4u);
+  const float* sb = FUSE ? stats + b * (int64_t)(3 * C) * R : nullptr;
+  if (TILE) {     // u | grad_out (| stats): all tiles of this warp in flight on one mbarrier
+    ub = warp_tile_load(dyn_smem, threadIdx.x >> 5, lane, FUSE ? 3 : 2, ub, gb, (uint32_t)(3 * C * R) * 4u, sb);
     gb = ub + 3 * C * R;
+    if (FUSE) sb = gb + 3 * C * R;
   }
-  float* dub = grad_u + b * (int64_t)(3 * C) * R;
+  float* dub = FUSE ? nullptr : grad_u + b * (int64_t)(3 * C) * R;
   const float invR = 1.0f / (float)R;
 
   float ybar[8];
@@ -449,6 +457,9 @@ cci_bwd_warp_kernel(const float* __restrict__ u, const float* __restrict__ kerne
   }
 
   // pass B: the gradients (rows are L1/L2 hot)
+  float dal[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) dal[c] = 0.f;
   for (int r = lane; r < R; r += 32) {
     float w[8], what[8], gzt[8], t[8], uu[8];
     softmax_c8<CT>(ub + C * R + r, C, R, w, what);
@@ -472,11 +483,29 @@ cci_bwd_warp_kernel(const float* __restrict__ u, const float* __restrict__ kerne
 #pragma unroll
     for (int c = 0; c < 8; ++c)
       if (c < C) {
-        dub[c * R + r] = what[c] * uu[c] - m_wu[c] + m_g[c];
-        dub[(C + c) * R + r] = what[c] * (t[c] - tw) + expf(w[c]) * gb[(C + c) * R + r];
-        dub[(2 * C + c) * R + r] = gb[(2 * C + c) * R + r];
+        const float gy = what[c] * uu[c] - m_wu[c] + m_g[c];
+        const float gw = what[c] * (t[c] - tw) + expf(w[c]) * gb[(C + c) * R + r];
+        const float gyp = gb[(2 * C + c) * R + r];
+        if (FUSE) {
+          const float u0 = sb[(C + c) * R + r];
+          if (u0 >= 0.f)        // U0 < 0 marks an all-masked vital: no contribution (its upstream gradients may be NaN)
+            dal[c] = fmaf(gy, sb[c * R + r], fmaf(gw, u0, fmaf(gyp, sb[(2 * C + c) * R + r], dal[c])));
+        } else {
+          dub[c * R + r] = gy;
+          dub[(C + c) * R + r] = gw;
+          dub[(2 * C + c) * R + r] = gyp;
+        }
       }
   }
+  if (FUSE) {
+    const float v = warp_reduce_multi<8>(dal, lane);          // lane l holds vital l >> 2
+    if ((lane & 3) == 0 && (lane >> 2) < C) sci_partial[b * C + (lane >> 2)] = -v;
+  }
+}
+
+__global__ void sigmoid_vec_kernel(const float* __restrict__ kernel, float* __restrict__ out, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) out[c] = sigmoid_ref(kernel[c]);
 }
 
 int check(const void* u, const void* kernel, int64_t B, int C, int R) {
@@ -541,15 +570,64 @@ extern "C" int dic_cci_bwd(const float* u, const float* kernel, const float* gra
     const unsigned grid = (unsigned)((B + kCciWarps - 1) / kCciWarps);
     const size_t tile = (size_t)3 * C * R * 4, smem = 64 + kCciWarps * 2 * tile;
     if (tile % 16 == 0 && aligned16(u) && aligned16(grad_out) && smem <= (size_t)kMaxSmemBytes) {
-      auto kf = C == 6 ? cci_bwd_warp_kernel<true, 6> : cci_bwd_warp_kernel<true, 0>;
+      auto kf = C == 6 ? cci_bwd_warp_kernel<true, 6, false> : cci_bwd_warp_kernel<true, 0, false>;
       if (smem > 48 * 1024)
         DIC_CUDA(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      kf<<<grid, kCciWarps * 32, smem, st>>>(u, kernel, grad_out, grad_u, partial, B, C, R);
+      kf<<<grid, kCciWarps * 32, smem, st>>>(u, kernel, grad_out, grad_u, partial, nullptr, nullptr, B, C, R);
     } else {
-      cci_bwd_warp_kernel<false, 0><<<grid, kCciWarps * 32, 0, st>>>(u, kernel, grad_out, grad_u, partial, B, C, R);
+      cci_bwd_warp_kernel<false, 0, false><<<grid, kCciWarps * 32, 0, st>>>(u, kernel, grad_out, grad_u, partial, nullptr,
+                                                                          nullptr, B, C, R);
     }
   } else
     cci_bwd_kernel<16><<<(unsigned)B, kCciThreads, 0, st>>>(u, kernel, grad_out, grad_u, partial, C, R);
   DIC_LAUNCH_CHECK("cci_bwd_kernel");
   return colsum_f32_launch(partial, nullptr, d_kernel, nullptr, red, B, C * C, st);
+}
+
+extern "C" size_t dic_cci_sci_bwd_workspace_bytes(int64_t B, int C) {
+  if (B < 0 || C <= 0) return 0;
+  const size_t p_cci = ((size_t)B * C * C * sizeof(float) + 255) / 256 * 256;
+  const size_t p_sci = ((size_t)B * C * sizeof(float) + 255) / 256 * 256;
+  return p_cci + p_sci + (size_t)kColsumBlocks * C * C * sizeof(double) + (size_t)C * sizeof(float) + 512;
+}
+
+extern "C" int dic_cci_sci_bwd(const float* u, const float* cci_kernel, const float* sci_kernel, const float* stats,
+                               const float* grad_out, float* d_cci_kernel, float* d_sci_kernel, void* workspace,
+                               int64_t B, int C, int R, dic_stream_t stream) {
+  int rc = check(u, cci_kernel, B, C, R);
+  if (rc) return rc;
+  DIC_REQUIRE(C <= 8, DIC_ERR_UNSUPPORTED, "the fused CCI + SCI backward covers d_dim <= 8 (got %d): call dic_cci_bwd and "
+              "dic_sci_bwd", C);
+  DIC_REQUIRE(((grad_out && stats && workspace) || B == 0) && d_cci_kernel && d_sci_kernel && sci_kernel,
+              DIC_ERR_INVALID_ARGUMENT, "null pointer argument");
+  cudaStream_t st = as_stream(stream);
+  if (B == 0) {
+    DIC_CUDA(cudaMemsetAsync(d_cci_kernel, 0, sizeof(float) * C * C, st));
+    DIC_CUDA(cudaMemsetAsync(d_sci_kernel, 0, sizeof(float) * C, st));
+    return DIC_OK;
+  }
+  unsigned char* ws = static_cast<unsigned char*>(workspace);
+  const size_t p_cci = ((size_t)B * C * C * sizeof(float) + 255) / 256 * 256;
+  const size_t p_sci = ((size_t)B * C * sizeof(float) + 255) / 256 * 256;
+  float* partial = reinterpret_cast<float*>(ws);
+  float* sci_partial = reinterpret_cast<float*>(ws + p_cci);
+  double* red = reinterpret_cast<double*>(ws + p_cci + p_sci);
+  float* sig = reinterpret_cast<float*>(ws + p_cci + p_sci + (size_t)kColsumBlocks * C * C * sizeof(double));
+  const unsigned grid = (unsigned)((B + kCciWarps - 1) / kCciWarps);
+  const size_t tile = (size_t)3 * C * R * 4, smem = 64 + kCciWarps * 3 * tile;
+  if (tile % 16 == 0 && aligned16(u) && aligned16(grad_out) && aligned16(stats) && smem <= (size_t)kMaxSmemBytes) {
+    auto kf = C == 6 ? cci_bwd_warp_kernel<true, 6, true> : cci_bwd_warp_kernel<true, 0, true>;
+    if (smem > 48 * 1024)
+      DIC_CUDA(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kf<<<grid, kCciWarps * 32, smem, st>>>(u, cci_kernel, grad_out, nullptr, partial, stats, sci_partial, B, C, R);
+  } else {
+    cci_bwd_warp_kernel<false, 0, true><<<grid, kCciWarps * 32, 0, st>>>(u, cci_kernel, grad_out, nullptr, partial, stats,
+                                                                       sci_partial, B, C, R);
+  }
+  DIC_LAUNCH_CHECK("cci_bwd_warp_kernel<fused>");
+  rc = colsum_f32_launch(partial, nullptr, d_cci_kernel, nullptr, red, B, C * C, st);
+  if (rc) return rc;
+  sigmoid_vec_kernel<<<(C + 127) / 128, 128, 0, st>>>(sci_kernel, sig, C);
+  DIC_LAUNCH_CHECK("sigmoid_vec_kernel");
+  return colsum_f32_launch(sci_partial, nullptr, d_sci_kernel, sig, red, B, C, st);
 }

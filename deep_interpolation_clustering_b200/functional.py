@@ -91,10 +91,12 @@ class _SCI(torch.autograd.Function):
                        "dic_sci_fwd")
         if need_grad:
             ctx.save_for_backward(x, kernel, ref_t, u, stats)
-        return u
+            ctx.mark_non_differentiable(stats)
+            return u, stats
+        return u, None
 
     @staticmethod
-    def backward(ctx, grad_u):
+    def backward(ctx, grad_u, _grad_stats=None):
         x, kernel, ref_t, u, stats = ctx.saved_tensors
         B, _, T = x.shape
         C, R = kernel.numel(), ref_t.numel()
@@ -114,7 +116,12 @@ def sci(x, kernel, ref_t):
         _require_cuda_f32(t, n)
     _no_input_grad(x, "x")
     x, xs = _planes(x, kernel.numel(), "x")
-    return _SCI.apply(x, kernel.contiguous(), ref_t.contiguous(), xs)
+    u, stats = _SCI.apply(x, kernel.contiguous(), ref_t.contiguous(), xs)
+    if stats is not None:
+        # what a CrossChannelInterp fed with this very tensor needs to fold the SCI backward into its own
+        # (cci_after_sci): the saved moment rows and the parameter they carry the gradient of
+        u._dic_sci = (stats, kernel)
+    return u
 
 
 class _CCI(torch.autograd.Function):
@@ -145,6 +152,50 @@ class _CCI(torch.autograd.Function):
                                               _lib.ptr(dk), _lib.ptr(ws), B, C, R,
                                               _lib.current_stream(u.device)), "dic_cci_bwd")
         return gu, dk
+
+
+class _CCIAfterSCI(torch.autograd.Function):
+    """cci(sci(x)) with ONE backward kernel (dic_cci_sci_bwd): the gradient of the SCI output never reaches HBM.
+    u is the SCI output, detached (its own autograd node only sees gradients from other consumers of u)."""
+
+    @staticmethod
+    def forward(ctx, u, kernel, sci_kernel, stats):
+        B, C3, R = u.shape
+        C = C3 // 3
+        with torch.cuda.device(u.device):
+            out = torch.empty_like(u)
+            _lib.check(_lib.lib().dic_cci_fwd(_lib.ptr(u), _lib.ptr(kernel), _lib.ptr(out), B, C, R,
+                                              _lib.current_stream(u.device)), "dic_cci_fwd")
+        ctx.save_for_backward(u, kernel, sci_kernel, stats)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        u, kernel, sci_kernel, stats = ctx.saved_tensors
+        B, C3, R = u.shape
+        C = C3 // 3
+        grad_out = grad_out.contiguous()
+        with torch.cuda.device(u.device):
+            dk = torch.empty_like(kernel)
+            dks = torch.empty_like(sci_kernel)
+            ws = _ws(_lib.lib().dic_cci_sci_bwd_workspace_bytes(B, C), u.device)
+            _lib.check(_lib.lib().dic_cci_sci_bwd(_lib.ptr(u), _lib.ptr(kernel), _lib.ptr(sci_kernel), _lib.ptr(stats),
+                                                  _lib.ptr(grad_out), _lib.ptr(dk), _lib.ptr(dks), _lib.ptr(ws), B, C, R,
+                                                  _lib.current_stream(u.device)), "dic_cci_sci_bwd")
+        return None, dk, dks, None
+
+
+def cci_after_sci(u, kernel):
+    """CrossChannelInterp on a tensor that `sci` produced in this graph: same result and gradients as ``cci(u, kernel)``,
+    with the SCI backward folded into the CCI backward kernel.  Returns None when `u` does not qualify (not an SCI
+    output of this graph, gradients off, d_dim > 8): the caller then takes the plain ``cci``."""
+    link = getattr(u, "_dic_sci", None)
+    if link is None or not torch.is_grad_enabled() or kernel.shape[0] > 8:
+        return None
+    stats, sci_kernel = link
+    if not (sci_kernel.requires_grad and u.is_contiguous() and u.shape[1] == 3 * kernel.shape[0]):
+        return None
+    return _CCIAfterSCI.apply(u.detach(), kernel.contiguous(), sci_kernel, stats)
 
 
 def cci(u, kernel):

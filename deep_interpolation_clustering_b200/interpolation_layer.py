@@ -14,6 +14,12 @@ import torch.nn as nn
 from . import functional as F_
 
 
+# cci(sci(x)): fold the SCI backward into the CCI backward kernel (functional.cci_after_sci).  The gradient of the SCI
+# output then never exists as a tensor; set to False if code outside these modules asks autograd for it
+# (torch.autograd.grad(..., inputs=sci_output)); retain_grad() / hooks on it are detected and keep the plain path.
+FUSE_SCI_CCI_BACKWARD = True
+
+
 class SingleChannelInterp(nn.Module):
     """Masked RBF interpolation of irregular observations onto a uniform grid.
 
@@ -51,7 +57,10 @@ class SingleChannelInterp(nn.Module):
             raise RuntimeError(f"The size of tensor a ({self.timestamp}) must match the size of tensor b "
                                f"({x.shape[2]}) at non-singleton dimension 1 (timestamp mismatch)")
         u = F_.sci(x, self.kernel, self._grid(x.device))
-        return u.permute(0, 2, 1)
+        out = u.permute(0, 2, 1)
+        if hasattr(u, "_dic_sci"):
+            out._dic_sci_planar = u          # lets a CrossChannelInterp fed with THIS tensor fuse the two backward passes
+        return out
 
 
 class CrossChannelInterp(nn.Module):
@@ -71,5 +80,12 @@ class CrossChannelInterp(nn.Module):
         if x.dim() != 3 or x.shape[2] != 3 * self.d_dim:
             raise RuntimeError(f"expected input (B, R, {3 * self.d_dim}); got {tuple(x.shape)}")
         self.output_dim = x.shape[1]
-        out = F_.cci(x.permute(0, 2, 1), self.kernel)     # planar (B, 3C, R); a view for SCI's output
+        # cci(sci(x)) - the chain of pretrain_interp.py:138-139 - runs ONE fused backward kernel.  Not when the caller looks
+        # at the gradient of the SCI output itself (retain_grad / hooks on x): that tensor then takes the plain path.
+        u = getattr(x, "_dic_sci_planar", None) if FUSE_SCI_CCI_BACKWARD else None
+        if u is not None and (x.retains_grad or x._backward_hooks):
+            u = None
+        out = F_.cci_after_sci(u, self.kernel) if u is not None else None
+        if out is None:
+            out = F_.cci(x.permute(0, 2, 1), self.kernel)     # planar (B, 3C, R); a view for SCI's output
         return out.permute(0, 2, 1)

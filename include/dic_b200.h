@@ -92,6 +92,14 @@ int dic_cci_fwd(const float* u, const float* kernel, float* out, int64_t B, int 
 size_t dic_cci_bwd_workspace_bytes(int64_t B, int C);
 
 /* Gradients of dic_cci_fwd: grad_u (B,3C,R) and d_kernel (C,C). */
+/* CCI backward with the SCI backward folded in (the common chain cci(sci(x)), pretrain_interp.py:138-139): the
+ * gradient with respect to the SCI output is contracted with the saved moment rows `stats` inside the kernel instead of
+ * being written to HBM and read back by dic_sci_bwd.  Results equal dic_cci_bwd + dic_sci_bwd.  d_dim <= 8.
+ * workspace: dic_cci_sci_bwd_workspace_bytes(B, C). */
+size_t dic_cci_sci_bwd_workspace_bytes(int64_t B, int C);
+int dic_cci_sci_bwd(const float* u, const float* cci_kernel, const float* sci_kernel, const float* stats,
+                    const float* grad_out, float* d_cci_kernel, float* d_sci_kernel, void* workspace,
+                    int64_t B, int C, int R, dic_stream_t stream);
 int dic_cci_bwd(const float* u, const float* kernel, const float* grad_out, float* grad_u,
                 float* d_kernel, void* workspace, int64_t B, int C, int R, dic_stream_t stream);
 

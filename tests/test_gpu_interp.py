@@ -458,3 +458,45 @@ def test_config2_slice_of_4096_encounters_vs_the_staged_reference_in_float64():
     _check("c2_slice4096/d_sci_kernel", sci.kernel.grad, r_sci.kernel.grad.numpy())
     _check("c2_slice4096/d_cci_kernel", cci.kernel.grad, r_cci.kernel.grad.numpy())
     _check("c2_slice4096/d_rbf_kernel", rbf.kernel.grad, r_rbf.kernel.grad.numpy())
+
+
+@pytest.mark.parametrize("case", ["interp_c2", "interp_odd", "interp_kernels", "interp_allmasked"])
+def test_fused_cci_sci_backward_equals_the_two_kernel_chain(golden, case):
+    """cci(sci(x)) through the modules folds the SCI backward into the CCI backward kernel (dic_cci_sci_bwd): the
+    parameter gradients must equal those of the plain chain (dic_cci_bwd -> grad_u in HBM -> dic_sci_bwd) - same
+    arithmetic on the same numbers, so to float32 rounding of the reduction order - and the float64 reference's."""
+    from deep_interpolation_clustering_b200 import interpolation_layer as il
+    g = golden(case)
+    dev = torch.device("cuda:0")
+    x = torch.tensor(g["x"], device=dev)
+    gc = torch.tensor(g["g_cci"], device=dev)
+    grads = {}
+    for fused in (True, False):
+        il.FUSE_SCI_CCI_BACKWARD = fused
+        try:
+            sci, cci, _ = _modules(g, dev)
+            s = sci(x)
+            c = cci(s)
+            (c * gc).sum().backward()
+            grads[fused] = (sci.kernel.grad.clone(), cci.kernel.grad.clone(), c.detach().clone())
+        finally:
+            il.FUSE_SCI_CCI_BACKWARD = True
+    assert torch.allclose(grads[True][2], grads[False][2], rtol=0, atol=0, equal_nan=True)     # same forward kernel
+    if case != "interp_allmasked":
+        _check(f"{case}/fused_d_sci_kernel", grads[True][0], g["d_sci_kernel_f64"])
+        _check(f"{case}/fused_d_cci_kernel", grads[True][1], g["d_cci_kernel_f64"])
+    for a, b in zip(grads[True][:2], grads[False][:2]):
+        fin = torch.isfinite(b)
+        assert torch.equal(torch.isfinite(a), fin)
+        assert torch.allclose(a[fin], b[fin], rtol=2e-6, atol=2e-6 * float(b[fin].abs().max() if fin.any() else 1.0))
+
+
+def test_fusion_steps_aside_when_the_sci_output_gradient_is_observed(golden):
+    g = golden("interp_c2")
+    dev = torch.device("cuda:0")
+    sci, cci, _ = _modules(g, dev)
+    s = sci(torch.tensor(g["x"], device=dev))
+    s.retain_grad()
+    (cci(s) * torch.tensor(g["g_cci"], device=dev)).sum().backward()
+    assert s.grad is not None and sci.kernel.grad is not None
+    _check_groups("retain/d_sci_out", s.grad, g["d_sci_out_f64"], g["x"].shape[1] // 4)
