@@ -21,7 +21,7 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
 from deep_interpolation_clustering_b200.build import sources_sha256  # noqa: E402
 
-NAMES = {"sci_fwd_kernel": "sci_fwd", "cci_fwd": "cci_fwd", "cci_bwd": "cci_bwd", "sci_bwd_kernel": "sci_bwd",
+NAMES = {"sci_fwd_kernel": "sci_fwd", "cci_fwd": "cci_fwd", "cci_bwd": "cci_sci_bwd", "sci_bwd_kernel": "sci_bwd",
          "rbf_fwd": "rbf_fwd", "rbf_bwd_kernel": "rbf_bwd", "dec_q": "dec_q", "dec_p_kernel": "dec_p",
          "interp_fused_fwd": "sci_cci_fwd", "interp_fused_bwd": "cci_sci_bwd"}
 

@@ -42,12 +42,16 @@ def _deps():
     return hdrs
 
 
+# the sources that define the kernels of the headline (c2) step: what profiles/dram_traffic.json is tied to
+STEP_SOURCES = ["common.cuh", "interp_stage.cuh", "interp_sci.cu", "interp_cci.cu", "interp_rbf.cu", "dec.cu"]
+
+
 def sources_sha256():
-    """SHA-256 over the kernel sources and the public header (sorted by name): what a measured profile is tied to."""
+    """SHA-256 over the sources of the headline step's kernels (sorted by name): what a measured ncu capture of that
+    step is tied to (changes to the k-means / pairwise / LSTM sources do not invalidate it)."""
     import hashlib
     h = hashlib.sha256()
-    files = sorted([os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))] +
-                   [os.path.join(INCLUDE, f) for f in os.listdir(INCLUDE)])
+    files = sorted(os.path.join(CSRC, f) for f in STEP_SOURCES)
     for f in files:
         h.update(os.path.basename(f).encode())
         h.update(open(f, "rb").read())
