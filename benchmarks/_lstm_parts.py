@@ -28,9 +28,16 @@ for I in (18, 256):
         res["perm_index"], perm = timed(lambda: _perm_index(dev))
         res["permute_weights"], (wp, bp) = timed(lambda: (torch.cat([m.weight_ih_l0, m.weight_ih_l0_reverse], 0)[perm],
                                                           torch.cat([m.bias_ih_l0 + m.bias_hh_l0, m.bias_ih_l0_reverse + m.bias_hh_l0_reverse], 0)[perm]))
-        res["addmm"], pre = timed(lambda: torch.addmm(bp, x.reshape(R * B, I), wp.t()))
-        packed = torch.empty(int(L.dic_lstm_packed_bytes()), dtype=torch.uint8, device=dev)
+        res["addmm_f32_simt"], pre = timed(lambda: torch.addmm(bp, x.reshape(R * B, I), wp.t()))
         st = _lib.current_stream(dev)
+        wpc, bpc, x2 = wp.contiguous(), bp.contiguous(), x.reshape(R * B, I)
+        pw = torch.empty(int(L.dic_lstm_project_packed_bytes(I)), dtype=torch.uint8, device=dev)
+        res["pack_wih"], _ = timed(lambda: L.dic_lstm_pack_wih(wpc.data_ptr(), pw.data_ptr(), I, st))
+        pre2 = torch.empty((R * B, 1024), device=dev)
+        res["project_tcgen05"], _ = timed(lambda: L.dic_lstm_project(x2.data_ptr(), I, pw.data_ptr(), bpc.data_ptr(), pre2.data_ptr(), R * B, I, 0, st))
+        res["project_max_abs_diff_vs_f32"] = float((pre2 - pre).abs().max())
+        del pre2
+        packed = torch.empty(int(L.dic_lstm_packed_bytes()), dtype=torch.uint8, device=dev)
         res["pack"], _ = timed(lambda: L.dic_lstm_pack_whh(m.weight_hh_l0.data_ptr(), m.weight_hh_l0_reverse.data_ptr(), packed.data_ptr(), st))
         out = torch.empty((R, B, 2 * H), device=dev); hn = torch.empty((2, B, H), device=dev); cn = torch.empty((2, B, H), device=dev)
         res["kernel_inference"], _ = timed(lambda: L.dic_lstm_fwd(pre.data_ptr(), packed.data_ptr(), None, None, out.data_ptr(), hn.data_ptr(), cn.data_ptr(), None, R, B, H, st))

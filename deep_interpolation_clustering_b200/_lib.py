@@ -60,6 +60,9 @@ SIGNATURES = {
     "dic_cluster_scatter_workspace_bytes": (c_size_t, [c_int]),
     "dic_cluster_scatter": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, _P]),
     "dic_dunn_minmax": (c_int, [_P, _P, _P, c_int64, c_int, c_int, c_int, _P]),
+    "dic_lstm_project_packed_bytes": (c_size_t, [c_int]),
+    "dic_lstm_pack_wih": (c_int, [_P, _P, c_int, _P]),
+    "dic_lstm_project": (c_int, [_P, c_int64, _P, _P, _P, c_int64, c_int, c_int, _P]),
     "dic_lstm_packed_bytes": (c_size_t, []),
     "dic_lstm_pack_whh": (c_int, [_P, _P, _P, _P]),
     "dic_lstm_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int64, c_int, _P]),

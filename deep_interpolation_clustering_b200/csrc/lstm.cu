@@ -373,6 +373,178 @@ __global__ void lstm_bwd_step_kernel(const float* __restrict__ save_t, const flo
   dc_rec[idx] = dc * f;
 }
 
+// ---- input projection on the tensor cores --------------------------------------------------------------------
+// pre (M, 1024) = A (M, K) Wp^T + bias for all R * B rows at once (dic_lstm_project): the float32 SIMT library GEMM that
+// fed the recurrence cost 2-4x the recurrence itself (24 / 48 ms against 10 ms at B = 32,768), and the library's TF32
+// tensor-core GEMMs are outside the 1e-5 parity.  Same arithmetic as the recurrence instead: operands split into fp16
+// hi + lo halves (A on the fly, while it is staged; Wp once, power-of-two scaled), three tcgen05 MMAs per K step
+// (hi.hi + hi.lo + lo.hi, M = 128, N = 256, K = 16), float32 accumulation in TMEM over K <= 256.
+//   CTA = 128 rows of A x 256 of the 1024 output columns at a time; K in chunks of 64 (zero padded);
+//   two CTAs per SM (96 KB of shared memory, 256 TMEM columns each) overlap one CTA's operand staging with the
+//   other's MMAs; the epilogue adds the bias and stores whole 128-byte lines per thread.
+constexpr int kPN = 256;                         // output columns per accumulator
+constexpr int kPK = 64;                          // K chunk
+constexpr int kPLboA = kRows * 16;               // A: 128 rows x 16 B per K chunk of 8 halves
+constexpr int kPLboB = kPN * 16;                 // B: 256 columns x 16 B
+constexpr int kPTileA = (kPK / 8) * kPLboA;      // 16 KB (hi or lo)
+constexpr int kPTileB = (kPK / 8) * kPLboB;      // 32 KB (hi or lo)
+constexpr uint32_t kIdescProj = make_idesc(0u, 128u, 256u);
+
+struct ProjSmem {
+  static constexpr size_t a = 0;                                   // [hi | lo]
+  static constexpr size_t b = a + 2 * (size_t)kPTileA;             // [hi | lo]
+  static constexpr size_t bars = b + 2 * (size_t)kPTileB;
+  static constexpr size_t total = bars + 64;
+};
+
+// Wp (1024, K) row-major float32 -> per (column block nb, K chunk kc): the UMMA B operand [hi | lo] (fp16, scaled)
+__global__ void lstm_pack_wih_kernel(const float* __restrict__ wp, unsigned char* __restrict__ packed,
+                                     float* __restrict__ inv_scale, int K, int nkc) {
+  __shared__ float red[32];
+  float mx = 0.f;
+  for (int i = threadIdx.x; i < 1024 * K; i += blockDim.x) mx = fmaxf(mx, fabsf(wp[i]));
+  mx = warp_max(mx);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = 0.f;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) mx = fmaxf(mx, red[w]);
+  int e = 0;
+  if (mx > 0.f && isfinite(mx)) frexpf(mx, &e);
+  const float s = ldexpf(1.0f, 13 - e);
+  if (blockIdx.x == 0 && threadIdx.x == 0) inv_scale[0] = 1.0f / s;
+  const int nb = blockIdx.x / nkc, kc = blockIdx.x % nkc;
+  unsigned char* dst = packed + (size_t)blockIdx.x * 2 * kPTileB;
+  for (int idx = threadIdx.x; idx < kPN * (kPK / 8); idx += blockDim.x) {
+    const int n = idx / (kPK / 8), c = idx % (kPK / 8);
+    float x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int k = kc * kPK + c * 8 + i;
+      x[i] = k < K ? s * wp[(size_t)(nb * kPN + n) * K + k] : 0.f;
+    }
+    uint4 hi, lo;
+    split8(x, hi, lo);
+    const size_t off = (size_t)c * kPLboB + (size_t)n * 16;
+    *reinterpret_cast<uint4*>(dst + off) = hi;
+    *reinterpret_cast<uint4*>(dst + kPTileB + off) = lo;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 2)
+lstm_project_kernel(const float* __restrict__ A, int64_t lda, const unsigned char* __restrict__ packed,
+                    const float* __restrict__ inv_scale, const float* __restrict__ bias, float* __restrict__ out,
+                    int64_t M, int K, int nkc, int relu) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char* sa = smem + ProjSmem::a;
+  unsigned char* sb = smem + ProjSmem::b;
+  uint64_t* bar_b = reinterpret_cast<uint64_t*>(smem + ProjSmem::bars);
+  uint64_t* bar_acc = bar_b + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_b + 2);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    mbar_init(bar_b, 1);
+    mbar_init(bar_acc, 1);
+    fence_proxy_async();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, kPN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const float inv_s = __ldg(inv_scale);
+  const uint32_t sa_u = smem_u32(sa), sb_u = smem_u32(sb);
+  const int64_t mtiles = (M + kRows - 1) / kRows;
+  const bool vec4 = (K % 4 == 0) && (lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15u) == 0);
+  uint32_t ph_b = 0, ph_acc = 0;
+  for (int64_t job = blockIdx.x; job < mtiles * 4; job += gridDim.x) {
+    const int64_t mt = job >> 2;
+    const int nb = (int)(job & 3);
+    const int64_t r0 = mt * kRows;
+    for (int kc = 0; kc < nkc; ++kc) {
+      if (tid == 0) {                                // the weight chunk: one 64 KB bulk copy (L2 resident after the first tile)
+        mbar_expect_tx(bar_b, 2u * kPTileB);
+        bulk_g2s(sb, packed + (size_t)(nb * nkc + kc) * 2 * kPTileB, 2u * kPTileB, bar_b);
+      }
+      // A chunk: 128 rows x 64 floats -> fp16 hi / lo in the UMMA layout; item = (row, 8-float K chunk)
+      for (int item = tid; item < kRows * (kPK / 8); item += kThreads) {
+        const int c = item & 7, row = item >> 3;     // 8 consecutive lanes read 256 contiguous bytes of one row
+        const int64_t gr = r0 + row;
+        const int k0 = kc * kPK + c * 8;
+        float x[8];
+        if (gr < M && vec4 && k0 + 8 <= K) {
+          const float4 v0 = __ldg(reinterpret_cast<const float4*>(A + gr * lda + k0));
+          const float4 v1 = __ldg(reinterpret_cast<const float4*>(A + gr * lda + k0) + 1);
+          x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w; x[4] = v1.x; x[5] = v1.y; x[6] = v1.z; x[7] = v1.w;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) x[i] = (gr < M && k0 + i < K) ? __ldg(A + gr * lda + k0 + i) : 0.f;
+        }
+        if (relu) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) x[i] = fmaxf(x[i], 0.f);
+        }
+        uint4 hi, lo;
+        split8(x, hi, lo);
+        const size_t off = (size_t)c * kPLboA + (size_t)row * 16;
+        *reinterpret_cast<uint4*>(sa + off) = hi;
+        *reinterpret_cast<uint4*>(sa + kPTileA + off) = lo;
+      }
+      fence_proxy_async();
+      __syncthreads();
+      if (warp == 0) {
+        mbar_wait(bar_b, ph_b);
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < kPK / 16; ++ks) {
+            const uint64_t dah = make_desc_kmajor(sa_u + ks * 2 * kPLboA, kPLboA, kSbo);
+            const uint64_t dal = make_desc_kmajor(sa_u + kPTileA + ks * 2 * kPLboA, kPLboA, kSbo);
+            const uint64_t dbh = make_desc_kmajor(sb_u + ks * 2 * kPLboB, kPLboB, kSbo);
+            const uint64_t dbl = make_desc_kmajor(sb_u + kPTileB + ks * 2 * kPLboB, kPLboB, kSbo);
+            umma_f16(tmem, dah, dbh, kIdescProj, (kc > 0 || ks > 0) ? 1u : 0u);
+            umma_f16(tmem, dah, dbl, kIdescProj, 1u);
+            umma_f16(tmem, dal, dbh, kIdescProj, 1u);
+          }
+          umma_commit(bar_acc);
+        }
+        __syncwarp();
+      }
+      ph_b ^= 1u;
+      mbar_wait(bar_acc, ph_acc);                    // the MMAs have read both operand buffers: they may be refilled
+      ph_acc ^= 1u;
+    }
+    // epilogue: thread = (row, 128 of the 256 columns): + bias, whole 128-byte lines per thread
+    tc_fence_after();
+    {
+      const int row = 32 * (warp & 3) + lane, half = warp >> 2;
+      const int64_t gr = r0 + row;
+      float* orow = out + gr * 1024 + nb * kPN + half * 128;
+      const float* brow = bias + nb * kPN + half * 128;
+#pragma unroll 1
+      for (int cb = 0; cb < 4; ++cb) {
+        uint32_t v[32];
+        tmem_ld32(tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(half * 128 + cb * 32), v);
+        if (gr < M) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(brow + cb * 32) + i);
+            float4 o;
+            o.x = fmaf(__uint_as_float(v[4 * i]), inv_s, b4.x);
+            o.y = fmaf(__uint_as_float(v[4 * i + 1]), inv_s, b4.y);
+            o.z = fmaf(__uint_as_float(v[4 * i + 2]), inv_s, b4.z);
+            o.w = fmaf(__uint_as_float(v[4 * i + 3]), inv_s, b4.w);
+            reinterpret_cast<float4*>(orow + cb * 32)[i] = o;
+          }
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();                                 // the accumulator is drained before the next job overwrites it
+    tc_fence_after();
+  }
+  if (warp == 0) tmem_dealloc(tmem, kPN);
+}
+
 }  // namespace
 }  // namespace dic
 
@@ -420,5 +592,45 @@ extern "C" int dic_lstm_bwd_step(const float* save_t, const float* c_prev, int64
   lstm_bwd_step_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(save_t, c_prev, c_prev_stride, gh_out,
                                                                                   gh_stride, dh_rec, dc_rec, da, B);
   DIC_LAUNCH_CHECK("lstm_bwd_step_kernel");
+  return DIC_OK;
+}
+
+extern "C" size_t dic_lstm_project_packed_bytes(int K) {
+  if (K <= 0) return 0;
+  const int nkc = (K + kPK - 1) / kPK;
+  return (size_t)4 * nkc * 2 * kPTileB + 64;
+}
+
+extern "C" int dic_lstm_pack_wih(const float* wp, void* packed, int K, dic_stream_t stream) {
+  DIC_REQUIRE(wp && packed && K > 0 && K <= 1024, DIC_ERR_INVALID_ARGUMENT, "bad arguments (K=%d)", K);
+  DIC_REQUIRE(aligned16(packed), DIC_ERR_INVALID_ARGUMENT, "packed must be 16-byte aligned");
+  const int nkc = (K + kPK - 1) / kPK;
+  unsigned char* p = static_cast<unsigned char*>(packed);
+  float* inv_scale = reinterpret_cast<float*>(p + (size_t)4 * nkc * 2 * kPTileB);
+  lstm_pack_wih_kernel<<<4 * nkc, 256, 0, as_stream(stream)>>>(wp, p, inv_scale, K, nkc);
+  DIC_LAUNCH_CHECK("lstm_pack_wih_kernel");
+  return DIC_OK;
+}
+
+extern "C" int dic_lstm_project(const float* A, int64_t lda, const void* packed, const float* bias, float* out, int64_t M,
+                                int K, int relu, dic_stream_t stream) {
+  DIC_REQUIRE(M >= 0 && K > 0 && K <= 1024 && lda >= K, DIC_ERR_INVALID_ARGUMENT, "bad sizes M=%lld K=%d lda=%lld",
+              (long long)M, K, (long long)lda);
+  DIC_REQUIRE(packed && bias && ((A && out) || M == 0), DIC_ERR_INVALID_ARGUMENT, "null pointer argument");
+  DIC_REQUIRE(aligned16(out) && aligned16(packed) && aligned16(bias), DIC_ERR_INVALID_ARGUMENT,
+              "out / packed / bias must be 16-byte aligned");
+  if (M == 0) return DIC_OK;
+  const int nkc = (K + kPK - 1) / kPK;
+  const unsigned char* p = static_cast<const unsigned char*>(packed);
+  const float* inv_scale = reinterpret_cast<const float*>(p + (size_t)4 * nkc * 2 * kPTileB);
+  int dev = 0, sms = 148;
+  DIC_CUDA(cudaGetDevice(&dev));
+  DIC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int64_t jobs = ((M + kRows - 1) / kRows) * 4;
+  const int grid = (int)(jobs < 2LL * sms ? jobs : 2LL * sms);
+  DIC_CUDA(cudaFuncSetAttribute(lstm_project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ProjSmem::total));
+  lstm_project_kernel<<<grid, kThreads, ProjSmem::total, as_stream(stream)>>>(A, lda, p, inv_scale, bias, out, M, K, nkc,
+                                                                             relu);
+  DIC_LAUNCH_CHECK("lstm_project_kernel");
   return DIC_OK;
 }

@@ -6,9 +6,10 @@ The reference wraps ``nn.LSTM(input, 128, num_layers=1, bidirectional=True)`` in
 (``weight_ih_l0 (512, I)``, ``weight_hh_l0 (512, 128)``, ``bias_ih_l0``, ``bias_hh_l0`` and the ``_reverse`` set), so
 ``encoder.lstm.*`` / ``decoder.lstm.*`` checkpoints load unchanged, and computes
 
-  * the input projection of all steps and both directions as ONE library GEMM (``torch.addmm``, plain float32: a
-    split-TF32 evaluation through the library's tensor-core GEMMs was measured 3x faster but 3-8x less accurate - their
-    accumulation is not round-to-nearest - and fell outside the 1e-5 parity, profiles/r02_lstm_notes.txt),
+  * the input projection of all steps and both directions in ONE tcgen05 kernel with the recurrence's arithmetic
+    (``dic_lstm_project``: fp16 hi + lo operands split on the fly, float32 accumulation in TMEM; the float32 SIMT
+    library GEMM it replaces cost 2-4x the whole recurrence, and the library's TF32 tensor-core GEMMs are 3-8x less
+    accurate - their accumulation is not round-to-nearest - i.e. outside the 1e-5 parity, profiles/r02_lstm_notes.txt),
   * the recurrence of all R steps in ONE persistent sm_100a kernel (``dic_lstm_fwd``: 4-CTA clusters, W_hh resident
     in shared memory, h exchanged over distributed shared memory, tcgen05 MMAs on split-fp16 operands),
   * the backward recurrence with one fused gate-gradient kernel per step (``dic_lstm_bwd_step``) and library GEMMs
@@ -50,7 +51,13 @@ class _BiLSTM(torch.autograd.Function):
             perm = _perm_index(dev)
             wp = torch.cat([w_ih, w_ih_r], 0)[perm]                                   # (1024, I)
             bp = torch.cat([b_ih + b_hh, b_ih_r + b_hh_r], 0)[perm]
-            pre = torch.addmm(bp, x.reshape(R * B, I), wp.t())                        # (R*B, 1024), library GEMM
+            # the input projection of all steps and both directions: split-fp16 tcgen05 GEMM (dic_lstm_project)
+            wp, bp, x2 = wp.contiguous(), bp.contiguous(), x.reshape(R * B, I)
+            pw = torch.empty(int(L.dic_lstm_project_packed_bytes(I)), dtype=torch.uint8, device=dev)
+            _lib.check(L.dic_lstm_pack_wih(_lib.ptr(wp), _lib.ptr(pw), I, st), "dic_lstm_pack_wih")
+            pre = torch.empty((R * B, 8 * H), dtype=torch.float32, device=dev)
+            _lib.check(L.dic_lstm_project(_lib.ptr(x2), I, _lib.ptr(pw), _lib.ptr(bp), _lib.ptr(pre), R * B, I, 0, st),
+                       "dic_lstm_project")
             packed = torch.empty(int(L.dic_lstm_packed_bytes()), dtype=torch.uint8, device=dev)
             w_hh, w_hh_r = w_hh.contiguous(), w_hh_r.contiguous()
             _lib.check(L.dic_lstm_pack_whh(_lib.ptr(w_hh), _lib.ptr(w_hh_r), _lib.ptr(packed), st), "dic_lstm_pack_whh")

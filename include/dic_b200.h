@@ -322,6 +322,14 @@ int dic_dunn_minmax(const void* X, const int32_t* labels, double* out, int64_t N
  *   cell): da (B,512) = d a_t in gate order i|f|g|o, dc_rec (B,128) in/out; save_t (B,5,128) the step's saved row,
  *   c_prev (row stride c_prev_stride) the previous cell state or NULL (zeros), gh_out (row stride gh_stride) the upstream
  *   gradient of this direction's h_t or NULL, dh_rec (B,128) the recurrent gradient d a_(t+1) W_hh (a library GEMM). */
+/* dic_lstm_pack_wih / dic_lstm_project: the input projection pre (M,1024) = A (M,K) Wp^T + bias of all R*B rows on the
+ *   tensor cores with the recurrence's arithmetic (fp16 hi + lo operands, float32 accumulation in TMEM, K <= 1024):
+ *   Wp (1024,K) row-major in the column order dic_lstm_fwd expects; packed holds dic_lstm_project_packed_bytes(K) bytes;
+ *   A has row stride lda (elements); relu != 0 applies max(., 0) to A on the fly (DecoderRNN.forward, :38). */
+size_t dic_lstm_project_packed_bytes(int K);
+int dic_lstm_pack_wih(const float* wp, void* packed, int K, dic_stream_t stream);
+int dic_lstm_project(const float* A, int64_t lda, const void* packed, const float* bias, float* out, int64_t M, int K,
+                     int relu, dic_stream_t stream);
 size_t dic_lstm_packed_bytes(void);
 int dic_lstm_pack_whh(const float* w_hh, const float* w_hh_reverse, void* packed, dic_stream_t stream);
 int dic_lstm_fwd(const float* pre, const void* packed, const float* h0, const float* c0, float* out, float* hn,
