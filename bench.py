@@ -553,6 +553,11 @@ def device_arm(args, rank, world, local_rank):
     exec_ex2 = None
     if ncu_k and ncu_k.get("xu_warp_inst"):
         exec_ex2 = ncu_k["xu_warp_inst"] * 32.0 * (B / tr["encounters"])
+    elif ncu_k and ncu_k.get("xu_pipe_pct") and ncu_k.get("ncu_duration_us"):
+        # no absolute count in the export: XU-pipe utilisation of the capture (executed MUFU instructions per cycle over
+        # the pipe's peak) x the capture's duration = executed lane-operations at the probe's peak rate
+        ncu_ms = ncu_k["ncu_duration_us"] * (1.0 if ncu_k["ncu_duration_us"] < 1e3 else 1e-3)     # export unit: ms
+        exec_ex2 = ncu_k["xu_pipe_pct"] / 100.0 * mufu.value * (ncu_ms * 1e-3) * (B / tr["encounters"])
     roofline_sfu = {"kernel": dom, "bound": "sfu", "unit": "Gex2/s",
                     "achieved": round(exec_ex2 / 1e9 / (kms[dom] * 1e-3), 1) if exec_ex2 else None,
                     "peak": round(mufu.value / 1e9, 1),
