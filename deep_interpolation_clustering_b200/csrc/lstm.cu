@@ -23,6 +23,8 @@
 // product d h_(t-1) = d a_t W_hh and the weight gradients are library GEMMs on the saved tensors (host side).
 #include <cuda_fp16.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -348,6 +350,245 @@ lstm_fwd_kernel(const float* __restrict__ pre, const unsigned char* __restrict__
   }
 }
 
+// The same recurrence with TWO 128-encounter tiles per cluster, interleaved (dic_lstm_fwd takes this kernel when
+// B > 128).  The single-tile kernel above is a chain barrier -> MMA -> TMEM load -> MUFU-bound epilogue -> DSMEM stores ->
+// barrier with nothing to overlap (ncu: tensor pipe 5 % busy, issue slots 14 %, a cluster step 13.7 k clk against ~4 k
+// of epilogue work).  Here every half-step issues the MMAs of one tile and then runs the epilogue of the OTHER tile
+// underneath them:
+//     half-step hs (tile = hs & 1):  issue MMA(other, next step)  |  epilogue(tile): gates, h -> A[tile] of all 4 CTAs
+//                                    wait until MMA(other) has completed  ->  barrier.cluster
+//   * A[tile] is single buffered (2 x 64 KB: the shared-memory budget of the double-buffered single tile): its next
+//     writers are the epilogues of half-step hs, and every CTA has waited for ITS MMA on that tile before the barrier
+//     that ended half-step hs - 1, so no CTA's tensor core still reads what a fast peer overwrites;
+//   * the h slices written in half-step hs are consumed by the MMA issued in half-step hs + 1, after the barrier;
+//   * two 128-column TMEM accumulators, one mbarrier each;
+//   * pre of the next half-step is pulled into L2 with prefetch.global.L2 one half-step ahead (no registers), the
+//     register loads at the start of an epilogue then cost an L2 hit.
+struct Lstm2Smem {
+  static constexpr size_t w = 0;                          // [hi | lo] W_hh slice, 64 KB
+  static constexpr size_t a = w + 2 * (size_t)kTileB;     // [tile 0: hi | lo][tile 1: hi | lo], 128 KB
+  static constexpr size_t bars = a + 4 * (size_t)kTileB;
+  static constexpr size_t total = bars + 64;
+};
+
+__global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kThreads, 1)
+lstm_fwd2_kernel(const float* __restrict__ pre, const unsigned char* __restrict__ packed, const float* __restrict__ inv_scale,
+                 const float* __restrict__ h0, const float* __restrict__ c0, float* __restrict__ out,
+                 float* __restrict__ hn, float* __restrict__ cn, float* __restrict__ save, int R, int64_t B) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char* sw = smem + Lstm2Smem::w;
+  unsigned char* sa = smem + Lstm2Smem::a;
+  uint64_t* bar_w = reinterpret_cast<uint64_t*>(smem + Lstm2Smem::bars);
+  uint64_t* bar_acc = bar_w + 1;                   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_w + 3);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t q = cluster_ctarank();
+  const int64_t cluster_id = blockIdx.x / kCl;
+  const int dir = (int)(cluster_id & 1);
+  const int64_t b0 = (cluster_id >> 1) * (2 * kRows);
+  const int row = 32 * (warp & 3) + lane;
+  const int half = warp >> 2;
+  const int j0 = 32 * (int)q + 16 * half;
+  const int64_t bt[2] = {b0 + row, b0 + kRows + row};
+  const bool live[2] = {bt[0] < B, bt[1] < B};
+
+  if (tid == 0) {
+    mbar_init(bar_w, 1);
+    mbar_init(bar_acc, 1);
+    mbar_init(bar_acc + 1, 1);
+    fence_proxy_async();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 256);
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(bar_w, 2u * kTileB);
+    bulk_g2s(sw, packed + (size_t)(dir * kCl + q) * 2 * kTileB, 2u * kTileB, bar_w);
+  }
+  float c[2][16];
+#pragma unroll
+  for (int tl = 0; tl < 2; ++tl) {
+    const int k0 = 64 * half;
+    unsigned char* at = sa + (size_t)tl * 2 * kTileB;
+#pragma unroll
+    for (int cc = 0; cc < 8; ++cc) {
+      float x[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        x[i] = (h0 && live[tl]) ? __ldg(h0 + ((int64_t)dir * B + bt[tl]) * kH + k0 + cc * 8 + i) : 0.f;
+      uint4 hi, lo;
+      split8(x, hi, lo);
+      const size_t off = (size_t)(k0 / 8 + cc) * kLbo + (size_t)row * 16;
+      *reinterpret_cast<uint4*>(at + off) = hi;
+      *reinterpret_cast<uint4*>(at + kTileB + off) = lo;
+    }
+#pragma unroll
+    for (int u = 0; u < 16; ++u)
+      c[tl][u] = (c0 && live[tl]) ? __ldg(c0 + ((int64_t)dir * B + bt[tl]) * kH + j0 + u) : 0.f;
+  }
+  const float inv_s = __ldg(inv_scale + dir);
+  fence_proxy_async_cluster();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  mbar_wait(bar_w, 0);
+  cluster_arrive();
+  cluster_wait();
+
+  const uint32_t sa_u = smem_u32(sa), sw_u = smem_u32(sw);
+  uint32_t remote_a[kCl];
+#pragma unroll
+  for (int p = 0; p < kCl; ++p) remote_a[p] = map_to_cta(sa_u, (uint32_t)p);
+  const uint32_t my_chunk_off = (uint32_t)((4 * q + 2 * half) * kLbo + row * 16);
+
+  auto issue_mma = [&](int tl) {                     // h_(t-1) W_hh^T of tile tl -> accumulator tl (whole warp 0 calls)
+    fence_proxy_async();
+    tc_fence_after();
+    if (elect_one()) {
+      const uint32_t a_hi = sa_u + (uint32_t)tl * 2u * kTileB, a_lo = a_hi + kTileB;
+      const uint32_t d_tmem = tmem + (uint32_t)tl * 128u;
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {
+        const uint64_t dah = make_desc_kmajor(a_hi + ks * 2 * kLbo, kLbo, kSbo);
+        const uint64_t dal = make_desc_kmajor(a_lo + ks * 2 * kLbo, kLbo, kSbo);
+        const uint64_t dbh = make_desc_kmajor(sw_u + ks * 2 * kLbo, kLbo, kSbo);
+        const uint64_t dbl = make_desc_kmajor(sw_u + kTileB + ks * 2 * kLbo, kLbo, kSbo);
+        umma_f16(d_tmem, dah, dbh, kIdescF16, ks > 0 ? 1u : 0u);
+        umma_f16(d_tmem, dah, dbl, kIdescF16, 1u);
+        umma_f16(d_tmem, dal, dbh, kIdescF16, 1u);
+      }
+      umma_commit(bar_acc + tl);
+    }
+    __syncwarp();
+  };
+  auto pre_ptr = [&](int tl, int step) {
+    const int t = dir ? R - 1 - step : step;
+    return pre + ((int64_t)t * B + (live[tl] ? bt[tl] : 0)) * (2 * 4 * kH) + dir * 4 * kH + (int)q * 128 + 64 * half;
+  };
+
+  uint32_t phase[2] = {0u, 0u};
+  if (warp == 0) issue_mma(0);
+  mbar_wait(bar_acc, phase[0]);
+  phase[0] ^= 1u;
+  cluster_arrive();                                  // every CTA's first MMAs have read A[0] before its first overwrite
+  cluster_wait();
+  const int nhs = 2 * R;
+  auto half_step = [&](auto tile_c, int hs) {          // the tile is a compile-time constant: its state stays in registers
+    constexpr int tl = decltype(tile_c)::value, ot = tl ^ 1;
+    const int step = hs >> 1;
+    const int t = dir ? R - 1 - step : step;
+    float(&ct)[16] = c[tl];
+    // (a) the other tile's next MMAs run underneath this epilogue
+    const bool more = hs + 1 < nhs;
+    if (more && warp == 0) issue_mma(ot);
+    // this epilogue's input projection (L2 hit: prefetched one half-step ago), and the next one's prefetch
+    float4 pv[16];
+    {
+      const float4* src = reinterpret_cast<const float4*>(pre_ptr(tl, step));
+#pragma unroll
+      for (int i = 0; i < 16; ++i) pv[i] = live[tl] ? __ldg(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (more) {
+        const float* nx = pre_ptr(ot, (hs + 1) >> 1);
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + 32));
+      }
+    }
+    // (b) epilogue of tile tl (its accumulator was awaited at the end of the previous half-step)
+    tc_fence_after();
+    const float* pf = reinterpret_cast<const float*>(pv);
+    float* sp = (save && live[tl]) ? save + (((int64_t)dir * R + t) * B + bt[tl]) * (5 * kH) + j0 : nullptr;
+    float hh[16];
+#pragma unroll
+    for (int ps = 0; ps < 2; ++ps) {
+      uint32_t ai[8], af[8], ag[8], ao[8];
+      const uint32_t tcol = tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(128 * tl + 64 * half + 8 * ps);
+      tmem_ld8_issue(tcol, ai);
+      tmem_ld8_issue(tcol + 16u, af);
+      tmem_ld8_issue(tcol + 32u, ag);
+      tmem_ld8_issue(tcol + 48u, ao);
+      tmem_wait4x8(ai, af, ag, ao);
+      float gi[8], gf[8], gg[8], go[8];
+#pragma unroll
+      for (int v = 0; v < 8; ++v) {
+        const int u = 8 * ps + v;
+        gi[v] = sigmoid_acc(fmaf(__uint_as_float(ai[v]), inv_s, pf[u]));
+        gf[v] = sigmoid_acc(fmaf(__uint_as_float(af[v]), inv_s, pf[16 + u]));
+        gg[v] = tanh_acc(fmaf(__uint_as_float(ag[v]), inv_s, pf[32 + u]));
+        go[v] = sigmoid_acc(fmaf(__uint_as_float(ao[v]), inv_s, pf[48 + u]));
+        ct[u] = fmaf(gf[v], ct[u], gi[v] * gg[v]);
+        hh[u] = go[v] * tanh_acc(ct[u]);
+      }
+      if (sp) {
+        float4* s4 = reinterpret_cast<float4*>(sp + 8 * ps);
+        s4[0] = make_float4(gi[0], gi[1], gi[2], gi[3]);
+        s4[1] = make_float4(gi[4], gi[5], gi[6], gi[7]);
+        s4 = reinterpret_cast<float4*>(sp + kH + 8 * ps);
+        s4[0] = make_float4(gf[0], gf[1], gf[2], gf[3]);
+        s4[1] = make_float4(gf[4], gf[5], gf[6], gf[7]);
+        s4 = reinterpret_cast<float4*>(sp + 2 * kH + 8 * ps);
+        s4[0] = make_float4(gg[0], gg[1], gg[2], gg[3]);
+        s4[1] = make_float4(gg[4], gg[5], gg[6], gg[7]);
+        s4 = reinterpret_cast<float4*>(sp + 3 * kH + 8 * ps);
+        s4[0] = make_float4(go[0], go[1], go[2], go[3]);
+        s4[1] = make_float4(go[4], go[5], go[6], go[7]);
+        s4 = reinterpret_cast<float4*>(sp + 4 * kH + 8 * ps);
+        s4[0] = make_float4(ct[8 * ps], ct[8 * ps + 1], ct[8 * ps + 2], ct[8 * ps + 3]);
+        s4[1] = make_float4(ct[8 * ps + 4], ct[8 * ps + 5], ct[8 * ps + 6], ct[8 * ps + 7]);
+      }
+    }
+    tc_fence_before();
+    {   // h_t -> A[tile] of all four CTAs
+      uint4 hi0, lo0, hi1, lo1;
+      const float(&x0)[8] = *reinterpret_cast<const float(*)[8]>(&hh[0]);
+      const float(&x1)[8] = *reinterpret_cast<const float(*)[8]>(&hh[8]);
+      split8(x0, hi0, lo0);
+      split8(x1, hi1, lo1);
+      const uint32_t nb = (uint32_t)tl * 2u * kTileB + my_chunk_off;
+#pragma unroll
+      for (int p = 0; p < kCl; ++p) {
+        const uint32_t base = remote_a[p] + nb;
+        st_cluster_v4(base, hi0);
+        st_cluster_v4(base + kLbo, hi1);
+        st_cluster_v4(base + kTileB, lo0);
+        st_cluster_v4(base + kTileB + kLbo, lo1);
+      }
+    }
+    // (c) my MMAs on the other tile are complete before anybody may overwrite its A operand (next half-step)
+    if (more) {
+      mbar_wait(bar_acc + ot, phase[ot]);
+      phase[ot] ^= 1u;
+    }
+    fence_proxy_async_cluster();
+    cluster_arrive();
+    if (live[tl]) {
+      float4* o4 = reinterpret_cast<float4*>(out + ((int64_t)t * B + bt[tl]) * (2 * kH) + dir * kH + j0);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) o4[i] = make_float4(hh[4 * i], hh[4 * i + 1], hh[4 * i + 2], hh[4 * i + 3]);
+      if (step == R - 1) {
+        float* hp = hn + ((int64_t)dir * B + bt[tl]) * kH + j0;
+        float* cp = cn + ((int64_t)dir * B + bt[tl]) * kH + j0;
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          hp[u] = hh[u];
+          cp[u] = ct[u];
+        }
+      }
+    }
+    __syncwarp();
+    cluster_wait();
+  };
+  for (int step = 0; step < R; ++step) {
+    half_step(std::integral_constant<int, 0>{}, 2 * step);
+    half_step(std::integral_constant<int, 1>{}, 2 * step + 1);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 256);
+  }
+}
+
 // One step of the backward recurrence, all gate algebra fused (thread = (encounter, hidden unit)):
 //   d h = gh_out[t] + dh_rec;  d o = d h tanh(c);  d c = d h o (1 - tanh(c)^2) + dc_rec
 //   d a = [ d c g i (1 - i) | d c c_prev f (1 - f) | d c i (1 - g^2) | d o o (1 - o) ];  dc_rec <- d c f
@@ -575,6 +816,14 @@ extern "C" int dic_lstm_fwd(const float* pre, const void* packed, const float* h
   DIC_REQUIRE(tiles * 2 * kCl <= 2147483647LL, DIC_ERR_UNSUPPORTED, "B=%lld exceeds the grid limit", (long long)B);
   const unsigned char* p = static_cast<const unsigned char*>(packed);
   const float* inv_scale = reinterpret_cast<const float*>(p + (size_t)2 * kCl * 2 * kTileB);
+  if (B > kRows) {       // two interleaved 128-encounter tiles per cluster
+    const int64_t pairs = (B + 2 * kRows - 1) / (2 * kRows);
+    DIC_CUDA(cudaFuncSetAttribute(lstm_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Lstm2Smem::total));
+    lstm_fwd2_kernel<<<(unsigned)(pairs * 2 * kCl), kThreads, Lstm2Smem::total, as_stream(stream)>>>(
+        pre, p, inv_scale, h0, c0, out, hn, cn, save, R, B);
+    DIC_LAUNCH_CHECK("lstm_fwd2_kernel");
+    return DIC_OK;
+  }
   DIC_CUDA(cudaFuncSetAttribute(lstm_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LstmSmem::total));
   lstm_fwd_kernel<<<(unsigned)(tiles * 2 * kCl), kThreads, LstmSmem::total, as_stream(stream)>>>(
       pre, p, inv_scale, h0, c0, out, hn, cn, save, R, B);

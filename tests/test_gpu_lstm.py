@@ -25,11 +25,15 @@ def _reference(lstm_b200, x, hx, g_out, g_hn, g_cn):
 
 def _check(name, got, want, rtol=1e-5):
     want = want.detach().numpy()
+    if not np.any(want):            # e.g. d weight_hh of a one-step sequence without an initial state: exactly zero
+        assert not np.any(got.detach().cpu().numpy()), f"{name}: expected exact zeros"
+        return None
     return record(name, got.detach().cpu().numpy(), want, rtol, scale_atol(want, rtol))
 
 
 @pytest.mark.parametrize("R,B,I,with_state", [(5, 7, 18, False), (12, 130, 18, False), (9, 300, 256, True),
-                                               (96, 257, 18, False), (48, 64, 256, True)])
+                                               (96, 257, 18, False), (48, 64, 256, True), (1, 1, 18, False),
+                                               (2, 129, 256, True), (3, 128, 100, True)])
 def test_bilstm_matches_torch_float64(R, B, I, with_state):
     from deep_interpolation_clustering_b200.lstm import BiLSTMB200
     torch.manual_seed(R * 1000 + B)
