@@ -1,35 +1,30 @@
-// One Lloyd pass with the E-step on the tensor cores (tcgen05 + TMEM): float32 rows of 64 / 128 / 256 elements,
-// K <= 16.  sklearn/cluster/_k_means_lloyd.pyx:23-218 (E-step: argmin_j ||c_j||^2 - 2 x.c_j, lowest index on ties;
-// accumulation of the per-cluster sums and counts for the M-step).
+// One Lloyd pass with the E-step on the tensor cores (tcgen05 + TMEM), fed by 2-D tensor-map TMA: float32 rows of
+// 64 / 128 / 256 elements, K <= 16.  sklearn/cluster/_k_means_lloyd.pyx:23-218 (E-step: argmin_j ||c_j||^2 - 2 x.c_j,
+// lowest index on ties; accumulation of the per-cluster sums and counts for the M-step).
 //
-// Why: the CUDA-core kernels (kmeans.cu) pay one shared-memory broadcast operand per FMA - K*D operands per row -
-// and sit at 0.1-0.4 of the HBM roofline (ncu: issue / LSU bound).  D x K >= 64 x 8 is a genuine dense contraction
-// (north_star), so the x.c products move to tcgen05.mma and the CUDA cores keep only what is not a contraction:
-// operand conversion, the arg-min and the per-cluster accumulation.
+// Why: the CUDA-core kernels (kmeans.cu) pay one shared-memory broadcast operand per FMA - K*D operands per row - and
+// sit at 0.1-0.4 of the HBM roofline (ncu: bound by their instruction count).  D x K >= 64 x 8 is a genuine dense
+// contraction (north_star), so the x.c products move to tcgen05.mma and the CUDA cores keep only what is not a
+// contraction: the low-order operand halves, the arg-min and the per-cluster accumulation.
 //
-// Structure (one persistent CTA per SM: TMA producer warp | 4 converter warps | 4 epilogue warps):
-//   * work unit ("job") = 128 rows x 64 floats (32 KB), brought in by the producer warp with TMA bulk copies (ONE
-//     copy per job when D = 64: the rows of a tile are contiguous; 128 row copies otherwise) into a slot ring;
-//   * conversion: every float is split into hi = rna_tf32(x), lo = rna_tf32(x - hi) and written as the two operand
-//     tiles in the canonical no-swizzle K-major UMMA layout; the K-chunk stride is 128 x 16 + 16 bytes, which makes
-//     both the row-major reads and the chunk-major writes of a warp bank-conflict free;
-//   * 3 MMAs per K step (kind::tf32, M = 128, N = 16, K = 8): hi.hi + hi.lo + lo.hi accumulate float32-grade dot
-//     products in 16 TMEM columns (the dropped lo.lo term is < 2^-22 |x||c|);
-//   * epilogue: thread = row reads its 16 dots with tcgen05.ld, d_j = ||c_j||^2 - 2 x.c_j, strict '<' arg-min;
-//   * accumulation (M-step sums): thread = (row group, 16-byte column) adds x into sacc[copy][label][column] in
-//     shared memory - the label is an address, no atomics, fixed order (deterministic); wide rows are re-read from
-//     L2 once the labels are known, with 8 / (D / 64) private accumulator copies used in rounds;
-//   * the epilogue of tile t overlaps the conversion and the MMAs of tile t + 1 (two TMEM accumulators).
-// Only the Lloyd-loop form of the pass (DIC_KM_NO_INERTIA, labels re-assigned) takes this kernel; the final
-// labelling pass with its direct ||x - c||^2 sums stays on the CUDA-core kernels.
-//
-// Measured (B200, 1M x 64, profiles/r02_kmeans_tc_*.txt): 0.145 ms per pass for every K <= 16 (the contraction itself
-// is free) against 0.097 (K = 4) ... 0.148 ms (K = 16) of the specialised CUDA-core kernel, i.e. no win yet.  Phase
-// probes: an empty pipeline (TMA + hand-offs + arg-min) runs at 0.053 ms = 4.8 TB/s; the 24 MMAs of a tile issued by
-// one thread cost ~3.2 k clk (an operand-descriptor waterfall per UTCHMMA - the MMA warp must run in uniform control
-// flow as in pairwise_tc.cu), the tf32 split ~3.4 k clk (cvt.rna.tf32 is 4 ALU instructions; 4 warps) and the
-// accumulation ~2.1 k clk per tile, against 1.5 k clk of HBM time per tile.  The kernel is therefore selectable
-// (DIC_KM_KERNEL(5), parity-tested) but not dispatched by default.
+// Version 2 (round 2).  Version 1 converted every tile to split-tf32 operand tiles on the CUDA cores (8 instructions per
+// element) into ONE operand buffer and issued the MMAs from a single thread: conversion, MMA issue and accumulation ran
+// in series, 0.145 ms per pass at 1M x 64 against 0.097-0.148 ms of the CUDA-core kernel.  Here
+//   * the rows arrive by cp.async.bulk.tensor.2d (SASS UTMALDG) through a tensor map with 128-byte swizzle, 128 rows x
+//     32 floats (16 KB) per copy, i.e. ALREADY in the K-major SWIZZLE_128B layout tcgen05.mma reads: the raw float32
+//     tile IS the high operand (kind::tf32 ignores the 13 low significand bits: hi = trunc_tf32(x), no instruction);
+//   * the low operand is lo = x - trunc_tf32(x) (exact), rounded to tf32 by an integer add of half an ulp: three
+//     instructions per element, position-identical copy (linear, bank-conflict free) into a two-unit ring;
+//   * hi.c_hi + hi.c_lo + lo.c_hi accumulate float32-grade dot products in 16 TMEM columns (error of a product
+//     < 2^-21 |x||c|, unbiased); the MMA warp runs in uniform control flow with only the tcgen05 instructions elected;
+//   * arg-min (4 warps, thread = row, tcgen05.ld) and the M-step accumulation (8 warps, warp = row group, lane = 8
+//     bytes of the row, the label is an address: no atomics, fixed order, deterministic) are separate pipeline stages
+//     linked by mbarriers, and the M-step reads the rows from the same resident raw units (all widths: no L2 re-read).
+// One persistent CTA per SM, 18 warps: TMA producer | MMA issuer | 4 low-half warps | 4 arg-min warps | 8 M-step warps.
+// Only the Lloyd-loop form of the pass (DIC_KM_NO_INERTIA, labels re-assigned) takes this kernel; the final labelling
+// pass with its direct ||x - c||^2 sums stays on the CUDA-core kernels.
+#include <cuda.h>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -38,40 +33,42 @@ namespace {
 
 using namespace tc;
 
-constexpr int kRows = 128;
-constexpr int kSlotB = kRows * 256;            // one job: 128 rows x 64 floats
-constexpr int kLboA = kRows * 16 + 16;         // bytes between consecutive 16-byte K chunks of an A operand tile
-constexpr int kATileB = 16 * kLboA;            // hi or lo tile of one job (16 K chunks)
-constexpr int kLboB = 16 * 16;                 // centres: 16 rows x 16 bytes per K chunk
+constexpr int kRows = 128;                     // rows per tile (M of the MMA)
+constexpr int kUnitB = kRows * 128;            // one ring unit: 128 rows x 32 floats, SWIZZLE_128B K-major (16 KB)
+constexpr int kMaxUnits = 12;
+constexpr int kLboB = 16 * 16;                 // centres: 16 rows x 16 bytes per K chunk (no swizzle)
 constexpr int kBTileB = 16 * kLboB;            // hi or lo centre tile of one 64-wide K chunk
-constexpr int kSbo = 128;                      // bytes between 8-row groups
-constexpr int kRole = 128;                     // threads per role (converters, epilogue)
-constexpr int kTcThreads = 32 + 2 * kRole;     // producer warp | 4 converter warps | 4 epilogue warps
+constexpr int kSbo = 128;                      // bytes between 8-row groups of the centre tiles
+constexpr int kNLo = 4, kNArg = 4, kNAcc = 8;  // warps per role
+constexpr int kTcThreads = 32 * (2 + kNLo + kNArg + kNAcc);
 constexpr uint32_t kIdescTf32N16 = make_idesc(2u, 128u, 16u);
 
 struct TcBars {
-  uint64_t full[3], slot_free[3], a_free, acc_full[2], acc_free[2];
+  uint64_t full[kMaxUnits], slot_free[kMaxUnits];
+  uint64_t lo_full[2], lo_free[2], acc_full[2], acc_free[2], lab_full[2], lab_free[2];
   uint32_t tmem_base;
   int timeout;
 };
 
-template <int NCH>
-struct TcLayout {
-  static constexpr int D = 64 * NCH;
-  static constexpr int G = 8 / NCH;             // private accumulator copies
-  static constexpr int NSLOT = NCH == 1 ? 3 : 2;
-  static constexpr size_t slots = 0;
-  static constexpr size_t a_hi = slots + NSLOT * (size_t)kSlotB;
-  static constexpr size_t a_lo = a_hi + kATileB;
-  static constexpr size_t b_hi = a_lo + kATileB;
-  static constexpr size_t b_lo = b_hi + (size_t)NCH * kBTileB;
-  static constexpr size_t sacc = b_lo + (size_t)NCH * kBTileB;          // [G][16][D] floats (K <= 16)
-  static constexpr size_t scn = sacc + (size_t)G * 16 * D * 4;          // [16] floats
-  static constexpr size_t scnt = scn + 64;                              // [8][16] ints
-  static constexpr size_t slab = scnt + 8 * 16 * 4;                     // [128] ints
-  static constexpr size_t bars = slab + kRows * 4;
-  static constexpr size_t total = bars + sizeof(TcBars) + 16;
+// Shared-memory plan (offsets from the 1024-byte aligned base); `nu` ring units.
+struct TcPlan {
+  int nu;
+  size_t lo, b_hi, b_lo, sacc, scn, scnt, slab, bars, total;
 };
+__host__ __device__ inline TcPlan tc_plan(int NCH, int K, int nu) {
+  TcPlan p;
+  p.nu = nu;
+  p.lo = (size_t)nu * kUnitB;
+  p.b_hi = p.lo + 2 * (size_t)kUnitB;
+  p.b_lo = p.b_hi + (size_t)NCH * kBTileB;
+  p.sacc = p.b_lo + (size_t)NCH * kBTileB;                    // [G][K][D] floats, G * NCH = 8
+  p.scn = p.sacc + (size_t)8 * K * 64 * 4;
+  p.scnt = p.scn + 64;                                        // [8][16] ints
+  p.slab = p.scnt + 8 * 16 * 4;                               // [2][128] ints
+  p.bars = p.slab + 2 * kRows * 4;
+  p.total = p.bars + sizeof(TcBars) + 1024;                   // + alignment slack
+  return p;
+}
 
 __device__ __forceinline__ bool wait_bar(TcBars* B, uint64_t* bar, uint32_t phase) {
   if (*reinterpret_cast<volatile int*>(&B->timeout)) return false;
@@ -80,47 +77,77 @@ __device__ __forceinline__ bool wait_bar(TcBars* B, uint64_t* bar, uint32_t phas
   return false;
 }
 
+// K-major SWIZZLE_128B operand (cute::UMMA::SmemDescriptor): start >> 4 | LBO (unused for swizzled K-major) = 1 |
+// SBO = 1024 bytes between 8-row groups | version 1 | layout type 2 at [61,64).
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) |
+         (2ull << 61);
+}
+
+__device__ __forceinline__ void tma_load_2d(void* dst_smem, const CUtensorMap* tmap, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(smem_u32(dst_smem)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+
+__device__ __forceinline__ float lo_tf32(float x) {
+  // x - trunc_tf32(x) is exact; + 0x1000 on the bit pattern = round to nearest (ties away) once the tensor core drops
+  // the 13 low bits of the operand
+  const float lo = x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+  return __uint_as_float(__float_as_uint(lo) + 0x1000u);
+}
+
 __device__ __forceinline__ void split_tf32(const float4& x, float4& h, float4& l) {
   h.x = to_tf32(x.x); h.y = to_tf32(x.y); h.z = to_tf32(x.z); h.w = to_tf32(x.w);
   l.x = to_tf32(x.x - h.x); l.y = to_tf32(x.y - h.y); l.z = to_tf32(x.z - h.z); l.w = to_tf32(x.w - h.w);
 }
 
-// Warp-specialised pipeline, one persistent CTA per SM:
-//   warp 0      producer: TMA bulk copies of the jobs (128 rows x 64 floats) into the slot ring
-//   warps 1-4   converters: slot -> split tf32 operand tiles; their thread 0 issues the 24 MMAs of the job
-//   warps 5-8   epilogue: tcgen05.ld of tile t's 16 dots per row, arg-min, labels, per-cluster accumulation - while
-//               the converters and the tensor core work on tile t + 1 (two TMEM accumulators of 16 columns)
+// Ring position of the i-th unit this CTA handles.
+struct RingPos {
+  int slot;
+  uint32_t phase;
+  __device__ __forceinline__ void advance(int nu) {
+    if (++slot == nu) {
+      slot = 0;
+      phase ^= 1u;
+    }
+  }
+};
+
 template <int NCH>
 __global__ void __launch_bounds__(kTcThreads, 1)
-kmeans_assign_tc_kernel(const float* __restrict__ X, const float* __restrict__ centers, int32_t* labels,
-                        double* __restrict__ ws, int64_t N, int K, int flags, int want_sums,
+kmeans_assign_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ centers, int32_t* labels,
+                        double* __restrict__ ws, int64_t N, int K, int flags, int want_sums, int nu,
                         const double* __restrict__ done) {
   if (done && *done != 0.0) return;
-  using L = TcLayout<NCH>;
-  constexpr int D = L::D, G = L::G, ROUNDS = NCH, NSLOT = L::NSLOT;
-  extern __shared__ __align__(128) unsigned char smem[];
-  unsigned char* slots = smem + L::slots;
-  unsigned char* a_hi = smem + L::a_hi;
-  unsigned char* a_lo = smem + L::a_lo;
-  unsigned char* b_hi = smem + L::b_hi;
-  unsigned char* b_lo = smem + L::b_lo;
-  float* sacc = reinterpret_cast<float*>(smem + L::sacc);
-  float* scn = reinterpret_cast<float*>(smem + L::scn);
-  int* scnt = reinterpret_cast<int*>(smem + L::scnt);
-  int* slab = reinterpret_cast<int*>(smem + L::slab);
-  TcBars* B = reinterpret_cast<TcBars*>(smem + L::bars);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const bool m_from_slot = NCH == 1 && want_sums;      // the epilogue reads the rows of a one-job tile from its slot
+  constexpr int D = 64 * NCH, G = 8 / NCH, UPT = 2 * NCH;     // units per tile
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const TcPlan P = tc_plan(NCH, K, nu);
+  unsigned char* units = smem;
+  unsigned char* lo_buf = smem + P.lo;
+  unsigned char* b_hi = smem + P.b_hi;
+  unsigned char* b_lo = smem + P.b_lo;
+  float* sacc = reinterpret_cast<float*>(smem + P.sacc);
+  float* scn = reinterpret_cast<float*>(smem + P.scn);
+  int* scnt = reinterpret_cast<int*>(smem + P.scnt);
+  int* slab = reinterpret_cast<int*>(smem + P.slab);
+  TcBars* B = reinterpret_cast<TcBars*>(smem + P.bars);
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
 
   if (tid == 0) {
-    for (int s = 0; s < 3; ++s) {
+    for (int s = 0; s < kMaxUnits; ++s) {
       mbar_init(&B->full[s], 1);
-      mbar_init(&B->slot_free[s], m_from_slot ? 2 : 1);      // converters (+ epilogue) are done with the slot
+      mbar_init(&B->slot_free[s], 1 + (want_sums ? G : 0));    // MMAs done (+ the M-step warps of the unit's chunk)
     }
-    mbar_init(&B->a_free, 1);
     for (int k = 0; k < 2; ++k) {
+      mbar_init(&B->lo_full[k], kNLo);
+      mbar_init(&B->lo_free[k], 1);
       mbar_init(&B->acc_full[k], 1);
-      mbar_init(&B->acc_free[k], 4);                           // one arrival per epilogue warp
+      mbar_init(&B->acc_free[k], kNArg);
+      mbar_init(&B->lab_full[k], kNArg);
+      mbar_init(&B->lab_free[k], kNAcc);
     }
     B->timeout = 0;
     fence_proxy_async();
@@ -137,7 +164,7 @@ kmeans_assign_tc_kernel(const float* __restrict__ X, const float* __restrict__ c
     *reinterpret_cast<float4*>(b_lo + off) = l;
   }
   if (want_sums)
-    for (int i = tid; i < G * 16 * D; i += kTcThreads) sacc[i] = 0.f;
+    for (int i = tid; i < 8 * K * 64; i += kTcThreads) sacc[i] = 0.f;
   for (int i = tid; i < 8 * 16; i += kTcThreads) scnt[i] = 0;
   if (tid < 16) {
     float sum = 0.f;
@@ -158,87 +185,107 @@ kmeans_assign_tc_kernel(const float* __restrict__ X, const float* __restrict__ c
   int changed = 0;
 
   if (warp == 0) {
-    // ================= producer =================
-    int64_t j = 0;
-    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-      const int rows = (int)min((int64_t)kRows, N - t * kRows);
-      for (int ch = 0; ch < NCH; ++ch, ++j) {
-        const int slot = (int)(j % NSLOT);
-        const uint32_t use = (uint32_t)(j / NSLOT);
-        const bool ok = wait_bar(B, &B->slot_free[slot], (use & 1u) ^ 1u);
-        if (!__all_sync(0xffffffffu, ok)) break;
-        unsigned char* dst = slots + (size_t)slot * kSlotB;
-        if (lane == 0) mbar_expect_tx(&B->full[slot], (uint32_t)rows * 256u);
-        __syncwarp();
-        if (NCH == 1) {
-          if (lane == 0) bulk_g2s(dst, X + (size_t)t * kRows * D, (uint32_t)rows * 256u, &B->full[slot]);
-        } else {
-          for (int r = lane; r < rows; r += 32)
-            bulk_g2s(dst + r * 256, X + ((size_t)t * kRows + r) * D + ch * 64, 256u, &B->full[slot]);
+    // ================= producer: one tensor-map copy per unit =================
+    RingPos rp{0, 0u};
+    bool ok = true;
+    for (int64_t t = blockIdx.x; t < ntiles && ok; t += gridDim.x) {
+      for (int u = 0; u < UPT; ++u) {
+        ok = __all_sync(0xffffffffu, wait_bar(B, &B->slot_free[rp.slot], rp.phase ^ 1u));
+        if (!ok) break;
+        if (elect_one()) {
+          mbar_expect_tx(&B->full[rp.slot], (uint32_t)kUnitB);
+          tma_load_2d(units + (size_t)rp.slot * kUnitB, &tmap, u * 32, (int)(t * kRows), &B->full[rp.slot]);
         }
+        rp.advance(nu);
       }
     }
-  } else if (warp <= 4) {
-    // ================= converters + MMA issue =================
-    const int ct = tid - 32;
-    const uint32_t a_hi_u = smem_u32(a_hi), a_lo_u = smem_u32(a_lo), b_hi_u = smem_u32(b_hi), b_lo_u = smem_u32(b_lo);
-    int64_t j = 0, tl = 0;                     // job and tile counters of this CTA
-    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++tl) {
-      const int buf = (int)(tl & 1);
-      for (int ch = 0; ch < NCH; ++ch, ++j) {
-        const int slot = (int)(j % NSLOT);
-        wait_bar(B, &B->full[slot], (uint32_t)(j / NSLOT) & 1u);
-        if (j > 0) wait_bar(B, &B->a_free, (uint32_t)(j - 1) & 1u);      // the MMAs of the previous job have read A
-        const float* sx = reinterpret_cast<const float*>(slots + (size_t)slot * kSlotB);
-#pragma unroll 4
-        for (int it = 0; it < 16; ++it) {
-          const int item = it * kRole + ct;
-          const int row = item >> 4, c = item & 15;        // lanes 0-15: one row's 16 chunks; 16-31: the next row
-          const float4 x = *reinterpret_cast<const float4*>(sx + row * 64 + c * 4);
-          float4 h, l;
-          split_tf32(x, h, l);
-          const int off = c * kLboA + row * 16;
-          *reinterpret_cast<float4*>(a_hi + off) = h;
-          *reinterpret_cast<float4*>(a_lo + off) = l;
-        }
-        fence_proxy_async();               // generic-proxy stores -> visible to the tensor core (async proxy)
-        named_bar_sync(1, kRole);
-        if (ct == 0) {
-          mbar_arrive(&B->slot_free[slot]);                                 // the converters are done with the slot
-          if (ch == 0 && tl >= 2) wait_bar(B, &B->acc_free[buf], (uint32_t)((tl >> 1) - 1) & 1u);   // accumulator drained
-          tc_fence_after();
-          const uint32_t d_tmem = tmem + (uint32_t)buf * 16u;
+  } else if (warp == 1) {
+    // ================= MMA issuer (whole warp in uniform control flow, tcgen05 under elect) =================
+    const uint32_t tmem_u = __reduce_or_sync(0xffffffffu, tmem);
+    const uint32_t units_u = smem_u32(units), lo_u = smem_u32(lo_buf), b_hi_u = smem_u32(b_hi), b_lo_u = smem_u32(b_lo);
+    RingPos rp{0, 0u};
+    uint32_t v = 0;                                 // unit counter (low-half ring)
+    int64_t tl = 0;
+    bool ok = true;
+    for (int64_t t = blockIdx.x; t < ntiles && ok; t += gridDim.x, ++tl) {
+      const uint32_t buf = (uint32_t)(tl & 1);
+      const uint32_t d_tmem = tmem_u + buf * 16u;
+      for (int u = 0; u < UPT && ok; ++u, ++v) {
+        const uint32_t lb = v & 1u;
+        ok = __all_sync(0xffffffffu, wait_bar(B, &B->full[rp.slot], rp.phase));
+        ok = ok && __all_sync(0xffffffffu, wait_bar(B, &B->lo_full[lb], (v >> 1) & 1u));
+        if (u == 0) ok = ok && __all_sync(0xffffffffu, wait_bar(B, &B->acc_free[buf], ((uint32_t)(tl >> 1) & 1u) ^ 1u));
+        if (!ok) break;
+        tc_fence_after();
+        const uint32_t a_hi = units_u + (uint32_t)rp.slot * (uint32_t)kUnitB;
+        const uint32_t a_lo = lo_u + lb * (uint32_t)kUnitB;
+        const uint32_t bo = (uint32_t)((u >> 1) * kBTileB + (u & 1) * 8 * kLboB);
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks) {       // one MMA consumes K = 8 tf32 = two 16-byte chunks
-            const uint64_t dah = make_desc_kmajor(a_hi_u + ks * 2 * kLboA, kLboA, kSbo);
-            const uint64_t dal = make_desc_kmajor(a_lo_u + ks * 2 * kLboA, kLboA, kSbo);
-            const uint64_t dbh = make_desc_kmajor(b_hi_u + ch * kBTileB + ks * 2 * kLboB, kLboB, kSbo);
-            const uint64_t dbl = make_desc_kmajor(b_lo_u + ch * kBTileB + ks * 2 * kLboB, kLboB, kSbo);
-            umma_tf32(d_tmem, dah, dbh, kIdescTf32N16, (ch > 0 || ks > 0) ? 1u : 0u);
+        for (int ks = 0; ks < 4; ++ks) {          // one MMA consumes K = 8 tf32 = 32 bytes of every row
+          const uint64_t dah = make_desc_sw128(a_hi + ks * 32);
+          const uint64_t dal = make_desc_sw128(a_lo + ks * 32);
+          const uint64_t dbh = make_desc_kmajor(b_hi_u + bo + ks * 2 * kLboB, kLboB, kSbo);
+          const uint64_t dbl = make_desc_kmajor(b_lo_u + bo + ks * 2 * kLboB, kLboB, kSbo);
+          if (elect_one()) {
+            umma_tf32(d_tmem, dah, dbh, kIdescTf32N16, (u > 0 || ks > 0) ? 1u : 0u);
             umma_tf32(d_tmem, dah, dbl, kIdescTf32N16, 1u);
             umma_tf32(d_tmem, dal, dbh, kIdescTf32N16, 1u);
           }
-          umma_commit(&B->a_free);                           // operand tiles reusable once these MMAs have read them
-          if (ch == NCH - 1) umma_commit(&B->acc_full[buf]); // the tile's 16 dots per row are complete
         }
+        if (elect_one()) {
+          umma_commit(&B->lo_free[lb]);                         // the low-half unit is reusable
+          umma_commit(&B->slot_free[rp.slot]);                  // the MMAs have read the raw unit
+          if (u == UPT - 1) umma_commit(&B->acc_full[buf]);     // the tile's 16 dots per row are complete
+        }
+        __syncwarp();
+        rp.advance(nu);
       }
     }
-  } else {
-    // ================= epilogue: arg-min, labels, per-cluster accumulation =================
-    const int et = tid - 32 - kRole;                  // 0..127
-    const int row = 32 * (warp & 3) + lane;           // TMEM lane quarter of this warp = warp % 4
-    const int g8 = et >> 4, col = et & 15;
+  } else if (warp < 2 + kNLo) {
+    // ================= low operand halves: lo = rn_tf32(x - trunc_tf32(x)), same position as x =================
+    const int ct = tid - 64;
+    RingPos rp{0, 0u};
+    uint32_t v = 0;
+    bool ok = true;
+    for (int64_t t = blockIdx.x; t < ntiles && ok; t += gridDim.x) {
+      for (int u = 0; u < UPT; ++u, ++v) {
+        const uint32_t lb = v & 1u;
+        ok = wait_bar(B, &B->full[rp.slot], rp.phase) && wait_bar(B, &B->lo_free[lb], ((v >> 1) & 1u) ^ 1u);
+        ok = __all_sync(0xffffffffu, ok);
+        if (!ok) break;
+        const float4* src = reinterpret_cast<const float4*>(units + (size_t)rp.slot * kUnitB);
+        float4* dst = reinterpret_cast<float4*>(lo_buf + (size_t)lb * kUnitB);
+#pragma unroll
+        for (int it = 0; it < kUnitB / 16 / (32 * kNLo); ++it) {
+          const float4 x = src[it * 32 * kNLo + ct];
+          float4 l;
+          l.x = lo_tf32(x.x); l.y = lo_tf32(x.y); l.z = lo_tf32(x.z); l.w = lo_tf32(x.w);
+          dst[it * 32 * kNLo + ct] = l;
+        }
+        fence_proxy_async();               // generic-proxy stores -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&B->lo_full[lb]);
+        rp.advance(nu);
+      }
+    }
+  } else if (warp < 2 + kNLo + kNArg) {
+    // ================= arg-min: thread = row =================
+    const int q = warp & 3;                           // TMEM lane quarter this warp may read
+    const int row = 32 * q + lane;
     int64_t tl = 0;
-    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++tl) {
-      const int buf = (int)(tl & 1);
+    bool ok = true;
+    for (int64_t t = blockIdx.x; t < ntiles && ok; t += gridDim.x, ++tl) {
+      const uint32_t buf = (uint32_t)(tl & 1);
+      const uint32_t ph = (uint32_t)(tl >> 1) & 1u;
       const int64_t row0 = t * kRows;
       const int rows = (int)min((int64_t)kRows, N - row0);
       int oldl = -1;
       if (count_changes && row < rows) oldl = labels[row0 + row];
-      wait_bar(B, &B->acc_full[buf], (uint32_t)(tl >> 1) & 1u);
+      ok = __all_sync(0xffffffffu, wait_bar(B, &B->acc_full[buf], ph));
+      if (!ok) break;
       tc_fence_after();
       uint32_t v[16];
-      tmem_ld16(tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)buf * 16u, v);
+      tmem_ld16(tmem + ((uint32_t)(32 * q) << 16) + buf * 16u, v);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&B->acc_free[buf]);           // this warp has its dots in registers
@@ -257,34 +304,63 @@ kmeans_assign_tc_kernel(const float* __restrict__ X, const float* __restrict__ c
         labels[row0 + row] = best;
       }
       if (want_sums) {
-        slab[row] = best;
-        named_bar_sync(2, kRole);                              // the labels of the tile are visible to the epilogue warps
-        const int slot = (int)(tl % NSLOT);                    // NCH == 1: tile t of this CTA is job t
-        if (NCH == 1) wait_bar(B, &B->full[slot], (uint32_t)(tl / NSLOT) & 1u);      // (long complete: acquire only)
-        const float4* sx4 = reinterpret_cast<const float4*>(slots + (size_t)slot * kSlotB);
+        ok = __all_sync(0xffffffffu, wait_bar(B, &B->lab_free[buf], ph ^ 1u));
+        if (!ok) break;
+        slab[buf * kRows + row] = best;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&B->lab_full[buf]);
+      }
+    }
+  } else if (want_sums) {
+    // ================= M-step accumulation: warp = (row group g, chunk ch), lane = 8 bytes of the chunk =================
+    const int w = warp - (2 + kNLo + kNArg);
+    const int g = w % G, ch = w / G;
+    const int hf = lane >> 4, c = (lane & 15) >> 1, sub = lane & 1;
+    int* cnt = scnt + w * 16;
+    int64_t tl = 0;
+    bool ok = true;
+    for (int64_t t = blockIdx.x; t < ntiles && ok; t += gridDim.x, ++tl) {
+      const uint32_t buf = (uint32_t)(tl & 1);
+      const int rows = (int)min((int64_t)kRows, N - t * kRows);
+      // ring positions of this warp's two units of the tile (halves of chunk ch)
+      const int64_t u0 = tl * UPT + 2 * ch;
+      const int s0 = (int)(u0 % nu), s1 = (int)((u0 + 1) % nu);
+      const uint32_t p0 = (uint32_t)(u0 / nu) & 1u, p1 = (uint32_t)((u0 + 1) / nu) & 1u;
+      ok = wait_bar(B, &B->lab_full[buf], (uint32_t)(tl >> 1) & 1u) && wait_bar(B, &B->full[s0], p0) &&
+           wait_bar(B, &B->full[s1], p1);                      // (the units are long complete: acquire only)
+      ok = __all_sync(0xffffffffu, ok);
+      if (!ok) break;
+      const unsigned char* ub = units + (size_t)(hf ? s1 : s0) * kUnitB + sub * 8;
+      const int* lab_t = slab + buf * kRows;
+      float2* acc0 = reinterpret_cast<float2*>(sacc + (size_t)g * K * D + ch * 64) + lane;
+      for (int r = g; r < rows; r += 4 * G) {
+        int lab[4];
+        float2 x[4];
 #pragma unroll
-        for (int ch = 0; ch < NCH; ++ch) {
+        for (int i = 0; i < 4; ++i) {
+          const int rr = r + i * G;
+          const bool in = rr < rows;
+          const int r2 = in ? rr : r;
+          lab[i] = in ? lab_t[r2] : -1;
+          x[i] = *reinterpret_cast<const float2*>(ub + (r2 >> 3) * 1024 + (r2 & 7) * 128 + ((c ^ (r2 & 7)) << 4));
+        }
 #pragma unroll
-          for (int round = 0; round < ROUNDS; ++round) {
-            if ((g8 % ROUNDS) == round) {
-              const int copy = g8 / ROUNDS;
-              for (int r = g8; r < rows; r += 8) {
-                const int lab = slab[r];
-                // wide rows: the tile went through L2 a moment ago (E jobs); plain coalesced re-reads, no staging
-                const float4 xv = NCH == 1 ? sx4[r * 16 + col]
-                                           : __ldg(reinterpret_cast<const float4*>(X + (size_t)(row0 + r) * D + ch * 64) + col);
-                float4* dst = reinterpret_cast<float4*>(sacc) + ((size_t)(copy * 16 + lab) * NCH + ch) * 16 + col;
-                float4 a = *dst;
-                a.x += xv.x; a.y += xv.y; a.z += xv.z; a.w += xv.w;
-                *dst = a;
-                if (col == 0 && ch == 0) scnt[g8 * 16 + lab] += 1;
-              }
-            }
-            if (ROUNDS > 1) named_bar_sync(2, kRole);
+        for (int i = 0; i < 4; ++i) {
+          if (lab[i] >= 0) {
+            float2* dst = acc0 + (size_t)lab[i] * (D / 2);
+            float2 a = *dst;
+            a.x += x[i].x;
+            a.y += x[i].y;
+            *dst = a;
+            if (ch == 0 && lane == 0) cnt[lab[i]] += 1;
           }
         }
-        named_bar_sync(2, kRole);                              // slab and the slot are no longer read
-        if (NCH == 1 && et == 0) mbar_arrive(&B->slot_free[slot]);
+      }
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&B->slot_free[s0]);
+        mbar_arrive(&B->slot_free[s1]);
+        mbar_arrive(&B->lab_free[buf]);
       }
     }
   }
@@ -297,24 +373,23 @@ kmeans_assign_tc_kernel(const float* __restrict__ X, const float* __restrict__ c
   const bool dead = B->timeout != 0;
   if (want_sums) {
     for (int i = tid; i < K * D; i += kTcThreads) {
-      const int k = i / D, d = i - k * D;
       double sum = 0.0;
-      for (int c = 0; c < G; ++c) sum += (double)sacc[(size_t)(c * 16 + k) * D + d];
+      for (int gg = 0; gg < G; ++gg) sum += (double)sacc[(size_t)gg * K * D + i];
       out[i] = dead ? nan : sum;
     }
     for (int i = tid; i < K; i += kTcThreads) {
-      int c = 0;
-      for (int gg = 0; gg < 8; ++gg) c += scnt[gg * 16 + i];
-      out[(int64_t)K * D + i] = (double)c;
+      int cc = 0;
+      for (int gg = 0; gg < 8; ++gg) cc += scnt[gg * 16 + i];
+      out[(int64_t)K * D + i] = (double)cc;
     }
   }
-  double* red = reinterpret_cast<double*>(slots);
+  double* red = reinterpret_cast<double*>(units);
   const double chs = warp_sum((double)changed);
   if (lane == 0) red[warp] = chs;
   __syncthreads();
   if (tid == 0) {
     double s = 0.0;
-    for (int w = 0; w < kTcThreads / 32; ++w) s += red[w];
+    for (int wq = 0; wq < kTcThreads / 32; ++wq) s += red[wq];
     out[(int64_t)K * D + K + 0] = dead ? nan : 0.0;      // inertia: not computed in this form of the pass
     out[(int64_t)K * D + K + 1] = dead ? nan : s;
     out[(int64_t)K * D + K + 2] = 0.0;
@@ -324,6 +399,22 @@ kmeans_assign_tc_kernel(const float* __restrict__ X, const float* __restrict__ c
     tc_fence_after();
     tmem_dealloc(tmem, 32);
   }
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
 }
 
 }  // namespace
@@ -346,12 +437,32 @@ int launch_kmeans_assign_tc(const float* X, const float* centers, int32_t* label
   if (ntiles < nb) nb = (int)ntiles;
   if (nb < 1) nb = 1;
   *nb_out = nb;
+
+  // rows as a 2-D tensor (D, N) of float32, boxes of 32 floats x 128 rows, 128-byte swizzle, rows past N read as zero
+  EncodeTiledFn encode = encode_tiled_fn();
+  DIC_REQUIRE(encode != nullptr, DIC_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  CUtensorMap tmap;
+  const cuuint64_t gdim[2] = {(cuuint64_t)D, (cuuint64_t)N};
+  const cuuint64_t gstride[1] = {(cuuint64_t)D * sizeof(float)};
+  const cuuint32_t box[2] = {32u, (cuuint32_t)kRows};
+  const cuuint32_t estr[2] = {1u, 1u};
+  const CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2u, const_cast<float*>(X), gdim, gstride, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DIC_REQUIRE(cr == CUDA_SUCCESS, DIC_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for N=%lld D=%d", (int)cr,
+              (long long)N, D);
+
+  const int NCH = D / 64;
+  int nu = kMaxUnits;
+  while (nu > 2 * NCH && tc_plan(NCH, K, nu).total > (size_t)kMaxSmemBytes) --nu;
+  const size_t smem = tc_plan(NCH, K, nu).total;
+  DIC_REQUIRE(smem <= (size_t)kMaxSmemBytes, DIC_ERR_UNSUPPORTED, "tensor-core Lloyd pass: %zu bytes of shared memory",
+              smem);
 #define DIC_KTC(NCH_)                                                                                          \
   {                                                                                                            \
     auto kf = kmeans_assign_tc_kernel<NCH_>;                                                                   \
-    const size_t smem = TcLayout<NCH_>::total;                                                                 \
     DIC_CUDA(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                \
-    kf<<<nb, kTcThreads, smem, st>>>(X, centers, labels, ws, N, K, flags, want_sums, done);                    \
+    kf<<<nb, kTcThreads, smem, st>>>(tmap, centers, labels, ws, N, K, flags, want_sums, nu, done);             \
   }
   if (D == 64) DIC_KTC(1) else if (D == 128) DIC_KTC(2) else DIC_KTC(4)
 #undef DIC_KTC
