@@ -28,6 +28,10 @@
 #include "common.cuh"
 #include "tc_common.cuh"
 
+#ifndef DIC_KTC_SKIP
+#define DIC_KTC_SKIP 0      // benchmark builds: phases removed at compile time (benchmarks/_ktc_probe.sh)
+#endif
+
 namespace dic {
 namespace {
 
@@ -36,12 +40,15 @@ using namespace tc;
 constexpr int kRows = 128;                     // rows per tile (M of the MMA)
 constexpr int kUnitB = kRows * 128;            // one ring unit: 128 rows x 32 floats, SWIZZLE_128B K-major (16 KB)
 constexpr int kMaxUnits = 12;
-constexpr int kLboB = 16 * 16;                 // centres: 16 rows x 16 bytes per K chunk (no swizzle)
-constexpr int kBTileB = 16 * kLboB;            // hi or lo centre tile of one 64-wide K chunk
+constexpr int kLboB = 32 * 16;                 // centres: 32 rows (16 hi | 16 lo) x 16 bytes per K chunk (no swizzle)
+constexpr int kBTileB = 16 * kLboB;            // stacked centre tile of one 64-wide K chunk (8 KB)
 constexpr int kSbo = 128;                      // bytes between 8-row groups of the centre tiles
 constexpr int kNLo = 4, kNArg = 4, kNAcc = 8;  // warps per role
 constexpr int kTcThreads = 32 * (2 + kNLo + kNArg + kNAcc);
 constexpr uint32_t kIdescTf32N16 = make_idesc(2u, 128u, 16u);
+constexpr uint32_t kIdescTf32N32 = make_idesc(2u, 128u, 32u);
+constexpr uint32_t kTmemCols = 128;            // [0,64): two accumulators of 32 columns; [64,128): two low-half units
+constexpr uint32_t kTmemLo = 64;
 
 struct TcBars {
   uint64_t full[kMaxUnits], slot_free[kMaxUnits];
@@ -53,19 +60,18 @@ struct TcBars {
 // Shared-memory plan (offsets from the 1024-byte aligned base); `nu` ring units.
 struct TcPlan {
   int nu;
-  size_t lo, b_hi, b_lo, sacc, scn, scnt, slab, bars, total;
+  size_t bt, sacc, scn, scnt, ssort, wcnt, bars, total;
 };
 __host__ __device__ inline TcPlan tc_plan(int NCH, int K, int nu) {
   TcPlan p;
   p.nu = nu;
-  p.lo = (size_t)nu * kUnitB;
-  p.b_hi = p.lo + 2 * (size_t)kUnitB;
-  p.b_lo = p.b_hi + (size_t)NCH * kBTileB;
-  p.sacc = p.b_lo + (size_t)NCH * kBTileB;                    // [G][K][D] floats, G * NCH = 8
+  p.bt = (size_t)nu * kUnitB;
+  p.sacc = p.bt + (size_t)NCH * kBTileB;                      // [G][K][D] floats, G * NCH = 8
   p.scn = p.sacc + (size_t)8 * K * 64 * 4;
   p.scnt = p.scn + 64;                                        // [8][16] ints
-  p.slab = p.scnt + 8 * 16 * 4;                               // [2][128] ints
-  p.bars = p.slab + 2 * kRows * 4;
+  p.ssort = p.scnt + 8 * 16 * 4;                              // [2][128] ints: (label << 8 | row), sorted by label
+  p.wcnt = p.ssort + 2 * kRows * 4;                           // [2][4][32] ints: per-warp label counts of a tile
+  p.bars = p.wcnt + 2 * 4 * 32 * 4;
   p.total = p.bars + sizeof(TcBars) + 1024;                   // + alignment slack
   return p;
 }
@@ -126,20 +132,19 @@ kmeans_assign_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* _
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const TcPlan P = tc_plan(NCH, K, nu);
   unsigned char* units = smem;
-  unsigned char* lo_buf = smem + P.lo;
-  unsigned char* b_hi = smem + P.b_hi;
-  unsigned char* b_lo = smem + P.b_lo;
+  unsigned char* bt = smem + P.bt;
   float* sacc = reinterpret_cast<float*>(smem + P.sacc);
   float* scn = reinterpret_cast<float*>(smem + P.scn);
   int* scnt = reinterpret_cast<int*>(smem + P.scnt);
-  int* slab = reinterpret_cast<int*>(smem + P.slab);
+  int* ssort = reinterpret_cast<int*>(smem + P.ssort);
+  int* wcnt = reinterpret_cast<int*>(smem + P.wcnt);
   TcBars* B = reinterpret_cast<TcBars*>(smem + P.bars);
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
 
   if (tid == 0) {
     for (int s = 0; s < kMaxUnits; ++s) {
       mbar_init(&B->full[s], 1);
-      mbar_init(&B->slot_free[s], 1 + (want_sums ? G : 0));    // MMAs done (+ the M-step warps of the unit's chunk)
+      mbar_init(&B->slot_free[s], 1 + kNLo + (want_sums ? G : 0));   // MMAs done, low halves taken (+ the M-step warps)
     }
     for (int k = 0; k < 2; ++k) {
       mbar_init(&B->lo_full[k], kNLo);
@@ -152,16 +157,17 @@ kmeans_assign_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* _
     B->timeout = 0;
     fence_proxy_async();
   }
-  if (warp == 0) tmem_alloc(&B->tmem_base, 32);
-  // centres -> split operand tiles [chunk][K chunk][16 rows][16 bytes] (rows >= K are zero), norms, zeroed accumulators
+  if (warp == 0) tmem_alloc(&B->tmem_base, kTmemCols);
+  // centres -> stacked split operand tiles [chunk][K chunk][16 hi rows | 16 lo rows][16 bytes] (rows >= K are zero),
+  // norms, zeroed accumulators
   for (int idx = tid; idx < NCH * 256; idx += kTcThreads) {
     const int n = idx & 15, c16 = (idx >> 4) & 15, ch = idx >> 8;
     float4 x = make_float4(0.f, 0.f, 0.f, 0.f), h, l;
     if (n < K) x = __ldg(reinterpret_cast<const float4*>(centers + (size_t)n * D + ch * 64 + c16 * 4));
     split_tf32(x, h, l);
     const int off = ch * kBTileB + c16 * kLboB + n * 16;
-    *reinterpret_cast<float4*>(b_hi + off) = h;
-    *reinterpret_cast<float4*>(b_lo + off) = l;
+    *reinterpret_cast<float4*>(bt + off) = h;
+    *reinterpret_cast<float4*>(bt + off + 256) = l;
   }
   if (want_sums)
     for (int i = tid; i < 8 * K * 64; i += kTcThreads) sacc[i] = 0.f;
@@ -202,14 +208,14 @@ kmeans_assign_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* _
   } else if (warp == 1) {
     // ================= MMA issuer (whole warp in uniform control flow, tcgen05 under elect) =================
     const uint32_t tmem_u = __reduce_or_sync(0xffffffffu, tmem);
-    const uint32_t units_u = smem_u32(units), lo_u = smem_u32(lo_buf), b_hi_u = smem_u32(b_hi), b_lo_u = smem_u32(b_lo);
+    const uint32_t units_u = smem_u32(units), bt_u = smem_u32(bt);
     RingPos rp{0, 0u};
     uint32_t v = 0;                                 // unit counter (low-half ring)
     int64_t tl = 0;
     bool ok = true;
     for (int64_t t = blockIdx.x; t < ntiles && ok; t += gridDim.x, ++tl) {
       const uint32_t buf = (uint32_t)(tl & 1);
-      const uint32_t d_tmem = tmem_u + buf * 16u;
+      const uint32_t d_tmem = tmem_u + buf * 32u;
       for (int u = 0; u < UPT && ok; ++u, ++v) {
         const uint32_t lb = v & 1u;
         ok = __all_sync(0xffffffffu, wait_bar(B, &B->full[rp.slot], rp.phase));
@@ -218,32 +224,32 @@ kmeans_assign_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* _
         if (!ok) break;
         tc_fence_after();
         const uint32_t a_hi = units_u + (uint32_t)rp.slot * (uint32_t)kUnitB;
-        const uint32_t a_lo = lo_u + lb * (uint32_t)kUnitB;
-        const uint32_t bo = (uint32_t)((u >> 1) * kBTileB + (u & 1) * 8 * kLboB);
+        const uint32_t a_lo = tmem_u + kTmemLo + lb * 32u;
+        const uint32_t bo = bt_u + (uint32_t)((u >> 1) * kBTileB + (u & 1) * 8 * kLboB);
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {          // one MMA consumes K = 8 tf32 = 32 bytes of every row
           const uint64_t dah = make_desc_sw128(a_hi + ks * 32);
-          const uint64_t dal = make_desc_sw128(a_lo + ks * 32);
-          const uint64_t dbh = make_desc_kmajor(b_hi_u + bo + ks * 2 * kLboB, kLboB, kSbo);
-          const uint64_t dbl = make_desc_kmajor(b_lo_u + bo + ks * 2 * kLboB, kLboB, kSbo);
-          if (elect_one()) {
-            umma_tf32(d_tmem, dah, dbh, kIdescTf32N16, (u > 0 || ks > 0) ? 1u : 0u);
-            umma_tf32(d_tmem, dah, dbl, kIdescTf32N16, 1u);
-            umma_tf32(d_tmem, dal, dbh, kIdescTf32N16, 1u);
+          const uint64_t db = make_desc_kmajor(bo + ks * 2 * kLboB, kLboB, kSbo);
+          if (!(DIC_KTC_SKIP & 2) && elect_one()) {
+            // columns [0,16): x_hi.c_hi + x_lo.c_hi, columns [16,32): x_hi.c_lo
+            umma_tf32(d_tmem, dah, db, kIdescTf32N32, (u > 0 || ks > 0) ? 1u : 0u);
+            umma_tf32_ts(d_tmem, a_lo + ks * 8, db, kIdescTf32N16, 1u);
           }
         }
         if (elect_one()) {
-          umma_commit(&B->lo_free[lb]);                         // the low-half unit is reusable
+          umma_commit(&B->lo_free[lb]);                         // the low-half unit (TMEM) is reusable
           umma_commit(&B->slot_free[rp.slot]);                  // the MMAs have read the raw unit
-          if (u == UPT - 1) umma_commit(&B->acc_full[buf]);     // the tile's 16 dots per row are complete
+          if (u == UPT - 1) umma_commit(&B->acc_full[buf]);     // the tile's dots are complete
         }
         __syncwarp();
         rp.advance(nu);
       }
     }
   } else if (warp < 2 + kNLo) {
-    // ================= low operand halves: lo = rn_tf32(x - trunc_tf32(x)), same position as x =================
-    const int ct = tid - 64;
+    // ================= low operand halves: thread = row, lo = rn_tf32(x - trunc_tf32(x)) -> TMEM (A operand) =========
+    const int q = warp & 3, row = 32 * q + lane;
+    const uint32_t sw = (uint32_t)(row & 7);
+    const size_t roff = (size_t)(row >> 3) * 1024 + (size_t)sw * 128;
     RingPos rp{0, 0u};
     uint32_t v = 0;
     bool ok = true;
@@ -253,25 +259,33 @@ kmeans_assign_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* _
         ok = wait_bar(B, &B->full[rp.slot], rp.phase) && wait_bar(B, &B->lo_free[lb], ((v >> 1) & 1u) ^ 1u);
         ok = __all_sync(0xffffffffu, ok);
         if (!ok) break;
-        const float4* src = reinterpret_cast<const float4*>(units + (size_t)rp.slot * kUnitB);
-        float4* dst = reinterpret_cast<float4*>(lo_buf + (size_t)lb * kUnitB);
+        tc_fence_after();
+        const unsigned char* src = units + (size_t)rp.slot * kUnitB + roff;
+        uint32_t l[32];
 #pragma unroll
-        for (int it = 0; it < kUnitB / 16 / (32 * kNLo); ++it) {
-          const float4 x = src[it * 32 * kNLo + ct];
-          float4 l;
-          l.x = lo_tf32(x.x); l.y = lo_tf32(x.y); l.z = lo_tf32(x.z); l.w = lo_tf32(x.w);
-          dst[it * 32 * kNLo + ct] = l;
+        for (int c = 0; c < 8; ++c) {
+          float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (!(DIC_KTC_SKIP & 1)) x = *reinterpret_cast<const float4*>(src + (((uint32_t)c ^ sw) << 4));
+          l[4 * c + 0] = __float_as_uint(lo_tf32(x.x));
+          l[4 * c + 1] = __float_as_uint(lo_tf32(x.y));
+          l[4 * c + 2] = __float_as_uint(lo_tf32(x.z));
+          l[4 * c + 3] = __float_as_uint(lo_tf32(x.w));
         }
-        fence_proxy_async();               // generic-proxy stores -> visible to the tensor core (async proxy)
+        tmem_st32(tmem + ((uint32_t)(32 * q) << 16) + kTmemLo + lb * 32u, l);
+        tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&B->lo_full[lb]);
+        if (lane == 0) {
+          mbar_arrive(&B->lo_full[lb]);
+          mbar_arrive(&B->slot_free[rp.slot]);
+        }
         rp.advance(nu);
       }
     }
   } else if (warp < 2 + kNLo + kNArg) {
-    // ================= arg-min: thread = row =================
+    // ================= arg-min: thread = row; then the tile's rows sorted by label for the M-step =================
     const int q = warp & 3;                           // TMEM lane quarter this warp may read
     const int row = 32 * q + lane;
+    const uint32_t lt_mask = (1u << lane) - 1u;
     int64_t tl = 0;
     bool ok = true;
     for (int64_t t = blockIdx.x; t < ntiles && ok; t += gridDim.x, ++tl) {
@@ -284,16 +298,16 @@ kmeans_assign_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* _
       ok = __all_sync(0xffffffffu, wait_bar(B, &B->acc_full[buf], ph));
       if (!ok) break;
       tc_fence_after();
-      uint32_t v[16];
-      tmem_ld16(tmem + ((uint32_t)(32 * q) << 16) + buf * 16u, v);
+      uint32_t v[32];
+      tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + buf * 32u, v);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&B->acc_free[buf]);           // this warp has its dots in registers
       int best = 0;
-      float bestd = fmaf(-2.f, __uint_as_float(v[0]), scn[0]);
+      float bestd = fmaf(-2.f, __uint_as_float(v[0]) + __uint_as_float(v[16]), scn[0]);
 #pragma unroll
       for (int k = 1; k < 16; ++k) {
-        const float dk = fmaf(-2.f, __uint_as_float(v[k]), scn[k]);     // ||c||^2 - 2 x.c  (||x||^2 omitted)
+        const float dk = fmaf(-2.f, __uint_as_float(v[k]) + __uint_as_float(v[16 + k]), scn[k]);   // ||c||^2 - 2 x.c
         if (k < K && dk < bestd) {                                      // strict '<': lowest index wins ties
           bestd = dk;
           best = k;
@@ -304,24 +318,52 @@ kmeans_assign_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* _
         labels[row0 + row] = best;
       }
       if (want_sums) {
+        // stable counting sort of the tile's 128 rows by label (bin 16 = rows past N): position = rows of smaller
+        // bins + rows of the same bin in earlier warps + rank inside the warp
+        const int bin = row < rows ? best : 16;
+        int mycnt = 0, myrank = 0;
+#pragma unroll
+        for (int b = 0; b <= 16; ++b) {
+          if (b < K || b == 16) {
+            const uint32_t m = __ballot_sync(0xffffffffu, bin == b);
+            if (lane == b) mycnt = __popc(m);
+            if (bin == b) myrank = __popc(m & lt_mask);
+          }
+        }
+        int* wc = wcnt + (int)buf * 128;
+        wc[q * 32 + lane] = mycnt;                     // lanes >= 17 hold 0
+        named_bar_sync(1, 32 * kNArg);
+        const int c0 = wc[lane], c1 = wc[32 + lane], c2 = wc[64 + lane], c3 = wc[96 + lane];
+        const int tot = c0 + c1 + c2 + c3;
+        int incl = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int up = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += up;
+        }
+        const int base = incl - tot + (q > 0 ? c0 : 0) + (q > 1 ? c1 : 0) + (q > 2 ? c2 : 0);
+        const int pos = __shfl_sync(0xffffffffu, base, bin) + myrank;
         ok = __all_sync(0xffffffffu, wait_bar(B, &B->lab_free[buf], ph ^ 1u));
         if (!ok) break;
-        slab[buf * kRows + row] = best;
+        ssort[buf * kRows + pos] = (bin << 8) | row;
         __syncwarp();
         if (lane == 0) mbar_arrive(&B->lab_full[buf]);
       }
     }
   } else if (want_sums) {
-    // ================= M-step accumulation: warp = (row group g, chunk ch), lane = 8 bytes of the chunk =================
+    // ================= M-step accumulation: warp = (part g of the sorted rows, chunk ch), lane = 8 bytes of the chunk ====
+    // Runs of equal labels are summed in registers and flushed into the warp's private sacc[g][label] row when the label
+    // changes: the label is an address, no atomics, fixed order (deterministic).
     const int w = warp - (2 + kNLo + kNArg);
     const int g = w % G, ch = w / G;
     const int hf = lane >> 4, c = (lane & 15) >> 1, sub = lane & 1;
+    constexpr int NPOS = kRows / G;
     int* cnt = scnt + w * 16;
+    float2* acc0 = reinterpret_cast<float2*>(sacc + (size_t)g * K * D + ch * 64) + lane;
     int64_t tl = 0;
     bool ok = true;
     for (int64_t t = blockIdx.x; t < ntiles && ok; t += gridDim.x, ++tl) {
       const uint32_t buf = (uint32_t)(tl & 1);
-      const int rows = (int)min((int64_t)kRows, N - t * kRows);
       // ring positions of this warp's two units of the tile (halves of chunk ch)
       const int64_t u0 = tl * UPT + 2 * ch;
       const int s0 = (int)(u0 % nu), s1 = (int)((u0 + 1) % nu);
@@ -331,31 +373,48 @@ kmeans_assign_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* _
       ok = __all_sync(0xffffffffu, ok);
       if (!ok) break;
       const unsigned char* ub = units + (size_t)(hf ? s1 : s0) * kUnitB + sub * 8;
-      const int* lab_t = slab + buf * kRows;
-      float2* acc0 = reinterpret_cast<float2*>(sacc + (size_t)g * K * D + ch * 64) + lane;
-      for (int r = g; r < rows; r += 4 * G) {
-        int lab[4];
+      const int4* srt = reinterpret_cast<const int4*>(ssort + buf * kRows + g * NPOS);
+      int cur = -1, run = 0;
+      float2 acc = make_float2(0.f, 0.f);
+      auto flush = [&]() {
+        if (cur >= 0) {
+          float2* dst = acc0 + (size_t)cur * (D / 2);
+          float2 a = *dst;
+          a.x += acc.x;
+          a.y += acc.y;
+          *dst = a;
+          if (ch == 0 && lane == 0) cnt[cur] += run;
+        }
+      };
+      bool more = !(DIC_KTC_SKIP & 4);
+      for (int i = 0; i < NPOS / 4 && more; ++i) {
+        const int4 ev = srt[i];
+        const int e[4] = {ev.x, ev.y, ev.z, ev.w};
         float2 x[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int rr = r + i * G;
-          const bool in = rr < rows;
-          const int r2 = in ? rr : r;
-          lab[i] = in ? lab_t[r2] : -1;
-          x[i] = *reinterpret_cast<const float2*>(ub + (r2 >> 3) * 1024 + (r2 & 7) * 128 + ((c ^ (r2 & 7)) << 4));
+        for (int j = 0; j < 4; ++j) {
+          const int r2 = e[j] & 255;
+          x[j] = *reinterpret_cast<const float2*>(ub + (r2 >> 3) * 1024 + (r2 & 7) * 128 + ((c ^ (r2 & 7)) << 4));
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          if (lab[i] >= 0) {
-            float2* dst = acc0 + (size_t)lab[i] * (D / 2);
-            float2 a = *dst;
-            a.x += x[i].x;
-            a.y += x[i].y;
-            *dst = a;
-            if (ch == 0 && lane == 0) cnt[lab[i]] += 1;
+        for (int j = 0; j < 4; ++j) {
+          const int lab = e[j] >> 8;
+          if (lab == 16) more = false;                 // rows past N sort last
+          if (more) {
+            if (lab != cur) {
+              flush();
+              cur = lab;
+              acc = x[j];
+              run = 1;
+            } else {
+              acc.x += x[j].x;
+              acc.y += x[j].y;
+              ++run;
+            }
           }
         }
       }
+      flush();
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(&B->slot_free[s0]);
@@ -397,7 +456,7 @@ kmeans_assign_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* _
   }
   if (warp == 0) {
     tc_fence_after();
-    tmem_dealloc(tmem, 32);
+    tmem_dealloc(tmem, kTmemCols);
   }
 }
 
