@@ -3,7 +3,7 @@ sys.path.insert(0, '.')
 from deep_interpolation_clustering_b200 import synth
 from deep_interpolation_clustering_b200.kmeans import _Device
 out = {}
-for D, N in ((64, 1_000_000), (256, 500_000)):
+for D, N in ((64, 1_000_000), (128, 500_000), (128, 1_000_000), (256, 250_000), (256, 500_000)):
     X = torch.from_numpy(synth.make_blobs(N, D, 5, seed=4)).cuda()
     for K in (10,):
         for ws in (True, False):
@@ -18,5 +18,5 @@ for D, N in ((64, 1_000_000), (256, 500_000)):
                 st.assign(cen, flags, want_sums=ws)
             e1.record()
             torch.cuda.synchronize()
-            out[f"D{D}_K{K}_sums{int(ws)}"] = round(e0.elapsed_time(e1) / 20, 4)
+            out[f"D{D}_N{N}_sums{int(ws)}"] = round(e0.elapsed_time(e1) / 20, 4)
 print(json.dumps(out))

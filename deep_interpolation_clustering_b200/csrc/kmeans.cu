@@ -1203,8 +1203,15 @@ int km_blocks(int K, int D) {
   return (int)b;
 }
 
-// Where the tensor-core pass beats the CUDA-core kernels (measured, benchmarks/_km_pass.py).
-static bool kmeans_tc_wins(int D, int K) { return false && D >= 64 && K >= 1; }
+// Where the tensor-core pass beats the CUDA-core kernels (measured per pass under a CUDA graph, benchmarks/_km_small.py
+// and _km_pass.py: 80 against 96-148 us at 1M x 64, 136 against 370-810 us at 500k x 256; below ~20k rows both run at
+// their launch + ramp floor of 8-10 us).
+static bool kmeans_tc_wins(int64_t N, int D, int K) {
+  if (D == 256) return N >= 4096;
+  if (D == 128) return N >= 50000 || (K >= 8 && N >= 8192);
+  if (D == 64) return N >= 100000 || (K >= 10 && N >= 20000);
+  return false;
+}
 
 template <typename T>
 int launch_assign(const void* X, const void* centers, int32_t* labels, double* sums, double* counts,
@@ -1220,7 +1227,7 @@ int launch_assign(const void* X, const void* centers, int32_t* labels, double* s
     DIC_REQUIRE(tc_ok || which != 5, DIC_ERR_UNSUPPORTED, "DIC_KM_KERNEL(5): the tensor-core pass covers float32, D in "
                 "{64,128,256}, K <= 16 with DIC_KM_NO_INERTIA and without DIC_KM_KEEP_LABELS (got D=%d K=%d flags=%d)", D, K,
                 flags & 255);
-    if (tc_ok && (which == 5 || (which == 0 && kmeans_tc_wins(D, K)))) {
+    if (tc_ok && (which == 5 || (which == 0 && kmeans_tc_wins(N, D, K)))) {
       double* wsd = static_cast<double*>(workspace);
       int nb = 0;
       int rc = launch_kmeans_assign_tc(static_cast<const float*>(X), static_cast<const float*>(centers), labels, wsd, N, D, K,

@@ -32,6 +32,12 @@
 #define DIC_KTC_SKIP 0      // benchmark builds: phases removed at compile time (benchmarks/_ktc_probe.sh)
 #endif
 
+#ifdef DIC_KTC_PROF      // benchmark builds: per-role cycle counters of CTA 0, printed at the end of the pass
+#define KPROF(...) __VA_ARGS__
+#else
+#define KPROF(...)
+#endif
+
 namespace dic {
 namespace {
 
@@ -47,7 +53,11 @@ constexpr int kNLo = 4, kNArg = 4, kNAcc = 8;  // warps per role
 constexpr int kTcThreads = 32 * (2 + kNLo + kNArg + kNAcc);
 constexpr uint32_t kIdescTf32N16 = make_idesc(2u, 128u, 16u);
 constexpr uint32_t kIdescTf32N32 = make_idesc(2u, 128u, 32u);
-constexpr uint32_t kTmemCols = 128;            // [0,64): two accumulators of 32 columns; [64,128): two low-half units
+#ifdef DIC_KTC_MMAVAR
+constexpr uint32_t kTmemCols = 512;
+#else
+constexpr uint32_t kTmemCols = 128;
+#endif            // [0,64): two accumulators of 32 columns; [64,128): two low-half units
 constexpr uint32_t kTmemLo = 64;
 
 struct TcBars {
@@ -76,9 +86,42 @@ __host__ __device__ inline TcPlan tc_plan(int NCH, int K, int nu) {
   return p;
 }
 
+#ifndef DIC_KTC_WAIT
+#define DIC_KTC_WAIT 0
+#endif
+__device__ __forceinline__ bool bar_wait_v(uint64_t* bar, uint32_t phase) {
+#if DIC_KTC_WAIT == 0
+  return bar_wait_bounded(bar, phase);
+#else
+  for (int spin = 0; spin < (1 << 20); ++spin) {
+    uint32_t ok;
+#if DIC_KTC_WAIT == 1
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(phase)
+        : "memory");
+    if (ok) return true;
+    __nanosleep(40);
+#else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(phase), "r"(2000u)
+        : "memory");
+    if (ok) return true;
+#endif
+  }
+  return false;
+#endif
+}
 __device__ __forceinline__ bool wait_bar(TcBars* B, uint64_t* bar, uint32_t phase) {
   if (*reinterpret_cast<volatile int*>(&B->timeout)) return false;
-  if (bar_wait_bounded(bar, phase)) return true;
+  if (bar_wait_v(bar, phase)) return true;
   *reinterpret_cast<volatile int*>(&B->timeout) = 1;      // a stalled hand-off ends the pass with NaN statistics, not a hang
   return false;
 }
@@ -121,12 +164,17 @@ struct RingPos {
   }
 };
 
-template <int NCH>
+// MG: the M-step re-reads the rows of a tile from global memory (L2: the tile went through it a moment ago) instead of
+// the ring, whose units are then free as soon as the MMAs have read them.  Taken for D = 256, where one 128-row tile
+// is 8 of the at most 12 units and holding it until the labels are known would serialise load and M-step.
+template <int NCH, bool MG>
 __global__ void __launch_bounds__(kTcThreads, 1)
-kmeans_assign_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ centers, int32_t* labels,
+kmeans_assign_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ X,
+                        const float* __restrict__ centers, int32_t* labels,
                         double* __restrict__ ws, int64_t N, int K, int flags, int want_sums, int nu,
                         const double* __restrict__ done) {
   if (done && *done != 0.0) return;
+  KPROF(const long long kT0 = clock64();)
   constexpr int D = 64 * NCH, G = 8 / NCH, UPT = 2 * NCH;     // units per tile
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -144,7 +192,7 @@ kmeans_assign_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* _
   if (tid == 0) {
     for (int s = 0; s < kMaxUnits; ++s) {
       mbar_init(&B->full[s], 1);
-      mbar_init(&B->slot_free[s], 1 + kNLo + (want_sums ? G : 0));   // MMAs done, low halves taken (+ the M-step warps)
+      mbar_init(&B->slot_free[s], 1 + kNLo + (want_sums && !MG ? G : 0));   // MMAs done, low halves taken (+ M-step warps)
     }
     for (int k = 0; k < 2; ++k) {
       mbar_init(&B->lo_full[k], kNLo);
@@ -172,19 +220,26 @@ kmeans_assign_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* _
   if (want_sums)
     for (int i = tid; i < 8 * K * 64; i += kTcThreads) sacc[i] = 0.f;
   for (int i = tid; i < 8 * 16; i += kTcThreads) scnt[i] = 0;
-  if (tid < 16) {
+  for (int i = tid; i < 2 * 4 * 32; i += kTcThreads) wcnt[i] = 0;
+  if (tid < 256) {                               // ||c_k||^2: 16 lanes per centre, fixed summation order
+    const int k = tid >> 4, l16 = tid & 15;
     float sum = 0.f;
-    if (tid < K)
-      for (int d = 0; d < D; ++d) {
-        const float c = __ldg(centers + (size_t)tid * D + d);
-        sum += c * c;
+    if (k < K) {
+#pragma unroll
+      for (int d = 0; d < D / 16; ++d) {
+        const float c = __ldg(centers + (size_t)k * D + d * 16 + l16);
+        sum = fmaf(c, c, sum);
       }
-    scn[tid] = sum;
+    }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (l16 == 0) scn[k] = sum;
   }
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  KPROF(if (blockIdx.x == 0 && tid == 0) printf("setup: %lld clk\n", clock64() - kT0);)
   const uint32_t tmem = B->tmem_base;
   const bool count_changes = (flags & DIC_KM_COUNT_CHANGES) != 0;
   const int64_t ntiles = (N + kRows - 1) / kRows;
@@ -194,9 +249,12 @@ kmeans_assign_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* _
     // ================= producer: one tensor-map copy per unit =================
     RingPos rp{0, 0u};
     bool ok = true;
+    KPROF(long long w0 = 0, T0 = clock64();)
     for (int64_t t = blockIdx.x; t < ntiles && ok; t += gridDim.x) {
       for (int u = 0; u < UPT; ++u) {
+        KPROF(long long c0 = clock64();)
         ok = __all_sync(0xffffffffu, wait_bar(B, &B->slot_free[rp.slot], rp.phase ^ 1u));
+        KPROF(w0 += clock64() - c0;)
         if (!ok) break;
         if (elect_one()) {
           mbar_expect_tx(&B->full[rp.slot], (uint32_t)kUnitB);
@@ -205,6 +263,7 @@ kmeans_assign_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* _
         rp.advance(nu);
       }
     }
+    KPROF(if (blockIdx.x == 0 && lane == 0) printf("producer: total %lld wait_slot_free %lld\n", clock64() - T0, w0);)
   } else if (warp == 1) {
     // ================= MMA issuer (whole warp in uniform control flow, tcgen05 under elect) =================
     const uint32_t tmem_u = __reduce_or_sync(0xffffffffu, tmem);
@@ -213,30 +272,53 @@ kmeans_assign_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* _
     uint32_t v = 0;                                 // unit counter (low-half ring)
     int64_t tl = 0;
     bool ok = true;
+    KPROF(long long w0 = 0, w1 = 0, w2 = 0, T0 = clock64();)
     for (int64_t t = blockIdx.x; t < ntiles && ok; t += gridDim.x, ++tl) {
       const uint32_t buf = (uint32_t)(tl & 1);
       const uint32_t d_tmem = tmem_u + buf * 32u;
       for (int u = 0; u < UPT && ok; ++u, ++v) {
         const uint32_t lb = v & 1u;
+        KPROF(long long c0 = clock64();)
         ok = __all_sync(0xffffffffu, wait_bar(B, &B->full[rp.slot], rp.phase));
+        KPROF(long long c1 = clock64(); w0 += c1 - c0;)
         ok = ok && __all_sync(0xffffffffu, wait_bar(B, &B->lo_full[lb], (v >> 1) & 1u));
+        KPROF(long long c2 = clock64(); w1 += c2 - c1;)
         if (u == 0) ok = ok && __all_sync(0xffffffffu, wait_bar(B, &B->acc_free[buf], ((uint32_t)(tl >> 1) & 1u) ^ 1u));
+        KPROF(w2 += clock64() - c2;)
         if (!ok) break;
         tc_fence_after();
         const uint32_t a_hi = units_u + (uint32_t)rp.slot * (uint32_t)kUnitB;
         const uint32_t a_lo = tmem_u + kTmemLo + lb * 32u;
         const uint32_t bo = bt_u + (uint32_t)((u >> 1) * kBTileB + (u & 1) * 8 * kLboB);
+        uint64_t dah[4], db[4];
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {          // one MMA consumes K = 8 tf32 = 32 bytes of every row
-          const uint64_t dah = make_desc_sw128(a_hi + ks * 32);
-          const uint64_t db = make_desc_kmajor(bo + ks * 2 * kLboB, kLboB, kSbo);
-          if (!(DIC_KTC_SKIP & 2) && elect_one()) {
-            // columns [0,16): x_hi.c_hi + x_lo.c_hi, columns [16,32): x_hi.c_lo
-            umma_tf32(d_tmem, dah, db, kIdescTf32N32, (u > 0 || ks > 0) ? 1u : 0u);
-            umma_tf32_ts(d_tmem, a_lo + ks * 8, db, kIdescTf32N16, 1u);
-          }
+          dah[ks] = make_desc_sw128(a_hi + ks * 32);
+          db[ks] = make_desc_kmajor(bo + ks * 2 * kLboB, kLboB, kSbo);
         }
         if (elect_one()) {
+          if (!(DIC_KTC_SKIP & 2)) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              // columns [0,16): x_hi.c_hi + x_lo.c_hi, columns [16,32): x_hi.c_lo
+#ifndef DIC_KTC_MMAVAR
+#define DIC_KTC_MMAVAR 0
+#endif
+#if DIC_KTC_MMAVAR == 0
+              umma_tf32(d_tmem, dah[ks], db[ks], kIdescTf32N32, (u > 0 || ks > 0) ? 1u : 0u);
+              umma_tf32_ts(d_tmem, a_lo + ks * 8, db[ks], kIdescTf32N16, 1u);
+#elif DIC_KTC_MMAVAR == 1      // timing probe: high halves only
+              umma_tf32(d_tmem, dah[ks], db[ks], kIdescTf32N32, (u > 0 || ks > 0) ? 1u : 0u);
+#elif DIC_KTC_MMAVAR == 2      // timing probe: low halves only
+              umma_tf32_ts(d_tmem, a_lo + ks * 8, db[ks], kIdescTf32N16, (u > 0 || ks > 0) ? 1u : 0u);
+#elif DIC_KTC_MMAVAR == 3      // timing probe: four independent accumulator chains
+              umma_tf32(d_tmem + (ks & 1) * 64, dah[ks], db[ks], kIdescTf32N32, (u > 0 || ks > 1) ? 1u : 0u);
+              umma_tf32_ts(d_tmem + 128 + (ks & 1) * 64, a_lo + ks * 8, db[ks], kIdescTf32N16, (u > 0 || ks > 1) ? 1u : 0u);
+#elif DIC_KTC_MMAVAR == 4      // timing probe: N = 128 (cost of a wider instruction)
+              umma_tf32(d_tmem + 128, dah[ks], db[ks], make_idesc(2u, 128u, 128u), (u > 0 || ks > 0) ? 1u : 0u);
+#endif
+            }
+          }
           umma_commit(&B->lo_free[lb]);                         // the low-half unit (TMEM) is reusable
           umma_commit(&B->slot_free[rp.slot]);                  // the MMAs have read the raw unit
           if (u == UPT - 1) umma_commit(&B->acc_full[buf]);     // the tile's dots are complete
@@ -245,6 +327,7 @@ kmeans_assign_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* _
         rp.advance(nu);
       }
     }
+    KPROF(if (blockIdx.x == 0 && lane == 0) printf("mma: total %lld wait_full %lld wait_lo_full %lld wait_acc_free %lld tiles %lld\n", clock64() - T0, w0, w1, w2, (long long)tl);)
   } else if (warp < 2 + kNLo) {
     // ================= low operand halves: thread = row, lo = rn_tf32(x - trunc_tf32(x)) -> TMEM (A operand) =========
     const int q = warp & 3, row = 32 * q + lane;
@@ -253,11 +336,16 @@ kmeans_assign_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* _
     RingPos rp{0, 0u};
     uint32_t v = 0;
     bool ok = true;
+    KPROF(long long w0 = 0, w1 = 0, T0 = clock64();)
     for (int64_t t = blockIdx.x; t < ntiles && ok; t += gridDim.x) {
       for (int u = 0; u < UPT; ++u, ++v) {
         const uint32_t lb = v & 1u;
-        ok = wait_bar(B, &B->full[rp.slot], rp.phase) && wait_bar(B, &B->lo_free[lb], ((v >> 1) & 1u) ^ 1u);
+        KPROF(long long c0 = clock64();)
+        ok = wait_bar(B, &B->full[rp.slot], rp.phase);
+        KPROF(long long c1 = clock64(); w0 += c1 - c0;)
+        ok = ok && wait_bar(B, &B->lo_free[lb], ((v >> 1) & 1u) ^ 1u);
         ok = __all_sync(0xffffffffu, ok);
+        KPROF(w1 += clock64() - c1;)
         if (!ok) break;
         tc_fence_after();
         const unsigned char* src = units + (size_t)rp.slot * kUnitB + roff;
@@ -281,21 +369,31 @@ kmeans_assign_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* _
         rp.advance(nu);
       }
     }
+    KPROF(if (blockIdx.x == 0 && tid == 64) printf("lo: total %lld wait_full %lld wait_lo_free %lld\n", clock64() - T0, w0, w1);)
   } else if (warp < 2 + kNLo + kNArg) {
     // ================= arg-min: thread = row; then the tile's rows sorted by label for the M-step =================
     const int q = warp & 3;                           // TMEM lane quarter this warp may read
     const int row = 32 * q + lane;
     const uint32_t lt_mask = (1u << lane) - 1u;
     int64_t tl = 0;
+    int mycount = 0;
     bool ok = true;
+    int oldl_next = -1;
+    if (count_changes && (int64_t)blockIdx.x * kRows + row < N) oldl_next = labels[(int64_t)blockIdx.x * kRows + row];
+    KPROF(long long aw0 = 0, aw1 = 0, aw2 = 0, T0 = clock64();)
     for (int64_t t = blockIdx.x; t < ntiles && ok; t += gridDim.x, ++tl) {
       const uint32_t buf = (uint32_t)(tl & 1);
       const uint32_t ph = (uint32_t)(tl >> 1) & 1u;
       const int64_t row0 = t * kRows;
       const int rows = (int)min((int64_t)kRows, N - row0);
-      int oldl = -1;
-      if (count_changes && row < rows) oldl = labels[row0 + row];
+      const int oldl = oldl_next;                      // previous labels: fetched one tile ahead
+      {
+        const int64_t rn = row0 + (int64_t)gridDim.x * kRows + row;
+        oldl_next = (count_changes && rn < N) ? labels[rn] : -1;
+      }
+      KPROF(long long c0 = clock64();)
       ok = __all_sync(0xffffffffu, wait_bar(B, &B->acc_full[buf], ph));
+      KPROF(aw0 += clock64() - c0;)
       if (!ok) break;
       tc_fence_after();
       uint32_t v[32];
@@ -307,8 +405,9 @@ kmeans_assign_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* _
       float bestd = fmaf(-2.f, __uint_as_float(v[0]) + __uint_as_float(v[16]), scn[0]);
 #pragma unroll
       for (int k = 1; k < 16; ++k) {
+        if (k >= K) break;                                              // (uniform)
         const float dk = fmaf(-2.f, __uint_as_float(v[k]) + __uint_as_float(v[16 + k]), scn[k]);   // ||c||^2 - 2 x.c
-        if (k < K && dk < bestd) {                                      // strict '<': lowest index wins ties
+        if (dk < bestd) {                                               // strict '<': lowest index wins ties
           bestd = dk;
           best = k;
         }
@@ -319,22 +418,20 @@ kmeans_assign_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* _
       }
       if (want_sums) {
         // stable counting sort of the tile's 128 rows by label (bin 16 = rows past N): position = rows of smaller
-        // bins + rows of the same bin in earlier warps + rank inside the warp
+        // bins + rows of the same bin in earlier warps + rank inside the warp.  Every warp owns one row of the count
+        // table; the row of the OTHER buffer is cleared after the barrier (its readers passed the previous barrier).
         const int bin = row < rows ? best : 16;
-        int mycnt = 0, myrank = 0;
-#pragma unroll
-        for (int b = 0; b <= 16; ++b) {
-          if (b < K || b == 16) {
-            const uint32_t m = __ballot_sync(0xffffffffu, bin == b);
-            if (lane == b) mycnt = __popc(m);
-            if (bin == b) myrank = __popc(m & lt_mask);
-          }
-        }
+        const uint32_t peers = __match_any_sync(0xffffffffu, bin);
+        const int myrank = __popc(peers & lt_mask);
         int* wc = wcnt + (int)buf * 128;
-        wc[q * 32 + lane] = mycnt;                     // lanes >= 17 hold 0
+        if (myrank == 0) wc[q * 32 + bin] = __popc(peers);
+        KPROF(long long k1 = clock64();)
         named_bar_sync(1, 32 * kNArg);
+        KPROF(aw1 += clock64() - k1;)
         const int c0 = wc[lane], c1 = wc[32 + lane], c2 = wc[64 + lane], c3 = wc[96 + lane];
+        wcnt[(int)(buf ^ 1u) * 128 + q * 32 + lane] = 0;
         const int tot = c0 + c1 + c2 + c3;
+        if (lane < 16) mycount += q == 0 ? c0 : (q == 1 ? c1 : (q == 2 ? c2 : c3));
         int incl = tot;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -343,85 +440,112 @@ kmeans_assign_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* _
         }
         const int base = incl - tot + (q > 0 ? c0 : 0) + (q > 1 ? c1 : 0) + (q > 2 ? c2 : 0);
         const int pos = __shfl_sync(0xffffffffu, base, bin) + myrank;
+        KPROF(long long k2 = clock64();)
         ok = __all_sync(0xffffffffu, wait_bar(B, &B->lab_free[buf], ph ^ 1u));
+        KPROF(aw2 += clock64() - k2;)
         if (!ok) break;
         ssort[buf * kRows + pos] = (bin << 8) | row;
         __syncwarp();
         if (lane == 0) mbar_arrive(&B->lab_full[buf]);
       }
     }
+    if (lane < 16) scnt[q * 16 + lane] = mycount;       // rows per cluster seen by this warp
+    KPROF(if (blockIdx.x == 0 && lane == 0 && q == 0) printf("argmin: total %lld wait_acc_full %lld bar %lld wait_lab_free %lld\n", clock64() - T0, aw0, aw1, aw2);)
   } else if (want_sums) {
-    // ================= M-step accumulation: warp = (part g of the sorted rows, chunk ch), lane = 8 bytes of the chunk ====
-    // Runs of equal labels are summed in registers and flushed into the warp's private sacc[g][label] row when the label
-    // changes: the label is an address, no atomics, fixed order (deterministic).
+    // ================= M-step accumulation: warp = (part g of the sorted rows, chunk ch) =================
+    // A half-warp owns 8 consecutive sorted rows per step and a lane 16 bytes of the 256-byte chunk row: runs of equal
+    // labels are summed in registers and flushed into the warp's private sacc[g][label] row when the label changes
+    // (the label is an address: no atomics, fixed order, deterministic).  The two half-warps of a warp walk
+    // consecutive ranges, so their flush targets differ except for the last run of the first against the second's:
+    // that one is handed over by shuffle.  Rows past N are zero (TMA fill) and carry bin 16: never flushed.
     const int w = warp - (2 + kNLo + kNArg);
     const int g = w % G, ch = w / G;
-    const int hf = lane >> 4, c = (lane & 15) >> 1, sub = lane & 1;
-    constexpr int NPOS = kRows / G;
-    int* cnt = scnt + w * 16;
-    float2* acc0 = reinterpret_cast<float2*>(sacc + (size_t)g * K * D + ch * 64) + lane;
+    const int h = lane >> 4, cc = lane & 15;
+    constexpr int NPOS = kRows / G;                   // sorted rows per warp: 16 / 32 / 64
+    float4* acc0 = reinterpret_cast<float4*>(sacc + (size_t)g * K * D + ch * 64) + cc;
     int64_t tl = 0;
     bool ok = true;
+    KPROF(long long w0 = 0, T0 = clock64();)
     for (int64_t t = blockIdx.x; t < ntiles && ok; t += gridDim.x, ++tl) {
       const uint32_t buf = (uint32_t)(tl & 1);
       // ring positions of this warp's two units of the tile (halves of chunk ch)
       const int64_t u0 = tl * UPT + 2 * ch;
       const int s0 = (int)(u0 % nu), s1 = (int)((u0 + 1) % nu);
       const uint32_t p0 = (uint32_t)(u0 / nu) & 1u, p1 = (uint32_t)((u0 + 1) / nu) & 1u;
-      ok = wait_bar(B, &B->lab_full[buf], (uint32_t)(tl >> 1) & 1u) && wait_bar(B, &B->full[s0], p0) &&
-           wait_bar(B, &B->full[s1], p1);                      // (the units are long complete: acquire only)
+      KPROF(long long c0 = clock64();)
+      ok = wait_bar(B, &B->lab_full[buf], (uint32_t)(tl >> 1) & 1u);
+      if (!MG) ok = ok && wait_bar(B, &B->full[s0], p0) && wait_bar(B, &B->full[s1], p1);   // (long complete: acquire only)
       ok = __all_sync(0xffffffffu, ok);
+      KPROF(w0 += clock64() - c0;)
       if (!ok) break;
-      const unsigned char* ub = units + (size_t)(hf ? s1 : s0) * kUnitB + sub * 8;
-      const int4* srt = reinterpret_cast<const int4*>(ssort + buf * kRows + g * NPOS);
-      int cur = -1, run = 0;
-      float2 acc = make_float2(0.f, 0.f);
-      auto flush = [&]() {
-        if (cur >= 0) {
-          float2* dst = acc0 + (size_t)cur * (D / 2);
-          float2 a = *dst;
-          a.x += acc.x;
-          a.y += acc.y;
-          *dst = a;
-          if (ch == 0 && lane == 0) cnt[cur] += run;
+      const unsigned char* ub = units + (size_t)((cc & 8) ? s1 : s0) * kUnitB;
+      const float4* xg = reinterpret_cast<const float4*>(X + (size_t)t * kRows * D + ch * 64) + cc;
+      const int4* srt = reinterpret_cast<const int4*>(ssort + buf * kRows + g * NPOS + h * (NPOS / 2));
+      auto flush = [&](int lab, const float4& a) {
+        if (lab < 16) {
+          float4* dst = acc0 + (size_t)lab * (D / 4);
+          float4 o = *dst;
+          o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+          *dst = o;
         }
       };
-      bool more = !(DIC_KTC_SKIP & 4);
-      for (int i = 0; i < NPOS / 4 && more; ++i) {
-        const int4 ev = srt[i];
-        const int e[4] = {ev.x, ev.y, ev.z, ev.w};
-        float2 x[4];
+      int cur = 0;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (!(DIC_KTC_SKIP & 4)) {
+#pragma unroll 1
+        for (int st = 0; st < NPOS / 16; ++st) {
+          const int4 ea = srt[2 * st], eb = srt[2 * st + 1];
+          const int e[8] = {ea.x, ea.y, ea.z, ea.w, eb.x, eb.y, eb.z, eb.w};
+          float4 x[8];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int r2 = e[j] & 255;
-          x[j] = *reinterpret_cast<const float2*>(ub + (r2 >> 3) * 1024 + (r2 & 7) * 128 + ((c ^ (r2 & 7)) << 4));
-        }
+          for (int j = 0; j < 8; ++j) {
+            const int r = e[j] & 255;
+            if (MG)
+              x[j] = (e[j] >> 8) < 16 ? __ldg(xg + (size_t)r * (D / 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            else
+              x[j] = *reinterpret_cast<const float4*>(ub + ((((r << 3) | ((r ^ cc) & 7))) << 4));
+          }
+          if (st == 0) cur = e[0] >> 8;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int lab = e[j] >> 8;
-          if (lab == 16) more = false;                 // rows past N sort last
-          if (more) {
+          for (int j = 0; j < 8; ++j) {
+            const int lab = e[j] >> 8;
             if (lab != cur) {
-              flush();
+              flush(cur, acc);
               cur = lab;
               acc = x[j];
-              run = 1;
             } else {
-              acc.x += x[j].x;
-              acc.y += x[j].y;
-              ++run;
+              acc.x += x[j].x; acc.y += x[j].y; acc.z += x[j].z; acc.w += x[j].w;
             }
           }
         }
+        // Last runs.  In sorted order the flush targets of the two half-warps differ (first half < second half) unless
+        // the whole second half continues the first half's last label: then the first half's sum is handed over.
+        __syncwarp();
+        const int last1 = __shfl_sync(0xffffffffu, cur, 0), last2 = __shfl_sync(0xffffffffu, cur, 16);
+        if (last1 == last2) {
+          float4 o;
+          o.x = __shfl_xor_sync(0xffffffffu, acc.x, 16);
+          o.y = __shfl_xor_sync(0xffffffffu, acc.y, 16);
+          o.z = __shfl_xor_sync(0xffffffffu, acc.z, 16);
+          o.w = __shfl_xor_sync(0xffffffffu, acc.w, 16);
+          if (h == 1) {
+            acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+            flush(cur, acc);
+          }
+        } else {
+          flush(cur, acc);
+        }
       }
-      flush();
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(&B->slot_free[s0]);
-        mbar_arrive(&B->slot_free[s1]);
+        if (!MG) {
+          mbar_arrive(&B->slot_free[s0]);
+          mbar_arrive(&B->slot_free[s1]);
+        }
         mbar_arrive(&B->lab_free[buf]);
       }
     }
+    KPROF(if (blockIdx.x == 0 && lane == 0 && w == 0) printf("mstep: total %lld wait_lab_full %lld\n", clock64() - T0, w0);)
   }
   tc_fence_before();
   __syncthreads();
@@ -458,6 +582,7 @@ kmeans_assign_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* _
     tc_fence_after();
     tmem_dealloc(tmem, kTmemCols);
   }
+  KPROF(if (blockIdx.x == 0 && tid == 0) printf("kernel: %lld clk\n", clock64() - kT0);)
 }
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda).
@@ -512,18 +637,25 @@ int launch_kmeans_assign_tc(const float* X, const float* centers, int32_t* label
               (long long)N, D);
 
   const int NCH = D / 64;
+#ifdef DIC_KTC_MAXU
+  int nu = DIC_KTC_MAXU < 2 * NCH ? 2 * NCH : DIC_KTC_MAXU;
+#else
   int nu = kMaxUnits;
+#endif
   while (nu > 2 * NCH && tc_plan(NCH, K, nu).total > (size_t)kMaxSmemBytes) --nu;
   const size_t smem = tc_plan(NCH, K, nu).total;
   DIC_REQUIRE(smem <= (size_t)kMaxSmemBytes, DIC_ERR_UNSUPPORTED, "tensor-core Lloyd pass: %zu bytes of shared memory",
               smem);
-#define DIC_KTC(NCH_)                                                                                          \
+#ifndef DIC_KTC_MG128
+#define DIC_KTC_MG128 false
+#endif
+#define DIC_KTC(NCH_, MG_)                                                                                     \
   {                                                                                                            \
-    auto kf = kmeans_assign_tc_kernel<NCH_>;                                                                   \
+    auto kf = kmeans_assign_tc_kernel<NCH_, MG_>;                                                              \
     DIC_CUDA(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                \
-    kf<<<nb, kTcThreads, smem, st>>>(tmap, centers, labels, ws, N, K, flags, want_sums, nu, done);             \
+    kf<<<nb, kTcThreads, smem, st>>>(tmap, X, centers, labels, ws, N, K, flags, want_sums, nu, done);          \
   }
-  if (D == 64) DIC_KTC(1) else if (D == 128) DIC_KTC(2) else DIC_KTC(4)
+  if (D == 64) DIC_KTC(1, false) else if (D == 128) DIC_KTC(2, DIC_KTC_MG128) else DIC_KTC(4, true)
 #undef DIC_KTC
   DIC_LAUNCH_CHECK("kmeans_assign_tc_kernel");
   return DIC_OK;
