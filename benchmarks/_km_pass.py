@@ -3,7 +3,7 @@ import sys, json, torch
 sys.path.insert(0, '.')
 from deep_interpolation_clustering_b200 import synth
 from deep_interpolation_clustering_b200.kmeans import _Device
-KERNELS = (("auto", 0), ("tile2", 1), ("rw", 2), ("tile", 3), ("tc", 5))
+KERNELS = (("auto", 0), ("tile2", 1), ("rw", 2), ("tile", 3), ("tc", 5), ("tc64", 6))
 out = {}
 for D, N in ((64, 1_000_000), (128, 500_000), (256, 500_000)):
     X32 = torch.from_numpy(synth.make_blobs(N, D, 5, seed=4)).cuda()

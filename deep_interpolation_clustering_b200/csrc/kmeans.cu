@@ -29,6 +29,9 @@ int launch_cluster_rowsums_tc(const float* X, const int32_t* perm, const int32_t
 bool kmeans_tc_covers(const void* X, int D, int K, int flags);
 int launch_kmeans_assign_tc(const float* X, const float* centers, int32_t* labels, double* ws, int64_t N, int D, int K,
                             int flags, int want_sums, const double* done, int max_blocks, int* nb_out, cudaStream_t st);
+bool kmeans_tc64_covers(const void* X, int D, int K, int flags);
+int launch_kmeans_assign_tc64(const double* X, const double* centers, int32_t* labels, double* ws, int64_t N, int K,
+                              int flags, int want_sums, const double* done, int max_blocks, int* nb_out, cudaStream_t st);
 
 namespace {
 
@@ -1213,6 +1216,8 @@ static bool kmeans_tc_wins(int64_t N, int D, int K) {
   return false;
 }
 
+static bool kmeans_tc64_wins(int64_t N, int K) { return false && N >= 0 && K >= 1; }
+
 template <typename T>
 int launch_assign(const void* X, const void* centers, int32_t* labels, double* sums, double* counts,
                   double* stats, void* workspace, int64_t N, int D, int K, int flags, cudaStream_t st,
@@ -1220,7 +1225,7 @@ int launch_assign(const void* X, const void* centers, int32_t* labels, double* s
   // bits 8..11 of flags: 0 = pick by shape and measured cost; 1..4 = that kernel or DIC_ERR_UNSUPPORTED (parity tests
   // and benchmarks address every kernel through the ABI; nothing here reads the environment)
   const int which = (flags >> 8) & 15;
-  DIC_REQUIRE(which <= 5, DIC_ERR_INVALID_ARGUMENT, "DIC_KM_KERNEL(%d): unknown kernel", which);
+  DIC_REQUIRE(which <= 6, DIC_ERR_INVALID_ARGUMENT, "DIC_KM_KERNEL(%d): unknown kernel", which);
   // tensor-core E-step (kmeans_tc.cu): float32 rows of 64 / 128 / 256 elements in the Lloyd-loop form of the pass
   if constexpr (sizeof(T) == 4) {
     const bool tc_ok = kmeans_tc_covers(X, D, K, flags);
@@ -1238,8 +1243,24 @@ int launch_assign(const void* X, const void* centers, int32_t* labels, double* s
       DIC_LAUNCH_CHECK("kmeans_finish_kernel");
       return DIC_OK;
     }
+    DIC_REQUIRE(which != 6, DIC_ERR_UNSUPPORTED, "DIC_KM_KERNEL(6): the float64 tensor-core pass is float64 only");
   } else {
     DIC_REQUIRE(which != 5, DIC_ERR_UNSUPPORTED, "DIC_KM_KERNEL(5): the tensor-core pass is float32 only");
+    // float64 rows of 64 elements (the gap statistic's reference sets): tensor-core screen + exact rows (kmeans_tc.cu)
+    const bool tc_ok = kmeans_tc64_covers(X, D, K, flags);
+    DIC_REQUIRE(tc_ok || which != 6, DIC_ERR_UNSUPPORTED, "DIC_KM_KERNEL(6): the float64 tensor-core pass covers D = 64, "
+                "K <= 16 with DIC_KM_NO_INERTIA and without DIC_KM_KEEP_LABELS (got D=%d K=%d flags=%d)", D, K, flags & 255);
+    if (tc_ok && (which == 6 || (which == 0 && kmeans_tc64_wins(N, K)))) {
+      double* wsd = static_cast<double*>(workspace);
+      int nb = 0;
+      int rc = launch_kmeans_assign_tc64(static_cast<const double*>(X), static_cast<const double*>(centers), labels, wsd, N,
+                                         K, flags, sums != nullptr, done, km_blocks(K, D), &nb, st);
+      if (rc) return rc;
+      const int nn = K * D + K + 4;
+      kmeans_finish_kernel<<<(nn + 7) / 8, 256, 0, st>>>(wsd, sums, counts, stats, nb, K, D, done);
+      DIC_LAUNCH_CHECK("kmeans_finish_kernel");
+      return DIC_OK;
+    }
   }
   // specialised tile kernel: rows of exactly 16, 32 or 64 sixteen-byte vectors (D = 64 / 128 / 256 float32,
   // 32 / 64 / 128 float64).  64 vectors (the reference's latent width, D = 256) leave room for ONE resident CTA per

@@ -585,6 +585,413 @@ kmeans_assign_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* _
   KPROF(if (blockIdx.x == 0 && tid == 0) printf("kernel: %lld clk\n", clock64() - kT0);)
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// float64 rows (the reference sets of the gap statistic are numpy float64 draws, p2_clustering_optK.py:353-410), D = 64.
+// The tensor core SCREENS: every double is split into two tf32 halves (hi = trunc_tf32(float(x)), lo = rn_tf32(x - hi)),
+// both written to tensor memory as A operands (TS MMAs: no shared-memory operand traffic at all), and the float32-grade
+// distances decide the label wherever the margin between the two nearest centres exceeds their error bound
+// 2^-17 (|x|^2 + max|c|^2) (the products carry < 2^-21 |x||c| each).  Rows inside the bound - a few per million - are
+// re-evaluated exactly, direct (x - c)^2 in float64 from the resident tile, by the whole warp.  Sums are float64.
+// Units are 128 rows x 16 doubles (128 bytes, SWIZZLE_128B: conflict-free row reads), 4 per tile.
+struct Tc64Plan {
+  int nu;
+  size_t bt, cen, sacc, scn32, scn64, xn, ssort, wcnt, bars, total;
+};
+__host__ __device__ inline Tc64Plan tc64_plan(int K, int nu) {
+  Tc64Plan p;
+  p.nu = nu;
+  p.bt = (size_t)nu * kUnitB;
+  p.cen = p.bt + kBTileB;                                     // [16][64] doubles (exact re-evaluation)
+  p.sacc = p.cen + 16 * 64 * 8;                               // [8][K][64] doubles
+  p.scn32 = p.sacc + (size_t)8 * K * 64 * 8;
+  p.scn64 = p.scn32 + 64;
+  p.xn = p.scn64 + 128;                                       // [2][128] floats: |x|^2 of the rows of a tile
+  p.ssort = p.xn + 2 * kRows * 4;
+  p.wcnt = p.ssort + 2 * kRows * 4;
+  p.bars = p.wcnt + 2 * 4 * 32 * 4;
+  p.total = p.bars + sizeof(TcBars) + 1024;
+  return p;
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+kmeans_assign_tc64_kernel(const __grid_constant__ CUtensorMap tmap, const double* __restrict__ centers, int32_t* labels,
+                          double* __restrict__ ws, int64_t N, int K, int flags, int want_sums, int nu,
+                          const double* __restrict__ done) {
+  if (done && *done != 0.0) return;
+  constexpr int D = 64, UPT = 4;
+  constexpr uint32_t kHi = 64, kLo = 96;                       // TMEM columns: [0,64) accumulators, 2 x 16 hi, 2 x 16 lo
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const Tc64Plan P = tc64_plan(K, nu);
+  unsigned char* units = smem;
+  unsigned char* bt = smem + P.bt;
+  double* cen = reinterpret_cast<double*>(smem + P.cen);
+  double* sacc = reinterpret_cast<double*>(smem + P.sacc);
+  float* scn32 = reinterpret_cast<float*>(smem + P.scn32);
+  double* scn64 = reinterpret_cast<double*>(smem + P.scn64);
+  float* xnorm = reinterpret_cast<float*>(smem + P.xn);
+  int* ssort = reinterpret_cast<int*>(smem + P.ssort);
+  int* wcnt = reinterpret_cast<int*>(smem + P.wcnt);
+  TcBars* B = reinterpret_cast<TcBars*>(smem + P.bars);
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
+
+  if (tid == 0) {
+    for (int s = 0; s < kMaxUnits; ++s) {
+      mbar_init(&B->full[s], 1);
+      mbar_init(&B->slot_free[s], kNLo + kNArg + (want_sums ? kNAcc : 0));   // split, arg-min (exact rows), M-step
+    }
+    for (int k = 0; k < 2; ++k) {
+      mbar_init(&B->lo_full[k], kNLo);
+      mbar_init(&B->lo_free[k], 1);
+      mbar_init(&B->acc_full[k], 1);
+      mbar_init(&B->acc_free[k], kNArg);
+      mbar_init(&B->lab_full[k], kNArg);
+      mbar_init(&B->lab_free[k], kNAcc);
+    }
+    B->timeout = 0;
+    fence_proxy_async();
+  }
+  if (warp == 0) tmem_alloc(&B->tmem_base, 128);
+  // centres: float64 copy, stacked split tf32 operand tile [K chunk][16 hi rows | 16 lo rows][16 bytes], norms
+  for (int idx = tid; idx < 256; idx += kTcThreads) {
+    const int n = idx & 15, c16 = idx >> 4;
+    float h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const double c = n < K ? centers[(size_t)n * D + c16 * 4 + i] : 0.0;
+      cen[n * D + c16 * 4 + i] = c;
+      h[i] = to_tf32((float)c);
+      l[i] = to_tf32((float)(c - (double)h[i]));
+    }
+    const int off = c16 * kLboB + n * 16;
+    *reinterpret_cast<float4*>(bt + off) = make_float4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<float4*>(bt + off + 256) = make_float4(l[0], l[1], l[2], l[3]);
+  }
+  if (want_sums)
+    for (int i = tid; i < 8 * K * 64; i += kTcThreads) sacc[i] = 0.0;
+  for (int i = tid; i < 2 * 4 * 32; i += kTcThreads) wcnt[i] = 0;
+  if (tid < 256) {                               // ||c_k||^2: 16 lanes per centre
+    const int k = tid >> 4, l16 = tid & 15;
+    double sum = 0.0;
+    if (k < K) {
+#pragma unroll
+      for (int d = 0; d < D / 16; ++d) {
+        const double c = centers[(size_t)k * D + d * 16 + l16];
+        sum = fma(c, c, sum);
+      }
+    }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (l16 == 0) {
+      scn64[k] = sum;
+      scn32[k] = (float)sum;
+    }
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = B->tmem_base;
+  const bool count_changes = (flags & DIC_KM_COUNT_CHANGES) != 0;
+  const int64_t ntiles = (N + kRows - 1) / kRows;
+  int changed = 0;
+  int mycount = 0;
+
+  if (warp == 0) {
+    // ================= producer =================
+    RingPos rp{0, 0u};
+    bool ok = true;
+    for (int64_t t = blockIdx.x; t < ntiles && ok; t += gridDim.x) {
+      for (int u = 0; u < UPT; ++u) {
+        ok = __all_sync(0xffffffffu, wait_bar(B, &B->slot_free[rp.slot], rp.phase ^ 1u));
+        if (!ok) break;
+        if (elect_one()) {
+          mbar_expect_tx(&B->full[rp.slot], (uint32_t)kUnitB);
+          tma_load_2d(units + (size_t)rp.slot * kUnitB, &tmap, u * 16, (int)(t * kRows), &B->full[rp.slot]);
+        }
+        rp.advance(nu);
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer: both operand halves come from tensor memory =================
+    const uint32_t tmem_u = __reduce_or_sync(0xffffffffu, tmem);
+    const uint32_t bt_u = smem_u32(bt);
+    uint32_t v = 0;
+    int64_t tl = 0;
+    bool ok = true;
+    for (int64_t t = blockIdx.x; t < ntiles && ok; t += gridDim.x, ++tl) {
+      const uint32_t buf = (uint32_t)(tl & 1);
+      const uint32_t d_tmem = tmem_u + buf * 32u;
+      for (int u = 0; u < UPT && ok; ++u, ++v) {
+        const uint32_t lb = v & 1u;
+        ok = __all_sync(0xffffffffu, wait_bar(B, &B->lo_full[lb], (v >> 1) & 1u));
+        if (u == 0) ok = ok && __all_sync(0xffffffffu, wait_bar(B, &B->acc_free[buf], ((uint32_t)(tl >> 1) & 1u) ^ 1u));
+        if (!ok) break;
+        tc_fence_after();
+        const uint32_t a_hi = tmem_u + kHi + lb * 16u, a_lo = tmem_u + kLo + lb * 16u;
+        uint64_t db[2];
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) db[ks] = make_desc_kmajor(bt_u + (u * 4 + ks * 2) * kLboB, kLboB, kSbo);
+        if (elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks) {
+            // columns [0,16): x_hi.c_hi + x_lo.c_hi, columns [16,32): x_hi.c_lo
+            umma_tf32_ts(d_tmem, a_hi + ks * 8, db[ks], kIdescTf32N32, (u > 0 || ks > 0) ? 1u : 0u);
+            umma_tf32_ts(d_tmem, a_lo + ks * 8, db[ks], kIdescTf32N16, 1u);
+          }
+          umma_commit(&B->lo_free[lb]);
+          if (u == UPT - 1) umma_commit(&B->acc_full[buf]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp < 2 + kNLo) {
+    // ================= split: thread = row; 16 doubles of a unit -> hi | lo tf32 columns in tensor memory =================
+    const int q = warp & 3, row = 32 * q + lane;
+    const uint32_t sw = (uint32_t)(row & 7);
+    const size_t roff = (size_t)row * 128;
+    RingPos rp{0, 0u};
+    uint32_t v = 0;
+    int64_t tl = 0;
+    bool ok = true;
+    for (int64_t t = blockIdx.x; t < ntiles && ok; t += gridDim.x, ++tl) {
+      float xn = 0.f;
+      for (int u = 0; u < UPT; ++u, ++v) {
+        const uint32_t lb = v & 1u;
+        ok = wait_bar(B, &B->full[rp.slot], rp.phase) && wait_bar(B, &B->lo_free[lb], ((v >> 1) & 1u) ^ 1u);
+        ok = __all_sync(0xffffffffu, ok);
+        if (!ok) break;
+        tc_fence_after();
+        const unsigned char* src = units + (size_t)rp.slot * kUnitB + roff;
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const double2 x = *reinterpret_cast<const double2*>(src + (((uint32_t)c ^ sw) << 4));
+          const double xs[2] = {x.x, x.y};
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const float f = (float)xs[i];
+            const uint32_t hb = __float_as_uint(f) & 0xFFFFE000u;
+            const float l = (float)(xs[i] - (double)__uint_as_float(hb));
+            hi[2 * c + i] = hb;
+            lo[2 * c + i] = __float_as_uint(l) + 0x1000u;
+            xn = fmaf(f, f, xn);
+          }
+        }
+        tmem_st16(tmem + ((uint32_t)(32 * q) << 16) + kHi + lb * 16u, hi);
+        tmem_st16(tmem + ((uint32_t)(32 * q) << 16) + kLo + lb * 16u, lo);
+        if (u == UPT - 1) xnorm[(tl & 1) * kRows + row] = xn;      // read by the arg-min warps after acc_full
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&B->lo_full[lb]);
+          mbar_arrive(&B->slot_free[rp.slot]);
+        }
+        rp.advance(nu);
+      }
+    }
+  } else if (warp < 2 + kNLo + kNArg) {
+    // ================= arg-min (float32 screen + exact float64 rows), counting sort =================
+    const int q = warp & 3;
+    const int row = 32 * q + lane;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    float cmax = 0.f;
+    for (int k = 0; k < K; ++k) cmax = fmaxf(cmax, scn32[k]);
+    int64_t tl = 0;
+    bool ok = true;
+    int oldl_next = -1;
+    if (count_changes && (int64_t)blockIdx.x * kRows + row < N) oldl_next = labels[(int64_t)blockIdx.x * kRows + row];
+    for (int64_t t = blockIdx.x; t < ntiles && ok; t += gridDim.x, ++tl) {
+      const uint32_t buf = (uint32_t)(tl & 1);
+      const uint32_t ph = (uint32_t)(tl >> 1) & 1u;
+      const int64_t row0 = t * kRows;
+      const int rows = (int)min((int64_t)kRows, N - row0);
+      const int oldl = oldl_next;
+      {
+        const int64_t rn = row0 + (int64_t)gridDim.x * kRows + row;
+        oldl_next = (count_changes && rn < N) ? labels[rn] : -1;
+      }
+      ok = __all_sync(0xffffffffu, wait_bar(B, &B->acc_full[buf], ph));
+      if (!ok) break;
+      tc_fence_after();
+      uint32_t v[32];
+      tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + buf * 32u, v);
+      const float xn_r = xnorm[buf * kRows + row];               // (before the accumulator is handed back)
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&B->acc_free[buf]);
+      int best = 0;
+      float b1 = fmaf(-2.f, __uint_as_float(v[0]) + __uint_as_float(v[16]), scn32[0]), b2 = 3.0e38f;
+#pragma unroll
+      for (int k = 1; k < 16; ++k) {
+        if (k >= K) break;
+        const float dk = fmaf(-2.f, __uint_as_float(v[k]) + __uint_as_float(v[16 + k]), scn32[k]);
+        if (dk < b1) {
+          b2 = b1;
+          b1 = dk;
+          best = k;
+        } else {
+          b2 = fminf(b2, dk);
+        }
+      }
+      // rows whose two nearest centres are closer than the error bound of the screen: exact float64, whole warp per row
+      const float tau = 1.52587890625e-05f * (xn_r + cmax) * 0.5f;
+      uint32_t unc = __ballot_sync(0xffffffffu, row < rows && K > 1 && (b2 - b1) <= tau);
+      if (unc) {
+        const int64_t u0 = tl * UPT;
+        const int un = lane >> 3, chunk = lane & 7;
+        const int slot = (int)((u0 + un) % nu);
+        wait_bar(B, &B->full[slot], (uint32_t)((u0 + un) / nu) & 1u);      // (long complete: acquire only)
+        while (unc) {
+          const int src = __ffs(unc) - 1;
+          unc &= unc - 1;
+          const int r = 32 * q + src;
+          const double2 xv = *reinterpret_cast<const double2*>(units + (size_t)slot * kUnitB + (size_t)r * 128 +
+                                                                ((chunk ^ (r & 7)) << 4));
+          int eb = 0;
+          double ed = 0.0;
+          for (int k = 0; k < K; ++k) {
+            const double2 cv = *reinterpret_cast<const double2*>(cen + k * D + 2 * lane);
+            const double a = xv.x - cv.x, b = xv.y - cv.y;
+            double part = fma(a, a, b * b);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+            if (k == 0 || part < ed) {
+              ed = part;
+              eb = k;
+            }
+          }
+          if (lane == src) best = eb;
+        }
+      }
+      __syncwarp();
+      if (lane == 0)
+        for (int u = 0; u < UPT; ++u) mbar_arrive(&B->slot_free[(int)((tl * UPT + u) % nu)]);
+      if (row < rows) {
+        if (count_changes) changed += (oldl != best);
+        labels[row0 + row] = best;
+      }
+      if (want_sums) {
+        const int bin = row < rows ? best : 16;
+        const uint32_t peers = __match_any_sync(0xffffffffu, bin);
+        const int myrank = __popc(peers & lt_mask);
+        int* wc = wcnt + (int)buf * 128;
+        if (myrank == 0) wc[q * 32 + bin] = __popc(peers);
+        named_bar_sync(1, 32 * kNArg);
+        const int c0 = wc[lane], c1 = wc[32 + lane], c2 = wc[64 + lane], c3 = wc[96 + lane];
+        wcnt[(int)(buf ^ 1u) * 128 + q * 32 + lane] = 0;
+        const int tot = c0 + c1 + c2 + c3;
+        if (lane < 16) mycount += q == 0 ? c0 : (q == 1 ? c1 : (q == 2 ? c2 : c3));
+        int incl = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int up = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += up;
+        }
+        const int base = incl - tot + (q > 0 ? c0 : 0) + (q > 1 ? c1 : 0) + (q > 2 ? c2 : 0);
+        const int pos = __shfl_sync(0xffffffffu, base, bin) + myrank;
+        ok = __all_sync(0xffffffffu, wait_bar(B, &B->lab_free[buf], ph ^ 1u));
+        if (!ok) break;
+        ssort[buf * kRows + pos] = (bin << 8) | row;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&B->lab_full[buf]);
+      }
+    }
+  } else if (want_sums) {
+    // ================= M-step: warp = 16 sorted rows, lane = 2 doubles of the 512-byte row; float64 run sums =================
+    const int g = warp - (2 + kNLo + kNArg);
+    const int un = lane >> 3, chunk = lane & 7;
+    double2* acc0 = reinterpret_cast<double2*>(sacc + (size_t)g * K * D) + lane;
+    int64_t tl = 0;
+    bool ok = true;
+    for (int64_t t = blockIdx.x; t < ntiles && ok; t += gridDim.x, ++tl) {
+      const uint32_t buf = (uint32_t)(tl & 1);
+      const int64_t u0 = tl * UPT;
+      const int slot = (int)((u0 + un) % nu);
+      ok = wait_bar(B, &B->lab_full[buf], (uint32_t)(tl >> 1) & 1u) &&
+           wait_bar(B, &B->full[slot], (uint32_t)((u0 + un) / nu) & 1u);   // (long complete: acquire only)
+      ok = __all_sync(0xffffffffu, ok);
+      if (!ok) break;
+      const unsigned char* ub = units + (size_t)slot * kUnitB;
+      const int4* srt = reinterpret_cast<const int4*>(ssort + buf * kRows + g * 16);
+      auto flush = [&](int lab, const double2& a) {
+        if (lab < 16) {
+          double2* dst = acc0 + (size_t)lab * (D / 2);
+          double2 o = *dst;
+          o.x += a.x;
+          o.y += a.y;
+          *dst = o;
+        }
+      };
+      int cur = 0;
+      double2 acc = make_double2(0.0, 0.0);
+#pragma unroll 1
+      for (int st = 0; st < 2; ++st) {
+        const int4 ea = srt[2 * st], eb = srt[2 * st + 1];
+        const int e[8] = {ea.x, ea.y, ea.z, ea.w, eb.x, eb.y, eb.z, eb.w};
+        double2 x[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int r = e[j] & 255;
+          x[j] = *reinterpret_cast<const double2*>(ub + (((r << 3) | ((r ^ chunk) & 7)) << 4));
+        }
+        if (st == 0) cur = e[0] >> 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int lab = e[j] >> 8;
+          if (lab != cur) {
+            flush(cur, acc);
+            cur = lab;
+            acc = x[j];
+          } else {
+            acc.x += x[j].x;
+            acc.y += x[j].y;
+          }
+        }
+      }
+      flush(cur, acc);
+      __syncwarp();
+      if (lane == 0) {
+        for (int u = 0; u < UPT; ++u) mbar_arrive(&B->slot_free[(int)((u0 + u) % nu)]);
+        mbar_arrive(&B->lab_free[buf]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp >= 2 + kNLo && warp < 2 + kNLo + kNArg && lane < 16) wcnt[(warp & 3) * 16 + lane] = mycount;
+  __syncthreads();
+
+  double* out = ws + (int64_t)blockIdx.x * ((int64_t)K * D + K + 4);
+  const double nan = __longlong_as_double(0x7ff8000000000000LL);
+  const bool dead = B->timeout != 0;
+  if (want_sums) {
+    for (int i = tid; i < K * D; i += kTcThreads) {
+      double sum = 0.0;
+      for (int gg = 0; gg < 8; ++gg) sum += sacc[(size_t)gg * K * D + i];
+      out[i] = dead ? nan : sum;
+    }
+    for (int i = tid; i < K; i += kTcThreads)
+      out[(int64_t)K * D + i] = (double)(wcnt[i] + wcnt[16 + i] + wcnt[32 + i] + wcnt[48 + i]);
+  }
+  double* red = reinterpret_cast<double*>(units);
+  const double chs = warp_sum((double)changed);
+  if (lane == 0) red[warp] = chs;
+  __syncthreads();
+  if (tid == 0) {
+    double s = 0.0;
+    for (int wq = 0; wq < kTcThreads / 32; ++wq) s += red[wq];
+    out[(int64_t)K * D + K + 0] = dead ? nan : 0.0;
+    out[(int64_t)K * D + K + 1] = dead ? nan : s;
+    out[(int64_t)K * D + K + 2] = 0.0;
+    out[(int64_t)K * D + K + 3] = 0.0;
+  }
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 128);
+  }
+}
+
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda).
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -658,6 +1065,47 @@ int launch_kmeans_assign_tc(const float* X, const float* centers, int32_t* label
   if (D == 64) DIC_KTC(1, false) else if (D == 128) DIC_KTC(2, DIC_KTC_MG128) else DIC_KTC(4, true)
 #undef DIC_KTC
   DIC_LAUNCH_CHECK("kmeans_assign_tc_kernel");
+  return DIC_OK;
+}
+
+bool kmeans_tc64_covers(const void* X, int D, int K, int flags) {
+  return D == 64 && K >= 1 && K <= 16 && aligned16(X) && (flags & DIC_KM_NO_INERTIA) != 0 &&
+         (flags & DIC_KM_KEEP_LABELS) == 0;
+}
+
+// float64 rows of 64 elements; same contract as launch_kmeans_assign_tc.
+int launch_kmeans_assign_tc64(const double* X, const double* centers, int32_t* labels, double* ws, int64_t N, int K,
+                              int flags, int want_sums, const double* done, int max_blocks, int* nb_out,
+                              cudaStream_t st) {
+  int dev = 0, sms = 148;
+  DIC_CUDA(cudaGetDevice(&dev));
+  DIC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int64_t ntiles = (N + kRows - 1) / kRows;
+  int nb = sms < max_blocks ? sms : max_blocks;
+  if (ntiles < nb) nb = (int)ntiles;
+  if (nb < 1) nb = 1;
+  *nb_out = nb;
+  EncodeTiledFn encode = encode_tiled_fn();
+  DIC_REQUIRE(encode != nullptr, DIC_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  CUtensorMap tmap;
+  const cuuint64_t gdim[2] = {64u, (cuuint64_t)N};
+  const cuuint64_t gstride[1] = {64u * sizeof(double)};
+  const cuuint32_t box[2] = {16u, (cuuint32_t)kRows};
+  const cuuint32_t estr[2] = {1u, 1u};
+  const CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2u, const_cast<double*>(X), gdim, gstride, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DIC_REQUIRE(cr == CUDA_SUCCESS, DIC_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for N=%lld (float64)", (int)cr,
+              (long long)N);
+  int nu = kMaxUnits;
+  while (nu > 4 && tc64_plan(K, nu).total > (size_t)kMaxSmemBytes) --nu;
+  const size_t smem = tc64_plan(K, nu).total;
+  DIC_REQUIRE(smem <= (size_t)kMaxSmemBytes, DIC_ERR_UNSUPPORTED, "tensor-core Lloyd pass: %zu bytes of shared memory",
+              smem);
+  auto kf = kmeans_assign_tc64_kernel;
+  DIC_CUDA(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kf<<<nb, kTcThreads, smem, st>>>(tmap, centers, labels, ws, N, K, flags, want_sums, nu, done);
+  DIC_LAUNCH_CHECK("kmeans_assign_tc64_kernel");
   return DIC_OK;
 }
 

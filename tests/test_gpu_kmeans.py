@@ -325,13 +325,14 @@ def test_stalled_pipeline_sentinel_raises():
         check_pairwise_sums([1.0, float("nan")])
 
 
-@pytest.mark.parametrize("dtag,D,K", [("f32", 64, 4), ("f32", 64, 10), ("f64", 64, 4), ("f32", 256, 10), ("f32", 128, 16),
+@pytest.mark.parametrize("dtag,D,K", [("f32", 64, 4), ("f32", 64, 10), ("f64", 64, 4), ("f64", 64, 10), ("f64", 64, 16),
+                                      ("f64", 64, 1), ("f32", 256, 10), ("f32", 128, 16),
                                       ("f32", 100, 7), ("f64", 32, 12), ("f32", 64, 16), ("f32", 256, 4), ("f32", 128, 2),
                                       ("f32", 256, 16), ("f32", 64, 1)])
 @pytest.mark.parametrize("n", [20011, 128, 77])
 def test_every_lloyd_kernel_through_the_abi_selector(dtag, D, K, n):
     """DIC_KM_KERNEL(k) in the flags addresses each Lloyd kernel explicitly (no environment switches): all of them -
-    CUDA-core kernels 1-4 and the tcgen05 E-step kernel 5 - must produce the labels, sums, counts and changed-label
+    CUDA-core kernels 1-4, the tcgen05 E-step kernel 5 (float32) and its float64 form 6 - must produce the labels, sums, counts and changed-label
     count of the general kernel in the Lloyd-loop form of the pass; a kernel that does not cover the shape says so."""
     from deep_interpolation_clustering_b200 import synth
     from deep_interpolation_clustering_b200.kmeans import _Device
@@ -341,19 +342,22 @@ def test_every_lloyd_kernel_through_the_abi_selector(dtag, D, K, n):
     prev = torch.from_numpy(np.random.RandomState(n).randint(0, K, size=n).astype(np.int32)).cuda()
     out = {}
     base = 1 | 4                                     # DIC_KM_COUNT_CHANGES | DIC_KM_NO_INERTIA: what a Lloyd iteration passes
-    for sel in (4, 0, 1, 2, 3, 5):
+    for sel in (4, 0, 1, 2, 3, 5, 6):
         st = _Device(X, K)
         st.labels.copy_(prev)
         try:
             st.assign(cen, base | sel << 8)
         except ValueError as e:
-            assert "does not cover" in str(e) or "covers" in str(e) or "float32 only" in str(e), str(e)
+            assert "does not cover" in str(e) or "covers" in str(e) or "float32 only" in str(e) or \
+                "float64 only" in str(e), str(e)
             continue
         out[sel] = (st.labels.cpu().numpy().copy(), st.sums.cpu().numpy().copy(), st.counts.cpu().numpy().copy(),
                     st.stats.cpu().numpy().copy())
     assert 4 in out and 0 in out and len(out) >= 3
     if dtag == "f32" and D in (64, 128, 256):
         assert 5 in out, "the tensor-core pass must cover this shape"
+    if dtag == "f64" and D == 64:
+        assert 6 in out, "the float64 tensor-core pass must cover this shape"
     lab, sums, counts, stats = out[4]
     for sel, (l2, s2, c2, t2) in out.items():
         _labels_equal_mod_ties(f"selector{sel}", l2, lab, X.cpu().numpy(), cen.cpu().numpy())
