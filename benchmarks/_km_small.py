@@ -4,11 +4,15 @@ sys.path.insert(0, '.')
 from deep_interpolation_clustering_b200 import synth
 from deep_interpolation_clustering_b200.kmeans import _Device
 out = {}
-for D in (64, 128, 256):
+import os
+F64 = os.environ.get("KM_SMALL_F64") == "1"
+for D in ((64,) if F64 else (64, 128, 256)):
     for N in (10_000, 20_000, 50_000, 100_000, 300_000):
         X = torch.from_numpy(synth.make_blobs(N, D, 5, seed=4)).cuda()
+        if F64:
+            X = X.double()
         for K in (2, 4, 10, 16):
-            for kern, sel in (("tile2", 1), ("tc", 5)):
+            for kern, sel in (("tile2", 1), ("tc", 6 if F64 else 5)):
                 st = _Device(X, K)
                 cen = X[:K].clone().contiguous()
                 flags = 1 | 4 | sel << 8

@@ -1216,7 +1216,8 @@ static bool kmeans_tc_wins(int64_t N, int D, int K) {
   return false;
 }
 
-static bool kmeans_tc64_wins(int64_t N, int K) { return false && N >= 0 && K >= 1; }
+// float64 rows (D = 64): 108-157 us against 166-290 us of the CUDA-core kernel at 1M rows; at the launch floor below ~20k.
+static bool kmeans_tc64_wins(int64_t N, int K) { return N >= 50000 || (K >= 10 && N >= 16384); }
 
 template <typename T>
 int launch_assign(const void* X, const void* centers, int32_t* labels, double* sums, double* counts,

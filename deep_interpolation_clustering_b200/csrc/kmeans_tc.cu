@@ -49,7 +49,8 @@ constexpr int kMaxUnits = 12;
 constexpr int kLboB = 32 * 16;                 // centres: 32 rows (16 hi | 16 lo) x 16 bytes per K chunk (no swizzle)
 constexpr int kBTileB = 16 * kLboB;            // stacked centre tile of one 64-wide K chunk (8 KB)
 constexpr int kSbo = 128;                      // bytes between 8-row groups of the centre tiles
-constexpr int kNLo = 4, kNArg = 4, kNAcc = 8;  // warps per role
+constexpr int kNLoGroups = 2;                  // the low-half / split role: groups of 4 warps taking alternate units
+constexpr int kNLo = 4 * kNLoGroups, kNArg = 4, kNAcc = 8;  // warps per role
 constexpr int kTcThreads = 32 * (2 + kNLo + kNArg + kNAcc);
 constexpr uint32_t kIdescTf32N16 = make_idesc(2u, 128u, 16u);
 constexpr uint32_t kIdescTf32N32 = make_idesc(2u, 128u, 32u);
@@ -167,6 +168,16 @@ struct RingPos {
 // MG: the M-step re-reads the rows of a tile from global memory (L2: the tile went through it a moment ago) instead of
 // the ring, whose units are then free as soon as the MMAs have read them.  Taken for D = 256, where one 128-row tile
 // is 8 of the at most 12 units and holding it until the labels are known would serialise load and M-step.
+// Ring position `off` (< nu) units after `base` (no division: the per-tile positions are tracked incrementally).
+__device__ __forceinline__ RingPos ring_at(const RingPos& base, int off, int nu) {
+  RingPos r{base.slot + off, base.phase};
+  if (r.slot >= nu) {
+    r.slot -= nu;
+    r.phase ^= 1u;
+  }
+  return r;
+}
+
 template <int NCH, bool MG>
 __global__ void __launch_bounds__(kTcThreads, 1)
 kmeans_assign_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ X,
@@ -192,10 +203,10 @@ kmeans_assign_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* _
   if (tid == 0) {
     for (int s = 0; s < kMaxUnits; ++s) {
       mbar_init(&B->full[s], 1);
-      mbar_init(&B->slot_free[s], 1 + kNLo + (want_sums && !MG ? G : 0));   // MMAs done, low halves taken (+ M-step warps)
+      mbar_init(&B->slot_free[s], 1 + 4 + (want_sums && !MG ? G : 0));   // MMAs done, low halves taken (+ M-step warps)
     }
     for (int k = 0; k < 2; ++k) {
-      mbar_init(&B->lo_full[k], kNLo);
+      mbar_init(&B->lo_full[k], 4);
       mbar_init(&B->lo_free[k], 1);
       mbar_init(&B->acc_full[k], 1);
       mbar_init(&B->acc_free[k], kNArg);
@@ -331,6 +342,7 @@ kmeans_assign_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* _
   } else if (warp < 2 + kNLo) {
     // ================= low operand halves: thread = row, lo = rn_tf32(x - trunc_tf32(x)) -> TMEM (A operand) =========
     const int q = warp & 3, row = 32 * q + lane;
+    const uint32_t grp = (uint32_t)(warp - 2) >> 2;          // this group takes the units with (unit & 1) == grp
     const uint32_t sw = (uint32_t)(row & 7);
     const size_t roff = (size_t)(row >> 3) * 1024 + (size_t)sw * 128;
     RingPos rp{0, 0u};
@@ -340,6 +352,10 @@ kmeans_assign_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* _
     for (int64_t t = blockIdx.x; t < ntiles && ok; t += gridDim.x) {
       for (int u = 0; u < UPT; ++u, ++v) {
         const uint32_t lb = v & 1u;
+        if (lb != grp) {
+          rp.advance(nu);
+          continue;
+        }
         KPROF(long long c0 = clock64();)
         ok = wait_bar(B, &B->full[rp.slot], rp.phase);
         KPROF(long long c1 = clock64(); w0 += c1 - c0;)
@@ -464,14 +480,16 @@ kmeans_assign_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* _
     constexpr int NPOS = kRows / G;                   // sorted rows per warp: 16 / 32 / 64
     float4* acc0 = reinterpret_cast<float4*>(sacc + (size_t)g * K * D + ch * 64) + cc;
     int64_t tl = 0;
+    RingPos tp{0, 0u};                                // first unit of the current tile
     bool ok = true;
     KPROF(long long w0 = 0, T0 = clock64();)
     for (int64_t t = blockIdx.x; t < ntiles && ok; t += gridDim.x, ++tl) {
       const uint32_t buf = (uint32_t)(tl & 1);
       // ring positions of this warp's two units of the tile (halves of chunk ch)
-      const int64_t u0 = tl * UPT + 2 * ch;
-      const int s0 = (int)(u0 % nu), s1 = (int)((u0 + 1) % nu);
-      const uint32_t p0 = (uint32_t)(u0 / nu) & 1u, p1 = (uint32_t)((u0 + 1) / nu) & 1u;
+      const RingPos r0 = ring_at(tp, 2 * ch, nu), r1 = ring_at(tp, 2 * ch + 1, nu);
+      tp = ring_at(tp, UPT, nu);
+      const int s0 = r0.slot, s1 = r1.slot;
+      const uint32_t p0 = r0.phase, p1 = r1.phase;
       KPROF(long long c0 = clock64();)
       ok = wait_bar(B, &B->lab_full[buf], (uint32_t)(tl >> 1) & 1u);
       if (!MG) ok = ok && wait_bar(B, &B->full[s0], p0) && wait_bar(B, &B->full[s1], p1);   // (long complete: acquire only)
@@ -605,16 +623,18 @@ __host__ __device__ inline Tc64Plan tc64_plan(int K, int nu) {
   p.sacc = p.cen + 16 * 64 * 8;                               // [8][K][64] doubles
   p.scn32 = p.sacc + (size_t)8 * K * 64 * 8;
   p.scn64 = p.scn32 + 64;
-  p.xn = p.scn64 + 128;                                       // [2][128] floats: |x|^2 of the rows of a tile
-  p.ssort = p.xn + 2 * kRows * 4;
+  p.xn = p.scn64 + 128;                                       // [2][2][128] floats: |x|^2 of a tile's rows, per group
+  p.ssort = p.xn + 4 * kRows * 4;
   p.wcnt = p.ssort + 2 * kRows * 4;
   p.bars = p.wcnt + 2 * 4 * 32 * 4;
   p.total = p.bars + sizeof(TcBars) + 1024;
   return p;
 }
 
+template <bool MG>
 __global__ void __launch_bounds__(kTcThreads, 1)
-kmeans_assign_tc64_kernel(const __grid_constant__ CUtensorMap tmap, const double* __restrict__ centers, int32_t* labels,
+kmeans_assign_tc64_kernel(const __grid_constant__ CUtensorMap tmap, const double* __restrict__ X,
+                          const double* __restrict__ centers, int32_t* labels,
                           double* __restrict__ ws, int64_t N, int K, int flags, int want_sums, int nu,
                           const double* __restrict__ done) {
   if (done && *done != 0.0) return;
@@ -638,10 +658,10 @@ kmeans_assign_tc64_kernel(const __grid_constant__ CUtensorMap tmap, const double
   if (tid == 0) {
     for (int s = 0; s < kMaxUnits; ++s) {
       mbar_init(&B->full[s], 1);
-      mbar_init(&B->slot_free[s], kNLo + kNArg + (want_sums ? kNAcc : 0));   // split, arg-min (exact rows), M-step
+      mbar_init(&B->slot_free[s], MG ? 4 : 4 + kNArg + (want_sums ? kNAcc : 0));   // split (+ arg-min exact rows, M-step)
     }
     for (int k = 0; k < 2; ++k) {
-      mbar_init(&B->lo_full[k], kNLo);
+      mbar_init(&B->lo_full[k], 4);
       mbar_init(&B->lo_free[k], 1);
       mbar_init(&B->acc_full[k], 1);
       mbar_init(&B->acc_free[k], kNArg);
@@ -748,6 +768,7 @@ kmeans_assign_tc64_kernel(const __grid_constant__ CUtensorMap tmap, const double
   } else if (warp < 2 + kNLo) {
     // ================= split: thread = row; 16 doubles of a unit -> hi | lo tf32 columns in tensor memory =================
     const int q = warp & 3, row = 32 * q + lane;
+    const uint32_t grp = (uint32_t)(warp - 2) >> 2;          // this group takes the units with (unit & 1) == grp
     const uint32_t sw = (uint32_t)(row & 7);
     const size_t roff = (size_t)row * 128;
     RingPos rp{0, 0u};
@@ -758,6 +779,10 @@ kmeans_assign_tc64_kernel(const __grid_constant__ CUtensorMap tmap, const double
       float xn = 0.f;
       for (int u = 0; u < UPT; ++u, ++v) {
         const uint32_t lb = v & 1u;
+        if (lb != grp) {
+          rp.advance(nu);
+          continue;
+        }
         ok = wait_bar(B, &B->full[rp.slot], rp.phase) && wait_bar(B, &B->lo_free[lb], ((v >> 1) & 1u) ^ 1u);
         ok = __all_sync(0xffffffffu, ok);
         if (!ok) break;
@@ -780,7 +805,7 @@ kmeans_assign_tc64_kernel(const __grid_constant__ CUtensorMap tmap, const double
         }
         tmem_st16(tmem + ((uint32_t)(32 * q) << 16) + kHi + lb * 16u, hi);
         tmem_st16(tmem + ((uint32_t)(32 * q) << 16) + kLo + lb * 16u, lo);
-        if (u == UPT - 1) xnorm[(tl & 1) * kRows + row] = xn;      // read by the arg-min warps after acc_full
+        if (u >= UPT - 2) xnorm[((tl & 1) * 2 + grp) * kRows + row] = xn;   // this group's half of |x|^2 (arg-min warps)
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
@@ -798,6 +823,7 @@ kmeans_assign_tc64_kernel(const __grid_constant__ CUtensorMap tmap, const double
     float cmax = 0.f;
     for (int k = 0; k < K; ++k) cmax = fmaxf(cmax, scn32[k]);
     int64_t tl = 0;
+    RingPos tp{0, 0u};                                // first unit of the current tile
     bool ok = true;
     int oldl_next = -1;
     if (count_changes && (int64_t)blockIdx.x * kRows + row < N) oldl_next = labels[(int64_t)blockIdx.x * kRows + row];
@@ -816,7 +842,7 @@ kmeans_assign_tc64_kernel(const __grid_constant__ CUtensorMap tmap, const double
       tc_fence_after();
       uint32_t v[32];
       tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + buf * 32u, v);
-      const float xn_r = xnorm[buf * kRows + row];               // (before the accumulator is handed back)
+      const float xn_r = xnorm[buf * 2 * kRows + row] + xnorm[(buf * 2 + 1) * kRows + row];   // (before acc_free)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&B->acc_free[buf]);
@@ -838,16 +864,17 @@ kmeans_assign_tc64_kernel(const __grid_constant__ CUtensorMap tmap, const double
       const float tau = 1.52587890625e-05f * (xn_r + cmax) * 0.5f;
       uint32_t unc = __ballot_sync(0xffffffffu, row < rows && K > 1 && (b2 - b1) <= tau);
       if (unc) {
-        const int64_t u0 = tl * UPT;
         const int un = lane >> 3, chunk = lane & 7;
-        const int slot = (int)((u0 + un) % nu);
-        wait_bar(B, &B->full[slot], (uint32_t)((u0 + un) / nu) & 1u);      // (long complete: acquire only)
+        const RingPos ru = ring_at(tp, un, nu);
+        const int slot = ru.slot;
+        if (!MG) wait_bar(B, &B->full[slot], ru.phase);      // (long complete: acquire only)
         while (unc) {
           const int src = __ffs(unc) - 1;
           unc &= unc - 1;
           const int r = 32 * q + src;
-          const double2 xv = *reinterpret_cast<const double2*>(units + (size_t)slot * kUnitB + (size_t)r * 128 +
-                                                                ((chunk ^ (r & 7)) << 4));
+          const double2 xv = MG ? *(reinterpret_cast<const double2*>(X + (size_t)(row0 + r) * D) + lane)
+                                : *reinterpret_cast<const double2*>(units + (size_t)slot * kUnitB + (size_t)r * 128 +
+                                                                    ((chunk ^ (r & 7)) << 4));
           int eb = 0;
           double ed = 0.0;
           for (int k = 0; k < K; ++k) {
@@ -865,8 +892,9 @@ kmeans_assign_tc64_kernel(const __grid_constant__ CUtensorMap tmap, const double
         }
       }
       __syncwarp();
-      if (lane == 0)
-        for (int u = 0; u < UPT; ++u) mbar_arrive(&B->slot_free[(int)((tl * UPT + u) % nu)]);
+      if (!MG && lane == 0)
+        for (int u = 0; u < UPT; ++u) mbar_arrive(&B->slot_free[ring_at(tp, u, nu).slot]);
+      tp = ring_at(tp, UPT, nu);
       if (row < rows) {
         if (count_changes) changed += (oldl != best);
         labels[row0 + row] = best;
@@ -903,16 +931,18 @@ kmeans_assign_tc64_kernel(const __grid_constant__ CUtensorMap tmap, const double
     const int un = lane >> 3, chunk = lane & 7;
     double2* acc0 = reinterpret_cast<double2*>(sacc + (size_t)g * K * D) + lane;
     int64_t tl = 0;
+    RingPos tp{0, 0u};                                // first unit of the current tile
     bool ok = true;
     for (int64_t t = blockIdx.x; t < ntiles && ok; t += gridDim.x, ++tl) {
       const uint32_t buf = (uint32_t)(tl & 1);
-      const int64_t u0 = tl * UPT;
-      const int slot = (int)((u0 + un) % nu);
+      const RingPos ru = ring_at(tp, un, nu);
+      const int slot = ru.slot;
       ok = wait_bar(B, &B->lab_full[buf], (uint32_t)(tl >> 1) & 1u) &&
-           wait_bar(B, &B->full[slot], (uint32_t)((u0 + un) / nu) & 1u);   // (long complete: acquire only)
+           (MG || wait_bar(B, &B->full[slot], ru.phase));   // (long complete: acquire only)
       ok = __all_sync(0xffffffffu, ok);
       if (!ok) break;
       const unsigned char* ub = units + (size_t)slot * kUnitB;
+      const double2* xg = reinterpret_cast<const double2*>(X + (size_t)t * kRows * D) + lane;
       const int4* srt = reinterpret_cast<const int4*>(ssort + buf * kRows + g * 16);
       auto flush = [&](int lab, const double2& a) {
         if (lab < 16) {
@@ -933,7 +963,10 @@ kmeans_assign_tc64_kernel(const __grid_constant__ CUtensorMap tmap, const double
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int r = e[j] & 255;
-          x[j] = *reinterpret_cast<const double2*>(ub + (((r << 3) | ((r ^ chunk) & 7)) << 4));
+          if (MG)
+            x[j] = (e[j] >> 8) < 16 ? xg[(size_t)r * (D / 2)] : make_double2(0.0, 0.0);
+          else
+            x[j] = *reinterpret_cast<const double2*>(ub + (((r << 3) | ((r ^ chunk) & 7)) << 4));
         }
         if (st == 0) cur = e[0] >> 8;
 #pragma unroll
@@ -952,9 +985,11 @@ kmeans_assign_tc64_kernel(const __grid_constant__ CUtensorMap tmap, const double
       flush(cur, acc);
       __syncwarp();
       if (lane == 0) {
-        for (int u = 0; u < UPT; ++u) mbar_arrive(&B->slot_free[(int)((u0 + u) % nu)]);
+        if (!MG)
+          for (int u = 0; u < UPT; ++u) mbar_arrive(&B->slot_free[ring_at(tp, u, nu).slot]);
         mbar_arrive(&B->lab_free[buf]);
       }
+      tp = ring_at(tp, UPT, nu);
     }
   }
   tc_fence_before();
@@ -1102,9 +1137,12 @@ int launch_kmeans_assign_tc64(const double* X, const double* centers, int32_t* l
   const size_t smem = tc64_plan(K, nu).total;
   DIC_REQUIRE(smem <= (size_t)kMaxSmemBytes, DIC_ERR_UNSUPPORTED, "tensor-core Lloyd pass: %zu bytes of shared memory",
               smem);
-  auto kf = kmeans_assign_tc64_kernel;
+#ifndef DIC_KTC_MG64
+#define DIC_KTC_MG64 false
+#endif
+  auto kf = kmeans_assign_tc64_kernel<DIC_KTC_MG64>;
   DIC_CUDA(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kf<<<nb, kTcThreads, smem, st>>>(tmap, centers, labels, ws, N, K, flags, want_sums, nu, done);
+  kf<<<nb, kTcThreads, smem, st>>>(tmap, X, centers, labels, ws, N, K, flags, want_sums, nu, done);
   DIC_LAUNCH_CHECK("kmeans_assign_tc64_kernel");
   return DIC_OK;
 }
