@@ -32,12 +32,6 @@
 #define DIC_KTC_SKIP 0      // benchmark builds: phases removed at compile time (benchmarks/_ktc_probe.sh)
 #endif
 
-#ifdef DIC_KTC_PROF      // benchmark builds: per-role cycle counters of CTA 0, printed at the end of the pass
-#define KPROF(...) __VA_ARGS__
-#else
-#define KPROF(...)
-#endif
-
 namespace dic {
 namespace {
 
@@ -54,12 +48,8 @@ constexpr int kNLo = 4 * kNLoGroups, kNArg = 4, kNAcc = 8;  // warps per role
 constexpr int kTcThreads = 32 * (2 + kNLo + kNArg + kNAcc);
 constexpr uint32_t kIdescTf32N16 = make_idesc(2u, 128u, 16u);
 constexpr uint32_t kIdescTf32N32 = make_idesc(2u, 128u, 32u);
-#ifdef DIC_KTC_MMAVAR
-constexpr uint32_t kTmemCols = 512;
-#else
-constexpr uint32_t kTmemCols = 128;
-#endif            // [0,64): two accumulators of 32 columns; [64,128): two low-half units
-constexpr uint32_t kTmemLo = 64;
+constexpr uint32_t kTmemCols = 256;            // [0,64): two accumulators of 32 columns; [64,128): two units of high
+constexpr uint32_t kTmemHi = 64, kTmemLo = 128;   // operand halves (the raw float32 bits); [128,192): their low halves
 
 struct TcBars {
   uint64_t full[kMaxUnits], slot_free[kMaxUnits];
@@ -87,42 +77,9 @@ __host__ __device__ inline TcPlan tc_plan(int NCH, int K, int nu) {
   return p;
 }
 
-#ifndef DIC_KTC_WAIT
-#define DIC_KTC_WAIT 0
-#endif
-__device__ __forceinline__ bool bar_wait_v(uint64_t* bar, uint32_t phase) {
-#if DIC_KTC_WAIT == 0
-  return bar_wait_bounded(bar, phase);
-#else
-  for (int spin = 0; spin < (1 << 20); ++spin) {
-    uint32_t ok;
-#if DIC_KTC_WAIT == 1
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}\n"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(phase)
-        : "memory");
-    if (ok) return true;
-    __nanosleep(40);
-#else
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}\n"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(phase), "r"(2000u)
-        : "memory");
-    if (ok) return true;
-#endif
-  }
-  return false;
-#endif
-}
 __device__ __forceinline__ bool wait_bar(TcBars* B, uint64_t* bar, uint32_t phase) {
   if (*reinterpret_cast<volatile int*>(&B->timeout)) return false;
-  if (bar_wait_v(bar, phase)) return true;
+  if (bar_wait_bounded(bar, phase)) return true;
   *reinterpret_cast<volatile int*>(&B->timeout) = 1;      // a stalled hand-off ends the pass with NaN statistics, not a hang
   return false;
 }
@@ -165,9 +122,6 @@ struct RingPos {
   }
 };
 
-// MG: the M-step re-reads the rows of a tile from global memory (L2: the tile went through it a moment ago) instead of
-// the ring, whose units are then free as soon as the MMAs have read them.  Taken for D = 256, where one 128-row tile
-// is 8 of the at most 12 units and holding it until the labels are known would serialise load and M-step.
 // Ring position `off` (< nu) units after `base` (no division: the per-tile positions are tracked incrementally).
 __device__ __forceinline__ RingPos ring_at(const RingPos& base, int off, int nu) {
   RingPos r{base.slot + off, base.phase};
@@ -178,14 +132,15 @@ __device__ __forceinline__ RingPos ring_at(const RingPos& base, int off, int nu)
   return r;
 }
 
-template <int NCH, bool MG>
+// (An M-step that re-reads the tile from L2 instead of holding its units - D = 256: one tile is 8 of the <= 12 units - was
+// measured: 0.135 ms per pass while the E-step was slower, 0.18 against 0.14-0.16 ms of the resident form once the
+// front of the pipeline ran at HBM speed, because the re-read then misses L2.  Not kept.)
+template <int NCH>
 __global__ void __launch_bounds__(kTcThreads, 1)
-kmeans_assign_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ X,
-                        const float* __restrict__ centers, int32_t* labels,
+kmeans_assign_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ centers, int32_t* labels,
                         double* __restrict__ ws, int64_t N, int K, int flags, int want_sums, int nu,
                         const double* __restrict__ done) {
   if (done && *done != 0.0) return;
-  KPROF(const long long kT0 = clock64();)
   constexpr int D = 64 * NCH, G = 8 / NCH, UPT = 2 * NCH;     // units per tile
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -203,7 +158,7 @@ kmeans_assign_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* _
   if (tid == 0) {
     for (int s = 0; s < kMaxUnits; ++s) {
       mbar_init(&B->full[s], 1);
-      mbar_init(&B->slot_free[s], 1 + 4 + (want_sums && !MG ? G : 0));   // MMAs done, low halves taken (+ M-step warps)
+      mbar_init(&B->slot_free[s], 4 + (want_sums ? G : 0));   // operand halves taken (+ the M-step warps)
     }
     for (int k = 0; k < 2; ++k) {
       mbar_init(&B->lo_full[k], 4);
@@ -250,7 +205,6 @@ kmeans_assign_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* _
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  KPROF(if (blockIdx.x == 0 && tid == 0) printf("setup: %lld clk\n", clock64() - kT0);)
   const uint32_t tmem = B->tmem_base;
   const bool count_changes = (flags & DIC_KM_COUNT_CHANGES) != 0;
   const int64_t ntiles = (N + kRows - 1) / kRows;
@@ -260,12 +214,9 @@ kmeans_assign_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* _
     // ================= producer: one tensor-map copy per unit =================
     RingPos rp{0, 0u};
     bool ok = true;
-    KPROF(long long w0 = 0, T0 = clock64();)
     for (int64_t t = blockIdx.x; t < ntiles && ok; t += gridDim.x) {
       for (int u = 0; u < UPT; ++u) {
-        KPROF(long long c0 = clock64();)
         ok = __all_sync(0xffffffffu, wait_bar(B, &B->slot_free[rp.slot], rp.phase ^ 1u));
-        KPROF(w0 += clock64() - c0;)
         if (!ok) break;
         if (elect_one()) {
           mbar_expect_tx(&B->full[rp.slot], (uint32_t)kUnitB);
@@ -274,73 +225,45 @@ kmeans_assign_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* _
         rp.advance(nu);
       }
     }
-    KPROF(if (blockIdx.x == 0 && lane == 0) printf("producer: total %lld wait_slot_free %lld\n", clock64() - T0, w0);)
   } else if (warp == 1) {
     // ================= MMA issuer (whole warp in uniform control flow, tcgen05 under elect) =================
     const uint32_t tmem_u = __reduce_or_sync(0xffffffffu, tmem);
-    const uint32_t units_u = smem_u32(units), bt_u = smem_u32(bt);
-    RingPos rp{0, 0u};
-    uint32_t v = 0;                                 // unit counter (low-half ring)
+    const uint32_t bt_u = smem_u32(bt);
+    uint32_t v = 0;                                 // unit counter (operand ring in tensor memory)
     int64_t tl = 0;
     bool ok = true;
-    KPROF(long long w0 = 0, w1 = 0, w2 = 0, T0 = clock64();)
     for (int64_t t = blockIdx.x; t < ntiles && ok; t += gridDim.x, ++tl) {
       const uint32_t buf = (uint32_t)(tl & 1);
       const uint32_t d_tmem = tmem_u + buf * 32u;
       for (int u = 0; u < UPT && ok; ++u, ++v) {
         const uint32_t lb = v & 1u;
-        KPROF(long long c0 = clock64();)
-        ok = __all_sync(0xffffffffu, wait_bar(B, &B->full[rp.slot], rp.phase));
-        KPROF(long long c1 = clock64(); w0 += c1 - c0;)
-        ok = ok && __all_sync(0xffffffffu, wait_bar(B, &B->lo_full[lb], (v >> 1) & 1u));
-        KPROF(long long c2 = clock64(); w1 += c2 - c1;)
+        // (lo_full implies the unit has landed; the raw unit itself may already be recycled when nothing else holds it)
+        ok = __all_sync(0xffffffffu, wait_bar(B, &B->lo_full[lb], (v >> 1) & 1u));
         if (u == 0) ok = ok && __all_sync(0xffffffffu, wait_bar(B, &B->acc_free[buf], ((uint32_t)(tl >> 1) & 1u) ^ 1u));
-        KPROF(w2 += clock64() - c2;)
         if (!ok) break;
         tc_fence_after();
-        const uint32_t a_hi = units_u + (uint32_t)rp.slot * (uint32_t)kUnitB;
-        const uint32_t a_lo = tmem_u + kTmemLo + lb * 32u;
+        const uint32_t a_hi = tmem_u + kTmemHi + lb * 32u, a_lo = tmem_u + kTmemLo + lb * 32u;
         const uint32_t bo = bt_u + (uint32_t)((u >> 1) * kBTileB + (u & 1) * 8 * kLboB);
-        uint64_t dah[4], db[4];
+        uint64_t db[4];
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {          // one MMA consumes K = 8 tf32 = 32 bytes of every row
-          dah[ks] = make_desc_sw128(a_hi + ks * 32);
-          db[ks] = make_desc_kmajor(bo + ks * 2 * kLboB, kLboB, kSbo);
-        }
+        for (int ks = 0; ks < 4; ++ks) db[ks] = make_desc_kmajor(bo + ks * 2 * kLboB, kLboB, kSbo);   // K = 8 per MMA
         if (elect_one()) {
           if (!(DIC_KTC_SKIP & 2)) {
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
               // columns [0,16): x_hi.c_hi + x_lo.c_hi, columns [16,32): x_hi.c_lo
-#ifndef DIC_KTC_MMAVAR
-#define DIC_KTC_MMAVAR 0
-#endif
-#if DIC_KTC_MMAVAR == 0
-              umma_tf32(d_tmem, dah[ks], db[ks], kIdescTf32N32, (u > 0 || ks > 0) ? 1u : 0u);
+              umma_tf32_ts(d_tmem, a_hi + ks * 8, db[ks], kIdescTf32N32, (u > 0 || ks > 0) ? 1u : 0u);
               umma_tf32_ts(d_tmem, a_lo + ks * 8, db[ks], kIdescTf32N16, 1u);
-#elif DIC_KTC_MMAVAR == 1      // timing probe: high halves only
-              umma_tf32(d_tmem, dah[ks], db[ks], kIdescTf32N32, (u > 0 || ks > 0) ? 1u : 0u);
-#elif DIC_KTC_MMAVAR == 2      // timing probe: low halves only
-              umma_tf32_ts(d_tmem, a_lo + ks * 8, db[ks], kIdescTf32N16, (u > 0 || ks > 0) ? 1u : 0u);
-#elif DIC_KTC_MMAVAR == 3      // timing probe: four independent accumulator chains
-              umma_tf32(d_tmem + (ks & 1) * 64, dah[ks], db[ks], kIdescTf32N32, (u > 0 || ks > 1) ? 1u : 0u);
-              umma_tf32_ts(d_tmem + 128 + (ks & 1) * 64, a_lo + ks * 8, db[ks], kIdescTf32N16, (u > 0 || ks > 1) ? 1u : 0u);
-#elif DIC_KTC_MMAVAR == 4      // timing probe: N = 128 (cost of a wider instruction)
-              umma_tf32(d_tmem + 128, dah[ks], db[ks], make_idesc(2u, 128u, 128u), (u > 0 || ks > 0) ? 1u : 0u);
-#endif
             }
           }
-          umma_commit(&B->lo_free[lb]);                         // the low-half unit (TMEM) is reusable
-          umma_commit(&B->slot_free[rp.slot]);                  // the MMAs have read the raw unit
+          umma_commit(&B->lo_free[lb]);                         // the unit's operand columns (TMEM) are reusable
           if (u == UPT - 1) umma_commit(&B->acc_full[buf]);     // the tile's dots are complete
         }
         __syncwarp();
-        rp.advance(nu);
       }
     }
-    KPROF(if (blockIdx.x == 0 && lane == 0) printf("mma: total %lld wait_full %lld wait_lo_full %lld wait_acc_free %lld tiles %lld\n", clock64() - T0, w0, w1, w2, (long long)tl);)
   } else if (warp < 2 + kNLo) {
-    // ================= low operand halves: thread = row, lo = rn_tf32(x - trunc_tf32(x)) -> TMEM (A operand) =========
+    // ================= operand halves: thread = row, raw bits | lo = rn_tf32(x - trunc_tf32(x)) -> TMEM (A operand) =========
     const int q = warp & 3, row = 32 * q + lane;
     const uint32_t grp = (uint32_t)(warp - 2) >> 2;          // this group takes the units with (unit & 1) == grp
     const uint32_t sw = (uint32_t)(row & 7);
@@ -348,7 +271,6 @@ kmeans_assign_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* _
     RingPos rp{0, 0u};
     uint32_t v = 0;
     bool ok = true;
-    KPROF(long long w0 = 0, w1 = 0, T0 = clock64();)
     for (int64_t t = blockIdx.x; t < ntiles && ok; t += gridDim.x) {
       for (int u = 0; u < UPT; ++u, ++v) {
         const uint32_t lb = v & 1u;
@@ -356,26 +278,30 @@ kmeans_assign_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* _
           rp.advance(nu);
           continue;
         }
-        KPROF(long long c0 = clock64();)
         ok = wait_bar(B, &B->full[rp.slot], rp.phase);
-        KPROF(long long c1 = clock64(); w0 += c1 - c0;)
         ok = ok && wait_bar(B, &B->lo_free[lb], ((v >> 1) & 1u) ^ 1u);
         ok = __all_sync(0xffffffffu, ok);
-        KPROF(w1 += clock64() - c1;)
         if (!ok) break;
         tc_fence_after();
         const unsigned char* src = units + (size_t)rp.slot * kUnitB + roff;
-        uint32_t l[32];
+        const uint32_t t_hi = tmem + ((uint32_t)(32 * q) << 16) + kTmemHi + lb * 32u;
+        const uint32_t t_lo = tmem + ((uint32_t)(32 * q) << 16) + kTmemLo + lb * 32u;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (!(DIC_KTC_SKIP & 1)) x = *reinterpret_cast<const float4*>(src + (((uint32_t)c ^ sw) << 4));
-          l[4 * c + 0] = __float_as_uint(lo_tf32(x.x));
-          l[4 * c + 1] = __float_as_uint(lo_tf32(x.y));
-          l[4 * c + 2] = __float_as_uint(lo_tf32(x.z));
-          l[4 * c + 3] = __float_as_uint(lo_tf32(x.w));
+        for (int hh = 0; hh < 2; ++hh) {             // 16 elements at a time: raw bits = high operand, lo_tf32 = low
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (!(DIC_KTC_SKIP & 1)) x = *reinterpret_cast<const float4*>(src + (((uint32_t)(4 * hh + c) ^ sw) << 4));
+            hi[4 * c + 0] = __float_as_uint(x.x); lo[4 * c + 0] = __float_as_uint(lo_tf32(x.x));
+            hi[4 * c + 1] = __float_as_uint(x.y); lo[4 * c + 1] = __float_as_uint(lo_tf32(x.y));
+            hi[4 * c + 2] = __float_as_uint(x.z); lo[4 * c + 2] = __float_as_uint(lo_tf32(x.z));
+            hi[4 * c + 3] = __float_as_uint(x.w); lo[4 * c + 3] = __float_as_uint(lo_tf32(x.w));
+          }
+          tmem_st16(t_hi + 16 * hh, hi);
+          tmem_st16(t_lo + 16 * hh, lo);
         }
-        tmem_st32(tmem + ((uint32_t)(32 * q) << 16) + kTmemLo + lb * 32u, l);
+        tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
@@ -385,7 +311,6 @@ kmeans_assign_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* _
         rp.advance(nu);
       }
     }
-    KPROF(if (blockIdx.x == 0 && tid == 64) printf("lo: total %lld wait_full %lld wait_lo_free %lld\n", clock64() - T0, w0, w1);)
   } else if (warp < 2 + kNLo + kNArg) {
     // ================= arg-min: thread = row; then the tile's rows sorted by label for the M-step =================
     const int q = warp & 3;                           // TMEM lane quarter this warp may read
@@ -396,7 +321,6 @@ kmeans_assign_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* _
     bool ok = true;
     int oldl_next = -1;
     if (count_changes && (int64_t)blockIdx.x * kRows + row < N) oldl_next = labels[(int64_t)blockIdx.x * kRows + row];
-    KPROF(long long aw0 = 0, aw1 = 0, aw2 = 0, T0 = clock64();)
     for (int64_t t = blockIdx.x; t < ntiles && ok; t += gridDim.x, ++tl) {
       const uint32_t buf = (uint32_t)(tl & 1);
       const uint32_t ph = (uint32_t)(tl >> 1) & 1u;
@@ -407,9 +331,7 @@ kmeans_assign_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* _
         const int64_t rn = row0 + (int64_t)gridDim.x * kRows + row;
         oldl_next = (count_changes && rn < N) ? labels[rn] : -1;
       }
-      KPROF(long long c0 = clock64();)
       ok = __all_sync(0xffffffffu, wait_bar(B, &B->acc_full[buf], ph));
-      KPROF(aw0 += clock64() - c0;)
       if (!ok) break;
       tc_fence_after();
       uint32_t v[32];
@@ -441,9 +363,7 @@ kmeans_assign_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* _
         const int myrank = __popc(peers & lt_mask);
         int* wc = wcnt + (int)buf * 128;
         if (myrank == 0) wc[q * 32 + bin] = __popc(peers);
-        KPROF(long long k1 = clock64();)
         named_bar_sync(1, 32 * kNArg);
-        KPROF(aw1 += clock64() - k1;)
         const int c0 = wc[lane], c1 = wc[32 + lane], c2 = wc[64 + lane], c3 = wc[96 + lane];
         wcnt[(int)(buf ^ 1u) * 128 + q * 32 + lane] = 0;
         const int tot = c0 + c1 + c2 + c3;
@@ -456,9 +376,7 @@ kmeans_assign_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* _
         }
         const int base = incl - tot + (q > 0 ? c0 : 0) + (q > 1 ? c1 : 0) + (q > 2 ? c2 : 0);
         const int pos = __shfl_sync(0xffffffffu, base, bin) + myrank;
-        KPROF(long long k2 = clock64();)
         ok = __all_sync(0xffffffffu, wait_bar(B, &B->lab_free[buf], ph ^ 1u));
-        KPROF(aw2 += clock64() - k2;)
         if (!ok) break;
         ssort[buf * kRows + pos] = (bin << 8) | row;
         __syncwarp();
@@ -466,7 +384,6 @@ kmeans_assign_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* _
       }
     }
     if (lane < 16) scnt[q * 16 + lane] = mycount;       // rows per cluster seen by this warp
-    KPROF(if (blockIdx.x == 0 && lane == 0 && q == 0) printf("argmin: total %lld wait_acc_full %lld bar %lld wait_lab_free %lld\n", clock64() - T0, aw0, aw1, aw2);)
   } else if (want_sums) {
     // ================= M-step accumulation: warp = (part g of the sorted rows, chunk ch) =================
     // A half-warp owns 8 consecutive sorted rows per step and a lane 16 bytes of the 256-byte chunk row: runs of equal
@@ -482,7 +399,6 @@ kmeans_assign_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* _
     int64_t tl = 0;
     RingPos tp{0, 0u};                                // first unit of the current tile
     bool ok = true;
-    KPROF(long long w0 = 0, T0 = clock64();)
     for (int64_t t = blockIdx.x; t < ntiles && ok; t += gridDim.x, ++tl) {
       const uint32_t buf = (uint32_t)(tl & 1);
       // ring positions of this warp's two units of the tile (halves of chunk ch)
@@ -490,14 +406,11 @@ kmeans_assign_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* _
       tp = ring_at(tp, UPT, nu);
       const int s0 = r0.slot, s1 = r1.slot;
       const uint32_t p0 = r0.phase, p1 = r1.phase;
-      KPROF(long long c0 = clock64();)
       ok = wait_bar(B, &B->lab_full[buf], (uint32_t)(tl >> 1) & 1u);
-      if (!MG) ok = ok && wait_bar(B, &B->full[s0], p0) && wait_bar(B, &B->full[s1], p1);   // (long complete: acquire only)
+      ok = ok && wait_bar(B, &B->full[s0], p0) && wait_bar(B, &B->full[s1], p1);   // (long complete: acquire only)
       ok = __all_sync(0xffffffffu, ok);
-      KPROF(w0 += clock64() - c0;)
       if (!ok) break;
       const unsigned char* ub = units + (size_t)((cc & 8) ? s1 : s0) * kUnitB;
-      const float4* xg = reinterpret_cast<const float4*>(X + (size_t)t * kRows * D + ch * 64) + cc;
       const int4* srt = reinterpret_cast<const int4*>(ssort + buf * kRows + g * NPOS + h * (NPOS / 2));
       auto flush = [&](int lab, const float4& a) {
         if (lab < 16) {
@@ -518,10 +431,7 @@ kmeans_assign_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* _
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const int r = e[j] & 255;
-            if (MG)
-              x[j] = (e[j] >> 8) < 16 ? __ldg(xg + (size_t)r * (D / 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            else
-              x[j] = *reinterpret_cast<const float4*>(ub + ((((r << 3) | ((r ^ cc) & 7))) << 4));
+            x[j] = *reinterpret_cast<const float4*>(ub + ((((r << 3) | ((r ^ cc) & 7))) << 4));
           }
           if (st == 0) cur = e[0] >> 8;
 #pragma unroll
@@ -556,14 +466,11 @@ kmeans_assign_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* _
       }
       __syncwarp();
       if (lane == 0) {
-        if (!MG) {
-          mbar_arrive(&B->slot_free[s0]);
-          mbar_arrive(&B->slot_free[s1]);
-        }
+        mbar_arrive(&B->slot_free[s0]);
+        mbar_arrive(&B->slot_free[s1]);
         mbar_arrive(&B->lab_free[buf]);
       }
     }
-    KPROF(if (blockIdx.x == 0 && lane == 0 && w == 0) printf("mstep: total %lld wait_lab_full %lld\n", clock64() - T0, w0);)
   }
   tc_fence_before();
   __syncthreads();
@@ -600,7 +507,6 @@ kmeans_assign_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* _
     tc_fence_after();
     tmem_dealloc(tmem, kTmemCols);
   }
-  KPROF(if (blockIdx.x == 0 && tid == 0) printf("kernel: %lld clk\n", clock64() - kT0);)
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -631,10 +537,8 @@ __host__ __device__ inline Tc64Plan tc64_plan(int K, int nu) {
   return p;
 }
 
-template <bool MG>
 __global__ void __launch_bounds__(kTcThreads, 1)
-kmeans_assign_tc64_kernel(const __grid_constant__ CUtensorMap tmap, const double* __restrict__ X,
-                          const double* __restrict__ centers, int32_t* labels,
+kmeans_assign_tc64_kernel(const __grid_constant__ CUtensorMap tmap, const double* __restrict__ centers, int32_t* labels,
                           double* __restrict__ ws, int64_t N, int K, int flags, int want_sums, int nu,
                           const double* __restrict__ done) {
   if (done && *done != 0.0) return;
@@ -658,7 +562,7 @@ kmeans_assign_tc64_kernel(const __grid_constant__ CUtensorMap tmap, const double
   if (tid == 0) {
     for (int s = 0; s < kMaxUnits; ++s) {
       mbar_init(&B->full[s], 1);
-      mbar_init(&B->slot_free[s], MG ? 4 : 4 + kNArg + (want_sums ? kNAcc : 0));   // split (+ arg-min exact rows, M-step)
+      mbar_init(&B->slot_free[s], 4 + kNArg + (want_sums ? kNAcc : 0));   // split, arg-min (exact rows), M-step
     }
     for (int k = 0; k < 2; ++k) {
       mbar_init(&B->lo_full[k], 4);
@@ -805,6 +709,7 @@ kmeans_assign_tc64_kernel(const __grid_constant__ CUtensorMap tmap, const double
         }
         tmem_st16(tmem + ((uint32_t)(32 * q) << 16) + kHi + lb * 16u, hi);
         tmem_st16(tmem + ((uint32_t)(32 * q) << 16) + kLo + lb * 16u, lo);
+        tmem_st_wait();
         if (u >= UPT - 2) xnorm[((tl & 1) * 2 + grp) * kRows + row] = xn;   // this group's half of |x|^2 (arg-min warps)
         tc_fence_before();
         __syncwarp();
@@ -867,14 +772,13 @@ kmeans_assign_tc64_kernel(const __grid_constant__ CUtensorMap tmap, const double
         const int un = lane >> 3, chunk = lane & 7;
         const RingPos ru = ring_at(tp, un, nu);
         const int slot = ru.slot;
-        if (!MG) wait_bar(B, &B->full[slot], ru.phase);      // (long complete: acquire only)
+        wait_bar(B, &B->full[slot], ru.phase);      // (long complete: acquire only)
         while (unc) {
           const int src = __ffs(unc) - 1;
           unc &= unc - 1;
           const int r = 32 * q + src;
-          const double2 xv = MG ? *(reinterpret_cast<const double2*>(X + (size_t)(row0 + r) * D) + lane)
-                                : *reinterpret_cast<const double2*>(units + (size_t)slot * kUnitB + (size_t)r * 128 +
-                                                                    ((chunk ^ (r & 7)) << 4));
+          const double2 xv = *reinterpret_cast<const double2*>(units + (size_t)slot * kUnitB + (size_t)r * 128 +
+                                                                ((chunk ^ (r & 7)) << 4));
           int eb = 0;
           double ed = 0.0;
           for (int k = 0; k < K; ++k) {
@@ -892,7 +796,7 @@ kmeans_assign_tc64_kernel(const __grid_constant__ CUtensorMap tmap, const double
         }
       }
       __syncwarp();
-      if (!MG && lane == 0)
+      if (lane == 0)
         for (int u = 0; u < UPT; ++u) mbar_arrive(&B->slot_free[ring_at(tp, u, nu).slot]);
       tp = ring_at(tp, UPT, nu);
       if (row < rows) {
@@ -938,11 +842,10 @@ kmeans_assign_tc64_kernel(const __grid_constant__ CUtensorMap tmap, const double
       const RingPos ru = ring_at(tp, un, nu);
       const int slot = ru.slot;
       ok = wait_bar(B, &B->lab_full[buf], (uint32_t)(tl >> 1) & 1u) &&
-           (MG || wait_bar(B, &B->full[slot], ru.phase));   // (long complete: acquire only)
+           wait_bar(B, &B->full[slot], ru.phase);   // (long complete: acquire only)
       ok = __all_sync(0xffffffffu, ok);
       if (!ok) break;
       const unsigned char* ub = units + (size_t)slot * kUnitB;
-      const double2* xg = reinterpret_cast<const double2*>(X + (size_t)t * kRows * D) + lane;
       const int4* srt = reinterpret_cast<const int4*>(ssort + buf * kRows + g * 16);
       auto flush = [&](int lab, const double2& a) {
         if (lab < 16) {
@@ -963,10 +866,7 @@ kmeans_assign_tc64_kernel(const __grid_constant__ CUtensorMap tmap, const double
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int r = e[j] & 255;
-          if (MG)
-            x[j] = (e[j] >> 8) < 16 ? xg[(size_t)r * (D / 2)] : make_double2(0.0, 0.0);
-          else
-            x[j] = *reinterpret_cast<const double2*>(ub + (((r << 3) | ((r ^ chunk) & 7)) << 4));
+          x[j] = *reinterpret_cast<const double2*>(ub + (((r << 3) | ((r ^ chunk) & 7)) << 4));
         }
         if (st == 0) cur = e[0] >> 8;
 #pragma unroll
@@ -985,8 +885,7 @@ kmeans_assign_tc64_kernel(const __grid_constant__ CUtensorMap tmap, const double
       flush(cur, acc);
       __syncwarp();
       if (lane == 0) {
-        if (!MG)
-          for (int u = 0; u < UPT; ++u) mbar_arrive(&B->slot_free[ring_at(tp, u, nu).slot]);
+        for (int u = 0; u < UPT; ++u) mbar_arrive(&B->slot_free[ring_at(tp, u, nu).slot]);
         mbar_arrive(&B->lab_free[buf]);
       }
       tp = ring_at(tp, UPT, nu);
@@ -1079,25 +978,18 @@ int launch_kmeans_assign_tc(const float* X, const float* centers, int32_t* label
               (long long)N, D);
 
   const int NCH = D / 64;
-#ifdef DIC_KTC_MAXU
-  int nu = DIC_KTC_MAXU < 2 * NCH ? 2 * NCH : DIC_KTC_MAXU;
-#else
   int nu = kMaxUnits;
-#endif
   while (nu > 2 * NCH && tc_plan(NCH, K, nu).total > (size_t)kMaxSmemBytes) --nu;
   const size_t smem = tc_plan(NCH, K, nu).total;
   DIC_REQUIRE(smem <= (size_t)kMaxSmemBytes, DIC_ERR_UNSUPPORTED, "tensor-core Lloyd pass: %zu bytes of shared memory",
               smem);
-#ifndef DIC_KTC_MG128
-#define DIC_KTC_MG128 false
-#endif
-#define DIC_KTC(NCH_, MG_)                                                                                     \
+#define DIC_KTC(NCH_)                                                                                          \
   {                                                                                                            \
-    auto kf = kmeans_assign_tc_kernel<NCH_, MG_>;                                                              \
+    auto kf = kmeans_assign_tc_kernel<NCH_>;                                                                   \
     DIC_CUDA(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                \
-    kf<<<nb, kTcThreads, smem, st>>>(tmap, X, centers, labels, ws, N, K, flags, want_sums, nu, done);          \
+    kf<<<nb, kTcThreads, smem, st>>>(tmap, centers, labels, ws, N, K, flags, want_sums, nu, done);             \
   }
-  if (D == 64) DIC_KTC(1, false) else if (D == 128) DIC_KTC(2, DIC_KTC_MG128) else DIC_KTC(4, true)
+  if (D == 64) DIC_KTC(1) else if (D == 128) DIC_KTC(2) else DIC_KTC(4)
 #undef DIC_KTC
   DIC_LAUNCH_CHECK("kmeans_assign_tc_kernel");
   return DIC_OK;
@@ -1137,12 +1029,9 @@ int launch_kmeans_assign_tc64(const double* X, const double* centers, int32_t* l
   const size_t smem = tc64_plan(K, nu).total;
   DIC_REQUIRE(smem <= (size_t)kMaxSmemBytes, DIC_ERR_UNSUPPORTED, "tensor-core Lloyd pass: %zu bytes of shared memory",
               smem);
-#ifndef DIC_KTC_MG64
-#define DIC_KTC_MG64 false
-#endif
-  auto kf = kmeans_assign_tc64_kernel<DIC_KTC_MG64>;
+  auto kf = kmeans_assign_tc64_kernel;
   DIC_CUDA(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kf<<<nb, kTcThreads, smem, st>>>(tmap, X, centers, labels, ws, N, K, flags, want_sums, nu, done);
+  kf<<<nb, kTcThreads, smem, st>>>(tmap, centers, labels, ws, N, K, flags, want_sums, nu, done);
   DIC_LAUNCH_CHECK("kmeans_assign_tc64_kernel");
   return DIC_OK;
 }

@@ -77,8 +77,8 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
       ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
       "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
       : "memory");
-  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // One lane of a converged warp (cute::elect_one_sync): code under `if (elect_one())` is single-thread by construction.
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred = 0;

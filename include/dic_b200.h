@@ -215,7 +215,9 @@ int dic_dec_kl_fwd_bwd(const float* z, const float* mu, const double* colsum, fl
 #define DIC_KM_NO_INERTIA 4 /* skip stats[0] and stats[2] (a Lloyd iteration does not need them) */
 /* Kernel selector in bits 8..11 of `flags` (parity tests and benchmarks address every kernel through the ABI; the
  * library reads no environment variables): 0 = chosen by shape and measured cost, 1 = specialised tile kernel,
- * 2 = streaming half-warp-per-row, 3 = generic tile kernel, 4 = general kernel; a kernel that does not cover the
+ * 2 = streaming half-warp-per-row, 3 = generic tile kernel, 4 = general kernel, 5 = tcgen05 pass (float32 rows of
+ * 64 / 128 / 256 elements, K <= 16, DIC_KM_NO_INERTIA form), 6 = its float64 form (rows of 64 elements: tensor-core
+ * screen + exact float64 evaluation of the rows inside the screen's error bound); a kernel that does not cover the
  * shape answers DIC_ERR_UNSUPPORTED. */
 #define DIC_KM_KERNEL(k) ((k) << 8)
 size_t dic_kmeans_workspace_bytes(int K, int D);

@@ -372,6 +372,39 @@ def test_every_lloyd_kernel_through_the_abi_selector(dtag, D, K, n):
         _Device(X, K).assign(cen, 9 << 8)
 
 
+@pytest.mark.parametrize("dtag,D,K,sel", [("f32", 64, 10, 5), ("f32", 128, 7, 5), ("f32", 256, 4, 5), ("f64", 64, 10, 6),
+                                          ("f64", 64, 16, 6)])
+@pytest.mark.parametrize("want_sums", [True, False])
+def test_tensor_core_lloyd_pass_many_tiles_per_cta(dtag, D, K, sel, want_sums):
+    """The tcgen05 passes at a size where every CTA walks its unit ring around several times (300k rows = 16 tiles per
+    CTA; the selector test above has at most two), in the Lloyd form (sums) and the predict form (labels only: the raw
+    units are recycled as soon as the operand halves are taken), against the general CUDA-core kernel."""
+    from deep_interpolation_clustering_b200 import synth
+    from deep_interpolation_clustering_b200.kmeans import _Device
+    n = 300_017
+    dt = torch.float32 if dtag == "f32" else torch.float64
+    X = torch.from_numpy(synth.make_blobs(n, D, 6, seed=D + K)).cuda().to(dt)
+    cen = X[:K].clone().contiguous()
+    prev = torch.from_numpy(np.random.RandomState(n).randint(0, K, size=n).astype(np.int32)).cuda()
+    out = {}
+    for which in (4, sel):
+        st = _Device(X, K)
+        st.labels.copy_(prev)
+        for _ in range(2):                           # twice: the second launch must not depend on leftovers of the first
+            st.labels.copy_(prev)
+            st.assign(cen, 1 | 4 | which << 8, want_sums=want_sums)
+        out[which] = (st.labels.cpu().numpy().copy(), st.sums.cpu().numpy().copy(), st.counts.cpu().numpy().copy(),
+                      st.stats.cpu().numpy().copy())
+    lab, sums, counts, stats = out[4]
+    l2, s2, c2, t2 = out[sel]
+    assert np.isfinite(t2).all(), "stalled pipeline sentinel"
+    _labels_equal_mod_ties(f"many_tiles_{dtag}_D{D}_K{K}", l2, lab, X.cpu().numpy(), cen.cpu().numpy())
+    if want_sums and np.array_equal(l2, lab):
+        np.testing.assert_allclose(s2, sums, rtol=2e-6, atol=2e-6 * float(np.abs(sums).max()))
+        np.testing.assert_array_equal(c2, counts)
+        assert t2[1] == stats[1]
+
+
 def test_tensor_core_lloyd_pass_inside_a_fit_matches_sklearn(monkeypatch):
     """A whole fit with every Lloyd iteration forced onto the tcgen05 pass (DIC_KM_KERNEL(5)) against scikit-learn with
     the same initial centres: labels mod near-ties, centres, inertia, iteration count (D = 64 and the real latent 256)."""
