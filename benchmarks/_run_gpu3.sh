@@ -1,9 +1,10 @@
 #!/bin/bash
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-python benchmarks/_ktc_one.py > /dev/null 2>&1 || exit 1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:kmeans_assign_tc_kernel --launch-skip 2 --launch-count 1 -o gpurun_out/ktc_f32 -f python benchmarks/_ktc_one.py > gpurun_out/ncu_ktc.log 2>&1
-echo ncu rc=$?
-ncu -i gpurun_out/ktc_f32.ncu-rep --page raw --csv > gpurun_out/ktc_f32_raw.csv 2>/dev/null
-ncu -i gpurun_out/ktc_f32.ncu-rep --page source --csv > gpurun_out/ktc_f32_src.csv 2>/dev/null
-ls -la gpurun_out | tail -5
+for t in f32 f64; do
+  python benchmarks/_ktc_one.py $t > /dev/null 2>&1 || exit 1
+  timeout 300 ncu --set full --clock-control none --import-source on -k regex:kmeans_assign_tc --launch-skip 2 --launch-count 1 -o gpurun_out/ktc_$t -f python benchmarks/_ktc_one.py $t > gpurun_out/ncu_ktc_$t.log 2>&1
+  echo ncu $t rc=$?
+  ncu -i gpurun_out/ktc_$t.ncu-rep --page raw --csv > gpurun_out/ktc_${t}_raw.csv 2>/dev/null
+  ncu -i gpurun_out/ktc_$t.ncu-rep --page source --csv > gpurun_out/ktc_${t}_src.csv 2>/dev/null
+done
