@@ -442,6 +442,39 @@ def test_tensor_core_lloyd_pass_inside_a_fit_matches_sklearn(monkeypatch):
             cur = ref.cluster_centers_.copy()
 
 
+def test_float64_tensor_core_lloyd_pass_matches_sklearn_float64():
+    """The float64 form of the tcgen05 pass (DIC_KM_KERNEL(6): tensor-core screen + exact float64 rows, float64 sums) on a
+    reference-set-like matrix (uniform float64 draws, the operand of the gap statistic's fits) against scikit-learn's
+    float64 Lloyd iteration from the same centres: labels identical up to float64 near-ties, centres to 1e-12."""
+    import warnings
+    from sklearn.cluster import KMeans
+    from deep_interpolation_clustering_b200 import kmeans as km_mod
+    orig = km_mod._Device.lloyd_run
+
+    def forced(self, centers, flags, n_steps, tol):
+        return orig(self, centers, flags | 6 << 8, n_steps, tol)
+    rng = np.random.RandomState(11)
+    X = rng.uniform(-1.0, 3.0, size=(200_003, 64))
+    for K in (3, 10, 16):
+        cur = X[:K].copy()
+        for it in (1, 2):
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                ref = KMeans(n_clusters=K, init=cur, n_init=1, max_iter=1, tol=0.0).fit(X)
+            km_mod._Device.lloyd_run = forced
+            try:
+                km = km_mod.KMeansB200(n_clusters=K, init=cur, n_init=1, max_iter=1, tol=0.0).fit(X)
+            finally:
+                km_mod._Device.lloyd_run = orig
+            tag = f"tc64_fit_K{K}_it{it}"
+            _labels_equal_mod_ties(tag, km.labels_, ref.labels_, X, ref.cluster_centers_, tie=1e-9, max_frac=1e-4)
+            assert km.n_iter_ == ref.n_iter_
+            if np.array_equal(km.labels_, ref.labels_):
+                np.testing.assert_allclose(km.cluster_centers_, ref.cluster_centers_, rtol=1e-12, atol=1e-12)
+            record(tag + "_inertia", km.inertia_, ref.inertia_, 1e-10, 0)
+            cur = ref.cluster_centers_.copy()
+
+
 def test_config4_size_lloyd_matches_sklearn_with_fixed_init():
     """BASELINE config 4 size (1M x 64, K = 10): three Lloyd iterations from the same initial centres against
     scikit-learn run here on the host (sklearn/cluster/_k_means_lloyd.pyx:196-213 decides ties): labels equal except
