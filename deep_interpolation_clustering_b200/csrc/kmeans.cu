@@ -26,6 +26,7 @@ int launch_cluster_rowsums_tc(const float* X, const int32_t* perm, const int32_t
                               void* workspace, int64_t n_pad, int D, int K, cudaStream_t st);
 
 // kmeans_tc.cu
+bool kmeans_tc_available();
 bool kmeans_tc_covers(const void* X, int D, int K, int flags);
 int launch_kmeans_assign_tc(const float* X, const float* centers, int32_t* labels, double* ws, int64_t N, int D, int K,
                             int flags, int want_sums, const double* done, int max_blocks, int* nb_out, cudaStream_t st);
@@ -1233,7 +1234,7 @@ int launch_assign(const void* X, const void* centers, int32_t* labels, double* s
     DIC_REQUIRE(tc_ok || which != 5, DIC_ERR_UNSUPPORTED, "DIC_KM_KERNEL(5): the tensor-core pass covers float32, D in "
                 "{64,128,256}, K <= 16 with DIC_KM_NO_INERTIA and without DIC_KM_KEEP_LABELS (got D=%d K=%d flags=%d)", D, K,
                 flags & 255);
-    if (tc_ok && (which == 5 || (which == 0 && kmeans_tc_wins(N, D, K)))) {
+    if (tc_ok && (which == 5 || (which == 0 && kmeans_tc_wins(N, D, K) && kmeans_tc_available()))) {
       double* wsd = static_cast<double*>(workspace);
       int nb = 0;
       int rc = launch_kmeans_assign_tc(static_cast<const float*>(X), static_cast<const float*>(centers), labels, wsd, N, D, K,
@@ -1251,7 +1252,7 @@ int launch_assign(const void* X, const void* centers, int32_t* labels, double* s
     const bool tc_ok = kmeans_tc64_covers(X, D, K, flags);
     DIC_REQUIRE(tc_ok || which != 6, DIC_ERR_UNSUPPORTED, "DIC_KM_KERNEL(6): the float64 tensor-core pass covers D = 64, "
                 "K <= 16 with DIC_KM_NO_INERTIA and without DIC_KM_KEEP_LABELS (got D=%d K=%d flags=%d)", D, K, flags & 255);
-    if (tc_ok && (which == 6 || (which == 0 && kmeans_tc64_wins(N, K)))) {
+    if (tc_ok && (which == 6 || (which == 0 && kmeans_tc64_wins(N, K) && kmeans_tc_available()))) {
       double* wsd = static_cast<double*>(workspace);
       int nb = 0;
       int rc = launch_kmeans_assign_tc64(static_cast<const double*>(X), static_cast<const double*>(centers), labels, wsd, N,

@@ -944,6 +944,9 @@ EncodeTiledFn encode_tiled_fn() {
 
 }  // namespace
 
+// The passes need cuTensorMapEncodeTiled from the driver; without it the dispatcher keeps the CUDA-core kernels.
+bool kmeans_tc_available() { return encode_tiled_fn() != nullptr; }
+
 // Shapes and flags the tensor-core pass covers (see the header comment).
 bool kmeans_tc_covers(const void* X, int D, int K, int flags) {
   return (D == 64 || D == 128 || D == 256) && K >= 1 && K <= 16 && aligned16(X) &&
