@@ -1,5 +1,5 @@
 // One Lloyd pass with the E-step on the tensor cores (tcgen05 + TMEM), fed by 2-D tensor-map TMA: float32 rows of
-// 64 / 128 / 256 elements, K <= 16.  sklearn/cluster/_k_means_lloyd.pyx:23-218 (E-step: argmin_j ||c_j||^2 - 2 x.c_j,
+// 64 / 128 / 256 elements and float64 rows of 64, K <= 16.  sklearn/cluster/_k_means_lloyd.pyx:23-218 (E-step: argmin_j ||c_j||^2 - 2 x.c_j,
 // lowest index on ties; accumulation of the per-cluster sums and counts for the M-step).
 //
 // Why: the CUDA-core kernels (kmeans.cu) pay one shared-memory broadcast operand per FMA - K*D operands per row - and
@@ -11,18 +11,23 @@
 // element) into ONE operand buffer and issued the MMAs from a single thread: conversion, MMA issue and accumulation ran
 // in series, 0.145 ms per pass at 1M x 64 against 0.097-0.148 ms of the CUDA-core kernel.  Here
 //   * the rows arrive by cp.async.bulk.tensor.2d (SASS UTMALDG) through a tensor map with 128-byte swizzle, 128 rows x
-//     32 floats (16 KB) per copy, i.e. ALREADY in the K-major SWIZZLE_128B layout tcgen05.mma reads: the raw float32
-//     tile IS the high operand (kind::tf32 ignores the 13 low significand bits: hi = trunc_tf32(x), no instruction);
-//   * the low operand is lo = x - trunc_tf32(x) (exact), rounded to tf32 by an integer add of half an ulp: three
-//     instructions per element, position-identical copy (linear, bank-conflict free) into a two-unit ring;
-//   * hi.c_hi + hi.c_lo + lo.c_hi accumulate float32-grade dot products in 16 TMEM columns (error of a product
-//     < 2^-21 |x||c|, unbiased); the MMA warp runs in uniform control flow with only the tcgen05 instructions elected;
-//   * arg-min (4 warps, thread = row, tcgen05.ld) and the M-step accumulation (8 warps, warp = row group, lane = 8
-//     bytes of the row, the label is an address: no atomics, fixed order, deterministic) are separate pipeline stages
-//     linked by mbarriers, and the M-step reads the rows from the same resident raw units (all widths: no L2 re-read).
-// One persistent CTA per SM, 18 warps: TMA producer | MMA issuer | 4 low-half warps | 4 arg-min warps | 8 M-step warps.
-// Only the Lloyd-loop form of the pass (DIC_KM_NO_INERTIA, labels re-assigned) takes this kernel; the final labelling
-// pass with its direct ||x - c||^2 sums stays on the CUDA-core kernels.
+//     128 bytes (16 KB) per copy: row-wise 128-bit reads of such a unit are bank-conflict free;
+//   * the raw float32 bits ARE the high operand (kind::tf32 ignores the 13 low significand bits: hi = trunc_tf32(x), no
+//     instruction); the low operand is lo = x - trunc_tf32(x) (exact), rounded to tf32 by an integer add of half an ulp:
+//     three instructions per element; both halves are written to TENSOR MEMORY (tcgen05.st, thread = row) and the MMAs
+//     take their A operand from there (no shared-memory operand traffic for A);
+//   * x_hi.[c_hi; c_lo] (N = 32) and x_lo.c_hi (N = 16) per K step of 8 accumulate float32-grade dot products in 32 TMEM
+//     columns (error of a product < 2^-21 |x||c|, unbiased); the MMA warp runs in uniform control flow with only the
+//     tcgen05 instructions elected;
+//   * arg-min (4 warps, thread = row, tcgen05.ld) ends with a stable counting sort of the tile's rows by label, and the
+//     M-step (8 warps, half-warp = 8 consecutive sorted rows, lane = 16 bytes of the row) sums runs of equal labels in
+//     registers and flushes a run into its private accumulator row when the label changes: the label is an address, no
+//     atomics, fixed order, deterministic; the rows are read from the same resident raw units (no second read of X).
+// One persistent CTA per SM, 22 warps: TMA producer | MMA issuer | 2 x 4 operand-half warps (alternate units) | 4 arg-min
+// warps | 8 M-step warps, linked by mbarriers only.  The float64 form (reference sets of the gap statistic) follows the
+// float32 kernel below.  Only the Lloyd-loop form of the pass (DIC_KM_NO_INERTIA, labels re-assigned) takes these
+// kernels; the final labelling pass with its direct ||x - c||^2 sums stays on the CUDA-core kernels.
+// Measured: DESIGN.md section 4.5, profiles/r02_kmeans_*; phase probes: benchmarks/_ktc_probe.sh (-DDIC_KTC_SKIP).
 #include <cuda.h>
 
 #include "common.cuh"
