@@ -743,7 +743,8 @@ def c4_arm(args, rank, world, local_rank):
     ms = a.elapsed_time(b) / 3
     pairs = n_pw * (n_pw - 1) / 2
     kern["pairwise_inertia"] = {"ms": round(ms, 3), "rows": n_pw, "unordered_pairs_per_s": round(pairs / (ms * 1e-3), 1),
-                                "tflops_dense_equiv": round(3 * 2 * pairs * 2 * D / (ms * 1e-3) / 1e12, 2),
+                                # 3 split products x (2 flop per multiply-add) x D per UNORDERED pair: the tile grid is the upper triangle
+                                "tflops_dense_equiv": round(3 * 2 * pairs * D / (ms * 1e-3) / 1e12, 2),
                                 "note": "3 split-float16 MMAs per product (hi.hi + hi.lo + lo.hi), upper triangle only; "
                                         "one sqrt per pair in the epilogue"}
     if rank != 0:
