@@ -396,11 +396,12 @@ class KMeansB200:
         return st.labels.clone(), inertia, centers, n_iter
 
     def _same_as_best(self, labels, best_labels, K, comm):
-        if not comm.on:
-            return _same_clustering(labels.cpu().numpy(), best_labels.cpu().numpy(), K)
-        table = torch.zeros(K * K, dtype=torch.float64, device=labels.device)
-        table.index_add_(0, labels.long() * K + best_labels.long(), torch.ones(labels.numel(), dtype=torch.float64,
-                                                                               device=labels.device))
+        # K x K contingency table on the device (every label of one run maps to at most one label of the other:
+        # _same_clustering); the labels stay where they are.  Restarts that find the same partition with permuted
+        # labels differ in the last bits of their inertia (the order of the float32 run sums follows the labels), so
+        # this test runs for many restarts: two D2H copies of the labels and a host-side np.unique each time cost
+        # more than the restart's Lloyd iterations.
+        table = torch.bincount(labels.long() * K + best_labels.long(), minlength=K * K)[:K * K].to(torch.float64)
         comm.sum_(table)
         return bool(((table.view(K, K) > 0).sum(1) <= 1).all())
 
