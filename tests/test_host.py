@@ -128,6 +128,35 @@ def test_same_clustering_and_random_state_helpers():
     assert _check_random_state(3).uniform() == np.random.RandomState(3).uniform()
 
 
+def test_restart_comparison_on_tensors_equals_the_host_rule():
+    """KMeansB200._same_as_best (K x K contingency table where the labels live) against _same_clustering
+    (sklearn's _is_same_clustering restated) on random pairs of label vectors: equal, permuted, merged, split."""
+    import torch
+    from deep_interpolation_clustering_b200.kmeans import KMeansB200, _Comm, _same_clustering
+    comm = _Comm.__new__(_Comm)
+    comm.group, comm.on, comm.rank, comm.size = None, False, 0, 1
+    km = KMeansB200(n_clusters=4)
+    rng = np.random.RandomState(5)
+    seen = set()
+    for trial in range(60):
+        K = int(rng.randint(2, 7))
+        a = rng.randint(0, K, size=200)
+        mode = trial % 4
+        if mode == 0:
+            b = a.copy()
+        elif mode == 1:
+            b = rng.permutation(K)[a]
+        elif mode == 2:
+            b = np.where(a == K - 1, 0, a)                      # two clusters merged
+        else:
+            b = np.where((a == 0) & (rng.uniform(size=a.size) < 0.5), K - 1, a)   # one cluster split
+        want = _same_clustering(a, b, K)
+        got = km._same_as_best(torch.from_numpy(a.astype(np.int32)), torch.from_numpy(b.astype(np.int32)), K, comm)
+        assert got == want, (trial, mode, K)
+        seen.add(want)
+    assert seen == {True, False}
+
+
 @pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="reference checkout not present")
 def test_dropin_makes_reference_models_use_b200_operators():
     """pretrain_interp.Net / clustering_interp.Net (unchanged upstream files) build on top of the
