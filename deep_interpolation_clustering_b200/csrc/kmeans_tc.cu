@@ -43,7 +43,7 @@ namespace {
 using namespace tc;
 
 constexpr int kRows = 128;                     // rows per tile (M of the MMA)
-constexpr int kUnitB = kRows * 128;            // one ring unit: 128 rows x 32 floats, SWIZZLE_128B K-major (16 KB)
+constexpr int kUnitB = kRows * 128;            // one ring unit: 128 rows x 128 bytes, 128-byte swizzle (16 KB)
 constexpr int kMaxUnits = 12;
 constexpr int kLboB = 32 * 16;                 // centres: 32 rows (16 hi | 16 lo) x 16 bytes per K chunk (no swizzle)
 constexpr int kBTileB = 16 * kLboB;            // stacked centre tile of one 64-wide K chunk (8 KB)
@@ -87,13 +87,6 @@ __device__ __forceinline__ bool wait_bar(TcBars* B, uint64_t* bar, uint32_t phas
   if (bar_wait_bounded(bar, phase)) return true;
   *reinterpret_cast<volatile int*>(&B->timeout) = 1;      // a stalled hand-off ends the pass with NaN statistics, not a hang
   return false;
-}
-
-// K-major SWIZZLE_128B operand (cute::UMMA::SmemDescriptor): start >> 4 | LBO (unused for swizzled K-major) = 1 |
-// SBO = 1024 bytes between 8-row groups | version 1 | layout type 2 at [61,64).
-__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
-  return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) |
-         (2ull << 61);
 }
 
 __device__ __forceinline__ void tma_load_2d(void* dst_smem, const CUtensorMap* tmap, int c0, int c1, uint64_t* bar) {
