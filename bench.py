@@ -397,6 +397,41 @@ def other_configs(args, rank, world, dev):
                                     "kmeans_fits_per_sweep": 9 * 3 * 2, "pairwise_evaluations_per_sweep": 27,
                                     "parallelism": f"task-parallel x{world}"},
                          "best_k": int(df["gap"].astype(float).idxmax())}
+    # the kernel the sweep spends its time in, live: one Lloyd pass (K = 10, loop form) over the data matrix (float32) and
+    # over a reference-set-sized float64 matrix, against the measured HBM figure (matrices larger than L2)
+    try:
+        from deep_interpolation_clustering_b200.kmeans import _Device
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        stream = torch.cuda.current_stream(dev)
+        passes = {}
+        for name, Xk in (("data_f32", X), ("reference_set_f64", X.to(torch.float64))):
+            st = _Device(Xk, 10)
+            cen = Xk[:10].clone().contiguous()
+            for _ in range(3):
+                st.assign(cen, 1 | 4)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            for _ in range(20):
+                st.assign(cen, 1 | 4)
+            b.record(stream)
+            b.synchronize()
+            ms = a.elapsed_time(b) / 20
+            nbytes = N * D * Xk.element_size() + N * 4
+            passes[name] = {"ms": round(ms, 4), "gbps": round(nbytes / 1e9 / (ms * 1e-3), 1),
+                            "hbm_frac": round(nbytes / 1e9 / (ms * 1e-3) / hbm_peak, 4)}
+            del st, Xk
+        out["c4_reduced"]["lloyd_pass_K10"] = passes
+        out["c4_reduced"]["lloyd_pass_note"] = ("dic_kmeans_assign (COUNT_CHANGES | NO_INERTIA) incl. its partial-sum pass, 20 "
+                                                "launches, CUDA events on the launching stream; algorithmic bytes = one read "
+                                                "of the matrix + the labels; peak = " +
+                                                ("MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback 6650 GB/s"))
+    except Exception as e:                      # a reporting extra: never the reason a bench line is lost
+        out["c4_reduced"]["lloyd_pass_K10"] = {"error": str(e)[:200]}
     del X
     torch.cuda.empty_cache()
     return out
